@@ -1,0 +1,113 @@
+"""ORACLE fixture generator (test infrastructure).  Run only where /root/reference is mounted:
+
+    python -m oracle.make_golden
+
+Imports the reference's own Unet3D / VideoDecoder (unmodified, on the restated primitives), loads
+deterministic synthetic weights (oracle/weights.py), runs the hot path on seeded inputs and writes
+small fixtures into tests/golden/.  The committed fixtures are what pins the oracle restatement
+(oracle/unet3d.py) and the CUDA path on boxes where /root/reference does not exist.
+"""
+from __future__ import annotations
+
+import json
+import os
+
+import torch
+
+from . import reference
+from .weights import synth_state_dict
+
+GOLDEN = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+CASES = {
+    # BASELINE.json configs[0] topology (tiny), video-embed conditioned
+    "tiny": dict(unet=dict(dim=32, video_embed_dim=512, dim_mults=(1, 2), cond_on_video_embeds=True),
+                 shape=(2, 3, 8, 32, 32), times=(10, 37), text=None),
+    # tiny + text cross-attention (configs[2] semantics), CFG two-pass
+    "tiny_text": dict(unet=dict(dim=32, video_embed_dim=512, dim_mults=(1, 2), cond_on_video_embeds=True,
+                                cond_on_text_encodings=True, text_embed_dim=64),
+                      shape=(2, 3, 4, 16, 16), times=(3, 44), text=(5, 64), cond_scale=2.0),
+    # configs[1] channel plan (64..768 channels, 4 stages) at reduced frames/resolution
+    "headline_small": dict(unet=dict(dim=64, video_embed_dim=512, dim_mults=(1, 2, 4, 8), cond_on_video_embeds=True),
+                           shape=(1, 3, 4, 32, 32), times=(500,), text=None),
+}
+
+
+def shapes_of(module):
+    return {k: list(v.shape) for k, v in module.state_dict().items()}
+
+
+def main():
+    os.makedirs(GOLDEN, exist_ok=True)
+    ref = reference.load()
+    layouts = {}
+    for name, case in CASES.items():
+        torch.manual_seed(0)
+        unet = ref.Unet3D(**case["unet"]).eval()
+        shapes = shapes_of(unet)
+        layouts[name] = shapes
+        unet.load_state_dict(synth_state_dict(shapes, seed=7), strict=True)
+        g = torch.Generator().manual_seed(11)
+        b = case["shape"][0]
+        x = torch.randn(case["shape"], generator=g)
+        emb = torch.randn(b, 512, generator=g)
+        txt = None
+        if case["text"]:
+            txt = torch.randn(b, *case["text"], generator=g)
+            txt[0, -2:] = 0.0  # zero rows exercise the text mask (dalle2_video.py:823)
+        t = torch.tensor(case["times"], dtype=torch.long)
+        with torch.no_grad():
+            out = unet.forward_with_cond_scale(x, t, video_embed=emb, text_encodings=txt,
+                                               cond_scale=case.get("cond_scale", 1.0))
+        torch.save({"x": x, "video_embed": emb, "text_encodings": txt, "times": t, "eps": out,
+                    "unet_kwargs": case["unet"], "weight_seed": 7, "cond_scale": case.get("cond_scale", 1.0)},
+                   os.path.join(GOLDEN, f"unet3d_{name}.pt"))
+        print(name, tuple(out.shape), float(out.abs().mean()))
+
+    # config-2 state_dict layouts with and without text (pins SURVEY B.3 key names)
+    for name, kw in {"config2": dict(dim=64, video_embed_dim=512, dim_mults=(1, 2, 4, 8), cond_on_video_embeds=True),
+                     "config3": dict(dim=64, video_embed_dim=512, dim_mults=(1, 2, 4, 8), cond_on_video_embeds=True,
+                                     cond_on_text_encodings=True, text_embed_dim=512)}.items():
+        layouts[name] = shapes_of(ref.Unet3D(**kw))
+    with open(os.path.join(GOLDEN, "state_dict_layouts.json"), "w") as f:
+        json.dump(layouts, f, indent=0, sort_keys=True)
+
+    # sampler goldens through VideoDecoder.sample (tiny; 8 and 50 steps; configs[0])
+    for steps in (8, 50):
+        torch.manual_seed(0)
+        unet = ref.Unet3D(**CASES["tiny"]["unet"])
+        dec = ref.VideoDecoder(unet, frame_size=32, frame_numbers=(8,), timesteps=steps, learned_variance=False)
+        dec.unets[0].load_state_dict(synth_state_dict(layouts["tiny"], seed=7), strict=True)
+        sched = dec.noise_schedulers[0]
+        emb = torch.randn(2, 512, generator=torch.Generator().manual_seed(21))
+        torch.manual_seed(1234)
+        vid = dec.sample(video_embed=emb)
+        torch.save({"video_embed": emb, "sample": vid, "timesteps": steps, "sample_seed": 1234, "weight_seed": 7,
+                    "betas": sched.betas.clone(),
+                    "posterior_log_variance_clipped": sched.posterior_log_variance_clipped.clone(),
+                    "posterior_mean_coef1": sched.posterior_mean_coef1.clone(),
+                    "posterior_mean_coef2": sched.posterior_mean_coef2.clone(),
+                    "sqrt_recip_alphas_cumprod": sched.sqrt_recip_alphas_cumprod.clone(),
+                    "sqrt_recipm1_alphas_cumprod": sched.sqrt_recipm1_alphas_cumprod.clone()},
+                   os.path.join(GOLDEN, f"sample_tiny_{steps}.pt"))
+        print("sample", steps, tuple(vid.shape), float(vid.mean()))
+
+    # text + CFG sampling through p_sample_loop directly (sample() asserts for text)
+    torch.manual_seed(0)
+    unet = ref.Unet3D(**CASES["tiny_text"]["unet"])
+    dec = ref.VideoDecoder(unet, frame_size=16, frame_numbers=(4,), timesteps=6, learned_variance=False)
+    dec.unets[0].load_state_dict(synth_state_dict(layouts["tiny_text"], seed=7), strict=True)
+    dec.eval()
+    g = torch.Generator().manual_seed(31)
+    emb = torch.randn(2, 512, generator=g)
+    txt = torch.randn(2, 5, 64, generator=g)
+    torch.manual_seed(4321)
+    vid = dec.p_sample_loop(dec.unets[0], (2, 3, 4, 16, 16), video_embed=emb, text_encodings=txt, cond_scale=2.0,
+                            noise_scheduler=dec.noise_schedulers[0])
+    torch.save({"video_embed": emb, "text_encodings": txt, "sample": vid, "timesteps": 6, "sample_seed": 4321,
+                "weight_seed": 7, "cond_scale": 2.0}, os.path.join(GOLDEN, "sample_tiny_text_cfg_6.pt"))
+    print("sample text cfg", tuple(vid.shape), float(vid.mean()))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,39 @@
+"""ORACLE helper — loads the reference's OWN Unet3D / VideoDecoder code (unmodified, from
+/root/reference/dalle2_video/dalle2_video.py) on top of the restated primitives.
+
+Only available where /root/reference is mounted (this container); never on the GPU box.
+Used by oracle/make_golden.py and by CPU tests that cross-check the restatement.
+"""
+from __future__ import annotations
+
+import importlib.util
+import os
+import sys
+
+REFERENCE_ROOT = os.environ.get("DV_REFERENCE_ROOT", "/root/reference")
+_SHIM = os.path.join(os.path.dirname(os.path.abspath(__file__)), "shim")
+_REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_cached = None
+
+
+def available() -> bool:
+    return os.path.isfile(os.path.join(REFERENCE_ROOT, "dalle2_video", "dalle2_video.py"))
+
+
+def load():
+    """Return the reference module object (dalle2_video.dalle2_video), imported from where it lies."""
+    global _cached
+    if _cached is not None:
+        return _cached
+    if not available():
+        raise FileNotFoundError(f"reference not mounted at {REFERENCE_ROOT}")
+    for p in (_REPO, _SHIM):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    path = os.path.join(REFERENCE_ROOT, "dalle2_video", "dalle2_video.py")
+    spec = importlib.util.spec_from_file_location("_reference_dalle2_video", path)
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules["_reference_dalle2_video"] = mod
+    spec.loader.exec_module(mod)
+    _cached = mod
+    return mod
