@@ -1,0 +1,13 @@
+"""dalle2_video_b200 — B200-native decoder denoising step for DALLE2-video.
+
+Public surface (mirrors /root/reference/dalle2_video/dalle2_video.py):
+    Unet3D, VideoDecoder, NoiseScheduler, NullVQGanVAE
+plus `shard_rows` for batch-sharded multi-GPU sampling (no collective on the data path).
+The CUDA extension (libdv_b200.so, built by __graft_entry__.build()) is mandatory.
+"""
+from .decoder import NullVQGanVAE, VideoDecoder
+from .parallel import shard_rows
+from .scheduler import NoiseScheduler
+from .unet3d import Unet3D
+
+__all__ = ["Unet3D", "VideoDecoder", "NoiseScheduler", "NullVQGanVAE", "shard_rows"]

@@ -1,0 +1,137 @@
+"""ctypes binding of libdv_b200.so (C ABI declared in include/dv_b200.h).
+
+The product path has no CPU or library fallback: if the shared library is missing or a call returns
+a non-zero code this module raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libdv_b200.so")
+
+DV_F32, DV_BF16 = 0, 1
+CONV_NORMAL, CONV_UNSHUFFLE, CONV_NCDHW_F32_IN = 0, 1, 2
+EPI_STORE, EPI_SHUFFLE_SILU = 0, 1
+ACT_NONE, ACT_SILU, ACT_GELU = 0, 1, 2
+
+vp, i32, i64, f32 = C.c_void_p, C.c_int, C.c_int64, C.c_float
+
+
+class DdpmStepParams(C.Structure):
+    _fields_ = [("x_t", vp), ("eps", vp), ("eps_null", vp), ("noise", vp), ("out", vp), ("unnormalize_out", vp),
+                ("coef", vp), ("t_dev", vp), ("t_host", i32), ("t_dev_decrement", i32), ("num_timesteps", i32),
+                ("n", i64), ("cond_scale", f32), ("clip_denoised", i32), ("eps_dtype", i32)]
+
+
+class ConvParams(C.Structure):
+    _fields_ = [("src0", vp), ("src1", vp), ("weight", vp), ("bias", vp), ("add", vp), ("out", vp), ("stats", vp),
+                ("n_img", i32), ("frames", i32), ("H", i32), ("W", i32), ("C0", i32), ("C1", i32), ("Cout", i32),
+                ("kh", i32), ("kw", i32), ("pad", i32), ("mode", i32), ("epilogue", i32), ("groups", i32),
+                ("out_ld", i32), ("out_coff", i32), ("dtype", i32), ("impl", i32)]
+
+
+class GnApplyParams(C.Structure):
+    _fields_ = [("x", vp), ("out", vp), ("residual", vp), ("stats", vp), ("gamma", vp), ("beta", vp), ("scale", vp),
+                ("shift", vp), ("ss_ld", i32), ("B", i32), ("P", i64), ("C", i32), ("groups", i32), ("eps", f32),
+                ("dtype", i32)]
+
+
+class GnStatsParams(C.Structure):
+    _fields_ = [("x", vp), ("stats", vp), ("B", i32), ("P", i64), ("C", i32), ("groups", i32), ("dtype", i32)]
+
+
+class LayerNormParams(C.Structure):
+    _fields_ = [("x", vp), ("out", vp), ("residual", vp), ("g", vp), ("beta", vp), ("rows", i64), ("C", i32),
+                ("eps", f32), ("dtype", i32)]
+
+
+class XattnParams(C.Structure):
+    _fields_ = [("q", vp), ("out", vp), ("kv", vp), ("null_kv", vp), ("B", i32), ("P", i64), ("heads", i32),
+                ("dh", i32), ("n_ctx", i32), ("kv_ld", i64), ("k_off", i32), ("v_off", i32), ("scale", f32),
+                ("dtype", i32)]
+
+
+class AttnMqaParams(C.Structure):
+    _fields_ = [("q", vp), ("kv", vp), ("out", vp), ("null_kv", vp), ("bias", vp), ("S", i64), ("n", i32),
+                ("heads", i32), ("dh", i32), ("scale", f32), ("dtype", i32)]
+
+
+class TimeEmbedParams(C.Structure):
+    _fields_ = [("time", vp), ("t_dev", vp), ("freqs", vp), ("out", vp), ("B", i32), ("dim", i32)]
+
+
+class LinearSmallParams(C.Structure):
+    _fields_ = [("x", vp), ("w", vp), ("bias", vp), ("y", vp), ("accum", vp), ("keep", vp), ("alt", vp), ("M1", i32), ("M2", i32), ("N", i32),
+                ("K", i32), ("ldx1", i64), ("ldx2", i64), ("ldy1", i64), ("ldy2", i64), ("pre_act", i32),
+                ("post_act", i32)]
+
+
+class CondTokensParams(C.Structure):
+    _fields_ = [("time_tokens", vp), ("video_tokens", vp), ("null_video", vp), ("text_tokens", vp), ("text_enc", vp),
+                ("null_text", vp), ("ln_w", vp), ("ln_b", vp), ("ln_mid_w", vp), ("ln_mid_b", vp), ("keep_video", vp),
+                ("keep_text", vp), ("c", vp), ("mid_c", vp), ("B", i32), ("D", i32), ("n_time", i32), ("n_video", i32),
+                ("n_text_in", i32), ("max_text", i32), ("text_dim", i32), ("tok_begin", i32), ("tok_end", i32),
+                ("eps", f32)]
+
+
+class ToOutParams(C.Structure):
+    _fields_ = [("x", vp), ("w", vp), ("bias", vp), ("out", vp), ("B", i32), ("P", i64), ("C", i32), ("Cout", i32),
+                ("dtype", i32)]
+
+
+# every symbol include/dv_b200.h declares: name -> params struct (None for the plain helpers)
+ENTRY_POINTS = {
+    "dv_ddpm_step": DdpmStepParams, "dv_conv_igemm": ConvParams, "dv_gn_apply": GnApplyParams,
+    "dv_gn_stats": GnStatsParams, "dv_layernorm": LayerNormParams, "dv_xattn_core": XattnParams,
+    "dv_attn_mqa": AttnMqaParams, "dv_time_embed": TimeEmbedParams, "dv_linear_small": LinearSmallParams,
+    "dv_cond_tokens": CondTokensParams, "dv_to_out": ToOutParams,
+}
+PLAIN_SYMBOLS = ("dv_version", "dv_last_error_string", "dv_device_sm_count", "dv_conv_uses_tcgen05")
+
+_lib = None
+launch_count = 0  # number of C-ABI kernel-enqueue calls made by this process (bench.py reports it)
+
+
+class DvError(RuntimeError):
+    pass
+
+
+def lib():
+    """Load the shared library (once).  Raises if it has not been built — there is no fallback path."""
+    global _lib
+    if _lib is None:
+        if not os.path.isfile(LIB_PATH):
+            raise DvError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                          "(the CUDA extension is mandatory; there is no CPU fallback)")
+        _lib = C.CDLL(LIB_PATH)
+        for name, st in ENTRY_POINTS.items():
+            fn = getattr(_lib, name)
+            fn.argtypes = [C.POINTER(st), vp]
+            fn.restype = i32
+        _lib.dv_version.restype = i32
+        _lib.dv_last_error_string.restype = C.c_char_p
+        _lib.dv_device_sm_count.argtypes = [i32]
+        _lib.dv_device_sm_count.restype = i32
+        _lib.dv_conv_uses_tcgen05.argtypes = [C.POINTER(ConvParams)]
+        _lib.dv_conv_uses_tcgen05.restype = i32
+    return _lib
+
+
+def call(name: str, params, stream: int):
+    """Enqueue one C-ABI op on the raw cudaStream_t `stream`; raise DvError on a non-zero return."""
+    global launch_count
+    rc = getattr(lib(), name)(C.byref(params), vp(stream))
+    if rc != 0:
+        raise DvError(f"{name} failed ({rc}): {lib().dv_last_error_string().decode()}")
+    launch_count += 1
+
+
+def dtype_code(torch_dtype) -> int:
+    import torch
+    if torch_dtype == torch.float32:
+        return DV_F32
+    if torch_dtype == torch.bfloat16:
+        return DV_BF16
+    raise DvError(f"unsupported compute dtype {torch_dtype}")

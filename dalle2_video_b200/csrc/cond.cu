@@ -1,0 +1,202 @@
+// K8 — conditioning prologue pieces (fp32, batch-sized GEMVs) and the to_out head.
+// See include/dv_b200.h for the reference call sites each one replaces.
+#include "common.cuh"
+
+namespace dv {
+
+__global__ void time_embed_kernel(dv_time_embed_params p) {
+  const int half = p.dim / 2;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= p.B * half) return;
+  const int b = idx / half, j = idx % half;
+  // time.type_as(x) with fp32 activations (dalle2_video.py:755)
+  const float t = p.time ? (float)p.time[b] : (float)(*p.t_dev);
+  const float a = t * p.freqs[j];
+  p.out[(int64_t)b * p.dim + j] = sinf(a);
+  p.out[(int64_t)b * p.dim + half + j] = cosf(a);
+}
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+  if (act == DV_ACT_SILU) return v / (1.0f + expf(-v));
+  if (act == DV_ACT_GELU) return gelu_f(v);
+  return v;
+}
+
+// One warp per output feature n; the warp walks the rows in chunks of MC so that the weight row is
+// read once per chunk.  Lanes stride over K (coalesced weight reads).
+constexpr int MC = 8;
+__global__ void __launch_bounds__(128) linear_small_kernel(dv_linear_small_params p) {
+  const int lane = threadIdx.x & 31;
+  const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (n >= p.N) return;
+  const float* w = p.w + (int64_t)n * p.K;
+  const float bias = p.bias ? p.bias[n] : 0.0f;
+  const int M = p.M1 * p.M2;
+  for (int m0 = 0; m0 < M; m0 += MC) {
+    float acc[MC];
+#pragma unroll
+    for (int i = 0; i < MC; ++i) acc[i] = 0.f;
+    for (int k = lane; k < p.K; k += 32) {
+      const float wk = w[k];
+#pragma unroll
+      for (int i = 0; i < MC; ++i) {
+        const int m = m0 + i;
+        if (m < M) {
+          const float xv = p.x[(int64_t)(m / p.M2) * p.ldx1 + (int64_t)(m % p.M2) * p.ldx2 + k];
+          acc[i] = fmaf(apply_act(xv, p.pre_act), wk, acc[i]);
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < MC; ++i) {
+      const float s = warp_sum(acc[i]);
+      const int m = m0 + i;
+      if (lane == 0 && m < M) {
+        float v = apply_act(s + bias, p.post_act);
+        if (p.keep && !p.keep[m / p.M2]) v = p.alt[(int64_t)(m % p.M2) * p.N + n];
+        if (p.accum) v += p.accum[(int64_t)m * p.N + n];
+        p.y[(int64_t)(m / p.M2) * p.ldy1 + (int64_t)(m % p.M2) * p.ldy2 + n] = v;
+      }
+    }
+  }
+}
+
+// One warp per (sample, token) of the concatenated conditioning sequence [time | video | text].
+__global__ void __launch_bounds__(128) cond_tokens_kernel(dv_cond_tokens_params p) {
+  const int lane = threadIdx.x & 31;
+  const int ntok = p.tok_end - p.tok_begin;
+  const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (w >= p.B * ntok) return;
+  const int b = w / ntok, j = p.tok_begin + w % ntok;
+  const int n_c = p.n_time + p.n_video, n_all = n_c + p.max_text;
+  const float* src;
+  if (j < p.n_time) {
+    src = p.time_tokens + ((int64_t)b * p.n_time + j) * p.D;
+  } else if (j < n_c) {
+    const int v = j - p.n_time;
+    src = p.keep_video[b] ? p.video_tokens + ((int64_t)b * p.n_video + v) * p.D : p.null_video + (int64_t)v * p.D;
+  } else {
+    const int tj = j - n_c;
+    bool keep = false;
+    if (tj < p.n_text_in && p.keep_text[b]) {
+      // text_mask = any(text_encodings != 0, dim=-1)   (dalle2_video.py:823)
+      const float* e = p.text_enc + ((int64_t)b * p.n_text_in + tj) * p.text_dim;
+      bool nz = false;
+      for (int k = lane; k < p.text_dim; k += 32) nz |= (e[k] != 0.0f);
+      keep = __any_sync(0xffffffffu, nz);
+    }
+    src = keep ? p.text_tokens + ((int64_t)b * p.n_text_in + tj) * p.D : p.null_text + (int64_t)tj * p.D;
+  }
+  // nn.LayerNorm statistics (biased variance), two passes over <= 4 values per lane (D <= 128)
+  float v[4];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int d = lane + 32 * i;
+    v[i] = d < p.D ? src[d] : 0.f;
+    s += v[i];
+  }
+  const float mean = warp_sum(s) / (float)p.D;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int d = lane + 32 * i;
+    if (d < p.D) { const float t = v[i] - mean; q += t * t; }
+  }
+  const float rstd = rsqrtf(warp_sum(q) / (float)p.D + p.eps);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int d = lane + 32 * i;
+    if (d < p.D) {
+      const float xn = (v[i] - mean) * rstd;
+      if (j < n_c) p.c[((int64_t)b * n_c + j) * p.D + d] = xn * p.ln_w[d] + p.ln_b[d];
+      p.mid_c[((int64_t)b * n_all + j) * p.D + d] = xn * p.ln_mid_w[d] + p.ln_mid_b[d];
+    }
+  }
+}
+
+// to_out: thread per position, weights in shared memory, output planes written coalesced.
+template <typename T, int CO>
+__global__ void __launch_bounds__(256) to_out_kernel(dv_to_out_params p) {
+  extern __shared__ float w[];  // [CO][C]
+  for (int i = threadIdx.x; i < CO * p.C; i += blockDim.x) w[i] = p.w[i];
+  __syncthreads();
+  const int b = blockIdx.y;
+  const int64_t pos = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (pos >= p.P) return;
+  const T* x = reinterpret_cast<const T*>(p.x) + ((int64_t)b * p.P + pos) * p.C;
+  float acc[CO];
+#pragma unroll
+  for (int o = 0; o < CO; ++o) acc[o] = p.bias ? p.bias[o] : 0.f;
+  for (int c = 0; c < p.C; c += 8) {
+    float v[8];
+    load8(x + c, v);
+#pragma unroll
+    for (int o = 0; o < CO; ++o)
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc[o] = fmaf(v[k], w[o * p.C + c + k], acc[o]);
+  }
+#pragma unroll
+  for (int o = 0; o < CO; ++o) p.out[((int64_t)b * CO + o) * p.P + pos] = acc[o];
+}
+
+}  // namespace dv
+
+extern "C" int dv_time_embed(const dv_time_embed_params* p, dv_stream_t stream) {
+  using namespace dv;
+  DV_REQUIRE(p && (p->time || p->t_dev) && p->freqs && p->out, DV_EINVAL, "dv_time_embed: null pointer");
+  DV_REQUIRE(p->B > 0 && p->dim >= 4 && p->dim % 2 == 0, DV_EINVAL, "dv_time_embed: bad dimensions");
+  const int n = p->B * (p->dim / 2);
+  time_embed_kernel<<<(n + 127) / 128, 128, 0, as_stream(stream)>>>(*p);
+  DV_CHECK_LAUNCH("dv_time_embed");
+  return DV_OK;
+}
+
+extern "C" int dv_linear_small(const dv_linear_small_params* p, dv_stream_t stream) {
+  using namespace dv;
+  DV_REQUIRE(p && p->x && p->w && p->y, DV_EINVAL, "dv_linear_small: null pointer");
+  DV_REQUIRE(p->M1 > 0 && p->M2 > 0 && p->N > 0 && p->K > 0, DV_EINVAL, "dv_linear_small: bad dimensions");
+  DV_REQUIRE(!p->keep || p->alt, DV_EINVAL, "dv_linear_small: keep needs alt");
+  DV_REQUIRE(p->pre_act >= 0 && p->pre_act <= 2 && p->post_act >= 0 && p->post_act <= 2, DV_EINVAL,
+             "dv_linear_small: bad activation");
+  linear_small_kernel<<<(p->N + 3) / 4, 128, 0, as_stream(stream)>>>(*p);
+  DV_CHECK_LAUNCH("dv_linear_small");
+  return DV_OK;
+}
+
+extern "C" int dv_cond_tokens(const dv_cond_tokens_params* p, dv_stream_t stream) {
+  using namespace dv;
+  DV_REQUIRE(p && p->time_tokens && p->ln_w && p->ln_b && p->ln_mid_w && p->ln_mid_b && p->c && p->mid_c, DV_EINVAL,
+             "dv_cond_tokens: null pointer");
+  DV_REQUIRE(p->B > 0 && p->D > 0 && p->D <= 128, DV_EUNSUPPORTED, "dv_cond_tokens: cond_dim must be <= 128 (got %d)",
+             p->D);
+  DV_REQUIRE(p->n_video == 0 || (p->video_tokens && p->null_video && p->keep_video), DV_EINVAL,
+             "dv_cond_tokens: video tokens need video_tokens/null_video/keep_video");
+  DV_REQUIRE(p->max_text == 0 || (p->null_text && p->keep_text && (p->n_text_in == 0 || (p->text_tokens && p->text_enc))),
+             DV_EINVAL, "dv_cond_tokens: text tokens need text_tokens/text_enc/null_text/keep_text");
+  DV_REQUIRE(p->n_text_in <= p->max_text, DV_EINVAL, "dv_cond_tokens: n_text_in > max_text (slice on the host)");
+  const int n_all = p->n_time + p->n_video + p->max_text;
+  DV_REQUIRE(0 <= p->tok_begin && p->tok_begin < p->tok_end && p->tok_end <= n_all, DV_EINVAL,
+             "dv_cond_tokens: bad token range");
+  const int warps = p->B * (p->tok_end - p->tok_begin);
+  cond_tokens_kernel<<<(warps + 3) / 4, 128, 0, as_stream(stream)>>>(*p);
+  DV_CHECK_LAUNCH("dv_cond_tokens");
+  return DV_OK;
+}
+
+extern "C" int dv_to_out(const dv_to_out_params* p, dv_stream_t stream) {
+  using namespace dv;
+  DV_REQUIRE(p && p->x && p->w && p->out, DV_EINVAL, "dv_to_out: null pointer");
+  DV_REQUIRE(p->B > 0 && p->P > 0 && p->C > 0 && p->C % 8 == 0, DV_EINVAL, "dv_to_out: bad dimensions (C %% 8)");
+  DV_REQUIRE(p->Cout == 3 || p->Cout == 6, DV_EUNSUPPORTED, "dv_to_out: channels_out must be 3 or 6 (got %d)", p->Cout);
+  DV_REQUIRE(aligned16(p->x), DV_EALIGN, "dv_to_out: x must be 16-byte aligned");
+  dim3 grid((unsigned)((p->P + 255) / 256), p->B);
+  const size_t smem = sizeof(float) * p->Cout * p->C;
+  cudaStream_t s = as_stream(stream);
+#define DV_TO_OUT(T, CO) to_out_kernel<T, CO><<<grid, 256, smem, s>>>(*p)
+  if (p->dtype == DV_F32) { if (p->Cout == 3) DV_TO_OUT(float, 3); else DV_TO_OUT(float, 6); }
+  else { if (p->Cout == 3) DV_TO_OUT(__nv_bfloat16, 3); else DV_TO_OUT(__nv_bfloat16, 6); }
+#undef DV_TO_OUT
+  DV_CHECK_LAUNCH("dv_to_out");
+  return DV_OK;
+}

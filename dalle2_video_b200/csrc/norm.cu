@@ -1,0 +1,215 @@
+// K2 — GroupNorm statistics / finalize+apply+scale-shift+SiLU(+residual), and a15 — LayerNorm.
+// HBM-bound streaming kernels (see include/dv_b200.h for the reference call sites they replace).
+//   dv_gn_apply : algorithmic bytes = read x + write y (+ read residual) = 2..3 * elem_size per element.
+#include "common.cuh"
+
+namespace dv {
+
+// ---------------------------------------------------------------- GroupNorm statistics
+// grid (chunks, B); block = (C/4) * rpi threads; thread owns one channel quad and strides over rows.
+template <typename T>
+__global__ void gn_stats_kernel(dv_gn_stats_params p, int rows_per_block, int rpi) {
+  extern __shared__ double sred[];  // [groups][2]
+  const int c4n = p.C / 4;
+  const int c4 = threadIdx.x % c4n, rl = threadIdx.x / c4n;
+  const int b = blockIdx.y;
+  const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
+  int64_t r1 = r0 + rows_per_block;
+  if (r1 > p.P) r1 = p.P;
+  for (int i = threadIdx.x; i < p.groups * 2; i += blockDim.x) sred[i] = 0.0;
+  __syncthreads();
+  const T* x = reinterpret_cast<const T*>(p.x) + (int64_t)b * p.P * p.C;
+  float s1 = 0.f, s2 = 0.f;
+  for (int64_t r = r0 + rl; r < r1; r += rpi) {
+    float v[4];
+    load4(x + r * p.C + c4 * 4, v);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { s1 += v[k]; s2 += v[k] * v[k]; }
+  }
+  const int grp = (c4 * 4) / (p.C / p.groups);
+  atomicAdd(&sred[grp * 2 + 0], (double)s1);
+  atomicAdd(&sred[grp * 2 + 1], (double)s2);
+  __syncthreads();
+  for (int i = threadIdx.x; i < p.groups * 2; i += blockDim.x)
+    atomicAdd(&p.stats[(int64_t)b * p.groups * 2 + i], sred[i]);
+}
+
+// ---------------------------------------------------------------- GroupNorm apply
+// grid (chunks, B); per-(b,c) affine folded into two fp32 coefficients held in shared memory.
+template <typename T>
+__global__ void __launch_bounds__(256) gn_apply_kernel(dv_gn_apply_params p, int rows_per_block) {
+  extern __shared__ float coef[];  // [2][C]
+  const int b = blockIdx.y;
+  const int cpg = p.C / p.groups;
+  const double cnt = (double)p.P * cpg;
+  for (int c = threadIdx.x; c < p.C; c += blockDim.x) {
+    const int g = c / cpg;
+    const double s1 = p.stats[((int64_t)b * p.groups + g) * 2 + 0];
+    const double s2 = p.stats[((int64_t)b * p.groups + g) * 2 + 1];
+    const double mean = s1 / cnt;
+    double var = s2 / cnt - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const float rstd = (float)(1.0 / sqrt(var + (double)p.eps));
+    float a = rstd * p.gamma[c];
+    float d = p.beta[c] - (float)mean * a;
+    if (p.scale) {
+      const float sc = 1.0f + p.scale[(int64_t)b * p.ss_ld + c];
+      a *= sc;
+      d = d * sc + p.shift[(int64_t)b * p.ss_ld + c];
+    }
+    coef[c] = a;
+    coef[p.C + c] = d;
+  }
+  __syncthreads();
+  const int c8n = p.C / 8;
+  const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
+  int64_t r1 = r0 + rows_per_block;
+  if (r1 > p.P) r1 = p.P;
+  const int64_t base = (int64_t)b * p.P * p.C;
+  const T* x = reinterpret_cast<const T*>(p.x) + base;
+  const T* res = p.residual ? reinterpret_cast<const T*>(p.residual) + base : nullptr;
+  T* out = reinterpret_cast<T*>(p.out) + base;
+  const int64_t nvec = (r1 - r0) * c8n;
+  for (int64_t i = threadIdx.x; i < nvec; i += blockDim.x) {
+    const int64_t r = r0 + i / c8n;
+    const int c = (int)(i % c8n) * 8;
+    float v[8];
+    load8(x + r * p.C + c, v);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = silu_f(fmaf(v[k], coef[c + k], coef[p.C + c + k]));
+    if (res) {
+      float rr[8];
+      load8(res + r * p.C + c, rr);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] += rr[k];
+    }
+    store8(out + r * p.C + c, v);
+  }
+}
+
+// ---------------------------------------------------------------- LayerNorm (one warp per row)
+template <typename T, int MAXV>
+__global__ void __launch_bounds__(256) layernorm_kernel(dv_layernorm_params p) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= p.rows) return;
+  const T* x = reinterpret_cast<const T*>(p.x) + row * p.C;
+  float v[MAXV][4];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int c = (i * 32 + lane) * 4;
+    if (c < p.C) {
+      load4(x + c, v[i]);
+      s += v[i][0] + v[i][1] + v[i][2] + v[i][3];
+    }
+  }
+  const float mean = warp_sum(s) / (float)p.C;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int c = (i * 32 + lane) * 4;
+    if (c < p.C) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { const float d = v[i][k] - mean; q += d * d; }
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(q) / (float)p.C + p.eps);
+  T* out = reinterpret_cast<T*>(p.out) + row * p.C;
+  const T* res = p.residual ? reinterpret_cast<const T*>(p.residual) + row * p.C : nullptr;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int c = (i * 32 + lane) * 4;
+    if (c < p.C) {
+      float o[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        o[k] = (v[i][k] - mean) * rstd * p.g[c + k];
+        if (p.beta) o[k] += p.beta[c + k];
+      }
+      if (res) {
+        float rr[4];
+        load4(res + c, rr);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) o[k] += rr[k];
+      }
+      store4(out + c, o);
+    }
+  }
+}
+
+template <typename T>
+static int launch_ln(const dv_layernorm_params& p, cudaStream_t s) {
+  const int wpb = 8;
+  const unsigned blocks = (unsigned)((p.rows + wpb - 1) / wpb);
+  if (p.C <= 128)
+    layernorm_kernel<T, 1><<<blocks, wpb * 32, 0, s>>>(p);
+  else if (p.C <= 512)
+    layernorm_kernel<T, 4><<<blocks, wpb * 32, 0, s>>>(p);
+  else
+    layernorm_kernel<T, 8><<<blocks, wpb * 32, 0, s>>>(p);
+  DV_CHECK_LAUNCH("dv_layernorm");
+  return DV_OK;
+}
+
+}  // namespace dv
+
+extern "C" int dv_gn_stats(const dv_gn_stats_params* p, dv_stream_t stream) {
+  using namespace dv;
+  DV_REQUIRE(p && p->x && p->stats, DV_EINVAL, "dv_gn_stats: null pointer");
+  DV_REQUIRE(p->B > 0 && p->P > 0 && p->C > 0 && p->groups > 0 && p->C % p->groups == 0, DV_EINVAL,
+             "dv_gn_stats: bad dimensions");
+  DV_REQUIRE((p->C / p->groups) % 4 == 0 && p->C <= 1024, DV_EUNSUPPORTED,
+             "dv_gn_stats: needs C/groups %% 4 == 0 and C <= 1024 (C=%d groups=%d)", p->C, p->groups);
+  DV_REQUIRE(aligned16(p->x), DV_EALIGN, "dv_gn_stats: x must be 16-byte aligned");
+  const int c4n = p->C / 4;
+  int rpi = 256 / c4n;
+  if (rpi < 1) rpi = 1;
+  const int threads = c4n * rpi;
+  int chunks = (148 * 8 + p->B - 1) / p->B;
+  int64_t rpb = (p->P + chunks - 1) / chunks;
+  if (rpb < rpi) rpb = rpi;
+  chunks = (int)((p->P + rpb - 1) / rpb);
+  dim3 grid(chunks, p->B);
+  const size_t smem = sizeof(double) * 2 * p->groups;
+  if (p->dtype == DV_F32)
+    gn_stats_kernel<float><<<grid, threads, smem, as_stream(stream)>>>(*p, (int)rpb, rpi);
+  else
+    gn_stats_kernel<__nv_bfloat16><<<grid, threads, smem, as_stream(stream)>>>(*p, (int)rpb, rpi);
+  DV_CHECK_LAUNCH("dv_gn_stats");
+  return DV_OK;
+}
+
+extern "C" int dv_gn_apply(const dv_gn_apply_params* p, dv_stream_t stream) {
+  using namespace dv;
+  DV_REQUIRE(p && p->x && p->out && p->stats && p->gamma && p->beta, DV_EINVAL, "dv_gn_apply: null pointer");
+  DV_REQUIRE((p->scale == nullptr) == (p->shift == nullptr), DV_EINVAL, "dv_gn_apply: scale/shift must come together");
+  DV_REQUIRE(p->B > 0 && p->P > 0 && p->C > 0 && p->groups > 0 && p->C % p->groups == 0, DV_EINVAL,
+             "dv_gn_apply: bad dimensions");
+  DV_REQUIRE(p->C % 8 == 0 && p->C <= 4096, DV_EUNSUPPORTED, "dv_gn_apply: needs C %% 8 == 0 and C <= 4096 (C=%d)", p->C);
+  DV_REQUIRE(aligned16(p->x) && aligned16(p->out) && aligned16(p->residual), DV_EALIGN,
+             "dv_gn_apply: tensors must be 16-byte aligned");
+  int chunks = (148 * 8 + p->B - 1) / p->B;
+  int64_t rpb = (p->P + chunks - 1) / chunks;
+  if (rpb < 1) rpb = 1;
+  chunks = (int)((p->P + rpb - 1) / rpb);
+  dim3 grid(chunks, p->B);
+  const size_t smem = sizeof(float) * 2 * p->C;
+  if (p->dtype == DV_F32)
+    gn_apply_kernel<float><<<grid, 256, smem, as_stream(stream)>>>(*p, (int)rpb);
+  else
+    gn_apply_kernel<__nv_bfloat16><<<grid, 256, smem, as_stream(stream)>>>(*p, (int)rpb);
+  DV_CHECK_LAUNCH("dv_gn_apply");
+  return DV_OK;
+}
+
+extern "C" int dv_layernorm(const dv_layernorm_params* p, dv_stream_t stream) {
+  using namespace dv;
+  DV_REQUIRE(p && p->x && p->out && p->g, DV_EINVAL, "dv_layernorm: null pointer");
+  DV_REQUIRE(p->rows > 0 && p->C > 0 && p->C % 4 == 0 && p->C <= 1024, DV_EUNSUPPORTED,
+             "dv_layernorm: needs C %% 4 == 0 and C <= 1024 (C=%d)", p->C);
+  DV_REQUIRE(aligned16(p->x) && aligned16(p->out) && aligned16(p->residual), DV_EALIGN,
+             "dv_layernorm: tensors must be 16-byte aligned");
+  if (p->dtype == DV_BF16) DV_REQUIRE(p->C % 8 == 0, DV_EALIGN, "dv_layernorm: bf16 rows need C %% 8 == 0");
+  return (p->dtype == DV_F32) ? launch_ln<float>(*p, as_stream(stream)) : launch_ln<__nv_bfloat16>(*p, as_stream(stream));
+}

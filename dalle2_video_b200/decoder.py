@@ -1,0 +1,353 @@
+"""VideoDecoder — drop-in for the sampling half of the reference's diffusion wrapper
+(/root/reference/dalle2_video/dalle2_video.py:1169-2299).
+
+Kept from the reference: constructor kwargs, `sample`, `p_sample_loop`, `p_sample_loop_ddpm`, `p_sample`,
+`p_mean_variance` signatures, tensor layouts ((B,C,T,H,W) float32 videos), the cosine/linear noise
+schedule, the RNG contract (one `randn(shape)` then one `randn` per step, also at t=0), the
+classifier-free-guidance blend and the documented quirks.
+
+Changed: the loop body.  One denoising step = the Unet3D launch plan (unet3d._Engine) + ONE fused
+posterior-update kernel (dv_ddpm_step), optionally replayed as a CUDA graph whose timestep lives in
+device memory; classifier-free guidance runs cond+uncond as one 2B batch instead of two forwards.
+"""
+from __future__ import annotations
+
+from contextlib import nullcontext
+
+import torch
+from torch import nn
+
+from . import _lib as L
+from .scheduler import NoiseScheduler
+from .unet3d import Unet3D, _cast_tuple
+
+
+class NullVQGanVAE(nn.Module):
+    """Identity autoencoder (pixel-space diffusion), as dalle2_pytorch.vqgan_vae.NullVQGanVAE (:1295)."""
+
+    def __init__(self, *, channels):
+        super().__init__()
+        self.encoded_dim = channels
+        self.layers = 0
+
+    def get_encoded_fmap_size(self, size):
+        return size
+
+    def copy_for_eval(self):
+        return self
+
+    def encode(self, x):
+        return x
+
+    def decode(self, x):
+        return x
+
+
+def _pad_tuple(t, length, fill=None):
+    return t if len(t) >= length else (*t, *((fill,) * (length - len(t))))
+
+
+class VideoDecoder(nn.Module):
+    def __init__(self, unet, *, clip=None, frame_size=None, channels=3, vae=tuple(), timesteps=1000,
+                 sample_timesteps=None, video_cond_drop_prob=0.1, text_cond_drop_prob=0.5, loss_type="l2",
+                 beta_schedule=None, predict_x_start=False, predict_v=False,
+                 predict_x_start_for_latent_diffusion=False, frame_sizes=None, frame_numbers=None,
+                 random_crop_sizes=None, use_noise_for_lowres_cond=False, use_blur_for_lowres_cond=True,
+                 lowres_downsample_first=True, blur_prob=0.5, blur_sigma=0.6, blur_kernel_size=3,
+                 lowres_noise_sample_level=0.2, clip_denoised=True, clip_x_start=True, clip_adapter_overrides=dict(),
+                 learned_variance=True, learned_variance_constrain_frac=False, vb_loss_weight=0.001,
+                 unconditional=False, auto_normalize_video=True, use_dynamic_thres=False,
+                 dynamic_thres_percentile=0.95, p2_loss_weight_gamma=0.0, p2_loss_weight_k=1, ddim_sampling_eta=0.0):
+        super().__init__()
+        if clip is not None:
+            raise NotImplementedError("CLIP adapters are outside the accelerated path: pass video_embed directly")
+        if frame_size is None and frame_sizes is None:
+            raise Exception("either image_size, image_sizes, or clip must be given to decoder")
+        assert (frame_size is not None) ^ (frame_sizes is not None), "only one of image_size or image_sizes must be given"
+        frame_size = frame_size if frame_size is not None else frame_sizes[-1]
+
+        self.channels = channels
+        self.auto_normalize_video = auto_normalize_video
+        self.normalize_video = (lambda v: v * 2 - 1) if auto_normalize_video else (lambda v: v)
+        self.unnormalize_video = (lambda v: (v + 1) * 0.5) if auto_normalize_video else (lambda v: v)
+
+        unets = _cast_tuple(unet)
+        self.num_unets = len(unets)
+        if self.num_unets != 1:
+            raise NotImplementedError("cascades (super-resolution unets with low-res conditioning) are the next "
+                                      "scope row (SURVEY.md §8f N2); this build accelerates the base decoder")
+        if len(_cast_tuple(vae)) > 0:
+            raise NotImplementedError("latent diffusion (VQGanVAE) is outside the accelerated path")
+        self.unconditional = unconditional
+        vaes = _pad_tuple(tuple(), len(unets), NullVQGanVAE(channels=channels))
+        learned_variance = _pad_tuple(_cast_tuple(learned_variance), len(unets), False)
+        self.learned_variance = learned_variance
+        self.learned_variance_constrain_frac = learned_variance_constrain_frac
+        self.vb_loss_weight = vb_loss_weight
+
+        self.unets = nn.ModuleList([])
+        self.vaes = nn.ModuleList([])
+        for ind, (one_unet, one_vae, lv) in enumerate(zip(unets, vaes, learned_variance)):
+            assert isinstance(one_unet, Unet3D)
+            is_first = ind == 0
+            ch_out = one_vae.encoded_dim * (1 if not lv else 2)
+            # same call as the reference (:1347-1355) — may re-instantiate the unet with fresh weights
+            one_unet = one_unet.cast_model_parameters(
+                lowres_cond=not is_first, lowres_noise_cond=False,
+                cond_on_image_embeds=not unconditional and is_first,
+                cond_on_text_encodings=not unconditional and one_unet.cond_on_text_encodings,
+                channels=one_vae.encoded_dim, channels_out=ch_out)
+            self.unets.append(one_unet)
+            self.vaes.append(one_vae.copy_for_eval())
+
+        self.sample_timesteps = _cast_tuple(sample_timesteps, self.num_unets)
+        self.ddim_sampling_eta = ddim_sampling_eta
+        if beta_schedule is None:
+            beta_schedule = ("cosine", *(("cosine",) * max(self.num_unets - 2, 0)),
+                             *(("linear",) * int(self.num_unets > 1)))
+        beta_schedule = _cast_tuple(beta_schedule, self.num_unets)
+        gammas = _cast_tuple(p2_loss_weight_gamma, self.num_unets)
+        self.noise_schedulers = nn.ModuleList([])
+        for ind, (sched, gamma, st) in enumerate(zip(beta_schedule, gammas, self.sample_timesteps)):
+            assert st is None or st <= timesteps, \
+                f"sampling timesteps {st} must be less than or equal to the number of training timesteps {timesteps}"
+            self.noise_schedulers.append(NoiseScheduler(beta_schedule=sched, timesteps=timesteps, loss_type=loss_type,
+                                                        p2_loss_weight_gamma=gamma, p2_loss_weight_k=p2_loss_weight_k))
+
+        frame_sizes = tuple(sorted(set(frame_sizes if frame_sizes is not None else (frame_size,))))
+        assert self.num_unets == len(frame_sizes)
+        self.frame_sizes = frame_sizes
+        self.sample_channels = _cast_tuple(self.channels, len(frame_sizes))
+        self.frame_numbers = frame_numbers
+        self.predict_x_start = _cast_tuple(predict_x_start, len(unets))
+        self.predict_v = _cast_tuple(predict_v, len(unets))
+        self.input_video_range = (-1.0 if not auto_normalize_video else 0.0, 1.0)
+        self.lowres_conds = [None]
+        self.video_cond_drop_prob = video_cond_drop_prob
+        self.text_cond_drop_prob = text_cond_drop_prob
+        self.can_classifier_guidance = video_cond_drop_prob > 0.0 or text_cond_drop_prob > 0.0
+        self.clip_denoised = clip_denoised
+        self.clip_x_start = clip_x_start
+        self.use_dynamic_thres = use_dynamic_thres
+        self.dynamic_thres_percentile = dynamic_thres_percentile
+        self.register_buffer("_dummy", torch.Tensor([True]), persistent=False)
+
+        # sampler options that are not part of the reference surface
+        self.use_cuda_graph = True      # replay one captured step per timestep
+        self.last_launch_stats = {}
+
+    # ------------------------------------------------------------------ reference helpers
+    @property
+    def device(self):
+        return self._dummy.device
+
+    @property
+    def condition_on_text_encodings(self):
+        # the reference tests isinstance(unet, Unet) — the 2-D upstream class — which is never true for a
+        # Unet3D (:1489-1493), so this is always False and sample()/forward() reject text.
+        return False
+
+    def get_unet(self, unet_number):
+        assert 0 < unet_number <= self.num_unets
+        return self.unets[unet_number - 1]
+
+    # ------------------------------------------------------------------ the hot loop
+    def _check_native(self, predict_x_start, predict_v, learned_variance, lowres_cond_vid, lowres_noise_level):
+        if learned_variance:
+            raise NotImplementedError("learned_variance=True is broken for (b,c,t,h,w) tensors in the reference too "
+                                      "(chunk on dim=2, SURVEY.md F5); construct with learned_variance=False")
+        if predict_x_start or predict_v:
+            raise NotImplementedError("only epsilon-prediction is accelerated")
+        if lowres_cond_vid is not None or lowres_noise_level is not None:
+            raise NotImplementedError("low-resolution conditioning is outside the accelerated path")
+        if self.use_dynamic_thres:
+            raise NotImplementedError("dynamic thresholding (quantile) is outside the accelerated path")
+
+    @torch.no_grad()
+    def p_sample_loop_ddpm(self, unet, shape, video_embed, noise_scheduler, predict_x_start=False, predict_v=False,
+                           learned_variance=False, clip_denoised=True, lowres_cond_vid=None, text_encodings=None,
+                           cond_scale=1, is_latent_diffusion=False, lowres_noise_level=None, *, noise_fn=None,
+                           record=None):
+        """Reference: dalle2_video.py:1666-1755.  `noise_fn(shape, step)` (optional) supplies the noise draws
+        (draw 0 = x_T) for parity tests; by default they come from torch.randn on the device, in the
+        reference's order.  `record(t, eps, x)` (optional) observes every step (disables graph replay)."""
+        self._check_native(predict_x_start, predict_v, learned_variance, lowres_cond_vid, lowres_noise_level)
+        assert not (cond_scale != 1.0 and not self.can_classifier_guidance), \
+            "the decoder was not trained with conditional dropout, and thus one cannot use classifier free guidance"
+        device = self.device
+        if device.type != "cuda":
+            raise L.DvError("VideoDecoder(b200) samples on CUDA only: there is no CPU path")
+        b, c, T, H, W = shape
+        cfg = cond_scale != 1
+        beff = 2 * b if cfg else b
+        use_text = text_encodings is not None and unet.cond_on_text_encodings
+        n_text = 0
+        if use_text:
+            text_encodings = text_encodings[:, : unet.max_text_len]
+            n_text = text_encodings.shape[1]
+        eng = unet.engine(beff, T, H, W, unet._resolve_dtype(), device, n_text)
+
+        ones = torch.ones(b, dtype=torch.uint8, device=device)
+        keep = torch.cat((ones, torch.zeros_like(ones))) if cfg else ones
+        rep = (lambda t: torch.cat((t, t), dim=0)) if cfg else (lambda t: t)
+        eng.set_conditioning(rep(video_embed) if video_embed is not None else None,
+                             rep(text_encodings) if use_text else None, keep, keep)
+        eng.set_time_source(True)
+
+        n = b * c * T * H * W
+        steps = noise_scheduler.num_timesteps
+        coef = noise_scheduler.coef_table().to(device)
+        draw = (lambda i: noise_fn(shape, i).to(device)) if noise_fn is not None else \
+            (lambda i: torch.randn(shape, device=device))
+        x = eng.x_in[:b]
+        x.copy_(draw(0))
+        if cfg:
+            eng.x_in[b:].copy_(x)
+        noise = torch.empty(shape, device=device)
+        result = torch.empty(shape, device=device)
+        eps_elems = b * unet.channels_out * T * H * W
+        params = L.DdpmStepParams(
+            x_t=x.data_ptr(), eps=eng.eps.data_ptr(), eps_null=eng.eps.data_ptr() + eps_elems * 4 if cfg else None,
+            noise=noise.data_ptr(), out=x.data_ptr(), unnormalize_out=result.data_ptr(), coef=coef.data_ptr(),
+            t_dev=eng.t_dev.data_ptr(), t_host=0, t_dev_decrement=1, num_timesteps=steps, n=n,
+            cond_scale=float(cond_scale), clip_denoised=int(bool(clip_denoised)), eps_dtype=L.DV_F32)
+        stream_of = lambda: torch.cuda.current_stream(device).cuda_stream  # noqa: E731
+
+        def one_step():
+            eng.run()
+            L.call("dv_ddpm_step", params, stream_of())
+            if cfg:
+                eng.x_in[b:].copy_(x)
+
+        eng.t_dev.fill_(steps - 1)
+        graph = None
+        launches0 = L.launch_count
+        if self.use_cuda_graph and record is None and steps > 2:
+            # warm-up step outside capture (lazy module loading, function attributes), then rewind
+            saved = x.clone()
+            noise.zero_()
+            one_step()
+            torch.cuda.synchronize(device)
+            x.copy_(saved)
+            if cfg:
+                eng.x_in[b:].copy_(x)
+            eng.t_dev.fill_(steps - 1)
+            graph = torch.cuda.CUDAGraph()
+            side = torch.cuda.Stream(device)
+            side.wait_stream(torch.cuda.current_stream(device))
+            with torch.cuda.stream(side):
+                with torch.cuda.graph(graph, stream=side):
+                    one_step()
+            torch.cuda.current_stream(device).wait_stream(side)
+            # capture does not execute: state is still x_T and t_dev == steps-1
+        per_step = L.launch_count - launches0 if graph is None else (L.launch_count - launches0) // 2
+        for i, t in enumerate(reversed(range(steps))):
+            noise.copy_(draw(i + 1))
+            if graph is not None:
+                graph.replay()
+            else:
+                one_step()
+                if record is not None:
+                    record(t, eng.eps[:b].view(b, -1, T, H, W), x)
+        self.last_launch_stats = {"graph": graph is not None, "c_abi_calls_per_step": eng.launches_per_step + 1,
+                                  "tcgen05_convs_per_step": eng.n_tc, "steps": steps}
+        eng.set_time_source(False)
+        out = result if self.auto_normalize_video else x
+        return out.clone()
+
+    @torch.no_grad()
+    def p_sample_loop(self, *args, noise_scheduler, timesteps=None, **kwargs):
+        """Reference: dalle2_video.py:1891-1906."""
+        num_timesteps = noise_scheduler.num_timesteps
+        timesteps = timesteps if timesteps is not None else num_timesteps
+        assert timesteps <= num_timesteps
+        if timesteps < num_timesteps:
+            # the reference's DDIM branch raises TypeError (kwarg mismatch); a working strided
+            # sampler is scope row N1
+            raise NotImplementedError("DDIM / strided sampling is unreachable in the reference and not built yet")
+        return self.p_sample_loop_ddpm(*args, noise_scheduler=noise_scheduler, **kwargs)
+
+    @torch.no_grad()
+    def p_mean_variance(self, unet, x, t, video_embed, noise_scheduler, text_encodings=None, lowres_cond_vid=None,
+                        self_cond=None, clip_denoised=True, predict_x_start=False, predict_v=False,
+                        learned_variance=False, cond_scale=1.0, model_output=None, lowres_noise_level=None):
+        """Reference: dalle2_video.py:1551-1618 (epsilon prediction, fixed variance)."""
+        self._check_native(predict_x_start, predict_v, learned_variance, lowres_cond_vid, lowres_noise_level)
+        assert not (cond_scale != 1.0 and not self.can_classifier_guidance)
+        if model_output is None:
+            model_output = unet.forward_with_cond_scale(x, t, video_embed=video_embed, text_encodings=text_encodings,
+                                                        cond_scale=cond_scale, self_cond=self_cond)
+        x_start = noise_scheduler.predict_start_from_noise(x, t=t, noise=model_output)
+        if clip_denoised:
+            x_start = x_start.clamp(-1.0, 1.0)
+        mean, var, logvar = noise_scheduler.q_posterior(x_start=x_start, x_t=x, t=t)
+        return mean, var, logvar, x_start
+
+    @torch.no_grad()
+    def p_sample(self, unet, x, t, video_embed, noise_scheduler, text_encodings=None, cond_scale=1.0,
+                 lowres_cond_vid=None, self_cond=None, predict_x_start=False, predict_v=False, learned_variance=False,
+                 clip_denoised=True, lowres_noise_level=None, *, noise=None):
+        """Reference: dalle2_video.py:1620-1664.  One step with per-sample timesteps `t` (B,), through the fused
+        kernel when all samples share the timestep, else through the table gathers."""
+        self._check_native(predict_x_start, predict_v, learned_variance, lowres_cond_vid, lowres_noise_level)
+        eps = unet.forward_with_cond_scale(x, t, video_embed=video_embed, text_encodings=text_encodings,
+                                           cond_scale=cond_scale, self_cond=self_cond)
+        if noise is None:
+            noise = torch.randn_like(x)
+        t0 = int(t[0])
+        if bool((t == t0).all()):
+            sched = noise_scheduler
+            coef = sched.coef_table().to(x.device)
+            out = torch.empty_like(x)
+            xc, ec, nc = x.contiguous(), eps.contiguous().float(), noise.contiguous()
+            L.call("dv_ddpm_step", L.DdpmStepParams(
+                x_t=xc.data_ptr(), eps=ec.data_ptr(), eps_null=None, noise=nc.data_ptr(), out=out.data_ptr(),
+                unnormalize_out=None, coef=coef.data_ptr(), t_dev=None, t_host=t0, t_dev_decrement=0,
+                num_timesteps=sched.num_timesteps, n=x.numel(), cond_scale=1.0,
+                clip_denoised=int(bool(clip_denoised)), eps_dtype=L.DV_F32),
+                torch.cuda.current_stream(x.device).cuda_stream)
+            x_start = sched.predict_start_from_noise(x, t=t, noise=eps)
+            return out, (x_start.clamp(-1.0, 1.0) if clip_denoised else x_start)
+        mean, _, logvar, x_start = self.p_mean_variance(unet, x, t, video_embed, noise_scheduler, model_output=eps,
+                                                        clip_denoised=clip_denoised)
+        nonzero = (1 - (t == 0).float()).reshape(x.shape[0], *((1,) * (x.ndim - 1)))
+        return mean + nonzero * (0.5 * logvar).exp() * noise, x_start
+
+    # ------------------------------------------------------------------ user entry point
+    @torch.no_grad()
+    def sample(self, video=None, video_embed=None, text=None, text_encodings=None, batch_size=1, cond_scale=1.0,
+               start_at_unet_number=1, stop_at_unet_number=None, distributed=False, one_unet_in_gpu_at_time=True,
+               cuda="cuda", **loop_kwargs):
+        """Reference: dalle2_video.py:2053-2186 (single base unet)."""
+        assert self.unconditional or video_embed is not None, \
+            "image embed must be present on sampling from decoder unless if trained unconditionally"
+        if not self.unconditional:
+            batch_size = video_embed.shape[0]
+        assert text is None, "raw text needs a CLIP adapter, which is outside the accelerated path"
+        assert not (self.condition_on_text_encodings and text_encodings is None), \
+            "text or text encodings must be passed into decoder if specified"
+        assert not (not self.condition_on_text_encodings and text_encodings is not None), \
+            "decoder specified not to be conditioned on text, yet it is presented"
+        assert start_at_unet_number == 1, "only the base unet is built"
+        if self.frame_numbers is None:
+            raise TypeError("frame_numbers must be given (the reference zips over it, SURVEY.md Q13)")
+        was_training = self.training
+        self.eval()
+        try:
+            unet, vae = self.unets[0], self.vaes[0]
+            sched = self.noise_schedulers[0]
+            frame_size = vae.get_encoded_fmap_size(self.frame_sizes[0])
+            shape = (batch_size, vae.encoded_dim, self.frame_numbers[0], frame_size, frame_size)
+            vid = self.p_sample_loop(unet, shape, video_embed=video_embed, text_encodings=text_encodings,
+                                     cond_scale=_cast_tuple(cond_scale, 1)[0], predict_x_start=self.predict_x_start[0],
+                                     predict_v=self.predict_v[0], learned_variance=self.learned_variance[0],
+                                     clip_denoised=True, noise_scheduler=sched, timesteps=self.sample_timesteps[0],
+                                     **loop_kwargs)
+        finally:
+            self.train(was_training)
+        return vid
+
+    def forward(self, video, video_embed, text=None, text_encodings=None, unet_number=None,
+                return_lowres_cond_video=False):
+        raise NotImplementedError("the training step (p_losses + backward, SURVEY.md §8 a16 / config 4) is not built "
+                                  "in this round: forward kernels have no backward yet (scope row N3)")

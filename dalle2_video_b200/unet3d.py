@@ -1,0 +1,843 @@
+"""Unet3D — drop-in for the reference's denoiser (/root/reference/dalle2_video/dalle2_video.py:247-952).
+
+Same constructor kwargs, same `forward` / `forward_with_cond_scale` / `cast_model_parameters`
+signatures, same `state_dict()` keys and shapes and — because the parameter holders
+below are created with the same torch constructors in the same order — the same random-init weights
+for the same seed.  What differs is everything under `forward`: instead of ~900 ATen calls on NCDHW
+tensors, a static launch plan (`_Engine`) of hand-written sm_100a kernels runs on channels-last
+(NDHWC) activations through the C ABI in include/dv_b200.h.  There is no CPU path: `forward` on a
+non-CUDA tensor raises.
+"""
+from __future__ import annotations
+
+import math
+from functools import partial
+
+import torch
+from torch import nn
+
+from . import _lib as L
+
+
+# ----------------------------------------------------------------------------------------------
+# parameter holders (names/ordering mirror the reference so state_dicts and seeds interchange)
+# ----------------------------------------------------------------------------------------------
+def _default(v, d):
+    return v if v is not None else d
+
+
+def _cast_tuple(val, length=None):
+    if isinstance(val, list):
+        val = tuple(val)
+    out = val if isinstance(val, tuple) else ((val,) * _default(length, 1))
+    if length is not None:
+        assert len(out) == length
+    return out
+
+
+class _Gain(nn.Module):
+    """Holder for dalle2_pytorch.LayerNorm's single parameter `g`."""
+
+    def __init__(self, dim):
+        super().__init__()
+        self.g = nn.Parameter(torch.ones(dim))
+
+
+class _CrossAttn(nn.Module):
+    """Parameters of dalle2_pytorch.CrossAttention(dim, context_dim, heads=8, dim_head=64) (:160-162)."""
+    heads, dim_head = 8, 64
+
+    def __init__(self, dim, context_dim):
+        super().__init__()
+        inner = self.heads * self.dim_head
+        self.norm = _Gain(dim)
+        self.null_kv = nn.Parameter(torch.randn(2, self.dim_head))
+        self.to_q = nn.Linear(dim, inner, bias=False)
+        self.to_kv = nn.Linear(context_dim, inner * 2, bias=False)
+        self.to_out = nn.Sequential(nn.Linear(inner, dim, bias=False), _Gain(dim))
+
+
+class _SelfAttn(nn.Module):
+    """Parameters of dalle2_pytorch.Attention(dim, heads, dim_head) — one shared k/v head (:424-432)."""
+
+    def __init__(self, dim, heads, dim_head):
+        super().__init__()
+        self.heads, self.dim_head = heads, dim_head
+        inner = heads * dim_head
+        self.norm = _Gain(dim)
+        self.null_kv = nn.Parameter(torch.randn(2, dim_head))
+        self.to_q = nn.Linear(dim, inner, bias=False)
+        self.to_kv = nn.Linear(dim, dim_head * 2, bias=False)
+        self.to_out = nn.Sequential(nn.Linear(inner, dim, bias=False), _Gain(dim))
+
+
+class _Fn(nn.Module):
+    """`.fn` wrapper level (RearrangeToSequence / Residual in the reference) — naming only."""
+
+    def __init__(self, fn):
+        super().__init__()
+        self.fn = fn
+
+
+class _Block(nn.Module):
+    def __init__(self, dim, dim_out, groups):
+        super().__init__()
+        self.project = nn.Conv3d(dim, dim_out, kernel_size=(1, 3, 3), padding=(0, 1, 1))
+        self.norm = nn.GroupNorm(groups, dim_out)
+
+
+class _ResBlock(nn.Module):
+    def __init__(self, dim, dim_out, *, cond_dim=None, time_cond_dim=None, groups=8):
+        super().__init__()
+        self.dim, self.dim_out, self.groups = dim, dim_out, groups
+        self.time_mlp = nn.Sequential(nn.SiLU(), nn.Linear(time_cond_dim, dim_out * 2)) if time_cond_dim else None
+        self.cross_attn = _CrossAttn(dim_out, cond_dim) if cond_dim else None
+        self.block1 = _Block(dim, dim_out, groups)
+        self.block2 = _Block(dim_out, dim_out, groups)
+        self.res_conv = nn.Conv3d(dim, dim_out, 1) if dim != dim_out else nn.Identity()
+
+
+class _PixelShuffleUp(nn.Module):
+    def __init__(self, dim, dim_out):
+        super().__init__()
+        self.conv = nn.Conv3d(dim, dim_out * 4, 1)
+        # same initialisation recipe as the reference (:55-62): one kaiming draw repeated x4, zero bias
+        o, i, t, h, w = self.conv.weight.shape
+        base = torch.empty(o // 4, i, t, h, w)
+        nn.init.kaiming_uniform_(base)
+        self.conv.weight.data.copy_(base.repeat_interleave(4, dim=0))
+        nn.init.zeros_(self.conv.bias.data)
+
+
+class _CrossEmbed(nn.Module):
+    def __init__(self, dim_in, kernel_sizes, dim_out):
+        super().__init__()
+        ks = sorted(kernel_sizes)
+        scales = [int(dim_out / (2 ** i)) for i in range(1, len(ks))]
+        scales = [*scales, dim_out - sum(scales)]
+        self.kernel_sizes = ks
+        self.convs = nn.ModuleList([
+            nn.Conv3d(dim_in, d, (1, k, k), stride=(1, 1, 1), padding=(0, (k - 1) // 2, (k - 1) // 2))
+            for k, d in zip(ks, scales)])
+
+
+class Unet3D(nn.Module):
+    """See module docstring.  Constructor kwargs: /root/reference/dalle2_video/dalle2_video.py:248-291."""
+
+    def __init__(self, dim, *, video_embed_dim=None, text_embed_dim=None, cond_dim=None, num_image_tokens=4,
+                 num_time_tokens=2, out_dim=None, dim_mults=(1, 2, 4, 8), channels=3, channels_out=None,
+                 self_attn=False, attn_dim_head=32, attn_heads=16, lowres_cond=False, lowres_noise_cond=False,
+                 self_cond=False, sparse_attn=False, cosine_sim_cross_attn=False, cosine_sim_self_attn=False,
+                 attend_at_middle=True, cond_on_text_encodings=False, max_text_len=256, cond_on_video_embeds=False,
+                 add_video_embeds_to_time=True, init_dim=None, init_conv_ksize=7, resnet_groups=8,
+                 resnet_weight_standardization=False, num_resnet_blocks=2, init_cross_embed=True,
+                 init_cross_embed_kernel_sizes=(3, 7, 15), cross_embed_downsample=False,
+                 cross_embed_downsample_kernel_sizes=(2, 4), memory_efficient=False, scale_skip_connection=False,
+                 pixel_shuffle_upsample=True, final_conv_ksize=1, combine_upsample_fmaps=False,
+                 checkpoint_during_training=False, **kwargs):
+        super().__init__()
+        self._locals = {k: v for k, v in locals().items() if k not in ("self", "__class__")}
+
+        unsupported = dict(sparse_attn=sparse_attn, cosine_sim_cross_attn=cosine_sim_cross_attn,
+                           cosine_sim_self_attn=cosine_sim_self_attn, cross_embed_downsample=cross_embed_downsample,
+                           memory_efficient=memory_efficient, combine_upsample_fmaps=combine_upsample_fmaps,
+                           resnet_weight_standardization=resnet_weight_standardization,
+                           lowres_noise_cond=lowres_noise_cond)
+        bad = [k for k, v in unsupported.items() if v]
+        if bad or not pixel_shuffle_upsample or final_conv_ksize != 1:
+            raise NotImplementedError(f"Unet3D(b200): options outside the accelerated hot path: "
+                                      f"{bad or ['pixel_shuffle_upsample=False / final_conv_ksize!=1']}")
+
+        self.lowres_cond, self.self_cond = lowres_cond, self_cond
+        self.lowres_noise_cond = lowres_noise_cond
+        self.channels = channels
+        self.channels_out = _default(channels_out, channels)
+        self.dim = dim
+        init_channels = channels * (1 + int(lowres_cond) + int(self_cond))
+        init_dim = _default(init_dim, dim)
+        self.init_dim = init_dim
+
+        if init_cross_embed:
+            self.init_conv = _CrossEmbed(init_channels, init_cross_embed_kernel_sizes, init_dim)
+        else:
+            self.init_conv = nn.Conv3d(init_channels, init_dim, (1, init_conv_ksize, init_conv_ksize),
+                                       padding=(0, init_conv_ksize // 2, init_conv_ksize // 2))
+
+        dims = [init_dim, *[dim * m for m in dim_mults]]
+        in_out = list(zip(dims[:-1], dims[1:]))
+        n_stages = len(in_out)
+
+        cond_dim = _default(cond_dim, dim)
+        time_cond_dim = dim * 4
+        self.cond_dim, self.time_cond_dim = cond_dim, time_cond_dim
+        self.num_time_tokens, self.num_image_tokens = num_time_tokens, num_image_tokens
+        self.video_embed_dim = video_embed_dim
+
+        # index 0 / 2 are parameter-free in the reference (SinusoidalPosEmb, GELU): keep the numbering
+        self.to_time_hiddens = nn.Sequential(nn.Identity(), nn.Linear(dim, time_cond_dim), nn.GELU())
+        self.to_time_tokens = nn.Sequential(nn.Linear(time_cond_dim, cond_dim * num_time_tokens), nn.Identity())
+        self.to_time_cond = nn.Sequential(nn.Linear(time_cond_dim, time_cond_dim))
+        self.video_to_tokens = (nn.Sequential(nn.Linear(video_embed_dim, cond_dim * num_image_tokens), nn.Identity())
+                                if cond_on_video_embeds and video_embed_dim != cond_dim else nn.Identity())
+        self.to_video_hiddens = (nn.Sequential(nn.Linear(video_embed_dim, time_cond_dim), nn.GELU())
+                                 if cond_on_video_embeds and add_video_embeds_to_time else None)
+        self.norm_cond = nn.LayerNorm(cond_dim)
+        self.norm_mid_cond = nn.LayerNorm(cond_dim)
+
+        self.text_to_cond, self.text_embed_dim = None, None
+        if cond_on_text_encodings:
+            assert text_embed_dim is not None, \
+                "text_embed_dim must be given to the unet if cond_on_text_encodings is True"
+            self.text_to_cond = nn.Linear(text_embed_dim, cond_dim)
+            self.text_embed_dim = text_embed_dim
+        self.to_lowres_noise_cond = None
+
+        self.cond_on_text_encodings = cond_on_text_encodings
+        self.cond_on_video_embeds = cond_on_video_embeds
+
+        self.null_video_embed = nn.Parameter(torch.randn(1, num_image_tokens, cond_dim))
+        self.null_video_hiddens = nn.Parameter(torch.randn(1, time_cond_dim))
+        self.max_text_len = max_text_len
+        self.null_text_embed = nn.Parameter(torch.randn(1, max_text_len, cond_dim))
+
+        self.skip_connect_scale = 1.0 if not scale_skip_connection else (2 ** -0.5)
+        self.attn_heads, self.attn_dim_head = attn_heads, attn_dim_head
+        self_attn = _cast_tuple(self_attn, n_stages)
+        resnet_groups = _cast_tuple(resnet_groups, n_stages)
+        num_resnet_blocks = _cast_tuple(num_resnet_blocks, n_stages)
+        self._stage_self_attn, self._stage_groups, self._stage_blocks = self_attn, resnet_groups, num_resnet_blocks
+        make_attn = lambda d: _Fn(_Fn(_SelfAttn(d, attn_heads, attn_dim_head)))  # noqa: E731
+        res = partial(_ResBlock, time_cond_dim=time_cond_dim)
+
+        self.init_resnet_block = None
+        self.downs = nn.ModuleList([])
+        self.ups = nn.ModuleList([])
+        skip_dims = []
+        for ind, ((d_in, d_out), groups, nblk, sattn) in enumerate(
+                zip(in_out, resnet_groups, num_resnet_blocks, self_attn)):
+            is_first, is_last = ind == 0, ind >= n_stages - 1
+            layer_cond = cond_dim if not is_first else None
+            skip_dims.append(d_in)
+            self.downs.append(nn.ModuleList([
+                None,
+                res(d_in, d_in, groups=groups),
+                nn.ModuleList([res(d_in, d_in, cond_dim=layer_cond, groups=groups) for _ in range(nblk)]),
+                make_attn(d_in) if sattn else nn.Identity(),
+                # Downsample3D = Sequential(Rearrange, Conv3d(4*dim, dim_out, 1)) (:19-26) / plain 1x1x1 conv (:537)
+                nn.Sequential(nn.Identity(), nn.Conv3d(d_in * 4, d_out, 1)) if not is_last else nn.Conv3d(d_in, d_out, 1),
+            ]))
+
+        mid_dim = dims[-1]
+        self.mid_block1 = res(mid_dim, mid_dim, cond_dim=cond_dim, groups=resnet_groups[-1])
+        self.mid_attn = make_attn(mid_dim)  # built unconditionally in the reference (:551)
+        self.mid_block2 = res(mid_dim, mid_dim, cond_dim=cond_dim, groups=resnet_groups[-1])
+
+        for ind, ((d_in, d_out), groups, nblk, sattn) in enumerate(
+                zip(reversed(in_out), reversed(resnet_groups), reversed(num_resnet_blocks), reversed(self_attn))):
+            is_last = ind >= n_stages - 1
+            layer_cond = cond_dim if not is_last else None
+            skip = skip_dims.pop()
+            self.ups.append(nn.ModuleList([
+                res(d_out + skip, d_out, cond_dim=layer_cond, groups=groups),
+                nn.ModuleList([res(d_out + skip, d_out, cond_dim=layer_cond, groups=groups) for _ in range(nblk)]),
+                make_attn(d_out) if sattn else nn.Identity(),
+                _PixelShuffleUp(d_out, d_in) if not is_last else nn.Identity(),
+            ]))
+
+        self.upsample_combiner = nn.Identity()  # disabled combiner: parameter-free, dim_out == dim
+        self.final_resnet_block = res(dim + dim, dim, groups=resnet_groups[0])
+        out_dim_in = dim + (channels if lowres_cond else 0)
+        self.to_out = nn.Conv3d(out_dim_in, self.channels_out, kernel_size=(1, 1, 1))
+        nn.init.zeros_(self.to_out.weight)  # zero_init_ (:644)
+        nn.init.zeros_(self.to_out.bias)
+        self.checkpoint_during_training = checkpoint_during_training
+
+        self.compute_dtype = None  # None: follow autocast (bf16) else fp32; or torch.float32 / torch.bfloat16
+        self._engines = {}
+        self._param_version = None
+
+    # ------------------------------------------------------------------ reference API surface
+    def cast_model_parameters(self, *, lowres_cond, lowres_noise_cond, channels, channels_out,
+                              cond_on_image_embeds, cond_on_text_encodings):
+        """Same semantics as the reference (:652-681), including the re-instantiation with the kwarg
+        spelt `cond_on_image_embeds` that the constructor swallows."""
+        if (lowres_cond == self.lowres_cond and channels == self.channels
+                and cond_on_image_embeds == self.cond_on_video_embeds
+                and cond_on_text_encodings == self.cond_on_text_encodings
+                and lowres_noise_cond == self.lowres_noise_cond and channels_out == self.channels_out):
+            return self
+        updated = dict(lowres_cond=lowres_cond, channels=channels, channels_out=channels_out,
+                       cond_on_image_embeds=cond_on_image_embeds, cond_on_text_encodings=cond_on_text_encodings,
+                       lowres_noise_cond=lowres_noise_cond)
+        return self.__class__(**{**self._locals, **updated})
+
+    def forward_with_cond_scale(self, *args, cond_scale=1.0, **kwargs):
+        """Reference semantics (:683-692).  The sampler uses the batched cond+uncond plan instead
+        (VideoDecoder.p_sample_loop_ddpm); this entry point keeps the two-pass form for API parity."""
+        logits = self.forward(*args, **kwargs)
+        if cond_scale == 1:
+            return logits
+        null_logits = self.forward(*args, text_cond_drop_prob=1.0, video_cond_drop_prob=1.0, **kwargs)
+        return null_logits + (logits - null_logits) * cond_scale
+
+    def _resolve_dtype(self):
+        if self.compute_dtype is not None:
+            return self.compute_dtype
+        if torch.is_autocast_enabled() and torch.get_autocast_gpu_dtype() == torch.bfloat16:
+            return torch.bfloat16
+        return torch.float32
+
+    def invalidate_cache(self):
+        self._engines.clear()
+
+    def _versions(self):
+        return tuple(p._version for p in self.parameters())
+
+    def engine(self, batch, frames, height, width, dtype, device, n_text=0):
+        ver = self._versions()
+        if ver != self._param_version:  # weights changed (load_state_dict / optimiser step): repack
+            self._engines.clear()
+            self._param_version = ver
+        key = (batch, frames, height, width, dtype, str(device), n_text)
+        eng = self._engines.get(key)
+        if eng is None:
+            eng = _Engine(self, batch, frames, height, width, dtype, device, n_text)
+            self._engines[key] = eng
+        return eng
+
+    @torch.no_grad()
+    def forward(self, x, time, *, video_embed, lowres_cond_video=None, lowres_noise_level=None, text_encodings=None,
+                video_cond_drop_prob=0.0, text_cond_drop_prob=0.0, blur_sigma=None, blur_kernel_size=None,
+                disable_checkpoint=False, self_cond=None):
+        if not x.is_cuda:
+            raise L.DvError("Unet3D(b200).forward needs CUDA tensors: there is no CPU path")
+        if self.lowres_cond or lowres_cond_video is not None or lowres_noise_level is not None:
+            raise NotImplementedError("low-resolution conditioning (cascade stage 2) is outside the accelerated path")
+        b = x.shape[0]
+        if self.self_cond:
+            sc = self_cond if self_cond is not None else torch.zeros_like(x)
+            x = torch.cat((x, sc), dim=1)
+        use_text = text_encodings is not None and self.cond_on_text_encodings
+        n_text = 0
+        if use_text:
+            assert text_encodings.shape[0] == b, "text encodings batch size mismatch"
+            assert self.text_embed_dim == text_encodings.shape[-1], "text encodings dimension mismatch"
+            text_encodings = text_encodings[:, : self.max_text_len]
+            n_text = text_encodings.shape[1]
+        eng = self.engine(b, x.shape[2], x.shape[3], x.shape[4], self._resolve_dtype(), x.device, n_text)
+        keep_v = _prob_mask(b, 1 - video_cond_drop_prob, x.device)
+        keep_t = _prob_mask(b, 1 - text_cond_drop_prob, x.device)
+        eng.set_conditioning(video_embed, text_encodings if use_text else None, keep_v, keep_t)
+        eng.x_in.copy_(x)
+        eng.time_in.copy_(time)
+        eng.run()
+        return eng.eps.clone().view(b, self.channels_out, *x.shape[2:]).to(x.dtype)
+
+
+def _prob_mask(n, prob, device):
+    """prob_mask_like (dalle2_pytorch): p in {0,1} consumes no RNG."""
+    if prob == 1:
+        return torch.ones(n, device=device, dtype=torch.uint8)
+    if prob == 0:
+        return torch.zeros(n, device=device, dtype=torch.uint8)
+    return (torch.zeros(n, device=device).float().uniform_(0, 1) < prob).to(torch.uint8)
+
+
+# ----------------------------------------------------------------------------------------------
+# launch plan
+# ----------------------------------------------------------------------------------------------
+class _Pool:
+    """Plan-time buffer pool: exact-size free lists; buffers are torch allocations (memory plumbing only)."""
+
+    def __init__(self, device):
+        self.device = device
+        self.free = {}
+        self.total = 0
+
+    def get(self, nbytes):
+        nbytes = (int(nbytes) + 255) // 256 * 256
+        lst = self.free.get(nbytes)
+        if lst:
+            return lst.pop()
+        self.total += nbytes
+        return torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+
+    def put(self, buf):
+        self.free.setdefault(buf.numel(), []).append(buf)
+
+
+class _Act:
+    """A channels-last activation [rows][C] living in a pooled buffer."""
+    __slots__ = ("buf", "C", "refs")
+
+    def __init__(self, buf, C):
+        self.buf, self.C, self.refs = buf, C, 1
+
+    @property
+    def ptr(self):
+        return self.buf.data_ptr()
+
+
+class _Engine:
+    """Static launch plan for one (batch, T, H, W, dtype): packed weights, workspaces and the ordered list
+    of C-ABI calls.  `run()` enqueues one full Unet3D forward on the current CUDA stream; inputs are read
+    from the fixed buffers x_in / time_in (or the device step counter t_dev), the result lands in `eps`."""
+
+    def __init__(self, unet: Unet3D, B, T, H, W, dtype, device, n_text):
+        self.u, self.B, self.T, self.H, self.W = unet, B, T, H, W
+        self.dtype, self.device = dtype, device
+        self.code = L.dtype_code(dtype)
+        self.esz = 4 if dtype == torch.float32 else 2
+        self.n_text = n_text
+        self.impl = 0
+        L.lib()
+        self.pool = _Pool(device)
+        self.keep = []          # tensors that must stay alive (packed weights, small fp32 buffers)
+        self.ops = []           # per-step ops
+        self.static_ops = []    # conditioning ops that only depend on video_embed / text
+        self.n_tc = 0
+        f32 = dict(dtype=torch.float32, device=device)
+        u = unet
+        cin = u.channels * (1 + int(u.self_cond))
+        self.x_in = torch.zeros(B, cin, T, H, W, **f32)
+        self.time_in = torch.zeros(B, dtype=torch.int64, device=device)
+        self.t_dev = torch.zeros(1, dtype=torch.int32, device=device)
+        self.use_t_dev = False
+        self.eps = torch.zeros(B, u.channels_out, T * H * W, **f32)
+        self._build()
+
+    # -------------------------------------------------------------- small helpers
+    def _f32(self, t):
+        t = t.detach().to(device=self.device, dtype=torch.float32).contiguous()
+        self.keep.append(t)
+        return t
+
+    def _w(self, t):
+        t = t.detach().to(device=self.device, dtype=self.dtype).contiguous()
+        self.keep.append(t)
+        return t
+
+    def _zeros(self, *shape, dtype=torch.float32):
+        t = torch.zeros(*shape, dtype=dtype, device=self.device)
+        self.keep.append(t)
+        return t
+
+    def _new_act(self, rows, C):
+        return _Act(self.pool.get(rows * C * self.esz), C)
+
+    def _release(self, act):
+        act.refs -= 1
+        if act.refs == 0:
+            self.pool.put(act.buf)
+
+    def _op(self, name, params, static=False):
+        (self.static_ops if static else self.ops).append((name, params))
+
+    def _linear(self, x, w, bias, y, M1, M2, N, K, ldx1, ldx2, ldy1, ldy2, pre=L.ACT_NONE, post=L.ACT_NONE,
+                accum=None, keep=None, alt=None, static=False):
+        p = L.LinearSmallParams(x=x, w=w.data_ptr(), bias=bias.data_ptr() if bias is not None else None, y=y,
+                                accum=accum, keep=keep, alt=alt, M1=M1, M2=M2, N=N, K=K, ldx1=ldx1, ldx2=ldx2,
+                                ldy1=ldy1, ldy2=ldy2, pre_act=pre, post_act=post)
+        self._op("dv_linear_small", p, static)
+
+    # -------------------------------------------------------------- conv / gemm
+    def _conv(self, srcs, weight, bias, out_ptr, Cout, n_img, H, W, *, k=1, mode=L.CONV_NORMAL, epilogue=L.EPI_STORE,
+              stats=None, groups=0, add=None, out_ld=0, out_coff=0, dtype_code=None, frames=None):
+        """srcs: list of (ptr, C).  Falls back to a separate statistics pass when the fused one does not apply."""
+        p = L.ConvParams(src0=srcs[0][0], src1=srcs[1][0] if len(srcs) > 1 else None, weight=weight.data_ptr(),
+                         bias=bias.data_ptr() if bias is not None else None, add=add, out=out_ptr, stats=stats,
+                         n_img=n_img, frames=frames or self.T, H=H, W=W, C0=srcs[0][1],
+                         C1=srcs[1][1] if len(srcs) > 1 else 0, Cout=Cout, kh=k, kw=k, pad=k // 2, mode=mode,
+                         epilogue=epilogue, groups=groups, out_ld=out_ld, out_coff=out_coff,
+                         dtype=self.code if dtype_code is None else dtype_code, impl=self.impl)
+        Ho, Wo = (H // 2, W // 2) if mode == L.CONV_UNSHUFFLE else (H, W)
+        rows_per_sample = (frames or self.T) * Ho * Wo
+        separate_stats = stats is not None and rows_per_sample % 64 != 0
+        if separate_stats:
+            p.stats = None
+        if L.lib().dv_conv_uses_tcgen05(p):
+            self.n_tc += 1
+        self._op("dv_conv_igemm", p)
+        if separate_stats:
+            self._op("dv_gn_stats", L.GnStatsParams(x=out_ptr, stats=stats, B=self.B, P=rows_per_sample, C=Cout,
+                                                    groups=groups, dtype=self.code))
+
+    @staticmethod
+    def _pack_conv(w, skip_scale=1.0, c0=None):
+        """[Cout, Cin, 1, kh, kw] -> [Cout, kh*kw*Cin] with K ordered [tap][cin] (optionally scaling the skip half)."""
+        co, ci, _, kh, kw = w.shape
+        w = w.detach()[:, :, 0]
+        if skip_scale != 1.0 and c0 is not None:
+            w = w.clone()
+            w[:, c0:] *= skip_scale
+        return w.permute(0, 2, 3, 1).reshape(co, kh * kw * ci)
+
+    # -------------------------------------------------------------- plan construction
+    def _build(self):
+        u, B, T, H, W = self.u, self.B, self.T, self.H, self.W
+        dev = self.device
+        dim, cond, tcd = u.dim, u.cond_dim, u.time_cond_dim
+        nt, nv = u.num_time_tokens, (u.num_image_tokens if u.cond_on_video_embeds else 0)
+        use_text = u.cond_on_text_encodings and self.n_text > 0
+        mt = u.max_text_len if use_text else 0
+        n_c, n_mid = nt + nv, nt + nv + mt
+        self.n_c, self.n_mid = n_c, n_mid
+
+        # ---- enumerate resnet blocks (for the concatenated time-MLP) and cross-attention layers
+        blocks = []   # (prefix-less module, ctx kind)
+        for s, st in enumerate(u.downs):
+            blocks.append((st[1], "c"))
+            blocks += [(m, "c") for m in st[2]]
+        blocks += [(u.mid_block1, "mid"), (u.mid_block2, "mid")]
+        for st in u.ups:
+            blocks.append((st[0], "c"))
+            blocks += [(m, "c") for m in st[1]]
+        blocks.append((u.final_resnet_block, "c"))
+        ss_off, off = {}, 0
+        for m, _ in blocks:
+            ss_off[id(m)] = off
+            off += 2 * m.dim_out
+        self.ss_total = off
+        self._ss_offsets = ss_off
+        w_ss = self._f32(torch.cat([m.time_mlp[1].weight for m, _ in blocks], dim=0))
+        b_ss = self._f32(torch.cat([m.time_mlp[1].bias for m, _ in blocks], dim=0))
+        self.ss = self._zeros(B, self.ss_total)
+
+        xa = {"c": [m for m, k in blocks if m.cross_attn is not None and k == "c"],
+              "mid": [m for m, k in blocks if m.cross_attn is not None and k == "mid"]}
+        inner2 = 2 * _CrossAttn.heads * _CrossAttn.dim_head
+        self.kv, kv_w, self.kv_idx = {}, {}, {}
+        for kind, n_tok in (("c", n_c), ("mid", n_mid)):
+            mods = xa[kind]
+            for i, m in enumerate(mods):
+                self.kv_idx[id(m)] = (kind, i)
+            if mods:
+                kv_w[kind] = self._f32(torch.cat([m.cross_attn.to_kv.weight for m in mods], dim=0))
+                self.kv[kind] = self._zeros(B, n_tok, len(mods) * inner2)
+
+        # ---- conditioning buffers
+        self.ve = self._zeros(B, u.video_embed_dim or 1)
+        self.text_enc = self._zeros(B, max(self.n_text, 1), u.text_embed_dim or 1)
+        self.keep_v = self._zeros(B, dtype=torch.uint8)
+        self.keep_t = self._zeros(B, dtype=torch.uint8)
+        self.c_tok = self._zeros(B, n_c, cond)
+        self.mid_tok = self._zeros(B, n_mid, cond)
+        sin_emb, hid = self._zeros(B, dim), self._zeros(B, tcd)
+        time_tok, t_emb = self._zeros(B, nt * cond), self._zeros(B, tcd)
+        t_static = self._zeros(B, tcd) if u.to_video_hiddens is not None else None
+        video_tok = self._zeros(B, max(nv, 1) * cond)
+        text_tok = self._zeros(B, max(self.n_text, 1), cond)
+        half = dim // 2
+        # frequency table computed on the host with torch, exactly as SinusoidalPosEmb does in fp32
+        freqs = self._f32(torch.exp(torch.arange(half, dtype=torch.float32) * -(math.log(10000) / (half - 1))))
+        self._time_embed_params = L.TimeEmbedParams(time=self.time_in.data_ptr(), t_dev=self.t_dev.data_ptr(),
+                                                    freqs=freqs.data_ptr(), out=sin_emb.data_ptr(), B=B, dim=dim)
+
+        # ---- static conditioning ops (depend only on video_embed / text / keep masks)
+        if u.to_video_hiddens is not None:
+            lin = u.to_video_hiddens[0]
+            self._linear(self.ve.data_ptr(), self._f32(lin.weight), self._f32(lin.bias), t_static.data_ptr(), B, 1, tcd,
+                         u.video_embed_dim, u.video_embed_dim, 0, tcd, 0, post=L.ACT_GELU,
+                         keep=self.keep_v.data_ptr(), alt=self._f32(u.null_video_hiddens).data_ptr(), static=True)
+        if nv:
+            if isinstance(u.video_to_tokens, nn.Identity):
+                raise NotImplementedError("video_embed_dim == cond_dim (Identity video_to_tokens) is ill-formed in the "
+                                          "reference as well (SURVEY.md Q2)")
+            lin = u.video_to_tokens[0]
+            self._linear(self.ve.data_ptr(), self._f32(lin.weight), self._f32(lin.bias), video_tok.data_ptr(), B, 1,
+                         nv * cond, u.video_embed_dim, u.video_embed_dim, 0, nv * cond, 0, static=True)
+        if use_text:
+            lin = u.text_to_cond
+            self._linear(self.text_enc.data_ptr(), self._f32(lin.weight), self._f32(lin.bias), text_tok.data_ptr(),
+                         B, self.n_text, cond, u.text_embed_dim, self.n_text * u.text_embed_dim, u.text_embed_dim,
+                         self.n_text * cond, cond, static=True)
+        ln = dict(ln_w=self._f32(u.norm_cond.weight).data_ptr(), ln_b=self._f32(u.norm_cond.bias).data_ptr(),
+                  ln_mid_w=self._f32(u.norm_mid_cond.weight).data_ptr(),
+                  ln_mid_b=self._f32(u.norm_mid_cond.bias).data_ptr())
+        tok_common = dict(time_tokens=time_tok.data_ptr(), video_tokens=video_tok.data_ptr() if nv else None,
+                          null_video=self._f32(u.null_video_embed).data_ptr() if nv else None,
+                          text_tokens=text_tok.data_ptr() if use_text else None,
+                          text_enc=self.text_enc.data_ptr() if use_text else None,
+                          null_text=self._f32(u.null_text_embed).data_ptr() if use_text else None,
+                          keep_video=self.keep_v.data_ptr(), keep_text=self.keep_t.data_ptr(),
+                          c=self.c_tok.data_ptr(), mid_c=self.mid_tok.data_ptr(), B=B, D=cond, n_time=nt, n_video=nv,
+                          n_text_in=self.n_text if use_text else 0, max_text=mt, text_dim=u.text_embed_dim or 1,
+                          eps=float(u.norm_cond.eps), **ln)
+        if n_mid > nt:
+            self._op("dv_cond_tokens", L.CondTokensParams(tok_begin=nt, tok_end=n_mid, **tok_common), static=True)
+
+        def kv_ops(tok0, tok1, static):
+            for kind, toks, n_tok in (("c", self.c_tok, n_c), ("mid", self.mid_tok, n_mid)):
+                if kind not in self.kv:
+                    continue
+                hi = min(tok1, n_tok)
+                if hi <= tok0:
+                    continue
+                N = self.kv[kind].shape[-1]
+                self._linear(toks.data_ptr() + tok0 * cond * 4, kv_w[kind], None,
+                             self.kv[kind].data_ptr() + tok0 * N * 4, B, hi - tok0, N, cond, n_tok * cond, cond,
+                             n_tok * N, N, static=static)
+
+        kv_ops(nt, n_mid, True)
+
+        # ---- per-step conditioning ops
+        self._op("dv_time_embed", self._time_embed_params)
+        lin = u.to_time_hiddens[1]
+        self._linear(sin_emb.data_ptr(), self._f32(lin.weight), self._f32(lin.bias), hid.data_ptr(), B, 1, tcd, dim,
+                     dim, 0, tcd, 0, post=L.ACT_GELU)
+        lin = u.to_time_tokens[0]
+        self._linear(hid.data_ptr(), self._f32(lin.weight), self._f32(lin.bias), time_tok.data_ptr(), B, 1, nt * cond,
+                     tcd, tcd, 0, nt * cond, 0)
+        lin = u.to_time_cond[0]
+        self._linear(hid.data_ptr(), self._f32(lin.weight), self._f32(lin.bias), t_emb.data_ptr(), B, 1, tcd, tcd, tcd,
+                     0, tcd, 0, accum=t_static.data_ptr() if t_static is not None else None)
+        self._linear(t_emb.data_ptr(), w_ss, b_ss, self.ss.data_ptr(), B, 1, self.ss_total, tcd, tcd, 0, self.ss_total,
+                     0, pre=L.ACT_SILU)
+        self._op("dv_cond_tokens", L.CondTokensParams(tok_begin=0, tok_end=nt, **tok_common))
+        kv_ops(0, nt, False)
+
+        # ---- GroupNorm statistics arena: one (B, G, 2) double slot per GroupNorm, zeroed once per forward
+        n_gn = 2 * len(blocks)
+        max_groups = max(m.groups for m, _ in blocks)
+        self.stats = self._zeros(n_gn, B, max_groups, 2, dtype=torch.float64)
+        self._gn_i = 0
+
+        # ---- the network
+        n_img, P = B * T, T * H * W
+        rows = B * P
+        x0 = self._new_act(rows, u.init_dim)
+        if isinstance(u.init_conv, _CrossEmbed):
+            coff = 0
+            for conv, k in zip(u.init_conv.convs, u.init_conv.kernel_sizes):
+                co = conv.weight.shape[0]
+                self._conv([(self.x_in.data_ptr(), conv.weight.shape[1])], self._w(self._pack_conv(conv.weight)),
+                           self._f32(conv.bias), x0.ptr, co, n_img, H, W, k=k, mode=L.CONV_NCDHW_F32_IN,
+                           out_ld=u.init_dim, out_coff=coff)
+                coff += co
+        else:
+            conv = u.init_conv
+            self._conv([(self.x_in.data_ptr(), conv.weight.shape[1])], self._w(self._pack_conv(conv.weight)),
+                       self._f32(conv.bias), x0.ptr, u.init_dim, n_img, H, W, k=conv.kernel_size[1],
+                       mode=L.CONV_NCDHW_F32_IN)
+        x0.refs += 1  # `r = x.clone()` (:751): kept for the head, never copied
+        r = x0
+        x = x0
+        h, w = H, W
+        hiddens = []
+        n_st = len(u.downs)
+        for s, st in enumerate(u.downs):
+            x = self._resblock(st[1], [x], h, w)
+            for m in st[2]:
+                x = self._resblock(m, [x], h, w)
+                x.refs += 1
+                hiddens.append(x)
+            if not isinstance(st[3], nn.Identity):
+                x = self._self_attention(st[3].fn.fn, x, h, w)
+            x.refs += 1
+            hiddens.append(x)
+            post = st[4]
+            if s < n_st - 1:
+                conv = post[1]
+                co, c4 = conv.weight.shape[0], conv.weight.shape[1]
+                ci = c4 // 4
+                # in-channel index of the reference is (c s1 s2) (:24); K order here is [s1][s2][c]
+                wp = conv.weight.detach().reshape(co, ci, 2, 2).permute(0, 2, 3, 1).reshape(co, 4 * ci)
+                y = self._new_act(B * T * (h // 2) * (w // 2), co)
+                self._conv([(x.ptr, ci)], self._w(wp), self._f32(conv.bias), y.ptr, co, n_img, h, w,
+                           mode=L.CONV_UNSHUFFLE)
+                h, w = h // 2, w // 2
+            else:
+                conv = post
+                co = conv.weight.shape[0]
+                y = self._new_act(B * T * h * w, co)
+                self._conv([(x.ptr, x.C)], self._w(conv.weight.detach().reshape(co, -1)), self._f32(conv.bias), y.ptr,
+                           co, n_img, h, w)
+            self._release(x)
+            x = y
+
+        x = self._resblock(u.mid_block1, [x], h, w)
+        x = self._self_attention(u.mid_attn.fn.fn, x, h, w)
+        x = self._resblock(u.mid_block2, [x], h, w)
+
+        for s, st in enumerate(u.ups):
+            skip = hiddens.pop()
+            x = self._resblock(st[0], [x, skip], h, w)
+            for m in st[1]:
+                skip = hiddens.pop()
+                x = self._resblock(m, [x, skip], h, w)
+            if not isinstance(st[2], nn.Identity):
+                x = self._self_attention(st[2].fn.fn, x, h, w)
+            up = st[3]
+            if not isinstance(up, nn.Identity):
+                conv = up.conv
+                co4, ci = conv.weight.shape[0], conv.weight.shape[1]
+                cq = co4 // 4
+                # out-channel index of nn.PixelShuffle is c*4 + 2i + j (:76); rows here are ordered [(i,j)][c]
+                wp = conv.weight.detach().reshape(cq, 4, ci).permute(1, 0, 2).reshape(co4, ci)
+                bp = conv.bias.detach().reshape(cq, 4).permute(1, 0).reshape(co4)
+                y = self._new_act(B * T * (2 * h) * (2 * w), cq)
+                self._conv([(x.ptr, ci)], self._w(wp), self._f32(bp), y.ptr, co4, n_img, h, w,
+                           epilogue=L.EPI_SHUFFLE_SILU)
+                self._release(x)
+                x = y
+                h, w = 2 * h, 2 * w
+
+        x = self._resblock(u.final_resnet_block, [x, r], h, w, skip_scale=1.0)
+        wo = self._f32(u.to_out.weight.reshape(u.channels_out, -1))
+        self._op("dv_to_out", L.ToOutParams(x=x.ptr, w=wo.data_ptr(), bias=self._f32(u.to_out.bias).data_ptr(),
+                                            out=self.eps.data_ptr(), B=B, P=P, C=x.C, Cout=u.channels_out,
+                                            dtype=self.code))
+        self.final_act = x  # kept alive
+
+    def _next_stats(self):
+        i = self._gn_i
+        self._gn_i += 1
+        return self.stats[i].data_ptr()
+
+    def _resblock(self, m: _ResBlock, srcs, h, w, skip_scale=None):
+        """ResnetBlock3D.forward (:172-205); consumes (releases) its sources, returns the output activation."""
+        B, T = self.B, self.T
+        n_img, P = B * T, T * h * w
+        rows = B * P
+        Co, G = m.dim_out, m.groups
+        if skip_scale is None:
+            skip_scale = self.u.skip_connect_scale
+        src_list = [(a.ptr, a.C) for a in srcs]
+        c0 = srcs[0].C if len(srcs) > 1 else None
+        assert sum(a.C for a in srcs) == m.dim
+        off = self._ss_off(m)
+
+        h1 = self._new_act(rows, Co)
+        st1 = self._next_stats()
+        self._conv(src_list, self._w(self._pack_conv(m.block1.project.weight, skip_scale, c0)),
+                   self._f32(m.block1.project.bias), h1.ptr, Co, n_img, h, w, k=3, stats=st1, groups=G)
+        self._op("dv_gn_apply", L.GnApplyParams(
+            x=h1.ptr, out=h1.ptr, residual=None, stats=st1, gamma=self._f32(m.block1.norm.weight).data_ptr(),
+            beta=self._f32(m.block1.norm.bias).data_ptr(), scale=self.ss.data_ptr() + off * 4,
+            shift=self.ss.data_ptr() + (off + Co) * 4, ss_ld=self.ss_total, B=B, P=P, C=Co, groups=G,
+            eps=float(m.block1.norm.eps), dtype=self.code))
+        if m.cross_attn is not None:
+            self._cross_attention(m, h1, rows, P)
+
+        h2 = self._new_act(rows, Co)
+        st2 = self._next_stats()
+        self._conv([(h1.ptr, Co)], self._w(self._pack_conv(m.block2.project.weight)), self._f32(m.block2.project.bias),
+                   h2.ptr, Co, n_img, h, w, k=3, stats=st2, groups=G)
+        self._release(h1)
+        if isinstance(m.res_conv, nn.Identity):
+            assert len(srcs) == 1
+            res_ptr, res_act = srcs[0].ptr, None
+        else:
+            res_act = self._new_act(rows, Co)
+            wr = m.res_conv.weight.detach().reshape(Co, -1)
+            if skip_scale != 1.0 and c0 is not None:
+                wr = wr.clone()
+                wr[:, c0:] *= skip_scale
+            self._conv(src_list, self._w(wr), self._f32(m.res_conv.bias), res_act.ptr, Co, n_img, h, w)
+            res_ptr = res_act.ptr
+        self._op("dv_gn_apply", L.GnApplyParams(
+            x=h2.ptr, out=h2.ptr, residual=res_ptr, stats=st2, gamma=self._f32(m.block2.norm.weight).data_ptr(),
+            beta=self._f32(m.block2.norm.bias).data_ptr(), scale=None, shift=None, ss_ld=0, B=B, P=P, C=Co, groups=G,
+            eps=float(m.block2.norm.eps), dtype=self.code))
+        if res_act is not None:
+            self._release(res_act)
+        for a in srcs:
+            self._release(a)
+        return h2
+
+    def _ss_off(self, m):
+        return self._ss_offsets[id(m)]
+
+    def _cross_attention(self, m: _ResBlock, hact: _Act, rows, P):
+        """h = CrossAttention(h, ctx) + h (:192-201), in place on `hact`."""
+        ca = m.cross_attn
+        C, heads, dh = hact.C, ca.heads, ca.dim_head
+        inner = heads * dh
+        kind, idx = self.kv_idx[id(m)]
+        kv = self.kv[kind]
+        n_ctx = kv.shape[1]
+        xn = self._new_act(rows, C)
+        self._op("dv_layernorm", L.LayerNormParams(x=hact.ptr, out=xn.ptr, residual=None,
+                                                   g=self._f32(ca.norm.g).data_ptr(), beta=None, rows=rows, C=C,
+                                                   eps=1e-5, dtype=self.code))
+        q = self._new_act(rows, inner)
+        self._conv([(xn.ptr, C)], self._w(ca.to_q.weight), None, q.ptr, inner, rows, 1, 1, frames=P)
+        self._op("dv_xattn_core", L.XattnParams(q=q.ptr, out=q.ptr, kv=kv.data_ptr(),
+                                                null_kv=self._f32(ca.null_kv).data_ptr(), B=self.B, P=P, heads=heads,
+                                                dh=dh, n_ctx=n_ctx, kv_ld=kv.shape[2], k_off=idx * 2 * inner,
+                                                v_off=idx * 2 * inner + inner, scale=float(dh ** -0.5),
+                                                dtype=self.code))
+        self._conv([(q.ptr, inner)], self._w(ca.to_out[0].weight), None, xn.ptr, C, rows, 1, 1, frames=P)
+        self._release(q)
+        self._op("dv_layernorm", L.LayerNormParams(x=xn.ptr, out=hact.ptr, residual=hact.ptr,
+                                                   g=self._f32(ca.to_out[1].g).data_ptr(), beta=None, rows=rows, C=C,
+                                                   eps=self._post_proj_eps(), dtype=self.code))
+        self._release(xn)
+
+    def _post_proj_eps(self):
+        # dalle2_pytorch LayerNorm uses eps 1e-5 for fp32 input and 1e-3 otherwise; under bf16 autocast the LN after
+        # the output projection sees bf16.  All LN statistics here are computed in fp32 from
+        # fp32 accumulators, so 1e-5 is used in both modes unless the autocast behaviour is requested explicitly.
+        if self.dtype != torch.float32 and getattr(self.u, "ln_eps_autocast_semantics", False):
+            return 1e-3
+        return 1e-5
+
+    def _self_attention(self, at: _SelfAttn, xact: _Act, h, w):
+        """x = Attention(x) + x over all T*h*w tokens of each sample (:430-432, :921-922), in place."""
+        B, P = self.B, self.T * h * w
+        rows, C = B * P, xact.C
+        heads, dh = at.heads, at.dim_head
+        inner = heads * dh
+        xn = self._new_act(rows, C)
+        self._op("dv_layernorm", L.LayerNormParams(x=xact.ptr, out=xn.ptr, residual=None,
+                                                   g=self._f32(at.norm.g).data_ptr(), beta=None, rows=rows, C=C,
+                                                   eps=1e-5, dtype=self.code))
+        q = self._new_act(rows, inner)
+        kvb = self._new_act(rows, 2 * dh)
+        self._conv([(xn.ptr, C)], self._w(at.to_q.weight), None, q.ptr, inner, rows, 1, 1, frames=P)
+        self._conv([(xn.ptr, C)], self._w(at.to_kv.weight), None, kvb.ptr, 2 * dh, rows, 1, 1, frames=P)
+        # q*scale, then q,k *= sqrt(scale): logits = q.k * scale^2 = q.k / dim_head
+        self._op("dv_attn_mqa", L.AttnMqaParams(q=q.ptr, kv=kvb.ptr, out=q.ptr,
+                                                null_kv=self._f32(at.null_kv).data_ptr(), bias=None, S=B, n=P,
+                                                heads=heads, dh=dh, scale=float(1.0 / dh), dtype=self.code))
+        self._release(kvb)
+        self._conv([(q.ptr, inner)], self._w(at.to_out[0].weight), None, xn.ptr, C, rows, 1, 1, frames=P)
+        self._release(q)
+        # in place unless the input is also held as a skip connection (stage-level self attention)
+        out = xact if xact.refs == 1 else self._new_act(rows, C)
+        self._op("dv_layernorm", L.LayerNormParams(x=xn.ptr, out=out.ptr, residual=xact.ptr,
+                                                   g=self._f32(at.to_out[1].g).data_ptr(), beta=None, rows=rows, C=C,
+                                                   eps=self._post_proj_eps(), dtype=self.code))
+        self._release(xn)
+        if out is not xact:
+            self._release(xact)
+        return out
+
+    # -------------------------------------------------------------- execution
+    def set_conditioning(self, video_embed, text_encodings, keep_video, keep_text):
+        """Copy the step-invariant conditioning inputs into the plan's buffers and run the static ops."""
+        if video_embed is not None and self.u.video_embed_dim:
+            self.ve.copy_(video_embed)
+        if text_encodings is not None and self.n_text:
+            self.text_enc.copy_(text_encodings)
+        self.keep_v.copy_(keep_video)
+        self.keep_t.copy_(keep_text)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        for name, p in self.static_ops:
+            L.call(name, p, stream)
+
+    def set_time_source(self, use_t_dev: bool):
+        """Per-sample int64 `time_in` (Unet3D.forward) or the device step counter `t_dev` (sampler graph)."""
+        self.use_t_dev = use_t_dev
+        self._time_embed_params.time = None if use_t_dev else self.time_in.data_ptr()
+
+    def run(self):
+        """Enqueue one forward on the current stream: eps <- Unet3D(x_in, time)."""
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        self.stats.zero_()
+        for name, p in self.ops:
+            L.call(name, p, stream)
+
+    @property
+    def launches_per_step(self):
+        return len(self.ops) + 1  # + statistics memset

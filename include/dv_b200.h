@@ -1,0 +1,300 @@
+/*
+ * dv_b200.h — C ABI of libdv_b200.so: the B200 (sm_100a) kernels behind the DALLE2-video decoder
+ * denoising step (one Unet3D forward inside the DDPM p_sample loop).
+ *
+ * The reference has no FFI layer: its hot path is Python nn.Modules calling torch/cuDNN/cuBLAS
+ * (SURVEY.md §8b).  Each entry point below names the reference interface it replaces
+ * (file:line under /root/reference/).  The host code that mirrors the reference's Python surface
+ * (dalle2_video_b200.Unet3D / VideoDecoder) binds these with ctypes; INTEGRATION.md shows the stub a
+ * reference maintainer would add.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is DEVICE memory unless the field says "host";
+ *   - the caller owns every buffer (inputs, outputs, scratch); the library never allocates or
+ *     retains pointers past the call (exception: a per-process cache of TMA descriptors keyed by
+ *     the arguments that produced them — values only, no caller memory is referenced);
+ *   - all functions only ENQUEUE work on `stream` (no implicit synchronisation; CUDA-graph
+ *     capturable) and return 0 (DV_OK) or a negative DV_E* code; dv_last_error_string() gives the
+ *     thread-local message of the last failure;
+ *   - activations are channels-last "NDHWC": [B][T][H][W][C], C contiguous, i.e. a row-major
+ *     [rows = B*T*H*W][C] matrix of `dv_dtype` elements; base pointers 16-byte aligned and
+ *     C % 8 == 0 for the vectorised / TMA paths;
+ *   - the 3-channel video tensors at the two ends of the network keep the reference layout
+ *     (B, C, T, H, W) float32.
+ */
+#ifndef DV_B200_H_
+#define DV_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* dv_stream_t; /* cudaStream_t */
+
+typedef enum { DV_F32 = 0, DV_BF16 = 1 } dv_dtype;
+
+#define DV_OK 0
+#define DV_EINVAL (-1)       /* bad shape / null pointer / inconsistent sizes */
+#define DV_EALIGN (-2)       /* pointer or channel count not aligned as required */
+#define DV_EUNSUPPORTED (-3) /* valid request this build has no kernel for */
+#define DV_ECUDA (-4)        /* CUDA launch / driver error (message has cudaGetErrorString) */
+
+int dv_version(void);                    /* ABI version, currently 1 */
+const char* dv_last_error_string(void);  /* thread-local, never NULL */
+int dv_device_sm_count(int device);      /* helper for grid sizing from the host side */
+
+/* ------------------------------------------------------------------------------------------------
+ * K7  fused DDPM posterior update.
+ * Replaces VideoDecoder.p_mean_variance + p_sample arithmetic (dalle2_video/dalle2_video.py:1591-1600,
+ * 1657-1662) and Unet3D.forward_with_cond_scale's CFG blend (:692):
+ *     eps  = eps_null + (eps - eps_null) * cond_scale          (if eps_null != NULL)
+ *     x0   = clamp(c0[t]*x_t - c1[t]*eps, -1, 1)               (clamp iff clip_denoised)
+ *     mean = c2[t]*x0 + c3[t]*x_t
+ *     out  = mean + (t != 0) * exp(0.5*c4[t]) * noise
+ *     if unnormalize_out != NULL and t == 0:  unnormalize_out = (out + 1) / 2   (:1753)
+ * coef is the (T,5) float table  sqrt_recip_alphas_cumprod, sqrt_recipm1_alphas_cumprod,
+ * posterior_mean_coef1, posterior_mean_coef2, posterior_log_variance_clipped.
+ * t is read from *t_dev when t_dev != NULL (graph replay), else from t_host.
+ * If t_dev_decrement != 0 the kernel's last block stores t-1 back to *t_dev.
+ */
+typedef struct {
+  const float* x_t;      /* [n] */
+  const void* eps;       /* [n] eps_dtype, same (B,C,T,H,W) order as x_t */
+  const void* eps_null;  /* [n] or NULL */
+  const float* noise;    /* [n] */
+  float* out;            /* [n] x_{t-1}; may alias x_t */
+  float* unnormalize_out;/* [n] or NULL */
+  const float* coef;     /* [T][5] */
+  int* t_dev;            /* device int or NULL */
+  int t_host;
+  int t_dev_decrement;
+  int num_timesteps;     /* T, bounds check for t_host */
+  int64_t n;             /* total elements */
+  float cond_scale;
+  int clip_denoised;
+  dv_dtype eps_dtype;
+} dv_ddpm_step_params;
+int dv_ddpm_step(const dv_ddpm_step_params* p, dv_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K1 / K3 / K4  implicit-GEMM convolution over channels-last activations.
+ * Replaces nn.Conv3d with (1,k,k) kernels — Block3D.project (:107,124), res_conv (:170),
+ * Downsample3D's rearrange + 1x1x1 conv (:19-26), the last-stage 1x1x1 conv (:537),
+ * PixelShuffleUpsample3D conv + SiLU + PixelShuffle (:64-78), CrossEmbedLayer3D convs (:222-244) —
+ * and, with kh=kw=1 on a [rows][C] matrix, the nn.Linear projections inside CrossAttention /
+ * Attention (external dalle2_pytorch; call sites :160-162, :192-201, :430-432).  torch.cat of skip
+ * connections (:926-928, :945) is replaced by the two-source K loop (src0 channels then src1).
+ *
+ *   out[n][y][x][co] = bias[co] + sum_{tap,ci} W[co][tap*(C0+C1) + ci] * src(n, y*s+dy, x*s+dx, ci)
+ *
+ * weight: [Cout][kh*kw*(C0+C1)] row-major, element type = act dtype (packed once on the host).
+ * DV_CONV_UNSHUFFLE: 2x2 stride-2 gather (pixel-unshuffle), taps ordered [s1][s2], pad 0; out is H/2 x W/2.
+ * DV_CONV_NCDHW_F32_IN: src0 is the (B,C0,T,H,W) float32 video tensor (K4 init conv), frames = T.
+ * Epilogues: bias; optional per-(sample,group) sum / sum-of-squares accumulation for the GroupNorm
+ * that follows (double[B][groups][2], must be zeroed by the caller); optional residual add
+ * (`add`, same layout as out); DV_EPI_SHUFFLE_SILU writes SiLU(v) to the 2x-upsampled tensor
+ * [n][2H][2W][Cout/4] with weight rows pre-ordered [(i,j)][c].
+ * out_ld / out_coff let several convolutions write channel slices of one tensor (K4).
+ * impl: 0 = auto (tcgen05 when the shape qualifies, else SIMT), 1 = force SIMT, 2 = force tcgen05.
+ */
+enum { DV_CONV_NORMAL = 0, DV_CONV_UNSHUFFLE = 1, DV_CONV_NCDHW_F32_IN = 2 };
+enum { DV_EPI_STORE = 0, DV_EPI_SHUFFLE_SILU = 1 };
+typedef struct {
+  const void* src0;
+  const void* src1;   /* NULL when C1 == 0 */
+  const void* weight;
+  const float* bias;  /* [Cout] or NULL */
+  const void* add;    /* residual [rows][Cout] act dtype, or NULL */
+  void* out;
+  double* stats;      /* [B][groups][2] or NULL */
+  int n_img;          /* B*T images */
+  int frames;         /* T (images per sample) */
+  int H, W;           /* input spatial size */
+  int C0, C1, Cout;
+  int kh, kw, pad;
+  int mode;           /* DV_CONV_* */
+  int epilogue;       /* DV_EPI_* */
+  int groups;         /* GroupNorm groups for stats */
+  int out_ld;         /* output row stride in elements (0 = Cout, or Cout/4 for shuffle) */
+  int out_coff;       /* first output channel inside the row */
+  dv_dtype dtype;     /* activations + weights */
+  int impl;
+} dv_conv_params;
+int dv_conv_igemm(const dv_conv_params* p, dv_stream_t stream);
+/* 1 if dv_conv_igemm(impl=auto) would take the tcgen05 path for these params */
+int dv_conv_uses_tcgen05(const dv_conv_params* p);
+
+/* ------------------------------------------------------------------------------------------------
+ * K2  GroupNorm finalize + apply + scale/shift + SiLU (+ residual).
+ * Replaces nn.GroupNorm on the 5-D tensor (statistics over (C/G, T, H, W) jointly, :109,125),
+ * `x * (scale + 1) + shift` (:127-129), nn.SiLU (:131) and the block's residual add (:205).
+ *   y = SiLU( ((x-mean_g)*rstd_g*gamma_c + beta_c) * (1+scale_bc) + shift_bc ) + residual
+ * stats is the double[B][G][2] (sum, sumsq) buffer filled by dv_conv_igemm or dv_gn_stats.
+ */
+typedef struct {
+  const void* x;
+  void* out;              /* may alias x */
+  const void* residual;   /* [B][P][C] or NULL */
+  const double* stats;
+  const float* gamma;
+  const float* beta;
+  const float* scale;     /* &ss[b=0][scale0]; element (b,c) at scale[b*ss_ld + c]; NULL = none */
+  const float* shift;
+  int ss_ld;
+  int B;
+  int64_t P;              /* positions per sample */
+  int C, groups;
+  float eps;
+  dv_dtype dtype;
+} dv_gn_apply_params;
+int dv_gn_apply(const dv_gn_apply_params* p, dv_stream_t stream);
+
+/* Standalone statistics pass (fp32-parity mode and tests): accumulates into zeroed stats. */
+typedef struct {
+  const void* x;
+  double* stats;
+  int B;
+  int64_t P;
+  int C, groups;
+  dv_dtype dtype;
+} dv_gn_stats_params;
+int dv_gn_stats(const dv_gn_stats_params* p, dv_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * a15  LayerNorm over the last dimension (dalle2_pytorch LayerNorm: gain only, biased variance;
+ * nn.LayerNorm when beta != NULL; call sites :374-375 and inside CrossAttention / Attention).
+ *   y = (x-mean)*rsqrt(var+eps)*g (+ beta) (+ residual)
+ */
+typedef struct {
+  const void* x;
+  void* out;
+  const void* residual; /* or NULL */
+  const float* g;
+  const float* beta;    /* or NULL */
+  int64_t rows;
+  int C;
+  float eps;
+  dv_dtype dtype;
+} dv_layernorm_params;
+int dv_layernorm(const dv_layernorm_params* p, dv_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K5 core  cross-attention over a short conditioning context with a learned null key/value.
+ * Replaces CrossAttention.forward between to_q and to_out (external dalle2_pytorch==1.14.2,
+ * SURVEY.md A.4; call site :192-201).  q: [B][P][heads*dh] act dtype.  kv: float32, token j of
+ * sample b at kv + (b*n_ctx + j)*kv_ld, keys at [k_off + h*dh + d], values at [v_off + h*dh + d].
+ * null_kv: float32 [2][dh], prepended as key/value 0 for every head.  logits = scale * q.k,
+ * softmax in fp32.
+ */
+typedef struct {
+  const void* q;
+  void* out;
+  const float* kv;
+  const float* null_kv;
+  int B;
+  int64_t P;
+  int heads, dh;
+  int n_ctx;
+  int64_t kv_ld;
+  int k_off, v_off;
+  float scale;
+  dv_dtype dtype;
+} dv_xattn_params;
+int dv_xattn_core(const dv_xattn_params* p, dv_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K6  multi-query self-attention, flash style (never materialises the n x (n+1) logits).
+ * Replaces Attention.forward between to_q/to_kv and to_out (external dalle2_pytorch==1.14.2,
+ * SURVEY.md A.3; built :424-432, called :921-922): `heads` query heads share ONE key/value head;
+ * a learned null key/value is prepended; logits = scale * q.k (+ bias[h][i][j], j including the
+ * null column, for the temporal-attention extension).
+ * q: [S][n][heads*dh], kv: [S][n][2*dh] (k then v), out like q; S = independent sequences.
+ */
+typedef struct {
+  const void* q;
+  const void* kv;
+  void* out;
+  const float* null_kv; /* [2][dh] */
+  const float* bias;    /* [heads][n][n+1] or NULL */
+  int64_t S;
+  int n;
+  int heads, dh;
+  float scale;
+  dv_dtype dtype;
+} dv_attn_mqa_params;
+int dv_attn_mqa(const dv_attn_mqa_params* p, dv_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K8  conditioning prologue pieces (float32 throughout; M = batch-sized GEMVs).
+ * dv_time_embed replaces SinusoidalPosEmb (:349) on time.type_as(x) (:755).
+ * dv_linear_small replaces the nn.Linear / SiLU / GELU chains of :348-372, :386 and every
+ * ResnetBlock3D.time_mlp (:153-155) and CrossAttention.to_kv: y = post(W . pre(x) + b).
+ * dv_cond_tokens replaces the where(keep, tokens, null) selects, the token concatenation and
+ * norm_cond / norm_mid_cond (:784-865).
+ */
+typedef struct {
+  const int64_t* time; /* [B], or NULL to broadcast *t_dev to every sample (graph replay) */
+  const int* t_dev;    /* device int, used when time == NULL */
+  const float* freqs;  /* [dim/2] exp(-j*ln(10000)/(dim/2-1)), computed on the host exactly as the reference does */
+  float* out;          /* [B][dim] = cat(sin(t*f), cos(t*f)) */
+  int B, dim;
+} dv_time_embed_params;
+int dv_time_embed(const dv_time_embed_params* p, dv_stream_t stream);
+
+enum { DV_ACT_NONE = 0, DV_ACT_SILU = 1, DV_ACT_GELU = 2 };
+typedef struct {
+  const float* x;   /* row (m1,m2) at x + m1*ldx1 + m2*ldx2, K contiguous floats */
+  const float* w;   /* [N][K] */
+  const float* bias;/* [N] or NULL */
+  float* y;         /* row (m1,m2) at y + m1*ldy1 + m2*ldy2, N contiguous floats */
+  const float* accum; /* optional, row (m1,m2) at accum + (m1*M2+m2)*N, added after post-activation */
+  const uint8_t* keep; /* optional [M1]: where keep[m1]==0 the result row is replaced by alt (torch.where, :790-792) */
+  const float* alt;    /* [M2][N], required when keep != NULL */
+  int M1, M2, N, K;
+  int64_t ldx1, ldx2, ldy1, ldy2;
+  int pre_act, post_act;
+} dv_linear_small_params;
+int dv_linear_small(const dv_linear_small_params* p, dv_stream_t stream);
+
+typedef struct {
+  const float* time_tokens;   /* [B][n_time][D] */
+  const float* video_tokens;  /* [B][n_video][D] or NULL */
+  const float* null_video;    /* [n_video][D] */
+  const float* text_tokens;   /* [B][n_text_in][D] or NULL (already projected by text_to_cond) */
+  const float* text_enc;      /* [B][n_text_in][text_dim] raw encodings, for the any(!=0) mask */
+  const float* null_text;     /* [max_text][D] */
+  const float* ln_w; const float* ln_b;         /* norm_cond */
+  const float* ln_mid_w; const float* ln_mid_b; /* norm_mid_cond */
+  const uint8_t* keep_video;  /* [B] 0/1 */
+  const uint8_t* keep_text;   /* [B] 0/1 */
+  float* c;                   /* [B][n_time+n_video][D] */
+  float* mid_c;               /* [B][n_time+n_video+max_text][D] (max_text = 0 without text) */
+  int B, D, n_time, n_video, n_text_in, max_text, text_dim;
+  int tok_begin, tok_end;     /* only tokens [tok_begin, tok_end) of the concatenation are (re)computed:
+                                 the time tokens change every step, the video/text tokens do not */
+  float eps;
+} dv_cond_tokens_params;
+int dv_cond_tokens(const dv_cond_tokens_params* p, dv_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Head: to_out 1x1x1 convolution from channels-last activations to the reference's (B,C,T,H,W)
+ * float32 layout (:637-642, :952).  w: float32 [Cout][C].
+ */
+typedef struct {
+  const void* x;   /* [B][P][C] */
+  const float* w;
+  const float* bias;
+  float* out;      /* [B][Cout][P] */
+  int B;
+  int64_t P;
+  int C, Cout;
+  dv_dtype dtype;
+} dv_to_out_params;
+int dv_to_out(const dv_to_out_params* p, dv_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DV_B200_H_ */

@@ -276,8 +276,8 @@ def unet3d_forward(sd, cfg: UnetConfig, x, time, *, video_embed=None, text_encod
 
     # middle (:919-924)
     x = _resnet_block(sd, "mid_block1.", x, t, mid_c, groups[-1])
-    if cfg.attend_at_middle:
-        x = _joint_attention(sd, "mid_attn.", x, cfg.attn_heads, cfg.attn_dim_head)
+    # mid_attn is built and applied unconditionally: `attend_at_middle` is accepted but never read (:551, :921)
+    x = _joint_attention(sd, "mid_attn.", x, cfg.attn_heads, cfg.attn_dim_head)
     x = _resnet_block(sd, "mid_block2.", x, t, mid_c, groups[-1])
 
     # up path (:930-941)

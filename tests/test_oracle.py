@@ -1,0 +1,135 @@
+"""CPU: the oracle restatement against the committed golden fixtures (generated from the reference's own
+Unet3D / VideoDecoder code by oracle/make_golden.py) and against known answers."""
+import math
+
+import pytest
+import torch
+
+from conftest import golden
+from oracle import primitives as P
+from oracle.unet3d import UnetConfig, ddpm_coefficients, forward_with_cond_scale, p_sample_loop_ddpm
+from oracle.weights import synth_state_dict
+
+
+@pytest.mark.parametrize("name", ["tiny", "tiny_text", "headline_small"])
+def test_unet_forward_matches_reference_fixture(name, layouts):
+    g = golden(f"unet3d_{name}.pt")
+    sd = synth_state_dict(layouts[name], seed=g["weight_seed"])
+    with torch.no_grad():
+        out = forward_with_cond_scale(sd, UnetConfig(**g["unet_kwargs"]), g["x"], g["times"],
+                                      video_embed=g["video_embed"], text_encodings=g["text_encodings"],
+                                      cond_scale=g["cond_scale"])
+    rel = float((out - g["eps"]).norm() / g["eps"].norm())
+    assert rel < 1e-5, rel  # fp32, same op order up to reduction order
+
+
+def test_sampler_matches_reference_fixture(layouts):
+    g = golden("sample_tiny_8.pt")
+    cfg = UnetConfig(dim=32, video_embed_dim=512, dim_mults=(1, 2), cond_on_video_embeds=True)
+    sd = synth_state_dict(layouts["tiny"], seed=g["weight_seed"])
+    sched = P.NoiseScheduler(beta_schedule="cosine", timesteps=g["timesteps"], loss_type="l2")
+    torch.manual_seed(g["sample_seed"])  # RNG contract: randn(shape) then one randn per step (:1689, :1657)
+    with torch.no_grad():
+        vid = p_sample_loop_ddpm(sd, cfg, sched, tuple(g["sample"].shape), video_embed=g["video_embed"])
+    assert float((vid - g["sample"]).abs().max()) < 1e-3
+    assert 0.0 <= float(vid.min()) and float(vid.max()) <= 1.0
+
+
+def test_text_cfg_sampler_matches_reference_fixture(layouts):
+    g = golden("sample_tiny_text_cfg_6.pt")
+    cfg = UnetConfig(dim=32, video_embed_dim=512, dim_mults=(1, 2), cond_on_video_embeds=True,
+                     cond_on_text_encodings=True, text_embed_dim=64)
+    sd = synth_state_dict(layouts["tiny_text"], seed=g["weight_seed"])
+    sched = P.NoiseScheduler(beta_schedule="cosine", timesteps=g["timesteps"], loss_type="l2")
+    torch.manual_seed(g["sample_seed"])
+    with torch.no_grad():
+        vid = p_sample_loop_ddpm(sd, cfg, sched, tuple(g["sample"].shape), video_embed=g["video_embed"],
+                                 text_encodings=g["text_encodings"], cond_scale=g["cond_scale"])
+    assert float((vid - g["sample"]).abs().max()) < 1e-3
+
+
+def test_schedule_tables_match_reference_fixture():
+    g = golden("sample_tiny_50.pt")
+    s = P.NoiseScheduler(beta_schedule="cosine", timesteps=50, loss_type="l2")
+    for k in ("betas", "posterior_log_variance_clipped", "posterior_mean_coef1", "posterior_mean_coef2",
+              "sqrt_recip_alphas_cumprod", "sqrt_recipm1_alphas_cumprod"):
+        assert torch.equal(getattr(s, k), g[k]), k
+
+
+def test_cosine_schedule_known_answers():
+    # observed on the reference run during the survey (SURVEY.md §8c anchor (i))
+    b = P.cosine_beta_schedule(50)
+    assert [round(float(v), 4) for v in b[:3]] == [0.0017, 0.0037, 0.0056]
+    assert [round(float(v), 4) for v in b[-3:]] == [0.5548, 0.7498, 0.9990]
+    assert b.dtype == torch.float64
+
+
+def test_linear_schedule_endpoints():
+    b = P.linear_beta_schedule(1000)
+    assert abs(float(b[0]) - 1e-4) < 1e-12 and abs(float(b[-1]) - 0.02) < 1e-12
+
+
+def test_sampler_identities():
+    # anchors (iii): predict_start_from_noise inverts q_sample; posterior of the true x0 is consistent
+    s = P.NoiseScheduler(beta_schedule="cosine", timesteps=100, loss_type="l2")
+    g = torch.Generator().manual_seed(0)
+    x0 = torch.rand(3, 3, 2, 4, 4, generator=g) * 2 - 1
+    eps = torch.randn(x0.shape, generator=g)
+    t = torch.tensor([0, 40, 98])
+    xt = s.q_sample(x0, t, eps)
+    back = s.predict_start_from_noise(xt, t, eps)
+    assert float((back - x0).abs().max()) < 5e-3  # sqrt_recipm1 is large near t=T; fp32 tables
+    mean, var, logvar = s.q_posterior(x0, xt, t)
+    assert mean.shape == xt.shape and var.shape == (3, 1, 1, 1, 1)
+    assert torch.allclose(logvar.exp()[1:], var[1:], rtol=1e-5)
+    co = ddpm_coefficients(s)
+    assert co.shape == (100, 5) and co.dtype == torch.float32
+
+
+def test_prob_mask_like_consumes_no_rng_at_0_and_1():
+    torch.manual_seed(3)
+    a = torch.rand(1)
+    torch.manual_seed(3)
+    m1 = P.prob_mask_like((4,), 1.0, "cpu")
+    m0 = P.prob_mask_like((4,), 0.0, "cpu")
+    b = torch.rand(1)
+    assert torch.equal(a, b) and bool(m1.all()) and not bool(m0.any())
+    torch.manual_seed(3)
+    P.prob_mask_like((4,), 0.5, "cpu")
+    assert not torch.equal(a, torch.rand(1))
+
+
+def test_layernorm_eps_switch_and_gain_only():
+    ln = P.LayerNorm(8)
+    assert [n for n, _ in ln.named_parameters()] == ["g"]
+    x = torch.randn(2, 8) * 1e-3
+    y32 = ln(x)
+    y16 = ln(x.bfloat16()).float()
+    var = x.var(-1, unbiased=False, keepdim=True)
+    assert torch.allclose(y32, (x - x.mean(-1, keepdim=True)) * (var + 1e-5).rsqrt(), atol=1e-6)
+    # eps 1e-3 dominates a 1e-6 variance: output much smaller than with 1e-5
+    assert float(y16.abs().max()) < 0.5 * float(y32.abs().max())
+
+
+def test_attention_double_scaling():
+    # cosine_sim=False: logits = q.k / dim_head (q*scale, then q,k * sqrt(scale)) — SURVEY.md A.3
+    torch.manual_seed(0)
+    at = P.Attention(16, heads=2, dim_head=8, cosine_sim=False)
+    x = torch.randn(1, 5, 16)
+    xn = at.norm(x)
+    q = at.to_q(xn).reshape(1, 5, 2, 8).permute(0, 2, 1, 3)
+    k, v = at.to_kv(xn).chunk(2, -1)
+    k = torch.cat((at.null_kv[0].expand(1, 1, 8), k), 1)
+    v = torch.cat((at.null_kv[1].expand(1, 1, 8), v), 1)
+    attn = (torch.einsum("bhid,bjd->bhij", q, k) / 8).softmax(-1)
+    out = torch.einsum("bhij,bjd->bhid", attn, v).permute(0, 2, 1, 3).reshape(1, 5, 16)
+    ref = at.to_out(out)
+    assert torch.allclose(at(x), ref, atol=1e-5)
+
+
+def test_sinusoidal_pos_emb_layout():
+    e = P.SinusoidalPosEmb(8)(torch.tensor([0.0, 3.0]))
+    assert e.shape == (2, 8)
+    assert torch.allclose(e[0], torch.tensor([0.0] * 4 + [1.0] * 4))
+    f1 = math.exp(-math.log(10000) / 3)
+    assert abs(float(e[1, 1]) - math.sin(3.0 * f1)) < 1e-6 and abs(float(e[1, 5]) - math.cos(3.0 * f1)) < 1e-6
