@@ -1,0 +1,347 @@
+"""-m gpu: every C-ABI kernel against a plain torch fp32 statement of the reference op it replaces, on
+seeded inputs.  Tolerances: fp32 kernels 1e-5 relative (reduction order only); bf16 kernels 1e-2
+relative against the fp32 result computed from the same bf16-rounded inputs."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from dalle2_video_b200 import _lib as L
+from gpu_util import code, conv, ptr, rel_err, stream
+
+pytestmark = pytest.mark.gpu
+DT = [torch.float32, torch.bfloat16]
+TOL = {torch.float32: 2e-5, torch.bfloat16: 1.2e-2}
+
+
+def dev():
+    return torch.device("cuda:0")
+
+
+def rnd(*shape, dtype=torch.float32, seed=0, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).to(dev()).to(dtype)
+
+
+def cl_to_ncdhw(x, B, T, H, W):  # [B*T*H*W, C] -> (B, C, T, H, W)
+    return x.float().reshape(B, T, H, W, -1).permute(0, 4, 1, 2, 3)
+
+
+def ncdhw_to_cl(x):
+    return x.permute(0, 2, 3, 4, 1).reshape(-1, x.shape[1])
+
+
+# ------------------------------------------------------------------ K7
+@pytest.mark.parametrize("eps_dtype", DT)
+@pytest.mark.parametrize("t", [0, 1, 23, 49])
+def test_ddpm_step_matches_reference_math(eps_dtype, t):
+    from dalle2_video_b200 import NoiseScheduler
+    s = NoiseScheduler(beta_schedule="cosine", timesteps=50, loss_type="l2").to(dev())
+    shape = (2, 3, 4, 16, 16)
+    coef = s.coef_table()
+    x, eps, noise = rnd(*shape, seed=1), rnd(*shape, seed=2).to(eps_dtype), rnd(*shape, seed=3)
+    eps0 = rnd(*shape, seed=4).to(eps_dtype)
+    for cfg in (False, True):
+        out, un = torch.empty_like(x), torch.full_like(x, -7.0)
+        L.call("dv_ddpm_step", L.DdpmStepParams(
+            x_t=ptr(x), eps=ptr(eps), eps_null=ptr(eps0) if cfg else None, noise=ptr(noise), out=ptr(out),
+            unnormalize_out=ptr(un), coef=ptr(coef), t_dev=None, t_host=t, t_dev_decrement=0,
+            num_timesteps=50, n=x.numel(), cond_scale=2.5, clip_denoised=1, eps_dtype=code(eps)), stream())
+        tt = torch.full((2,), t, device=dev())
+        e = eps.float()
+        if cfg:
+            e = eps0.float() + (e - eps0.float()) * 2.5
+        x0 = s.predict_start_from_noise(x, tt, e).clamp(-1, 1)
+        mean, _, logvar = s.q_posterior(x0, x, tt)
+        ref = mean + (0.0 if t == 0 else 1.0) * (0.5 * logvar).exp() * noise
+        assert rel_err(out, ref) < 1e-6
+        if t == 0:
+            assert rel_err(un, (ref + 1) * 0.5) < 1e-6
+        else:
+            assert float(un.max()) == -7.0  # untouched unless t == 0
+
+
+def test_ddpm_step_device_counter_and_errors():
+    from dalle2_video_b200 import NoiseScheduler
+    s = NoiseScheduler(beta_schedule="cosine", timesteps=10, loss_type="l2").to(dev())
+    coef = s.coef_table()
+    x, eps, noise = rnd(64, seed=1), rnd(64, seed=2), rnd(64, seed=3)
+    t_dev = torch.tensor([5], dtype=torch.int32, device=dev())
+    out = torch.empty_like(x)
+    p = L.DdpmStepParams(x_t=ptr(x), eps=ptr(eps), eps_null=None, noise=ptr(noise), out=ptr(out),
+                         unnormalize_out=None, coef=ptr(coef), t_dev=ptr(t_dev), t_host=0,
+                         t_dev_decrement=1, num_timesteps=10, n=64, cond_scale=1.0, clip_denoised=0,
+                         eps_dtype=L.DV_F32)
+    L.call("dv_ddpm_step", p, stream())
+    assert int(t_dev) == 4
+    tt = torch.full((1,), 5, device=dev())
+    x0 = s.predict_start_from_noise(x[None], tt, eps[None])
+    mean, _, lv = s.q_posterior(x0, x[None], tt)
+    assert rel_err(out, (mean + (0.5 * lv).exp() * noise[None])[0]) < 1e-6
+    p.n = 63
+    with pytest.raises(L.DvError, match="multiple of 4"):
+        L.call("dv_ddpm_step", p, stream())
+    p.n, p.t_dev, p.t_host = 64, None, 10
+    with pytest.raises(L.DvError, match="outside"):
+        L.call("dv_ddpm_step", p, stream())
+
+
+# ------------------------------------------------------------------ K1 / K3 / K4
+@pytest.mark.parametrize("dtype", DT)
+@pytest.mark.parametrize("case", [
+    dict(B=2, T=2, H=8, W=8, C=(32,), Co=32, k=3),                # tiny-config block
+    dict(B=1, T=2, H=16, W=16, C=(64, 32), Co=64, k=3),           # two-source (skip concat) 3x3
+    dict(B=1, T=4, H=8, W=8, C=(128, 64), Co=128, k=1),           # res_conv over a concat
+    dict(B=2, T=1, H=4, W=4, C=(256,), Co=512, k=1),              # last-stage 1x1x1
+    dict(B=1, T=2, H=6, W=10, C=(16,), Co=20, k=3),               # ragged: rows not a multiple of the tile
+])
+def test_conv_igemm_matches_conv3d(dtype, case):
+    B, T, H, W, Co, k = (case[x] for x in ("B", "T", "H", "W", "Co", "k"))
+    xs = [rnd(B * T * H * W, c, dtype=dtype, seed=10 + i) for i, c in enumerate(case["C"])]
+    cin = sum(case["C"])
+    w5 = rnd(Co, cin, 1, k, k, seed=20, scale=1 / math.sqrt(cin * k * k))
+    bias = rnd(Co, seed=21)
+    wp = w5[:, :, 0].permute(0, 2, 3, 1).reshape(Co, -1).to(dtype).contiguous()
+    G = 4
+    rows = B * T * H * W
+    fused = (T * H * W) % 64 == 0 and (Co // G) % 4 == 0
+    stats = torch.zeros(B, G, 2, dtype=torch.float64, device=dev())
+    add = rnd(rows, Co, dtype=dtype, seed=22)
+    out = torch.empty(rows, Co, dtype=dtype, device=dev())
+    conv(xs, wp, bias, out, n_img=B * T, frames=T, H=H, W=W, k=k, stats=stats if fused else None, groups=G, add=add)
+    xin = torch.cat([cl_to_ncdhw(x, B, T, H, W) for x in xs], dim=1)
+    w_ref = wp.float().reshape(Co, k, k, cin).permute(0, 3, 1, 2)[:, :, None]
+    y = F.conv3d(xin, w_ref, bias, padding=(0, k // 2, k // 2))
+    ref = ncdhw_to_cl(y)
+    assert rel_err(out, ref + add.float()) < TOL[dtype]
+    if fused:
+        yq = ref.to(dtype).float().reshape(B, -1, G, Co // G)
+        s1 = yq.sum(dim=(1, 3)).double()
+        s2 = (yq * yq).sum(dim=(1, 3)).double()
+        assert rel_err(stats[..., 1], s2) < 1e-3 and float((stats[..., 0] - s1).abs().max()) < 1e-2 * float(s2.max().sqrt())
+
+
+@pytest.mark.parametrize("dtype", DT)
+def test_conv_unshuffle_matches_downsample3d(dtype):
+    B, T, H, W, C, Co = 1, 2, 8, 8, 32, 64
+    x = rnd(B * T * H * W, C, dtype=dtype, seed=1)
+    w5 = rnd(Co, 4 * C, 1, 1, 1, seed=2, scale=1 / math.sqrt(4 * C))
+    bias = rnd(Co, seed=3)
+    wp = w5.reshape(Co, C, 2, 2).permute(0, 2, 3, 1).reshape(Co, 4 * C).to(dtype).contiguous()
+    out = torch.empty(B * T * (H // 2) * (W // 2), Co, dtype=dtype, device=dev())
+    conv([x], wp, bias, out, n_img=B * T, frames=T, H=H, W=W, mode=L.CONV_UNSHUFFLE)
+    xin = cl_to_ncdhw(x, B, T, H, W)
+    # Rearrange "b c t (h s1) (w s2) -> b (c s1 s2) t h w" (dalle2_video.py:24)
+    xr = xin.reshape(B, C, T, H // 2, 2, W // 2, 2).permute(0, 1, 4, 6, 2, 3, 5).reshape(B, 4 * C, T, H // 2, W // 2)
+    w_ref = wp.float().reshape(Co, 2, 2, C).permute(0, 3, 1, 2).reshape(Co, 4 * C)[:, :, None, None, None]
+    ref = ncdhw_to_cl(F.conv3d(xr, w_ref, bias))
+    assert rel_err(out, ref) < TOL[dtype]
+
+
+@pytest.mark.parametrize("dtype", DT)
+def test_conv_shuffle_silu_matches_pixelshuffleupsample3d(dtype):
+    B, T, H, W, C, Cq = 1, 2, 4, 4, 64, 32
+    x = rnd(B * T * H * W, C, dtype=dtype, seed=1)
+    w5 = rnd(4 * Cq, C, 1, 1, 1, seed=2, scale=1 / math.sqrt(C))
+    bias = rnd(4 * Cq, seed=3)
+    wq = w5.to(dtype)
+    wp = wq.reshape(Cq, 4, C).permute(1, 0, 2).reshape(4 * Cq, C).contiguous()
+    bp = bias.reshape(Cq, 4).permute(1, 0).reshape(-1).contiguous()
+    out = torch.empty(B * T * 2 * H * 2 * W, Cq, dtype=dtype, device=dev())
+    conv([x], wp, bp, out, n_img=B * T, frames=T, H=H, W=W, epilogue=L.EPI_SHUFFLE_SILU)
+    y = F.silu(F.conv3d(cl_to_ncdhw(x, B, T, H, W), wq.float(), bias))
+    y = F.pixel_shuffle(y.permute(0, 2, 1, 3, 4).reshape(B * T, 4 * Cq, H, W), 2)
+    ref = y.reshape(B, T, Cq, 2 * H, 2 * W).permute(0, 1, 3, 4, 2).reshape(-1, Cq)
+    assert rel_err(out, ref) < TOL[dtype]
+
+
+@pytest.mark.parametrize("dtype", DT)
+@pytest.mark.parametrize("k", [3, 7, 15])
+def test_init_conv_from_ncdhw_f32(dtype, k):
+    B, T, H, W, Co = 2, 2, 16, 16, 16
+    x = rnd(B, 3, T, H, W, seed=1)
+    w5 = rnd(Co, 3, 1, k, k, seed=2, scale=1 / math.sqrt(3 * k * k))
+    bias = rnd(Co, seed=3)
+    wp = w5[:, :, 0].permute(0, 2, 3, 1).reshape(Co, -1).to(dtype).contiguous()
+    out = torch.zeros(B * T * H * W, 32, dtype=dtype, device=dev())
+    conv([x], wp, bias, out, n_img=B * T, frames=T, H=H, W=W, k=k, mode=L.CONV_NCDHW_F32_IN, out_ld=32, out_coff=16)
+    w_ref = wp.float().reshape(Co, k, k, 3).permute(0, 3, 1, 2)[:, :, None]
+    ref = ncdhw_to_cl(F.conv3d(x, w_ref, bias, padding=(0, k // 2, k // 2)))
+    assert rel_err(out[:, 16:], ref) < TOL[dtype]
+    assert float(out[:, :16].abs().max()) == 0.0  # channel slice only
+
+
+def test_conv_rejects_bad_arguments():
+    x = rnd(64, 24)
+    w = rnd(8, 24)
+    out = torch.empty(64, 8, device=dev())
+    with pytest.raises(L.DvError, match="multiples of 16"):
+        conv([x], w, None, out, n_img=1, frames=1, H=8, W=8)
+    x = rnd(64, 32)
+    w = rnd(6, 32)
+    with pytest.raises(L.DvError, match="multiple of 4"):
+        conv([x], w, None, torch.empty(64, 6, device=dev()), n_img=1, frames=1, H=8, W=8)
+
+
+# ------------------------------------------------------------------ K2
+@pytest.mark.parametrize("dtype", DT)
+@pytest.mark.parametrize("C,G,with_ss,with_res", [(32, 8, True, False), (96, 8, False, True), (64, 8, True, True)])
+def test_groupnorm_stats_apply(dtype, C, G, with_ss, with_res):
+    B, T, H, W = 2, 3, 8, 8
+    P = T * H * W
+    x = rnd(B * P, C, dtype=dtype, seed=1, scale=2.0) + 0.5
+    gamma, beta = rnd(C, seed=2) * 0.1 + 1, rnd(C, seed=3) * 0.1
+    ss = rnd(B, 2 * C + 8, seed=4) * 0.3
+    res = rnd(B * P, C, dtype=dtype, seed=5)
+    stats = torch.zeros(B, G, 2, dtype=torch.float64, device=dev())
+    L.call("dv_gn_stats", L.GnStatsParams(x=ptr(x), stats=ptr(stats), B=B, P=P, C=C, groups=G, dtype=code(x)), stream())
+    out = torch.empty_like(x)
+    L.call("dv_gn_apply", L.GnApplyParams(
+        x=ptr(x), out=ptr(out), residual=ptr(res) if with_res else None, stats=ptr(stats), gamma=ptr(gamma),
+        beta=ptr(beta), scale=ss.data_ptr() + 16 if with_ss else None, shift=ss.data_ptr() + 16 + 4 * C if with_ss else None,
+        ss_ld=2 * C + 8, B=B, P=P, C=C, groups=G, eps=1e-5, dtype=code(x)), stream())
+    xn = cl_to_ncdhw(x, B, T, H, W)
+    y = F.group_norm(xn, G, gamma, beta, eps=1e-5)  # 5-D: statistics over (C/G, T, H, W) jointly (:109)
+    if with_ss:
+        sc, sh = ss[:, 4:4 + C], ss[:, 4 + C:4 + 2 * C]
+        y = y * (sc[:, :, None, None, None] + 1) + sh[:, :, None, None, None]
+    y = ncdhw_to_cl(F.silu(y))
+    if with_res:
+        y = y + res.float()
+    assert rel_err(out, y) < (1e-5 if dtype == torch.float32 else 6e-3)
+
+
+# ------------------------------------------------------------------ a15
+@pytest.mark.parametrize("dtype", DT)
+@pytest.mark.parametrize("C", [32, 96, 512])
+def test_layernorm_gain_only_and_affine(dtype, C):
+    rows = 77
+    x = rnd(rows, C, dtype=dtype, seed=1, scale=3.0)
+    g, b = rnd(C, seed=2) * 0.1 + 1, rnd(C, seed=3)
+    res = rnd(rows, C, dtype=dtype, seed=4)
+    for beta, residual in ((None, None), (b, res)):
+        out = torch.empty_like(x)
+        L.call("dv_layernorm", L.LayerNormParams(x=ptr(x), out=ptr(out), residual=ptr(residual), g=ptr(g),
+                                                 beta=ptr(beta), rows=rows, C=C, eps=1e-5, dtype=code(x)), stream())
+        xf = x.float()
+        var, mean = xf.var(-1, unbiased=False, keepdim=True), xf.mean(-1, keepdim=True)
+        ref = (xf - mean) * (var + 1e-5).rsqrt() * g
+        if beta is not None:
+            ref = ref + beta + residual.float()
+        assert rel_err(out, ref) < (1e-5 if dtype == torch.float32 else 6e-3)
+
+
+# ------------------------------------------------------------------ K5 core
+@pytest.mark.parametrize("dtype", DT)
+@pytest.mark.parametrize("n_ctx", [6, 262])
+def test_cross_attention_core(dtype, n_ctx):
+    B, P, H, D = 2, 200, 8, 64
+    q = rnd(B * P, H * D, dtype=dtype, seed=1)
+    n_layers, layer = 3, 1
+    kv = rnd(B, n_ctx, n_layers * 2 * H * D, seed=2)
+    null_kv = rnd(2, D, seed=3)
+    out = torch.empty_like(q)
+    L.call("dv_xattn_core", L.XattnParams(q=ptr(q), out=ptr(out), kv=ptr(kv), null_kv=ptr(null_kv), B=B, P=P, heads=H,
+                                          dh=D, n_ctx=n_ctx, kv_ld=kv.shape[-1], k_off=layer * 2 * H * D,
+                                          v_off=layer * 2 * H * D + H * D, scale=D ** -0.5, dtype=code(q)), stream())
+    k = kv[..., layer * 2 * H * D: layer * 2 * H * D + H * D].reshape(B, n_ctx, H, D).permute(0, 2, 1, 3)
+    v = kv[..., layer * 2 * H * D + H * D: (layer + 1) * 2 * H * D].reshape(B, n_ctx, H, D).permute(0, 2, 1, 3)
+    k = torch.cat((null_kv[0].expand(B, H, 1, D), k), dim=2)
+    v = torch.cat((null_kv[1].expand(B, H, 1, D), v), dim=2)
+    qh = q.float().reshape(B, P, H, D).permute(0, 2, 1, 3)
+    s = math.sqrt(D ** -0.5)
+    attn = ((qh * s) @ (k * s).transpose(-1, -2)).softmax(-1)
+    ref = (attn @ v).permute(0, 2, 1, 3).reshape(B * P, H * D)
+    assert rel_err(out, ref) < (2e-5 if dtype == torch.float32 else 6e-3)
+
+
+# ------------------------------------------------------------------ K6
+@pytest.mark.parametrize("dtype", DT)
+@pytest.mark.parametrize("S,n,H,D,bias", [(2, 300, 16, 32, False), (5, 16, 16, 32, True), (1, 65, 4, 64, False)])
+def test_mqa_flash_attention(dtype, S, n, H, D, bias):
+    q = rnd(S * n, H * D, dtype=dtype, seed=1)
+    kv = rnd(S * n, 2 * D, dtype=dtype, seed=2)
+    null_kv = rnd(2, D, seed=3)
+    b = rnd(H, n, n + 1, seed=4) if bias else None
+    out = torch.empty_like(q)
+    L.call("dv_attn_mqa", L.AttnMqaParams(q=ptr(q), kv=ptr(kv), out=ptr(out), null_kv=ptr(null_kv), bias=ptr(b), S=S,
+                                          n=n, heads=H, dh=D, scale=1.0 / D, dtype=code(q)), stream())
+    qh = q.float().reshape(S, n, H, D).permute(0, 2, 1, 3)
+    k, v = kv.float().reshape(S, n, 2 * D).chunk(2, dim=-1)
+    k = torch.cat((null_kv[0].expand(S, 1, D), k), dim=1)
+    v = torch.cat((null_kv[1].expand(S, 1, D), v), dim=1)
+    sim = torch.einsum("shid,sjd->shij", qh, k) / D
+    if bias:
+        sim = sim + b
+    ref = torch.einsum("shij,sjd->shid", sim.softmax(-1), v).permute(0, 2, 1, 3).reshape(S * n, H * D)
+    assert rel_err(out, ref) < (2e-5 if dtype == torch.float32 else 6e-3)
+
+
+# ------------------------------------------------------------------ K8 + head
+def test_time_embed_and_small_linear():
+    B, dim = 3, 32
+    t = torch.tensor([0, 513, 999], device=dev())
+    half = dim // 2
+    freqs = torch.exp(torch.arange(half, dtype=torch.float32) * -(math.log(10000) / (half - 1))).to(dev())
+    emb = torch.empty(B, dim, device=dev())
+    L.call("dv_time_embed", L.TimeEmbedParams(time=ptr(t), t_dev=None, freqs=ptr(freqs), out=ptr(emb), B=B, dim=dim),
+           stream())
+    a = t.float()[:, None] * freqs[None]
+    assert rel_err(emb, torch.cat((a.sin(), a.cos()), -1)) < 1e-6
+    t_dev = torch.tensor([77], dtype=torch.int32, device=dev())
+    L.call("dv_time_embed", L.TimeEmbedParams(time=None, t_dev=ptr(t_dev), freqs=ptr(freqs), out=ptr(emb), B=B, dim=dim),
+           stream())
+    a = torch.full((B, 1), 77.0, device=dev()) * freqs[None]
+    assert rel_err(emb, torch.cat((a.sin(), a.cos()), -1)) < 1e-6
+
+    M1, M2, N, K = 3, 2, 70, 48
+    x, w, bias = rnd(M1, M2, K, seed=1), rnd(N, K, seed=2), rnd(N, seed=3)
+    acc = rnd(M1 * M2, N, seed=4)
+    keep = torch.tensor([1, 0, 1], dtype=torch.uint8, device=dev())
+    alt = rnd(M2, N, seed=5)
+    y = torch.zeros(M1, M2, N + 10, device=dev())
+    L.call("dv_linear_small", L.LinearSmallParams(
+        x=ptr(x), w=ptr(w), bias=ptr(bias), y=ptr(y), accum=ptr(acc), keep=ptr(keep), alt=ptr(alt), M1=M1, M2=M2, N=N,
+        K=K, ldx1=M2 * K, ldx2=K, ldy1=M2 * (N + 10), ldy2=N + 10, pre_act=L.ACT_SILU, post_act=L.ACT_GELU), stream())
+    ref = F.gelu(F.linear(F.silu(x), w, bias))
+    ref = torch.where(keep.bool()[:, None, None], ref, alt[None]) + acc.reshape(M1, M2, N)
+    assert rel_err(y[..., :N], ref) < 1e-5 and float(y[..., N:].abs().max()) == 0.0
+
+
+def test_cond_tokens_select_mask_and_layernorm():
+    B, D, nt, nv, L_in, mt, td = 3, 32, 2, 4, 5, 9, 16
+    tt, vt = rnd(B, nt, D, seed=1), rnd(B, nv, D, seed=2)
+    nullv, nulltx = rnd(nv, D, seed=3), rnd(mt, D, seed=4)
+    txt_tok, txt_enc = rnd(B, L_in, D, seed=5), rnd(B, L_in, td, seed=6)
+    txt_enc[0, 3:] = 0.0   # masked rows
+    keep_v = torch.tensor([1, 0, 1], dtype=torch.uint8, device=dev())
+    keep_t = torch.tensor([1, 1, 0], dtype=torch.uint8, device=dev())
+    lw, lb, mw, mb = rnd(D, seed=7), rnd(D, seed=8), rnd(D, seed=9), rnd(D, seed=10)
+    c = torch.zeros(B, nt + nv, D, device=dev())
+    mid = torch.zeros(B, nt + nv + mt, D, device=dev())
+    L.call("dv_cond_tokens", L.CondTokensParams(
+        time_tokens=ptr(tt), video_tokens=ptr(vt), null_video=ptr(nullv), text_tokens=ptr(txt_tok), text_enc=ptr(txt_enc),
+        null_text=ptr(nulltx), ln_w=ptr(lw), ln_b=ptr(lb), ln_mid_w=ptr(mw), ln_mid_b=ptr(mb), keep_video=ptr(keep_v),
+        keep_text=ptr(keep_t), c=ptr(c), mid_c=ptr(mid), B=B, D=D, n_time=nt, n_video=nv, n_text_in=L_in, max_text=mt,
+        text_dim=td, tok_begin=0, tok_end=nt + nv + mt, eps=1e-5), stream())
+    v = torch.where(keep_v.bool()[:, None, None], vt, nullv[None])
+    mask = (txt_enc != 0).any(-1)
+    tpad = F.pad(txt_tok, (0, 0, 0, mt - L_in))
+    mpad = F.pad(mask, (0, mt - L_in), value=False)
+    tx = torch.where((mpad & keep_t.bool()[:, None])[:, :, None], tpad, nulltx[None])
+    craw = torch.cat((tt, v), 1)
+    assert rel_err(c, F.layer_norm(craw, (D,), lw, lb)) < 1e-5
+    assert rel_err(mid, F.layer_norm(torch.cat((craw, tx), 1), (D,), mw, mb)) < 1e-5
+
+
+@pytest.mark.parametrize("dtype", DT)
+def test_to_out_head(dtype):
+    B, P, C = 2, 300, 32
+    x = rnd(B * P, C, dtype=dtype, seed=1)
+    w, b = rnd(3, C, seed=2), rnd(3, seed=3)
+    out = torch.empty(B, 3, P, device=dev())
+    L.call("dv_to_out", L.ToOutParams(x=ptr(x), w=ptr(w), bias=ptr(b), out=ptr(out), B=B, P=P, C=C, Cout=3,
+                                      dtype=code(x)), stream())
+    ref = (x.float().reshape(B, P, C) @ w.t() + b).permute(0, 2, 1)
+    assert rel_err(out, ref) < 1e-5

@@ -1,0 +1,85 @@
+"""-m gpu: the whole denoiser through the C ABI against (a) the committed reference fixtures and (b) the CPU
+oracle on fresh seeded inputs.  Bar (north_star): fp32 within 1e-4 relative error per step; bf16 compute is
+bounded at 3e-2 relative on eps (per step) — the final-sample PSNR bound lives in test_gpu_sampler.py."""
+import pytest
+import torch
+
+from conftest import golden
+from dalle2_video_b200 import Unet3D
+from gpu_util import rel_err
+from oracle.unet3d import UnetConfig, unet3d_forward
+from oracle.weights import synth_state_dict
+
+pytestmark = pytest.mark.gpu
+FP32_TOL, BF16_TOL = 1e-4, 3e-2
+
+
+def make_unet(kw, layout, seed=7):
+    u = Unet3D(**kw)
+    u.load_state_dict(synth_state_dict(layout, seed=seed), strict=True)
+    return u.cuda()
+
+
+@pytest.mark.parametrize("name", ["tiny", "tiny_text", "headline_small"])
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, FP32_TOL), (torch.bfloat16, BF16_TOL)])
+def test_forward_matches_reference_fixture(name, dtype, tol, layouts):
+    g = golden(f"unet3d_{name}.pt")
+    u = make_unet(g["unet_kwargs"], layouts[name], g["weight_seed"])
+    u.compute_dtype = dtype
+    txt = g["text_encodings"].cuda() if g["text_encodings"] is not None else None
+    out = u.forward_with_cond_scale(g["x"].cuda(), g["times"].cuda(), video_embed=g["video_embed"].cuda(),
+                                    text_encodings=txt, cond_scale=g["cond_scale"])
+    assert out.shape == g["eps"].shape and out.dtype == torch.float32
+    err = rel_err(out, g["eps"])
+    assert err < tol, err
+
+
+def test_forward_vs_oracle_with_drop_masks_and_per_sample_times(layouts):
+    kw = dict(dim=32, video_embed_dim=512, dim_mults=(1, 2), cond_on_video_embeds=True,
+              cond_on_text_encodings=True, text_embed_dim=64)
+    sd = synth_state_dict(layouts["tiny_text"], seed=3)
+    u = Unet3D(**kw)
+    u.load_state_dict(sd, strict=True)
+    u = u.cuda()
+    g = torch.Generator().manual_seed(2)
+    x = torch.randn(3, 3, 4, 16, 16, generator=g)
+    emb, txt = torch.randn(3, 512, generator=g), torch.randn(3, 7, 64, generator=g)
+    t = torch.tensor([0, 500, 999])
+    for dv, dt in ((False, False), (True, True)):
+        with torch.no_grad():
+            ref = unet3d_forward(sd, UnetConfig(**kw), x, t, video_embed=emb, text_encodings=txt, drop_video=dv,
+                                 drop_text=dt)
+        out = u(x.cuda(), t.cuda(), video_embed=emb.cuda(), text_encodings=txt.cuda(),
+                video_cond_drop_prob=float(dv), text_cond_drop_prob=float(dt))
+        assert rel_err(out, ref) < FP32_TOL
+
+
+def test_batch_rows_are_independent(layouts):
+    # the property multi-GPU sharding rests on: a row's result does not depend on its batch mates
+    kw = dict(dim=32, video_embed_dim=512, dim_mults=(1, 2), cond_on_video_embeds=True)
+    u = make_unet(kw, layouts["tiny"])
+    g = torch.Generator().manual_seed(4)
+    x = torch.randn(4, 3, 8, 32, 32, generator=g).cuda()
+    emb = torch.randn(4, 512, generator=g).cuda()
+    t = torch.tensor([5, 5, 900, 900]).cuda()
+    full = u(x, t, video_embed=emb)
+    halves = torch.cat([u(x[i:i + 2], t[i:i + 2], video_embed=emb[i:i + 2]) for i in (0, 2)])
+    assert rel_err(halves, full) < 1e-5
+
+
+def test_weights_are_repacked_after_load_state_dict(layouts):
+    kw = dict(dim=32, video_embed_dim=512, dim_mults=(1, 2), cond_on_video_embeds=True)
+    u = make_unet(kw, layouts["tiny"], seed=7)
+    x = torch.randn(1, 3, 8, 32, 32).cuda()
+    emb, t = torch.randn(1, 512).cuda(), torch.tensor([3]).cuda()
+    a = u(x, t, video_embed=emb)
+    u.load_state_dict({k: v.cuda() for k, v in synth_state_dict(layouts["tiny"], seed=8).items()})
+    b = u(x, t, video_embed=emb)
+    assert rel_err(a, b) > 1e-2
+
+
+def test_zero_init_to_out_gives_exact_zero():
+    torch.manual_seed(0)
+    u = Unet3D(dim=32, video_embed_dim=512, dim_mults=(1, 2), cond_on_video_embeds=True).cuda()
+    y = u(torch.randn(1, 3, 8, 32, 32).cuda(), torch.tensor([5]).cuda(), video_embed=torch.randn(1, 512).cuda())
+    assert float(y.abs().max()) == 0.0  # SURVEY.md F6 anchor
