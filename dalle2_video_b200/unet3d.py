@@ -330,6 +330,7 @@ class Unet3D(nn.Module):
         eng.set_conditioning(video_embed, text_encodings if use_text else None, keep_v, keep_t)
         eng.x_in.copy_(x)
         eng.time_in.copy_(time)
+        eng.set_time_source(False)
         eng.run()
         return eng.eps.clone().view(b, self.channels_out, *x.shape[2:]).to(x.dtype)
 
