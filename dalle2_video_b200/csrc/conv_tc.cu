@@ -1,6 +1,608 @@
-// placeholder until the tcgen05 kernel lands
+// K1/K3 — implicit-GEMM convolution on the 5th-generation tensor cores (tcgen05 + TMEM + TMA), bf16 in,
+// fp32 accumulate.  Replaces the nn.Conv3d (1,k,k) / nn.Linear call sites listed in include/dv_b200.h.
+//
+// Formulation: D[128 positions x BN channels] += A[128 x 64] . B[BN x 64]^T per (tap, 64-channel chunk).
+//   A tile : TMA tiled load of a (64ch, bw, bh, bn) box of the channels-last activation tensor, shifted by the
+//            tap offset (dy,dx); out-of-image coordinates are zero-filled by the TMA unit, so padding costs
+//            nothing and the tile lands in shared memory already in the K-major SWIZZLE_128B layout the MMA reads.
+//            A second tensor map walks the second source (skip connection) — torch.cat is never materialised.
+//            The pixel-unshuffle of Downsample3D is a 5-D view (2C, W/2, 2, H/2, N) of the same tensor.
+//   B tile : TMA load of BN rows x 64 K-columns of the packed weight [Cout][taps*(C0+C1)].
+//   MMA    : one elected thread issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N=BN, K=16) x4 per stage;
+//            accumulators live in TMEM, double-buffered (2 x BN columns) so the epilogue of tile i overlaps the
+//            main loop of tile i+1.
+//   Epilogue (4 warps): tcgen05.ld 32 lanes x 32 columns -> +bias -> [GroupNorm partial sums] -> [+residual] ->
+//            bf16 -> 64-byte row stores (or SiLU + pixel-shuffle scatter).
+// Persistent CTAs (one per SM) walk contiguous tile ranges so that GroupNorm partials are flushed with few atomics.
+#include <cuda.h>
+
+#include <mutex>
+#include <unordered_map>
+
 #include "common.cuh"
+
 namespace dv {
-int conv_tc_supported(const dv_conv_params& p) { (void)p; return 0; }
-int conv_tc_launch(const dv_conv_params& p, cudaStream_t s) { (void)p; (void)s; set_error("tcgen05 path not built"); return DV_EUNSUPPORTED; }
+
+constexpr int TC_BM = 128;      // positions per tile (TMEM lanes)
+constexpr int TC_BK = 64;       // channels per pipeline stage (one 128-byte swizzle row)
+constexpr int TC_THREADS = 192; // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-5: epilogue
+constexpr int TC_SMEM_BUDGET = 200 * 1024;
+
+struct TcParams {
+  // problem
+  int ntaps, kw, pad, mode;
+  int H, W;              // input spatial size
+  int Ho, Wo;            // output spatial size
+  int c0_chunks, c1_chunks;
+  int Cout, BN, n_tiles_n;
+  int64_t m_tiles, total_tiles;
+  int64_t rows_per_sample;
+  int stages;
+  // epilogue
+  const float* bias;
+  const __nv_bfloat16* add;
+  __nv_bfloat16* out;
+  double* stats;
+  int groups, epilogue, out_ld, out_coff;
+};
+
+// ------------------------------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra WAIT_DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t"
+      "}" ::"r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ void tma_load_5d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2,
+                                            int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+// K-major, SWIZZLE_128B shared-memory matrix descriptor: rows of 128 bytes, 8-row groups 1024 bytes apart.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);        // start address  [0,14)
+  d |= (uint64_t)1 << 16;                         // leading byte offset (unused for swizzled K-major) [16,30)
+  d |= (uint64_t)(1024 >> 4) << 32;               // stride byte offset = 1024 B [32,46)
+  d |= (uint64_t)1 << 46;                         // descriptor version (Blackwell) [46,48)
+  d |= (uint64_t)2 << 61;                         // layout type SWIZZLE_128B [61,64)
+  return d;
+}
+// kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N=bn.
+__device__ __forceinline__ uint32_t make_idesc(int bn) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// ------------------------------------------------------------------------------------------ the kernel
+__global__ void __launch_bounds__(TC_THREADS, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
+               const __grid_constant__ CUtensorMap map_b, const TcParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // carve: [stages x (A 16 KB | B BN*128 B)] then barriers
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const uint32_t a_bytes = TC_BM * TC_BK * 2, b_bytes = (uint32_t)p.BN * TC_BK * 2;
+  const uint32_t stage_bytes = a_bytes + b_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
+  uint64_t* full_bar = bars;                 // [stages]
+  uint64_t* empty_bar = bars + p.stages;     // [stages]
+  uint64_t* tmem_full = bars + 2 * p.stages; // [2]
+  uint64_t* tmem_empty = tmem_full + 2;      // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  float* sred = reinterpret_cast<float*>(tmem_slot + 2);  // [64] GroupNorm partials: [group-in-tile][2]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t tmem_cols = (uint32_t)(2 * p.BN);  // 128 / 256 / 512: a power of two >= 32
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_a0);
+    tma_prefetch_desc(&map_a1);
+    tma_prefetch_desc(&map_b);
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full[a], 1);
+      mbar_init(&tmem_empty[a], 4);  // one arrival per epilogue warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (threadIdx.x < 64) sred[threadIdx.x] = 0.f;
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // contiguous tile range of this CTA; tile = m_tile * n_tiles_n + n_tile
+  const int64_t per_cta = (p.total_tiles + gridDim.x - 1) / gridDim.x;
+  const int64_t tile_begin = (int64_t)blockIdx.x * per_cta;
+  const int64_t tile_end = tile_begin + per_cta < p.total_tiles ? tile_begin + per_cta : p.total_tiles;
+  const int k_iters = p.ntaps * (p.c0_chunks + p.c1_chunks);
+
+  if (warp == 0) {
+    // ================================================================ TMA producer
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int64_t tile = tile_begin; tile < tile_end; ++tile) {
+        const int64_t m_tile = tile / p.n_tiles_n;
+        const int n_tile = (int)(tile % p.n_tiles_n);
+        const int64_t row0 = m_tile * TC_BM;
+        const int img0 = (int)(row0 / ((int64_t)p.Ho * p.Wo));
+        const int rem = (int)(row0 % ((int64_t)p.Ho * p.Wo));
+        const int y0 = rem / p.Wo, x0 = rem % p.Wo;
+        for (int tap = 0; tap < p.ntaps; ++tap) {
+          for (int src = 0; src < 2; ++src) {
+            const int chunks = src ? p.c1_chunks : p.c0_chunks;
+            const CUtensorMap* map = src ? &map_a1 : &map_a0;
+            for (int c = 0; c < chunks; ++c) {
+              mbar_wait(&empty_bar[stage], phase ^ 1);
+              uint8_t* sa = smem + (size_t)stage * stage_bytes;
+              mbar_expect_tx(&full_bar[stage], stage_bytes);
+              const int kcol = (tap * (p.c0_chunks + p.c1_chunks) + (src ? p.c0_chunks : 0) + c) * TC_BK;
+              if (p.mode == DV_CONV_UNSHUFFLE) {
+                // view (2C, W/2, 2, H/2, N): tap = s1, the 2C run covers (s2, c); chunk index walks it
+                tma_load_5d(map, &full_bar[stage], sa, c * TC_BK, x0, tap, y0, img0);
+              } else {
+                const int dy = tap / p.kw - p.pad, dx = tap % p.kw - p.pad;
+                tma_load_5d(map, &full_bar[stage], sa, c * TC_BK, x0 + dx, y0 + dy, img0, 0);
+              }
+              tma_load_2d(&map_b, &full_bar[stage], sa + a_bytes, kcol, n_tile * p.BN);
+              if (++stage == p.stages) { stage = 0; phase ^= 1; }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================================================ MMA issuer
+    const uint32_t idesc = make_idesc(p.BN);
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int64_t tile = tile_begin; tile < tile_end; ++tile) {
+      mbar_wait(&tmem_empty[acc], acc_phase ^ 1);  // epilogue has drained this accumulator
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.BN);
+      for (int k = 0; k < k_iters; ++k) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
+          const uint64_t adesc = make_smem_desc(sa);
+          const uint64_t bdesc = make_smem_desc(sa + a_bytes);
+#pragma unroll
+          for (int kk = 0; kk < TC_BK / 16; ++kk) {
+            // advance 16 bf16 = 32 bytes along K inside the 128-byte swizzle row: +2 in the (addr >> 4) field
+            umma_f16(d_tmem, adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), idesc, (k | kk) != 0);
+          }
+          umma_commit(&empty_bar[stage]);                      // frees the smem stage when these MMAs retire
+          if (k == k_iters - 1) umma_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
+        }
+        __syncwarp();
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  } else {
+    // ================================================================ epilogue warps (2..5)
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int row_in_tile = q * 32 + lane;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    int cur_sample = -1;
+    const int cpg = p.stats ? p.Cout / p.groups : 1;
+    auto flush_stats = [&](int sample, int n_tile) {
+      // all 4 epilogue warps: make partials visible, then 2*groups_in_tile threads push them to global
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      const int t = (warp - 2) * 32 + lane;
+      const int groups_in_tile = p.BN / cpg;
+      if (t < 2 * groups_in_tile) {
+        const int g = n_tile * groups_in_tile + (t >> 1);
+        atomicAdd(&p.stats[((int64_t)sample * p.groups + g) * 2 + (t & 1)], (double)sred[t]);
+        sred[t] = 0.f;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+    };
+    int last_n_tile = 0;
+    for (int64_t tile = tile_begin; tile < tile_end; ++tile) {
+      const int64_t m_tile = tile / p.n_tiles_n;
+      const int n_tile = (int)(tile % p.n_tiles_n);
+      const int64_t row = m_tile * TC_BM + row_in_tile;
+      const int sample = (int)((m_tile * TC_BM) / p.rows_per_sample);
+      if (p.stats && cur_sample >= 0 && (sample != cur_sample || n_tile != last_n_tile)) flush_stats(cur_sample, last_n_tile);
+      cur_sample = sample;
+      last_n_tile = n_tile;
+
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.BN);
+
+      // output addressing
+      __nv_bfloat16* orow;
+      int shuffle_cq = 0;
+      int64_t sh_base = 0;
+      if (p.epilogue == DV_EPI_SHUFFLE_SILU) {
+        shuffle_cq = p.Cout / 4;
+        const int img = (int)(row / ((int64_t)p.Ho * p.Wo));
+        const int rem = (int)(row % ((int64_t)p.Ho * p.Wo));
+        sh_base = ((int64_t)img * (2 * p.Ho) + 2 * (rem / p.Wo)) * (2 * p.Wo) + 2 * (rem % p.Wo);
+        orow = p.out;
+      } else {
+        orow = p.out + row * p.out_ld + p.out_coff + n_tile * p.BN;
+      }
+      const __nv_bfloat16* arow = p.add ? p.add + row * p.Cout + n_tile * p.BN : nullptr;
+
+      for (int c0 = 0; c0 < p.BN; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld32(t_base + (uint32_t)c0, r);
+        float v[32];
+        const int ncol = n_tile * p.BN + c0;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + (p.bias ? __ldg(p.bias + ncol + j) : 0.f);
+        if (p.stats) {
+          // partial sums of the bf16-rounded values the next kernel will read, per 8-column segment
+          float ps1[4], ps2[4];
+#pragma unroll
+          for (int s0 = 0; s0 < 4; ++s0) {
+            ps1[s0] = 0.f;
+            ps2[s0] = 0.f;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float rr = __bfloat162float(__float2bfloat16_rn(v[s0 * 8 + j]));
+              ps1[s0] += rr;
+              ps2[s0] += rr * rr;
+            }
+          }
+          if (cpg == 8) {
+#pragma unroll
+            for (int s0 = 0; s0 < 4; ++s0) {
+              const float a = warp_sum(ps1[s0]), b = warp_sum(ps2[s0]);
+              if (lane == 0) { atomicAdd(&sred[(c0 / 8 + s0) * 2], a); atomicAdd(&sred[(c0 / 8 + s0) * 2 + 1], b); }
+            }
+          } else if (cpg == 16) {
+#pragma unroll
+            for (int s0 = 0; s0 < 2; ++s0) {
+              const float a = warp_sum(ps1[2 * s0] + ps1[2 * s0 + 1]), b = warp_sum(ps2[2 * s0] + ps2[2 * s0 + 1]);
+              if (lane == 0) { atomicAdd(&sred[(c0 / 16 + s0) * 2], a); atomicAdd(&sred[(c0 / 16 + s0) * 2 + 1], b); }
+            }
+          } else {  // cpg is a multiple of 32: the whole chunk belongs to one group
+            const float a = warp_sum(ps1[0] + ps1[1] + ps1[2] + ps1[3]), b = warp_sum(ps2[0] + ps2[1] + ps2[2] + ps2[3]);
+            if (lane == 0) { atomicAdd(&sred[(c0 / cpg) * 2], a); atomicAdd(&sred[(c0 / cpg) * 2 + 1], b); }
+          }
+        }
+        if (arow) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            float a[8];
+            load8(arow + c0 + j, a);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[j + e] += a[e];
+          }
+        }
+        if (p.epilogue == DV_EPI_SHUFFLE_SILU) {
+          const int qq = ncol / shuffle_cq, cc = ncol % shuffle_cq;
+          __nv_bfloat16* dst = p.out + (sh_base + (int64_t)(qq / 2) * (2 * p.Wo) + (qq % 2)) * p.out_ld + p.out_coff + cc;
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            float o[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) o[e] = silu_f(v[j + e]);
+            store8(dst + j, o);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            float o[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) o[e] = v[j + e];
+            store8(orow + c0 + j, o);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+    if (p.stats && cur_sample >= 0) flush_stats(cur_sample, last_n_tile);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(sym);
+    else
+      (void)cudaGetLastError();
+  });
+  return fn;
+}
+
+struct TileGeom {
+  int bw, bh, bn;
+};
+
+// Tile of 128 consecutive output rows as a (bw, bh, bn) box; false if such a box does not exist.
+static bool tile_geometry(int Ho, int Wo, int n_img, int frames, TileGeom* g) {
+  if (Wo >= TC_BM) {
+    if (Wo % TC_BM) return false;
+    *g = {TC_BM, 1, 1};
+    return true;
+  }
+  if (TC_BM % Wo) return false;
+  const int rows = TC_BM / Wo;
+  if (rows <= Ho) {
+    if (Ho % rows) return false;
+    *g = {Wo, rows, 1};
+    return true;
+  }
+  if (rows % Ho) return false;
+  const int imgs = rows / Ho;
+  if (frames % imgs || n_img % imgs) return false;
+  *g = {Wo, Ho, imgs};
+  return true;
+}
+
+static int pick_bn(int Cout) {
+  if (Cout % 256 == 0) return 256;
+  if (Cout % 128 == 0) return 128;
+  if (Cout % 64 == 0) return 64;
+  return 0;
+}
+
+int conv_tc_supported(const dv_conv_params& p) {
+  if (p.dtype != DV_BF16) return 0;
+  if (p.mode != DV_CONV_NORMAL && p.mode != DV_CONV_UNSHUFFLE) return 0;
+  if (p.C0 % TC_BK || p.C1 % TC_BK) return 0;
+  const int bn = pick_bn(p.Cout);
+  if (!bn) return 0;
+  int Ho = p.H, Wo = p.W;
+  if (p.mode == DV_CONV_UNSHUFFLE) {
+    if (p.H % 2 || p.W % 2 || p.C1) return 0;
+    Ho /= 2;
+    Wo /= 2;
+  } else if (p.kh != p.kw || p.kh != 2 * p.pad + 1) {
+    return 0;
+  }
+  TileGeom g;
+  if (!tile_geometry(Ho, Wo, p.n_img, p.frames, &g)) return 0;
+  const int64_t rows = (int64_t)p.n_img * Ho * Wo;
+  const int64_t rps = (int64_t)p.frames * Ho * Wo;
+  if (rows % TC_BM || rps % TC_BM) return 0;
+  if (p.epilogue == DV_EPI_SHUFFLE_SILU) {
+    if ((p.Cout / 4) % 32) return 0;
+  }
+  if (p.stats) {
+    const int cpg = p.Cout / p.groups;
+    if (p.Cout % p.groups || !(cpg == 8 || cpg == 16 || cpg % 32 == 0) || (bn % cpg) || bn / cpg > 32) return 0;
+  }
+  const int out_ld = p.out_ld ? p.out_ld : (p.epilogue == DV_EPI_SHUFFLE_SILU ? p.Cout / 4 : p.Cout);
+  if (out_ld % 8 || p.out_coff % 8) return 0;
+  return 1;
+}
+
+struct MapKey {
+  const void* ptr;
+  uint64_t d[5], s[4];
+  uint32_t b[5];
+  int rank;
+  bool operator==(const MapKey& o) const { return memcmp(this, &o, sizeof(MapKey)) == 0; }
+};
+struct MapKeyHash {
+  size_t operator()(const MapKey& k) const {
+    const uint64_t* w = reinterpret_cast<const uint64_t*>(&k);
+    size_t h = 1469598103934665603ull;
+    for (size_t i = 0; i < sizeof(MapKey) / 8; ++i) h = (h ^ w[i]) * 1099511628211ull;
+    return h;
+  }
+};
+
+static int encode_map(CUtensorMap* out, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides,
+                      const uint32_t* box) {
+  static std::mutex mu;
+  static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
+  MapKey key;
+  memset(&key, 0, sizeof(key));
+  key.ptr = ptr;
+  key.rank = rank;
+  for (int i = 0; i < rank; ++i) { key.d[i] = dims[i]; key.b[i] = box[i]; }
+  for (int i = 0; i < rank - 1; ++i) key.s[i] = strides[i];
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) { *out = it->second; return DV_OK; }
+  }
+  EncodeTiledFn fn = get_encode_fn();
+  DV_REQUIRE(fn != nullptr, DV_ECUDA, "dv_conv_igemm(tcgen05): cuTensorMapEncodeTiled is not available from the driver");
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(ptr), dims, strides, box,
+                  estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  DV_REQUIRE(r == CUDA_SUCCESS, DV_ECUDA, "dv_conv_igemm(tcgen05): cuTensorMapEncodeTiled failed (CUresult %d)", (int)r);
+  std::lock_guard<std::mutex> lk(mu);
+  if (cache.size() > 8192) cache.clear();
+  cache.emplace(key, *out);
+  return DV_OK;
+}
+
+static int make_act_map(CUtensorMap* out, const void* ptr, int C, const dv_conv_params& p, const TileGeom& g) {
+  uint64_t dims[5], strides[4];
+  uint32_t box[5];
+  const uint64_t e = 2;
+  if (p.mode == DV_CONV_UNSHUFFLE) {
+    dims[0] = 2ull * C; dims[1] = p.W / 2; dims[2] = 2; dims[3] = p.H / 2; dims[4] = p.n_img;
+    strides[0] = 2ull * C * e; strides[1] = (uint64_t)p.W * C * e; strides[2] = 2ull * p.W * C * e;
+    strides[3] = (uint64_t)p.H * p.W * C * e;
+    box[0] = TC_BK; box[1] = g.bw; box[2] = 1; box[3] = g.bh; box[4] = g.bn;
+  } else {
+    dims[0] = C; dims[1] = p.W; dims[2] = p.H; dims[3] = p.n_img; dims[4] = 1;
+    strides[0] = (uint64_t)C * e; strides[1] = (uint64_t)p.W * C * e; strides[2] = (uint64_t)p.H * p.W * C * e;
+    strides[3] = (uint64_t)p.n_img * p.H * p.W * C * e;
+    box[0] = TC_BK; box[1] = g.bw; box[2] = g.bh; box[3] = g.bn; box[4] = 1;
+  }
+  return encode_map(out, ptr, 5, dims, strides, box);
+}
+
+int conv_tc_launch(const dv_conv_params& p, cudaStream_t s) {
+  int Ho = p.H, Wo = p.W;
+  if (p.mode == DV_CONV_UNSHUFFLE) { Ho /= 2; Wo /= 2; }
+  TileGeom g;
+  DV_REQUIRE(tile_geometry(Ho, Wo, p.n_img, p.frames, &g), DV_EUNSUPPORTED, "dv_conv_igemm(tcgen05): no 128-row tile box");
+  TcParams t;
+  memset(&t, 0, sizeof(t));
+  t.ntaps = (p.mode == DV_CONV_UNSHUFFLE) ? 2 : p.kh * p.kw;
+  t.kw = p.kw; t.pad = p.pad; t.mode = p.mode;
+  t.H = p.H; t.W = p.W; t.Ho = Ho; t.Wo = Wo;
+  if (p.mode == DV_CONV_UNSHUFFLE) {
+    t.c0_chunks = 2 * p.C0 / TC_BK;  // one "tap" per s1, each a run of 2*C0 channels (s2, c)
+    t.c1_chunks = 0;
+  } else {
+    t.c0_chunks = p.C0 / TC_BK;
+    t.c1_chunks = p.C1 / TC_BK;
+  }
+  t.Cout = p.Cout;
+  t.BN = pick_bn(p.Cout);
+  t.n_tiles_n = p.Cout / t.BN;
+  t.m_tiles = (int64_t)p.n_img * Ho * Wo / TC_BM;
+  t.total_tiles = t.m_tiles * t.n_tiles_n;
+  t.rows_per_sample = (int64_t)p.frames * Ho * Wo;
+  const int stage_bytes = TC_BM * TC_BK * 2 + t.BN * TC_BK * 2;
+  t.stages = TC_SMEM_BUDGET / stage_bytes;
+  if (t.stages > 8) t.stages = 8;
+  t.bias = p.bias;
+  t.add = reinterpret_cast<const __nv_bfloat16*>(p.add);
+  t.out = reinterpret_cast<__nv_bfloat16*>(p.out);
+  t.stats = p.stats;
+  t.groups = p.groups;
+  t.epilogue = p.epilogue;
+  t.out_ld = p.out_ld;
+  t.out_coff = p.out_coff;
+
+  CUtensorMap ma0, ma1, mb;
+  int rc = make_act_map(&ma0, p.src0, p.C0, p, g);
+  if (rc != DV_OK) return rc;
+  if (p.C1) {
+    rc = make_act_map(&ma1, p.src1, p.C1, p, g);
+    if (rc != DV_OK) return rc;
+  } else {
+    ma1 = ma0;
+  }
+  {
+    const uint64_t ktot = (uint64_t)((p.mode == DV_CONV_UNSHUFFLE ? 4 : p.kh * p.kw)) * (p.C0 + p.C1);
+    uint64_t dims[2] = {ktot, (uint64_t)p.Cout};
+    uint64_t strides[1] = {ktot * 2};
+    uint32_t box[2] = {TC_BK, (uint32_t)t.BN};
+    rc = encode_map(&mb, p.weight, 2, dims, strides, box);
+    if (rc != DV_OK) return rc;
+  }
+  static int sm_count = 0;
+  if (!sm_count) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
+    if (sm_count <= 0) sm_count = 148;
+  }
+  const size_t smem = (size_t)t.stages * stage_bytes + 1024 /*alignment slack*/ + 1024 /*barriers, tmem slot, partials*/;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    DV_REQUIRE(e == cudaSuccess, DV_ECUDA, "dv_conv_igemm(tcgen05): cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  const int grid = (int)(t.total_tiles < sm_count ? t.total_tiles : sm_count);
+  conv_tc_kernel<<<grid, TC_THREADS, smem, s>>>(ma0, ma1, mb, t);
+  DV_CHECK_LAUNCH("dv_conv_igemm(tcgen05)");
+  return DV_OK;
+}
+
+}  // namespace dv

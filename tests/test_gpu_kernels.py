@@ -345,3 +345,76 @@ def test_to_out_head(dtype):
                                       dtype=code(x)), stream())
     ref = (x.float().reshape(B, P, C) @ w.t() + b).permute(0, 2, 1)
     assert rel_err(out, ref) < 1e-5
+
+
+# ------------------------------------------------------------------ K1/K3 on tcgen05 (impl=2 forces the tensor-core path)
+TC_CASES = [
+    dict(B=1, T=1, H=1, W=1, rows=256, C=(64,), Co=64, k=1),                      # plain GEMM, one K chunk
+    dict(B=1, T=1, H=1, W=1, rows=512, C=(128,), Co=256, k=1),                    # GEMM, N=256
+    dict(B=1, T=2, H=64, W=64, C=(64,), Co=64, k=3, stats=True),                  # 64x64 block conv + GN partials
+    dict(B=2, T=2, H=32, W=32, C=(128, 64), Co=128, k=3, stats=True, add=True),   # two-source + residual
+    dict(B=1, T=4, H=8, W=8, C=(256,), Co=512, k=3, stats=True),                  # 8x8: tile spans 2 frames, 2 N tiles
+    dict(B=1, T=2, H=16, W=16, C=(128,), Co=128, k=3),
+    dict(B=1, T=8, H=4, W=4, C=(64,), Co=64, k=3),                                # 4x4: tile spans 8 frames
+    dict(B=1, T=2, H=16, W=16, C=(192, 64), Co=64, k=1),                          # res_conv over a concat
+]
+
+
+@pytest.mark.parametrize("case", TC_CASES)
+def test_conv_tcgen05_matches_conv3d(case):
+    dtype = torch.bfloat16
+    B, T, H, W, Co, k = (case[x] for x in ("B", "T", "H", "W", "Co", "k"))
+    rows = case.get("rows", B * T * H * W)
+    n_img = rows if "rows" in case else B * T
+    frames = rows if "rows" in case else T
+    xs = [rnd(rows, c, dtype=dtype, seed=10 + i) for i, c in enumerate(case["C"])]
+    cin = sum(case["C"])
+    wp = rnd(Co, k * k * cin, seed=20, scale=1 / math.sqrt(cin * k * k)).to(dtype)
+    bias = rnd(Co, seed=21)
+    G = 8
+    stats = torch.zeros(B, G, 2, dtype=torch.float64, device=dev()) if case.get("stats") else None
+    add = rnd(rows, Co, dtype=dtype, seed=22) if case.get("add") else None
+    out = torch.empty(rows, Co, dtype=dtype, device=dev())
+    conv(xs, wp, bias, out, n_img=n_img, frames=frames, H=H, W=W, k=k, stats=stats, groups=G, add=add, impl=2)
+    if "rows" in case:
+        ref = torch.cat([x.float() for x in xs], 1) @ wp.float().t() + bias
+    else:
+        xin = torch.cat([cl_to_ncdhw(x, B, T, H, W) for x in xs], dim=1)
+        w_ref = wp.float().reshape(Co, k, k, cin).permute(0, 3, 1, 2)[:, :, None]
+        ref = ncdhw_to_cl(F.conv3d(xin, w_ref, bias, padding=(0, k // 2, k // 2)))
+    if add is not None:
+        assert rel_err(out, ref + add.float()) < 1e-2
+    else:
+        assert rel_err(out, ref) < 1e-2
+    if stats is not None:
+        yq = ref.to(dtype).float().reshape(B, -1, G, Co // G)
+        s1, s2 = yq.sum(dim=(1, 3)).double(), (yq * yq).sum(dim=(1, 3)).double()
+        assert rel_err(stats[..., 1], s2) < 2e-3
+        assert float((stats[..., 0] - s1).abs().max()) < 2e-2 * float(s2.max().sqrt())
+    # and against the SIMT implementation of the same ABI call
+    out2 = torch.empty_like(out)
+    conv(xs, wp, bias, out2, n_img=n_img, frames=frames, H=H, W=W, k=k, add=add, impl=1)
+    assert rel_err(out, out2) < 6e-3
+
+
+def test_conv_tcgen05_unshuffle_and_shuffle():
+    dtype = torch.bfloat16
+    B, T, H, W, C, Co = 1, 2, 32, 32, 64, 128
+    x = rnd(B * T * H * W, C, dtype=dtype, seed=1)
+    wp = rnd(Co, 4 * C, seed=2, scale=1 / math.sqrt(4 * C)).to(dtype)
+    bias = rnd(Co, seed=3)
+    a = torch.empty(B * T * (H // 2) * (W // 2), Co, dtype=dtype, device=dev())
+    b = torch.empty_like(a)
+    conv([x], wp, bias, a, n_img=B * T, frames=T, H=H, W=W, mode=L.CONV_UNSHUFFLE, impl=2)
+    conv([x], wp, bias, b, n_img=B * T, frames=T, H=H, W=W, mode=L.CONV_UNSHUFFLE, impl=1)
+    assert rel_err(a, b) < 6e-3
+    H = W = 16
+    C, Cq = 256, 128
+    x = rnd(B * T * H * W, C, dtype=dtype, seed=4)
+    wp = rnd(4 * Cq, C, seed=5, scale=1 / math.sqrt(C)).to(dtype)
+    bias = rnd(4 * Cq, seed=6)
+    a = torch.empty(B * T * 2 * H * 2 * W, Cq, dtype=dtype, device=dev())
+    b = torch.empty_like(a)
+    conv([x], wp, bias, a, n_img=B * T, frames=T, H=H, W=W, epilogue=L.EPI_SHUFFLE_SILU, impl=2)
+    conv([x], wp, bias, b, n_img=B * T, frames=T, H=H, W=W, epilogue=L.EPI_SHUFFLE_SILU, impl=1)
+    assert rel_err(a, b) < 6e-3
