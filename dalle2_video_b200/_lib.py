@@ -76,6 +76,11 @@ class CondTokensParams(C.Structure):
                 ("eps", f32)]
 
 
+class Im2colParams(C.Structure):
+    _fields_ = [("x", vp), ("out", vp), ("B", i32), ("C", i32), ("T", i32), ("H", i32), ("W", i32), ("k", i32),
+                ("Kpad", i32), ("dtype", i32)]
+
+
 class ToOutParams(C.Structure):
     _fields_ = [("x", vp), ("w", vp), ("bias", vp), ("out", vp), ("B", i32), ("P", i64), ("C", i32), ("Cout", i32),
                 ("dtype", i32)]
@@ -86,7 +91,7 @@ ENTRY_POINTS = {
     "dv_ddpm_step": DdpmStepParams, "dv_conv_igemm": ConvParams, "dv_gn_apply": GnApplyParams,
     "dv_gn_stats": GnStatsParams, "dv_layernorm": LayerNormParams, "dv_xattn_core": XattnParams,
     "dv_attn_mqa": AttnMqaParams, "dv_time_embed": TimeEmbedParams, "dv_linear_small": LinearSmallParams,
-    "dv_cond_tokens": CondTokensParams, "dv_to_out": ToOutParams,
+    "dv_cond_tokens": CondTokensParams, "dv_to_out": ToOutParams, "dv_im2col_init": Im2colParams,
 }
 PLAIN_SYMBOLS = ("dv_version", "dv_last_error_string", "dv_device_sm_count", "dv_conv_uses_tcgen05")
 

@@ -25,8 +25,11 @@ namespace dv {
 
 constexpr int TC_BM = 128;      // positions per tile (TMEM lanes)
 constexpr int TC_BK = 64;       // channels per pipeline stage (one 128-byte swizzle row)
-constexpr int TC_THREADS = 192; // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-5: epilogue
-constexpr int TC_SMEM_BUDGET = 200 * 1024;
+constexpr int TC_EPI_WARPS = 8;
+constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;  // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-9: epilogue
+constexpr int TC_SLAB_BYTES = TC_BM * 128;           // one 128-row x 64-column bf16 output slab
+constexpr int TC_PIPE_BYTES = 192 * 1024;            // operand pipeline: 8 / 6 / 4 stages for BN = 64 / 128 / 256
+constexpr int TC_TAIL_BYTES = 2 * TC_SLAB_BYTES + 1024 /*bias*/ + 1024 /*barriers, tmem slot, partials*/;
 
 struct TcParams {
   // problem
@@ -139,15 +142,30 @@ __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence:
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
 // ------------------------------------------------------------------------------------------ the kernel
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map),
+               "r"(smem_u32(src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_5d(const CUtensorMap* map, const void* src, int c0, int c1, int c2, int c3,
+                                             int c4) {
+  asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];" ::"l"(map),
+               "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+               : "memory");
+}
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
-               const __grid_constant__ CUtensorMap map_b, const TcParams p) {
+               const __grid_constant__ CUtensorMap map_b, const __grid_constant__ CUtensorMap map_out, const TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  // carve: [stages x (A 16 KB | B BN*128 B)] then barriers
+  // carve: [stages x (A 16 KB | B BN*128 B)] [2 x 16 KB output slabs] [bias BN floats] [barriers ...]
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const uint32_t a_bytes = TC_BM * TC_BK * 2, b_bytes = (uint32_t)p.BN * TC_BK * 2;
   const uint32_t stage_bytes = a_bytes + b_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
+  uint8_t* slab = smem + (size_t)p.stages * stage_bytes;            // 2 x (128 rows x 128 B), SWIZZLE_128B
+  float* bias_s = reinterpret_cast<float*>(slab + 2 * TC_SLAB_BYTES);  // [256]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(bias_s + 256);
   uint64_t* full_bar = bars;                 // [stages]
   uint64_t* empty_bar = bars + p.stages;     // [stages]
   uint64_t* tmem_full = bars + 2 * p.stages; // [2]
@@ -162,13 +180,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     tma_prefetch_desc(&map_a0);
     tma_prefetch_desc(&map_a1);
     tma_prefetch_desc(&map_b);
+    tma_prefetch_desc(&map_out);
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full[a], 1);
-      mbar_init(&tmem_empty[a], 4);  // one arrival per epilogue warp
+      mbar_init(&tmem_empty[a], TC_EPI_WARPS);  // one arrival per epilogue warp
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -257,90 +276,110 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   } else {
-    // ================================================================ epilogue warps (2..5)
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    // ================================================================ epilogue: 8 warps = 2 warpgroups
+    // Each 64-column slab of the accumulator is converted by both warpgroups (32 columns each), staged in
+    // shared memory in the SWIZZLE_128B layout and written with one TMA store (coalesced, asynchronous).
+    const int ew = warp - 2;        // 0..7
+    const int wg = ew >> 2;         // column half inside the slab
+    const int q = warp & 3;         // TMEM lane quarter this warp may access
     const int row_in_tile = q * 32 + lane;
+    const int et = ew * 32 + lane;  // 0..255
+    const bool issuer = (et == 0);
     int acc = 0;
     uint32_t acc_phase = 0;
-    int cur_sample = -1;
-    const int cpg = p.stats ? p.Cout / p.groups : 1;
+    int cur_sample = -1, last_n_tile = -1, bias_n_tile = -1;
+    int slab_idx = 0;  // running slab counter -> staging buffer parity
+    const int cpg = p.stats ? p.Cout / p.groups : 8;
     auto flush_stats = [&](int sample, int n_tile) {
-      // all 4 epilogue warps: make partials visible, then 2*groups_in_tile threads push them to global
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      const int t = (warp - 2) * 32 + lane;
+      epi_bar();
       const int groups_in_tile = p.BN / cpg;
-      if (t < 2 * groups_in_tile) {
-        const int g = n_tile * groups_in_tile + (t >> 1);
-        atomicAdd(&p.stats[((int64_t)sample * p.groups + g) * 2 + (t & 1)], (double)sred[t]);
-        sred[t] = 0.f;
+      if (et < 2 * groups_in_tile) {
+        const int g = n_tile * groups_in_tile + (et >> 1);
+        atomicAdd(&p.stats[((int64_t)sample * p.groups + g) * 2 + (et & 1)], (double)sred[et]);
+        sred[et] = 0.f;
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      epi_bar();
     };
-    int last_n_tile = 0;
     for (int64_t tile = tile_begin; tile < tile_end; ++tile) {
       const int64_t m_tile = tile / p.n_tiles_n;
       const int n_tile = (int)(tile % p.n_tiles_n);
-      const int64_t row = m_tile * TC_BM + row_in_tile;
-      const int sample = (int)((m_tile * TC_BM) / p.rows_per_sample);
+      const int64_t row0 = m_tile * TC_BM;
+      const int64_t row = row0 + row_in_tile;
+      const int sample = (int)(row0 / p.rows_per_sample);
       if (p.stats && cur_sample >= 0 && (sample != cur_sample || n_tile != last_n_tile)) flush_stats(cur_sample, last_n_tile);
       cur_sample = sample;
       last_n_tile = n_tile;
+      if (n_tile != bias_n_tile) {
+        epi_bar();  // previous tile's readers are done with bias_s
+        if (et < p.BN) bias_s[et] = p.bias ? p.bias[n_tile * p.BN + et] : 0.f;
+        epi_bar();
+        bias_n_tile = n_tile;
+      }
+      // store coordinates of this tile
+      const int img0 = (int)(row0 / ((int64_t)p.Ho * p.Wo));
+      const int rem0 = (int)(row0 % ((int64_t)p.Ho * p.Wo));
+      const int y0 = rem0 / p.Wo, x0 = rem0 % p.Wo;
+      const __nv_bfloat16* arow = p.add ? p.add + row * p.Cout + n_tile * p.BN : nullptr;
 
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.BN);
 
-      // output addressing
-      __nv_bfloat16* orow;
-      int shuffle_cq = 0;
-      int64_t sh_base = 0;
-      if (p.epilogue == DV_EPI_SHUFFLE_SILU) {
-        shuffle_cq = p.Cout / 4;
-        const int img = (int)(row / ((int64_t)p.Ho * p.Wo));
-        const int rem = (int)(row % ((int64_t)p.Ho * p.Wo));
-        sh_base = ((int64_t)img * (2 * p.Ho) + 2 * (rem / p.Wo)) * (2 * p.Wo) + 2 * (rem % p.Wo);
-        orow = p.out;
-      } else {
-        orow = p.out + row * p.out_ld + p.out_coff + n_tile * p.BN;
-      }
-      const __nv_bfloat16* arow = p.add ? p.add + row * p.Cout + n_tile * p.BN : nullptr;
-
-      for (int c0 = 0; c0 < p.BN; c0 += 32) {
+      for (int s0 = 0; s0 < p.BN; s0 += 64, ++slab_idx) {
+        const int c0 = s0 + wg * 32;  // this warp's 32 accumulator columns
         uint32_t r[32];
         tmem_ld32(t_base + (uint32_t)c0, r);
         float v[32];
-        const int ncol = n_tile * p.BN + c0;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + (p.bias ? __ldg(p.bias + ncol + j) : 0.f);
+        for (int j = 0; j < 32; j += 4) {
+          const float4 bb = *reinterpret_cast<const float4*>(bias_s + c0 + j);
+          v[j] = __uint_as_float(r[j]) + bb.x;
+          v[j + 1] = __uint_as_float(r[j + 1]) + bb.y;
+          v[j + 2] = __uint_as_float(r[j + 2]) + bb.z;
+          v[j + 3] = __uint_as_float(r[j + 3]) + bb.w;
+        }
         if (p.stats) {
-          // partial sums of the bf16-rounded values the next kernel will read, per 8-column segment
-          float ps1[4], ps2[4];
+          // per-8-column partial sums (cpg is a multiple of 8, so a segment never straddles a group), reduced
+          // over the warp's 32 rows with a 9-shuffle reduce-scatter butterfly instead of 8 full reductions
+          float w8[8];
 #pragma unroll
-          for (int s0 = 0; s0 < 4; ++s0) {
-            ps1[s0] = 0.f;
-            ps2[s0] = 0.f;
+          for (int sg = 0; sg < 4; ++sg) {
+            float a1 = 0.f, a2 = 0.f;
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-              const float rr = __bfloat162float(__float2bfloat16_rn(v[s0 * 8 + j]));
-              ps1[s0] += rr;
-              ps2[s0] += rr * rr;
+              const float x = v[sg * 8 + j];
+              a1 += x;
+              a2 = fmaf(x, x, a2);
             }
+            w8[2 * sg] = a1;
+            w8[2 * sg + 1] = a2;
           }
-          if (cpg == 8) {
+          const bool hi16 = lane & 16, hi8 = lane & 8, hi4 = lane & 4;
+          float w4[4], w2[2];
 #pragma unroll
-            for (int s0 = 0; s0 < 4; ++s0) {
-              const float a = warp_sum(ps1[s0]), b = warp_sum(ps2[s0]);
-              if (lane == 0) { atomicAdd(&sred[(c0 / 8 + s0) * 2], a); atomicAdd(&sred[(c0 / 8 + s0) * 2 + 1], b); }
-            }
-          } else if (cpg == 16) {
+          for (int i = 0; i < 4; ++i) {
+            const float send = hi16 ? w8[i] : w8[i + 4];
+            const float recv = __shfl_xor_sync(0xffffffffu, send, 16);
+            w4[i] = (hi16 ? w8[i + 4] : w8[i]) + recv;
+          }
 #pragma unroll
-            for (int s0 = 0; s0 < 2; ++s0) {
-              const float a = warp_sum(ps1[2 * s0] + ps1[2 * s0 + 1]), b = warp_sum(ps2[2 * s0] + ps2[2 * s0 + 1]);
-              if (lane == 0) { atomicAdd(&sred[(c0 / 16 + s0) * 2], a); atomicAdd(&sred[(c0 / 16 + s0) * 2 + 1], b); }
-            }
-          } else {  // cpg is a multiple of 32: the whole chunk belongs to one group
-            const float a = warp_sum(ps1[0] + ps1[1] + ps1[2] + ps1[3]), b = warp_sum(ps2[0] + ps2[1] + ps2[2] + ps2[3]);
-            if (lane == 0) { atomicAdd(&sred[(c0 / cpg) * 2], a); atomicAdd(&sred[(c0 / cpg) * 2 + 1], b); }
+          for (int i = 0; i < 2; ++i) {
+            const float send = hi8 ? w4[i] : w4[i + 2];
+            const float recv = __shfl_xor_sync(0xffffffffu, send, 8);
+            w2[i] = (hi8 ? w4[i + 2] : w4[i]) + recv;
+          }
+          float w1;
+          {
+            const float send = hi4 ? w2[0] : w2[1];
+            const float recv = __shfl_xor_sync(0xffffffffu, send, 4);
+            w1 = (hi4 ? w2[1] : w2[0]) + recv;
+          }
+          w1 += __shfl_xor_sync(0xffffffffu, w1, 2);
+          w1 += __shfl_xor_sync(0xffffffffu, w1, 1);
+          if ((lane & 3) == 0) {
+            const int idx = lane >> 2;  // = 4*hi16 + 2*hi8 + hi4 : (segment, stat) = (idx >> 1, idx & 1)
+            const int gl = (c0 + 8 * (idx >> 1)) / cpg;
+            atomicAdd(&sred[gl * 2 + (idx & 1)], w1);
           }
         }
         if (arow) {
@@ -353,23 +392,38 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
           }
         }
         if (p.epilogue == DV_EPI_SHUFFLE_SILU) {
-          const int qq = ncol / shuffle_cq, cc = ncol % shuffle_cq;
-          __nv_bfloat16* dst = p.out + (sh_base + (int64_t)(qq / 2) * (2 * p.Wo) + (qq % 2)) * p.out_ld + p.out_coff + cc;
 #pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            float o[8];
+          for (int j = 0; j < 32; ++j) v[j] = silu_f(v[j]);
+        }
+        // the staging buffer of two slabs ago must have been read out by its TMA store
+        uint8_t* sbuf = slab + (slab_idx & 1) * TC_SLAB_BYTES;
+        if (issuer) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        epi_bar();
+        {
+          // row r of the slab = 128 bytes; 16-byte chunk index is XOR-swizzled with (r % 8)
+          uint8_t* srow = sbuf + row_in_tile * 128;
 #pragma unroll
-            for (int e = 0; e < 8; ++e) o[e] = silu_f(v[j + e]);
-            store8(dst + j, o);
+          for (int j = 0; j < 4; ++j) {
+            const int chunk = (wg * 4 + j) ^ (row_in_tile & 7);
+            uint4 pk;
+            __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&pk);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) h[e] = __floats2bfloat162_rn(v[j * 8 + 2 * e], v[j * 8 + 2 * e + 1]);
+            *reinterpret_cast<uint4*>(srow + chunk * 16) = pk;
           }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            float o[8];
-#pragma unroll
-            for (int e = 0; e < 8; ++e) o[e] = v[j + e];
-            store8(orow + c0 + j, o);
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        epi_bar();
+        if (issuer) {
+          const int ncol = n_tile * p.BN + s0;
+          if (p.epilogue == DV_EPI_SHUFFLE_SILU) {
+            // output view (Cq, j, Wo, i, n_img*Ho): columns [ncol, ncol+64) lie inside one (i,j) block
+            const int cq = p.Cout / 4, qq = ncol / cq, cc = ncol % cq;
+            tma_store_5d(&map_out, sbuf, p.out_coff + cc, qq & 1, x0, qq >> 1, img0 * p.Ho + y0);
+          } else {
+            tma_store_2d(&map_out, sbuf, p.out_coff + ncol, (int)row0);
           }
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
       }
       tc_fence_before();
@@ -378,6 +432,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
     if (p.stats && cur_sample >= 0) flush_stats(cur_sample, last_n_tile);
+    if (issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
 
   tc_fence_before();
@@ -460,11 +515,11 @@ int conv_tc_supported(const dv_conv_params& p) {
   const int64_t rps = (int64_t)p.frames * Ho * Wo;
   if (rows % TC_BM || rps % TC_BM) return 0;
   if (p.epilogue == DV_EPI_SHUFFLE_SILU) {
-    if ((p.Cout / 4) % 32) return 0;
+    if ((p.Cout / 4) % 64) return 0;
   }
   if (p.stats) {
     const int cpg = p.Cout / p.groups;
-    if (p.Cout % p.groups || !(cpg == 8 || cpg == 16 || cpg % 32 == 0) || (bn % cpg) || bn / cpg > 32) return 0;
+    if (p.Cout % p.groups || cpg % 8 || (bn % cpg) || bn / cpg > 32) return 0;
   }
   const int out_ld = p.out_ld ? p.out_ld : (p.epilogue == DV_EPI_SHUFFLE_SILU ? p.Cout / 4 : p.Cout);
   if (out_ld % 8 || p.out_coff % 8) return 0;
@@ -557,7 +612,7 @@ int conv_tc_launch(const dv_conv_params& p, cudaStream_t s) {
   t.total_tiles = t.m_tiles * t.n_tiles_n;
   t.rows_per_sample = (int64_t)p.frames * Ho * Wo;
   const int stage_bytes = TC_BM * TC_BK * 2 + t.BN * TC_BK * 2;
-  t.stages = TC_SMEM_BUDGET / stage_bytes;
+  t.stages = TC_PIPE_BYTES / stage_bytes;
   if (t.stages > 8) t.stages = 8;
   t.bias = p.bias;
   t.add = reinterpret_cast<const __nv_bfloat16*>(p.add);
@@ -585,6 +640,23 @@ int conv_tc_launch(const dv_conv_params& p, cudaStream_t s) {
     rc = encode_map(&mb, p.weight, 2, dims, strides, box);
     if (rc != DV_OK) return rc;
   }
+  CUtensorMap mo;
+  {
+    const int out_ld = p.out_ld;
+    if (p.epilogue == DV_EPI_SHUFFLE_SILU) {
+      // (Cq, j, Wo, i, n_img*Ho) view of the 2x-upsampled [n_img][2Ho][2Wo][out_ld] tensor
+      uint64_t dims[5] = {(uint64_t)out_ld, 2, (uint64_t)Wo, 2, (uint64_t)p.n_img * Ho};
+      uint64_t strides[4] = {(uint64_t)out_ld * 2, 2ull * out_ld * 2, 2ull * Wo * out_ld * 2, 4ull * Wo * out_ld * 2};
+      uint32_t box[5] = {64, 1, (uint32_t)g.bw, 1, (uint32_t)(g.bh * g.bn)};
+      rc = encode_map(&mo, p.out, 5, dims, strides, box);
+    } else {
+      uint64_t dims[2] = {(uint64_t)out_ld, (uint64_t)p.n_img * Ho * Wo};
+      uint64_t strides[1] = {(uint64_t)out_ld * 2};
+      uint32_t box[2] = {64, TC_BM};
+      rc = encode_map(&mo, p.out, 2, dims, strides, box);
+    }
+    if (rc != DV_OK) return rc;
+  }
   static int sm_count = 0;
   if (!sm_count) {
     int dev = 0;
@@ -592,7 +664,7 @@ int conv_tc_launch(const dv_conv_params& p, cudaStream_t s) {
     cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
     if (sm_count <= 0) sm_count = 148;
   }
-  const size_t smem = (size_t)t.stages * stage_bytes + 1024 /*alignment slack*/ + 1024 /*barriers, tmem slot, partials*/;
+  const size_t smem = (size_t)t.stages * stage_bytes + TC_TAIL_BYTES + 1024 /*alignment slack*/;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -600,7 +672,7 @@ int conv_tc_launch(const dv_conv_params& p, cudaStream_t s) {
     attr_set = true;
   }
   const int grid = (int)(t.total_tiles < sm_count ? t.total_tiles : sm_count);
-  conv_tc_kernel<<<grid, TC_THREADS, smem, s>>>(ma0, ma1, mb, t);
+  conv_tc_kernel<<<grid, TC_THREADS, smem, s>>>(ma0, ma1, mb, mo, t);
   DV_CHECK_LAUNCH("dv_conv_igemm(tcgen05)");
   return DV_OK;
 }

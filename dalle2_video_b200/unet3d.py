@@ -607,7 +607,9 @@ class _Engine:
         n_img, P = B * T, T * H * W
         rows = B * P
         x0 = self._new_act(rows, u.init_dim)
-        if isinstance(u.init_conv, _CrossEmbed):
+        if isinstance(u.init_conv, _CrossEmbed) and self._init_conv_as_gemm(x0, n_img, H, W):
+            pass
+        elif isinstance(u.init_conv, _CrossEmbed):
             coff = 0
             for conv, k in zip(u.init_conv.convs, u.init_conv.kernel_sizes):
                 co = conv.weight.shape[0]
@@ -689,6 +691,42 @@ class _Engine:
                                             out=self.eps.data_ptr(), B=B, P=P, C=x.C, Cout=u.channels_out,
                                             dtype=self.code))
         self.final_act = x  # kept alive
+
+    def _init_conv_as_gemm(self, x0, n_img, H, W):
+        """CrossEmbedLayer3D as im2col + ONE tensor-core GEMM (bf16 only): the 3x3 / 7x7 windows are centred
+        sub-windows of the largest one, so their weights are zero-padded into a single [dim][Kpad] matrix."""
+        u = self.u
+        if self.dtype != torch.bfloat16:
+            return False
+        convs, ks = list(u.init_conv.convs), list(u.init_conv.kernel_sizes)
+        kmax, cin = max(ks), convs[0].weight.shape[1]
+        if any(k % 2 == 0 for k in ks):
+            return False
+        ktot = kmax * kmax * cin
+        kpad = (ktot + 63) // 64 * 64
+        rows = n_img * H * W
+        probe = L.ConvParams(src0=1 << 20, src1=None, weight=1 << 20, bias=None, add=None, out=1 << 20, stats=None,
+                             n_img=rows, frames=self.T * H * W, H=1, W=1, C0=kpad, C1=0, Cout=u.init_dim, kh=1, kw=1,
+                             pad=0, mode=L.CONV_NORMAL, epilogue=L.EPI_STORE, groups=0, out_ld=0, out_coff=0,
+                             dtype=self.code, impl=self.impl)
+        if not L.lib().dv_conv_uses_tcgen05(probe):
+            return False
+        wfull = torch.zeros(u.init_dim, kmax, kmax, cin)
+        bfull, co0 = [], 0
+        for conv, k in zip(convs, ks):
+            co, off = conv.weight.shape[0], (kmax - k) // 2
+            wfull[co0:co0 + co, off:off + k, off:off + k, :] = conv.weight.detach()[:, :, 0].permute(0, 2, 3, 1).cpu()
+            bfull.append(conv.bias.detach().cpu())
+            co0 += co
+        wp = torch.zeros(u.init_dim, kpad)
+        wp[:, :ktot] = wfull.reshape(u.init_dim, ktot)
+        patches = self.pool.get(rows * kpad * self.esz)
+        self._op("dv_im2col_init", L.Im2colParams(x=self.x_in.data_ptr(), out=patches.data_ptr(), B=self.B, C=cin,
+                                                  T=self.T, H=H, W=W, k=kmax, Kpad=kpad, dtype=self.code))
+        self._conv([(patches.data_ptr(), kpad)], self._w(wp), self._f32(torch.cat(bfull)), x0.ptr, u.init_dim, rows,
+                   1, 1, frames=self.T * H * W)
+        self.pool.put(patches)
+        return True
 
     def _next_stats(self):
         i = self._gn_i

@@ -127,6 +127,22 @@ int dv_conv_igemm(const dv_conv_params* p, dv_stream_t stream);
 int dv_conv_uses_tcgen05(const dv_conv_params* p);
 
 /* ------------------------------------------------------------------------------------------------
+ * K4 (tensor-core form)  im2col of the (B,C,T,H,W) float32 video into a channels-last patch matrix
+ * [B*T*H*W][Kpad] (K order [dy][dx][c], zero padded to Kpad, a multiple of 64), so that the three
+ * CrossEmbedLayer3D convolutions (:222-244) — whose 3x3 and 7x7 windows are centred sub-windows of the
+ * 15x15 one — run as ONE tcgen05 GEMM against a zero-padded [Cout][Kpad] weight (dv_conv_igemm, kh=kw=1).
+ */
+typedef struct {
+  const float* x;  /* (B, C, T, H, W) */
+  void* out;       /* [B*T*H*W][Kpad] dtype */
+  int B, C, T, H, W;
+  int k;           /* window size (odd); pad = k/2 */
+  int Kpad;        /* >= k*k*C, multiple of 8 */
+  dv_dtype dtype;
+} dv_im2col_params;
+int dv_im2col_init(const dv_im2col_params* p, dv_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
  * K2  GroupNorm finalize + apply + scale/shift + SiLU (+ residual).
  * Replaces nn.GroupNorm on the 5-D tensor (statistics over (C/G, T, H, W) jointly, :109,125),
  * `x * (scale + 1) + shift` (:127-129), nn.SiLU (:131) and the block's residual add (:205).

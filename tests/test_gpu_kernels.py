@@ -418,3 +418,17 @@ def test_conv_tcgen05_unshuffle_and_shuffle():
     conv([x], wp, bias, a, n_img=B * T, frames=T, H=H, W=W, epilogue=L.EPI_SHUFFLE_SILU, impl=2)
     conv([x], wp, bias, b, n_img=B * T, frames=T, H=H, W=W, epilogue=L.EPI_SHUFFLE_SILU, impl=1)
     assert rel_err(a, b) < 6e-3
+
+
+@pytest.mark.parametrize("dtype", DT)
+def test_im2col_patch_matrix(dtype):
+    B, C, T, H, W, k, Kpad = 2, 3, 2, 8, 16, 5, 80
+    x = rnd(B, C, T, H, W, seed=1)
+    out = torch.full((B * T * H * W, Kpad), 7.0, dtype=dtype, device=dev())
+    L.call("dv_im2col_init", L.Im2colParams(x=ptr(x), out=ptr(out), B=B, C=C, T=T, H=H, W=W, k=k, Kpad=Kpad,
+                                            dtype=code(out)), stream())
+    xp = F.pad(x, (k // 2, k // 2, k // 2, k // 2))
+    cols = torch.stack([xp[:, :, :, dy:dy + H, dx:dx + W] for dy in range(k) for dx in range(k)], dim=-1)  # b c t h w tap
+    ref = cols.permute(0, 2, 3, 4, 5, 1).reshape(B * T * H * W, k * k * C)
+    assert rel_err(out[:, :k * k * C], ref.to(dtype)) == 0.0
+    assert float(out[:, k * k * C:].abs().max()) == 0.0
