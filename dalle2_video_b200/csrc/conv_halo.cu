@@ -1,0 +1,407 @@
+// K1 — 3x3 convolution for the wide, narrow-channel layers (64x64 / 32x32 resolution, Cout 64 or 128) as a
+// streaming-halo implicit GEMM on tcgen05.
+//
+// The per-tap kernel (conv_tc.cu) re-reads the activation tile from L2 once per filter tap; on B200 these
+// layers (30 % of the network's FLOPs) are then bound by L2 -> SM bandwidth (~13 TB/s measured), not by the
+// tensor cores.  Here the activation window is loaded ONCE per 64-channel chunk and all nine taps read it:
+//
+//   * positions are flattened in a zero-padded index space  Q = (n*(H+1) + y + 1)*(W+2) + x + 1  (one zero
+//     column left/right of every row, one zero row between frames), so a tap (dy,dx) is the uniform shift
+//     Q + dy*(W+2) + dx for every output position;
+//   * the window of padded rows covering 256 consecutive Q (+ halo) is brought in by TMA, one box per padded
+//     row, out-of-image coordinates (x=-1, x=W, y=-1, n>=N) zero-filled by the TMA unit;
+//   * the A operand of tap (dy,dx) is the SAME shared-memory window addressed through a K-major SWIZZLE_128B
+//     descriptor whose start address is shifted by (dy*(W+2)+dx) rows of 128 bytes.  Measured on B200
+//     (tools/experiments/desc_shift_probe.cu, tma_dst_shift_probe.cu): both TMA and tcgen05.mma apply the
+//     128-byte swizzle as a function of the absolute shared-memory address, so any 128-byte-aligned start
+//     (base_offset = 0) and any 128-byte-aligned TMA destination are consistent;
+//   * accumulator rows that fall on padding columns / separator rows (3-9 % of a tile) are discarded.
+//
+// Tile = 256 consecutive Q (two M=128 MMAs share every weight tile), accumulators double-buffered in TMEM
+// (4*BN columns).  Warp roles: 0 = TMA producer, 1 = MMA issuer, 2-9 = epilogue (bias, GroupNorm partial sums,
+// bf16, shared-memory transpose, coalesced 16-byte row stores of the valid rows).
+#include "tc_common.cuh"
+
+namespace dv {
+
+constexpr int HL_EPI_WARPS = 8;
+constexpr int HL_THREADS = 64 + 32 * HL_EPI_WARPS;
+constexpr int HL_TILE_Q = 256;
+constexpr int HL_A_STAGES = 2;
+
+struct HaloParams {
+  int H, W, Wp, Hp1, n_img, frames;
+  int c0_chunks, c1_chunks;
+  int BN, NR;
+  int a_stage_bytes, b_stages;
+  int tiles_per_sample;
+  int64_t total_tiles;
+  const float* bias;
+  __nv_bfloat16* out;
+  double* stats;
+  int groups, out_ld, out_coff;
+};
+
+__device__ __forceinline__ void hl_epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+__global__ void __launch_bounds__(HL_THREADS, 1)
+conv_halo_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
+                 const __grid_constant__ CUtensorMap map_b, const HaloParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const uint32_t b_bytes = (uint32_t)p.BN * 128;
+  uint8_t* a_ring = smem;
+  uint8_t* b_ring = a_ring + (size_t)HL_A_STAGES * p.a_stage_bytes;
+  uint8_t* stage_out = b_ring + (size_t)p.b_stages * b_bytes;          // 2 x [128 rows][128 B]
+  long long* rowpos = reinterpret_cast<long long*>(stage_out + 2 * 16384);  // 2 x [128]
+  float* bias_s = reinterpret_cast<float*>(rowpos + 256);                   // [128]
+  float* sred = bias_s + 128;                                               // [64]
+  uint64_t* full_a = reinterpret_cast<uint64_t*>(sred + 64);
+  uint64_t* empty_a = full_a + HL_A_STAGES;
+  uint64_t* full_b = empty_a + HL_A_STAGES;
+  uint64_t* empty_b = full_b + p.b_stages;
+  uint64_t* tmem_full = empty_b + p.b_stages;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t tmem_cols = (uint32_t)(4 * p.BN);  // 256 or 512
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_a0);
+    tma_prefetch_desc(&map_a1);
+    tma_prefetch_desc(&map_b);
+    for (int s = 0; s < HL_A_STAGES; ++s) { mbar_init(&full_a[s], 1); mbar_init(&empty_a[s], 1); }
+    for (int s = 0; s < p.b_stages; ++s) { mbar_init(&full_b[s], 1); mbar_init(&empty_b[s], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], HL_EPI_WARPS); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (threadIdx.x < 64) sred[threadIdx.x] = 0.f;
+  if (threadIdx.x >= 64 && threadIdx.x < 64 + p.BN) bias_s[threadIdx.x - 64] = p.bias ? p.bias[threadIdx.x - 64] : 0.f;
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int64_t per_cta = (p.total_tiles + gridDim.x - 1) / gridDim.x;
+  const int64_t tile_begin = (int64_t)blockIdx.x * per_cta;
+  const int64_t tile_end = tile_begin + per_cta < p.total_tiles ? tile_begin + per_cta : p.total_tiles;
+  const int n_chunks = p.c0_chunks + p.c1_chunks;
+  // first valid output of sample b: frame b*T, y = 0, x = 0
+  auto tile_q0 = [&](int64_t tile, int* sample) -> int64_t {
+    const int b = (int)(tile / p.tiles_per_sample);
+    const int j = (int)(tile % p.tiles_per_sample);
+    *sample = b;
+    return ((int64_t)b * p.frames * p.Hp1 + 1) * p.Wp + 1 + (int64_t)j * HL_TILE_Q;
+  };
+
+  if (warp == 0) {
+    // ================================================================ TMA producer
+    if (elect_one()) {
+      int sa = 0, sb = 0;
+      uint32_t pa = 0, pb = 0;
+      for (int64_t tile = tile_begin; tile < tile_end; ++tile) {
+        int sample;
+        const int64_t q0 = tile_q0(tile, &sample);
+        const int64_t r_lo = (q0 - p.Wp - 1) / p.Wp;
+        for (int ch = 0; ch < n_chunks; ++ch) {
+          const int src = ch >= p.c0_chunks;
+          const int c = src ? ch - p.c0_chunks : ch;
+          const CUtensorMap* map = src ? &map_a1 : &map_a0;
+          mbar_wait(&empty_a[sa], pa ^ 1);
+          uint8_t* dst = a_ring + (size_t)sa * p.a_stage_bytes;
+          mbar_expect_tx(&full_a[sa], (uint32_t)(p.NR * p.Wp * 128));
+          for (int r = 0; r < p.NR; ++r) {
+            const int64_t R = r_lo + r;
+            const int n = (int)(R / p.Hp1);
+            const int yy = (int)(R % p.Hp1) - 1;
+            tma_load_5d(map, &full_a[sa], dst + (size_t)r * p.Wp * 128, c * TC_BK, -1, yy, n, 0);
+          }
+          if (++sa == HL_A_STAGES) { sa = 0; pa ^= 1; }
+          for (int tap = 0; tap < 9; ++tap) {
+            mbar_wait(&empty_b[sb], pb ^ 1);
+            mbar_expect_tx(&full_b[sb], b_bytes);
+            tma_load_2d(&map_b, &full_b[sb], b_ring + (size_t)sb * b_bytes, (tap * n_chunks + ch) * TC_BK, 0);
+            if (++sb == p.b_stages) { sb = 0; pb ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================================================ MMA issuer
+    const uint32_t idesc = make_idesc(p.BN);
+    int sa = 0, sb = 0, acc = 0;
+    uint32_t pa = 0, pb = 0, acc_phase = 0;
+    for (int64_t tile = tile_begin; tile < tile_end; ++tile) {
+      int sample;
+      const int64_t q0 = tile_q0(tile, &sample);
+      const int64_t r_lo = (q0 - p.Wp - 1) / p.Wp;
+      const int row_off = (int)(q0 - r_lo * p.Wp);  // window row of Q0
+      mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 2 * p.BN);
+      for (int ch = 0; ch < n_chunks; ++ch) {
+        mbar_wait(&full_a[sa], pa);
+        tc_fence_after();
+        const uint32_t a_base = smem_u32(a_ring + (size_t)sa * p.a_stage_bytes);
+        for (int tap = 0; tap < 9; ++tap) {
+          mbar_wait(&full_b[sb], pb);
+          tc_fence_after();
+          if (elect_one()) {
+            const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+            const uint64_t bdesc = make_smem_desc(smem_u32(b_ring + (size_t)sb * b_bytes));
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+              const uint64_t adesc = make_smem_desc(a_base + (uint32_t)(row_off + u * 128 + dy * p.Wp + dx) * 128u);
+#pragma unroll
+              for (int kk = 0; kk < TC_BK / 16; ++kk)
+                umma_f16(d_tmem + (uint32_t)(u * p.BN), adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), idesc,
+                         (ch | tap | kk) != 0);
+            }
+            umma_commit(&empty_b[sb]);
+            if (tap == 8) {
+              umma_commit(&empty_a[sa]);
+              if (ch == n_chunks - 1) umma_commit(&tmem_full[acc]);
+            }
+          }
+          __syncwarp();
+          if (++sb == p.b_stages) { sb = 0; pb ^= 1; }
+        }
+        if (++sa == HL_A_STAGES) { sa = 0; pa ^= 1; }
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  } else {
+    // ================================================================ epilogue (8 warps)
+    const int ew = warp - 2, wg = ew >> 2, q = warp & 3;
+    const int row_in_sub = q * 32 + lane;
+    const int et = ew * 32 + lane;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    int cur_sample = -1;
+    int buf = 0;
+    const int cpg = p.stats ? p.BN / p.groups : 8;
+    auto flush_stats = [&](int sample) {
+      hl_epi_bar();
+      if (et < 2 * p.groups) {
+        atomicAdd(&p.stats[((int64_t)sample * p.groups) * 2 + et], (double)sred[et]);
+        sred[et] = 0.f;
+      }
+      hl_epi_bar();
+    };
+    for (int64_t tile = tile_begin; tile < tile_end; ++tile) {
+      int sample;
+      const int64_t q0 = tile_q0(tile, &sample);
+      if (p.stats && cur_sample >= 0 && sample != cur_sample) flush_stats(cur_sample);
+      cur_sample = sample;
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      for (int u = 0; u < 2; ++u) {
+        // which output position does this accumulator row hold?
+        const int64_t Q = q0 + u * 128 + row_in_sub;
+        const int64_t R = Q / p.Wp;
+        const int xx = (int)(Q % p.Wp) - 1;
+        const int n = (int)(R / p.Hp1);
+        const int yy = (int)(R % p.Hp1) - 1;
+        const bool valid = xx >= 0 && xx < p.W && yy >= 0 && n < (sample + 1) * p.frames;
+        const long long pos = valid ? ((long long)n * p.H + yy) * p.W + xx : -1;
+        const uint32_t t_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((acc * 2 + u) * p.BN);
+        for (int s0 = 0; s0 < p.BN; s0 += 64) {
+          const int c0 = s0 + wg * 32;
+          uint32_t r[32];
+          tmem_ld32(t_base + (uint32_t)c0, r);
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 bb = *reinterpret_cast<const float4*>(bias_s + c0 + j);
+            v[j] = valid ? __uint_as_float(r[j]) + bb.x : 0.f;
+            v[j + 1] = valid ? __uint_as_float(r[j + 1]) + bb.y : 0.f;
+            v[j + 2] = valid ? __uint_as_float(r[j + 2]) + bb.z : 0.f;
+            v[j + 3] = valid ? __uint_as_float(r[j + 3]) + bb.w : 0.f;
+          }
+          if (p.stats) {
+            float w8[8];
+#pragma unroll
+            for (int sg = 0; sg < 4; ++sg) {
+              float a1 = 0.f, a2 = 0.f;
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float x = v[sg * 8 + j];
+                a1 += x;
+                a2 = fmaf(x, x, a2);
+              }
+              w8[2 * sg] = a1;
+              w8[2 * sg + 1] = a2;
+            }
+            const bool hi16 = lane & 16, hi8 = lane & 8, hi4 = lane & 4;
+            float w4[4], w2[2];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float send = hi16 ? w8[i] : w8[i + 4];
+              const float recv = __shfl_xor_sync(0xffffffffu, send, 16);
+              w4[i] = (hi16 ? w8[i + 4] : w8[i]) + recv;
+            }
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+              const float send = hi8 ? w4[i] : w4[i + 2];
+              const float recv = __shfl_xor_sync(0xffffffffu, send, 8);
+              w2[i] = (hi8 ? w4[i + 2] : w4[i]) + recv;
+            }
+            float w1;
+            {
+              const float send = hi4 ? w2[0] : w2[1];
+              const float recv = __shfl_xor_sync(0xffffffffu, send, 4);
+              w1 = (hi4 ? w2[1] : w2[0]) + recv;
+            }
+            w1 += __shfl_xor_sync(0xffffffffu, w1, 2);
+            w1 += __shfl_xor_sync(0xffffffffu, w1, 1);
+            if ((lane & 3) == 0) {
+              const int idx = lane >> 2;
+              const int gl = (c0 + 8 * (idx >> 1)) / cpg;
+              atomicAdd(&sred[gl * 2 + (idx & 1)], w1);
+            }
+          }
+          // transpose through shared memory: rows -> coalesced 16-byte stores of the valid rows
+          uint8_t* sbuf = stage_out + buf * 16384;
+          long long* rp = rowpos + buf * 128;
+          {
+            uint8_t* srow = sbuf + row_in_sub * 128;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int chunk = (wg * 4 + j) ^ (row_in_sub & 7);
+              uint4 pk;
+              __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&pk);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) h[e] = __floats2bfloat162_rn(v[j * 8 + 2 * e], v[j * 8 + 2 * e + 1]);
+              *reinterpret_cast<uint4*>(srow + chunk * 16) = pk;
+            }
+            if (wg == 0) rp[row_in_sub] = pos;
+          }
+          hl_epi_bar();
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int idx = et + 256 * i;
+            const int row = idx >> 3, chunk = idx & 7;
+            const long long gp = rp[row];
+            if (gp >= 0) {
+              const uint4 val = *reinterpret_cast<const uint4*>(sbuf + row * 128 + ((chunk ^ (row & 7)) * 16));
+              *reinterpret_cast<uint4*>(p.out + gp * p.out_ld + p.out_coff + s0 + chunk * 8) = val;
+            }
+          }
+          buf ^= 1;
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+    if (p.stats && cur_sample >= 0) flush_stats(cur_sample);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------ host side
+static int halo_nr(int Wp) { return (HL_TILE_Q + 2 * Wp + 2 + Wp - 2) / Wp + 1; }
+
+static size_t halo_smem(int Wp, int BN, int* a_stage_bytes, int* b_stages) {
+  const int a = (halo_nr(Wp) * Wp * 128 + 1023) / 1024 * 1024;
+  const int tail = 2 * 16384 + 2 * 128 * 8 + 128 * 4 + 64 * 4 + 1024;
+  int bs = (227 * 1024 - 1024 - HL_A_STAGES * a - tail) / (BN * 128);
+  if (bs > 9) bs = 9;
+  *a_stage_bytes = a;
+  *b_stages = bs;
+  return (size_t)HL_A_STAGES * a + (size_t)bs * BN * 128 + tail + 1024;
+}
+
+int conv_halo_supported(const dv_conv_params& p) {
+  if (p.dtype != DV_BF16 || p.mode != DV_CONV_NORMAL || p.kh != 3 || p.kw != 3 || p.pad != 1) return 0;
+  if (p.epilogue != DV_EPI_STORE || p.add) return 0;
+  if (p.Cout != 64 && p.Cout != 128) return 0;
+  if (p.C0 % TC_BK || p.C1 % TC_BK) return 0;
+  if (p.W < 32 || p.W > 128 || p.H < 8) return 0;
+  if (p.n_img % p.frames) return 0;
+  const int out_ld = p.out_ld ? p.out_ld : p.Cout;
+  if (out_ld % 8 || p.out_coff % 8) return 0;
+  if (p.stats) {
+    if (p.groups <= 0 || p.Cout % p.groups || (p.Cout / p.groups) % 8 || p.groups > 32) return 0;
+  }
+  int a, bs;
+  halo_smem(p.W + 2, p.Cout, &a, &bs);
+  return bs >= 3;
+}
+
+int conv_halo_launch(const dv_conv_params& p, cudaStream_t s) {
+  HaloParams h;
+  memset(&h, 0, sizeof(h));
+  h.H = p.H; h.W = p.W; h.Wp = p.W + 2; h.Hp1 = p.H + 1; h.n_img = p.n_img; h.frames = p.frames;
+  h.c0_chunks = p.C0 / TC_BK; h.c1_chunks = p.C1 / TC_BK;
+  h.BN = p.Cout;
+  h.NR = halo_nr(h.Wp);
+  const size_t smem = halo_smem(h.Wp, h.BN, &h.a_stage_bytes, &h.b_stages);
+  const int64_t span = ((int64_t)p.frames * h.Hp1 - 2) * h.Wp + p.W;
+  h.tiles_per_sample = (int)((span + HL_TILE_Q - 1) / HL_TILE_Q);
+  h.total_tiles = (int64_t)(p.n_img / p.frames) * h.tiles_per_sample;
+  h.bias = p.bias;
+  h.out = reinterpret_cast<__nv_bfloat16*>(p.out);
+  h.stats = p.stats;
+  h.groups = p.groups;
+  h.out_ld = p.out_ld ? p.out_ld : p.Cout;
+  h.out_coff = p.out_coff;
+
+  auto act_map = [&](CUtensorMap* m, const void* ptr, int C) {
+    uint64_t dims[5] = {(uint64_t)C, (uint64_t)p.W, (uint64_t)p.H, (uint64_t)p.n_img, 1};
+    uint64_t strides[4] = {(uint64_t)C * 2, (uint64_t)p.W * C * 2, (uint64_t)p.H * p.W * C * 2,
+                           (uint64_t)p.n_img * p.H * p.W * C * 2};
+    uint32_t box[5] = {TC_BK, (uint32_t)h.Wp, 1, 1, 1};
+    return encode_map(m, ptr, 5, dims, strides, box);
+  };
+  CUtensorMap ma0, ma1, mb;
+  int rc = act_map(&ma0, p.src0, p.C0);
+  if (rc != DV_OK) return rc;
+  if (p.C1) {
+    rc = act_map(&ma1, p.src1, p.C1);
+    if (rc != DV_OK) return rc;
+  } else {
+    ma1 = ma0;
+  }
+  {
+    const uint64_t ktot = 9ull * (p.C0 + p.C1);
+    uint64_t dims[2] = {ktot, (uint64_t)p.Cout};
+    uint64_t strides[1] = {ktot * 2};
+    uint32_t box[2] = {TC_BK, (uint32_t)h.BN};
+    rc = encode_map(&mb, p.weight, 2, dims, strides, box);
+    if (rc != DV_OK) return rc;
+  }
+  static int sm_count = 0;
+  if (!sm_count) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
+    if (sm_count <= 0) sm_count = 148;
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    DV_REQUIRE(e == cudaSuccess, DV_ECUDA, "dv_conv_igemm(halo): cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  const int grid = (int)(h.total_tiles < sm_count ? h.total_tiles : sm_count);
+  conv_halo_kernel<<<grid, HL_THREADS, smem, s>>>(ma0, ma1, mb, h);
+  DV_CHECK_LAUNCH("dv_conv_igemm(halo)");
+  return DV_OK;
+}
+
+}  // namespace dv

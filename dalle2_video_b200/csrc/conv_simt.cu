@@ -7,6 +7,8 @@
 //
 // Tiling: 64 output positions x 64 output channels per CTA, K chunks of 16, 256 threads, 4x4 register
 // micro-tile per thread, operands staged through shared memory as fp32.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace dv {
@@ -213,6 +215,14 @@ static int launch_simt(const dv_conv_params& p, const ConvGeom& g, cudaStream_t 
 
 int conv_tc_supported(const dv_conv_params& p);
 int conv_tc_launch(const dv_conv_params& p, cudaStream_t s);
+int conv_halo_supported(const dv_conv_params& p);
+int conv_halo_launch(const dv_conv_params& p, cudaStream_t s);
+
+static bool halo_enabled() {
+  static int v = -1;
+  if (v < 0) v = getenv("DV_CONV_DISABLE_HALO") ? 0 : 1;
+  return v != 0;
+}
 
 static int validate_conv(const dv_conv_params* p, ConvGeom* g) {
   DV_REQUIRE(p && p->src0 && p->weight && p->out, DV_EINVAL, "dv_conv_igemm: null pointer");
@@ -270,7 +280,8 @@ static int validate_conv(const dv_conv_params* p, ConvGeom* g) {
 extern "C" int dv_conv_uses_tcgen05(const dv_conv_params* p) {
   dv::ConvGeom g;
   if (dv::validate_conv(p, &g) != DV_OK) return 0;
-  return (p->impl != 1) && dv::conv_tc_supported(*p);
+  if (p->impl == 1) return 0;
+  return dv::conv_tc_supported(*p) || (dv::halo_enabled() && dv::conv_halo_supported(*p));
 }
 
 extern "C" int dv_conv_igemm(const dv_conv_params* pin, dv_stream_t stream) {
@@ -283,7 +294,10 @@ extern "C" int dv_conv_igemm(const dv_conv_params* pin, dv_stream_t stream) {
   DV_REQUIRE(p.out_ld % 4 == 0 && p.out_coff % 4 == 0, DV_EALIGN, "dv_conv_igemm: out_ld/out_coff must be multiples of 4");
   cudaStream_t s = as_stream(stream);
   const bool tc_ok = conv_tc_supported(p) != 0;
+  const bool halo_ok = conv_halo_supported(p) != 0;
   if (p.impl == 2) DV_REQUIRE(tc_ok, DV_EUNSUPPORTED, "dv_conv_igemm: tcgen05 path does not support this shape");
+  if (p.impl == 3) DV_REQUIRE(halo_ok, DV_EUNSUPPORTED, "dv_conv_igemm: streaming-halo path does not support this shape");
+  if (p.impl == 3 || (p.impl == 0 && halo_ok && halo_enabled())) return conv_halo_launch(p, s);
   if (tc_ok && p.impl != 1) return conv_tc_launch(p, s);
   return (p.dtype == DV_F32) ? launch_simt<float>(p, g, s) : launch_simt<__nv_bfloat16>(p, g, s);
 }

@@ -97,7 +97,8 @@ int dv_ddpm_step(const dv_ddpm_step_params* p, dv_stream_t stream);
  * (`add`, same layout as out); DV_EPI_SHUFFLE_SILU writes SiLU(v) to the 2x-upsampled tensor
  * [n][2H][2W][Cout/4] with weight rows pre-ordered [(i,j)][c].
  * out_ld / out_coff let several convolutions write channel slices of one tensor (K4).
- * impl: 0 = auto (tcgen05 when the shape qualifies, else SIMT), 1 = force SIMT, 2 = force tcgen05.
+ * impl: 0 = auto (tensor cores when the shape qualifies, else SIMT), 1 = force SIMT, 2 = force the per-tap
+ * tcgen05 kernel, 3 = force the streaming-halo tcgen05 kernel (3x3, Cout 64/128, W >= 32).
  */
 enum { DV_CONV_NORMAL = 0, DV_CONV_UNSHUFFLE = 1, DV_CONV_NCDHW_F32_IN = 2 };
 enum { DV_EPI_STORE = 0, DV_EPI_SHUFFLE_SILU = 1 };

@@ -432,3 +432,40 @@ def test_im2col_patch_matrix(dtype):
     ref = cols.permute(0, 2, 3, 4, 5, 1).reshape(B * T * H * W, k * k * C)
     assert rel_err(out[:, :k * k * C], ref.to(dtype)) == 0.0
     assert float(out[:, k * k * C:].abs().max()) == 0.0
+
+
+HALO_CASES = [
+    dict(B=1, T=1, H=64, W=64, C=(64,), Co=64),
+    dict(B=2, T=3, H=64, W=64, C=(64,), Co=64, stats=True),          # frame and sample boundaries inside tiles
+    dict(B=2, T=2, H=64, W=64, C=(64, 64), Co=64, stats=True),       # two sources
+    dict(B=1, T=4, H=32, W=32, C=(128, 64), Co=128, stats=True),     # 32x32, N=128
+    dict(B=3, T=2, H=32, W=32, C=(64,), Co=64, stats=True),
+    dict(B=1, T=2, H=16, W=64, C=(64,), Co=128),                     # non-square
+]
+
+
+@pytest.mark.parametrize("case", HALO_CASES)
+def test_conv_streaming_halo_matches_conv3d(case):
+    dtype = torch.bfloat16
+    B, T, H, W, Co = (case[x] for x in ("B", "T", "H", "W", "Co"))
+    rows = B * T * H * W
+    xs = [rnd(rows, c, dtype=dtype, seed=10 + i) for i, c in enumerate(case["C"])]
+    cin = sum(case["C"])
+    wp = rnd(Co, 9 * cin, seed=20, scale=1 / math.sqrt(cin * 9)).to(dtype)
+    bias = rnd(Co, seed=21)
+    G = 8
+    stats = torch.zeros(B, G, 2, dtype=torch.float64, device=dev()) if case.get("stats") else None
+    out = torch.full((rows, Co), 9.0, dtype=dtype, device=dev())
+    conv(xs, wp, bias, out, n_img=B * T, frames=T, H=H, W=W, k=3, stats=stats, groups=G, impl=3)
+    xin = torch.cat([cl_to_ncdhw(x, B, T, H, W) for x in xs], dim=1)
+    w_ref = wp.float().reshape(Co, 3, 3, cin).permute(0, 3, 1, 2)[:, :, None]
+    ref = ncdhw_to_cl(F.conv3d(xin, w_ref, bias, padding=(0, 1, 1)))
+    assert rel_err(out, ref) < 1e-2
+    if stats is not None:
+        yq = ref.to(dtype).float().reshape(B, -1, G, Co // G)
+        s1, s2 = yq.sum(dim=(1, 3)).double(), (yq * yq).sum(dim=(1, 3)).double()
+        assert rel_err(stats[..., 1], s2) < 2e-3
+        assert float((stats[..., 0] - s1).abs().max()) < 2e-2 * float(s2.max().sqrt())
+    out2 = torch.empty_like(out)
+    conv(xs, wp, bias, out2, n_img=B * T, frames=T, H=H, W=W, k=3, impl=2)
+    assert rel_err(out, out2) < 6e-3
