@@ -53,6 +53,17 @@ class XattnParams(C.Structure):
                 ("dtype", i32)]
 
 
+class XattnFoldPrepParams(C.Structure):
+    _fields_ = [("kv", vp), ("null_kv", vp), ("wq", vp), ("wout", vp), ("g", vp), ("mq", vp), ("u", vp), ("cs", vp),
+                ("B", i32), ("C", i32), ("heads", i32), ("dh", i32), ("n_ctx", i32), ("kv_ld", i64), ("k_off", i32),
+                ("v_off", i32), ("scale", f32)]
+
+
+class XattnFoldParams(C.Structure):
+    _fields_ = [("x", vp), ("out", vp), ("mq", vp), ("u", vp), ("cs", vp), ("g2", vp), ("B", i32), ("P", i64),
+                ("C", i32), ("heads", i32), ("nk", i32), ("eps_in", f32), ("eps_out", f32)]
+
+
 class AttnMqaParams(C.Structure):
     _fields_ = [("q", vp), ("kv", vp), ("out", vp), ("null_kv", vp), ("bias", vp), ("S", i64), ("n", i32),
                 ("heads", i32), ("dh", i32), ("scale", f32), ("dtype", i32)]
@@ -90,6 +101,7 @@ class ToOutParams(C.Structure):
 ENTRY_POINTS = {
     "dv_ddpm_step": DdpmStepParams, "dv_conv_igemm": ConvParams, "dv_gn_apply": GnApplyParams,
     "dv_gn_stats": GnStatsParams, "dv_layernorm": LayerNormParams, "dv_xattn_core": XattnParams,
+    "dv_xattn_fold_prep": XattnFoldPrepParams, "dv_xattn_fold": XattnFoldParams,
     "dv_attn_mqa": AttnMqaParams, "dv_time_embed": TimeEmbedParams, "dv_linear_small": LinearSmallParams,
     "dv_cond_tokens": CondTokensParams, "dv_to_out": ToOutParams, "dv_im2col_init": Im2colParams,
 }

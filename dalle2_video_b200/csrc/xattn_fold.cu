@@ -1,0 +1,452 @@
+// K5 fused — the whole CrossAttention block over a short conditioning context as ONE tcgen05 kernel
+// (see include/dv_b200.h for the algebra and the reference call sites it replaces).
+//
+// Per 128-token tile (one token per TMEM lane / epilogue thread):
+//   TMA     x tile [128][C] bf16 (kept in shared memory: GEMM operand, LayerNorm statistics and residual)
+//   MMA 1   raw[128][64]  = x . Mq^T            (M=128, N=64, K=C)        -> TMEM columns [0,64)
+//   threads logits = rstd_x * (raw - mean_x * cs);  per-head softmax over nk keys;  P (bf16) -> shared memory
+//   MMA 2   y[128][C]     = P . U^T             (M=128, N=min(C,256), K=64) -> TMEM columns [0,C)
+//   threads LayerNorm(y) * g2 + x -> bf16 -> shared-memory slab -> TMA store
+// HBM traffic is the minimum: read x once, write out once; the 512-wide q / attention-output tensors of the
+// unfused formulation never exist.
+#include "tc_common.cuh"
+
+namespace dv {
+
+// ------------------------------------------------------------------------------------------ prep
+__global__ void __launch_bounds__(256) xattn_fold_prep_kernel(dv_xattn_fold_prep_params p) {
+  __shared__ float ks[8][64];
+  __shared__ float vs[8][64];
+  __shared__ float cs_part[8];
+  const int h = blockIdx.x, b = blockIdx.y, nk = p.n_ctx + 1, inner = p.heads * p.dh;
+  for (int i = threadIdx.x; i < nk * p.dh; i += blockDim.x) {
+    const int j = i / p.dh, d = i % p.dh;
+    if (j == 0) {
+      ks[0][d] = p.null_kv[d];
+      vs[0][d] = p.null_kv[p.dh + d];
+    } else {
+      const float* row = p.kv + ((int64_t)b * p.n_ctx + (j - 1)) * p.kv_ld;
+      ks[j][d] = row[p.k_off + h * p.dh + d];
+      vs[j][d] = row[p.v_off + h * p.dh + d];
+    }
+  }
+  if (threadIdx.x < 8) cs_part[threadIdx.x] = 0.f;
+  __syncthreads();
+  __nv_bfloat16* mq = reinterpret_cast<__nv_bfloat16*>(p.mq) + (int64_t)b * 64 * p.C;
+  __nv_bfloat16* u = reinterpret_cast<__nv_bfloat16*>(p.u) + (int64_t)b * p.C * 64;
+  float csl[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) csl[j] = 0.f;
+  for (int c = threadIdx.x; c < p.C; c += blockDim.x) {
+    float am[8], au[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { am[j] = 0.f; au[j] = 0.f; }
+    for (int d = 0; d < p.dh; ++d) {
+      const float wq = p.wq[(int64_t)(h * p.dh + d) * p.C + c];
+      const float wo = p.wout[(int64_t)c * inner + h * p.dh + d];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (j < nk) {
+          am[j] = fmaf(ks[j][d], wq, am[j]);
+          au[j] = fmaf(vs[j][d], wo, au[j]);
+        }
+      }
+    }
+    const float gs = p.scale * p.g[c];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (j < nk) {
+        const __nv_bfloat16 m = __float2bfloat16_rn(gs * am[j]);
+        mq[(int64_t)(h * nk + j) * p.C + c] = m;
+        csl[j] += __bfloat162float(m);
+        u[(int64_t)c * 64 + h * nk + j] = __float2bfloat16_rn(au[j]);
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float s = warp_sum(csl[j]);
+    if ((threadIdx.x & 31) == 0 && j < nk) atomicAdd(&cs_part[j], s);
+  }
+  __syncthreads();
+  if (threadIdx.x < nk) p.cs[(int64_t)b * 64 + h * nk + threadIdx.x] = cs_part[threadIdx.x];
+}
+
+// ------------------------------------------------------------------------------------------ main kernel
+constexpr int XF_THREADS = 192;  // warp 0 TMA, warp 1 MMA, warps 2-5 softmax + epilogue (one token per thread)
+
+struct XfoldParams {
+  int C, chunks, NB, xs;  // channels, C/64, N of MMA 2 (min(C,256)), X stages
+  int heads, nk;
+  int64_t tiles, tiles_per_sample;
+  const float* cs;
+  const float* g2;
+  float eps_in, eps_out;
+};
+
+__device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void xf_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+template <int NK>
+__global__ void __launch_bounds__(XF_THREADS, 1)
+xattn_fold_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_mq,
+                  const __grid_constant__ CUtensorMap map_u, const __grid_constant__ CUtensorMap map_out,
+                  const XfoldParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const uint32_t x_stage_bytes = (uint32_t)p.chunks * 16384;
+  uint8_t* x_s = smem;                                           // [xs][chunks][128 rows x 128 B]
+  uint8_t* mq_s = x_s + (size_t)p.xs * x_stage_bytes;            // [chunks][64 rows x 128 B]
+  uint8_t* u_s = mq_s + (size_t)p.chunks * 8192;                 // [C rows x 128 B]
+  uint8_t* p_s = u_s + (size_t)p.C * 128;                        // [128 rows x 128 B]  P, then output slab
+  float* cs_s = reinterpret_cast<float*>(p_s + 16384);           // [64]
+  float* g2_s = cs_s + 64;                                       // [C]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(g2_s + p.C);
+  uint64_t* x_full = bars;        // [2]
+  uint64_t* x_empty = bars + 2;   // [2]
+  uint64_t* w_full = bars + 4;
+  uint64_t* w_free = bars + 5;
+  uint64_t* s_full = bars + 6;
+  uint64_t* p_ready = bars + 7;
+  uint64_t* y_full = bars + 8;
+  uint64_t* acc_free = bars + 9;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t tmem_cols = p.C < 64 ? 64u : (uint32_t)p.C;  // 64 / 128 / 256 / 512
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_x);
+    tma_prefetch_desc(&map_mq);
+    tma_prefetch_desc(&map_u);
+    tma_prefetch_desc(&map_out);
+    for (int s = 0; s < 2; ++s) { mbar_init(&x_full[s], 1); mbar_init(&x_empty[s], 4); }
+    mbar_init(w_full, 1);
+    mbar_init(w_free, 1);
+    mbar_init(s_full, 1);
+    mbar_init(p_ready, 4);
+    mbar_init(y_full, 1);
+    mbar_init(acc_free, 4);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  for (int i = threadIdx.x; i < p.C; i += blockDim.x) g2_s[i] = p.g2[i];
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int64_t per_cta = (p.tiles + gridDim.x - 1) / gridDim.x;
+  const int64_t tile_begin = (int64_t)blockIdx.x * per_cta;
+  const int64_t tile_end = tile_begin + per_cta < p.tiles ? tile_begin + per_cta : p.tiles;
+
+  if (warp == 0) {
+    // ================================================================ TMA producer
+    if (elect_one()) {
+      int cur = -1;
+      int t = 0;
+      for (int64_t tile = tile_begin; tile < tile_end; ++tile, ++t) {
+        const int b = (int)(tile / p.tiles_per_sample);
+        if (b != cur) {
+          if (t > 0) mbar_wait(w_free, (uint32_t)((t - 1) & 1));  // every MMA that read Mq / U has retired
+          mbar_expect_tx(w_full, (uint32_t)(p.chunks * 8192 + p.C * 128));
+          for (int c = 0; c < p.chunks; ++c) tma_load_3d(&map_mq, w_full, mq_s + (size_t)c * 8192, c * 64, 0, b);
+          for (int r0 = 0; r0 < p.C; r0 += p.NB) tma_load_3d(&map_u, w_full, u_s + (size_t)r0 * 128, 0, r0, b);
+          cur = b;
+        }
+        const int st = t % p.xs;
+        mbar_wait(&x_empty[st], (uint32_t)(((t / p.xs) & 1) ^ 1));
+        mbar_expect_tx(&x_full[st], x_stage_bytes);
+        for (int c = 0; c < p.chunks; ++c)
+          tma_load_2d(&map_x, &x_full[st], x_s + (size_t)st * x_stage_bytes + (size_t)c * 16384, c * 64,
+                      (int)(tile * TC_BM));
+      }
+    }
+  } else if (warp == 1) {
+    // ================================================================ MMA issuer
+    const uint32_t idesc1 = make_idesc(64), idesc2 = make_idesc(p.NB);
+    int cur = -1, wloads = 0, t = 0;
+    for (int64_t tile = tile_begin; tile < tile_end; ++tile, ++t) {
+      const int b = (int)(tile / p.tiles_per_sample);
+      if (b != cur) {
+        mbar_wait(w_full, (uint32_t)(wloads & 1));
+        ++wloads;
+        cur = b;
+      }
+      const int st = t % p.xs;
+      mbar_wait(&x_full[st], (uint32_t)((t / p.xs) & 1));
+      if (t > 0) mbar_wait(acc_free, (uint32_t)((t - 1) & 1));  // previous tile's y has been read out of TMEM
+      tc_fence_after();
+      if (elect_one()) {
+        for (int c = 0; c < p.chunks; ++c) {
+          const uint64_t ad = make_smem_desc(smem_u32(x_s + (size_t)st * x_stage_bytes + (size_t)c * 16384));
+          const uint64_t bd = make_smem_desc(smem_u32(mq_s + (size_t)c * 8192));
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk)
+            umma_f16(tmem_base, ad + (uint64_t)(kk * 2), bd + (uint64_t)(kk * 2), idesc1, (c | kk) != 0);
+        }
+        umma_commit(s_full);
+      }
+      __syncwarp();
+      mbar_wait(p_ready, (uint32_t)(t & 1));  // P written (and the logits read out of TMEM)
+      tc_fence_after();
+      if (elect_one()) {
+        const uint64_t ad = make_smem_desc(smem_u32(p_s));
+        for (int n0 = 0; n0 < p.C; n0 += p.NB) {
+          const uint64_t bd = make_smem_desc(smem_u32(u_s + (size_t)n0 * 128));
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk)
+            umma_f16(tmem_base + (uint32_t)n0, ad + (uint64_t)(kk * 2), bd + (uint64_t)(kk * 2), idesc2, kk != 0);
+        }
+        umma_commit(y_full);
+        umma_commit(w_free);
+      }
+      __syncwarp();
+    }
+  } else {
+    // ================================================================ softmax + epilogue: one token per thread
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int et = (warp - 2) * 32 + lane;
+    const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
+    int cur = -1, t = 0;
+    for (int64_t tile = tile_begin; tile < tile_end; ++tile, ++t) {
+      const int b = (int)(tile / p.tiles_per_sample);
+      if (b != cur) {
+        xf_bar();
+        if (et < 64) cs_s[et] = p.cs[(int64_t)b * 64 + et];
+        xf_bar();
+        cur = b;
+      }
+      const int st = t % p.xs;
+      const uint8_t* xrow = x_s + (size_t)st * x_stage_bytes + (size_t)row * 128;
+      mbar_wait(&x_full[st], (uint32_t)((t / p.xs) & 1));
+      // ---- LayerNorm statistics of the input row (biased variance, fp32)
+      float sx = 0.f, sxx = 0.f;
+      for (int c = 0; c < p.chunks; ++c) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const uint4 raw = *reinterpret_cast<const uint4*>(xrow + (size_t)c * 16384 + ((j ^ (row & 7)) * 16));
+          const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float a = __low2float(h2[e]), bb = __high2float(h2[e]);
+            sx += a + bb;
+            sxx = fmaf(a, a, fmaf(bb, bb, sxx));
+          }
+        }
+      }
+      const float mean_x = sx / (float)p.C;
+      const float rstd_x = rsqrtf(fmaxf(sxx / (float)p.C - mean_x * mean_x, 0.f) + p.eps_in);
+      // ---- logits -> per-head softmax -> P
+      mbar_wait(s_full, (uint32_t)(t & 1));
+      tc_fence_after();
+      float lg[64];
+      {
+        uint32_t r0[32], r1[32];
+        tmem_ld32(t_lane, r0);
+        tmem_ld32(t_lane + 32, r1);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          lg[j] = rstd_x * (__uint_as_float(r0[j]) - mean_x * cs_s[j]);
+          lg[32 + j] = rstd_x * (__uint_as_float(r1[j]) - mean_x * cs_s[32 + j]);
+        }
+      }
+      // 8 heads x NK keys, NK compile-time so that the logits stay in registers
+#pragma unroll
+      for (int h = 0; h < 8; ++h) {
+        float m = lg[h * NK];
+#pragma unroll
+        for (int j = 1; j < NK; ++j) m = fmaxf(m, lg[h * NK + j]);
+        float s = 0.f;
+#pragma unroll
+        for (int j = 0; j < NK; ++j) { lg[h * NK + j] = __expf(lg[h * NK + j] - m); s += lg[h * NK + j]; }
+        const float inv = 1.0f / s;
+#pragma unroll
+        for (int j = 0; j < NK; ++j) lg[h * NK + j] *= inv;
+      }
+#pragma unroll
+      for (int j = 8 * NK; j < 64; ++j) lg[j] = 0.f;
+      {
+        uint8_t* prow = p_s + (size_t)row * 128;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          uint4 pk;
+          __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&pk);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) h2[e] = __floats2bfloat162_rn(lg[j * 8 + 2 * e], lg[j * 8 + 2 * e + 1]);
+          *reinterpret_cast<uint4*>(prow + ((j ^ (row & 7)) * 16)) = pk;
+        }
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_ready);
+      // ---- y: LayerNorm statistics (pass 1), then normalise + gain + residual (pass 2)
+      mbar_wait(y_full, (uint32_t)(t & 1));
+      tc_fence_after();
+      float sy = 0.f, syy = 0.f;
+      for (int c0 = 0; c0 < p.C; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld32(t_lane + (uint32_t)c0, r);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float y = __uint_as_float(r[j]);
+          sy += y;
+          syy = fmaf(y, y, syy);
+        }
+      }
+      const float mean_y = sy / (float)p.C;
+      const float rstd_y = rsqrtf(fmaxf(syy / (float)p.C - mean_y * mean_y, 0.f) + p.eps_out);
+      for (int s0 = 0; s0 < p.C; s0 += 64) {
+        // the previous slab's TMA store (and, for the first slab, MMA 2's read of P) is done with p_s
+        if (et == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        xf_bar();
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          const int c0 = s0 + half * 32;
+          uint32_t r[32];
+          tmem_ld32(t_lane + (uint32_t)c0, r);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int chunk = half * 4 + j;  // 16-byte chunk of the 64-column slab
+            const uint4 xr = *reinterpret_cast<const uint4*>(xrow + (size_t)(s0 / 64) * 16384 + ((chunk ^ (row & 7)) * 16));
+            const __nv_bfloat162* xh = reinterpret_cast<const __nv_bfloat162*>(&xr);
+            uint4 pk;
+            __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&pk);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int c = c0 + j * 8 + 2 * e;
+              const float o0 = (__uint_as_float(r[j * 8 + 2 * e]) - mean_y) * rstd_y * g2_s[c] + __low2float(xh[e]);
+              const float o1 = (__uint_as_float(r[j * 8 + 2 * e + 1]) - mean_y) * rstd_y * g2_s[c + 1] + __high2float(xh[e]);
+              oh[e] = __floats2bfloat162_rn(o0, o1);
+            }
+            *reinterpret_cast<uint4*>(p_s + (size_t)row * 128 + ((chunk ^ (row & 7)) * 16)) = pk;
+          }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        xf_bar();
+        if (et == 0) {
+          tma_store_2d(&map_out, p_s, s0, (int)(tile * TC_BM));
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+      }
+      // release TMEM and the x stage; make sure the last store has read p_s before the next tile writes P
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(acc_free);
+        mbar_arrive(&x_empty[st]);
+      }
+      if (et == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      xf_bar();
+    }
+    if (et == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+  }
+}
+
+}  // namespace dv
+
+extern "C" int dv_xattn_fold_prep(const dv_xattn_fold_prep_params* p, dv_stream_t stream) {
+  using namespace dv;
+  DV_REQUIRE(p && p->kv && p->null_kv && p->wq && p->wout && p->g && p->mq && p->u && p->cs, DV_EINVAL,
+             "dv_xattn_fold_prep: null pointer");
+  DV_REQUIRE(p->B > 0 && p->C > 0 && p->heads > 0 && p->dh == 64 && p->n_ctx >= 0 && p->n_ctx <= 7, DV_EUNSUPPORTED,
+             "dv_xattn_fold_prep: needs dim_head 64 and at most 7 context tokens");
+  DV_REQUIRE(p->heads * (p->n_ctx + 1) <= 64, DV_EUNSUPPORTED, "dv_xattn_fold_prep: heads*(n_ctx+1) must be <= 64");
+  dim3 grid(p->heads, p->B);
+  xattn_fold_prep_kernel<<<grid, 256, 0, as_stream(stream)>>>(*p);
+  DV_CHECK_LAUNCH("dv_xattn_fold_prep");
+  return DV_OK;
+}
+
+extern "C" int dv_xattn_fold(const dv_xattn_fold_params* p, dv_stream_t stream) {
+  using namespace dv;
+  DV_REQUIRE(p && p->x && p->out && p->mq && p->u && p->cs && p->g2, DV_EINVAL, "dv_xattn_fold: null pointer");
+  DV_REQUIRE(p->C == 64 || p->C == 128 || p->C == 256, DV_EUNSUPPORTED,
+             "dv_xattn_fold: C must be 64, 128 or 256 (got %d)", p->C);
+  DV_REQUIRE(p->heads == 8 && (p->nk == 3 || p->nk == 7), DV_EUNSUPPORTED,
+             "dv_xattn_fold: built for 8 heads and 2 or 6 context tokens (+ null key), got heads=%d nk=%d", p->heads, p->nk);
+  DV_REQUIRE(p->B > 0 && p->P > 0 && p->P % TC_BM == 0, DV_EUNSUPPORTED,
+             "dv_xattn_fold: tokens per sample (%lld) must be a multiple of 128", (long long)p->P);
+  DV_REQUIRE(p->heads > 0 && p->nk > 0 && p->heads * p->nk <= 64, DV_EUNSUPPORTED, "dv_xattn_fold: heads*nk must be <= 64");
+  DV_REQUIRE(aligned16(p->x) && aligned16(p->out) && aligned16(p->mq) && aligned16(p->u), DV_EALIGN,
+             "dv_xattn_fold: tensors must be 16-byte aligned");
+  XfoldParams k;
+  memset(&k, 0, sizeof(k));
+  k.C = p->C;
+  k.chunks = p->C / 64;
+  k.NB = p->C < 256 ? p->C : 256;
+  k.xs = p->C <= 256 ? 2 : 1;
+  k.heads = p->heads;
+  k.nk = p->nk;
+  k.tiles_per_sample = p->P / TC_BM;
+  k.tiles = k.tiles_per_sample * p->B;
+  k.cs = p->cs;
+  k.g2 = p->g2;
+  k.eps_in = p->eps_in;
+  k.eps_out = p->eps_out;
+  const int64_t rows = (int64_t)p->B * p->P;
+  CUtensorMap mx, mm, mu, mo;
+  int rc;
+  {
+    uint64_t dims[2] = {(uint64_t)p->C, (uint64_t)rows};
+    uint64_t strides[1] = {(uint64_t)p->C * 2};
+    uint32_t box[2] = {64, TC_BM};
+    if ((rc = encode_map(&mx, p->x, 2, dims, strides, box)) != DV_OK) return rc;
+    if ((rc = encode_map(&mo, p->out, 2, dims, strides, box)) != DV_OK) return rc;
+  }
+  {
+    uint64_t dims[3] = {(uint64_t)p->C, 64, (uint64_t)p->B};
+    uint64_t strides[2] = {(uint64_t)p->C * 2, (uint64_t)p->C * 2 * 64};
+    uint32_t box[3] = {64, 64, 1};
+    if ((rc = encode_map(&mm, p->mq, 3, dims, strides, box)) != DV_OK) return rc;
+  }
+  {
+    uint64_t dims[3] = {64, (uint64_t)p->C, (uint64_t)p->B};
+    uint64_t strides[2] = {128, (uint64_t)p->C * 128};
+    uint32_t box[3] = {64, (uint32_t)k.NB, 1};
+    if ((rc = encode_map(&mu, p->u, 3, dims, strides, box)) != DV_OK) return rc;
+  }
+  const size_t smem = (size_t)k.xs * k.chunks * 16384 + (size_t)k.chunks * 8192 + (size_t)p->C * 128 + 16384 +
+                     64 * 4 + (size_t)p->C * 4 + 256 + 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(xattn_fold_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(xattn_fold_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    DV_REQUIRE(e == cudaSuccess, DV_ECUDA, "dv_xattn_fold: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  static int sm_count = 0;
+  if (!sm_count) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
+    if (sm_count <= 0) sm_count = 148;
+  }
+  const int grid = (int)(k.tiles < sm_count ? k.tiles : sm_count);
+  if (p->nk == 7)
+    xattn_fold_kernel<7><<<grid, XF_THREADS, smem, as_stream(stream)>>>(mx, mm, mu, mo, k);
+  else
+    xattn_fold_kernel<3><<<grid, XF_THREADS, smem, as_stream(stream)>>>(mx, mm, mu, mo, k);
+  DV_CHECK_LAUNCH("dv_xattn_fold");
+  return DV_OK;
+}

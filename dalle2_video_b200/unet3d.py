@@ -253,6 +253,7 @@ class Unet3D(nn.Module):
         self.checkpoint_during_training = checkpoint_during_training
 
         self.compute_dtype = None  # None: follow autocast (bf16) else fp32; or torch.float32 / torch.bfloat16
+        self.fuse_short_context_attention = True  # bf16: folded single-kernel CrossAttention for <= 7 keys
         self._engines = {}
         self._param_version = None
 
@@ -795,6 +796,24 @@ class _Engine:
         kind, idx = self.kv_idx[id(m)]
         kv = self.kv[kind]
         n_ctx = kv.shape[1]
+        if (self.dtype == torch.bfloat16 and self.u.fuse_short_context_attention and C in (64, 128, 256)
+                and P % 128 == 0 and heads == 8 and dh == 64 and (n_ctx + 1) in (3, 7)):
+            # short context (time + video tokens): the whole block is one tcgen05 kernel on per-sample folded
+            # matrices (include/dv_b200.h, "K5 fused"); the matrices are rebuilt every step (time tokens change)
+            mq = self._zeros(self.B, 64, C, dtype=torch.bfloat16)
+            uu = self._zeros(self.B, C, 64, dtype=torch.bfloat16)
+            cs = self._zeros(self.B, 64)
+            self._op("dv_xattn_fold_prep", L.XattnFoldPrepParams(
+                kv=kv.data_ptr(), null_kv=self._f32(ca.null_kv).data_ptr(), wq=self._f32(ca.to_q.weight).data_ptr(),
+                wout=self._f32(ca.to_out[0].weight).data_ptr(), g=self._f32(ca.norm.g).data_ptr(), mq=mq.data_ptr(),
+                u=uu.data_ptr(), cs=cs.data_ptr(), B=self.B, C=C, heads=heads, dh=dh, n_ctx=n_ctx, kv_ld=kv.shape[2],
+                k_off=idx * 2 * inner, v_off=idx * 2 * inner + inner, scale=float(dh ** -0.5)))
+            self._op("dv_xattn_fold", L.XattnFoldParams(
+                x=hact.ptr, out=hact.ptr, mq=mq.data_ptr(), u=uu.data_ptr(), cs=cs.data_ptr(),
+                g2=self._f32(ca.to_out[1].g).data_ptr(), B=self.B, P=P, C=C, heads=heads, nk=n_ctx + 1, eps_in=1e-5,
+                eps_out=self._post_proj_eps()))
+            self.n_tc += 1
+            return
         xn = self._new_act(rows, C)
         self._op("dv_layernorm", L.LayerNormParams(x=hact.ptr, out=xn.ptr, residual=None,
                                                    g=self._f32(ca.norm.g).data_ptr(), beta=None, rows=rows, C=C,

@@ -222,6 +222,49 @@ typedef struct {
 int dv_xattn_core(const dv_xattn_params* p, dv_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * K5 fused  whole CrossAttention block for a SHORT context (n_ctx + 1 null key <= 8; the 2 time + 4 video
+ * tokens of every outer ResnetBlock3D, :852-855) in one tcgen05 kernel:
+ *     out = LayerNorm_g2( to_out( softmax_h( scale * to_q(LayerNorm_g(x)) . K_h ) V_h ) ) + x      (:192-201)
+ * using the per-sample algebraic fold (exact in real arithmetic):
+ *     logits[h,j] = rstd_x * ( x . Mq[h*nk+j] - mean_x * cs[h*nk+j] ),  Mq[hj][c] = scale * g[c] * sum_d Wq[h*dh+d][c] K[h][j][d]
+ *     y[c]        = sum_hj p[hj] * U[c][hj],                            U[c][hj]  = sum_d Wout[c][h*dh+d] V[h][j][d]
+ * dv_xattn_fold_prep builds Mq / cs / U for one layer from the K/V projections of the conditioning tokens
+ * (per step: the time tokens change); dv_xattn_fold applies the block to every token in place.
+ * The unfused FLOP count of the reference formulation (2 Linear layers of width 512 per token) is NOT
+ * performed; bench.py keeps reporting the reference's algorithmic FLOPs separately from kernel FLOPs.
+ */
+typedef struct {
+  const float* kv;       /* as dv_xattn_params.kv */
+  const float* null_kv;  /* [2][dh] */
+  const float* wq;       /* to_q.weight  [heads*dh][C] float32 */
+  const float* wout;     /* to_out.0.weight [C][heads*dh] float32 */
+  const float* g;        /* norm.g [C] */
+  void* mq;              /* out: bf16 [B][64][C]   rows hj >= heads*nk are zero */
+  void* u;               /* out: bf16 [B][C][64]   cols hj >= heads*nk are zero */
+  float* cs;             /* out: float32 [B][64]   sum over c of the bf16-rounded Mq rows */
+  int B, C, heads, dh, n_ctx;
+  int64_t kv_ld;
+  int k_off, v_off;
+  float scale;
+} dv_xattn_fold_prep_params;
+int dv_xattn_fold_prep(const dv_xattn_fold_prep_params* p, dv_stream_t stream);
+
+typedef struct {
+  const void* x;    /* bf16 [B][P][C] */
+  void* out;        /* bf16 [B][P][C]; may alias x */
+  const void* mq;   /* bf16 [B][64][C] */
+  const void* u;    /* bf16 [B][C][64] */
+  const float* cs;  /* [B][64] */
+  const float* g2;  /* to_out.1.g [C] */
+  int B;
+  int64_t P;        /* tokens per sample, multiple of 128 */
+  int C;            /* 64, 128, 256 or 512 */
+  int heads, nk;    /* heads * nk <= 64; nk = n_ctx + 1 */
+  float eps_in, eps_out;
+} dv_xattn_fold_params;
+int dv_xattn_fold(const dv_xattn_fold_params* p, dv_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
  * K6  multi-query self-attention, flash style (never materialises the n x (n+1) logits).
  * Replaces Attention.forward between to_q/to_kv and to_out (external dalle2_pytorch==1.14.2,
  * SURVEY.md A.3; built :424-432, called :921-922): `heads` query heads share ONE key/value head;

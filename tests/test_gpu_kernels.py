@@ -469,3 +469,37 @@ def test_conv_streaming_halo_matches_conv3d(case):
     out2 = torch.empty_like(out)
     conv(xs, wp, bias, out2, n_img=B * T, frames=T, H=H, W=W, k=3, impl=2)
     assert rel_err(out, out2) < 6e-3
+
+
+@pytest.mark.parametrize("C,P,B,n_ctx", [(64, 256, 2, 6), (128, 1024, 1, 6), (256, 384, 3, 6), (64, 128, 2, 2)])
+def test_fused_folded_cross_attention_block(C, P, B, n_ctx):
+    """dv_xattn_fold_prep + dv_xattn_fold == CrossAttention(x, ctx) + x of the reference (dalle2_video.py:192-201)."""
+    from oracle.primitives import CrossAttention
+    torch.manual_seed(0)
+    ca = CrossAttention(dim=C, context_dim=32).to(dev())
+    with torch.no_grad():
+        ca.norm.g.add_(0.1 * torch.randn(C, device=dev()))
+        ca.to_out[1].g.add_(0.1 * torch.randn(C, device=dev()))
+    x = rnd(B, P, C, dtype=torch.bfloat16, seed=1)
+    ctx = rnd(B, n_ctx, 32, seed=2)
+    with torch.no_grad():
+        ref = ca(x.float(), ctx) + x.float()
+        kv = F.linear(ctx, ca.to_kv.weight).contiguous()  # [B][n_ctx][1024]: k (8x64) then v (8x64)
+    mq = torch.zeros(B, 64, C, dtype=torch.bfloat16, device=dev())
+    uu = torch.zeros(B, C, 64, dtype=torch.bfloat16, device=dev())
+    cs = torch.zeros(B, 64, device=dev())
+    wq, wo = ca.to_q.weight.detach().contiguous(), ca.to_out[0].weight.detach().contiguous()
+    g, g2, nkv = ca.norm.g.detach(), ca.to_out[1].g.detach(), ca.null_kv.detach().contiguous()
+    L.call("dv_xattn_fold_prep", L.XattnFoldPrepParams(
+        kv=ptr(kv), null_kv=ptr(nkv), wq=ptr(wq), wout=ptr(wo), g=ptr(g), mq=ptr(mq), u=ptr(uu), cs=ptr(cs), B=B, C=C,
+        heads=8, dh=64, n_ctx=n_ctx, kv_ld=1024, k_off=0, v_off=512, scale=64 ** -0.5), stream())
+    out = torch.empty_like(x)
+    L.call("dv_xattn_fold", L.XattnFoldParams(x=ptr(x), out=ptr(out), mq=ptr(mq), u=ptr(uu), cs=ptr(cs), g2=ptr(g2), B=B,
+                                              P=P, C=C, heads=8, nk=n_ctx + 1, eps_in=1e-5, eps_out=1e-5), stream())
+    err = rel_err(out.reshape(B, P, C), ref)
+    assert err < 1.5e-2, err
+    # in place
+    x2 = x.clone()
+    L.call("dv_xattn_fold", L.XattnFoldParams(x=ptr(x2), out=ptr(x2), mq=ptr(mq), u=ptr(uu), cs=ptr(cs), g2=ptr(g2), B=B,
+                                              P=P, C=C, heads=8, nk=n_ctx + 1, eps_in=1e-5, eps_out=1e-5), stream())
+    assert torch.equal(x2, out)

@@ -128,7 +128,8 @@ def test_abi_struct_sizes_match_header(built_lib):
              "dv_layernorm_params": "LayerNormParams", "dv_xattn_params": "XattnParams",
              "dv_attn_mqa_params": "AttnMqaParams", "dv_time_embed_params": "TimeEmbedParams",
              "dv_linear_small_params": "LinearSmallParams", "dv_cond_tokens_params": "CondTokensParams",
-             "dv_to_out_params": "ToOutParams", "dv_im2col_params": "Im2colParams"}
+             "dv_to_out_params": "ToOutParams", "dv_im2col_params": "Im2colParams",
+             "dv_xattn_fold_prep_params": "XattnFoldPrepParams", "dv_xattn_fold_params": "XattnFoldParams"}
     src = '#include <stdio.h>\n#include "dv_b200.h"\nint main(){' + "".join(
         f'printf("{c} %zu\\n", sizeof({c}));' for c in names) + "return 0;}"
     with tempfile.TemporaryDirectory() as d:
