@@ -108,6 +108,10 @@ ENTRY_POINTS = {
 PLAIN_SYMBOLS = ("dv_version", "dv_last_error_string", "dv_device_sm_count", "dv_conv_uses_tcgen05")
 
 _lib = None
+_SYNC_EACH = bool(os.environ.get("DV_SYNC_EACH"))
+_SYNC_BEFORE = set(filter(None, os.environ.get("DV_SYNC_BEFORE", "").split(",")))  # debug aids
+_SKIP = set(filter(None, os.environ.get("DV_DEBUG_SKIP", "").split(",")))
+_SYNC_AFTER = set(filter(None, os.environ.get("DV_SYNC_AFTER", "").split(",")))
 launch_count = 0  # number of C-ABI kernel-enqueue calls made by this process (bench.py reports it)
 
 
@@ -139,10 +143,25 @@ def lib():
 def call(name: str, params, stream: int):
     """Enqueue one C-ABI op on the raw cudaStream_t `stream`; raise DvError on a non-zero return."""
     global launch_count
+    if name in _SKIP:
+        return
+    if name in _SYNC_BEFORE:
+        import torch
+        torch.cuda.synchronize()
     rc = getattr(lib(), name)(C.byref(params), vp(stream))
+    if name in _SYNC_AFTER:
+        import torch
+        torch.cuda.synchronize()
     if rc != 0:
         raise DvError(f"{name} failed ({rc}): {lib().dv_last_error_string().decode()}")
     launch_count += 1
+    if _SYNC_EACH:  # debug: DV_SYNC_EACH=1 pinpoints the op whose kernel faults
+        import torch
+        try:
+            torch.cuda.synchronize()
+        except Exception as e:  # noqa: BLE001
+            fields = {f[0]: getattr(params, f[0]) for f in params._fields_}
+            raise DvError(f"{name} faulted on the device: {e}\nparams: {fields}") from e
 
 
 def dtype_code(torch_dtype) -> int:

@@ -20,6 +20,8 @@
 // Tile = 256 consecutive Q (two M=128 MMAs share every weight tile), accumulators double-buffered in TMEM
 // (4*BN columns).  Warp roles: 0 = TMA producer, 1 = MMA issuer, 2-9 = epilogue (bias, GroupNorm partial sums,
 // bf16, shared-memory transpose, coalesced 16-byte row stores of the valid rows).
+#include <stdlib.h>
+
 #include "tc_common.cuh"
 
 namespace dv {
@@ -27,38 +29,42 @@ namespace dv {
 constexpr int HL_EPI_WARPS = 8;
 constexpr int HL_THREADS = 64 + 32 * HL_EPI_WARPS;
 constexpr int HL_TILE_Q = 256;
-constexpr int HL_A_STAGES = 2;
 
 struct HaloParams {
   int H, W, Wp, Hp1, n_img, frames;
   int c0_chunks, c1_chunks;
   int BN, NR;
-  int a_stage_bytes, b_stages;
+  int a_stage_bytes, a_stages, b_stages, out_bufs;
+  int b_resident;  // all weight stages fit in the ring: loaded once per CTA, never recycled
   int tiles_per_sample;
-  int64_t total_tiles;
+  int total_tiles;
+  uint32_t wp_magic;  // (off * wp_magic) >> 16 == off / Wp for off < Wp + 256 (checked on the host)
   const float* bias;
   __nv_bfloat16* out;
   double* stats;
   int groups, out_ld, out_coff;
+  long long* prof;  // optional [grid][16] cycle counters (debug, DV_HALO_PROFILE env)
 };
 
 __device__ __forceinline__ void hl_epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+#define HL_T0() const long long t0__ = clock64()
+#define HL_ACC(var) var += clock64() - t0__
 
 __global__ void __launch_bounds__(HL_THREADS, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
                  const __grid_constant__ CUtensorMap map_b, const HaloParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const uint32_t b_bytes = (uint32_t)p.BN * 128;
+  const uint32_t b_bytes = (uint32_t)p.BN * 128 * 3;  // one weight stage = the three taps of one filter row
   uint8_t* a_ring = smem;
-  uint8_t* b_ring = a_ring + (size_t)HL_A_STAGES * p.a_stage_bytes;
+  uint8_t* b_ring = a_ring + (size_t)p.a_stages * p.a_stage_bytes;
   uint8_t* stage_out = b_ring + (size_t)p.b_stages * b_bytes;          // 2 x [128 rows][128 B]
-  long long* rowpos = reinterpret_cast<long long*>(stage_out + 2 * 16384);  // 2 x [128]
+  int* rowpos = reinterpret_cast<int*>(stage_out + p.out_bufs * 16384);  // 2 x [128] output row of each staged row (-1: discard)
   float* bias_s = reinterpret_cast<float*>(rowpos + 256);                   // [128]
   float* sred = bias_s + 128;                                               // [64]
   uint64_t* full_a = reinterpret_cast<uint64_t*>(sred + 64);
-  uint64_t* empty_a = full_a + HL_A_STAGES;
-  uint64_t* full_b = empty_a + HL_A_STAGES;
+  uint64_t* empty_a = full_a + p.a_stages;
+  uint64_t* full_b = empty_a + p.a_stages;
   uint64_t* empty_b = full_b + p.b_stages;
   uint64_t* tmem_full = empty_b + p.b_stages;
   uint64_t* tmem_empty = tmem_full + 2;
@@ -71,7 +77,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
     tma_prefetch_desc(&map_a0);
     tma_prefetch_desc(&map_a1);
     tma_prefetch_desc(&map_b);
-    for (int s = 0; s < HL_A_STAGES; ++s) { mbar_init(&full_a[s], 1); mbar_init(&empty_a[s], 1); }
+    for (int s = 0; s < p.a_stages; ++s) { mbar_init(&full_a[s], 1); mbar_init(&empty_a[s], 1); }
     for (int s = 0; s < p.b_stages; ++s) { mbar_init(&full_b[s], 1); mbar_init(&empty_b[s], 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], HL_EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -89,16 +95,23 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int64_t per_cta = (p.total_tiles + gridDim.x - 1) / gridDim.x;
-  const int64_t tile_begin = (int64_t)blockIdx.x * per_cta;
-  const int64_t tile_end = tile_begin + per_cta < p.total_tiles ? tile_begin + per_cta : p.total_tiles;
+  const int per_cta = (p.total_tiles + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int tile_begin = (int)blockIdx.x * per_cta;
+  const int tile_end = tile_begin + per_cta < p.total_tiles ? tile_begin + per_cta : p.total_tiles;
   const int n_chunks = p.c0_chunks + p.c1_chunks;
-  // first valid output of sample b: frame b*T, y = 0, x = 0
-  auto tile_q0 = [&](int64_t tile, int* sample) -> int64_t {
-    const int b = (int)(tile / p.tiles_per_sample);
-    const int j = (int)(tile % p.tiles_per_sample);
-    *sample = b;
-    return ((int64_t)b * p.frames * p.Hp1 + 1) * p.Wp + 1 + (int64_t)j * HL_TILE_Q;
+  // All index arithmetic is 32-bit (the host checks that the padded index space fits) and divisions happen once
+  // per tile, never per row.  Tile j of sample b starts at the sample's first valid output (frame b*T, y=0, x=0).
+  struct TileGeo { int sample, q0, R0, x0r, r_lo, row_off; };
+  auto tile_geo = [&](int tile) -> TileGeo {
+    TileGeo g;
+    g.sample = tile / p.tiles_per_sample;
+    const int j = tile - g.sample * p.tiles_per_sample;
+    g.q0 = (g.sample * p.frames * p.Hp1 + 1) * p.Wp + 1 + j * HL_TILE_Q;
+    g.R0 = g.q0 / p.Wp;
+    g.x0r = g.q0 - g.R0 * p.Wp;
+    g.r_lo = g.R0 - (g.x0r >= 1 ? 1 : 2);          // padded row of Q0 - Wp - 1
+    g.row_off = g.q0 - g.r_lo * p.Wp;              // window row of Q0
+    return g;
   };
 
   if (warp == 0) {
@@ -106,31 +119,40 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
     if (elect_one()) {
       int sa = 0, sb = 0;
       uint32_t pa = 0, pb = 0;
-      for (int64_t tile = tile_begin; tile < tile_end; ++tile) {
-        int sample;
-        const int64_t q0 = tile_q0(tile, &sample);
-        const int64_t r_lo = (q0 - p.Wp - 1) / p.Wp;
+      long long w_a = 0, w_b = 0;
+      const long long tstart = clock64();
+      for (int tile = tile_begin; tile < tile_end; ++tile) {
+        const TileGeo g = tile_geo(tile);
+        const int n_lo = g.r_lo / p.Hp1, y_lo = g.r_lo - n_lo * p.Hp1;  // padded row -> (frame, raw y index)
         for (int ch = 0; ch < n_chunks; ++ch) {
           const int src = ch >= p.c0_chunks;
           const int c = src ? ch - p.c0_chunks : ch;
           const CUtensorMap* map = src ? &map_a1 : &map_a0;
-          mbar_wait(&empty_a[sa], pa ^ 1);
+          { HL_T0(); mbar_wait(&empty_a[sa], pa ^ 1); HL_ACC(w_a); }
           uint8_t* dst = a_ring + (size_t)sa * p.a_stage_bytes;
           mbar_expect_tx(&full_a[sa], (uint32_t)(p.NR * p.Wp * 128));
+          int n = n_lo, yr = y_lo;
           for (int r = 0; r < p.NR; ++r) {
-            const int64_t R = r_lo + r;
-            const int n = (int)(R / p.Hp1);
-            const int yy = (int)(R % p.Hp1) - 1;
-            tma_load_5d(map, &full_a[sa], dst + (size_t)r * p.Wp * 128, c * TC_BK, -1, yy, n, 0);
+            tma_load_5d(map, &full_a[sa], dst + (size_t)r * p.Wp * 128, c * TC_BK, -1, yr - 1, n, 0);
+            if (++yr == p.Hp1) { yr = 0; ++n; }
           }
-          if (++sa == HL_A_STAGES) { sa = 0; pa ^= 1; }
-          for (int tap = 0; tap < 9; ++tap) {
-            mbar_wait(&empty_b[sb], pb ^ 1);
-            mbar_expect_tx(&full_b[sb], b_bytes);
-            tma_load_2d(&map_b, &full_b[sb], b_ring + (size_t)sb * b_bytes, (tap * n_chunks + ch) * TC_BK, 0);
-            if (++sb == p.b_stages) { sb = 0; pb ^= 1; }
+          if (++sa == p.a_stages) { sa = 0; pa ^= 1; }
+          if (!p.b_resident || tile == tile_begin) {
+            for (int g3 = 0; g3 < 3; ++g3) {
+              { HL_T0(); mbar_wait(&empty_b[sb], pb ^ 1); HL_ACC(w_b); }
+              mbar_expect_tx(&full_b[sb], b_bytes);
+              for (int t3 = 0; t3 < 3; ++t3)
+                tma_load_2d(&map_b, &full_b[sb], b_ring + (size_t)sb * b_bytes + (size_t)t3 * p.BN * 128,
+                            ((g3 * 3 + t3) * n_chunks + ch) * TC_BK, 0);
+              if (++sb == p.b_stages) { sb = 0; pb ^= 1; }
+            }
           }
         }
+      }
+      if (p.prof) {
+        p.prof[blockIdx.x * 16 + 0] = clock64() - tstart;
+        p.prof[blockIdx.x * 16 + 1] = w_a;
+        p.prof[blockIdx.x * 16 + 2] = w_b;
       }
     }
   } else if (warp == 1) {
@@ -138,44 +160,57 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
     const uint32_t idesc = make_idesc(p.BN);
     int sa = 0, sb = 0, acc = 0;
     uint32_t pa = 0, pb = 0, acc_phase = 0;
-    for (int64_t tile = tile_begin; tile < tile_end; ++tile) {
-      int sample;
-      const int64_t q0 = tile_q0(tile, &sample);
-      const int64_t r_lo = (q0 - p.Wp - 1) / p.Wp;
-      const int row_off = (int)(q0 - r_lo * p.Wp);  // window row of Q0
-      mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+    long long w_t = 0, w_a = 0, w_b = 0;
+    const long long tstart = clock64();
+    for (int tile = tile_begin; tile < tile_end; ++tile) {
+      const int row_off = tile_geo(tile).row_off;
+      { HL_T0(); mbar_wait(&tmem_empty[acc], acc_phase ^ 1); HL_ACC(w_t); }
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 2 * p.BN);
       for (int ch = 0; ch < n_chunks; ++ch) {
-        mbar_wait(&full_a[sa], pa);
+        { HL_T0(); mbar_wait(&full_a[sa], pa); HL_ACC(w_a); }
         tc_fence_after();
-        const uint32_t a_base = smem_u32(a_ring + (size_t)sa * p.a_stage_bytes);
-        for (int tap = 0; tap < 9; ++tap) {
-          mbar_wait(&full_b[sb], pb);
+        // descriptor of window row `row_off` (the tile's first output) in this stage; taps and sub-tiles are
+        // constant offsets in 16-byte units added to the low word
+        const uint64_t a_desc0 = make_smem_desc(smem_u32(a_ring + (size_t)sa * p.a_stage_bytes) + (uint32_t)row_off * 128u);
+        const bool first_tile = tile == tile_begin;
+        for (int g3 = 0; g3 < 3; ++g3) {
+          const int sbi = p.b_resident ? ch * 3 + g3 : sb;
+          if (!p.b_resident || first_tile) { HL_T0(); mbar_wait(&full_b[sbi], p.b_resident ? 0u : pb); HL_ACC(w_b); }
           tc_fence_after();
           if (elect_one()) {
-            const int dy = tap / 3 - 1, dx = tap % 3 - 1;
-            const uint64_t bdesc = make_smem_desc(smem_u32(b_ring + (size_t)sb * b_bytes));
+            const uint64_t b_desc0 = make_smem_desc(smem_u32(b_ring + (size_t)sbi * b_bytes));
 #pragma unroll
-            for (int u = 0; u < 2; ++u) {
-              const uint64_t adesc = make_smem_desc(a_base + (uint32_t)(row_off + u * 128 + dy * p.Wp + dx) * 128u);
+            for (int t3 = 0; t3 < 3; ++t3) {
+              const int shift = (g3 - 1) * p.Wp + (t3 - 1);  // tap (dy,dx) = (g3-1, t3-1): rows of 128 B = 8 units
+              const uint64_t bdesc = b_desc0 + (uint64_t)(t3 * p.BN * 8);
 #pragma unroll
-              for (int kk = 0; kk < TC_BK / 16; ++kk)
-                umma_f16(d_tmem + (uint32_t)(u * p.BN), adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), idesc,
-                         (ch | tap | kk) != 0);
+              for (int u = 0; u < 2; ++u) {
+                const uint64_t adesc = a_desc0 + (uint64_t)(int64_t)((shift + u * 128) * 8);
+#pragma unroll
+                for (int kk = 0; kk < TC_BK / 16; ++kk)
+                  umma_f16(d_tmem + (uint32_t)(u * p.BN), adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), idesc,
+                           (ch | g3 | t3 | kk) != 0);
+              }
             }
-            umma_commit(&empty_b[sb]);
-            if (tap == 8) {
+            if (!p.b_resident) umma_commit(&empty_b[sbi]);
+            if (g3 == 2) {
               umma_commit(&empty_a[sa]);
               if (ch == n_chunks - 1) umma_commit(&tmem_full[acc]);
             }
           }
           __syncwarp();
-          if (++sb == p.b_stages) { sb = 0; pb ^= 1; }
+          if (!p.b_resident) { if (++sb == p.b_stages) { sb = 0; pb ^= 1; } }
         }
-        if (++sa == HL_A_STAGES) { sa = 0; pa ^= 1; }
+        if (++sa == p.a_stages) { sa = 0; pa ^= 1; }
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+    if (p.prof && lane == 0) {
+      p.prof[blockIdx.x * 16 + 4] = clock64() - tstart;
+      p.prof[blockIdx.x * 16 + 5] = w_t;
+      p.prof[blockIdx.x * 16 + 6] = w_a;
+      p.prof[blockIdx.x * 16 + 7] = w_b;
     }
   } else {
     // ================================================================ epilogue (8 warps)
@@ -186,6 +221,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
     uint32_t acc_phase = 0;
     int cur_sample = -1;
     int buf = 0;
+    long long w_f = 0, w_bar = 0;
+    const long long tstart = clock64();
     const int cpg = p.stats ? p.BN / p.groups : 8;
     auto flush_stats = [&](int sample) {
       hl_epi_bar();
@@ -195,22 +232,25 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
       }
       hl_epi_bar();
     };
-    for (int64_t tile = tile_begin; tile < tile_end; ++tile) {
-      int sample;
-      const int64_t q0 = tile_q0(tile, &sample);
+    for (int tile = tile_begin; tile < tile_end; ++tile) {
+      const TileGeo g = tile_geo(tile);
+      const int sample = g.sample;
+      const int n0 = g.R0 / p.Hp1, y0r = g.R0 - n0 * p.Hp1;
       if (p.stats && cur_sample >= 0 && sample != cur_sample) flush_stats(cur_sample);
       cur_sample = sample;
-      mbar_wait(&tmem_full[acc], acc_phase);
+      { HL_T0(); mbar_wait(&tmem_full[acc], acc_phase); HL_ACC(w_f); }
       tc_fence_after();
       for (int u = 0; u < 2; ++u) {
         // which output position does this accumulator row hold?
-        const int64_t Q = q0 + u * 128 + row_in_sub;
-        const int64_t R = Q / p.Wp;
-        const int xx = (int)(Q % p.Wp) - 1;
-        const int n = (int)(R / p.Hp1);
-        const int yy = (int)(R % p.Hp1) - 1;
+        // row m of the tile is Q0 + m: at most 8 padded rows below R0, at most one frame boundary crossed
+        const int off = g.x0r + u * 128 + row_in_sub;
+        const int dR = (int)(((uint32_t)off * p.wp_magic) >> 16);
+        const int xx = off - dR * p.Wp - 1;
+        int yr = y0r + dR, n = n0;
+        if (yr >= p.Hp1) { yr -= p.Hp1; ++n; }
+        const int yy = yr - 1;
         const bool valid = xx >= 0 && xx < p.W && yy >= 0 && n < (sample + 1) * p.frames;
-        const long long pos = valid ? ((long long)n * p.H + yy) * p.W + xx : -1;
+        const int pos = valid ? (n * p.H + yy) * p.W + xx : -1;
         const uint32_t t_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((acc * 2 + u) * p.BN);
         for (int s0 = 0; s0 < p.BN; s0 += 64) {
           const int c0 = s0 + wg * 32;
@@ -269,7 +309,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
           }
           // transpose through shared memory: rows -> coalesced 16-byte stores of the valid rows
           uint8_t* sbuf = stage_out + buf * 16384;
-          long long* rp = rowpos + buf * 128;
+          int* rp = rowpos + buf * 128;
           {
             uint8_t* srow = sbuf + row_in_sub * 128;
 #pragma unroll
@@ -283,18 +323,19 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
             }
             if (wg == 0) rp[row_in_sub] = pos;
           }
-          hl_epi_bar();
+          { HL_T0(); hl_epi_bar(); HL_ACC(w_bar); }
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const int idx = et + 256 * i;
             const int row = idx >> 3, chunk = idx & 7;
-            const long long gp = rp[row];
+            const int gp = rp[row];
             if (gp >= 0) {
               const uint4 val = *reinterpret_cast<const uint4*>(sbuf + row * 128 + ((chunk ^ (row & 7)) * 16));
-              *reinterpret_cast<uint4*>(p.out + gp * p.out_ld + p.out_coff + s0 + chunk * 8) = val;
+              *reinterpret_cast<uint4*>(p.out + (int64_t)gp * p.out_ld + p.out_coff + s0 + chunk * 8) = val;
             }
           }
-          buf ^= 1;
+          if (p.out_bufs == 2) buf ^= 1;
+          else hl_epi_bar();  // single staging buffer: everyone has copied out before it is rewritten
         }
       }
       tc_fence_before();
@@ -303,6 +344,12 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
     if (p.stats && cur_sample >= 0) flush_stats(cur_sample);
+    if (p.prof && et == 0) {
+      p.prof[blockIdx.x * 16 + 8] = clock64() - tstart;
+      p.prof[blockIdx.x * 16 + 9] = w_f;
+      p.prof[blockIdx.x * 16 + 10] = w_bar;
+      p.prof[blockIdx.x * 16 + 11] = tile_end - tile_begin;
+    }
   }
 
   tc_fence_before();
@@ -316,14 +363,25 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
 // ------------------------------------------------------------------------------------------ host side
 static int halo_nr(int Wp) { return (HL_TILE_Q + 2 * Wp + 2 + Wp - 2) / Wp + 1; }
 
-static size_t halo_smem(int Wp, int BN, int* a_stage_bytes, int* b_stages) {
+static size_t halo_smem(int Wp, int BN, int n_chunks, int* a_stage_bytes, int* a_stages, int* b_stages, int* out_bufs,
+                        int* resident) {
   const int a = (halo_nr(Wp) * Wp * 128 + 1023) / 1024 * 1024;
-  const int tail = 2 * 16384 + 2 * 128 * 8 + 128 * 4 + 64 * 4 + 1024;
-  int bs = (227 * 1024 - 1024 - HL_A_STAGES * a - tail) / (BN * 128);
-  if (bs > 9) bs = 9;
+  const int bstage = 3 * BN * 128;
+  const int limit = 227 * 1024 - 1024;  // minus alignment slack
+  const int misc = 2 * 128 * 8 + 128 * 4 + 64 * 4 + 1024;
+  // two activation-window stages (measured: a third does not help), double-buffered output staging when it fits,
+  // the rest for weight stages (one stage = three taps); if ALL weights fit they are loaded once and stay resident
+  int as = 2, ob = 2;
+  int bs = (limit - as * a - ob * 16384 - misc) / bstage;
+  if (bs < 2) { ob = 1; bs = (limit - as * a - ob * 16384 - misc) / bstage; }
+  *resident = bs >= 3 * n_chunks;
+  if (*resident) bs = 3 * n_chunks;
+  if (bs > 6 && !*resident) bs = 6;
   *a_stage_bytes = a;
+  *a_stages = as;
   *b_stages = bs;
-  return (size_t)HL_A_STAGES * a + (size_t)bs * BN * 128 + tail + 1024;
+  *out_bufs = ob;
+  return (size_t)as * a + (size_t)bs * bstage + (size_t)ob * 16384 + misc + 1024;
 }
 
 int conv_halo_supported(const dv_conv_params& p) {
@@ -333,14 +391,15 @@ int conv_halo_supported(const dv_conv_params& p) {
   if (p.C0 % TC_BK || p.C1 % TC_BK) return 0;
   if (p.W < 32 || p.W > 128 || p.H < 8) return 0;
   if (p.n_img % p.frames) return 0;
+  if (((int64_t)p.n_img * (p.H + 1) + 2) * (p.W + 2) >= (1ll << 30)) return 0;  // 32-bit index arithmetic in the kernel
   const int out_ld = p.out_ld ? p.out_ld : p.Cout;
   if (out_ld % 8 || p.out_coff % 8) return 0;
   if (p.stats) {
     if (p.groups <= 0 || p.Cout % p.groups || (p.Cout / p.groups) % 8 || p.groups > 32) return 0;
   }
-  int a, bs;
-  halo_smem(p.W + 2, p.Cout, &a, &bs);
-  return bs >= 3;
+  int a, as, bs, ob, res;
+  halo_smem(p.W + 2, p.Cout, (p.C0 + p.C1) / TC_BK, &a, &as, &bs, &ob, &res);
+  return bs >= 2;
 }
 
 int conv_halo_launch(const dv_conv_params& p, cudaStream_t s) {
@@ -350,16 +409,30 @@ int conv_halo_launch(const dv_conv_params& p, cudaStream_t s) {
   h.c0_chunks = p.C0 / TC_BK; h.c1_chunks = p.C1 / TC_BK;
   h.BN = p.Cout;
   h.NR = halo_nr(h.Wp);
-  const size_t smem = halo_smem(h.Wp, h.BN, &h.a_stage_bytes, &h.b_stages);
+  const size_t smem = halo_smem(h.Wp, h.BN, h.c0_chunks + h.c1_chunks, &h.a_stage_bytes, &h.a_stages, &h.b_stages,
+                                &h.out_bufs, &h.b_resident);
   const int64_t span = ((int64_t)p.frames * h.Hp1 - 2) * h.Wp + p.W;
   h.tiles_per_sample = (int)((span + HL_TILE_Q - 1) / HL_TILE_Q);
-  h.total_tiles = (int64_t)(p.n_img / p.frames) * h.tiles_per_sample;
+  h.total_tiles = (p.n_img / p.frames) * h.tiles_per_sample;
+  h.wp_magic = (uint32_t)((65536 + h.Wp - 1) / h.Wp);
+  for (int off = 0; off < h.Wp + HL_TILE_Q; ++off)
+    DV_REQUIRE((int)(((uint32_t)off * h.wp_magic) >> 16) == off / h.Wp, DV_EUNSUPPORTED, "dv_conv_igemm(halo): division magic");
   h.bias = p.bias;
   h.out = reinterpret_cast<__nv_bfloat16*>(p.out);
   h.stats = p.stats;
   h.groups = p.groups;
   h.out_ld = p.out_ld ? p.out_ld : p.Cout;
   h.out_coff = p.out_coff;
+  {
+    // debug: DV_HALO_PROFILE=<device pointer as hex> makes every CTA dump its wait-cycle counters there
+    static long long* prof = nullptr;
+    static bool checked = false;
+    if (!checked) {
+      checked = true;
+      if (const char* e = getenv("DV_HALO_PROFILE")) prof = reinterpret_cast<long long*>(strtoull(e, nullptr, 16));
+    }
+    h.prof = prof;
+  }
 
   auto act_map = [&](CUtensorMap* m, const void* ptr, int C) {
     uint64_t dims[5] = {(uint64_t)C, (uint64_t)p.W, (uint64_t)p.H, (uint64_t)p.n_img, 1};
@@ -398,7 +471,7 @@ int conv_halo_launch(const dv_conv_params& p, cudaStream_t s) {
     DV_REQUIRE(e == cudaSuccess, DV_ECUDA, "dv_conv_igemm(halo): cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     attr_set = true;
   }
-  const int grid = (int)(h.total_tiles < sm_count ? h.total_tiles : sm_count);
+  const int grid = h.total_tiles < sm_count ? h.total_tiles : sm_count;
   conv_halo_kernel<<<grid, HL_THREADS, smem, s>>>(ma0, ma1, mb, h);
   DV_CHECK_LAUNCH("dv_conv_igemm(halo)");
   return DV_OK;

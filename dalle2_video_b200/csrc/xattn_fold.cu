@@ -127,7 +127,6 @@ xattn_fold_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
     tma_prefetch_desc(&map_out);
     for (int s = 0; s < 2; ++s) { mbar_init(&x_full[s], 1); mbar_init(&x_empty[s], 4); }
     mbar_init(w_full, 1);
-    mbar_init(w_free, 1);
     mbar_init(s_full, 1);
     mbar_init(p_ready, 4);
     mbar_init(y_full, 1);
@@ -146,24 +145,24 @@ xattn_fold_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int64_t per_cta = (p.tiles + gridDim.x - 1) / gridDim.x;
-  const int64_t tile_begin = (int64_t)blockIdx.x * per_cta;
-  const int64_t tile_end = tile_begin + per_cta < p.tiles ? tile_begin + per_cta : p.tiles;
+  // grid = (CTAs per sample, samples): a CTA never crosses a sample, so the folded matrices are loaded once
+  const int b = blockIdx.y;
+  const int64_t per_cta = (p.tiles_per_sample + gridDim.x - 1) / gridDim.x;
+  const int64_t lo = (int64_t)blockIdx.x * per_cta;
+  const int64_t hi = lo + per_cta < p.tiles_per_sample ? lo + per_cta : p.tiles_per_sample;
+  const int64_t tile_begin = (int64_t)b * p.tiles_per_sample + lo;
+  const int64_t tile_end = (int64_t)b * p.tiles_per_sample + (hi > lo ? hi : lo);
 
   if (warp == 0) {
     // ================================================================ TMA producer
     if (elect_one()) {
-      int cur = -1;
       int t = 0;
+      if (tile_begin < tile_end) {
+        mbar_expect_tx(w_full, (uint32_t)(p.chunks * 8192 + p.C * 128));
+        for (int c = 0; c < p.chunks; ++c) tma_load_3d(&map_mq, w_full, mq_s + (size_t)c * 8192, c * 64, 0, b);
+        for (int r0 = 0; r0 < p.C; r0 += p.NB) tma_load_3d(&map_u, w_full, u_s + (size_t)r0 * 128, 0, r0, b);
+      }
       for (int64_t tile = tile_begin; tile < tile_end; ++tile, ++t) {
-        const int b = (int)(tile / p.tiles_per_sample);
-        if (b != cur) {
-          if (t > 0) mbar_wait(w_free, (uint32_t)((t - 1) & 1));  // every MMA that read Mq / U has retired
-          mbar_expect_tx(w_full, (uint32_t)(p.chunks * 8192 + p.C * 128));
-          for (int c = 0; c < p.chunks; ++c) tma_load_3d(&map_mq, w_full, mq_s + (size_t)c * 8192, c * 64, 0, b);
-          for (int r0 = 0; r0 < p.C; r0 += p.NB) tma_load_3d(&map_u, w_full, u_s + (size_t)r0 * 128, 0, r0, b);
-          cur = b;
-        }
         const int st = t % p.xs;
         mbar_wait(&x_empty[st], (uint32_t)(((t / p.xs) & 1) ^ 1));
         mbar_expect_tx(&x_full[st], x_stage_bytes);
@@ -175,14 +174,9 @@ xattn_fold_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
   } else if (warp == 1) {
     // ================================================================ MMA issuer
     const uint32_t idesc1 = make_idesc(64), idesc2 = make_idesc(p.NB);
-    int cur = -1, wloads = 0, t = 0;
+    int t = 0;
+    if (tile_begin < tile_end) mbar_wait(w_full, 0u);
     for (int64_t tile = tile_begin; tile < tile_end; ++tile, ++t) {
-      const int b = (int)(tile / p.tiles_per_sample);
-      if (b != cur) {
-        mbar_wait(w_full, (uint32_t)(wloads & 1));
-        ++wloads;
-        cur = b;
-      }
       const int st = t % p.xs;
       mbar_wait(&x_full[st], (uint32_t)((t / p.xs) & 1));
       if (t > 0) mbar_wait(acc_free, (uint32_t)((t - 1) & 1));  // previous tile's y has been read out of TMEM
@@ -209,7 +203,6 @@ xattn_fold_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
             umma_f16(tmem_base + (uint32_t)n0, ad + (uint64_t)(kk * 2), bd + (uint64_t)(kk * 2), idesc2, kk != 0);
         }
         umma_commit(y_full);
-        umma_commit(w_free);
       }
       __syncwarp();
     }
@@ -219,15 +212,10 @@ xattn_fold_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
     const int row = q * 32 + lane;
     const int et = (warp - 2) * 32 + lane;
     const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
-    int cur = -1, t = 0;
+    int t = 0;
+    if (et < 64) cs_s[et] = p.cs[(int64_t)b * 64 + et];
+    xf_bar();
     for (int64_t tile = tile_begin; tile < tile_end; ++tile, ++t) {
-      const int b = (int)(tile / p.tiles_per_sample);
-      if (b != cur) {
-        xf_bar();
-        if (et < 64) cs_s[et] = p.cs[(int64_t)b * 64 + et];
-        xf_bar();
-        cur = b;
-      }
       const int st = t % p.xs;
       const uint8_t* xrow = x_s + (size_t)st * x_stage_bytes + (size_t)row * 128;
       mbar_wait(&x_full[st], (uint32_t)((t / p.xs) & 1));
@@ -442,7 +430,11 @@ extern "C" int dv_xattn_fold(const dv_xattn_fold_params* p, dv_stream_t stream) 
     cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
     if (sm_count <= 0) sm_count = 148;
   }
-  const int grid = (int)(k.tiles < sm_count ? k.tiles : sm_count);
+  int gx = sm_count / p->B;
+  if (gx < 1) gx = 1;
+  if (gx > k.tiles_per_sample) gx = (int)k.tiles_per_sample;
+  DV_REQUIRE(p->B <= 65535, DV_EUNSUPPORTED, "dv_xattn_fold: more than 65535 samples per launch");
+  dim3 grid(gx, p->B);
   if (p->nk == 7)
     xattn_fold_kernel<7><<<grid, XF_THREADS, smem, as_stream(stream)>>>(mx, mm, mu, mo, k);
   else

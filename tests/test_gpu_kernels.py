@@ -440,7 +440,7 @@ HALO_CASES = [
     dict(B=2, T=2, H=64, W=64, C=(64, 64), Co=64, stats=True),       # two sources
     dict(B=1, T=4, H=32, W=32, C=(128, 64), Co=128, stats=True),     # 32x32, N=128
     dict(B=3, T=2, H=32, W=32, C=(64,), Co=64, stats=True),
-    dict(B=1, T=2, H=16, W=64, C=(64,), Co=128),                     # non-square
+    dict(B=1, T=2, H=16, W=64, C=(64,), Co=64),                      # non-square
 ]
 
 

@@ -1,0 +1,25 @@
+"""Debug: per-role wait-cycle counters of the streaming-halo conv kernel (DV_HALO_PROFILE)."""
+import os, sys, math
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+import torch
+prof = torch.zeros(148, 16, dtype=torch.int64, device="cuda")
+os.environ["DV_HALO_PROFILE"] = hex(prof.data_ptr())
+from gpu_util import conv
+dev = torch.device("cuda:0")
+B, T, H, W, C, Co = 8, 16, 64, 64, 64, 64
+rows = B * T * H * W
+x = torch.randn(rows, C, device=dev).bfloat16()
+w = (torch.randn(Co, 9 * C, device=dev) / math.sqrt(9 * C)).bfloat16()
+bias = torch.randn(Co, device=dev)
+out = torch.empty(rows, Co, device=dev, dtype=torch.bfloat16)
+stats = torch.zeros(B, 8, 2, dtype=torch.float64, device=dev)
+for _ in range(3):
+    conv([x], w, bias, out, n_img=B * T, frames=T, H=H, W=W, k=3, stats=stats, groups=8, impl=3)
+torch.cuda.synchronize()
+p = prof.float().mean(0).tolist()
+tiles = p[11]
+print(f"tiles/CTA {tiles:.1f}")
+print(f"producer: total {p[0]:.0f} cyc ({p[0]/tiles:.0f}/tile)  wait empty_a {p[1]/tiles:.0f}/tile  wait empty_b {p[2]/tiles:.0f}/tile")
+print(f"mma     : total {p[4]:.0f} cyc ({p[4]/tiles:.0f}/tile)  wait tmem_empty {p[5]/tiles:.0f}/tile  wait full_a {p[6]/tiles:.0f}/tile  wait full_b {p[7]/tiles:.0f}/tile")
+print(f"epilogue: total {p[8]:.0f} cyc ({p[8]/tiles:.0f}/tile)  wait tmem_full {p[9]/tiles:.0f}/tile  in staging barrier {p[10]/tiles:.0f}/tile")
