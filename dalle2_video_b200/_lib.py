@@ -65,8 +65,9 @@ class XattnFoldParams(C.Structure):
 
 
 class AttnMqaParams(C.Structure):
-    _fields_ = [("q", vp), ("kv", vp), ("out", vp), ("null_kv", vp), ("bias", vp), ("S", i64), ("n", i32),
-                ("heads", i32), ("dh", i32), ("scale", f32), ("dtype", i32)]
+    _fields_ = [("q", vp), ("kv", vp), ("out", vp), ("null_kv", vp), ("bias", vp), ("workspace", vp),
+                ("workspace_bytes", i64), ("S", i64), ("n", i32), ("heads", i32), ("dh", i32), ("scale", f32),
+                ("dtype", i32), ("impl", i32)]
 
 
 class TimeEmbedParams(C.Structure):
@@ -105,7 +106,8 @@ ENTRY_POINTS = {
     "dv_attn_mqa": AttnMqaParams, "dv_time_embed": TimeEmbedParams, "dv_linear_small": LinearSmallParams,
     "dv_cond_tokens": CondTokensParams, "dv_to_out": ToOutParams, "dv_im2col_init": Im2colParams,
 }
-PLAIN_SYMBOLS = ("dv_version", "dv_last_error_string", "dv_device_sm_count", "dv_conv_uses_tcgen05")
+PLAIN_SYMBOLS = ("dv_version", "dv_last_error_string", "dv_device_sm_count", "dv_conv_uses_tcgen05",
+                 "dv_attn_mqa_workspace_bytes")
 
 _lib = None
 _SYNC_EACH = bool(os.environ.get("DV_SYNC_EACH"))
@@ -137,6 +139,8 @@ def lib():
         _lib.dv_device_sm_count.restype = i32
         _lib.dv_conv_uses_tcgen05.argtypes = [C.POINTER(ConvParams)]
         _lib.dv_conv_uses_tcgen05.restype = i32
+        _lib.dv_attn_mqa_workspace_bytes.argtypes = [C.POINTER(AttnMqaParams)]
+        _lib.dv_attn_mqa_workspace_bytes.restype = i64
     return _lib
 
 

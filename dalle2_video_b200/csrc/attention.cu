@@ -183,7 +183,15 @@ __global__ void __launch_bounds__(128) attn_mqa_kernel(dv_attn_mqa_params p) {
   }
 }
 
+int attn_tc_supported(const dv_attn_mqa_params& p);
+int attn_tc_launch(const dv_attn_mqa_params& p, cudaStream_t s);
+
 }  // namespace dv
+
+extern "C" int64_t dv_attn_mqa_workspace_bytes(const dv_attn_mqa_params* p) {
+  if (!p || p->dtype != DV_BF16 || p->bias || p->dh != 32 || p->n % 128 || p->heads <= 0 || 128 % p->heads) return 0;
+  return (int64_t)p->S * p->dh * p->n * 2;
+}
 
 extern "C" int dv_xattn_core(const dv_xattn_params* p, dv_stream_t stream) {
   using namespace dv;
@@ -217,8 +225,11 @@ extern "C" int dv_attn_mqa(const dv_attn_mqa_params* p, dv_stream_t stream) {
   DV_REQUIRE(p->S <= 65535, DV_EUNSUPPORTED, "dv_attn_mqa: more than 65535 sequences per launch");
   DV_REQUIRE(aligned16(p->q) && aligned16(p->kv) && aligned16(p->out), DV_EALIGN,
              "dv_attn_mqa: q/kv/out must be 16-byte aligned");
-  dim3 grid((unsigned)(((int64_t)p->n * p->heads + 127) / 128), (unsigned)p->S);
   cudaStream_t s = as_stream(stream);
+  const bool tc_ok = attn_tc_supported(*p) != 0;
+  if (p->impl == 2) DV_REQUIRE(tc_ok, DV_EUNSUPPORTED, "dv_attn_mqa: the tcgen05 kernel does not take these parameters");
+  if (tc_ok && p->impl != 1) return attn_tc_launch(*p, s);
+  dim3 grid((unsigned)(((int64_t)p->n * p->heads + 127) / 128), (unsigned)p->S);
   if (p->dtype == DV_F32) {
     if (p->dh == 32) attn_mqa_kernel<float, 32><<<grid, 128, 0, s>>>(*p);
     else attn_mqa_kernel<float, 64><<<grid, 128, 0, s>>>(*p);

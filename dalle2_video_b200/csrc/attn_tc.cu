@@ -1,0 +1,376 @@
+// K6 — multi-query flash self-attention on tcgen05 (bf16 in, fp32 softmax / accumulation).
+// Replaces Attention.forward between to_q/to_kv and to_out (dalle2_pytorch 1.14.2; built
+// dalle2_video/dalle2_video.py:424-432, called :921-922): `heads` query heads share ONE key/value head and a learned
+// null key/value is prepended.
+//
+// Mapping.  Because K/V are shared by all heads, the 128 rows of a Q tile are (query, head) pairs — 8 queries x 16
+// heads — so every K/V tile is loaded once for all heads.  Per Q tile, one thread per row keeps the online-softmax
+// state (m, l) and the fp32 output row in registers:
+//   init      m = scale*q.k_null, l = 1, O = v_null                      (the null key/value, no MMA needed)
+//   per 128-key tile j:
+//     MMA  S_j   = Q . K_j^T        (M=128, N=128, K=dh)  -> TMEM, double-buffered so S_{j+1} overlaps softmax_j
+//     thr  P_j   = exp2(S_j*c - m)  (bf16) -> shared memory, SWIZZLE_128B K-major
+//     MMA  Ot_j  = P_j . V_j        (M=128, N=dh, K=128)  -> TMEM (fresh accumulator per tile)
+//     thr  O     = O*corr + Ot_j    (rescaling stays in registers; TMEM is never rescaled)
+// V is needed K-major ([dh][keys]) for the second MMA, so a small pre-pass transposes V into caller-supplied scratch.
+// The n x (n+1) logits of the reference (67 MB per sample at n=1024) never exist.
+#include <math_constants.h>
+
+#include "tc_common.cuh"
+
+namespace dv {
+
+constexpr int AT_THREADS = 192;  // warp 0 TMA, warp 1 MMA, warps 2-5 softmax (one (query, head) row per thread)
+constexpr int AT_KT = 128;       // keys per tile
+constexpr int AT_STAGES = 3;
+
+struct AttnTcParams {
+  int n, heads, dh;
+  int q_tiles_per_seq;  // n*heads/128
+  int64_t total_tiles;  // S * q_tiles_per_seq
+  int k_tiles;          // n/128
+  const __nv_bfloat16* q;
+  __nv_bfloat16* out;
+  const float* null_kv;
+  float scale_log2e;    // scale * log2(e)
+  float scale;
+};
+
+// [S*n][2*dh] (k | v)  ->  vt [S][dh][n]
+__global__ void __launch_bounds__(256) v_transpose_kernel(const __nv_bfloat16* __restrict__ kv, __nv_bfloat16* __restrict__ vt,
+                                                          int n, int dh) {
+  __shared__ __nv_bfloat16 tile[64][66];
+  const int s = blockIdx.y;
+  const int j0 = blockIdx.x * 64;
+  for (int i = threadIdx.x; i < 64 * dh; i += blockDim.x) {
+    const int j = i / dh, d = i % dh;
+    tile[j][d] = kv[((int64_t)s * n + j0 + j) * (2 * dh) + dh + d];
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 64 * dh; i += blockDim.x) {
+    const int d = i / 64, j = i % 64;
+    vt[((int64_t)s * dh + d) * n + j0 + j] = tile[j][d];
+  }
+}
+
+__device__ __forceinline__ void tma_load_3d_at(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+
+template <int DH>
+__global__ void __launch_bounds__(AT_THREADS, 1)
+attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
+               const __grid_constant__ CUtensorMap map_vt, const AttnTcParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  constexpr int ROWB = DH * 2;                 // bytes per q/k row (64 for dh=32)
+  constexpr int Q_BYTES = 128 * ROWB;          // 8 KB
+  constexpr int K_BYTES = AT_KT * ROWB;        // 8 KB
+  constexpr int VT_BYTES = DH * AT_KT * 2;     // 8 KB: two [DH rows][64 keys] SWIZZLE_128B blocks
+  constexpr int STAGE_BYTES = K_BYTES + VT_BYTES;
+  uint8_t* q_s = smem;                                   // 2 x [128][ROWB] SWIZZLE_64B (double-buffered)
+  uint8_t* kv_s = q_s + 2 * Q_BYTES;                     // ring
+  uint8_t* p_s = kv_s + AT_STAGES * STAGE_BYTES;         // [2 blocks][128 rows][128 B] SWIZZLE_128B
+  uint64_t* bars = reinterpret_cast<uint64_t*>(p_s + 2 * 16384);
+  uint64_t* q_full = bars;            // [2]
+  uint64_t* q_free = bars + 2;        // [2] (4 arrivals each)
+  uint64_t* kv_full = bars + 4;       // [AT_STAGES]
+  uint64_t* kv_empty = kv_full + AT_STAGES;
+  uint64_t* s_full = kv_empty + AT_STAGES;  // [2]
+  uint64_t* p_ready = s_full + 2;           // 1 (4 arrivals)
+  uint64_t* o_full = p_ready + 1;           // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr uint32_t TMEM_COLS = 512;  // S: 2 x 128, Ot: 2 x DH (at 256, 256 + DH)
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_q);
+    tma_prefetch_desc(&map_k);
+    tma_prefetch_desc(&map_vt);
+    for (int a = 0; a < 2; ++a) { mbar_init(&q_full[a], 1); mbar_init(&q_free[a], 4); }
+    for (int s = 0; s < AT_STAGES; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&s_full[a], 1); mbar_init(&o_full[a], 1); }
+    mbar_init(p_ready, 4);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int64_t per_cta = (p.total_tiles + gridDim.x - 1) / gridDim.x;
+  const int64_t tile_begin = (int64_t)blockIdx.x * per_cta;
+  const int64_t tile_end = tile_begin + per_cta < p.total_tiles ? tile_begin + per_cta : p.total_tiles;
+  const int nt = p.k_tiles;
+
+  if (warp == 0) {
+    // ================================================================ TMA producer
+    if (elect_one()) {
+      int st = 0;
+      uint32_t ph = 0;
+      int t = 0;
+      for (int64_t tile = tile_begin; tile < tile_end; ++tile, ++t) {
+        const int seq = (int)(tile / p.q_tiles_per_seq);
+        mbar_wait(&q_free[t & 1], (uint32_t)(((t >> 1) & 1) ^ 1));  // the tile that used this Q buffer is done
+        mbar_expect_tx(&q_full[t & 1], Q_BYTES);
+        tma_load_2d(&map_q, &q_full[t & 1], q_s + (t & 1) * Q_BYTES, 0, (int)(tile * 128));
+        for (int j = 0; j < nt; ++j) {
+          mbar_wait(&kv_empty[st], ph ^ 1);
+          uint8_t* dst = kv_s + st * STAGE_BYTES;
+          mbar_expect_tx(&kv_full[st], STAGE_BYTES);
+          tma_load_2d(&map_k, &kv_full[st], dst, 0, seq * p.n + j * AT_KT);
+          tma_load_3d_at(&map_vt, &kv_full[st], dst + K_BYTES, j * AT_KT, 0, seq);
+          tma_load_3d_at(&map_vt, &kv_full[st], dst + K_BYTES + VT_BYTES / 2, j * AT_KT + 64, 0, seq);
+          if (++st == AT_STAGES) { st = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================================================ MMA issuer
+    const uint32_t idesc_s = make_idesc(AT_KT), idesc_o = make_idesc(DH);
+    int st = 0;       // stage of the next S to issue
+    uint32_t ph = 0;
+    int st_pv = 0;    // stage of the next PV to issue (trails st by one tile)
+    int t = 0;
+    int64_t jj = 0;   // running key-tile counter over all Q tiles of this CTA (barrier phases)
+    for (int64_t tile = tile_begin; tile < tile_end; ++tile, ++t) {
+      mbar_wait(&q_full[t & 1], (uint32_t)((t >> 1) & 1));
+      tc_fence_after();
+      const uint64_t qd = make_smem_desc_sw64(smem_u32(q_s + (t & 1) * Q_BYTES));
+      auto issue_s = [&](int j) {
+        // S_j into S buffer (jj+j)&1 ; needs K_j
+        mbar_wait(&kv_full[st], ph);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint64_t kd = make_smem_desc_sw64(smem_u32(kv_s + st * STAGE_BYTES));
+          const uint32_t d = tmem_base + (uint32_t)(((jj + j) & 1) * 128);
+#pragma unroll
+          for (int kk = 0; kk < DH / 16; ++kk) umma_f16(d, qd + (uint64_t)(kk * 2), kd + (uint64_t)(kk * 2), idesc_s, kk != 0);
+          umma_commit(&s_full[(jj + j) & 1]);
+        }
+        __syncwarp();
+        if (++st == AT_STAGES) { st = 0; ph ^= 1; }
+      };
+      issue_s(0);
+      for (int j = 0; j < nt; ++j) {
+        if (j + 1 < nt) issue_s(j + 1);  // S buffer (jj+j+1)&1 was drained before p_ready(j-1)
+        mbar_wait(p_ready, (uint32_t)((jj + j) & 1));
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t vbase = smem_u32(kv_s + st_pv * STAGE_BYTES + K_BYTES);
+          const uint32_t d = tmem_base + 256u + (uint32_t)(((jj + j) & 1) * DH);
+#pragma unroll
+          for (int kk = 0; kk < AT_KT / 16; ++kk) {
+            const uint64_t pd = make_smem_desc(smem_u32(p_s) + (uint32_t)(kk / 4) * 16384u) + (uint64_t)((kk % 4) * 2);
+            const uint64_t vd = make_smem_desc(vbase + (uint32_t)(kk / 4) * (VT_BYTES / 2)) + (uint64_t)((kk % 4) * 2);
+            umma_f16(d, pd, vd, idesc_o, kk != 0);
+          }
+          umma_commit(&kv_empty[st_pv]);           // K_j and V_j consumed
+          umma_commit(&o_full[(jj + j) & 1]);      // last commit of the tile: the softmax threads wait on it
+        }
+        __syncwarp();
+        if (++st_pv == AT_STAGES) st_pv = 0;
+      }
+      jj += nt;
+    }
+  } else {
+    // ================================================================ softmax / output: one (query, head) row per thread
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
+    int t = 0;
+    int64_t jj = 0;
+    for (int64_t tile = tile_begin; tile < tile_end; ++tile, ++t) {
+      const int64_t grow = tile * 128 + row;  // global (query, head) row: q / out are [rows][DH] contiguous
+      // null key / value initialise the online softmax (logit of key 0 = scale * q . k_null)
+      float o[DH];
+      float m, l = 1.0f;
+      {
+        float qv[DH];
+#pragma unroll
+        for (int e = 0; e < DH; e += 8) {
+          float tmp[8];
+          load8(p.q + grow * DH + e, tmp);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) qv[e + k] = tmp[k];
+        }
+        float d = 0.f;
+#pragma unroll
+        for (int e = 0; e < DH; ++e) {
+          d = fmaf(qv[e], __ldg(p.null_kv + e), d);
+          o[e] = __ldg(p.null_kv + DH + e);
+        }
+        m = d * p.scale_log2e;  // running max in the log2 domain
+      }
+      for (int j = 0; j < nt; ++j) {
+        const int buf = (int)((jj + j) & 1);
+        mbar_wait(&s_full[buf], (uint32_t)(((jj + j) >> 1) & 1));
+        tc_fence_after();
+        // pass 1: row maximum of this tile
+        float mx = m;
+#pragma unroll 1
+        for (int c0 = 0; c0 < AT_KT; c0 += 32) {
+          uint32_t r[32];
+          tmem_ld32(t_lane + (uint32_t)(buf * 128 + c0), r);
+#pragma unroll
+          for (int k = 0; k < 32; ++k) mx = fmaxf(mx, __uint_as_float(r[k]) * p.scale_log2e);
+        }
+        const float corr = exp2f(m - mx);
+        m = mx;
+        // the previous tile's P.V must have completed before P is overwritten; fold its result in now
+        if (j > 0) {
+          const int pb = (int)((jj + j - 1) & 1);
+          mbar_wait(&o_full[pb], (uint32_t)(((jj + j - 1) >> 1) & 1));
+          tc_fence_after();
+          uint32_t r[32];
+          tmem_ld32(t_lane + 256u + (uint32_t)(pb * DH), r);
+#pragma unroll
+          for (int e = 0; e < DH; ++e) o[e] += __uint_as_float(r[e]);
+        }
+        l *= corr;
+#pragma unroll
+        for (int e = 0; e < DH; ++e) o[e] *= corr;
+        // pass 2: P = exp2(s*c - m) -> bf16 -> shared memory (two 64-key SWIZZLE_128B blocks)
+        float lsum = 0.f;
+#pragma unroll 1
+        for (int c0 = 0; c0 < AT_KT; c0 += 32) {
+          uint32_t r[32];
+          tmem_ld32(t_lane + (uint32_t)(buf * 128 + c0), r);
+          uint8_t* prow = p_s + (c0 / 64) * 16384 + row * 128;
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            uint4 pk;
+            __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&pk);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float a = exp2f(fmaf(__uint_as_float(r[g * 8 + 2 * e]), p.scale_log2e, -m));
+              const float b = exp2f(fmaf(__uint_as_float(r[g * 8 + 2 * e + 1]), p.scale_log2e, -m));
+              h2[e] = __floats2bfloat162_rn(a, b);
+              // sum what the tensor core will actually multiply (the bf16-rounded probabilities)
+              lsum += __low2float(h2[e]) + __high2float(h2[e]);
+            }
+            const int chunk = ((c0 % 64) / 8 + g) ^ (row & 7);
+            *reinterpret_cast<uint4*>(prow + chunk * 16) = pk;
+          }
+        }
+        l += lsum;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(p_ready);
+      }
+      // last tile's P.V
+      {
+        const int pb = (int)((jj + nt - 1) & 1);
+        mbar_wait(&o_full[pb], (uint32_t)(((jj + nt - 1) >> 1) & 1));
+        tc_fence_after();
+        uint32_t r[32];
+        tmem_ld32(t_lane + 256u + (uint32_t)(pb * DH), r);
+#pragma unroll
+        for (int e = 0; e < DH; ++e) o[e] += __uint_as_float(r[e]);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&q_free[t & 1]);  // this Q buffer may be refilled
+      const float inv = 1.0f / l;
+      __nv_bfloat16* orow = p.out + grow * DH;
+#pragma unroll
+      for (int e = 0; e < DH; e += 8) {
+        float tmp[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) tmp[k] = o[e + k] * inv;
+        store8(orow + e, tmp);
+      }
+      jj += nt;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+int attn_tc_supported(const dv_attn_mqa_params& p) {
+  if (p.dtype != DV_BF16 || p.bias) return 0;
+  if (p.dh != 32) return 0;
+  if (p.heads <= 0 || 128 % p.heads) return 0;
+  if (p.n % AT_KT) return 0;
+  if (!p.workspace || p.workspace_bytes < (int64_t)p.S * p.dh * p.n * 2) return 0;
+  if ((int64_t)p.S * p.n * p.heads >= (1ll << 31)) return 0;
+  return 1;
+}
+
+int attn_tc_launch(const dv_attn_mqa_params& p, cudaStream_t s) {
+  const int DH = 32;
+  __nv_bfloat16* vt = reinterpret_cast<__nv_bfloat16*>(p.workspace);
+  {
+    dim3 grid(p.n / 64, (unsigned)p.S);
+    v_transpose_kernel<<<grid, 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(p.kv), vt, p.n, DH);
+    DV_CHECK_LAUNCH("dv_attn_mqa(v transpose)");
+  }
+  AttnTcParams k;
+  memset(&k, 0, sizeof(k));
+  k.n = p.n; k.heads = p.heads; k.dh = DH;
+  k.q_tiles_per_seq = p.n * p.heads / 128;
+  k.total_tiles = (int64_t)p.S * k.q_tiles_per_seq;
+  k.k_tiles = p.n / AT_KT;
+  k.q = reinterpret_cast<const __nv_bfloat16*>(p.q);
+  k.out = reinterpret_cast<__nv_bfloat16*>(p.out);
+  k.null_kv = p.null_kv;
+  k.scale = p.scale;
+  k.scale_log2e = p.scale * 1.4426950408889634f;
+  CUtensorMap mq, mk, mv;
+  int rc;
+  {
+    const uint64_t rows = (uint64_t)p.S * p.n * p.heads;
+    uint64_t dims[2] = {(uint64_t)DH, rows};
+    uint64_t strides[1] = {(uint64_t)DH * 2};
+    uint32_t box[2] = {(uint32_t)DH, 128};
+    if ((rc = encode_map(&mq, p.q, 2, dims, strides, box, 64)) != DV_OK) return rc;
+  }
+  {
+    uint64_t dims[2] = {(uint64_t)(2 * DH), (uint64_t)p.S * p.n};
+    uint64_t strides[1] = {(uint64_t)(2 * DH) * 2};
+    uint32_t box[2] = {(uint32_t)DH, AT_KT};
+    if ((rc = encode_map(&mk, p.kv, 2, dims, strides, box, 64)) != DV_OK) return rc;
+  }
+  {
+    uint64_t dims[3] = {(uint64_t)p.n, (uint64_t)DH, (uint64_t)p.S};
+    uint64_t strides[2] = {(uint64_t)p.n * 2, (uint64_t)p.n * 2 * DH};
+    uint32_t box[3] = {64, (uint32_t)DH, 1};
+    if ((rc = encode_map(&mv, vt, 3, dims, strides, box, 128)) != DV_OK) return rc;
+  }
+  const size_t smem = 2 * 128 * DH * 2 + AT_STAGES * (AT_KT * DH * 2 + DH * AT_KT * 2) + 2 * 16384 + 256 + 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(attn_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    DV_REQUIRE(e == cudaSuccess, DV_ECUDA, "dv_attn_mqa(tcgen05): cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  static int sm_count = 0;
+  if (!sm_count) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
+    if (sm_count <= 0) sm_count = 148;
+  }
+  const int grid = (int)(k.total_tiles < sm_count ? k.total_tiles : sm_count);
+  attn_tc_kernel<32><<<grid, AT_THREADS, smem, s>>>(mq, mk, mv, k);
+  DV_CHECK_LAUNCH("dv_attn_mqa(tcgen05)");
+  return DV_OK;
+}
+
+}  // namespace dv

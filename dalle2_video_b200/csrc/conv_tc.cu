@@ -424,6 +424,7 @@ struct MapKey {
   uint64_t d[5], s[4];
   uint32_t b[5];
   int rank;
+  int swizzle_bytes, pad_;
   bool operator==(const MapKey& o) const { return memcmp(this, &o, sizeof(MapKey)) == 0; }
 };
 struct MapKeyHash {
@@ -436,13 +437,14 @@ struct MapKeyHash {
 };
 
 int encode_map(CUtensorMap* out, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides,
-                      const uint32_t* box) {
+               const uint32_t* box, int swizzle_bytes) {
   static std::mutex mu;
   static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
   MapKey key;
   memset(&key, 0, sizeof(key));
   key.ptr = ptr;
   key.rank = rank;
+  key.swizzle_bytes = swizzle_bytes;
   for (int i = 0; i < rank; ++i) { key.d[i] = dims[i]; key.b[i] = box[i]; }
   for (int i = 0; i < rank - 1; ++i) key.s[i] = strides[i];
   {
@@ -454,7 +456,8 @@ int encode_map(CUtensorMap* out, const void* ptr, int rank, const uint64_t* dims
   DV_REQUIRE(fn != nullptr, DV_ECUDA, "dv_conv_igemm(tcgen05): cuTensorMapEncodeTiled is not available from the driver");
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
   CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(ptr), dims, strides, box,
-                  estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   DV_REQUIRE(r == CUDA_SUCCESS, DV_ECUDA, "dv_conv_igemm(tcgen05): cuTensorMapEncodeTiled failed (CUresult %d)", (int)r);
   std::lock_guard<std::mutex> lk(mu);

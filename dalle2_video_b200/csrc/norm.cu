@@ -1,9 +1,15 @@
 // K2 — GroupNorm statistics / finalize+apply+scale-shift+SiLU(+residual), and a15 — LayerNorm.
 // HBM-bound streaming kernels (see include/dv_b200.h for the reference call sites they replace).
 //   dv_gn_apply : algorithmic bytes = read x + write y (+ read residual) = 2..3 * elem_size per element.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace dv {
+
+#ifndef DV_GN_UNROLL
+#define DV_GN_UNROLL 8
+#endif
 
 // ---------------------------------------------------------------- GroupNorm statistics
 // grid (chunks, B); block = (C/4) * rpi threads; thread owns one channel quad and strides over rows.
@@ -69,21 +75,67 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(dv_gn_apply_params p, int
   const T* x = reinterpret_cast<const T*>(p.x) + base;
   const T* res = p.residual ? reinterpret_cast<const T*>(p.residual) + base : nullptr;
   T* out = reinterpret_cast<T*>(p.out) + base;
-  const int64_t nvec = (r1 - r0) * c8n;
-  for (int64_t i = threadIdx.x; i < nvec; i += blockDim.x) {
-    const int64_t r = r0 + i / c8n;
-    const int c = (int)(i % c8n) * 8;
-    float v[8];
-    load8(x + r * p.C + c, v);
+  const int nvec = (int)((r1 - r0) * c8n);  // vectors of 8 channels in this block's rows (rows are contiguous)
+  const int64_t vbase = r0 * c8n;
+  const T* xb = x + vbase * 8;
+  const T* rb = res ? res + vbase * 8 : nullptr;
+  T* ob = out + vbase * 8;
+  const int cmod0 = (int)(vbase % c8n);
+  constexpr int U = DV_GN_UNROLL;  // independent 16-byte loads in flight per thread and stream
+  if ((int)blockDim.x % c8n == 0) {
+    // the channel vector of a thread never changes (stride blockDim.x is a multiple of C/8): coefficients in registers
+    const int c = ((cmod0 + (int)threadIdx.x) % c8n) * 8;
+    float ca[8], cd[8];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) v[k] = silu_f(fmaf(v[k], coef[c + k], coef[p.C + c + k]));
-    if (res) {
-      float rr[8];
-      load8(res + r * p.C + c, rr);
+    for (int k = 0; k < 8; ++k) { ca[k] = coef[c + k]; cd[k] = coef[p.C + c + k]; }
+    // Little's law on B200 wants ~64 KB of loads in flight per SM: U raw 16/32-byte vectors per thread and stream are
+    // issued back to back (kept packed in registers), then unpacked, transformed and stored one by one.
+    constexpr int VW = sizeof(T) * 8 / 16;  // uint4 words per 8-element vector (1 for bf16, 2 for fp32)
+    for (int i0 = threadIdx.x; i0 < nvec; i0 += (int)blockDim.x * U) {
+      uint4 xr[U][VW], rraw[U][VW];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) v[k] += rr[k];
+      for (int u = 0; u < U; ++u) {
+        const int i = i0 + u * (int)blockDim.x;
+        if (i < nvec) {
+#pragma unroll
+          for (int w = 0; w < VW; ++w) {
+            xr[u][w] = reinterpret_cast<const uint4*>(xb + (int64_t)i * 8)[w];
+            if (rb) rraw[u][w] = reinterpret_cast<const uint4*>(rb + (int64_t)i * 8)[w];
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int i = i0 + u * (int)blockDim.x;
+        if (i < nvec) {
+          float v[8], rr[8];
+          load8(reinterpret_cast<const T*>(&xr[u][0]), v);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) v[k] = silu_f(fmaf(v[k], ca[k], cd[k]));
+          if (rb) {
+            load8(reinterpret_cast<const T*>(&rraw[u][0]), rr);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v[k] += rr[k];
+          }
+          store8(ob + (int64_t)i * 8, v);
+        }
+      }
     }
-    store8(out + r * p.C + c, v);
+  } else {
+    for (int i = threadIdx.x; i < nvec; i += (int)blockDim.x) {
+      const int c = ((cmod0 + i) % c8n) * 8;
+      float v[8];
+      load8(xb + (int64_t)i * 8, v);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = silu_f(fmaf(v[k], coef[c + k], coef[p.C + c + k]));
+      if (rb) {
+        float rr[8];
+        load8(rb + (int64_t)i * 8, rr);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] += rr[k];
+      }
+      store8(ob + (int64_t)i * 8, v);
+    }
   }
 }
 
@@ -189,7 +241,14 @@ extern "C" int dv_gn_apply(const dv_gn_apply_params* p, dv_stream_t stream) {
   DV_REQUIRE(p->C % 8 == 0 && p->C <= 4096, DV_EUNSUPPORTED, "dv_gn_apply: needs C %% 8 == 0 and C <= 4096 (C=%d)", p->C);
   DV_REQUIRE(aligned16(p->x) && aligned16(p->out) && aligned16(p->residual), DV_EALIGN,
              "dv_gn_apply: tensors must be 16-byte aligned");
-  int chunks = (148 * 8 + p->B - 1) / p->B;
+  // one resident wave: ~2 CTAs per SM in total, so the per-CTA coefficient prologue is paid once, not per wave
+  static int ctas_per_sm = 0;
+  if (!ctas_per_sm) {
+    const char* e = getenv("DV_GN_CTAS_PER_SM");  // tuning aid
+    ctas_per_sm = e ? atoi(e) : 2;
+    if (ctas_per_sm < 1) ctas_per_sm = 2;
+  }
+  int chunks = (148 * ctas_per_sm + p->B - 1) / p->B;
   int64_t rpb = (p->P + chunks - 1) / chunks;
   if (rpb < 1) rpb = 1;
   chunks = (int)((p->P + rpb - 1) / rpb);

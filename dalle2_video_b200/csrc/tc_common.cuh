@@ -112,8 +112,19 @@ __device__ __forceinline__ void tma_store_5d(const CUtensorMap* map, const void*
                : "memory");
 }
 
-// Encode (and cache) a SWIZZLE_128B bf16 tiled tensor map; returns DV_OK or a DV_E* code.
+// Encode (and cache) a bf16 tiled tensor map (SWIZZLE_128B, or SWIZZLE_64B for 64-byte rows); DV_OK or a DV_E* code.
 int encode_map(CUtensorMap* out, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides,
-               const uint32_t* box);
+               const uint32_t* box, int swizzle_bytes = 128);
+
+// K-major SWIZZLE_64B descriptor: rows of 64 bytes (32 bf16), 8-row groups 512 bytes apart.
+__device__ __forceinline__ uint64_t make_smem_desc_sw64(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(512 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)4 << 61;  // SWIZZLE_64B
+  return d;
+}
 
 }  // namespace dv

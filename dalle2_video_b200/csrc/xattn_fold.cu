@@ -14,12 +14,14 @@
 namespace dv {
 
 // ------------------------------------------------------------------------------------------ prep
-__global__ void __launch_bounds__(256) xattn_fold_prep_kernel(dv_xattn_fold_prep_params p) {
+// grid (C/64, heads, B), block (64, 2): y = 0 builds 64 columns of Mq for one head, y = 1 the matching rows of U.
+// The d loop is unrolled 8x so that eight independent weight loads are in flight per thread (latency-bound kernel).
+__global__ void __launch_bounds__(128) xattn_fold_prep_kernel(dv_xattn_fold_prep_params p) {
   __shared__ float ks[8][64];
   __shared__ float vs[8][64];
-  __shared__ float cs_part[8];
-  const int h = blockIdx.x, b = blockIdx.y, nk = p.n_ctx + 1, inner = p.heads * p.dh;
-  for (int i = threadIdx.x; i < nk * p.dh; i += blockDim.x) {
+  const int h = blockIdx.y, b = blockIdx.z, nk = p.n_ctx + 1, inner = p.heads * p.dh;
+  const int tid = threadIdx.y * 64 + threadIdx.x;
+  for (int i = tid; i < nk * p.dh; i += 128) {
     const int j = i / p.dh, d = i % p.dh;
     if (j == 0) {
       ks[0][d] = p.null_kv[d];
@@ -30,46 +32,45 @@ __global__ void __launch_bounds__(256) xattn_fold_prep_kernel(dv_xattn_fold_prep
       vs[j][d] = row[p.v_off + h * p.dh + d];
     }
   }
-  if (threadIdx.x < 8) cs_part[threadIdx.x] = 0.f;
   __syncthreads();
-  __nv_bfloat16* mq = reinterpret_cast<__nv_bfloat16*>(p.mq) + (int64_t)b * 64 * p.C;
-  __nv_bfloat16* u = reinterpret_cast<__nv_bfloat16*>(p.u) + (int64_t)b * p.C * 64;
-  float csl[8];
+  const int c = blockIdx.x * 64 + threadIdx.x;
+  if (c >= p.C) return;
+  float acc[8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) csl[j] = 0.f;
-  for (int c = threadIdx.x; c < p.C; c += blockDim.x) {
-    float am[8], au[8];
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  if (threadIdx.y == 0) {
+    const float* w = p.wq + (int64_t)(h * p.dh) * p.C + c;  // Wq[h*dh + d][c]: coalesced over c
+    for (int d0 = 0; d0 < p.dh; d0 += 8) {
+      float wv[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { am[j] = 0.f; au[j] = 0.f; }
-    for (int d = 0; d < p.dh; ++d) {
-      const float wq = p.wq[(int64_t)(h * p.dh + d) * p.C + c];
-      const float wo = p.wout[(int64_t)c * inner + h * p.dh + d];
+      for (int e = 0; e < 8; ++e) wv[e] = __ldg(w + (int64_t)(d0 + e) * p.C);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        if (j < nk) {
-          am[j] = fmaf(ks[j][d], wq, am[j]);
-          au[j] = fmaf(vs[j][d], wo, au[j]);
-        }
-      }
+      for (int e = 0; e < 8; ++e)
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (j < nk) acc[j] = fmaf(ks[j][d0 + e], wv[e], acc[j]);
     }
     const float gs = p.scale * p.g[c];
+    __nv_bfloat16* mq = reinterpret_cast<__nv_bfloat16*>(p.mq) + (int64_t)b * 64 * p.C;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      if (j < nk) {
-        const __nv_bfloat16 m = __float2bfloat16_rn(gs * am[j]);
-        mq[(int64_t)(h * nk + j) * p.C + c] = m;
-        csl[j] += __bfloat162float(m);
-        u[(int64_t)c * 64 + h * nk + j] = __float2bfloat16_rn(au[j]);
-      }
+    for (int j = 0; j < 8; ++j)
+      if (j < nk) mq[(int64_t)(h * nk + j) * p.C + c] = __float2bfloat16_rn(gs * acc[j]);
+  } else {
+    const float4* w = reinterpret_cast<const float4*>(p.wout + (int64_t)c * inner + h * p.dh);  // Wout[c][h*dh + d]
+    for (int d0 = 0; d0 < p.dh; d0 += 8) {
+      const float4 w0 = __ldg(w + d0 / 4), w1 = __ldg(w + d0 / 4 + 1);
+      const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+      for (int e = 0; e < 8; ++e)
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (j < nk) acc[j] = fmaf(vs[j][d0 + e], wv[e], acc[j]);
     }
-  }
+    __nv_bfloat16* u = reinterpret_cast<__nv_bfloat16*>(p.u) + (int64_t)b * p.C * 64;
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const float s = warp_sum(csl[j]);
-    if ((threadIdx.x & 31) == 0 && j < nk) atomicAdd(&cs_part[j], s);
+    for (int j = 0; j < 8; ++j)
+      if (j < nk) u[(int64_t)c * 64 + h * nk + j] = __float2bfloat16_rn(acc[j]);
   }
-  __syncthreads();
-  if (threadIdx.x < nk) p.cs[(int64_t)b * 64 + h * nk + threadIdx.x] = cs_part[threadIdx.x];
 }
 
 // ------------------------------------------------------------------------------------------ main kernel
@@ -213,7 +214,24 @@ xattn_fold_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
     const int et = (warp - 2) * 32 + lane;
     const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
     int t = 0;
-    if (et < 64) cs_s[et] = p.cs[(int64_t)b * 64 + et];
+    if (tile_begin < tile_end) {
+      // cs[hj] = sum over c of the bf16 Mq row the tensor core multiplies (needed to fold the LayerNorm mean)
+      mbar_wait(w_full, 0u);
+      if (et < 64) {
+        float acc = 0.f;
+        for (int c = 0; c < p.chunks; ++c) {
+          const uint8_t* rowp = mq_s + (size_t)c * 8192 + et * 128;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {  // the 16-byte chunks of a row are swizzled, but a sum does not care
+            const uint4 raw = *reinterpret_cast<const uint4*>(rowp + j * 16);
+            const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) acc += __low2float(h2[e]) + __high2float(h2[e]);
+          }
+        }
+        cs_s[et] = acc;
+      }
+    }
     xf_bar();
     for (int64_t tile = tile_begin; tile < tile_end; ++tile, ++t) {
       const int st = t % p.xs;
@@ -354,20 +372,21 @@ xattn_fold_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
 
 extern "C" int dv_xattn_fold_prep(const dv_xattn_fold_prep_params* p, dv_stream_t stream) {
   using namespace dv;
-  DV_REQUIRE(p && p->kv && p->null_kv && p->wq && p->wout && p->g && p->mq && p->u && p->cs, DV_EINVAL,
+  DV_REQUIRE(p && p->kv && p->null_kv && p->wq && p->wout && p->g && p->mq && p->u, DV_EINVAL,
              "dv_xattn_fold_prep: null pointer");
+  DV_REQUIRE(aligned16(p->wout) && (p->heads * p->dh) % 4 == 0, DV_EALIGN, "dv_xattn_fold_prep: wout must be 16-byte aligned");
   DV_REQUIRE(p->B > 0 && p->C > 0 && p->heads > 0 && p->dh == 64 && p->n_ctx >= 0 && p->n_ctx <= 7, DV_EUNSUPPORTED,
              "dv_xattn_fold_prep: needs dim_head 64 and at most 7 context tokens");
   DV_REQUIRE(p->heads * (p->n_ctx + 1) <= 64, DV_EUNSUPPORTED, "dv_xattn_fold_prep: heads*(n_ctx+1) must be <= 64");
-  dim3 grid(p->heads, p->B);
-  xattn_fold_prep_kernel<<<grid, 256, 0, as_stream(stream)>>>(*p);
+  dim3 grid((p->C + 63) / 64, p->heads, p->B);
+  xattn_fold_prep_kernel<<<grid, dim3(64, 2), 0, as_stream(stream)>>>(*p);
   DV_CHECK_LAUNCH("dv_xattn_fold_prep");
   return DV_OK;
 }
 
 extern "C" int dv_xattn_fold(const dv_xattn_fold_params* p, dv_stream_t stream) {
   using namespace dv;
-  DV_REQUIRE(p && p->x && p->out && p->mq && p->u && p->cs && p->g2, DV_EINVAL, "dv_xattn_fold: null pointer");
+  DV_REQUIRE(p && p->x && p->out && p->mq && p->u && p->g2, DV_EINVAL, "dv_xattn_fold: null pointer");
   DV_REQUIRE(p->C == 64 || p->C == 128 || p->C == 256, DV_EUNSUPPORTED,
              "dv_xattn_fold: C must be 64, 128 or 256 (got %d)", p->C);
   DV_REQUIRE(p->heads == 8 && (p->nk == 3 || p->nk == 7), DV_EUNSUPPORTED,

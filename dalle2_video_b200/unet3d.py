@@ -855,9 +855,18 @@ class _Engine:
         self._conv([(xn.ptr, C)], self._w(at.to_q.weight), None, q.ptr, inner, rows, 1, 1, frames=P)
         self._conv([(xn.ptr, C)], self._w(at.to_kv.weight), None, kvb.ptr, 2 * dh, rows, 1, 1, frames=P)
         # q*scale, then q,k *= sqrt(scale): logits = q.k * scale^2 = q.k / dim_head
-        self._op("dv_attn_mqa", L.AttnMqaParams(q=q.ptr, kv=kvb.ptr, out=q.ptr,
-                                                null_kv=self._f32(at.null_kv).data_ptr(), bias=None, S=B, n=P,
-                                                heads=heads, dh=dh, scale=float(1.0 / dh), dtype=self.code))
+        ap = L.AttnMqaParams(q=q.ptr, kv=kvb.ptr, out=q.ptr, null_kv=self._f32(at.null_kv).data_ptr(), bias=None,
+                             workspace=None, workspace_bytes=0, S=B, n=P, heads=heads, dh=dh, scale=float(1.0 / dh),
+                             dtype=self.code, impl=0)
+        ws_bytes = L.lib().dv_attn_mqa_workspace_bytes(ap)
+        ws = None
+        if ws_bytes > 0:
+            ws = self.pool.get(ws_bytes)
+            ap.workspace, ap.workspace_bytes = ws.data_ptr(), ws_bytes
+            self.n_tc += 1
+        self._op("dv_attn_mqa", ap)
+        if ws is not None:
+            self.pool.put(ws)
         self._release(kvb)
         self._conv([(q.ptr, inner)], self._w(at.to_out[0].weight), None, xn.ptr, C, rows, 1, 1, frames=P)
         self._release(q)

@@ -241,7 +241,7 @@ typedef struct {
   const float* g;        /* norm.g [C] */
   void* mq;              /* out: bf16 [B][64][C]   rows hj >= heads*nk are zero */
   void* u;               /* out: bf16 [B][C][64]   cols hj >= heads*nk are zero */
-  float* cs;             /* out: float32 [B][64]   sum over c of the bf16-rounded Mq rows */
+  float* cs;             /* unused (the column sums are rebuilt from Mq inside dv_xattn_fold); may be NULL */
   int B, C, heads, dh, n_ctx;
   int64_t kv_ld;
   int k_off, v_off;
@@ -254,7 +254,7 @@ typedef struct {
   void* out;        /* bf16 [B][P][C]; may alias x */
   const void* mq;   /* bf16 [B][64][C] */
   const void* u;    /* bf16 [B][C][64] */
-  const float* cs;  /* [B][64] */
+  const float* cs;  /* unused, may be NULL */
   const float* g2;  /* to_out.1.g [C] */
   int B;
   int64_t P;        /* tokens per sample, multiple of 128 */
@@ -278,13 +278,18 @@ typedef struct {
   void* out;
   const float* null_kv; /* [2][dh] */
   const float* bias;    /* [heads][n][n+1] or NULL */
+  void* workspace;      /* caller-owned scratch (tcgen05 path transposes V into it) or NULL -> CUDA-core path */
+  int64_t workspace_bytes;
   int64_t S;
   int n;
   int heads, dh;
   float scale;
   dv_dtype dtype;
+  int impl;             /* 0 auto, 1 force CUDA-core kernel, 2 force tcgen05 kernel */
 } dv_attn_mqa_params;
 int dv_attn_mqa(const dv_attn_mqa_params* p, dv_stream_t stream);
+/* scratch the tcgen05 path needs for these params (0 if it does not apply: bias, fp32, dh != 32, n % 128 != 0) */
+int64_t dv_attn_mqa_workspace_bytes(const dv_attn_mqa_params* p);
 
 /* ------------------------------------------------------------------------------------------------
  * K8  conditioning prologue pieces (float32 throughout; M = batch-sized GEMVs).

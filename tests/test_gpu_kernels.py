@@ -265,8 +265,9 @@ def test_mqa_flash_attention(dtype, S, n, H, D, bias):
     null_kv = rnd(2, D, seed=3)
     b = rnd(H, n, n + 1, seed=4) if bias else None
     out = torch.empty_like(q)
-    L.call("dv_attn_mqa", L.AttnMqaParams(q=ptr(q), kv=ptr(kv), out=ptr(out), null_kv=ptr(null_kv), bias=ptr(b), S=S,
-                                          n=n, heads=H, dh=D, scale=1.0 / D, dtype=code(q)), stream())
+    L.call("dv_attn_mqa", L.AttnMqaParams(q=ptr(q), kv=ptr(kv), out=ptr(out), null_kv=ptr(null_kv), bias=ptr(b),
+                                          workspace=None, workspace_bytes=0, S=S, n=n, heads=H, dh=D, scale=1.0 / D,
+                                          dtype=code(q), impl=1), stream())
     qh = q.float().reshape(S, n, H, D).permute(0, 2, 1, 3)
     k, v = kv.float().reshape(S, n, 2 * D).chunk(2, dim=-1)
     k = torch.cat((null_kv[0].expand(S, 1, D), k), dim=1)
@@ -503,3 +504,32 @@ def test_fused_folded_cross_attention_block(C, P, B, n_ctx):
     L.call("dv_xattn_fold", L.XattnFoldParams(x=ptr(x2), out=ptr(x2), mq=ptr(mq), u=ptr(uu), cs=ptr(cs), g2=ptr(g2), B=B,
                                               P=P, C=C, heads=8, nk=n_ctx + 1, eps_in=1e-5, eps_out=1e-5), stream())
     assert torch.equal(x2, out)
+
+
+@pytest.mark.parametrize("S,n,H", [(1, 128, 16), (2, 1024, 16), (3, 256, 8), (1, 2048, 16)])
+def test_mqa_flash_attention_tcgen05(S, n, H):
+    """tcgen05 flash MQA (impl=2) against the fp32 statement of Attention.forward's core."""
+    D = 32
+    q = rnd(S * n, H * D, dtype=torch.bfloat16, seed=1)
+    kv = rnd(S * n, 2 * D, dtype=torch.bfloat16, seed=2, scale=2.0)
+    null_kv = rnd(2, D, seed=3)
+    out = torch.empty_like(q)
+    p = L.AttnMqaParams(q=ptr(q), kv=ptr(kv), out=ptr(out), null_kv=ptr(null_kv), bias=None, workspace=None,
+                        workspace_bytes=0, S=S, n=n, heads=H, dh=D, scale=1.0 / D, dtype=code(q), impl=2)
+    nbytes = L.lib().dv_attn_mqa_workspace_bytes(p)
+    assert nbytes == S * D * n * 2
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev())
+    p.workspace, p.workspace_bytes = ptr(ws), nbytes
+    L.call("dv_attn_mqa", p, stream())
+    qh = q.float().reshape(S, n, H, D).permute(0, 2, 1, 3)
+    k, v = kv.float().reshape(S, n, 2 * D).chunk(2, dim=-1)
+    k = torch.cat((null_kv[0].expand(S, 1, D), k), dim=1)
+    v = torch.cat((null_kv[1].expand(S, 1, D), v), dim=1)
+    sim = torch.einsum("shid,sjd->shij", qh, k) / D
+    ref = torch.einsum("shij,sjd->shid", sim.softmax(-1), v).permute(0, 2, 1, 3).reshape(S * n, H * D)
+    assert rel_err(out, ref) < 1e-2
+    # in place (the engine overwrites q)
+    q2 = q.clone()
+    p.q, p.out = ptr(q2), ptr(q2)
+    L.call("dv_attn_mqa", p, stream())
+    assert torch.equal(q2, out)

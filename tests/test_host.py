@@ -111,7 +111,7 @@ def test_shard_bounds_cover_and_order():
 def test_library_builds_loads_and_exports_every_declared_symbol(built_lib):
     lib = built_lib.lib()
     header = open(os.path.join(ROOT, "include", "dv_b200.h")).read()
-    declared = set(re.findall(r"^(?:int|const char\*)\s+(dv_\w+)\s*\(", header, flags=re.M))
+    declared = set(re.findall(r"^(?:int|int64_t|const char\*)\s+(dv_\w+)\s*\(", header, flags=re.M))
     assert declared == set(built_lib.ENTRY_POINTS) | set(built_lib.PLAIN_SYMBOLS)
     for name in declared:
         assert getattr(lib, name) is not None
