@@ -90,7 +90,7 @@ class CondTokensParams(C.Structure):
 
 class Im2colParams(C.Structure):
     _fields_ = [("x", vp), ("out", vp), ("B", i32), ("C", i32), ("T", i32), ("H", i32), ("W", i32), ("k", i32),
-                ("Kpad", i32), ("dtype", i32)]
+                ("Kpad", i32), ("dtype", i32), ("layout", i32)]
 
 
 class ToOutParams(C.Structure):

@@ -703,7 +703,10 @@ class _Engine:
         kmax, cin = max(ks), convs[0].weight.shape[1]
         if any(k % 2 == 0 for k in ks):
             return False
-        ktot = kmax * kmax * cin
+        if kmax > 16:
+            return False
+        # K layout 1 of dv_im2col_init: K = (c*kmax + dy)*16 + dx (dx padded to 16) — the shared-memory halo kernel
+        ktot = cin * kmax * 16
         kpad = (ktot + 63) // 64 * 64
         rows = n_img * H * W
         probe = L.ConvParams(src0=1 << 20, src1=None, weight=1 << 20, bias=None, add=None, out=1 << 20, stats=None,
@@ -712,18 +715,18 @@ class _Engine:
                              dtype=self.code, impl=self.impl)
         if not L.lib().dv_conv_uses_tcgen05(probe):
             return False
-        wfull = torch.zeros(u.init_dim, kmax, kmax, cin)
+        wfull = torch.zeros(u.init_dim, cin, kmax, 16)
         bfull, co0 = [], 0
         for conv, k in zip(convs, ks):
             co, off = conv.weight.shape[0], (kmax - k) // 2
-            wfull[co0:co0 + co, off:off + k, off:off + k, :] = conv.weight.detach()[:, :, 0].permute(0, 2, 3, 1).cpu()
+            wfull[co0:co0 + co, :, off:off + k, off:off + k] = conv.weight.detach()[:, :, 0].cpu()
             bfull.append(conv.bias.detach().cpu())
             co0 += co
         wp = torch.zeros(u.init_dim, kpad)
         wp[:, :ktot] = wfull.reshape(u.init_dim, ktot)
         patches = self.pool.get(rows * kpad * self.esz)
         self._op("dv_im2col_init", L.Im2colParams(x=self.x_in.data_ptr(), out=patches.data_ptr(), B=self.B, C=cin,
-                                                  T=self.T, H=H, W=W, k=kmax, Kpad=kpad, dtype=self.code))
+                                                  T=self.T, H=H, W=W, k=kmax, Kpad=kpad, dtype=self.code, layout=1))
         self._conv([(patches.data_ptr(), kpad)], self._w(wp), self._f32(torch.cat(bfull)), x0.ptr, u.init_dim, rows,
                    1, 1, frames=self.T * H * W)
         self.pool.put(patches)

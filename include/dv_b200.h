@@ -138,8 +138,10 @@ typedef struct {
   void* out;       /* [B*T*H*W][Kpad] dtype */
   int B, C, T, H, W;
   int k;           /* window size (odd); pad = k/2 */
-  int Kpad;        /* >= k*k*C, multiple of 8 */
+  int Kpad;        /* row length, multiple of 8: >= k*k*C (layout 0) or >= C*k*16 (layout 1) */
   dv_dtype dtype;
+  int layout;      /* 0: K = (dy*k + dx)*C + c.   1: K = (c*k + dy)*16 + dx, dx padded to 16 (k <= 16):
+                      every 8-element group is one contiguous run of the input row -> shared-memory halo kernel */
 } dv_im2col_params;
 int dv_im2col_init(const dv_im2col_params* p, dv_stream_t stream);
 

@@ -427,7 +427,7 @@ def test_im2col_patch_matrix(dtype):
     x = rnd(B, C, T, H, W, seed=1)
     out = torch.full((B * T * H * W, Kpad), 7.0, dtype=dtype, device=dev())
     L.call("dv_im2col_init", L.Im2colParams(x=ptr(x), out=ptr(out), B=B, C=C, T=T, H=H, W=W, k=k, Kpad=Kpad,
-                                            dtype=code(out)), stream())
+                                            dtype=code(out), layout=0), stream())
     xp = F.pad(x, (k // 2, k // 2, k // 2, k // 2))
     cols = torch.stack([xp[:, :, :, dy:dy + H, dx:dx + W] for dy in range(k) for dx in range(k)], dim=-1)  # b c t h w tap
     ref = cols.permute(0, 2, 3, 4, 5, 1).reshape(B * T * H * W, k * k * C)
@@ -533,3 +533,22 @@ def test_mqa_flash_attention_tcgen05(S, n, H):
     p.q, p.out = ptr(q2), ptr(q2)
     L.call("dv_attn_mqa", p, stream())
     assert torch.equal(q2, out)
+
+
+@pytest.mark.parametrize("dtype", DT)
+@pytest.mark.parametrize("k,H", [(15, 8), (7, 6), (3, 4)])
+def test_im2col_halo_layout(dtype, k, H):
+    B, C, T, W = 2, 3, 2, 32
+    Kpad = (C * k * 16 + 63) // 64 * 64
+    x = rnd(B, C, T, H, W, seed=1)
+    out = torch.full((B * T * H * W, Kpad), 7.0, dtype=dtype, device=dev())
+    L.call("dv_im2col_init", L.Im2colParams(x=ptr(x), out=ptr(out), B=B, C=C, T=T, H=H, W=W, k=k, Kpad=Kpad,
+                                            dtype=code(out), layout=1), stream())
+    xp = F.pad(x, (k // 2, k // 2, k // 2, k // 2))
+    ref = torch.zeros(B, T, H, W, C, k, 16, device=dev())
+    for dy in range(k):
+        for dx in range(k):
+            ref[..., dy, dx] = xp[:, :, :, dy:dy + H, dx:dx + W].permute(0, 2, 3, 4, 1)
+    ref = ref.reshape(B * T * H * W, C * k * 16)
+    assert rel_err(out[:, :C * k * 16], ref.to(dtype)) == 0.0
+    assert float(out[:, C * k * 16:].abs().max()) == 0.0
