@@ -22,42 +22,74 @@ __device__ __forceinline__ float apply_act(float v, int act) {
   return v;
 }
 
-// One warp per output feature n; the warp walks the rows in chunks of MC so that the weight row is
-// read once per chunk.  Lanes stride over K (coalesced weight reads).
-constexpr int MC = 8;
-__global__ void __launch_bounds__(128) linear_small_kernel(dv_linear_small_params p) {
-  const int lane = threadIdx.x & 31;
-  const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (n >= p.N) return;
-  const float* w = p.w + (int64_t)n * p.K;
-  const float bias = p.bias ? p.bias[n] : 0.0f;
+// Batch-sized GEMM y[m][n] = post(sum_k pre(x[m][k]) * w[n][k] + b[n]) for M <= a few hundred rows.
+// lane = row m of a 32-row chunk (blockIdx.y), warp = LS_NPW consecutive outputs n.  pre(x) is evaluated
+// once per block into a transposed shared tile (xs[k][m], conflict-free), the weight rows are read with
+// warp-uniform 16-byte loads (one transaction per warp), so neither the activation nor the weights are
+// re-evaluated / re-read per row as a warp-per-output GEMV would.
+constexpr int LS_KT = 128;   // K tile staged in shared memory
+constexpr int LS_NPW = 4;    // outputs per warp
+constexpr int LS_WARPS = 8;
+__global__ void __launch_bounds__(LS_WARPS * 32) linear_small_kernel(dv_linear_small_params p) {
+  __shared__ float xs[LS_KT][33];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int M = p.M1 * p.M2;
-  for (int m0 = 0; m0 < M; m0 += MC) {
-    float acc[MC];
+  const int mbase = blockIdx.y * 32;
+  const int n0 = (blockIdx.x * LS_WARPS + warp) * LS_NPW;
+  const bool vec = (p.K & 3) == 0 && ((reinterpret_cast<uintptr_t>(p.w) & 15u) == 0);
+  const float* wrow[LS_NPW];
 #pragma unroll
-    for (int i = 0; i < MC; ++i) acc[i] = 0.f;
-    for (int k = lane; k < p.K; k += 32) {
-      const float wk = w[k];
+  for (int j = 0; j < LS_NPW; ++j) wrow[j] = p.w + (int64_t)min(n0 + j, p.N - 1) * p.K;
+  float acc[LS_NPW];
 #pragma unroll
-      for (int i = 0; i < MC; ++i) {
-        const int m = m0 + i;
-        if (m < M) {
-          const float xv = p.x[(int64_t)(m / p.M2) * p.ldx1 + (int64_t)(m % p.M2) * p.ldx2 + k];
-          acc[i] = fmaf(apply_act(xv, p.pre_act), wk, acc[i]);
+  for (int j = 0; j < LS_NPW; ++j) acc[j] = 0.f;
+  for (int k0 = 0; k0 < p.K; k0 += LS_KT) {
+    const int kn = min(LS_KT, p.K - k0);
+    for (int idx = threadIdx.x; idx < 32 * LS_KT; idx += LS_WARPS * 32) {
+      const int mm = idx / LS_KT, kk = idx % LS_KT;
+      const int m = mbase + mm;
+      float v = 0.f;
+      if (m < M && kk < kn)
+        v = apply_act(p.x[(int64_t)(m / p.M2) * p.ldx1 + (int64_t)(m % p.M2) * p.ldx2 + k0 + kk], p.pre_act);
+      xs[kk][mm] = v;
+    }
+    __syncthreads();
+    if (n0 < p.N) {
+      if (vec) {
+#pragma unroll 4
+        for (int kk = 0; kk < kn; kk += 4) {
+          const float x0 = xs[kk][lane], x1 = xs[kk + 1][lane], x2 = xs[kk + 2][lane], x3 = xs[kk + 3][lane];
+#pragma unroll
+          for (int j = 0; j < LS_NPW; ++j) {
+            const float4 wv = __ldg(reinterpret_cast<const float4*>(wrow[j] + k0 + kk));
+            acc[j] = fmaf(x0, wv.x, acc[j]);
+            acc[j] = fmaf(x1, wv.y, acc[j]);
+            acc[j] = fmaf(x2, wv.z, acc[j]);
+            acc[j] = fmaf(x3, wv.w, acc[j]);
+          }
+        }
+      } else {
+        for (int kk = 0; kk < kn; ++kk) {
+          const float xv = xs[kk][lane];
+#pragma unroll
+          for (int j = 0; j < LS_NPW; ++j) acc[j] = fmaf(xv, __ldg(wrow[j] + k0 + kk), acc[j]);
         }
       }
     }
+    __syncthreads();
+  }
+  const int m = mbase + lane;
+  if (m >= M) return;
+  const int m1 = m / p.M2, m2 = m % p.M2;
+  float* y = p.y + (int64_t)m1 * p.ldy1 + (int64_t)m2 * p.ldy2;
 #pragma unroll
-    for (int i = 0; i < MC; ++i) {
-      const float s = warp_sum(acc[i]);
-      const int m = m0 + i;
-      if (lane == 0 && m < M) {
-        float v = apply_act(s + bias, p.post_act);
-        if (p.keep && !p.keep[m / p.M2]) v = p.alt[(int64_t)(m % p.M2) * p.N + n];
-        if (p.accum) v += p.accum[(int64_t)m * p.N + n];
-        p.y[(int64_t)(m / p.M2) * p.ldy1 + (int64_t)(m % p.M2) * p.ldy2 + n] = v;
-      }
-    }
+  for (int j = 0; j < LS_NPW; ++j) {
+    const int n = n0 + j;
+    if (n >= p.N) break;
+    float v = apply_act(acc[j] + (p.bias ? p.bias[n] : 0.0f), p.post_act);
+    if (p.keep && !p.keep[m1]) v = p.alt[(int64_t)m2 * p.N + n];
+    if (p.accum) v += p.accum[(int64_t)m * p.N + n];
+    y[n] = v;
   }
 }
 
@@ -159,7 +191,9 @@ extern "C" int dv_linear_small(const dv_linear_small_params* p, dv_stream_t stre
   DV_REQUIRE(!p->keep || p->alt, DV_EINVAL, "dv_linear_small: keep needs alt");
   DV_REQUIRE(p->pre_act >= 0 && p->pre_act <= 2 && p->post_act >= 0 && p->post_act <= 2, DV_EINVAL,
              "dv_linear_small: bad activation");
-  linear_small_kernel<<<(p->N + 3) / 4, 128, 0, as_stream(stream)>>>(*p);
+  const int M = p->M1 * p->M2;
+  dim3 grid((p->N + LS_WARPS * LS_NPW - 1) / (LS_WARPS * LS_NPW), (M + 31) / 32);
+  linear_small_kernel<<<grid, LS_WARPS * 32, 0, as_stream(stream)>>>(*p);
   DV_CHECK_LAUNCH("dv_linear_small");
   return DV_OK;
 }
