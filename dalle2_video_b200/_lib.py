@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libdv_b200.so")
 
 DV_F32, DV_BF16 = 0, 1
-CONV_NORMAL, CONV_UNSHUFFLE, CONV_NCDHW_F32_IN = 0, 1, 2
+CONV_NORMAL, CONV_UNSHUFFLE, CONV_NCDHW_F32_IN, CONV_TEMPORAL = 0, 1, 2, 3
 EPI_STORE, EPI_SHUFFLE_SILU = 0, 1
 ACT_NONE, ACT_SILU, ACT_GELU = 0, 1, 2
 
@@ -70,6 +70,11 @@ class AttnMqaParams(C.Structure):
                 ("dtype", i32), ("impl", i32)]
 
 
+class AttnTemporalParams(C.Structure):
+    _fields_ = [("q", vp), ("kv", vp), ("out", vp), ("null_kv", vp), ("bias", vp), ("B", i32), ("T", i32), ("HW", i32),
+                ("heads", i32), ("dh", i32), ("scale", f32), ("dtype", i32), ("impl", i32)]
+
+
 class TimeEmbedParams(C.Structure):
     _fields_ = [("time", vp), ("t_dev", vp), ("freqs", vp), ("out", vp), ("B", i32), ("dim", i32)]
 
@@ -103,11 +108,12 @@ ENTRY_POINTS = {
     "dv_ddpm_step": DdpmStepParams, "dv_conv_igemm": ConvParams, "dv_gn_apply": GnApplyParams,
     "dv_gn_stats": GnStatsParams, "dv_layernorm": LayerNormParams, "dv_xattn_core": XattnParams,
     "dv_xattn_fold_prep": XattnFoldPrepParams, "dv_xattn_fold": XattnFoldParams,
-    "dv_attn_mqa": AttnMqaParams, "dv_time_embed": TimeEmbedParams, "dv_linear_small": LinearSmallParams,
+    "dv_attn_mqa": AttnMqaParams, "dv_attn_temporal": AttnTemporalParams,
+    "dv_time_embed": TimeEmbedParams, "dv_linear_small": LinearSmallParams,
     "dv_cond_tokens": CondTokensParams, "dv_to_out": ToOutParams, "dv_im2col_init": Im2colParams,
 }
 PLAIN_SYMBOLS = ("dv_version", "dv_last_error_string", "dv_device_sm_count", "dv_conv_uses_tcgen05",
-                 "dv_attn_mqa_workspace_bytes")
+                 "dv_attn_mqa_workspace_bytes", "dv_attn_temporal_uses_mma")
 
 _lib = None
 _SYNC_EACH = bool(os.environ.get("DV_SYNC_EACH"))
@@ -141,6 +147,8 @@ def lib():
         _lib.dv_conv_uses_tcgen05.restype = i32
         _lib.dv_attn_mqa_workspace_bytes.argtypes = [C.POINTER(AttnMqaParams)]
         _lib.dv_attn_mqa_workspace_bytes.restype = i64
+        _lib.dv_attn_temporal_uses_mma.argtypes = [C.POINTER(AttnTemporalParams)]
+        _lib.dv_attn_temporal_uses_mma.restype = i32
     return _lib
 
 

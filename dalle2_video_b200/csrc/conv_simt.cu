@@ -85,7 +85,7 @@ __global__ void __launch_bounds__(NT) conv_simt_kernel(dv_conv_params p, ConvGeo
         float v = 0.0f;
         if (arow_ok && k < g.Ktot) {
           const int tap = k / p.C0, c = k % p.C0;
-          const int iy = a_oy + tap / p.kw - p.pad, ix = a_ox + tap % p.kw - p.pad;
+          const int iy = a_oy + tap / p.kw - (p.kh >> 1), ix = a_ox + tap % p.kw - (p.kw >> 1);
           if (iy >= 0 && iy < p.H && ix >= 0 && ix < p.W)
             v = src[(((int64_t)b_idx * p.C0 + c) * nfr + t_idx) * plane + (int64_t)iy * p.W + ix];
         }
@@ -109,8 +109,8 @@ __global__ void __launch_bounds__(NT) conv_simt_kernel(dv_conv_params p, ConvGeo
         iy = 2 * a_oy + tap / 2;
         ix = 2 * a_ox + tap % 2;
       } else {
-        iy = a_oy + tap / p.kw - p.pad;
-        ix = a_ox + tap % p.kw - p.pad;
+        iy = a_oy + tap / p.kw - (p.kh >> 1);
+        ix = a_ox + tap % p.kw - (p.kw >> 1);
       }
       const bool in_ok = arow_ok && iy >= 0 && iy < p.H && ix >= 0 && ix < p.W;
       const int64_t pix = ((int64_t)a_img * p.H + iy) * p.W + ix;
@@ -224,6 +224,18 @@ static bool halo_enabled() {
   return v != 0;
 }
 
+// DV_CONV_TEMPORAL -> the NORMAL kernel on the (n_img = B, H = T, W = H*W) view with a kh x 1 'same' filter.
+static void rewrite_temporal(dv_conv_params* p) {
+  if (p->mode != DV_CONV_TEMPORAL || p->frames <= 0) return;
+  p->W = p->H * p->W;
+  p->H = p->frames;
+  p->n_img = p->n_img / p->frames;
+  p->frames = 1;
+  p->kw = 1;
+  p->pad = p->kh / 2;
+  p->mode = DV_CONV_NORMAL;
+}
+
 static int validate_conv(const dv_conv_params* p, ConvGeom* g) {
   DV_REQUIRE(p && p->src0 && p->weight && p->out, DV_EINVAL, "dv_conv_igemm: null pointer");
   DV_REQUIRE(p->dtype == DV_F32 || p->dtype == DV_BF16, DV_EINVAL, "dv_conv_igemm: bad dtype");
@@ -238,8 +250,8 @@ static int validate_conv(const dv_conv_params* p, ConvGeom* g) {
   g->Ho = p->H;
   g->Wo = p->W;
   if (p->mode == DV_CONV_NORMAL) {
-    DV_REQUIRE(p->kh >= 1 && p->kw >= 1 && p->pad >= 0 && p->kh == 2 * p->pad + 1 && p->kw == 2 * p->pad + 1,
-               DV_EUNSUPPORTED, "dv_conv_igemm: only 'same' odd kernels (kh=kw=2*pad+1) are supported");
+    DV_REQUIRE(p->kh >= 1 && p->kw >= 1 && p->pad >= 0 && p->kh == 2 * p->pad + 1 && (p->kw == p->kh || p->kw == 1),
+               DV_EUNSUPPORTED, "dv_conv_igemm: only 'same' odd kernels (kh=2*pad+1, kw=kh or 1) are supported");
     DV_REQUIRE(p->C0 % 16 == 0 && p->C1 % 16 == 0, DV_EALIGN,
                "dv_conv_igemm: channel counts (%d,%d) must be multiples of 16", p->C0, p->C1);
     g->ntaps = p->kh * p->kw;
@@ -277,8 +289,12 @@ static int validate_conv(const dv_conv_params* p, ConvGeom* g) {
 
 }  // namespace dv
 
-extern "C" int dv_conv_uses_tcgen05(const dv_conv_params* p) {
+extern "C" int dv_conv_uses_tcgen05(const dv_conv_params* pin) {
   dv::ConvGeom g;
+  if (!pin) return 0;
+  dv_conv_params q = *pin;
+  dv::rewrite_temporal(&q);
+  const dv_conv_params* p = &q;
   if (dv::validate_conv(p, &g) != DV_OK) return 0;
   if (p->impl == 1) return 0;
   return dv::conv_tc_supported(*p) || (dv::halo_enabled() && dv::conv_halo_supported(*p));
@@ -287,9 +303,14 @@ extern "C" int dv_conv_uses_tcgen05(const dv_conv_params* p) {
 extern "C" int dv_conv_igemm(const dv_conv_params* pin, dv_stream_t stream) {
   using namespace dv;
   ConvGeom g;
-  int rc = validate_conv(pin, &g);
-  if (rc != DV_OK) return rc;
+  DV_REQUIRE(pin, DV_EINVAL, "dv_conv_igemm: null params");
   dv_conv_params p = *pin;
+  if (p.mode == DV_CONV_TEMPORAL)
+    DV_REQUIRE(p.frames > 0 && p.n_img % p.frames == 0 && p.kh % 2 == 1 && p.epilogue == DV_EPI_STORE, DV_EINVAL,
+               "dv_conv_igemm: temporal mode needs an odd frame kernel, n_img %% frames == 0 and the plain epilogue");
+  rewrite_temporal(&p);
+  int rc = validate_conv(&p, &g);
+  if (rc != DV_OK) return rc;
   if (p.out_ld == 0) p.out_ld = (p.epilogue == DV_EPI_SHUFFLE_SILU) ? p.Cout / 4 : p.Cout;
   DV_REQUIRE(p.out_ld % 4 == 0 && p.out_coff % 4 == 0, DV_EALIGN, "dv_conv_igemm: out_ld/out_coff must be multiples of 4");
   cudaStream_t s = as_stream(stream);

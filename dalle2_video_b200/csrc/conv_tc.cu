@@ -29,7 +29,7 @@ constexpr int TC_TAIL_BYTES = 2 * TC_SLAB_BYTES + 1024 /*bias*/ + 1024 /*barrier
 
 struct TcParams {
   // problem
-  int ntaps, kw, pad, mode;
+  int ntaps, kw, pad, pad_w, mode;
   int H, W;              // input spatial size
   int Ho, Wo;            // output spatial size
   int c0_chunks, c1_chunks;
@@ -127,7 +127,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
                 // view (2C, W/2, 2, H/2, N): tap = s1, the 2C run covers (s2, c); chunk index walks it
                 tma_load_5d(map, &full_bar[stage], sa, c * TC_BK, x0, tap, y0, img0);
               } else {
-                const int dy = tap / p.kw - p.pad, dx = tap % p.kw - p.pad;
+                const int dy = tap / p.kw - p.pad, dx = tap % p.kw - p.pad_w;
                 tma_load_5d(map, &full_bar[stage], sa, c * TC_BK, x0 + dx, y0 + dy, img0, 0);
               }
               tma_load_2d(&map_b, &full_bar[stage], sa + a_bytes, kcol, n_tile * p.BN);
@@ -399,7 +399,7 @@ int conv_tc_supported(const dv_conv_params& p) {
     if (p.H % 2 || p.W % 2 || p.C1) return 0;
     Ho /= 2;
     Wo /= 2;
-  } else if (p.kh != p.kw || p.kh != 2 * p.pad + 1) {
+  } else if ((p.kh != p.kw && p.kw != 1) || p.kh != 2 * p.pad + 1) {
     return 0;
   }
   TileGeom g;
@@ -492,7 +492,7 @@ int conv_tc_launch(const dv_conv_params& p, cudaStream_t s) {
   TcParams t;
   memset(&t, 0, sizeof(t));
   t.ntaps = (p.mode == DV_CONV_UNSHUFFLE) ? 2 : p.kh * p.kw;
-  t.kw = p.kw; t.pad = p.pad; t.mode = p.mode;
+  t.kw = p.kw; t.pad = p.kh / 2; t.pad_w = p.kw / 2; t.mode = p.mode;
   t.H = p.H; t.W = p.W; t.Ho = Ho; t.Wo = Wo;
   if (p.mode == DV_CONV_UNSHUFFLE) {
     t.c0_chunks = 2 * p.C0 / TC_BK;  // one "tap" per s1, each a run of 2*C0 channels (s2, c)

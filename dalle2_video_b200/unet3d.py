@@ -71,6 +71,38 @@ class _SelfAttn(nn.Module):
         self.to_out = nn.Sequential(nn.Linear(inner, dim, bias=False), _Gain(dim))
 
 
+class _RelPosBias(nn.Module):
+    """Parameters of dalle2_pytorch.RelPosBias: an Embedding(num_buckets, heads) looked up by the
+    T5-style one-sided bucket of (key position - query position)."""
+
+    def __init__(self, heads, num_buckets=32, max_distance=128):
+        super().__init__()
+        self.num_buckets, self.max_distance = num_buckets, max_distance
+        self.relative_attention_bias = nn.Embedding(num_buckets, heads)
+
+    def table(self, i, j):
+        """(heads, i, j) bias table — index arithmetic of the upstream class, evaluated once per plan."""
+        w = self.relative_attention_bias.weight.detach()
+        q_pos = torch.arange(i, dtype=torch.long, device=w.device)
+        k_pos = torch.arange(j, dtype=torch.long, device=w.device)
+        n = (-(k_pos[None, :] - q_pos[:, None])).clamp_min(0)
+        max_exact = self.num_buckets // 2
+        large = max_exact + (torch.log(n.float() / max_exact) / math.log(self.max_distance / max_exact)
+                             * (self.num_buckets - max_exact)).long()
+        large = large.clamp_max(self.num_buckets - 1)
+        bucket = torch.where(n < max_exact, n, large)
+        return w[bucket].permute(2, 0, 1).contiguous()
+
+
+class _TemporalAttn(_SelfAttn):
+    """EXTENSION: the same multi-query Attention applied to '(b h w) t c'
+    sequences with attn_bias = RelPosBias(heads)(T, T+1)."""
+
+    def __init__(self, dim, heads, dim_head):
+        super().__init__(dim, heads, dim_head)
+        self.rel_pos_bias = _RelPosBias(heads)
+
+
 class _Fn(nn.Module):
     """`.fn` wrapper level (RearrangeToSequence / Residual in the reference) — naming only."""
 
@@ -80,20 +112,22 @@ class _Fn(nn.Module):
 
 
 class _Block(nn.Module):
-    def __init__(self, dim, dim_out, groups):
+    def __init__(self, dim, dim_out, groups, temporal_conv=False):
         super().__init__()
         self.project = nn.Conv3d(dim, dim_out, kernel_size=(1, 3, 3), padding=(0, 1, 1))
+        if temporal_conv:  # EXTENSION (section 8-pre item 1b): pseudo-3D = spatial conv then a (3,1,1) frame conv
+            self.temporal = nn.Conv3d(dim_out, dim_out, kernel_size=(3, 1, 1), padding=(1, 0, 0))
         self.norm = nn.GroupNorm(groups, dim_out)
 
 
 class _ResBlock(nn.Module):
-    def __init__(self, dim, dim_out, *, cond_dim=None, time_cond_dim=None, groups=8):
+    def __init__(self, dim, dim_out, *, cond_dim=None, time_cond_dim=None, groups=8, temporal_conv=False):
         super().__init__()
         self.dim, self.dim_out, self.groups = dim, dim_out, groups
         self.time_mlp = nn.Sequential(nn.SiLU(), nn.Linear(time_cond_dim, dim_out * 2)) if time_cond_dim else None
         self.cross_attn = _CrossAttn(dim_out, cond_dim) if cond_dim else None
-        self.block1 = _Block(dim, dim_out, groups)
-        self.block2 = _Block(dim_out, dim_out, groups)
+        self.block1 = _Block(dim, dim_out, groups, temporal_conv)
+        self.block2 = _Block(dim_out, dim_out, groups, temporal_conv)
         self.res_conv = nn.Conv3d(dim, dim_out, 1) if dim != dim_out else nn.Identity()
 
 
@@ -134,7 +168,14 @@ class Unet3D(nn.Module):
                  init_cross_embed_kernel_sizes=(3, 7, 15), cross_embed_downsample=False,
                  cross_embed_downsample_kernel_sizes=(2, 4), memory_efficient=False, scale_skip_connection=False,
                  pixel_shuffle_upsample=True, final_conv_ksize=1, combine_upsample_fmaps=False,
-                 checkpoint_during_training=False, **kwargs):
+                 checkpoint_during_training=False, temporal_conv=False, temporal_attn=False, attn_mode="joint",
+                 **kwargs):
+        """`temporal_conv`, `temporal_attn`, `attn_mode` are EXTENSIONS that the reference Unet3D does not have
+        (SURVEY.md section 8-pre items 1b / 3 / 2a), all default off = reference behaviour:
+          temporal_conv   every Block3D becomes conv(1,3,3) -> conv(3,1,1) -> GroupNorm (pseudo-3D);
+          temporal_attn   bool or per-stage tuple: a Residual temporal Attention with RelPosBias after the
+                          stage's blocks (and after mid_attn when any stage has one);
+          attn_mode       "joint" (reference: one sequence of T*H*W tokens) or "factorised" (per-frame H*W)."""
         super().__init__()
         self._locals = {k: v for k, v in locals().items() if k not in ("self", "__class__")}
 
@@ -207,7 +248,19 @@ class Unet3D(nn.Module):
         num_resnet_blocks = _cast_tuple(num_resnet_blocks, n_stages)
         self._stage_self_attn, self._stage_groups, self._stage_blocks = self_attn, resnet_groups, num_resnet_blocks
         make_attn = lambda d: _Fn(_Fn(_SelfAttn(d, attn_heads, attn_dim_head)))  # noqa: E731
-        res = partial(_ResBlock, time_cond_dim=time_cond_dim)
+        res = partial(_ResBlock, time_cond_dim=time_cond_dim, temporal_conv=temporal_conv)
+        assert attn_mode in ("joint", "factorised"), "attn_mode must be 'joint' or 'factorised'"
+        self.attn_mode, self.temporal_conv = attn_mode, temporal_conv
+        temporal_attn = _cast_tuple(temporal_attn, n_stages)
+        self._stage_temporal_attn = temporal_attn
+        make_tattn = lambda d: _TemporalAttn(d, attn_heads, attn_dim_head)  # noqa: E731
+        if any(temporal_attn):
+            dims_all = [dim * m for m in dim_mults]
+            self.down_temporal_attns = nn.ModuleList([make_tattn(d) if f else nn.Identity()
+                                                      for d, f in zip(dims[:-1], temporal_attn)])
+            self.mid_temporal_attn = make_tattn(dims_all[-1])
+            self.up_temporal_attns = nn.ModuleList([make_tattn(d) if f else nn.Identity()
+                                                    for d, f in zip(reversed(dims_all), reversed(temporal_attn))])
 
         self.init_resnet_block = None
         self.downs = nn.ModuleList([])
@@ -449,7 +502,8 @@ class _Engine:
         p = L.ConvParams(src0=srcs[0][0], src1=srcs[1][0] if len(srcs) > 1 else None, weight=weight.data_ptr(),
                          bias=bias.data_ptr() if bias is not None else None, add=add, out=out_ptr, stats=stats,
                          n_img=n_img, frames=frames or self.T, H=H, W=W, C0=srcs[0][1],
-                         C1=srcs[1][1] if len(srcs) > 1 else 0, Cout=Cout, kh=k, kw=k, pad=k // 2, mode=mode,
+                         C1=srcs[1][1] if len(srcs) > 1 else 0, Cout=Cout, kh=k,
+                         kw=1 if mode == L.CONV_TEMPORAL else k, pad=k // 2, mode=mode,
                          epilogue=epilogue, groups=groups, out_ld=out_ld, out_coff=out_coff,
                          dtype=self.code if dtype_code is None else dtype_code, impl=self.impl)
         Ho, Wo = (H // 2, W // 2) if mode == L.CONV_UNSHUFFLE else (H, W)
@@ -637,6 +691,8 @@ class _Engine:
                 hiddens.append(x)
             if not isinstance(st[3], nn.Identity):
                 x = self._self_attention(st[3].fn.fn, x, h, w)
+            if u._stage_temporal_attn[s]:
+                x = self._self_attention(u.down_temporal_attns[s], x, h, w, mode="temporal")
             x.refs += 1
             hiddens.append(x)
             post = st[4]
@@ -661,6 +717,8 @@ class _Engine:
 
         x = self._resblock(u.mid_block1, [x], h, w)
         x = self._self_attention(u.mid_attn.fn.fn, x, h, w)
+        if any(u._stage_temporal_attn):
+            x = self._self_attention(u.mid_temporal_attn, x, h, w, mode="temporal")
         x = self._resblock(u.mid_block2, [x], h, w)
 
         for s, st in enumerate(u.ups):
@@ -671,6 +729,8 @@ class _Engine:
                 x = self._resblock(m, [x, skip], h, w)
             if not isinstance(st[2], nn.Identity):
                 x = self._self_attention(st[2].fn.fn, x, h, w)
+            if u._stage_temporal_attn[n_st - 1 - s]:
+                x = self._self_attention(u.up_temporal_attns[s], x, h, w, mode="temporal")
             up = st[3]
             if not isinstance(up, nn.Identity):
                 conv = up.conv
@@ -750,10 +810,8 @@ class _Engine:
         assert sum(a.C for a in srcs) == m.dim
         off = self._ss_off(m)
 
-        h1 = self._new_act(rows, Co)
-        st1 = self._next_stats()
-        self._conv(src_list, self._w(self._pack_conv(m.block1.project.weight, skip_scale, c0)),
-                   self._f32(m.block1.project.bias), h1.ptr, Co, n_img, h, w, k=3, stats=st1, groups=G)
+        h1, st1 = self._block_convs(m.block1, src_list, self._pack_conv(m.block1.project.weight, skip_scale, c0),
+                                    rows, Co, n_img, h, w, G)
         self._op("dv_gn_apply", L.GnApplyParams(
             x=h1.ptr, out=h1.ptr, residual=None, stats=st1, gamma=self._f32(m.block1.norm.weight).data_ptr(),
             beta=self._f32(m.block1.norm.bias).data_ptr(), scale=self.ss.data_ptr() + off * 4,
@@ -762,10 +820,8 @@ class _Engine:
         if m.cross_attn is not None:
             self._cross_attention(m, h1, rows, P)
 
-        h2 = self._new_act(rows, Co)
-        st2 = self._next_stats()
-        self._conv([(h1.ptr, Co)], self._w(self._pack_conv(m.block2.project.weight)), self._f32(m.block2.project.bias),
-                   h2.ptr, Co, n_img, h, w, k=3, stats=st2, groups=G)
+        h2, st2 = self._block_convs(m.block2, [(h1.ptr, Co)], self._pack_conv(m.block2.project.weight), rows, Co,
+                                    n_img, h, w, G)
         self._release(h1)
         if isinstance(m.res_conv, nn.Identity):
             assert len(srcs) == 1
@@ -787,6 +843,24 @@ class _Engine:
         for a in srcs:
             self._release(a)
         return h2
+
+    def _block_convs(self, blk: _Block, src_list, wpacked, rows, Co, n_img, h, w, G):
+        """Block3D.project (:107,124) [+ the extension's (3,1,1) frame conv]; the LAST conv accumulates the
+        GroupNorm statistics.  Returns (activation, statistics slot)."""
+        st = self._next_stats()
+        temporal = getattr(blk, "temporal", None)
+        a = self._new_act(rows, Co)
+        self._conv(src_list, self._w(wpacked), self._f32(blk.project.bias), a.ptr, Co, n_img, h, w, k=3,
+                   stats=None if temporal is not None else st, groups=G)
+        if temporal is None:
+            return a, st
+        b = self._new_act(rows, Co)
+        kt = temporal.weight.shape[2]
+        wt = temporal.weight.detach()[:, :, :, 0, 0].permute(0, 2, 1).reshape(Co, kt * Co)  # K order [tap][cin]
+        self._conv([(a.ptr, Co)], self._w(wt), self._f32(temporal.bias), b.ptr, Co, n_img, h, w, k=kt,
+                   mode=L.CONV_TEMPORAL, stats=st, groups=G)
+        self._release(a)
+        return b, st
 
     def _ss_off(self, m):
         return self._ss_offsets[id(m)]
@@ -843,8 +917,11 @@ class _Engine:
             return 1e-3
         return 1e-5
 
-    def _self_attention(self, at: _SelfAttn, xact: _Act, h, w):
-        """x = Attention(x) + x over all T*h*w tokens of each sample (:430-432, :921-922), in place."""
+    def _self_attention(self, at: _SelfAttn, xact: _Act, h, w, mode=None):
+        """x = Attention(x) + x (:430-432, :921-922), in place.  mode "joint" (reference): one sequence of all
+        T*h*w tokens per sample; "factorised" (extension): one sequence of h*w tokens per frame; "temporal"
+        (extension): one sequence of T tokens per pixel with the relative-position bias table."""
+        mode = mode or self.u.attn_mode
         B, P = self.B, self.T * h * w
         rows, C = B * P, xact.C
         heads, dh = at.heads, at.dim_head
@@ -858,18 +935,25 @@ class _Engine:
         self._conv([(xn.ptr, C)], self._w(at.to_q.weight), None, q.ptr, inner, rows, 1, 1, frames=P)
         self._conv([(xn.ptr, C)], self._w(at.to_kv.weight), None, kvb.ptr, 2 * dh, rows, 1, 1, frames=P)
         # q*scale, then q,k *= sqrt(scale): logits = q.k * scale^2 = q.k / dim_head
-        ap = L.AttnMqaParams(q=q.ptr, kv=kvb.ptr, out=q.ptr, null_kv=self._f32(at.null_kv).data_ptr(), bias=None,
-                             workspace=None, workspace_bytes=0, S=B, n=P, heads=heads, dh=dh, scale=float(1.0 / dh),
-                             dtype=self.code, impl=0)
-        ws_bytes = L.lib().dv_attn_mqa_workspace_bytes(ap)
-        ws = None
-        if ws_bytes > 0:
-            ws = self.pool.get(ws_bytes)
-            ap.workspace, ap.workspace_bytes = ws.data_ptr(), ws_bytes
-            self.n_tc += 1
-        self._op("dv_attn_mqa", ap)
-        if ws is not None:
-            self.pool.put(ws)
+        if mode == "temporal":
+            bias = self._f32(at.rel_pos_bias.table(self.T, self.T + 1))
+            self._op("dv_attn_temporal", L.AttnTemporalParams(
+                q=q.ptr, kv=kvb.ptr, out=q.ptr, null_kv=self._f32(at.null_kv).data_ptr(), bias=bias.data_ptr(), B=B,
+                T=self.T, HW=h * w, heads=heads, dh=dh, scale=float(1.0 / dh), dtype=self.code, impl=0))
+        else:
+            S, n = (B, P) if mode == "joint" else (B * self.T, h * w)
+            ap = L.AttnMqaParams(q=q.ptr, kv=kvb.ptr, out=q.ptr, null_kv=self._f32(at.null_kv).data_ptr(), bias=None,
+                                 workspace=None, workspace_bytes=0, S=S, n=n, heads=heads, dh=dh,
+                                 scale=float(1.0 / dh), dtype=self.code, impl=0)
+            ws_bytes = L.lib().dv_attn_mqa_workspace_bytes(ap)
+            ws = None
+            if ws_bytes > 0:
+                ws = self.pool.get(ws_bytes)
+                ap.workspace, ap.workspace_bytes = ws.data_ptr(), ws_bytes
+                self.n_tc += 1
+            self._op("dv_attn_mqa", ap)
+            if ws is not None:
+                self.pool.put(ws)
         self._release(kvb)
         self._conv([(q.ptr, inner)], self._w(at.to_out[0].weight), None, xn.ptr, C, rows, 1, 1, frames=P)
         self._release(q)

@@ -92,6 +92,12 @@ int dv_ddpm_step(const dv_ddpm_step_params* p, dv_stream_t stream);
  * weight: [Cout][kh*kw*(C0+C1)] row-major, element type = act dtype (packed once on the host).
  * DV_CONV_UNSHUFFLE: 2x2 stride-2 gather (pixel-unshuffle), taps ordered [s1][s2], pad 0; out is H/2 x W/2.
  * DV_CONV_NCDHW_F32_IN: src0 is the (B,C0,T,H,W) float32 video tensor (K4 init conv), frames = T.
+ * DV_CONV_TEMPORAL (EXTENSION, default off in the host code): nn.Conv3d with a
+ *   (kh,1,1) kernel and 'same' padding along the frame axis, the form of UnetTemporalConv.temporal_conv (:966-972):
+ *   taps = kh frames, weight [Cout][kh*(C0+C1)]; inside the library it is the NORMAL kernel on the view
+ *   (n_img = B, H = T, W = H*W) with a kh x 1 filter, so the tcgen05 path, the fused statistics and the two-source
+ *   K loop all apply.
+ * NORMAL filters are 'same' per axis: kh and kw odd, pad = kh/2 rows and kw/2 columns (`pad` must equal kh/2).
  * Epilogues: bias; optional per-(sample,group) sum / sum-of-squares accumulation for the GroupNorm
  * that follows (double[B][groups][2], must be zeroed by the caller); optional residual add
  * (`add`, same layout as out); DV_EPI_SHUFFLE_SILU writes SiLU(v) to the 2x-upsampled tensor
@@ -100,7 +106,7 @@ int dv_ddpm_step(const dv_ddpm_step_params* p, dv_stream_t stream);
  * impl: 0 = auto (tensor cores when the shape qualifies, else SIMT), 1 = force SIMT, 2 = force the per-tap
  * tcgen05 kernel, 3 = force the streaming-halo tcgen05 kernel (3x3, Cout 64/128, W >= 32).
  */
-enum { DV_CONV_NORMAL = 0, DV_CONV_UNSHUFFLE = 1, DV_CONV_NCDHW_F32_IN = 2 };
+enum { DV_CONV_NORMAL = 0, DV_CONV_UNSHUFFLE = 1, DV_CONV_NCDHW_F32_IN = 2, DV_CONV_TEMPORAL = 3 };
 enum { DV_EPI_STORE = 0, DV_EPI_SHUFFLE_SILU = 1 };
 typedef struct {
   const void* src0;
@@ -292,6 +298,30 @@ typedef struct {
 int dv_attn_mqa(const dv_attn_mqa_params* p, dv_stream_t stream);
 /* scratch the tcgen05 path needs for these params (0 if it does not apply: bias, fp32, dh != 32, n % 128 != 0) */
 int64_t dv_attn_mqa_workspace_bytes(const dv_attn_mqa_params* p);
+
+/* ------------------------------------------------------------------------------------------------
+ * Temporal attention over the frame axis (EXTENSION, default off; SURVEY.md section 8-pre item 3 — the
+ * reference Unet3D has no temporal attention).  Semantics = the same upstream multi-query Attention
+ *  applied to "(b h w) t c" sequences with attn_bias = RelPosBias(heads)(T, T+1)
+ * (column 0 is the null key).  The channels-last buffers are read in place: the
+ * sequence of pixel (b, hw) is the T rows {((b*T + t)*HW + hw)}.
+ * q: [B][T][HW][heads*dh], kv: [B][T][HW][2*dh] (k then v), out like q (may alias q).
+ * bf16, dh = 32, T in {8,16,24,32}, heads % 4 == 0: warp-level mma.sync kernel with cp.async staging;
+ * anything else (fp32 parity mode, other T): CUDA-core kernel.
+ */
+typedef struct {
+  const void* q;
+  const void* kv;
+  void* out;
+  const float* null_kv; /* [2][dh] */
+  const float* bias;    /* [heads][T][T+1] float32 or NULL */
+  int B, T, HW, heads, dh;
+  float scale;          /* logits = scale * q.k + bias */
+  dv_dtype dtype;
+  int impl;             /* 0 auto, 1 force CUDA-core kernel, 2 force the mma.sync kernel */
+} dv_attn_temporal_params;
+int dv_attn_temporal(const dv_attn_temporal_params* p, dv_stream_t stream);
+int dv_attn_temporal_uses_mma(const dv_attn_temporal_params* p);
 
 /* ------------------------------------------------------------------------------------------------
  * K8  conditioning prologue pieces (float32 throughout; M = batch-sized GEMVs).

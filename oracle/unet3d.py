@@ -56,6 +56,11 @@ class UnetConfig:
     init_conv_ksize: int = 7
     scale_skip_connection: bool = False
     final_conv_ksize: int = 1
+    # extensions the reference Unet3D does not have (default off = reference behaviour);
+    # their oracle is the composition of reference / upstream primitives on rearranged tensors stated there
+    temporal_conv: bool = False      # Conv3d(C, C, (3,1,1), padding=(1,0,0)) after every Block3D.project
+    temporal_attn: object = False    # upstream Attention on "(b h w) t c" + RelPosBias(heads)(t, t+1)
+    attn_mode: str = "joint"         # "factorised": the same Attention on "(b t) (h w) c"
     extra: dict = field(default_factory=dict)
 
     @property
@@ -138,6 +143,8 @@ def _untokens(tok, like):
 def _block(sd, p, x, groups, scale_shift=None):
     """Block3D.forward (dalle2_video.py:112-133)."""
     x = F.conv3d(x, sd[p + "project.weight"], sd[p + "project.bias"], padding=(0, 1, 1))
+    if (p + "temporal.weight") in sd:  # extension 1b: the form of UnetTemporalConv.temporal_conv (:966-972)
+        x = F.conv3d(x, sd[p + "temporal.weight"], sd[p + "temporal.bias"], padding=(1, 0, 0))
     x = F.group_norm(x, groups, sd[p + "norm.weight"], sd[p + "norm.bias"])
     if scale_shift is not None:
         scale, shift = scale_shift
@@ -163,11 +170,36 @@ def _resnet_block(sd, p, x, t_emb, cond, groups):
     return h + x
 
 
-def _joint_attention(sd, p, x, heads, dim_head):
-    """RearrangeToSequence(Residual(Attention)) (dalle2_video.py:430-432): joint over T*H*W."""
+def _joint_attention(sd, p, x, heads, dim_head, mode="joint"):
+    """RearrangeToSequence(Residual(Attention)) (dalle2_video.py:430-432): joint over T*H*W.
+    mode "factorised" (extension 2a): the same module on "(b t) (h w) c"."""
+    if mode == "factorised":
+        b, c, t, h, w = x.shape
+        tok = x.permute(0, 2, 3, 4, 1).reshape(b * t, h * w, c)
+        tok = _self_attention(sd, p + "fn.fn.", tok, heads, dim_head) + tok
+        return tok.reshape(b, t, h, w, c).permute(0, 4, 1, 2, 3)
     tok = _tokens(x)
     tok = _self_attention(sd, p + "fn.fn.", tok, heads, dim_head) + tok
     return _untokens(tok, x)
+
+
+def rel_pos_bias_table(weight, i, j, num_buckets=32, max_distance=128):
+    """RelPosBias.forward(i, j) (oracle/primitives.py) from the embedding weight -> (heads, i, j)."""
+    from .primitives import RelPosBias
+    q_pos = torch.arange(i, dtype=torch.long)
+    k_pos = torch.arange(j, dtype=torch.long)
+    bucket = RelPosBias._relative_position_bucket(k_pos[None, :] - q_pos[:, None], num_buckets=num_buckets,
+                                                  max_distance=max_distance)
+    return weight[bucket.to(weight.device)].permute(2, 0, 1)
+
+
+def _temporal_attention(sd, p, x, heads, dim_head):
+    """Extension 3: Residual(Attention) on "(b h w) t c" with attn_bias = RelPosBias(heads)(t, t+1)."""
+    b, c, t, h, w = x.shape
+    tok = x.permute(0, 3, 4, 2, 1).reshape(b * h * w, t, c)
+    bias = rel_pos_bias_table(sd[p + "rel_pos_bias.relative_attention_bias.weight"], t, t + 1)
+    tok = _self_attention(sd, p, tok, heads, dim_head, attn_bias=bias) + tok
+    return tok.reshape(b, h, w, t, c).permute(0, 4, 3, 1, 2)
 
 
 def _pixel_unshuffle_down(sd, p, x):
@@ -198,6 +230,7 @@ def unet3d_forward(sd, cfg: UnetConfig, x, time, *, video_embed=None, text_encod
     groups = _tup(cfg.resnet_groups, n)
     n_blocks = _tup(cfg.num_resnet_blocks, n)
     self_attn = _tup(cfg.self_attn, n)
+    t_attn = _tup(cfg.temporal_attn, n)
 
     if cfg.self_cond:
         x = torch.cat((x, self_cond if self_cond is not None else torch.zeros_like(x)), dim=1)
@@ -267,7 +300,9 @@ def unet3d_forward(sd, cfg: UnetConfig, x, time, *, video_embed=None, text_encod
             x = _resnet_block(sd, f"downs.{s}.2.{j}.", x, t, c, groups[s])
             hiddens.append(x)
         if self_attn[s]:
-            x = _joint_attention(sd, f"downs.{s}.3.", x, cfg.attn_heads, cfg.attn_dim_head)
+            x = _joint_attention(sd, f"downs.{s}.3.", x, cfg.attn_heads, cfg.attn_dim_head, cfg.attn_mode)
+        if t_attn[s]:
+            x = _temporal_attention(sd, f"down_temporal_attns.{s}.", x, cfg.attn_heads, cfg.attn_dim_head)
         hiddens.append(x)
         if s < n - 1:
             x = _pixel_unshuffle_down(sd, f"downs.{s}.4.", x)
@@ -277,7 +312,9 @@ def unet3d_forward(sd, cfg: UnetConfig, x, time, *, video_embed=None, text_encod
     # middle (:919-924)
     x = _resnet_block(sd, "mid_block1.", x, t, mid_c, groups[-1])
     # mid_attn is built and applied unconditionally: `attend_at_middle` is accepted but never read (:551, :921)
-    x = _joint_attention(sd, "mid_attn.", x, cfg.attn_heads, cfg.attn_dim_head)
+    x = _joint_attention(sd, "mid_attn.", x, cfg.attn_heads, cfg.attn_dim_head, cfg.attn_mode)
+    if any(t_attn):
+        x = _temporal_attention(sd, "mid_temporal_attn.", x, cfg.attn_heads, cfg.attn_dim_head)
     x = _resnet_block(sd, "mid_block2.", x, t, mid_c, groups[-1])
 
     # up path (:930-941)
@@ -289,7 +326,9 @@ def unet3d_forward(sd, cfg: UnetConfig, x, time, *, video_embed=None, text_encod
             x = torch.cat((x, hiddens.pop() * skip_scale), dim=1)
             x = _resnet_block(sd, f"ups.{s}.1.{j}.", x, t, c, rgroups[s])
         if rattn[s]:
-            x = _joint_attention(sd, f"ups.{s}.2.", x, cfg.attn_heads, cfg.attn_dim_head)
+            x = _joint_attention(sd, f"ups.{s}.2.", x, cfg.attn_heads, cfg.attn_dim_head, cfg.attn_mode)
+        if t_attn[n - 1 - s]:
+            x = _temporal_attention(sd, f"up_temporal_attns.{s}.", x, cfg.attn_heads, cfg.attn_dim_head)
         if s < n - 1:
             x = _pixel_shuffle_up(sd, f"ups.{s}.3.", x)
 
