@@ -10,6 +10,7 @@ from .attention import AttentionBlock
 from .decoder import NullVQGanVAE, VideoDecoder
 from .parallel import shard_rows
 from .scheduler import NoiseScheduler
+from .train import VideoDecoderTrainer
 from .unet3d import Unet3D
 
-__all__ = ["Unet3D", "VideoDecoder", "NoiseScheduler", "NullVQGanVAE", "shard_rows", "AttentionBlock"]
+__all__ = ["Unet3D", "VideoDecoder", "NoiseScheduler", "NullVQGanVAE", "shard_rows", "AttentionBlock", "VideoDecoderTrainer"]

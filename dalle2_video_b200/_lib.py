@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(HERE, "libdv_b200.so")
 
 DV_F32, DV_BF16 = 0, 1
 CONV_NORMAL, CONV_UNSHUFFLE, CONV_NCDHW_F32_IN, CONV_TEMPORAL = 0, 1, 2, 3
-EPI_STORE, EPI_SHUFFLE_SILU = 0, 1
+EPI_STORE, EPI_SHUFFLE_SILU, EPI_SHUFFLE = 0, 1, 2
 ACT_NONE, ACT_SILU, ACT_GELU = 0, 1, 2
 
 vp, i32, i64, f32 = C.c_void_p, C.c_int, C.c_int64, C.c_float
@@ -103,6 +103,79 @@ class ToOutParams(C.Structure):
                 ("dtype", i32)]
 
 
+f64p = vp
+
+
+class ConvWgradParams(C.Structure):
+    _fields_ = [("src0", vp), ("src1", vp), ("dy", vp), ("dw", vp), ("n_img", i32), ("H", i32), ("W", i32), ("C0", i32),
+                ("C1", i32), ("Cout", i32), ("kh", i32), ("kw", i32), ("mode", i32), ("dtype", i32)]
+
+
+class ColsumParams(C.Structure):
+    _fields_ = [("x", vp), ("out", vp), ("rows", i64), ("C", i32), ("dtype", i32)]
+
+
+class GnBwdParams(C.Structure):
+    _fields_ = [("x", vp), ("dy", vp), ("dx", vp), ("stats", vp), ("gamma", vp), ("beta", vp), ("scale", vp),
+                ("shift", vp), ("sums", vp), ("dgamma", vp), ("dbeta", vp), ("dscale", vp), ("dshift", vp),
+                ("ss_ld", i32), ("dss_ld", i32), ("B", i32), ("P", i64), ("C", i32), ("groups", i32), ("eps", f32),
+                ("accumulate", i32), ("dtype", i32)]
+
+
+class LayerNormBwdParams(C.Structure):
+    _fields_ = [("x", vp), ("dy", vp), ("dx", vp), ("g", vp), ("dg", vp), ("rows", i64), ("C", i32), ("eps", f32),
+                ("accumulate", i32), ("dtype", i32)]
+
+
+class XattnBwdParams(C.Structure):
+    _fields_ = [("q", vp), ("dout", vp), ("dq", vp), ("kv", vp), ("dkv", vp), ("null_kv", vp), ("dnull_kv", vp),
+                ("B", i32), ("P", i64), ("heads", i32), ("dh", i32), ("n_ctx", i32), ("kv_ld", i64), ("k_off", i32),
+                ("v_off", i32), ("scale", f32), ("dtype", i32)]
+
+
+class AttnMqaBwdParams(C.Structure):
+    _fields_ = [("q", vp), ("kv", vp), ("out", vp), ("dout", vp), ("dq", vp), ("dkv", vp), ("null_kv", vp),
+                ("dnull_kv", vp), ("rowstats", vp), ("S", i64), ("n", i32), ("heads", i32), ("dh", i32),
+                ("scale", f32), ("dtype", i32)]
+
+
+class QSampleParams(C.Structure):
+    _fields_ = [("video", vp), ("noise", vp), ("times", vp), ("sqrt_ac", vp), ("sqrt_1mac", vp), ("out", vp),
+                ("n", i64), ("per_sample", i64), ("normalize", i32)]
+
+
+class MseLossParams(C.Structure):
+    _fields_ = [("pred", vp), ("target", vp), ("dpred", vp), ("loss", vp), ("n", i64), ("grad_scale", f32)]
+
+
+class ToOutBwdParams(C.Structure):
+    _fields_ = [("x", vp), ("w", vp), ("deps", vp), ("dx", vp), ("dw", vp), ("db", vp), ("B", i32), ("P", i64),
+                ("C", i32), ("Cout", i32), ("dtype", i32)]
+
+
+class SiluShuffleParams(C.Structure):
+    _fields_ = [("z", vp), ("out", vp), ("dz", vp), ("n_img", i32), ("H", i32), ("W", i32), ("Cq", i32),
+                ("dtype", i32)]
+
+
+class AddParams(C.Structure):
+    _fields_ = [("a", vp), ("b", vp), ("out", vp), ("n", i64), ("dtype", i32)]
+
+
+class CastParams(C.Structure):
+    _fields_ = [("src", vp), ("dst", vp), ("n", i64)]
+
+
+class SumsqParams(C.Structure):
+    _fields_ = [("x", vp), ("out", vp), ("n", i64)]
+
+
+class AdamwParams(C.Structure):
+    _fields_ = [("param", vp), ("grad", vp), ("exp_avg", vp), ("exp_avg_sq", vp), ("grad_sumsq", vp), ("n", i64),
+                ("lr", f32), ("beta1", f32), ("beta2", f32), ("eps", f32), ("weight_decay", f32),
+                ("bias_correction1", f32), ("bias_correction2", f32), ("max_grad_norm", f32)]
+
+
 # every symbol include/dv_b200.h declares: name -> params struct (None for the plain helpers)
 ENTRY_POINTS = {
     "dv_ddpm_step": DdpmStepParams, "dv_conv_igemm": ConvParams, "dv_gn_apply": GnApplyParams,
@@ -111,9 +184,15 @@ ENTRY_POINTS = {
     "dv_attn_mqa": AttnMqaParams, "dv_attn_temporal": AttnTemporalParams,
     "dv_time_embed": TimeEmbedParams, "dv_linear_small": LinearSmallParams,
     "dv_cond_tokens": CondTokensParams, "dv_to_out": ToOutParams, "dv_im2col_init": Im2colParams,
+    # training step (a16)
+    "dv_conv_wgrad": ConvWgradParams, "dv_colsum": ColsumParams, "dv_gn_bwd_reduce": GnBwdParams,
+    "dv_gn_bwd_apply": GnBwdParams, "dv_layernorm_bwd": LayerNormBwdParams, "dv_xattn_core_bwd": XattnBwdParams,
+    "dv_attn_mqa_bwd": AttnMqaBwdParams, "dv_q_sample": QSampleParams, "dv_mse_loss": MseLossParams,
+    "dv_to_out_bwd": ToOutBwdParams, "dv_silu_shuffle": SiluShuffleParams, "dv_silu_shuffle_bwd": SiluShuffleParams,
+    "dv_add": AddParams, "dv_cast_f32_bf16": CastParams, "dv_sumsq": SumsqParams, "dv_adamw": AdamwParams,
 }
 PLAIN_SYMBOLS = ("dv_version", "dv_last_error_string", "dv_device_sm_count", "dv_conv_uses_tcgen05",
-                 "dv_attn_mqa_workspace_bytes", "dv_attn_temporal_uses_mma")
+                 "dv_attn_mqa_workspace_bytes", "dv_attn_temporal_uses_mma", "dv_attn_mqa_bwd_workspace_bytes")
 
 _lib = None
 _SYNC_EACH = bool(os.environ.get("DV_SYNC_EACH"))
@@ -149,6 +228,8 @@ def lib():
         _lib.dv_attn_mqa_workspace_bytes.restype = i64
         _lib.dv_attn_temporal_uses_mma.argtypes = [C.POINTER(AttnTemporalParams)]
         _lib.dv_attn_temporal_uses_mma.restype = i32
+        _lib.dv_attn_mqa_bwd_workspace_bytes.argtypes = [C.POINTER(AttnMqaBwdParams)]
+        _lib.dv_attn_mqa_bwd_workspace_bytes.restype = i64
     return _lib
 
 

@@ -1,0 +1,325 @@
+// a16 (decoder training step) — backward of K2 (GroupNorm + scale/shift + SiLU [+ residual]) and of the gain-only
+// LayerNorm (a15).  Reference math: torch autograd through Block3D.forward (/root/reference/dalle2_video/
+// dalle2_video.py:112-133) and dalle2_pytorch.LayerNorm.
+//
+// GroupNorm block, forward:  xh = (x - mean_g) * rstd_g ;  u = xh*gamma + beta ;  v = u*(1+scale) + shift ;  y = SiLU(v)
+// backward with g_v = dy * SiLU'(v) and the two per-(sample, channel) sums  S1 = sum_pos g_v ,  S2 = sum_pos g_v * xh :
+//   dshift = S1                 dscale = gamma*S2 + beta*S1
+//   dbeta  = sum_b (1+scale)*S1  dgamma = sum_b (1+scale)*S2
+//   dx     = rstd * ( gamma*(1+scale)*g_v - m1 - xh*m2 ),  m1 / m2 = group means of gamma*(1+scale)*{S1,S2} / P
+// Three launches: reduce (streams x and dy once), params (tiny), apply (streams x, dy -> dx).  HBM-bound.
+#include "common.cuh"
+
+namespace dv {
+
+__device__ __forceinline__ float silu_grad(float v) {
+  const float s = 1.0f / (1.0f + __expf(-v));
+  return s * (1.0f + v * (1.0f - s));
+}
+
+struct GnCoef {  // per-channel forward coefficients: xh = x*rs - mr ; v = x*a + d
+  float rs, mr, a, d;
+};
+
+__device__ __forceinline__ GnCoef gn_coef(const dv_gn_bwd_params& p, int b, int c) {
+  const int cpg = p.C / p.groups;
+  const int g = c / cpg;
+  const double cnt = (double)p.P * cpg;
+  const double s1 = p.stats[((int64_t)b * p.groups + g) * 2 + 0];
+  const double s2 = p.stats[((int64_t)b * p.groups + g) * 2 + 1];
+  const double mean = s1 / cnt;
+  double var = s2 / cnt - mean * mean;
+  if (var < 0.0) var = 0.0;
+  GnCoef k;
+  k.rs = (float)(1.0 / sqrt(var + (double)p.eps));
+  k.mr = (float)mean * k.rs;
+  float a = k.rs * p.gamma[c];
+  float d = p.beta[c] - (float)mean * a;
+  if (p.scale) {
+    const float sc = 1.0f + p.scale[(int64_t)b * p.ss_ld + c];
+    a *= sc;
+    d = d * sc + p.shift[(int64_t)b * p.ss_ld + c];
+  }
+  k.a = a;
+  k.d = d;
+  return k;
+}
+
+// grid (chunks, B); block = (C/4)*rpi threads: thread owns one channel quad and strides over rows.
+template <typename T>
+__global__ void gn_bwd_reduce_kernel(dv_gn_bwd_params p, int rows_per_block, int rpi) {
+  extern __shared__ float sred[];  // [C][2]
+  const int c4n = p.C / 4;
+  const int c4 = threadIdx.x % c4n, rl = threadIdx.x / c4n;
+  const int b = blockIdx.y;
+  for (int i = threadIdx.x; i < 2 * p.C; i += blockDim.x) sred[i] = 0.f;
+  __syncthreads();
+  GnCoef k[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) k[j] = gn_coef(p, b, c4 * 4 + j);
+  const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
+  const int64_t r1 = r0 + rows_per_block < p.P ? r0 + rows_per_block : p.P;
+  const int64_t base = (int64_t)b * p.P * p.C;
+  const T* x = reinterpret_cast<const T*>(p.x) + base;
+  const T* dy = reinterpret_cast<const T*>(p.dy) + base;
+  float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+  if (rl < rpi)
+    for (int64_t r = r0 + rl; r < r1; r += rpi) {
+      float xv[4], gv[4];
+      load4(x + r * p.C + c4 * 4, xv);
+      load4(dy + r * p.C + c4 * 4, gv);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float g = gv[j] * silu_grad(fmaf(xv[j], k[j].a, k[j].d));
+        s1[j] += g;
+        s2[j] = fmaf(g, fmaf(xv[j], k[j].rs, -k[j].mr), s2[j]);
+      }
+    }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    atomicAdd(&sred[(c4 * 4 + j) * 2 + 0], s1[j]);
+    atomicAdd(&sred[(c4 * 4 + j) * 2 + 1], s2[j]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * p.C; i += blockDim.x) atomicAdd(&p.sums[(int64_t)b * p.C * 2 + i], sred[i]);
+}
+
+// one thread per channel: parameter / conditioning gradients from the [B][C][2] sums
+__global__ void gn_bwd_params_kernel(dv_gn_bwd_params p) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= p.C) return;
+  float dg = 0.f, db = 0.f;
+  for (int b = 0; b < p.B; ++b) {
+    const float S1 = p.sums[((int64_t)b * p.C + c) * 2 + 0], S2 = p.sums[((int64_t)b * p.C + c) * 2 + 1];
+    float sc = 1.0f;
+    if (p.scale) {
+      sc += p.scale[(int64_t)b * p.ss_ld + c];
+      p.dscale[(int64_t)b * p.dss_ld + c] = p.gamma[c] * S2 + p.beta[c] * S1;
+      p.dshift[(int64_t)b * p.dss_ld + c] = S1;
+    }
+    dg = fmaf(sc, S2, dg);
+    db = fmaf(sc, S1, db);
+  }
+  p.dgamma[c] += dg;
+  p.dbeta[c] += db;
+}
+
+// grid (chunks, B), 256 threads, 8-channel vectors
+template <typename T>
+__global__ void __launch_bounds__(256) gn_bwd_apply_kernel(dv_gn_bwd_params p, int rows_per_block) {
+  extern __shared__ float coef[];  // [6][C]: a, d, rs, mr, w (= rstd*gamma*(1+scale)), and per-channel copies of rstd*m1, rstd*m2
+  float* ca = coef;
+  float* cd = coef + p.C;
+  float* crs = coef + 2 * p.C;
+  float* cmr = coef + 3 * p.C;
+  float* cw = coef + 4 * p.C;
+  float* cm1 = coef + 5 * p.C;
+  float* cm2 = coef + 6 * p.C;
+  __shared__ float gsum[64][2];
+  const int b = blockIdx.y;
+  const int cpg = p.C / p.groups;
+  if (threadIdx.x < 2 * p.groups) gsum[threadIdx.x >> 1][threadIdx.x & 1] = 0.f;
+  __syncthreads();
+  for (int c = threadIdx.x; c < p.C; c += blockDim.x) {
+    const GnCoef k = gn_coef(p, b, c);
+    ca[c] = k.a; cd[c] = k.d; crs[c] = k.rs; cmr[c] = k.mr;
+    const float sc = p.scale ? 1.0f + p.scale[(int64_t)b * p.ss_ld + c] : 1.0f;
+    const float gw = p.gamma[c] * sc;
+    cw[c] = gw * k.rs;
+    atomicAdd(&gsum[c / cpg][0], gw * p.sums[((int64_t)b * p.C + c) * 2 + 0]);
+    atomicAdd(&gsum[c / cpg][1], gw * p.sums[((int64_t)b * p.C + c) * 2 + 1]);
+  }
+  __syncthreads();
+  const float inv_cnt = 1.0f / ((float)p.P * (float)cpg);
+  for (int c = threadIdx.x; c < p.C; c += blockDim.x) {
+    cm1[c] = crs[c] * gsum[c / cpg][0] * inv_cnt;
+    cm2[c] = crs[c] * gsum[c / cpg][1] * inv_cnt;
+  }
+  __syncthreads();
+  const int c8n = p.C / 8;
+  const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
+  const int64_t r1 = r0 + rows_per_block < p.P ? r0 + rows_per_block : p.P;
+  const int64_t base = (int64_t)b * p.P * p.C;
+  const T* x = reinterpret_cast<const T*>(p.x) + base;
+  const T* dy = reinterpret_cast<const T*>(p.dy) + base;
+  T* dx = reinterpret_cast<T*>(p.dx) + base;
+  const int64_t nvec = (r1 - r0) * c8n;
+  const int64_t vbase = r0 * c8n;
+  for (int64_t i = threadIdx.x; i < nvec; i += blockDim.x) {
+    const int c = (int)((vbase + i) % c8n) * 8;
+    float xv[8], gv[8], o[8];
+    load8(x + (vbase + i) * 8, xv);
+    load8(dy + (vbase + i) * 8, gv);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float g = gv[j] * silu_grad(fmaf(xv[j], ca[c + j], cd[c + j]));
+      const float xh = fmaf(xv[j], crs[c + j], -cmr[c + j]);
+      o[j] = fmaf(cw[c + j], g, -cm1[c + j]) - xh * cm2[c + j];
+    }
+    if (p.accumulate) {
+      float prev[8];
+      load8(dx + (vbase + i) * 8, prev);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] += prev[j];
+    }
+    store8(dx + (vbase + i) * 8, o);
+  }
+}
+
+// ---------------------------------------------------------------- LayerNorm backward (gain only), one warp per row
+//   y = xh * g ;  h = dy*g ;  dx = rstd * (h - mean(h) - xh*mean(h*xh)) ;  dg += sum_rows dy*xh
+template <typename T, int MAXV>
+__global__ void __launch_bounds__(256) layernorm_bwd_kernel(dv_layernorm_bwd_params p) {
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  float dg[MAXV][4];
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) dg[i][k] = 0.f;
+  for (int64_t row = (int64_t)blockIdx.x * wpb + (threadIdx.x >> 5); row < p.rows; row += (int64_t)gridDim.x * wpb) {
+    const T* x = reinterpret_cast<const T*>(p.x) + row * p.C;
+    const T* dy = reinterpret_cast<const T*>(p.dy) + row * p.C;
+    float v[MAXV][4], h[MAXV][4];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      const int c = (i * 32 + lane) * 4;
+      if (c < p.C) {
+        load4(x + c, v[i]);
+        load4(dy + c, h[i]);
+        s += v[i][0] + v[i][1] + v[i][2] + v[i][3];
+      }
+    }
+    const float mean = warp_sum(s) / (float)p.C;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      const int c = (i * 32 + lane) * 4;
+      if (c < p.C) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { const float d = v[i][k] - mean; q += d * d; }
+      }
+    }
+    const float rstd = rsqrtf(warp_sum(q) / (float)p.C + p.eps);
+    float m1 = 0.f, m2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      const int c = (i * 32 + lane) * 4;
+      if (c < p.C) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float xh = (v[i][k] - mean) * rstd;
+          dg[i][k] = fmaf(h[i][k], xh, dg[i][k]);
+          h[i][k] *= p.g[c + k];
+          v[i][k] = xh;
+          m1 += h[i][k];
+          m2 = fmaf(h[i][k], xh, m2);
+        }
+      }
+    }
+    m1 = warp_sum(m1) / (float)p.C;
+    m2 = warp_sum(m2) / (float)p.C;
+    T* dx = reinterpret_cast<T*>(p.dx) + row * p.C;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      const int c = (i * 32 + lane) * 4;
+      if (c < p.C) {
+        float o[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) o[k] = rstd * (h[i][k] - m1 - v[i][k] * m2);
+        if (p.accumulate) {
+          float prev[4];
+          load4(dx + c, prev);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) o[k] += prev[k];
+        }
+        store4(dx + c, o);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int c = (i * 32 + lane) * 4;
+    if (c < p.C) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) atomicAdd(p.dg + c + k, dg[i][k]);
+    }
+  }
+}
+
+}  // namespace dv
+
+static int gn_bwd_check(const dv_gn_bwd_params* p, const char* who) {
+  using namespace dv;
+  DV_REQUIRE(p && p->x && p->dy && p->stats && p->gamma && p->beta && p->sums, DV_EINVAL, "%s: null pointer", who);
+  DV_REQUIRE((p->scale == nullptr) == (p->shift == nullptr), DV_EINVAL, "%s: scale/shift must come together", who);
+  DV_REQUIRE(p->B > 0 && p->P > 0 && p->C > 0 && p->groups > 0 && p->groups <= 64 && p->C % p->groups == 0, DV_EINVAL,
+             "%s: bad dimensions", who);
+  DV_REQUIRE(p->C % 8 == 0 && p->C <= 1024, DV_EUNSUPPORTED, "%s: needs C %% 8 == 0 and C <= 1024 (C=%d)", who, p->C);
+  DV_REQUIRE(aligned16(p->x) && aligned16(p->dy) && aligned16(p->dx), DV_EALIGN, "%s: tensors must be 16-byte aligned", who);
+  return DV_OK;
+}
+
+extern "C" int dv_gn_bwd_reduce(const dv_gn_bwd_params* p, dv_stream_t stream) {
+  using namespace dv;
+  int rc = gn_bwd_check(p, "dv_gn_bwd_reduce");
+  if (rc != DV_OK) return rc;
+  const int c4n = p->C / 4;
+  int rpi = 256 / c4n;
+  if (rpi < 1) rpi = 1;
+  const int threads = c4n * rpi;
+  int chunks = (148 * 4 + p->B - 1) / p->B;
+  int64_t rpb = (p->P + chunks - 1) / chunks;
+  if (rpb < rpi) rpb = rpi;
+  chunks = (int)((p->P + rpb - 1) / rpb);
+  dim3 grid(chunks, p->B);
+  const size_t smem = sizeof(float) * 2 * p->C;
+  if (p->dtype == DV_F32) gn_bwd_reduce_kernel<float><<<grid, threads, smem, as_stream(stream)>>>(*p, (int)rpb, rpi);
+  else gn_bwd_reduce_kernel<__nv_bfloat16><<<grid, threads, smem, as_stream(stream)>>>(*p, (int)rpb, rpi);
+  DV_CHECK_LAUNCH("dv_gn_bwd_reduce");
+  return DV_OK;
+}
+
+extern "C" int dv_gn_bwd_apply(const dv_gn_bwd_params* p, dv_stream_t stream) {
+  using namespace dv;
+  int rc = gn_bwd_check(p, "dv_gn_bwd_apply");
+  if (rc != DV_OK) return rc;
+  DV_REQUIRE(p->dx && p->dgamma && p->dbeta, DV_EINVAL, "dv_gn_bwd_apply: null output pointer");
+  DV_REQUIRE(!p->scale || (p->dscale && p->dshift), DV_EINVAL, "dv_gn_bwd_apply: dscale/dshift required with scale/shift");
+  cudaStream_t s = as_stream(stream);
+  gn_bwd_params_kernel<<<(p->C + 127) / 128, 128, 0, s>>>(*p);
+  DV_CHECK_LAUNCH("dv_gn_bwd_apply(params)");
+  int chunks = (148 * 2 + p->B - 1) / p->B;
+  int64_t rpb = (p->P + chunks - 1) / chunks;
+  if (rpb < 1) rpb = 1;
+  chunks = (int)((p->P + rpb - 1) / rpb);
+  dim3 grid(chunks, p->B);
+  const size_t smem = sizeof(float) * 7 * p->C;
+  if (p->dtype == DV_F32) gn_bwd_apply_kernel<float><<<grid, 256, smem, s>>>(*p, (int)rpb);
+  else gn_bwd_apply_kernel<__nv_bfloat16><<<grid, 256, smem, s>>>(*p, (int)rpb);
+  DV_CHECK_LAUNCH("dv_gn_bwd_apply");
+  return DV_OK;
+}
+
+extern "C" int dv_layernorm_bwd(const dv_layernorm_bwd_params* p, dv_stream_t stream) {
+  using namespace dv;
+  DV_REQUIRE(p && p->x && p->dy && p->dx && p->g && p->dg, DV_EINVAL, "dv_layernorm_bwd: null pointer");
+  DV_REQUIRE(p->rows > 0 && p->C > 0 && p->C % 4 == 0 && p->C <= 1024, DV_EUNSUPPORTED,
+             "dv_layernorm_bwd: needs C %% 4 == 0 and C <= 1024 (C=%d)", p->C);
+  DV_REQUIRE(aligned16(p->x) && aligned16(p->dy) && aligned16(p->dx), DV_EALIGN, "dv_layernorm_bwd: tensors must be 16-byte aligned");
+  if (p->dtype == DV_BF16) DV_REQUIRE(p->C % 8 == 0, DV_EALIGN, "dv_layernorm_bwd: bf16 rows need C %% 8 == 0");
+  const int wpb = 8;
+  int64_t blocks = (p->rows + wpb - 1) / wpb;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  cudaStream_t s = as_stream(stream);
+#define DV_LNB(T, V) layernorm_bwd_kernel<T, V><<<(unsigned)blocks, wpb * 32, 0, s>>>(*p)
+  if (p->dtype == DV_F32) {
+    if (p->C <= 128) DV_LNB(float, 1); else if (p->C <= 512) DV_LNB(float, 4); else DV_LNB(float, 8);
+  } else {
+    if (p->C <= 128) DV_LNB(__nv_bfloat16, 1); else if (p->C <= 512) DV_LNB(__nv_bfloat16, 4); else DV_LNB(__nv_bfloat16, 8);
+  }
+#undef DV_LNB
+  DV_CHECK_LAUNCH("dv_layernorm_bwd");
+  return DV_OK;
+}

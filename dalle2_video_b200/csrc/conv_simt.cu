@@ -169,14 +169,16 @@ __global__ void __launch_bounds__(NT) conv_simt_kernel(dv_conv_params p, ConvGeo
 #pragma unroll
       for (int j = 0; j < 4; ++j) v[j] += a[j];
     }
-    if (p.epilogue == DV_EPI_SHUFFLE_SILU) {
+    if (p.epilogue != DV_EPI_STORE) {
       const int Cq = p.Cout / 4;
       const int q = ncol / Cq, c = ncol % Cq;
       const int img = (int)(row / ((int64_t)g.Ho * g.Wo));
       const int rem = (int)(row % ((int64_t)g.Ho * g.Wo));
       const int oy = 2 * (rem / g.Wo) + q / 2, ox = 2 * (rem % g.Wo) + q % 2;
+      if (p.epilogue == DV_EPI_SHUFFLE_SILU) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) v[j] = silu_f(v[j]);
+        for (int j = 0; j < 4; ++j) v[j] = silu_f(v[j]);
+      }
       store4(out + (((int64_t)img * (2 * g.Ho) + oy) * (2 * g.Wo) + ox) * p.out_ld + p.out_coff + c, v);
     } else {
       store4(out + row * p.out_ld + p.out_coff + ncol, v);
@@ -271,7 +273,7 @@ static int validate_conv(const dv_conv_params* p, ConvGeom* g) {
   g->Ktot = g->ntaps * (p->C0 + p->C1);
   g->rows = (int64_t)p->n_img * g->Ho * g->Wo;
   g->rows_per_sample = (int64_t)p->frames * g->Ho * g->Wo;
-  if (p->epilogue == DV_EPI_SHUFFLE_SILU) {
+  if (p->epilogue == DV_EPI_SHUFFLE_SILU || p->epilogue == DV_EPI_SHUFFLE) {
     DV_REQUIRE(p->Cout % 16 == 0 && !p->add && !p->stats, DV_EINVAL,
                "dv_conv_igemm: shuffle epilogue needs Cout %% 16 == 0 and no residual/stats");
   } else {
@@ -311,7 +313,7 @@ extern "C" int dv_conv_igemm(const dv_conv_params* pin, dv_stream_t stream) {
   rewrite_temporal(&p);
   int rc = validate_conv(&p, &g);
   if (rc != DV_OK) return rc;
-  if (p.out_ld == 0) p.out_ld = (p.epilogue == DV_EPI_SHUFFLE_SILU) ? p.Cout / 4 : p.Cout;
+  if (p.out_ld == 0) p.out_ld = (p.epilogue != DV_EPI_STORE) ? p.Cout / 4 : p.Cout;
   DV_REQUIRE(p.out_ld % 4 == 0 && p.out_coff % 4 == 0, DV_EALIGN, "dv_conv_igemm: out_ld/out_coff must be multiples of 4");
   cudaStream_t s = as_stream(stream);
   const bool tc_ok = conv_tc_supported(p) != 0;

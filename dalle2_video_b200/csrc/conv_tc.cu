@@ -288,6 +288,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = silu_f(v[j]);
         }
+        const bool shuffle_out = p.epilogue == DV_EPI_SHUFFLE_SILU || p.epilogue == DV_EPI_SHUFFLE;
         // the staging buffer of two slabs ago must have been read out by its TMA store
         uint8_t* sbuf = slab + (slab_idx & 1) * TC_SLAB_BYTES;
         if (issuer) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
@@ -309,7 +310,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
         epi_bar();
         if (issuer) {
           const int ncol = n_tile * p.BN + s0;
-          if (p.epilogue == DV_EPI_SHUFFLE_SILU) {
+          if (shuffle_out) {
             // output view (Cq, j, Wo, i, n_img*Ho): columns [ncol, ncol+64) lie inside one (i,j) block
             const int cq = p.Cout / 4, qq = ncol / cq, cc = ncol % cq;
             tma_store_5d(&map_out, sbuf, p.out_coff + cc, qq & 1, x0, qq >> 1, img0 * p.Ho + y0);
@@ -407,14 +408,14 @@ int conv_tc_supported(const dv_conv_params& p) {
   const int64_t rows = (int64_t)p.n_img * Ho * Wo;
   const int64_t rps = (int64_t)p.frames * Ho * Wo;
   if (rows % TC_BM || rps % TC_BM) return 0;
-  if (p.epilogue == DV_EPI_SHUFFLE_SILU) {
+  if (p.epilogue == DV_EPI_SHUFFLE_SILU || p.epilogue == DV_EPI_SHUFFLE) {
     if ((p.Cout / 4) % 64) return 0;
   }
   if (p.stats) {
     const int cpg = p.Cout / p.groups;
     if (p.Cout % p.groups || cpg % 8 || (bn % cpg) || bn / cpg > 32) return 0;
   }
-  const int out_ld = p.out_ld ? p.out_ld : (p.epilogue == DV_EPI_SHUFFLE_SILU ? p.Cout / 4 : p.Cout);
+  const int out_ld = p.out_ld ? p.out_ld : (p.epilogue != DV_EPI_STORE ? p.Cout / 4 : p.Cout);
   if (out_ld % 8 || p.out_coff % 8) return 0;
   return 1;
 }
@@ -539,7 +540,7 @@ int conv_tc_launch(const dv_conv_params& p, cudaStream_t s) {
   CUtensorMap mo;
   {
     const int out_ld = p.out_ld;
-    if (p.epilogue == DV_EPI_SHUFFLE_SILU) {
+    if (p.epilogue != DV_EPI_STORE) {
       // (Cq, j, Wo, i, n_img*Ho) view of the 2x-upsampled [n_img][2Ho][2Wo][out_ld] tensor
       uint64_t dims[5] = {(uint64_t)out_ld, 2, (uint64_t)Wo, 2, (uint64_t)p.n_img * Ho};
       uint64_t strides[4] = {(uint64_t)out_ld * 2, 2ull * out_ld * 2, 2ull * Wo * out_ld * 2, 4ull * Wo * out_ld * 2};

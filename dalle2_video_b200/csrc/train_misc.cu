@@ -1,0 +1,288 @@
+// a16 (decoder training step) — the small streaming kernels around the backward pass:
+//   dv_q_sample        x_t = sqrt(ac_t) (2 v - 1) + sqrt(1 - ac_t) noise          (dalle2_video.py:1950-1956)
+//   dv_mse_loss        loss = mean_b mean_rest (pred - target)^2 and d loss / d pred  (:1997-2006, F.mse_loss)
+//   dv_to_out_bwd      backward of the 1x1x1 head (:637-642, :952)
+//   dv_silu_shuffle(_bwd)  SiLU + PixelShuffle of PixelShuffleUpsample3D (:64-78) as its own pass (training keeps the
+//                      pre-activation) and its backward
+//   dv_add             out = a (+ b): gradient accumulation of residual / skip branches
+//   dv_sumsq, dv_adamw gradient-norm clipping + AdamW (trainer.py:247-274; torch.optim.AdamW semantics)
+#include "common.cuh"
+
+namespace dv {
+
+__device__ __forceinline__ float silu_grad_f(float v) {
+  const float s = 1.0f / (1.0f + __expf(-v));
+  return s * (1.0f + v * (1.0f - s));
+}
+
+__global__ void q_sample_kernel(dv_q_sample_params p) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= p.n) return;
+  const int b = (int)(i / p.per_sample);
+  const int64_t t = p.times[b];
+  const float x0 = p.normalize ? 2.0f * p.video[i] - 1.0f : p.video[i];
+  p.out[i] = p.sqrt_ac[t] * x0 + p.sqrt_1mac[t] * p.noise[i];
+}
+
+__global__ void __launch_bounds__(256) mse_loss_kernel(dv_mse_loss_params p) {
+  __shared__ double red[8];
+  double acc = 0.0;
+  const float k = 2.0f * p.grad_scale / (float)p.n;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < p.n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float d = p.pred[i] - p.target[i];
+    acc += (double)d * d;
+    if (p.dpred) p.dpred[i] = k * d;
+  }
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int w = 0; w < 8; ++w) s += red[w];
+    atomicAdd(p.loss, s / (double)p.n);
+  }
+}
+
+// warp per position (grid-stride): lanes own channels lane + 32*i
+template <typename T, int CO>
+__global__ void __launch_bounds__(256) to_out_bwd_kernel(dv_to_out_bwd_params p) {
+  const int lane = threadIdx.x & 31;
+  const int nci = p.C / 32;
+  float w[CO][8], dw[CO][8], db[CO];
+#pragma unroll
+  for (int o = 0; o < CO; ++o) {
+    db[o] = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { dw[o][i] = 0.f; w[o][i] = i < nci ? p.w[o * p.C + lane + 32 * i] : 0.f; }
+  }
+  const int64_t total = (int64_t)p.B * p.P;
+  const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < total; r += warps) {
+    const int64_t b = r / p.P, pos = r % p.P;
+    float de[CO];
+#pragma unroll
+    for (int o = 0; o < CO; ++o) { de[o] = p.deps[(b * CO + o) * p.P + pos]; db[o] += de[o]; }
+    const T* x = reinterpret_cast<const T*>(p.x) + r * p.C;
+    T* dx = reinterpret_cast<T*>(p.dx) + r * p.C;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (i < nci) {
+        const float xv = to_f<T>(x[lane + 32 * i]);
+        float g = 0.f;
+#pragma unroll
+        for (int o = 0; o < CO; ++o) { g = fmaf(w[o][i], de[o], g); dw[o][i] = fmaf(de[o], xv, dw[o][i]); }
+        dx[lane + 32 * i] = from_f<T>(g);
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 0; o < CO; ++o) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (i < nci) atomicAdd(p.dw + o * p.C + lane + 32 * i, dw[o][i]);
+    if (lane == 0) atomicAdd(p.db + o, db[o]);
+  }
+}
+
+// z [n_img][H][W][4*Cq] (rows ordered [(i,j)][c]) -> out [n_img][2H][2W][Cq]; one thread per 8-channel vector of z
+template <typename T, bool BWD>
+__global__ void silu_shuffle_kernel(dv_silu_shuffle_params p) {
+  const int c8n = 4 * p.Cq / 8;
+  const int64_t total = (int64_t)p.n_img * p.H * p.W * c8n;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int cv = (int)(i % c8n) * 8;
+  const int64_t pos = i / c8n;
+  const int x = (int)(pos % p.W), y = (int)((pos / p.W) % p.H);
+  const int64_t n = pos / ((int64_t)p.W * p.H);
+  const int q = cv / p.Cq, c = cv % p.Cq;
+  const int64_t opos = (n * (2 * p.H) + 2 * y + (q >> 1)) * (2 * p.W) + 2 * x + (q & 1);
+  float v[8];
+  load8(reinterpret_cast<const T*>(p.z) + pos * (4 * p.Cq) + cv, v);
+  if (!BWD) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = silu_f(v[k]);
+    store8(reinterpret_cast<T*>(p.out) + opos * p.Cq + c, v);
+  } else {
+    float g[8];
+    load8(reinterpret_cast<const T*>(p.out) + opos * p.Cq + c, g);  // `out` holds d(out) in the backward call
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = g[k] * silu_grad_f(v[k]);
+    store8(reinterpret_cast<T*>(p.dz) + pos * (4 * p.Cq) + cv, v);
+  }
+}
+
+template <typename T>
+__global__ void add_kernel(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ out, int64_t n8) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n8) return;
+  float x[8];
+  load8(a + i * 8, x);
+  if (b) {
+    float y[8];
+    load8(b + i * 8, y);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) x[k] += y[k];
+  }
+  store8(out + i * 8, x);
+}
+
+__global__ void cast_f32_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = __float2bfloat16_rn(src[i]);
+}
+
+__global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ x, double* __restrict__ out, int64_t n) {
+  __shared__ double red[8];
+  double acc = 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float v = x[i];
+    acc += (double)v * v;
+  }
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int w = 0; w < 8; ++w) s += red[w];
+    atomicAdd(out, s);
+  }
+}
+
+__global__ void adamw_kernel(dv_adamw_params p) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= p.n) return;
+  float clip = 1.0f;
+  if (p.grad_sumsq && p.max_grad_norm > 0.f) {
+    // torch.nn.utils.clip_grad_norm_: coef = max_norm / (total_norm + 1e-6), clamped to 1
+    const float norm = (float)sqrt(*p.grad_sumsq);
+    clip = fminf(1.0f, p.max_grad_norm / (norm + 1e-6f));
+  }
+  const float g = p.grad[i] * clip;
+  float w = p.param[i];
+  w *= 1.0f - p.lr * p.weight_decay;
+  const float m = p.beta1 * p.exp_avg[i] + (1.0f - p.beta1) * g;
+  const float v = p.beta2 * p.exp_avg_sq[i] + (1.0f - p.beta2) * g * g;
+  p.exp_avg[i] = m;
+  p.exp_avg_sq[i] = v;
+  const float denom = sqrtf(v) / sqrtf(p.bias_correction2) + p.eps;
+  w -= (p.lr / p.bias_correction1) * (m / denom);
+  p.param[i] = w;
+}
+
+}  // namespace dv
+
+extern "C" int dv_q_sample(const dv_q_sample_params* p, dv_stream_t stream) {
+  using namespace dv;
+  DV_REQUIRE(p && p->video && p->noise && p->times && p->sqrt_ac && p->sqrt_1mac && p->out, DV_EINVAL, "dv_q_sample: null pointer");
+  DV_REQUIRE(p->n > 0 && p->per_sample > 0 && p->n % p->per_sample == 0, DV_EINVAL, "dv_q_sample: bad sizes");
+  q_sample_kernel<<<(unsigned)((p->n + 255) / 256), 256, 0, as_stream(stream)>>>(*p);
+  DV_CHECK_LAUNCH("dv_q_sample");
+  return DV_OK;
+}
+
+extern "C" int dv_mse_loss(const dv_mse_loss_params* p, dv_stream_t stream) {
+  using namespace dv;
+  DV_REQUIRE(p && p->pred && p->target && p->loss, DV_EINVAL, "dv_mse_loss: null pointer");
+  DV_REQUIRE(p->n > 0, DV_EINVAL, "dv_mse_loss: bad size");
+  int64_t blocks = (p->n + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  mse_loss_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(*p);
+  DV_CHECK_LAUNCH("dv_mse_loss");
+  return DV_OK;
+}
+
+extern "C" int dv_to_out_bwd(const dv_to_out_bwd_params* p, dv_stream_t stream) {
+  using namespace dv;
+  DV_REQUIRE(p && p->x && p->w && p->deps && p->dx && p->dw && p->db, DV_EINVAL, "dv_to_out_bwd: null pointer");
+  DV_REQUIRE(p->B > 0 && p->P > 0 && p->C > 0 && p->C % 32 == 0 && p->C <= 256, DV_EUNSUPPORTED,
+             "dv_to_out_bwd: needs C %% 32 == 0 and C <= 256 (C=%d)", p->C);
+  DV_REQUIRE(p->Cout == 3 || p->Cout == 6, DV_EUNSUPPORTED, "dv_to_out_bwd: channels_out must be 3 or 6 (got %d)", p->Cout);
+  const unsigned blocks = 148 * 8;
+  cudaStream_t s = as_stream(stream);
+#define DV_TOB(T, CO) to_out_bwd_kernel<T, CO><<<blocks, 256, 0, s>>>(*p)
+  if (p->dtype == DV_F32) { if (p->Cout == 3) DV_TOB(float, 3); else DV_TOB(float, 6); }
+  else { if (p->Cout == 3) DV_TOB(__nv_bfloat16, 3); else DV_TOB(__nv_bfloat16, 6); }
+#undef DV_TOB
+  DV_CHECK_LAUNCH("dv_to_out_bwd");
+  return DV_OK;
+}
+
+static int silu_shuffle_check(const dv_silu_shuffle_params* p, bool bwd) {
+  using namespace dv;
+  DV_REQUIRE(p && p->z && p->out && (!bwd || p->dz), DV_EINVAL, "dv_silu_shuffle: null pointer");
+  DV_REQUIRE(p->n_img > 0 && p->H > 0 && p->W > 0 && p->Cq > 0 && p->Cq % 8 == 0, DV_EUNSUPPORTED,
+             "dv_silu_shuffle: needs Cq %% 8 == 0 (Cq=%d)", p->Cq);
+  DV_REQUIRE(aligned16(p->z) && aligned16(p->out) && aligned16(p->dz), DV_EALIGN, "dv_silu_shuffle: tensors must be 16-byte aligned");
+  return DV_OK;
+}
+
+extern "C" int dv_silu_shuffle(const dv_silu_shuffle_params* p, dv_stream_t stream) {
+  using namespace dv;
+  int rc = silu_shuffle_check(p, false);
+  if (rc != DV_OK) return rc;
+  const int64_t total = (int64_t)p->n_img * p->H * p->W * (4 * p->Cq / 8);
+  const unsigned blocks = (unsigned)((total + 255) / 256);
+  if (p->dtype == DV_F32) silu_shuffle_kernel<float, false><<<blocks, 256, 0, as_stream(stream)>>>(*p);
+  else silu_shuffle_kernel<__nv_bfloat16, false><<<blocks, 256, 0, as_stream(stream)>>>(*p);
+  DV_CHECK_LAUNCH("dv_silu_shuffle");
+  return DV_OK;
+}
+
+extern "C" int dv_silu_shuffle_bwd(const dv_silu_shuffle_params* p, dv_stream_t stream) {
+  using namespace dv;
+  int rc = silu_shuffle_check(p, true);
+  if (rc != DV_OK) return rc;
+  const int64_t total = (int64_t)p->n_img * p->H * p->W * (4 * p->Cq / 8);
+  const unsigned blocks = (unsigned)((total + 255) / 256);
+  if (p->dtype == DV_F32) silu_shuffle_kernel<float, true><<<blocks, 256, 0, as_stream(stream)>>>(*p);
+  else silu_shuffle_kernel<__nv_bfloat16, true><<<blocks, 256, 0, as_stream(stream)>>>(*p);
+  DV_CHECK_LAUNCH("dv_silu_shuffle_bwd");
+  return DV_OK;
+}
+
+extern "C" int dv_add(const dv_add_params* p, dv_stream_t stream) {
+  using namespace dv;
+  DV_REQUIRE(p && p->a && p->out, DV_EINVAL, "dv_add: null pointer");
+  DV_REQUIRE(p->n > 0 && p->n % 8 == 0, DV_EALIGN, "dv_add: n must be a positive multiple of 8");
+  DV_REQUIRE(aligned16(p->a) && aligned16(p->b) && aligned16(p->out), DV_EALIGN, "dv_add: tensors must be 16-byte aligned");
+  const int64_t n8 = p->n / 8;
+  const unsigned blocks = (unsigned)((n8 + 255) / 256);
+  if (p->dtype == DV_F32)
+    add_kernel<float><<<blocks, 256, 0, as_stream(stream)>>>(reinterpret_cast<const float*>(p->a), reinterpret_cast<const float*>(p->b),
+                                                          reinterpret_cast<float*>(p->out), n8);
+  else
+    add_kernel<__nv_bfloat16><<<blocks, 256, 0, as_stream(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(p->a),
+                                                                  reinterpret_cast<const __nv_bfloat16*>(p->b),
+                                                                  reinterpret_cast<__nv_bfloat16*>(p->out), n8);
+  DV_CHECK_LAUNCH("dv_add");
+  return DV_OK;
+}
+
+extern "C" int dv_cast_f32_bf16(const dv_cast_params* p, dv_stream_t stream) {
+  using namespace dv;
+  DV_REQUIRE(p && p->src && p->dst && p->n > 0, DV_EINVAL, "dv_cast_f32_bf16: bad arguments");
+  cast_f32_bf16_kernel<<<(unsigned)((p->n + 255) / 256), 256, 0, as_stream(stream)>>>(
+      reinterpret_cast<const float*>(p->src), reinterpret_cast<__nv_bfloat16*>(p->dst), p->n);
+  DV_CHECK_LAUNCH("dv_cast_f32_bf16");
+  return DV_OK;
+}
+
+extern "C" int dv_sumsq(const dv_sumsq_params* p, dv_stream_t stream) {
+  using namespace dv;
+  DV_REQUIRE(p && p->x && p->out && p->n > 0, DV_EINVAL, "dv_sumsq: bad arguments");
+  int64_t blocks = (p->n + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  sumsq_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(p->x, p->out, p->n);
+  DV_CHECK_LAUNCH("dv_sumsq");
+  return DV_OK;
+}
+
+extern "C" int dv_adamw(const dv_adamw_params* p, dv_stream_t stream) {
+  using namespace dv;
+  DV_REQUIRE(p && p->param && p->grad && p->exp_avg && p->exp_avg_sq && p->n > 0, DV_EINVAL, "dv_adamw: bad arguments");
+  DV_REQUIRE(p->bias_correction1 > 0.f && p->bias_correction2 > 0.f, DV_EINVAL, "dv_adamw: bias corrections must be positive");
+  adamw_kernel<<<(unsigned)((p->n + 255) / 256), 256, 0, as_stream(stream)>>>(*p);
+  DV_CHECK_LAUNCH("dv_adamw");
+  return DV_OK;
+}

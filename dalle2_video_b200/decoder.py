@@ -349,5 +349,25 @@ class VideoDecoder(nn.Module):
 
     def forward(self, video, video_embed, text=None, text_encodings=None, unet_number=None,
                 return_lowres_cond_video=False):
-        raise NotImplementedError("the training step (p_losses + backward, SURVEY.md §8 a16 / config 4) is not built "
-                                  "in this round: forward kernels have no backward yet (scope row N3)")
+        """Training loss of one denoising step (reference :2188-2299 -> p_losses :1908-2006): returns a scalar tensor
+        whose .backward() runs the native backward plan (dalle2_video_b200/train.py).  RNG order as the reference:
+        randint(times), randn_like(noise), then the two keep-mask draws."""
+        from .train import p_losses
+        assert not (len(self.unets) > 1 and unet_number is None)
+        unet_number = unet_number if unet_number is not None else 1
+        unet = self.get_unet(unet_number)
+        sched = self.noise_schedulers[unet_number - 1]
+        if text is not None or text_encodings is not None:
+            raise NotImplementedError("training with text conditioning is outside the accelerated path (the reference "
+                                      "asserts here as well, :2238)")
+        self._check_native(self.predict_x_start[unet_number - 1], self.predict_v[unet_number - 1],
+                           self.learned_variance[unet_number - 1], None, None)
+        b, c, t, h, w = video.shape
+        assert c == self.channels
+        size = self.frame_sizes[unet_number - 1]
+        if h != size or w != size:
+            raise NotImplementedError("per-frame nearest resizing (resize_image_to) is outside the accelerated path: pass "
+                                      f"videos at the training resolution ({size})")
+        times = torch.randint(0, sched.num_timesteps, (b,), device=video.device, dtype=torch.long)
+        loss = p_losses(self, unet, video, times, video_embed=video_embed, noise_scheduler=sched)
+        return (loss, None) if return_lowres_cond_video else loss

@@ -1,0 +1,701 @@
+"""Decoder training step on the B200 kernels — SURVEY.md section 8 row a16 / BASELINE.json configs[3].
+
+Reference: VideoDecoder.forward -> p_losses (/root/reference/dalle2_video/dalle2_video.py:2188-2299, :1908-2006) and
+VideoDecoderTrainer.forward / update (/root/reference/dalle2_video/trainer.py:322-365, :247-274):
+
+    t ~ U{0..T-1};  x0 = 2 v - 1;  x_t = sqrt(ac_t) x0 + sqrt(1-ac_t) eps;  eps_hat = unet(x_t, t, drop 0.1 / 0.5)
+    L = mean_b mean_rest (eps_hat - eps)^2;  backward;  [all-reduce];  clip_grad_norm_(0.5);  AdamW;  zero_grad
+
+The reference gets its backward from torch autograd.  Here `_TrainPlan` lays out, once per (B, T, H, W), the forward
+launch list (the sampler's kernels, run out of place so that what the backward needs survives) and the backward launch
+list: every convolution / linear contributes a data-gradient launch (dv_conv_igemm on dY with the transposed, tap-flipped
+weight — the tcgen05 kernels) and a weight-gradient launch (dv_conv_wgrad); GroupNorm+SiLU blocks, LayerNorms, the two
+attention cores, the pixel-shuffle and the head have their own backward kernels (include/dv_b200.h, "a16").  Gradients of
+multi-consumer activations (skip connections, residual branches) are accumulated in the epilogue of the data-gradient
+launches (`add`) or by the kernels' accumulate flags.
+
+What is NOT native yet: the conditioning prologue (time / video-embedding MLPs, token LayerNorms, the to_kv and time_mlp
+linears: M = batch-sized fp32 GEMVs, < 0.01 % of the step's FLOPs) runs as plain torch ops with torch autograd; its
+outputs (scale/shift rows, k/v rows) are copied into the plan's buffers and their gradients come back from the kernels.
+Text conditioning and the extensions (temporal conv / attention) have no backward and raise.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+from . import _lib as L
+from .unet3d import Unet3D, _CrossAttn, _CrossEmbed, _prob_mask
+
+
+# ---------------------------------------------------------------------------------------------- weight layouts
+def pack_fwd(w5):
+    """[Co][Ci][1][kh][kw] -> [Co][kh*kw*Ci] (K order [tap][cin]): the packed layout of dv_conv_igemm."""
+    co = w5.shape[0]
+    return w5[:, :, 0].permute(0, 2, 3, 1).reshape(co, -1)
+
+
+def pack_dgrad(w5, c_lo, c_hi):
+    """Weight of the data-gradient convolution for input channels [c_lo, c_hi): dX = conv(dY, Wd) with
+    Wd[ci][tap'][co] = W[co][ci][flip(tap')] -> [Ci_s][kh*kw*Co]."""
+    w = w5[:, c_lo:c_hi, 0]
+    return w.flip(2, 3).permute(1, 2, 3, 0).reshape(c_hi - c_lo, -1)
+
+
+def unpack_wgrad(g, co, ci, kh, kw):
+    """[Co][kh*kw*Ci] float32 (dv_conv_wgrad) -> [Co][Ci][1][kh][kw]."""
+    return g.reshape(co, kh, kw, ci).permute(0, 3, 1, 2)[:, :, None]
+
+
+class _Var:
+    """A channels-last activation [rows][C] (bf16) and, once something back-propagates into it, its gradient."""
+    __slots__ = ("t", "rows", "C", "grad", "gready")
+
+    def __init__(self, rows, C, device, dtype=torch.bfloat16):
+        self.t = torch.empty(rows, C, dtype=dtype, device=device)
+        self.rows, self.C = rows, C
+        self.grad, self.gready = None, False
+
+    @property
+    def ptr(self):
+        return self.t.data_ptr()
+
+
+class _TrainPlan:
+    def __init__(self, unet: Unet3D, B, T, H, W, device):
+        u = unet
+        if u.cond_on_text_encodings:
+            raise NotImplementedError("training with text conditioning has no backward kernels yet (long-context cross attention)")
+        if u.temporal_conv or any(u._stage_temporal_attn) or u.attn_mode != "joint":
+            raise NotImplementedError("the extensions (temporal conv / attention, factorised attention) have no backward kernels")
+        if u.lowres_cond or u.self_cond or u.skip_connect_scale != 1.0:
+            raise NotImplementedError("lowres / self conditioning and scaled skip connections are outside the training plan")
+        self.u, self.B, self.T, self.H, self.W, self.device = u, B, T, H, W, device
+        self.code = L.DV_BF16
+        L.lib()
+        self.fwd, self.bwd, self.tape = [], [], []
+        self.keep = []
+        self.refresh = []        # (dst tensor, producer()) pairs re-evaluated when the weights change
+        self.grad_map = []       # (parameter, producer() -> gradient in the parameter's shape)
+        self.gbufs = []          # float32 gradient accumulators (zeroed once per step)
+        self.stats_slots = 0
+        self._build()
+
+    # -------------------------------------------------------------- buffers
+    def _bind(self, producer, dtype):
+        """A persistent device tensor holding producer() (weights in a kernel layout), refreshed every step."""
+        with torch.no_grad():
+            src = producer()
+        t = torch.empty(src.shape, dtype=dtype, device=self.device)
+        self.refresh.append((t, producer))
+        self.keep.append(t)
+        return t
+
+    def _w(self, producer):
+        return self._bind(producer, torch.bfloat16)
+
+    def _f32(self, producer):
+        return self._bind(producer, torch.float32)
+
+    def _galloc(self, *shape):
+        """float32 gradient accumulator in a kernel layout (zeroed once per step); returns its index."""
+        self.gbufs.append(torch.zeros(*shape, device=self.device))
+        return len(self.gbufs) - 1
+
+    def _g(self, idx):
+        return self.gbufs[idx]
+
+    def _gptr(self, idx):
+        return self.gbufs[idx].data_ptr()
+
+    def _var(self, rows, C):
+        return _Var(rows, C, self.device)
+
+    def _grad_target(self, v: _Var):
+        """(pointer to v.grad, whether it already holds a value that must be accumulated into)."""
+        if v.grad is None:
+            v.grad = torch.empty_like(v.t)
+        ready = v.gready
+        v.gready = True
+        return v.grad.data_ptr(), ready
+
+    def _grad_add(self, v: _Var, src_ptr):
+        """v.grad (+)= the tensor at src_ptr (same shape and dtype)."""
+        dst, ready = self._grad_target(v)
+        self.bwd.append(("dv_add", L.AddParams(a=src_ptr, b=dst if ready else None, out=dst, n=v.rows * v.C, dtype=self.code)))
+
+    # -------------------------------------------------------------- layers
+    def _conv(self, srcs, w5_fn, bias_fn, param_w, from5, param_b, Co, n_img, h, w, *, k=1, mode=L.CONV_NORMAL, stats=None,
+              groups=0, bias_unperm=None, frames=None):
+        """One convolution / linear.  w5_fn() -> canonical [Co][Ci][1][kh][kw] float32 view of the parameter;
+        from5(g5) maps a gradient in that view back to the parameter's shape."""
+        ho, wo = (h // 2, w // 2) if mode == L.CONV_UNSHUFFLE else (h, w)
+        rows_out = n_img * ho * wo
+        kh = kw = 2 if mode == L.CONV_UNSHUFFLE else k
+        cin = [s.C for s in srcs]
+        ctot = sum(cin)
+        out = self._var(rows_out, Co)
+        wf = self._w(lambda: pack_fwd(w5_fn()))
+        bf = self._f32(bias_fn) if bias_fn is not None else None
+        rows_per_sample = rows_out // self.B
+        fused_stats = stats is not None and rows_per_sample % 64 == 0
+        self.fwd.append(("dv_conv_igemm", L.ConvParams(
+            src0=srcs[0].ptr, src1=srcs[1].ptr if len(srcs) > 1 else None, weight=wf.data_ptr(),
+            bias=bf.data_ptr() if bf is not None else None, add=None, out=out.ptr, stats=stats if fused_stats else None,
+            n_img=n_img, frames=frames or self.T,
+            H=h, W=w, C0=cin[0], C1=cin[1] if len(srcs) > 1 else 0, Cout=Co, kh=k, kw=k, pad=k // 2, mode=mode,
+            epilogue=L.EPI_STORE, groups=groups, out_ld=0, out_coff=0, dtype=self.code, impl=0)))
+        if stats is not None and not fused_stats:
+            self.fwd.append(("dv_gn_stats", L.GnStatsParams(x=out.ptr, stats=stats, B=self.B, P=rows_per_sample, C=Co,
+                                                            groups=groups, dtype=self.code)))
+        gw = self._galloc(Co, kh * kw * ctot)
+        gb = self._galloc(Co) if bias_fn is not None else None
+        self.grad_map.append((param_w, lambda: from5(unpack_wgrad(self._g(gw), Co, ctot, kh, kw))))
+        if gb is not None:
+            self.grad_map.append((param_b, (lambda: self._g(gb)) if bias_unperm is None else (lambda: bias_unperm(self._g(gb)))))
+        if mode == L.CONV_UNSHUFFLE:
+            wd = [self._w(lambda: pack_fwd(w5_fn()).t().contiguous())]       # [(s1,s2,c)][co]: rows in pixel-shuffle order
+        else:
+            offs = [0, cin[0]]
+            wd = [self._w(lambda lo=offs[i], hi=offs[i] + cin[i]: pack_dgrad(w5_fn(), lo, hi)) for i in range(len(srcs))]
+
+        def backward():
+            dy = out.grad.data_ptr()
+            self.bwd.append(("dv_conv_wgrad", L.ConvWgradParams(
+                src0=srcs[0].ptr, src1=srcs[1].ptr if len(srcs) > 1 else None, dy=dy, dw=self._gptr(gw), n_img=n_img, H=h,
+                W=w, C0=cin[0], C1=cin[1] if len(srcs) > 1 else 0, Cout=Co, kh=k, kw=k, mode=mode, dtype=self.code)))
+            if gb is not None:
+                self.bwd.append(("dv_colsum", L.ColsumParams(x=dy, out=self._gptr(gb), rows=rows_out, C=Co, dtype=self.code)))
+            if mode == L.CONV_UNSHUFFLE:
+                s = srcs[0]
+                tmp = torch.empty_like(s.t)
+                self.keep.append(tmp)
+                self.bwd.append(("dv_conv_igemm", L.ConvParams(
+                    src0=dy, src1=None, weight=wd[0].data_ptr(), bias=None, add=None, out=tmp.data_ptr(), stats=None,
+                    n_img=n_img, frames=frames or self.T, H=ho, W=wo, C0=Co, C1=0, Cout=4 * s.C, kh=1, kw=1, pad=0, mode=L.CONV_NORMAL,
+                    epilogue=L.EPI_SHUFFLE, groups=0, out_ld=0, out_coff=0, dtype=self.code, impl=0)))
+                self._grad_add(s, tmp.data_ptr())
+                return
+            for i, s in enumerate(srcs):
+                dst, ready = self._grad_target(s)
+                self.bwd.append(("dv_conv_igemm", L.ConvParams(
+                    src0=dy, src1=None, weight=wd[i].data_ptr(), bias=None, add=dst if ready else None, out=dst, stats=None,
+                    n_img=n_img, frames=frames or self.T, H=h, W=w, C0=Co, C1=0, Cout=s.C, kh=k, kw=k, pad=k // 2, mode=L.CONV_NORMAL,
+                    epilogue=L.EPI_STORE, groups=0, out_ld=0, out_coff=0, dtype=self.code, impl=0)))
+
+        self.tape.append(backward)
+        return out
+
+    def _std_conv(self, srcs, conv: nn.Conv3d, n_img, h, w, k, stats=None, groups=0):
+        return self._conv(srcs, lambda: conv.weight.detach().float(), lambda: conv.bias.detach().float(), conv.weight,
+                          lambda g5: g5, conv.bias, conv.weight.shape[0], n_img, h, w, k=k, stats=stats, groups=groups)
+
+    def _linear(self, src, lin_weight: nn.Parameter, rows):
+        """bias-free nn.Linear on a [rows][K] activation, as a 1x1 convolution (to_q / to_kv / to_out projections)."""
+        n_out = lin_weight.shape[0]
+        return self._conv([src], lambda: lin_weight.detach().float()[:, :, None, None, None], None, lin_weight,
+                          lambda g5: g5[:, :, 0, 0, 0], None, n_out, rows, 1, 1, k=1, frames=rows // self.B)
+
+    def _next_stats(self):
+        i = self.stats_slots
+        self.stats_slots += 1
+        return self.stats[i].data_ptr()
+
+    def _gn_block(self, xraw: _Var, st_ptr, norm: nn.GroupNorm, ss_off, residual, P):
+        """out = SiLU(GroupNorm(x) * (1+scale) + shift) [+ residual]  (Block3D.forward tail, :124-133; :205)."""
+        B, C, G = self.B, xraw.C, norm.num_groups
+        out = self._var(xraw.rows, C)
+        gamma, beta = self._f32(lambda: norm.weight.detach().float()), self._f32(lambda: norm.bias.detach().float())
+        sc = self.ss.data_ptr() + ss_off * 4 if ss_off is not None else None
+        sh = self.ss.data_ptr() + (ss_off + C) * 4 if ss_off is not None else None
+        self.fwd.append(("dv_gn_apply", L.GnApplyParams(
+            x=xraw.ptr, out=out.ptr, residual=residual.ptr if residual is not None else None, stats=st_ptr,
+            gamma=gamma.data_ptr(), beta=beta.data_ptr(), scale=sc, shift=sh, ss_ld=self.ss_total, B=B, P=P, C=C,
+            groups=G, eps=float(norm.eps), dtype=self.code)))
+        gg, gbt = self._galloc(C), self._galloc(C)
+        self.grad_map.append((norm.weight, lambda: self._g(gg)))
+        self.grad_map.append((norm.bias, lambda: self._g(gbt)))
+        sums = torch.zeros(B, C, 2, device=self.device)
+        self.zero_each_step.append(sums)
+
+        def backward():
+            dy = out.grad.data_ptr()
+            dst, ready = self._grad_target(xraw)
+            dsc = self.dss.data_ptr() + ss_off * 4 if ss_off is not None else None
+            dsh = self.dss.data_ptr() + (ss_off + C) * 4 if ss_off is not None else None
+            bp = L.GnBwdParams(
+                x=xraw.ptr, dy=dy, dx=dst, stats=st_ptr, gamma=gamma.data_ptr(), beta=beta.data_ptr(), scale=sc, shift=sh,
+                sums=sums.data_ptr(), dgamma=self._gptr(gg), dbeta=self._gptr(gbt), dscale=dsc, dshift=dsh,
+                ss_ld=self.ss_total, dss_ld=self.ss_total, B=B, P=P, C=C, groups=G, eps=float(norm.eps),
+                accumulate=1 if ready else 0, dtype=self.code)
+            self.bwd.append(("dv_gn_bwd_reduce", bp))
+            self.bwd.append(("dv_gn_bwd_apply", bp))
+            if residual is not None:
+                self._grad_add(residual, dy)
+
+        self.tape.append(backward)
+        return out
+
+    def _layernorm(self, x: _Var, g: nn.Parameter, residual=None, eps=1e-5):
+        out = self._var(x.rows, x.C)
+        gt = self._f32(lambda: g.detach().float())
+        self.fwd.append(("dv_layernorm", L.LayerNormParams(x=x.ptr, out=out.ptr, residual=residual.ptr if residual is not None else None,
+                                                           g=gt.data_ptr(), beta=None, rows=x.rows, C=x.C, eps=eps, dtype=self.code)))
+        gg = self._galloc(x.C)
+        self.grad_map.append((g, lambda: self._g(gg)))
+
+        def backward():
+            dy = out.grad.data_ptr()
+            dst, ready = self._grad_target(x)
+            self.bwd.append(("dv_layernorm_bwd", L.LayerNormBwdParams(x=x.ptr, dy=dy, dx=dst, g=gt.data_ptr(), dg=self._gptr(gg),
+                                                                      rows=x.rows, C=x.C, eps=eps, accumulate=1 if ready else 0,
+                                                                      dtype=self.code)))
+            if residual is not None:
+                self._grad_add(residual, dy)
+
+        self.tape.append(backward)
+        return out
+
+    def _cross_attention(self, m, h: _Var, P):
+        """h + CrossAttention(h, ctx)  (:192-201), unfused: LN -> to_q -> core -> to_out -> LN (+h)."""
+        ca = m.cross_attn
+        heads, dh = ca.heads, ca.dim_head
+        inner = heads * dh
+        kind, idx = self.kv_idx[id(m)]
+        kv, dkv = self.kv[kind], self.dkv[kind]
+        n_ctx = kv.shape[1]
+        xn = self._layernorm(h, ca.norm.g)
+        q = self._linear(xn, ca.to_q.weight, h.rows)
+        o = self._var(h.rows, inner)
+        nk = self._f32(lambda: ca.null_kv.detach().float())
+        common = dict(B=self.B, P=P, heads=heads, dh=dh, n_ctx=n_ctx, kv_ld=kv.shape[2], k_off=idx * 2 * inner,
+                      v_off=idx * 2 * inner + inner, scale=float(dh ** -0.5), dtype=self.code)
+        self.fwd.append(("dv_xattn_core", L.XattnParams(q=q.ptr, out=o.ptr, kv=kv.data_ptr(), null_kv=nk.data_ptr(), **common)))
+        gnk = self._galloc(2, dh)
+        self.grad_map.append((ca.null_kv, lambda: self._g(gnk)))
+
+        def backward():
+            dst, ready = self._grad_target(q)
+            assert not ready
+            self.bwd.append(("dv_xattn_core_bwd", L.XattnBwdParams(q=q.ptr, dout=o.grad.data_ptr(), dq=dst, kv=kv.data_ptr(),
+                                                                    dkv=dkv.data_ptr(), null_kv=nk.data_ptr(),
+                                                                    dnull_kv=self._gptr(gnk), **common)))
+
+        self.tape.append(backward)
+        y = self._linear(o, ca.to_out[0].weight, h.rows)
+        return self._layernorm(y, ca.to_out[1].g, residual=h)
+
+    def _self_attention(self, at, x: _Var, P):
+        """x + Attention(x) over all T*h*w tokens of each sample (:430-432, :921-922)."""
+        B = self.B
+        heads, dh = at.heads, at.dim_head
+        xn = self._layernorm(x, at.norm.g)
+        q = self._linear(xn, at.to_q.weight, x.rows)
+        kvb = self._linear(xn, at.to_kv.weight, x.rows)
+        o = self._var(x.rows, heads * dh)
+        nk = self._f32(lambda: at.null_kv.detach().float())
+        ap = L.AttnMqaParams(q=q.ptr, kv=kvb.ptr, out=o.ptr, null_kv=nk.data_ptr(), bias=None, workspace=None, workspace_bytes=0,
+                             S=B, n=P, heads=heads, dh=dh, scale=float(1.0 / dh), dtype=self.code, impl=0)
+        ws_bytes = L.lib().dv_attn_mqa_workspace_bytes(ap)
+        if ws_bytes > 0:
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=self.device)
+            self.keep.append(ws)
+            ap.workspace, ap.workspace_bytes = ws.data_ptr(), ws_bytes
+        self.fwd.append(("dv_attn_mqa", ap))
+        gnk = self._galloc(2, dh)
+        self.grad_map.append((at.null_kv, lambda: self._g(gnk)))
+        dkv32 = torch.zeros(x.rows, 2 * dh, device=self.device)
+        self.keep.append(dkv32)
+        self.zero_each_step.append(dkv32)
+
+        def backward():
+            bp = L.AttnMqaBwdParams(q=q.ptr, kv=kvb.ptr, out=o.ptr, dout=o.grad.data_ptr(), dq=None, dkv=dkv32.data_ptr(),
+                                    null_kv=nk.data_ptr(), dnull_kv=self._gptr(gnk), rowstats=None, S=B, n=P, heads=heads,
+                                    dh=dh, scale=float(1.0 / dh), dtype=self.code)
+            rs = torch.empty(L.lib().dv_attn_mqa_bwd_workspace_bytes(bp) // 4, device=self.device)
+            self.keep.append(rs)
+            dq, r1 = self._grad_target(q)
+            dk, r2 = self._grad_target(kvb)
+            assert not r1 and not r2
+            bp.dq, bp.rowstats = dq, rs.data_ptr()
+            self.bwd.append(("dv_attn_mqa_bwd", bp))
+            self.bwd.append(("dv_cast_f32_bf16", L.CastParams(src=dkv32.data_ptr(), dst=dk, n=dkv32.numel())))
+
+        self.tape.append(backward)
+        y = self._linear(o, at.to_out[0].weight, x.rows)
+        return self._layernorm(y, at.to_out[1].g, residual=x)
+
+    def _resblock(self, m, srcs, h, w):
+        """ResnetBlock3D.forward (:172-205)."""
+        B, T = self.B, self.T
+        n_img, P = B * T, T * h * w
+        off = self.ss_off[id(m)]
+        G = m.groups
+        st1 = self._next_stats()
+        h1r = self._std_conv(srcs, m.block1.project, n_img, h, w, 3, stats=st1, groups=G)
+        h1 = self._gn_block(h1r, st1, m.block1.norm, off, None, P)
+        if m.cross_attn is not None:
+            h1 = self._cross_attention(m, h1, P)
+        st2 = self._next_stats()
+        h2r = self._std_conv([h1], m.block2.project, n_img, h, w, 3, stats=st2, groups=G)
+        if isinstance(m.res_conv, nn.Identity):
+            res = srcs[0]
+        else:
+            res = self._std_conv(srcs, m.res_conv, n_img, h, w, 1)
+        return self._gn_block(h2r, st2, m.block2.norm, None, res, P)
+
+    # -------------------------------------------------------------- plan construction
+    def _build(self):
+        u, B, T, H, W, dev = self.u, self.B, self.T, self.H, self.W, self.device
+        cond = u.cond_dim
+        nt, nv = u.num_time_tokens, (u.num_image_tokens if u.cond_on_video_embeds else 0)
+        self.zero_each_step = []
+        blocks = []
+        for st in u.downs:
+            blocks.append((st[1], "c"))
+            blocks += [(m, "c") for m in st[2]]
+        blocks += [(u.mid_block1, "mid"), (u.mid_block2, "mid")]
+        for st in u.ups:
+            blocks.append((st[0], "c"))
+            blocks += [(m, "c") for m in st[1]]
+        blocks.append((u.final_resnet_block, "c"))
+        self.blocks = blocks
+        self.ss_off, off = {}, 0
+        for m, _ in blocks:
+            self.ss_off[id(m)] = off
+            off += 2 * m.dim_out
+        self.ss_total = off
+        self.stats = torch.zeros(2 * len(blocks), B, max(m.groups for m, _ in blocks), 2, dtype=torch.float64, device=dev)
+        self.ss = torch.zeros(B, off, device=dev)
+        self.dss = torch.zeros(B, off, device=dev)
+        inner2 = 2 * _CrossAttn.heads * _CrossAttn.dim_head
+        self.kv, self.dkv, self.kv_idx, self.kv_mods = {}, {}, {}, {}
+        n_tok = nt + nv
+        for kind in ("c", "mid"):
+            mods = [m for m, k in blocks if m.cross_attn is not None and k == kind]
+            self.kv_mods[kind] = mods
+            for i, m in enumerate(mods):
+                self.kv_idx[id(m)] = (kind, i)
+            if mods:
+                self.kv[kind] = torch.zeros(B, n_tok, len(mods) * inner2, device=dev)
+                self.dkv[kind] = torch.zeros(B, n_tok, len(mods) * inner2, device=dev)
+                self.zero_each_step.append(self.dkv[kind])
+        self.kv_kinds = [k for k in ("c", "mid") if k in self.kv]
+
+        n_img, P = B * T, T * H * W
+        rows = B * P
+        # ---- inputs: x_t (B,3,T,H,W) float32 -> CrossEmbedLayer3D as im2col + one GEMM (patches are kept for the wgrad)
+        self.x_in = torch.zeros(B, u.channels, T, H, W, device=dev)
+        if not isinstance(u.init_conv, _CrossEmbed):
+            raise NotImplementedError("training plan: init_cross_embed=False is not built")
+        convs, ks = list(u.init_conv.convs), list(u.init_conv.kernel_sizes)
+        kmax, cin = max(ks), convs[0].weight.shape[1]
+        assert all(k % 2 == 1 for k in ks) and kmax <= 16
+        ktot = cin * kmax * 16
+        kpad = (ktot + 63) // 64 * 64
+        patches = _Var(rows, kpad, dev)  # kept for the weight gradient; no data-gradient (network input)
+        self.fwd.append(("dv_im2col_init", L.Im2colParams(x=self.x_in.data_ptr(), out=patches.ptr, B=B, C=cin, T=T, H=H, W=W,
+                                                          k=kmax, Kpad=kpad, dtype=self.code, layout=1)))
+
+        def init_w5():
+            wfull = torch.zeros(u.init_dim, cin, kmax, 16, device=dev)
+            co0 = 0
+            for conv, k in zip(convs, ks):
+                co, o = conv.weight.shape[0], (kmax - k) // 2
+                wfull[co0:co0 + co, :, o:o + k, o:o + k] = conv.weight.detach()[:, :, 0].float()
+                co0 += co
+            wp = torch.zeros(u.init_dim, kpad, device=dev)
+            wp[:, :ktot] = wfull.reshape(u.init_dim, ktot)
+            return wp[:, :, None, None, None]
+
+        x0 = self._var(rows, u.init_dim)
+        wf = self._w(lambda: pack_fwd(init_w5()))
+        bf = self._f32(lambda: torch.cat([c.bias.detach().float() for c in convs]))
+        self.fwd.append(("dv_conv_igemm", L.ConvParams(
+            src0=patches.ptr, src1=None, weight=wf.data_ptr(), bias=bf.data_ptr(), add=None, out=x0.ptr, stats=None, n_img=rows,
+            frames=P, H=1, W=1, C0=kpad, C1=0, Cout=u.init_dim, kh=1, kw=1, pad=0, mode=L.CONV_NORMAL, epilogue=L.EPI_STORE,
+            groups=0, out_ld=0, out_coff=0, dtype=self.code, impl=0)))
+        gw0, gb0 = self._galloc(u.init_dim, kpad), self._galloc(u.init_dim)
+        co0 = 0
+        for conv, k in zip(convs, ks):
+            co, o = conv.weight.shape[0], (kmax - k) // 2
+            self.grad_map.append((conv.weight, lambda co0=co0, co=co, o=o, k=k: self._g(gw0)[co0:co0 + co, :ktot].reshape(
+                co, cin, kmax, 16)[:, :, o:o + k, o:o + k][:, :, None]))
+            self.grad_map.append((conv.bias, lambda co0=co0, co=co: self._g(gb0)[co0:co0 + co]))
+            co0 += co
+
+        def init_backward():
+            dy = x0.grad.data_ptr()
+            self.bwd.append(("dv_conv_wgrad", L.ConvWgradParams(src0=patches.ptr, src1=None, dy=dy, dw=self._gptr(gw0), n_img=rows,
+                                                                H=1, W=1, C0=kpad, C1=0, Cout=u.init_dim, kh=1, kw=1,
+                                                                mode=L.CONV_NORMAL, dtype=self.code)))
+            self.bwd.append(("dv_colsum", L.ColsumParams(x=dy, out=self._gptr(gb0), rows=rows, C=u.init_dim, dtype=self.code)))
+
+        self.tape.append(init_backward)
+
+        # ---- the network (same wiring as unet3d._Engine._build / the reference :900-952)
+        x, r = x0, x0
+        h, w = H, W
+        hiddens = []
+        n_st = len(u.downs)
+        for s, st in enumerate(u.downs):
+            x = self._resblock(st[1], [x], h, w)
+            for m in st[2]:
+                x = self._resblock(m, [x], h, w)
+                hiddens.append(x)
+            if not isinstance(st[3], nn.Identity):
+                x = self._self_attention(st[3].fn.fn, x, T * h * w)
+            hiddens.append(x)
+            post = st[4]
+            if s < n_st - 1:
+                conv = post[1]
+                co, ci = conv.weight.shape[0], conv.weight.shape[1] // 4
+                x = self._conv([x], lambda conv=conv, co=co, ci=ci: conv.weight.detach().float().reshape(co, ci, 2, 2)[:, :, None],
+                               lambda conv=conv: conv.bias.detach().float(), conv.weight,
+                               lambda g5, co=co, ci=ci: g5[:, :, 0].reshape(co, 4 * ci, 1, 1, 1), conv.bias, co, n_img, h, w,
+                               mode=L.CONV_UNSHUFFLE)
+                h, w = h // 2, w // 2
+            else:
+                x = self._std_conv([x], post, n_img, h, w, 1)
+        x = self._resblock(u.mid_block1, [x], h, w)
+        x = self._self_attention(u.mid_attn.fn.fn, x, T * h * w)
+        x = self._resblock(u.mid_block2, [x], h, w)
+        for s, st in enumerate(u.ups):
+            x = self._resblock(st[0], [x, hiddens.pop()], h, w)
+            for m in st[1]:
+                x = self._resblock(m, [x, hiddens.pop()], h, w)
+            if not isinstance(st[2], nn.Identity):
+                x = self._self_attention(st[2].fn.fn, x, T * h * w)
+            up = st[3]
+            if not isinstance(up, nn.Identity):
+                x = self._upsample(up, x, n_img, h, w)
+                h, w = 2 * h, 2 * w
+        x = self._resblock(u.final_resnet_block, [x, r], h, w)
+
+        # ---- head + loss
+        co = u.channels_out
+        self.eps = torch.zeros(B, co, P, device=dev)
+        self.deps = torch.zeros(B, co, P, device=dev)
+        wo = self._f32(lambda: u.to_out.weight.detach().float().reshape(co, -1))
+        bo = self._f32(lambda: u.to_out.bias.detach().float())
+        self.fwd.append(("dv_to_out", L.ToOutParams(x=x.ptr, w=wo.data_ptr(), bias=bo.data_ptr(), out=self.eps.data_ptr(), B=B,
+                                                    P=P, C=x.C, Cout=co, dtype=self.code)))
+        gwo, gbo = self._galloc(co, x.C), self._galloc(co)
+        self.grad_map.append((u.to_out.weight, lambda: self._g(gwo).reshape(u.to_out.weight.shape)))
+        self.grad_map.append((u.to_out.bias, lambda: self._g(gbo)))
+        dst, _ = self._grad_target(x)
+        self.bwd.append(("dv_to_out_bwd", L.ToOutBwdParams(x=x.ptr, w=wo.data_ptr(), deps=self.deps.data_ptr(), dx=dst,
+                                                           dw=self._gptr(gwo), db=self._gptr(gbo), B=B, P=P, C=x.C, Cout=co,
+                                                           dtype=self.code)))
+        # ---- backward launch list: replay the tape in reverse
+        for fn in reversed(self.tape):
+            fn()
+
+    def _upsample(self, up, x: _Var, n_img, h, w):
+        """PixelShuffleUpsample3D.forward (:64-78): 1x1 conv -> SiLU -> PixelShuffle(2); rows ordered [(i,j)][c]."""
+        conv = up.conv
+        co4, ci = conv.weight.shape[0], conv.weight.shape[1]
+        cq = co4 // 4
+        z = self._conv([x], lambda: conv.weight.detach().float().reshape(cq, 4, ci).permute(1, 0, 2).reshape(co4, ci)[:, :, None, None, None],
+                       lambda: conv.bias.detach().float().reshape(cq, 4).t().reshape(co4), conv.weight,
+                       lambda g5: g5[:, :, 0, 0, 0].reshape(4, cq, ci).permute(1, 0, 2).reshape(co4, ci, 1, 1, 1), conv.bias,
+                       co4, n_img, h, w, k=1, bias_unperm=lambda g: g.reshape(4, cq).t().reshape(co4))
+        out = self._var(n_img * 4 * h * w, cq)
+        self.fwd.append(("dv_silu_shuffle", L.SiluShuffleParams(z=z.ptr, out=out.ptr, dz=None, n_img=n_img, H=h, W=w, Cq=cq,
+                                                                 dtype=self.code)))
+
+        def backward():
+            dst, ready = self._grad_target(z)
+            assert not ready
+            self.bwd.append(("dv_silu_shuffle_bwd", L.SiluShuffleParams(z=z.ptr, out=out.grad.data_ptr(), dz=dst, n_img=n_img, H=h,
+                                                                         W=w, Cq=cq, dtype=self.code)))
+
+        self.tape.append(backward)
+        return out
+
+    # -------------------------------------------------------------- conditioning prologue (torch autograd, see module doc)
+    def prologue(self, time, video_embed, keep_v):
+        u, B = self.u, self.B
+        cond, nt = u.cond_dim, u.num_time_tokens
+        half = u.dim // 2
+        tf = time.to(torch.float32)
+        freqs = torch.exp(torch.arange(half, dtype=torch.float32, device=tf.device) * -(math.log(10000) / (half - 1)))
+        a = tf[:, None] * freqs[None, :]
+        emb = torch.cat((a.sin(), a.cos()), dim=-1)
+        hid = F.gelu(u.to_time_hiddens[1](emb))
+        time_tokens = u.to_time_tokens[0](hid).reshape(B, nt, cond)
+        t = u.to_time_cond[0](hid)
+        keep = keep_v.bool()
+        if u.to_video_hiddens is not None:
+            vh = F.gelu(u.to_video_hiddens[0](video_embed))
+            t = t + torch.where(keep[:, None], vh, u.null_video_hiddens.to(vh.dtype))
+        c = time_tokens
+        if u.cond_on_video_embeds:
+            vt = u.video_to_tokens[0](video_embed).reshape(B, u.num_image_tokens, cond)
+            vt = torch.where(keep[:, None, None], vt, u.null_video_embed.to(vt.dtype))
+            c = torch.cat((c, vt), dim=-2)
+        mid_c = u.norm_mid_cond(c)
+        c = u.norm_cond(c)
+        w_ss = torch.cat([m.time_mlp[1].weight for m, _ in self.blocks], dim=0)
+        b_ss = torch.cat([m.time_mlp[1].bias for m, _ in self.blocks], dim=0)
+        ss = F.linear(F.silu(t), w_ss, b_ss)
+        outs = {"ss": ss}
+        for kind, toks in (("c", c), ("mid", mid_c)):
+            if self.kv_mods[kind]:
+                wkv = torch.cat([m.cross_attn.to_kv.weight for m in self.kv_mods[kind]], dim=0)
+                outs[kind] = toks @ wkv.t()
+        return outs
+
+    # -------------------------------------------------------------- execution
+    def refresh_weights(self):
+        with torch.no_grad():
+            for dst, fn in self.refresh:
+                dst.copy_(fn())
+
+    def run_forward(self):
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        self.stats.zero_()
+        for name, p in self.fwd:
+            L.call(name, p, stream)
+
+    def run_backward(self):
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        torch._foreach_zero_(self.gbufs + self.zero_each_step)
+        for name, p in self.bwd:
+            L.call(name, p, stream)
+
+
+
+
+class _PlanFunction(torch.autograd.Function):
+    """Bridges the native plan into torch autograd: forward = plan forward + loss kernel, backward = plan backward.
+    Inputs are the prologue outputs (so autograd continues into the prologue parameters); the gradients of every other
+    parameter are written to `.grad` as a side effect of backward, the way DDP hooks do."""
+
+    @staticmethod
+    def forward(ctx, plan, noise, ss, *kv):
+        plan.ss.copy_(ss)
+        for kind, t in zip(plan.kv_kinds, kv):
+            plan.kv[kind].copy_(t)
+        plan.run_forward()
+        loss = torch.zeros(1, dtype=torch.float64, device=plan.device)
+        stream = torch.cuda.current_stream(plan.device).cuda_stream
+        L.call("dv_mse_loss", L.MseLossParams(pred=plan.eps.data_ptr(), target=noise.data_ptr(), dpred=None,
+                                              loss=loss.data_ptr(), n=noise.numel(), grad_scale=1.0), stream)
+        ctx.plan, ctx.noise = plan, noise
+        return loss[0].float()
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        plan, noise = ctx.plan, ctx.noise
+        stream = torch.cuda.current_stream(plan.device).cuda_stream
+        scratch = torch.zeros(1, dtype=torch.float64, device=plan.device)
+        L.call("dv_mse_loss", L.MseLossParams(pred=plan.eps.data_ptr(), target=noise.data_ptr(), dpred=plan.deps.data_ptr(),
+                                              loss=scratch.data_ptr(), n=noise.numel(), grad_scale=float(grad_out)), stream)
+        plan.run_backward()
+        with torch.no_grad():
+            for prm, fn in plan.grad_map:
+                g = fn()
+                if prm.grad is None:
+                    prm.grad = g.reshape(prm.shape).to(prm.dtype).clone()
+                else:
+                    prm.grad.add_(g.reshape(prm.shape))
+        return (None, None, plan.dss.clone(), *[plan.dkv[k].clone() for k in plan.kv_kinds])
+
+
+def p_losses(decoder, unet: Unet3D, x_start, times, *, video_embed, noise_scheduler, noise=None, is_latent_diffusion=False):
+    """VideoDecoder.p_losses (:1908-2006) for epsilon prediction with the l2 loss; returns a scalar loss tensor whose
+    .backward() runs the native backward plan."""
+    if not x_start.is_cuda:
+        raise L.DvError("VideoDecoder(b200).forward needs CUDA tensors: there is no CPU path")
+    B, C, T, H, W = x_start.shape
+    dev = x_start.device
+    noise = torch.randn_like(x_start) if noise is None else noise
+    plan = unet.train_plan(B, T, H, W, dev)
+    plan.refresh_weights()
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    x_start = x_start.contiguous().float()
+    noise = noise.contiguous().float()
+    L.call("dv_q_sample", L.QSampleParams(
+        video=x_start.data_ptr(), noise=noise.data_ptr(), times=times.data_ptr(),
+        sqrt_ac=noise_scheduler.sqrt_alphas_cumprod.data_ptr(),
+        sqrt_1mac=noise_scheduler.sqrt_one_minus_alphas_cumprod.data_ptr(), out=plan.x_in.data_ptr(), n=x_start.numel(),
+        per_sample=x_start.numel() // B, normalize=0 if is_latent_diffusion else 1), stream)
+    # prob_mask_like draws (reference :772-778): video mask, then text mask (drawn even without text conditioning)
+    keep_v = _prob_mask(B, 1 - decoder.video_cond_drop_prob, dev)
+    _prob_mask(B, 1 - decoder.text_cond_drop_prob, dev)
+    outs = plan.prologue(times, video_embed.float(), keep_v)
+    return _PlanFunction.apply(plan, noise, outs["ss"], *[outs[k] for k in plan.kv_kinds])
+
+
+class VideoDecoderTrainer(nn.Module):
+    """The optimiser half of the reference's VideoDecoderTrainer (/root/reference/dalle2_video/trainer.py:40-365) for a
+    single-unet decoder: forward() = loss + backward (+ gradient all-reduce when torch.distributed is initialised, the
+    only collective of the training config), update() = clip_grad_norm_ + AdamW + zero_grad on flat fp32 buffers with
+    two launches (dv_sumsq, dv_adamw per weight-decay group).  get_optimizer semantics: AdamW,
+    betas (0.9, 0.99), parameters with ndim < 2 excluded from weight decay when group_wd_params."""
+
+    def __init__(self, decoder, lr=1e-4, wd=1e-2, eps=1e-8, max_grad_norm=0.5, group_wd_params=True, betas=(0.9, 0.99), **_):
+        super().__init__()
+        self.decoder = decoder
+        self.lr, self.wd, self.eps, self.betas = lr, wd, eps, betas
+        self.max_grad_norm = max_grad_norm
+        unet = decoder.unets[0]
+        params = [p for p in decoder.parameters() if p.requires_grad]
+        decay = [p for p in params if p.ndim >= 2 or not group_wd_params]
+        no_decay = [p for p in params if not (p.ndim >= 2 or not group_wd_params)]
+        self._groups = []
+        dev = params[0].device
+        ordered = decay + no_decay
+        n = sum(p.numel() for p in ordered)
+        self.flat_p = torch.empty(n, device=dev)
+        self.flat_g = torch.zeros(n, device=dev)
+        self.exp_avg = torch.zeros(n, device=dev)
+        self.exp_avg_sq = torch.zeros(n, device=dev)
+        off = 0
+        with torch.no_grad():
+            for p in ordered:
+                k = p.numel()
+                self.flat_p[off:off + k].copy_(p.detach().reshape(-1))
+                p.data = self.flat_p[off:off + k].view(p.shape)
+                p.grad = self.flat_g[off:off + k].view(p.shape)
+                off += k
+        nd = sum(p.numel() for p in decay)
+        self._groups = [(0, nd, wd), (nd, n - nd, 0.0)]
+        self.register_buffer("steps", torch.tensor([0]))
+        self._sumsq = torch.zeros(1, dtype=torch.float64, device=dev)
+        unet.invalidate_cache()
+
+    def forward(self, video, video_embed, unet_number=None, **kwargs):
+        loss = self.decoder(video, video_embed=video_embed, unet_number=unet_number, **kwargs)
+        loss.backward()
+        if torch.distributed.is_available() and torch.distributed.is_initialized() and torch.distributed.get_world_size() > 1:
+            torch.distributed.all_reduce(self.flat_g)
+            self.flat_g.div_(torch.distributed.get_world_size())
+        return loss.item()
+
+    @torch.no_grad()
+    def update(self, unet_number=None):
+        dev = self.flat_p.device
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        step = int(self.steps[0]) + 1
+        self._sumsq.zero_()
+        use_clip = self.max_grad_norm is not None
+        if use_clip:
+            L.call("dv_sumsq", L.SumsqParams(x=self.flat_g.data_ptr(), out=self._sumsq.data_ptr(), n=self.flat_g.numel()), stream)
+        b1, b2 = self.betas
+        for off, n, wd in self._groups:
+            if n == 0:
+                continue
+            L.call("dv_adamw", L.AdamwParams(
+                param=self.flat_p.data_ptr() + off * 4, grad=self.flat_g.data_ptr() + off * 4,
+                exp_avg=self.exp_avg.data_ptr() + off * 4, exp_avg_sq=self.exp_avg_sq.data_ptr() + off * 4,
+                grad_sumsq=self._sumsq.data_ptr() if use_clip else None, n=n, lr=self.lr, beta1=b1, beta2=b2, eps=self.eps,
+                weight_decay=wd, bias_correction1=1 - b1 ** step, bias_correction2=1 - b2 ** step,
+                max_grad_norm=float(self.max_grad_norm or 0.0)), stream)
+        self.flat_g.zero_()
+        self.steps += 1
+        self.decoder.unets[0].invalidate_cache()  # sampler plans hold packed copies of the old weights

@@ -342,7 +342,9 @@ class Unet3D(nn.Module):
         return torch.float32
 
     def invalidate_cache(self):
-        self._engines.clear()
+        """Drop the sampler plans (they hold packed copies of the weights); training plans re-read the weights each step."""
+        for k in [k for k in self._engines if not (isinstance(k, tuple) and k and k[0] == "train")]:
+            del self._engines[k]
 
     def _versions(self):
         return tuple(p._version for p in self.parameters())
@@ -350,7 +352,7 @@ class Unet3D(nn.Module):
     def engine(self, batch, frames, height, width, dtype, device, n_text=0):
         ver = self._versions()
         if ver != self._param_version:  # weights changed (load_state_dict / optimiser step): repack
-            self._engines.clear()
+            self.invalidate_cache()
             self._param_version = ver
         key = (batch, frames, height, width, dtype, str(device), n_text)
         eng = self._engines.get(key)
@@ -358,6 +360,16 @@ class Unet3D(nn.Module):
             eng = _Engine(self, batch, frames, height, width, dtype, device, n_text)
             self._engines[key] = eng
         return eng
+
+    def train_plan(self, batch, frames, height, width, device):
+        """Forward + backward launch plan of the training step (dalle2_video_b200/train.py)."""
+        from .train import _TrainPlan
+        key = ("train", batch, frames, height, width, str(device))
+        pl = self._engines.get(key)
+        if pl is None:
+            pl = _TrainPlan(self, batch, frames, height, width, device)
+            self._engines[key] = pl
+        return pl
 
     @torch.no_grad()
     def forward(self, x, time, *, video_embed, lowres_cond_video=None, lowres_noise_level=None, text_encodings=None,

@@ -391,6 +391,152 @@ typedef struct {
 } dv_to_out_params;
 int dv_to_out(const dv_to_out_params* p, dv_stream_t stream);
 
+/* ================================================================================================
+ * a16 — decoder TRAINING step (/root/reference/dalle2_video/dalle2_video.py:1908-2006,
+ * dalle2_video/trainer.py:322-365, :247-274).  The reference gets its backward pass from torch autograd over the
+ * modules above; these entry points are the hand-written backward of each forward kernel.  The data-gradient of a
+ * convolution / linear is dv_conv_igemm itself on dY with the transposed, tap-flipped weight (the pixel-unshuffle
+ * convolution's data-gradient uses DV_EPI_SHUFFLE: the plain pixel-shuffle scatter, no activation).
+ */
+#define DV_EPI_SHUFFLE 2 /* dv_conv_params.epilogue: like DV_EPI_SHUFFLE_SILU without the SiLU */
+
+/* dW[co][tap*(C0+C1)+ci] += sum_pos dY[pos][co] * X[pos (+) tap][ci]; dw is float32 in the packed-weight layout of
+ * dv_conv_igemm and must be zeroed by the caller (results are accumulated with atomics). */
+typedef struct {
+  const void* src0;  /* forward inputs, bf16 channels-last */
+  const void* src1;  /* NULL when C1 == 0 */
+  const void* dy;    /* [n_img][Ho][Wo][Cout] bf16 */
+  float* dw;         /* [Cout][taps*(C0+C1)] */
+  int n_img, H, W;   /* input spatial size (output is H/2 x W/2 in UNSHUFFLE mode) */
+  int C0, C1, Cout;
+  int kh, kw;
+  int mode;          /* DV_CONV_NORMAL or DV_CONV_UNSHUFFLE */
+  dv_dtype dtype;    /* DV_BF16 */
+} dv_conv_wgrad_params;
+int dv_conv_wgrad(const dv_conv_wgrad_params* p, dv_stream_t stream);
+
+/* out[c] += sum_rows x[row][c]  (bias gradients) */
+typedef struct {
+  const void* x;
+  float* out;
+  int64_t rows;
+  int C;
+  dv_dtype dtype;
+} dv_colsum_params;
+int dv_colsum(const dv_colsum_params* p, dv_stream_t stream);
+
+/* Backward of dv_gn_apply (GroupNorm + (1+scale)/shift + SiLU; the residual branch's gradient is dy itself).
+ * dv_gn_bwd_reduce accumulates sums[b][c] = { sum_pos g_v, sum_pos g_v*xhat } (caller zeroes `sums`);
+ * dv_gn_bwd_apply then writes dx (may alias x or dy) and dgamma/dbeta (+=), dscale/dshift (=). */
+typedef struct {
+  const void* x;        /* pre-GroupNorm activation [B][P][C] */
+  const void* dy;       /* gradient of the block output [B][P][C] */
+  void* dx;             /* gradient wrt x */
+  const double* stats;  /* [B][groups][2] forward statistics */
+  const float* gamma; const float* beta;
+  const float* scale; const float* shift; /* forward conditioning (or NULL), row stride ss_ld */
+  float* sums;          /* [B][C][2] float32 workspace */
+  float* dgamma; float* dbeta;            /* [C], accumulated */
+  float* dscale; float* dshift;           /* row stride dss_ld, written (NULL without scale/shift) */
+  int ss_ld, dss_ld;
+  int B; int64_t P; int C, groups;
+  float eps;
+  int accumulate;       /* dx += instead of dx = */
+  dv_dtype dtype;
+} dv_gn_bwd_params;
+int dv_gn_bwd_reduce(const dv_gn_bwd_params* p, dv_stream_t stream);
+int dv_gn_bwd_apply(const dv_gn_bwd_params* p, dv_stream_t stream);
+
+/* Backward of the gain-only LayerNorm (dv_layernorm without beta): dx (=/+=), dg (+=). */
+typedef struct {
+  const void* x; const void* dy; void* dx;
+  const float* g; float* dg;
+  int64_t rows; int C;
+  float eps;
+  int accumulate;
+  dv_dtype dtype;
+} dv_layernorm_bwd_params;
+int dv_layernorm_bwd(const dv_layernorm_bwd_params* p, dv_stream_t stream);
+
+/* Backward of dv_xattn_core for short contexts (n_ctx + 1 <= 8): dq (=), dkv / dnull_kv (+=, float32, same layout
+ * and offsets as kv / null_kv). */
+typedef struct {
+  const void* q; const void* dout; void* dq;
+  const float* kv; float* dkv;
+  const float* null_kv; float* dnull_kv;
+  int B; int64_t P; int heads, dh, n_ctx;
+  int64_t kv_ld; int k_off, v_off;
+  float scale;
+  dv_dtype dtype;
+} dv_xattn_bwd_params;
+int dv_xattn_core_bwd(const dv_xattn_bwd_params* p, dv_stream_t stream);
+
+/* Backward of dv_attn_mqa (no bias): dq (=, act dtype), dkv [S][n][2*dh] / dnull_kv [2][dh] (+=, float32).
+ * `out` is the forward result, `rowstats` a float32 scratch of dv_attn_mqa_bwd_workspace_bytes(). */
+typedef struct {
+  const void* q; const void* kv; const void* out; const void* dout;
+  void* dq; float* dkv;
+  const float* null_kv; float* dnull_kv;
+  float* rowstats;
+  int64_t S; int n, heads, dh;
+  float scale;
+  dv_dtype dtype;
+} dv_attn_mqa_bwd_params;
+int dv_attn_mqa_bwd(const dv_attn_mqa_bwd_params* p, dv_stream_t stream);
+int64_t dv_attn_mqa_bwd_workspace_bytes(const dv_attn_mqa_bwd_params* p);
+
+/* x_t = sqrt_ac[t_b] * (normalize ? 2 v - 1 : v) + sqrt_1mac[t_b] * noise   (NoiseScheduler.q_sample) */
+typedef struct {
+  const float* video; const float* noise; const int64_t* times;
+  const float* sqrt_ac; const float* sqrt_1mac; float* out;
+  int64_t n, per_sample;
+  int normalize;
+} dv_q_sample_params;
+int dv_q_sample(const dv_q_sample_params* p, dv_stream_t stream);
+
+/* *loss += mean((pred-target)^2) (double, caller zeroes); dpred = grad_scale * 2 (pred-target) / n (or NULL) */
+typedef struct {
+  const float* pred; const float* target; float* dpred; double* loss;
+  int64_t n; float grad_scale;
+} dv_mse_loss_params;
+int dv_mse_loss(const dv_mse_loss_params* p, dv_stream_t stream);
+
+/* Backward of dv_to_out: deps [B][Cout][P] float32 -> dx [B][P][C] (=), dw [Cout][C] and db [Cout] (+=). */
+typedef struct {
+  const void* x; const float* w; const float* deps; void* dx; float* dw; float* db;
+  int B; int64_t P; int C, Cout;
+  dv_dtype dtype;
+} dv_to_out_bwd_params;
+int dv_to_out_bwd(const dv_to_out_bwd_params* p, dv_stream_t stream);
+
+/* SiLU + PixelShuffle(2) as a separate pass (training keeps the pre-activation z) and its backward:
+ * forward  out[n][2y+i][2x+j][c] = SiLU(z[n][y][x][(2i+j)*Cq + c]);  backward  dz = unshuffle(d out) * SiLU'(z)
+ * (in the backward call `out` carries d out). */
+typedef struct {
+  const void* z; void* out; void* dz;
+  int n_img, H, W, Cq;
+  dv_dtype dtype;
+} dv_silu_shuffle_params;
+int dv_silu_shuffle(const dv_silu_shuffle_params* p, dv_stream_t stream);
+int dv_silu_shuffle_bwd(const dv_silu_shuffle_params* p, dv_stream_t stream);
+
+typedef struct { const void* a; const void* b; void* out; int64_t n; dv_dtype dtype; } dv_add_params; /* out = a (+ b) */
+int dv_add(const dv_add_params* p, dv_stream_t stream);
+typedef struct { const void* src; void* dst; int64_t n; } dv_cast_params;
+int dv_cast_f32_bf16(const dv_cast_params* p, dv_stream_t stream);
+typedef struct { const float* x; double* out; int64_t n; } dv_sumsq_params; /* *out += sum x^2 */
+int dv_sumsq(const dv_sumsq_params* p, dv_stream_t stream);
+
+/* torch.optim.AdamW step on a flat float32 buffer, with clip_grad_norm_ folded in: when grad_sumsq != NULL the
+ * gradient is scaled by min(1, max_grad_norm / (sqrt(*grad_sumsq) + 1e-6)) (trainer.py:252-255). */
+typedef struct {
+  float* param; const float* grad; float* exp_avg; float* exp_avg_sq;
+  const double* grad_sumsq;
+  int64_t n;
+  float lr, beta1, beta2, eps, weight_decay, bias_correction1, bias_correction2, max_grad_norm;
+} dv_adamw_params;
+int dv_adamw(const dv_adamw_params* p, dv_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
