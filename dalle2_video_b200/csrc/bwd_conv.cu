@@ -10,7 +10,7 @@
 
 namespace dv {
 
-constexpr int WG_TM = 64, WG_TN = 64, WG_KS = 32, WG_THREADS = 128;
+constexpr int WG_TM = 64, WG_TN = 64, WG_KS = 32, WG_THREADS = 128, WG_STAGES = 4;
 constexpr int WG_LD = 72;  // padded row (elements): 144 B keeps the 8 rows of an ldmatrix on distinct banks
 
 __device__ __forceinline__ void cp_async16_zfill(void* smem_dst, const void* gsrc, bool valid) {
@@ -32,8 +32,8 @@ __device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], 
 
 __global__ void __launch_bounds__(WG_THREADS) conv_wgrad_kernel(const dv_conv_wgrad_params p, int Ho, int Wo, int64_t rows,
                                                                 int64_t rows_per_cta, int n_ci_tiles) {
-  __shared__ __align__(16) __nv_bfloat16 As[2][WG_KS][WG_LD];  // dY tile  [pos][co]
-  __shared__ __align__(16) __nv_bfloat16 Bs[2][WG_KS][WG_LD];  // X tile   [pos][ci]
+  __shared__ __align__(16) __nv_bfloat16 As[WG_STAGES][WG_KS][WG_LD];  // dY tile  [pos][co]
+  __shared__ __align__(16) __nv_bfloat16 Bs[WG_STAGES][WG_KS][WG_LD];  // X tile   [pos][ci]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int tap = blockIdx.y;
   const int co_tile = blockIdx.z / n_ci_tiles, ci_tile = blockIdx.z % n_ci_tiles;
@@ -54,29 +54,48 @@ __global__ void __launch_bounds__(WG_THREADS) conv_wgrad_kernel(const dv_conv_wg
   if (p.mode == DV_CONV_UNSHUFFLE) { dyo = tap >> 1; dxo = tap & 1; }
   else { dyo = tap / p.kw - (p.kh >> 1); dxo = tap % p.kw - (p.kw >> 1); }
 
-  // each thread moves two 16-byte pieces of each operand per K step: rows (tid>>3) and (tid>>3)+16, piece tid&7
+  // each thread moves two 16-byte pieces of each operand per K step: rows (tid>>3) and (tid>>3)+16, piece tid&7.
+  // The (image, y, x) coordinates of its two rows are carried incrementally (32-bit; one small division per step).
   const int prow = tid >> 3, pc = (tid & 7) * 8;
-  auto issue = [&](int buf, int64_t r0) {
+  const bool a_cok = (co0 + pc) < p.Cout, b_cok = (ci0 + pc) < Cs;
+  int rr[2], rimg[2], roy[2], rox[2];
+#pragma unroll
+  for (int h2 = 0; h2 < 2; ++h2) {
+    const int64_t r = r_begin + prow + h2 * 16;
+    rr[h2] = (int)(r - r_begin);
+    rimg[h2] = (int)(r / ((int64_t)Ho * Wo));
+    const int rem = (int)(r - (int64_t)rimg[h2] * Ho * Wo);
+    roy[h2] = rem / Wo;
+    rox[h2] = rem - roy[h2] * Wo;
+  }
+  const int nrows = (int)(r_end - r_begin);
+  const __nv_bfloat16* dy0 = dy + r_begin * p.Cout + co0 + pc;
+  auto issue = [&](int buf) {   // stages are issued strictly in order: the row state advances by WG_KS per call
 #pragma unroll
     for (int h2 = 0; h2 < 2; ++h2) {
       const int row = prow + h2 * 16;
-      const int64_t r = r0 + row;
-      const bool rok = r < r_end;
-      const bool aok = rok && (co0 + pc) < p.Cout;
-      cp_async16_zfill(&As[buf][row][pc], aok ? dy + r * p.Cout + co0 + pc : dy, aok);
-      bool bok = rok && (ci0 + pc) < Cs;
-      const __nv_bfloat16* bsrc = src;
-      if (bok) {
-        const int img = (int)(r / ((int64_t)Ho * Wo));
-        const int rem = (int)(r - (int64_t)img * Ho * Wo);
-        const int oy = rem / Wo, ox = rem - oy * Wo;
-        int iy, ix;
-        if (p.mode == DV_CONV_UNSHUFFLE) { iy = 2 * oy + dyo; ix = 2 * ox + dxo; }
-        else { iy = oy + dyo; ix = ox + dxo; }
-        bok = iy >= 0 && iy < p.H && ix >= 0 && ix < p.W;
-        if (bok) bsrc = src + (((int64_t)img * p.H + iy) * p.W + ix) * Cs + ci0 + pc;
-      }
+      const bool rok = rr[h2] < nrows;
+      const bool aok = rok && a_cok;
+      cp_async16_zfill(&As[buf][row][pc], aok ? dy0 + (int64_t)rr[h2] * p.Cout : dy, aok);
+      int iy, ix;
+      if (p.mode == DV_CONV_UNSHUFFLE) { iy = 2 * roy[h2] + dyo; ix = 2 * rox[h2] + dxo; }
+      else { iy = roy[h2] + dyo; ix = rox[h2] + dxo; }
+      const bool bok = rok && b_cok && (unsigned)iy < (unsigned)p.H && (unsigned)ix < (unsigned)p.W;
+      const __nv_bfloat16* bsrc = bok ? src + ((int64_t)(rimg[h2] * p.H + iy) * p.W + ix) * Cs + ci0 + pc : src;
       cp_async16_zfill(&Bs[buf][row][pc], bsrc, bok);
+      // advance this row by WG_KS positions
+      rr[h2] += WG_KS;
+      rox[h2] += WG_KS;
+      if (rox[h2] >= Wo) {
+        const int q = rox[h2] / Wo;
+        rox[h2] -= q * Wo;
+        roy[h2] += q;
+        if (roy[h2] >= Ho) {
+          const int q2 = roy[h2] / Ho;
+          roy[h2] -= q2 * Ho;
+          rimg[h2] += q2;
+        }
+      }
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
@@ -91,16 +110,19 @@ __global__ void __launch_bounds__(WG_THREADS) conv_wgrad_kernel(const dv_conv_wg
   const int wm = (warp >> 1) * 32, wn = (warp & 1) * 32;
 
   const int nsteps = (int)((r_end - r_begin + WG_KS - 1) / WG_KS);
-  issue(0, r_begin);
+  // WG_STAGES-deep cp.async ring, one __syncthreads per K step: the stage refilled in iteration s is the one every
+  // thread finished reading in iteration s-1
+#pragma unroll
+  for (int s = 0; s < WG_STAGES - 1; ++s) {
+    if (s < nsteps) issue(s);
+    else asm volatile("cp.async.commit_group;" ::: "memory");
+  }
   for (int s = 0; s < nsteps; ++s) {
-    const int buf = s & 1;
-    if (s + 1 < nsteps) {
-      issue(buf ^ 1, r_begin + (int64_t)(s + 1) * WG_KS);
-      asm volatile("cp.async.wait_group 1;" ::: "memory");
-    } else {
-      asm volatile("cp.async.wait_group 0;" ::: "memory");
-    }
+    const int buf = s % WG_STAGES;
+    asm volatile("cp.async.wait_group %0;" ::"n"(WG_STAGES - 2) : "memory");
     __syncthreads();
+    if (s + WG_STAGES - 1 < nsteps) issue((s + WG_STAGES - 1) % WG_STAGES);
+    else asm volatile("cp.async.commit_group;" ::: "memory");
 #pragma unroll
     for (int k0 = 0; k0 < WG_KS; k0 += 16) {
       uint32_t a[2][4], b[2][4];
@@ -115,7 +137,6 @@ __global__ void __launch_bounds__(WG_THREADS) conv_wgrad_kernel(const dv_conv_wg
 #pragma unroll
         for (int nt = 0; nt < 4; ++nt) mma16816(acc[mt][nt], a[mt], b[nt >> 1][(nt & 1) * 2], b[nt >> 1][(nt & 1) * 2 + 1]);
     }
-    __syncthreads();
   }
   const int ktot = (p.mode == DV_CONV_UNSHUFFLE ? 4 : p.kh * p.kw) * (p.C0 + p.C1);
   const int kbase = tap * (p.C0 + p.C1) + src_off + ci0;
@@ -177,10 +198,11 @@ extern "C" int dv_conv_wgrad(const dv_conv_wgrad_params* p, dv_stream_t stream) 
     taps = p->kh * p->kw;
   }
   const int64_t rows = (int64_t)p->n_img * Ho * Wo;
+  DV_REQUIRE((int64_t)p->n_img * p->H * p->W < (1ll << 31), DV_EUNSUPPORTED, "dv_conv_wgrad: more than 2^31 positions");
   const int n_co = (p->Cout + WG_TM - 1) / WG_TM;
   const int n_ci = (p->C0 + WG_TN - 1) / WG_TN + (p->C1 + WG_TN - 1) / WG_TN;
-  // enough position chunks for ~4 CTAs per SM in total, at least 8 K steps each
-  int64_t chunks = (148 * 4 + (int64_t)taps * n_co * n_ci - 1) / ((int64_t)taps * n_co * n_ci);
+  // enough position chunks for ~6 CTAs per SM in total, at least 8 K steps each
+  int64_t chunks = (148 * 6 + (int64_t)taps * n_co * n_ci - 1) / ((int64_t)taps * n_co * n_ci);
   const int64_t max_chunks = (rows + 8 * WG_KS - 1) / (8 * WG_KS);
   if (chunks > max_chunks) chunks = max_chunks;
   if (chunks < 1) chunks = 1;

@@ -170,8 +170,11 @@ __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(dv_gn_bwd_params p, i
 //   y = xh * g ;  h = dy*g ;  dx = rstd * (h - mean(h) - xh*mean(h*xh)) ;  dg += sum_rows dy*xh
 template <typename T, int MAXV>
 __global__ void __launch_bounds__(256) layernorm_bwd_kernel(dv_layernorm_bwd_params p) {
+  __shared__ float sdg[1024];  // per-CTA reduction of dg before the global atomics
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
+  for (int c = threadIdx.x; c < p.C; c += blockDim.x) sdg[c] = 0.f;
+  __syncthreads();
   float dg[MAXV][4];
 #pragma unroll
   for (int i = 0; i < MAXV; ++i)
@@ -243,9 +246,11 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(dv_layernorm_bwd_par
     const int c = (i * 32 + lane) * 4;
     if (c < p.C) {
 #pragma unroll
-      for (int k = 0; k < 4; ++k) atomicAdd(p.dg + c + k, dg[i][k]);
+      for (int k = 0; k < 4; ++k) atomicAdd(&sdg[c + k], dg[i][k]);
     }
   }
+  __syncthreads();
+  for (int c = threadIdx.x; c < p.C; c += blockDim.x) atomicAdd(p.dg + c, sdg[c]);
 }
 
 }  // namespace dv
@@ -311,7 +316,7 @@ extern "C" int dv_layernorm_bwd(const dv_layernorm_bwd_params* p, dv_stream_t st
   if (p->dtype == DV_BF16) DV_REQUIRE(p->C % 8 == 0, DV_EALIGN, "dv_layernorm_bwd: bf16 rows need C %% 8 == 0");
   const int wpb = 8;
   int64_t blocks = (p->rows + wpb - 1) / wpb;
-  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (blocks > 148 * 4) blocks = 148 * 4;
   cudaStream_t s = as_stream(stream);
 #define DV_LNB(T, V) layernorm_bwd_kernel<T, V><<<(unsigned)blocks, wpb * 32, 0, s>>>(*p)
   if (p->dtype == DV_F32) {

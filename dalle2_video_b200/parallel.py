@@ -23,3 +23,15 @@ def shard_rows(tensor, rank: int, world_size: int):
         return None
     lo, hi = shard_bounds(tensor.shape[0], rank, world_size)
     return tensor[lo:hi]
+
+
+def allreduce_mean_(flat):
+    """Data-parallel gradient averaging of the training config: ONE all-reduce of the flat gradient
+    buffer, then divide by the world size (accelerate-DDP semantics, /root/reference/dalle2_video/trainer.py:117-124,360).
+    NCCL for CUDA tensors, gloo in the CPU tests; a no-op without an initialised process group."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return flat
+    dist.all_reduce(flat)
+    flat.div_(dist.get_world_size())
+    return flat

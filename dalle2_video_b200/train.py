@@ -28,6 +28,7 @@ import torch.nn.functional as F
 from torch import nn
 
 from . import _lib as L
+from .parallel import allreduce_mean_
 from .unet3d import Unet3D, _CrossAttn, _CrossEmbed, _prob_mask
 
 
@@ -672,9 +673,7 @@ class VideoDecoderTrainer(nn.Module):
     def forward(self, video, video_embed, unet_number=None, **kwargs):
         loss = self.decoder(video, video_embed=video_embed, unet_number=unet_number, **kwargs)
         loss.backward()
-        if torch.distributed.is_available() and torch.distributed.is_initialized() and torch.distributed.get_world_size() > 1:
-            torch.distributed.all_reduce(self.flat_g)
-            self.flat_g.div_(torch.distributed.get_world_size())
+        allreduce_mean_(self.flat_g)
         return loss.item()
 
     @torch.no_grad()
