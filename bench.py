@@ -149,6 +149,13 @@ def profile_conv_family(eng, iters=3):
     flops = sum(conv_flops(p) for _, p in convs)
     tc = sum(1 for _, p in convs if L.lib().dv_conv_uses_tcgen05(p))
     total = 0.0
+    # the single dominant launch shape: the 3x3 64->64 convolution at full resolution (14 of the 88 launches, 35 % of the
+    # family's time) — its per-launch duration is what roofline.traffic (one ncu --set full capture) is quoted against
+    def is_dom(p):
+        return p.kh == 3 and p.H == SIZE and p.C0 == 64 and p.C1 == 0 and p.Cout == 64 and p.mode == 0
+    dom_n = sum(1 for _, p in convs if is_dom(p))
+    dom_flops = conv_flops(next(p for _, p in convs if is_dom(p))) if dom_n else 0.0
+    dom_sec = 0.0
     for it in range(iters + 1):
         evs = []
         eng.stats.zero_()
@@ -158,13 +165,14 @@ def profile_conv_family(eng, iters=3):
                 a.record()
                 L.call(name, p, stream)
                 b.record()
-                evs.append((a, b))
+                evs.append((a, b, is_dom(p)))
             else:
                 L.call(name, p, stream)
         torch.cuda.synchronize()
         if it > 0:
-            total += sum(a.elapsed_time(b) for a, b in evs) * 1e-3
-    return flops, total / iters, len(convs), tc
+            total += sum(a.elapsed_time(b) for a, b, _ in evs) * 1e-3
+            dom_sec += sum(a.elapsed_time(b) for a, b, d in evs if d) * 1e-3
+    return flops, total / iters, len(convs), tc, dom_sec / iters / max(dom_n, 1), dom_flops, dom_n
 
 
 def run_gpu_arm(args):
@@ -275,7 +283,11 @@ def run_gpu_arm(args):
 
     if rank == 0:
         pk = peaks()
-        flops, conv_sec, n_conv, n_tc = profile_conv_family(eng)
+        flops, conv_sec, n_conv, n_tc, dom_sec, dom_flops, dom_n = profile_conv_family(eng)
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+        if os.path.isfile(tp):
+            traffic = json.load(open(tp)).get(f"conv_halo_3x3_64x64_C64_C64_B{B}")
         achieved = flops / conv_sec / 1e12
         value = world * B * args.steps / elapsed
         e2e_val = world * B * e2e_steps / e2e_elapsed
@@ -309,7 +321,16 @@ def run_gpu_arm(args):
                          "peak": pk["bf16_sustained"], "unit": "TFLOP/s", "frac": achieved / pk["bf16_sustained"],
                          "peak_source": pk["source"] + " bf16_tflops_sustained (kernel timed inside the step)",
                          "algorithmic_gflop_per_step": flops / 1e9, "conv_ms_per_step": conv_sec * 1e3,
-                         "launches": n_conv, "tcgen05_launches": n_tc, "traffic": None},
+                         "launches": n_conv, "tcgen05_launches": n_tc,
+                         "dominant_launch": {"kernel": "conv_halo_kernel 3x3 64->64 @64x64 (dv_conv_igemm)", "launches_per_step": dom_n,
+                                             "algorithmic_gflop": dom_flops / 1e9, "avg_ms": dom_sec * 1e3,
+                                             "achieved": dom_flops / dom_sec / 1e12 if dom_sec else None,
+                                             "frac": dom_flops / dom_sec / 1e12 / pk["bf16_sustained"] if dom_sec else None,
+                                             "algorithmic_bytes": 2.0 * 2 * B * FRAMES * SIZE * SIZE * 64},
+                         "traffic": traffic,
+                         "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant launch shape, "
+                                         "one ncu --set full capture (profiles/r01_ncu_full_s3_summary.txt); null for batches "
+                                         "that were not captured"},
             "cpu_baseline": cpu,
         }
         print(json.dumps(line), flush=True)

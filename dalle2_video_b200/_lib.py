@@ -25,6 +25,12 @@ class DdpmStepParams(C.Structure):
                 ("n", i64), ("cond_scale", f32), ("clip_denoised", i32), ("eps_dtype", i32)]
 
 
+class DdimStepParams(C.Structure):
+    _fields_ = [("x_t", vp), ("eps", vp), ("eps_null", vp), ("noise", vp), ("out", vp), ("unnormalize_out", vp),
+                ("coef", vp), ("step_dev", vp), ("t_dev", vp), ("times", vp), ("step_host", i32), ("n_pairs", i32),
+                ("advance", i32), ("n", i64), ("cond_scale", f32), ("clip_denoised", i32), ("eps_dtype", i32)]
+
+
 class ConvParams(C.Structure):
     _fields_ = [("src0", vp), ("src1", vp), ("weight", vp), ("bias", vp), ("add", vp), ("out", vp), ("stats", vp),
                 ("n_img", i32), ("frames", i32), ("H", i32), ("W", i32), ("C0", i32), ("C1", i32), ("Cout", i32),
@@ -178,7 +184,7 @@ class AdamwParams(C.Structure):
 
 # every symbol include/dv_b200.h declares: name -> params struct (None for the plain helpers)
 ENTRY_POINTS = {
-    "dv_ddpm_step": DdpmStepParams, "dv_conv_igemm": ConvParams, "dv_gn_apply": GnApplyParams,
+    "dv_ddpm_step": DdpmStepParams, "dv_ddim_step": DdimStepParams, "dv_conv_igemm": ConvParams, "dv_gn_apply": GnApplyParams,
     "dv_gn_stats": GnStatsParams, "dv_layernorm": LayerNormParams, "dv_xattn_core": XattnParams,
     "dv_xattn_fold_prep": XattnFoldPrepParams, "dv_xattn_fold": XattnFoldParams,
     "dv_attn_mqa": AttnMqaParams, "dv_attn_temporal": AttnTemporalParams,

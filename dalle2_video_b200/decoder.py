@@ -262,10 +262,123 @@ class VideoDecoder(nn.Module):
         timesteps = timesteps if timesteps is not None else num_timesteps
         assert timesteps <= num_timesteps
         if timesteps < num_timesteps:
-            # the reference's DDIM branch raises TypeError (kwarg mismatch); a working strided
-            # sampler is scope row N1
-            raise NotImplementedError("DDIM / strided sampling is unreachable in the reference and not built yet")
+            # the reference's DDIM branch raises TypeError as shipped (kwarg mismatch); this is the
+            # working strided sampler of scope row N1 with the reference's arithmetic
+            return self.p_sample_loop_ddim(*args, noise_scheduler=noise_scheduler, timesteps=timesteps, **kwargs)
         return self.p_sample_loop_ddpm(*args, noise_scheduler=noise_scheduler, **kwargs)
+
+    @staticmethod
+    def ddim_time_pairs(total_timesteps, timesteps):
+        """(time, time_next) pairs exactly as the reference builds them (:1796-1799)."""
+        times = torch.linspace(0.0, total_timesteps, steps=timesteps + 2)[:-1]
+        times = list(reversed(times.int().tolist()))
+        return [(a, b) for a, b in zip(times[:-1], times[1:]) if a > b]
+
+    @torch.no_grad()
+    def p_sample_loop_ddim(self, unet, shape, video_embed, noise_scheduler, timesteps, eta=None, predict_x_start=False,
+                           predict_v=False, learned_variance=False, clip_denoised=True, lowres_cond_vid=None,
+                           text_encodings=None, cond_scale=1, is_latent_diffusion=False, lowres_noise_level=None, *,
+                           noise_fn=None, record=None):
+        """DDIM / strided sampling (scope row N1).  Arithmetic of the reference's p_sample_loop_ddim (:1757-1889, which is
+        unreachable as shipped): eta = self.ddim_sampling_eta, one `randn_like` per step except the last.  One step =
+        the Unet3D launch plan + ONE fused update kernel (dv_ddim_step), replayed as a CUDA graph whose pair index and
+        timestep live in device memory."""
+        self._check_native(predict_x_start, predict_v, learned_variance, lowres_cond_vid, lowres_noise_level)
+        assert not (cond_scale != 1.0 and not self.can_classifier_guidance), \
+            "the decoder was not trained with conditional dropout, and thus one cannot use classifier free guidance"
+        device = self.device
+        if device.type != "cuda":
+            raise L.DvError("VideoDecoder(b200) samples on CUDA only: there is no CPU path")
+        eta = self.ddim_sampling_eta if eta is None else eta
+        b, c, T, H, W = shape
+        cfg = cond_scale != 1
+        beff = 2 * b if cfg else b
+        use_text = text_encodings is not None and unet.cond_on_text_encodings
+        n_text = 0
+        if use_text:
+            text_encodings = text_encodings[:, : unet.max_text_len]
+            n_text = text_encodings.shape[1]
+        eng = unet.engine(beff, T, H, W, unet._resolve_dtype(), device, n_text)
+        ones = torch.ones(b, dtype=torch.uint8, device=device)
+        keep = torch.cat((ones, torch.zeros_like(ones))) if cfg else ones
+        rep = (lambda t: torch.cat((t, t), dim=0)) if cfg else (lambda t: t)
+        eng.set_conditioning(rep(video_embed) if video_embed is not None else None,
+                             rep(text_encodings) if use_text else None, keep, keep)
+        eng.set_time_source(True)
+
+        pairs = self.ddim_time_pairs(noise_scheduler.num_timesteps, timesteps)
+        n_pairs = len(pairs)
+        ns = noise_scheduler
+        t_idx = torch.tensor([p[0] for p in pairs], device=ns.alphas_cumprod.device)
+        n_idx = torch.tensor([p[1] for p in pairs], device=ns.alphas_cumprod.device)
+        alpha, alpha_next = ns.alphas_cumprod[t_idx], ns.alphas_cumprod[n_idx]          # float32, as the reference
+        c1 = eta * ((1 - alpha / alpha_next) * (1 - alpha_next) / (1 - alpha)).sqrt()
+        c2 = ((1 - alpha_next) - torch.square(c1)).sqrt()
+        c1 = torch.where(n_idx == 0, torch.zeros_like(c1), c1)                           # no noise on the last step
+        coef = torch.stack((ns.sqrt_recip_alphas_cumprod[t_idx], ns.sqrt_recipm1_alphas_cumprod[t_idx], alpha_next.sqrt(),
+                            c1, c2), dim=1).float().contiguous().to(device)
+        times_dev = torch.tensor([p[0] for p in pairs] + [pairs[-1][1]], dtype=torch.int32, device=device)
+        step_dev = torch.zeros(1, dtype=torch.int32, device=device)
+
+        n = b * c * T * H * W
+        draw = (lambda i: noise_fn(shape, i).to(device)) if noise_fn is not None else \
+            (lambda i: torch.randn(shape, device=device))
+        x = eng.x_in[:b]
+        x.copy_(draw(0))
+        if cfg:
+            eng.x_in[b:].copy_(x)
+        noise = torch.zeros(shape, device=device)
+        result = torch.empty(shape, device=device)
+        eps_elems = b * unet.channels_out * T * H * W
+        params = L.DdimStepParams(
+            x_t=x.data_ptr(), eps=eng.eps.data_ptr(), eps_null=eng.eps.data_ptr() + eps_elems * 4 if cfg else None,
+            noise=noise.data_ptr(), out=x.data_ptr(), unnormalize_out=result.data_ptr(), coef=coef.data_ptr(),
+            step_dev=step_dev.data_ptr(), t_dev=eng.t_dev.data_ptr(), times=times_dev.data_ptr(), step_host=0,
+            n_pairs=n_pairs, advance=1, n=n, cond_scale=float(cond_scale), clip_denoised=int(bool(clip_denoised)),
+            eps_dtype=L.DV_F32)
+        stream_of = lambda: torch.cuda.current_stream(device).cuda_stream  # noqa: E731
+
+        def one_step():
+            eng.run()
+            L.call("dv_ddim_step", params, stream_of())
+            if cfg:
+                eng.x_in[b:].copy_(x)
+
+        def rewind():
+            step_dev.zero_()
+            eng.t_dev.fill_(pairs[0][0])
+
+        rewind()
+        graph = None
+        if self.use_cuda_graph and record is None and n_pairs > 2:
+            saved = x.clone()
+            one_step()                      # warm-up outside capture, then rewind
+            torch.cuda.synchronize(device)
+            x.copy_(saved)
+            if cfg:
+                eng.x_in[b:].copy_(x)
+            rewind()
+            graph = torch.cuda.CUDAGraph()
+            side = torch.cuda.Stream(device)
+            side.wait_stream(torch.cuda.current_stream(device))
+            with torch.cuda.stream(side):
+                with torch.cuda.graph(graph, stream=side):
+                    one_step()
+            torch.cuda.current_stream(device).wait_stream(side)
+        for i, (t, t_next) in enumerate(pairs):
+            if t_next != 0:
+                noise.copy_(draw(i + 1))    # `randn_like(img) if not is_last_timestep else 0.0` (:1870)
+            if graph is not None:
+                graph.replay()
+            else:
+                one_step()
+                if record is not None:
+                    record(t, eng.eps[:b].view(b, -1, T, H, W), x)
+        self.last_launch_stats = {"graph": graph is not None, "c_abi_calls_per_step": eng.launches_per_step + 1,
+                                  "tcgen05_convs_per_step": eng.n_tc, "steps": n_pairs}
+        eng.set_time_source(False)
+        out = result if self.auto_normalize_video else x
+        return out.clone()
 
     @torch.no_grad()
     def p_mean_variance(self, unet, x, t, video_embed, noise_scheduler, text_encodings=None, lowres_cond_vid=None,

@@ -79,6 +79,30 @@ typedef struct {
 int dv_ddpm_step(const dv_ddpm_step_params* p, dv_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * K7b  fused DDIM / strided update.  The reference's p_sample_loop_ddim
+ * (dalle2_video/dalle2_video.py:1757-1889) is unreachable as shipped (kwarg mismatch); this is its
+ * arithmetic for epsilon prediction:
+ *     x0 = clamp(r0*x_t - r1*eps, -1, 1) ; pred_noise = (r0*x_t - x0) / r1
+ *     out = sqrt(ac[t_next])*x0 + c1*noise + c2*pred_noise            (no noise on the last pair)
+ * coef is the (n_pairs, 5) float table { sqrt_recip_ac[t], sqrt_recipm1_ac[t], sqrt(ac[t_next]), c1, c2 } with
+ * c1 = eta*sqrt((1-ac/ac_next)(1-ac_next)/(1-ac)), c2 = sqrt(1-ac_next-c1^2), built by the host in float32 as the
+ * reference does.  The pair index lives in *step_dev (graph replay) or step_host; with `advance` the kernel's tail
+ * increments *step_dev and stores times[*step_dev] to *t_dev (the timestep the next Unet3D forward embeds).
+ */
+typedef struct {
+  const float* x_t; const void* eps; const void* eps_null; const float* noise;
+  float* out; float* unnormalize_out;
+  const float* coef;   /* [n_pairs][5] */
+  int* step_dev; int* t_dev; const int* times; /* times: [n_pairs + 1] device ints (times[n_pairs] is never embedded) */
+  int step_host, n_pairs, advance;
+  int64_t n;
+  float cond_scale;
+  int clip_denoised;
+  dv_dtype eps_dtype;
+} dv_ddim_step_params;
+int dv_ddim_step(const dv_ddim_step_params* p, dv_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
  * K1 / K3 / K4  implicit-GEMM convolution over channels-last activations.
  * Replaces nn.Conv3d with (1,k,k) kernels — Block3D.project (:107,124), res_conv (:170),
  * Downsample3D's rearrange + 1x1x1 conv (:19-26), the last-stage 1x1x1 conv (:537),

@@ -385,3 +385,37 @@ def p_sample_loop_ddpm(sd, cfg, sched: NoiseScheduler, shape, *, video_embed, te
         if record is not None:
             record(t_int, eps, vid)
     return (vid + 1) * 0.5
+
+
+def ddim_time_pairs(total_timesteps, timesteps):
+    """dalle2_video.py:1796-1799."""
+    times = torch.linspace(0.0, total_timesteps, steps=timesteps + 2)[:-1]
+    times = list(reversed(times.int().tolist()))
+    return [(a, b) for a, b in zip(times[:-1], times[1:]) if a > b]
+
+
+def p_sample_loop_ddim(sd, cfg, sched: NoiseScheduler, shape, *, video_embed, timesteps, eta=0.0, text_encodings=None,
+                       cond_scale=1.0, generator=None, clip_denoised=True, record=None):
+    """Arithmetic of the reference's p_sample_loop_ddim (dalle2_video.py:1757-1889) for epsilon prediction.  The reference
+    method is unreachable as shipped (it passes image_embed= / lowres_cond_img= to a Unet3D that takes video_embed=,
+    SURVEY.md F5): PARITY UNPINNED against the reference, this restates its math with the keyword fixed.
+    RNG contract: randn(shape), then one randn per step except the last (:1870)."""
+    alphas = sched.alphas_cumprod
+    vid = torch.randn(shape, generator=generator)
+    for time, time_next in ddim_time_pairs(sched.num_timesteps, timesteps):
+        is_last = time_next == 0
+        alpha, alpha_next = alphas[time], alphas[time_next]
+        t = torch.full((shape[0],), time, dtype=torch.long)
+        pred = forward_with_cond_scale(sd, cfg, vid, t, video_embed=video_embed, text_encodings=text_encodings,
+                                       cond_scale=cond_scale)
+        x_start = sched.predict_start_from_noise(vid, t=t, noise=pred)
+        if clip_denoised:
+            x_start = x_start.clamp(-1.0, 1.0) / 1.0
+        pred_noise = sched.predict_noise_from_start(vid, t=t, x0=x_start)
+        c1 = eta * ((1 - alpha / alpha_next) * (1 - alpha_next) / (1 - alpha)).sqrt()
+        c2 = ((1 - alpha_next) - torch.square(c1)).sqrt()
+        noise = torch.randn(shape, generator=generator) if not is_last else 0.0
+        vid = x_start * alpha_next.sqrt() + c1 * noise + c2 * pred_noise
+        if record is not None:
+            record(time, pred, vid)
+    return (vid + 1) * 0.5

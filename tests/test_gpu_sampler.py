@@ -104,3 +104,63 @@ def test_p_sample_single_step_api(layouts):
     t2 = torch.tensor([0, 9]).cuda()
     out2, _ = d.p_sample(d.unets[0], x, t2, emb, s, noise=noise)
     assert float((out2[1] - out[1]).abs().max()) < 1e-5
+
+
+# ------------------------------------------------------------------ DDIM / strided sampling (scope row N1)
+def test_ddim_step_kernel_matches_reference_arithmetic():
+    from dalle2_video_b200 import NoiseScheduler
+    from dalle2_video_b200 import _lib as L
+    from gpu_util import ptr, rel_err, stream
+    dev = torch.device("cuda:0")
+    s = NoiseScheduler(beta_schedule="cosine", timesteps=100, loss_type="l2").to(dev)
+    pairs = VideoDecoder.ddim_time_pairs(100, 10)
+    assert pairs[0][0] < 100 and pairs[-1][1] == 0 and all(a > b for a, b in pairs)
+    g = torch.Generator().manual_seed(0)
+    shape = (2, 3, 4, 8, 8)
+    x, eps, noise = (torch.randn(shape, generator=g).to(dev) for _ in range(3))
+    eta = 0.6
+    for i in (0, len(pairs) // 2, len(pairs) - 1):
+        t, tn = pairs[i]
+        alpha, alpha_next = s.alphas_cumprod[t], s.alphas_cumprod[tn]
+        c1 = eta * ((1 - alpha / alpha_next) * (1 - alpha_next) / (1 - alpha)).sqrt()
+        c2 = ((1 - alpha_next) - torch.square(c1)).sqrt()
+        tt = torch.full((2,), t, device=dev)
+        x0 = s.predict_start_from_noise(x, tt, eps).clamp(-1, 1)
+        pn = s.predict_noise_from_start(x, tt, x0)
+        ref = x0 * alpha_next.sqrt() + (0.0 if tn == 0 else c1) * noise + c2 * pn
+        coef = torch.zeros(len(pairs), 5, device=dev)
+        coef[i] = torch.stack((s.sqrt_recip_alphas_cumprod[t], s.sqrt_recipm1_alphas_cumprod[t], alpha_next.sqrt(),
+                               c1 * (tn != 0), c2))
+        out, un = torch.empty_like(x), torch.full_like(x, -7.0)
+        L.call("dv_ddim_step", L.DdimStepParams(
+            x_t=ptr(x), eps=ptr(eps), eps_null=None, noise=ptr(noise), out=ptr(out), unnormalize_out=ptr(un), coef=ptr(coef),
+            step_dev=None, t_dev=None, times=None, step_host=i, n_pairs=len(pairs), advance=0, n=x.numel(), cond_scale=1.0,
+            clip_denoised=1, eps_dtype=L.DV_F32), stream())
+        assert rel_err(out, ref) < 2e-6
+        if tn == 0:
+            assert rel_err(un, (ref + 1) * 0.5) < 2e-6
+        else:
+            assert float(un.min()) == -7.0
+
+
+@pytest.mark.parametrize("eta", [0.0, 0.7])
+@pytest.mark.parametrize("graph", [False, True])
+def test_ddim_sampling_matches_oracle_loop(eta, graph, layouts):
+    from oracle.primitives import NoiseScheduler as OracleScheduler
+    from oracle.unet3d import UnetConfig, p_sample_loop_ddim
+    sd = synth_state_dict(layouts["tiny"], seed=7)
+    u = Unet3D(**TINY)
+    u.load_state_dict(sd, strict=True)
+    d = VideoDecoder(u, frame_size=16, frame_numbers=(4,), timesteps=100, sample_timesteps=12, learned_variance=False,
+                     ddim_sampling_eta=eta).cuda()
+    d.use_cuda_graph = graph
+    g = torch.Generator().manual_seed(4)
+    emb = torch.randn(2, 512, generator=g)
+    vid = d.sample(video_embed=emb.cuda(), noise_fn=cpu_noise(21))
+    assert d.last_launch_stats["graph"] == graph and d.last_launch_stats["steps"] == len(VideoDecoder.ddim_time_pairs(100, 12))
+    with torch.no_grad():
+        ref = p_sample_loop_ddim(sd, UnetConfig(**TINY), OracleScheduler(beta_schedule="cosine", timesteps=100, loss_type="l2"),
+                                 (2, 3, 4, 16, 16), video_embed=emb, timesteps=12, eta=eta,
+                                 generator=torch.Generator().manual_seed(21))
+    err = float((vid.cpu() - ref).abs().max())
+    assert err < 2e-3, err

@@ -85,9 +85,15 @@ def test_decoder_construction_and_quirks():
         d.sample(video_embed=torch.zeros(1, 512), text_encodings=torch.zeros(1, 4, 64))
     with pytest.raises(NotImplementedError):
         VideoDecoder((u, u), frame_sizes=(32, 64), frame_numbers=(8, 8))
-    with pytest.raises(NotImplementedError):
+    # strided (DDIM) sampling dispatches to the native loop, which — like every product path — refuses to run on CPU
+    from dalle2_video_b200._lib import DvError
+    with pytest.raises(DvError):
         d.p_sample_loop(u, (1, 3, 8, 32, 32), video_embed=torch.zeros(1, 512), noise_scheduler=d.noise_schedulers[0],
                         timesteps=10)
+    from oracle.unet3d import ddim_time_pairs
+    for total, steps in ((1000, 50), (100, 12), (50, 49)):
+        pairs = VideoDecoder.ddim_time_pairs(total, steps)
+        assert pairs == ddim_time_pairs(total, steps) and pairs[-1][1] == 0 and all(a > b for a, b in pairs)
 
 
 def test_cpu_tensors_raise_loudly():
