@@ -82,6 +82,8 @@ class _TrainPlan:
         self.refresh = []        # (dst tensor, producer()) pairs re-evaluated when the weights change
         self.grad_map = []       # (parameter, producer() -> gradient in the parameter's shape)
         self.gbufs = []          # float32 gradient accumulators (zeroed once per step)
+        self.use_cuda_graph = True
+        self._graphs = {}
         self.stats_slots = 0
         self._build()
 
@@ -556,19 +558,48 @@ class _TrainPlan:
             for dst, fn in self.refresh:
                 dst.copy_(fn())
 
-    def run_forward(self):
+    def _forward_body(self):
         stream = torch.cuda.current_stream(self.device).cuda_stream
         self.stats.zero_()
         for name, p in self.fwd:
             L.call(name, p, stream)
 
-    def run_backward(self):
+    def _backward_body(self):
         stream = torch.cuda.current_stream(self.device).cuda_stream
         torch._foreach_zero_(self.gbufs + self.zero_each_step)
         for name, p in self.bwd:
             L.call(name, p, stream)
 
+    def _replay(self, key, body):
+        """Eager on the first call (module loading, function attributes); captured into a CUDA graph on the second and
+        replayed afterwards — every pointer of the plan is fixed, so one capture serves all steps."""
+        if not self.use_cuda_graph:
+            return body()
+        state = self._graphs.get(key)
+        if state is None:
+            self._graphs[key] = "warm"
+            return body()
+        if state == "warm":
+            torch.cuda.synchronize(self.device)
+            graph = torch.cuda.CUDAGraph()
+            side = torch.cuda.Stream(self.device)
+            side.wait_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(side):
+                with torch.cuda.graph(graph, stream=side):
+                    body()
+            torch.cuda.current_stream(self.device).wait_stream(side)
+            self._graphs[key] = graph
+            state = graph
+        state.replay()
 
+    def run_refresh(self):
+        self._replay("refresh", self.refresh_weights)
+
+    def run_forward(self):
+        self._replay("fwd", self._forward_body)
+
+    def run_backward(self):
+        self._replay("bwd", self._backward_body)
 
 
 class _PlanFunction(torch.autograd.Function):
@@ -616,7 +647,7 @@ def p_losses(decoder, unet: Unet3D, x_start, times, *, video_embed, noise_schedu
     dev = x_start.device
     noise = torch.randn_like(x_start) if noise is None else noise
     plan = unet.train_plan(B, T, H, W, dev)
-    plan.refresh_weights()
+    plan.run_refresh()
     stream = torch.cuda.current_stream(dev).cuda_stream
     x_start = x_start.contiguous().float()
     noise = noise.contiguous().float()
@@ -668,7 +699,7 @@ class VideoDecoderTrainer(nn.Module):
         self._groups = [(0, nd, wd), (nd, n - nd, 0.0)]
         self.register_buffer("steps", torch.tensor([0]))
         self._sumsq = torch.zeros(1, dtype=torch.float64, device=dev)
-        unet.invalidate_cache()
+        unet._engines.clear()  # every plan (and captured graph) built before the parameters moved into the flat buffer is stale
 
     def forward(self, video, video_embed, unet_number=None, **kwargs):
         loss = self.decoder(video, video_embed=video_embed, unet_number=unet_number, **kwargs)
