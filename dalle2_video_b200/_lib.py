@@ -104,6 +104,11 @@ class Im2colParams(C.Structure):
                 ("Kpad", i32), ("dtype", i32), ("layout", i32)]
 
 
+class InitConvParams(C.Structure):
+    _fields_ = [("x", vp), ("weight", vp), ("bias", vp), ("out", vp), ("B", i32), ("C", i32), ("T", i32), ("H", i32),
+                ("W", i32), ("k", i32), ("Kpad", i32), ("Cout", i32), ("dtype", i32)]
+
+
 class ToOutParams(C.Structure):
     _fields_ = [("x", vp), ("w", vp), ("bias", vp), ("out", vp), ("B", i32), ("P", i64), ("C", i32), ("Cout", i32),
                 ("dtype", i32)]
@@ -190,6 +195,7 @@ ENTRY_POINTS = {
     "dv_attn_mqa": AttnMqaParams, "dv_attn_temporal": AttnTemporalParams,
     "dv_time_embed": TimeEmbedParams, "dv_linear_small": LinearSmallParams,
     "dv_cond_tokens": CondTokensParams, "dv_to_out": ToOutParams, "dv_im2col_init": Im2colParams,
+    "dv_init_conv": InitConvParams,
     # training step (a16)
     "dv_conv_wgrad": ConvWgradParams, "dv_colsum": ColsumParams, "dv_gn_bwd_reduce": GnBwdParams,
     "dv_gn_bwd_apply": GnBwdParams, "dv_layernorm_bwd": LayerNormBwdParams, "dv_xattn_core_bwd": XattnBwdParams,
@@ -198,7 +204,7 @@ ENTRY_POINTS = {
     "dv_add": AddParams, "dv_cast_f32_bf16": CastParams, "dv_sumsq": SumsqParams, "dv_adamw": AdamwParams,
 }
 PLAIN_SYMBOLS = ("dv_version", "dv_last_error_string", "dv_device_sm_count", "dv_conv_uses_tcgen05",
-                 "dv_attn_mqa_workspace_bytes", "dv_attn_temporal_uses_mma", "dv_attn_mqa_bwd_workspace_bytes")
+                 "dv_attn_mqa_workspace_bytes", "dv_attn_temporal_uses_mma", "dv_attn_mqa_bwd_workspace_bytes", "dv_init_conv_supported")
 
 _lib = None
 _SYNC_EACH = bool(os.environ.get("DV_SYNC_EACH"))
@@ -236,6 +242,8 @@ def lib():
         _lib.dv_attn_temporal_uses_mma.restype = i32
         _lib.dv_attn_mqa_bwd_workspace_bytes.argtypes = [C.POINTER(AttnMqaBwdParams)]
         _lib.dv_attn_mqa_bwd_workspace_bytes.restype = i64
+        _lib.dv_init_conv_supported.argtypes = [C.POINTER(InitConvParams)]
+        _lib.dv_init_conv_supported.restype = i32
     return _lib
 
 

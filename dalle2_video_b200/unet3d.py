@@ -307,6 +307,7 @@ class Unet3D(nn.Module):
 
         self.compute_dtype = None  # None: follow autocast (bf16) else fp32; or torch.float32 / torch.bfloat16
         self.fuse_short_context_attention = True  # bf16: folded single-kernel CrossAttention for <= 7 keys
+        self.fuse_init_conv = True                # bf16: CrossEmbedLayer3D as one tcgen05 kernel (no im2col in HBM)
         self._engines = {}
         self._param_version = None
 
@@ -796,6 +797,15 @@ class _Engine:
             co0 += co
         wp = torch.zeros(u.init_dim, kpad)
         wp[:, :ktot] = wfull.reshape(u.init_dim, ktot)
+        fused = L.InitConvParams(x=self.x_in.data_ptr(), weight=None, bias=None, out=x0.ptr, B=self.B, C=cin, T=self.T, H=H,
+                                 W=W, k=kmax, Kpad=kpad, Cout=u.init_dim, dtype=self.code)
+        if self.u.fuse_init_conv and L.lib().dv_init_conv_supported(fused):
+            # one kernel: the im2col tiles are built in shared memory and never reach HBM (include/dv_b200.h, "K4 fused")
+            fused.weight = self._w(wp).data_ptr()
+            fused.bias = self._f32(torch.cat(bfull)).data_ptr()
+            self._op("dv_init_conv", fused)
+            self.n_tc += 1
+            return True
         patches = self.pool.get(rows * kpad * self.esz)
         self._op("dv_im2col_init", L.Im2colParams(x=self.x_in.data_ptr(), out=patches.data_ptr(), B=self.B, C=cin,
                                                   T=self.T, H=H, W=W, k=kmax, Kpad=kpad, dtype=self.code, layout=1))

@@ -415,6 +415,28 @@ typedef struct {
 } dv_to_out_params;
 int dv_to_out(const dv_to_out_params* p, dv_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * K4 fused: CrossEmbedLayer3D (dalle2_video/dalle2_video.py:208-244, built :320-327) as ONE tcgen05 kernel: the
+ * im2col tiles are expanded from a shared-memory window of the (B,C,T,H,W) float32 video and never reach HBM.
+ * weight: bf16 [Cout][Kpad], K = (c*k + dy)*16 + dx (the "layout 1" packing of dv_im2col_init: the 3x3 / 7x7 filters are
+ * zero-padded, centred sub-windows of the k x k one); out: bf16 channels-last [B*T*H*W][Cout].
+ * dv_init_conv_supported: bf16, W in {32,64,128}, H % (128/W) == 0, Cout in {32,64}, weights fit in shared memory;
+ * otherwise the caller uses dv_im2col_init + dv_conv_igemm (or the CUDA-core NCDHW convolution).
+ */
+typedef struct {
+  const float* x;
+  const void* weight;
+  const float* bias;
+  void* out;
+  int B, C, T, H, W;
+  int k;      /* largest (odd) kernel size, <= 15 */
+  int Kpad;   /* row length of `weight`, multiple of 64, >= ceil(C*k/4)*64 */
+  int Cout;
+  dv_dtype dtype;
+} dv_init_conv_params;
+int dv_init_conv(const dv_init_conv_params* p, dv_stream_t stream);
+int dv_init_conv_supported(const dv_init_conv_params* p);
+
 /* ================================================================================================
  * a16 — decoder TRAINING step (/root/reference/dalle2_video/dalle2_video.py:1908-2006,
  * dalle2_video/trainer.py:322-365, :247-274).  The reference gets its backward pass from torch autograd over the

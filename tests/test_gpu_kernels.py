@@ -552,3 +552,46 @@ def test_im2col_halo_layout(dtype, k, H):
     ref = ref.reshape(B * T * H * W, C * k * 16)
     assert rel_err(out[:, :C * k * 16], ref.to(dtype)) == 0.0
     assert float(out[:, C * k * 16:].abs().max()) == 0.0
+
+
+# ------------------------------------------------------------------ K4 fused: CrossEmbedLayer3D as one tcgen05 kernel
+@pytest.mark.parametrize("B,T,H,W,dim", [(2, 3, 64, 64, 64), (1, 2, 32, 32, 32), (1, 1, 8, 128, 64), (3, 2, 16, 32, 64)])
+def test_fused_init_conv_matches_cross_embed(B, T, H, W, dim):
+    """dv_init_conv vs the three parallel Conv3d of CrossEmbedLayer3D (/root/reference/dalle2_video/dalle2_video.py:208-244)."""
+    ks, C = (3, 7, 15), 3
+    scales = [dim // 2, dim // 4, dim - dim // 2 - dim // 4]
+    x = rnd(B, C, T, H, W, seed=1)
+    ws = [rnd(co, C, 1, k, k, seed=10 + i, scale=(C * k * k) ** -0.5) for i, (k, co) in enumerate(zip(ks, scales))]
+    bs = [rnd(co, seed=20 + i) for i, co in enumerate(scales)]
+    kmax, kpad = 15, 768
+    wfull = torch.zeros(dim, C, kmax, 16, device=dev())
+    co0 = 0
+    for w, k in zip(ws, ks):
+        o = (kmax - k) // 2
+        wfull[co0:co0 + w.shape[0], :, o:o + k, o:o + k] = w[:, :, 0]
+        co0 += w.shape[0]
+    wp = torch.zeros(dim, kpad, device=dev())
+    wp[:, :C * kmax * 16] = wfull.reshape(dim, -1)
+    wp = wp.to(torch.bfloat16).contiguous()
+    bias = torch.cat(bs)
+    out = torch.empty(B * T * H * W, dim, device=dev(), dtype=torch.bfloat16)
+    p = L.InitConvParams(x=ptr(x), weight=ptr(wp), bias=ptr(bias), out=ptr(out), B=B, C=C, T=T, H=H, W=W, k=kmax, Kpad=kpad,
+                         Cout=dim, dtype=L.DV_BF16)
+    assert L.lib().dv_init_conv_supported(p) == 1
+    L.call("dv_init_conv", p, stream())
+    xb = x.to(torch.bfloat16).float()
+    ref = torch.cat([F.conv3d(xb, w.to(torch.bfloat16).float(), b, padding=(0, k // 2, k // 2)) for w, b, k in zip(ws, bs, ks)], dim=1)
+    assert rel_err(cl_to_ncdhw(out, B, T, H, W), ref) < TOL[torch.bfloat16]
+    # launching it twice back to back (persistent CTAs, double-buffered windows) gives the same bits
+    out2 = torch.empty_like(out)
+    p.out = ptr(out2)
+    L.call("dv_init_conv", p, stream())
+    assert torch.equal(out, out2)
+
+
+def test_fused_init_conv_rejects_unsupported_shapes():
+    p = L.InitConvParams(x=1 << 20, weight=1 << 20, bias=None, out=1 << 20, B=1, C=3, T=1, H=8, W=48, k=15, Kpad=768, Cout=64,
+                         dtype=L.DV_BF16)
+    assert L.lib().dv_init_conv_supported(p) == 0
+    with pytest.raises(L.DvError):
+        L.call("dv_init_conv", p, stream())
