@@ -56,7 +56,7 @@ class LayerNormParams(C.Structure):
 class XattnParams(C.Structure):
     _fields_ = [("q", vp), ("out", vp), ("kv", vp), ("null_kv", vp), ("B", i32), ("P", i64), ("heads", i32),
                 ("dh", i32), ("n_ctx", i32), ("kv_ld", i64), ("k_off", i32), ("v_off", i32), ("scale", f32),
-                ("dtype", i32)]
+                ("dtype", i32), ("workspace", vp), ("workspace_bytes", i64)]
 
 
 class XattnFoldPrepParams(C.Structure):
@@ -204,7 +204,7 @@ ENTRY_POINTS = {
     "dv_add": AddParams, "dv_cast_f32_bf16": CastParams, "dv_sumsq": SumsqParams, "dv_adamw": AdamwParams,
 }
 PLAIN_SYMBOLS = ("dv_version", "dv_last_error_string", "dv_device_sm_count", "dv_conv_uses_tcgen05",
-                 "dv_attn_mqa_workspace_bytes", "dv_attn_temporal_uses_mma", "dv_attn_mqa_bwd_workspace_bytes", "dv_init_conv_supported")
+                 "dv_attn_mqa_workspace_bytes", "dv_xattn_core_workspace_bytes", "dv_attn_temporal_uses_mma", "dv_attn_mqa_bwd_workspace_bytes", "dv_init_conv_supported")
 
 _lib = None
 _SYNC_EACH = bool(os.environ.get("DV_SYNC_EACH"))
@@ -238,6 +238,8 @@ def lib():
         _lib.dv_conv_uses_tcgen05.restype = i32
         _lib.dv_attn_mqa_workspace_bytes.argtypes = [C.POINTER(AttnMqaParams)]
         _lib.dv_attn_mqa_workspace_bytes.restype = i64
+        _lib.dv_xattn_core_workspace_bytes.argtypes = [C.POINTER(XattnParams)]
+        _lib.dv_xattn_core_workspace_bytes.restype = i64
         _lib.dv_attn_temporal_uses_mma.argtypes = [C.POINTER(AttnTemporalParams)]
         _lib.dv_attn_temporal_uses_mma.restype = i32
         _lib.dv_attn_mqa_bwd_workspace_bytes.argtypes = [C.POINTER(AttnMqaBwdParams)]

@@ -185,6 +185,9 @@ __global__ void __launch_bounds__(128) attn_mqa_kernel(dv_attn_mqa_params p) {
 
 int attn_tc_supported(const dv_attn_mqa_params& p);
 int attn_tc_launch(const dv_attn_mqa_params& p, cudaStream_t s);
+int64_t xattn_tc_workspace_bytes(const dv_xattn_params& p);
+int xattn_tc_supported(const dv_xattn_params& p);
+int xattn_tc_launch(const dv_xattn_params& p, cudaStream_t s);
 
 }  // namespace dv
 
@@ -193,12 +196,22 @@ extern "C" int64_t dv_attn_mqa_workspace_bytes(const dv_attn_mqa_params* p) {
   return (int64_t)p->S * p->dh * p->n * 2;
 }
 
+extern "C" int64_t dv_xattn_core_workspace_bytes(const dv_xattn_params* p) {
+  return p ? dv::xattn_tc_workspace_bytes(*p) : 0;
+}
+
 extern "C" int dv_xattn_core(const dv_xattn_params* p, dv_stream_t stream) {
   using namespace dv;
   DV_REQUIRE(p && p->q && p->out && p->kv && p->null_kv, DV_EINVAL, "dv_xattn_core: null pointer");
   DV_REQUIRE(p->B > 0 && p->P > 0 && p->heads > 0 && p->n_ctx > 0, DV_EINVAL, "dv_xattn_core: bad dimensions");
   DV_REQUIRE(p->dh == 64, DV_EUNSUPPORTED, "dv_xattn_core: only dim_head=64 is built (got %d)", p->dh);
   DV_REQUIRE(aligned16(p->q) && aligned16(p->out), DV_EALIGN, "dv_xattn_core: q/out must be 16-byte aligned");
+  if (p->workspace) {
+    DV_REQUIRE(xattn_tc_supported(*p), DV_EUNSUPPORTED,
+               "dv_xattn_core: a workspace was passed but the tcgen05 kernel does not take these parameters "
+               "(bf16, dh 64, P %% 128 == 0, workspace >= dv_xattn_core_workspace_bytes, 128-byte aligned)");
+    return xattn_tc_launch(*p, as_stream(stream));
+  }
   const size_t smem = sizeof(float) * 2 * (size_t)(p->n_ctx + 1) * p->dh;
   DV_REQUIRE(smem <= 200 * 1024, DV_EUNSUPPORTED, "dv_xattn_core: context of %d tokens does not fit shared memory",
              p->n_ctx);

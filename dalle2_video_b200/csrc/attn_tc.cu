@@ -14,6 +14,12 @@
 //     thr  O     = O*corr + Ot_j    (rescaling stays in registers; TMEM is never rescaled)
 // V is needed K-major ([dh][keys]) for the second MMA, so a small pre-pass transposes V into caller-supplied scratch.
 // The n x (n+1) logits of the reference (67 MB per sample at n=1024) never exist.
+//
+// The same kernel, instantiated <64, MHA>, is the K5 core for LONG contexts (CrossAttention over the 262 text + time +
+// video tokens of the two mid blocks, dalle2_video.py:860, :919-924): there every head has its own K/V, so a
+// Q tile is 128 queries of ONE head (3-D TMA view of the [tokens][heads*dh] projection), a pre-pass packs the float32
+// conditioning K/V (+ the null key as key 0) into bf16 K [b,h][keys][64] / V^T [b,h][64][keys] padded to a multiple
+// of 128 keys, and the padded keys are masked out of the softmax.
 #include <math_constants.h>
 
 #include "tc_common.cuh"
@@ -26,9 +32,11 @@ constexpr int AT_STAGES = 3;
 
 struct AttnTcParams {
   int n, heads, dh;
-  int q_tiles_per_seq;  // n*heads/128
-  int64_t total_tiles;  // S * q_tiles_per_seq
-  int k_tiles;          // n/128
+  int q_tiles_per_seq;  // MQA: n*heads/128; MHA: n/128 (per (sequence, head))
+  int64_t total_tiles;  // MQA: S * q_tiles_per_seq; MHA: S * heads * q_tiles_per_seq
+  int k_tiles;          // key tiles of 128
+  int keys_per_seq;     // rows of one K / V^T block (MQA: n; MHA: padded key count)
+  int n_valid;          // keys that take part in the softmax (MHA: n_ctx + 1; MQA: n, i.e. no masking)
   const __nv_bfloat16* q;
   __nv_bfloat16* out;
   const float* null_kv;
@@ -61,6 +69,11 @@ __device__ __forceinline__ void tma_load_3d_at(const CUtensorMap* map, uint64_t*
 }
 
 template <int DH>
+__device__ __forceinline__ uint64_t qk_desc(uint32_t saddr) {
+  return DH == 32 ? make_smem_desc_sw64(saddr) : make_smem_desc(saddr);  // 64-byte rows vs 128-byte rows
+}
+
+template <int DH, bool MHA>
 __global__ void __launch_bounds__(AT_THREADS, 1)
 attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                const __grid_constant__ CUtensorMap map_vt, const AttnTcParams p) {
@@ -86,6 +99,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr uint32_t TMEM_COLS = 512;  // S: 2 x 128, Ot: 2 x DH (at 256, 256 + DH)
+  static_assert(DH == 32 || DH == 64, "dim_head 32 or 64");
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_q);
@@ -120,15 +134,22 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
       uint32_t ph = 0;
       int t = 0;
       for (int64_t tile = tile_begin; tile < tile_end; ++tile, ++t) {
+        // MQA: seq = sequence; MHA: seq = (sequence, head) pair, the unit that owns a K / V^T block
         const int seq = (int)(tile / p.q_tiles_per_seq);
         mbar_wait(&q_free[t & 1], (uint32_t)(((t >> 1) & 1) ^ 1));  // the tile that used this Q buffer is done
         mbar_expect_tx(&q_full[t & 1], Q_BYTES);
-        tma_load_2d(&map_q, &q_full[t & 1], q_s + (t & 1) * Q_BYTES, 0, (int)(tile * 128));
+        if (MHA) {
+          const int qt = (int)(tile - (int64_t)seq * p.q_tiles_per_seq);
+          const int s_idx = seq / p.heads, h = seq - s_idx * p.heads;
+          tma_load_3d_at(&map_q, &q_full[t & 1], q_s + (t & 1) * Q_BYTES, 0, h, s_idx * p.n + qt * 128);
+        } else {
+          tma_load_2d(&map_q, &q_full[t & 1], q_s + (t & 1) * Q_BYTES, 0, (int)(tile * 128));
+        }
         for (int j = 0; j < nt; ++j) {
           mbar_wait(&kv_empty[st], ph ^ 1);
           uint8_t* dst = kv_s + st * STAGE_BYTES;
           mbar_expect_tx(&kv_full[st], STAGE_BYTES);
-          tma_load_2d(&map_k, &kv_full[st], dst, 0, seq * p.n + j * AT_KT);
+          tma_load_2d(&map_k, &kv_full[st], dst, 0, seq * p.keys_per_seq + j * AT_KT);
           tma_load_3d_at(&map_vt, &kv_full[st], dst + K_BYTES, j * AT_KT, 0, seq);
           tma_load_3d_at(&map_vt, &kv_full[st], dst + K_BYTES + VT_BYTES / 2, j * AT_KT + 64, 0, seq);
           if (++st == AT_STAGES) { st = 0; ph ^= 1; }
@@ -146,13 +167,13 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
     for (int64_t tile = tile_begin; tile < tile_end; ++tile, ++t) {
       mbar_wait(&q_full[t & 1], (uint32_t)((t >> 1) & 1));
       tc_fence_after();
-      const uint64_t qd = make_smem_desc_sw64(smem_u32(q_s + (t & 1) * Q_BYTES));
+      const uint64_t qd = qk_desc<DH>(smem_u32(q_s + (t & 1) * Q_BYTES));
       auto issue_s = [&](int j) {
         // S_j into S buffer (jj+j)&1 ; needs K_j
         mbar_wait(&kv_full[st], ph);
         tc_fence_after();
         if (elect_one()) {
-          const uint64_t kd = make_smem_desc_sw64(smem_u32(kv_s + st * STAGE_BYTES));
+          const uint64_t kd = qk_desc<DH>(smem_u32(kv_s + st * STAGE_BYTES));
           const uint32_t d = tmem_base + (uint32_t)(((jj + j) & 1) * 128);
 #pragma unroll
           for (int kk = 0; kk < DH / 16; ++kk) umma_f16(d, qd + (uint64_t)(kk * 2), kd + (uint64_t)(kk * 2), idesc_s, kk != 0);
@@ -191,11 +212,28 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
     int t = 0;
     int64_t jj = 0;
     for (int64_t tile = tile_begin; tile < tile_end; ++tile, ++t) {
-      const int64_t grow = tile * 128 + row;  // global (query, head) row: q / out are [rows][DH] contiguous
-      // null key / value initialise the online softmax (logit of key 0 = scale * q . k_null)
+      // global (query, head) row: q / out are [tokens][heads][DH]; MQA tiles walk it linearly, MHA tiles walk the tokens
+      // of one head
+      int64_t grow;
+      if (MHA) {
+        const int seq = (int)(tile / p.q_tiles_per_seq);
+        const int qt = (int)(tile - (int64_t)seq * p.q_tiles_per_seq);
+        const int s_idx = seq / p.heads, h = seq - s_idx * p.heads;
+        grow = ((int64_t)s_idx * p.n + qt * 128 + row) * p.heads + h;
+      } else {
+        grow = tile * 128 + row;
+      }
       float o[DH];
-      float m, l = 1.0f;
-      {
+      float m, l;
+      if (MHA) {
+        // the null key / value are key 0 of the packed K / V^T blocks: plain online-softmax start
+        m = -CUDART_INF_F;
+        l = 0.f;
+#pragma unroll
+        for (int e = 0; e < DH; ++e) o[e] = 0.f;
+      } else {
+        // null key / value initialise the online softmax (logit of key 0 = scale * q . k_null)
+        l = 1.0f;
         float qv[DH];
 #pragma unroll
         for (int e = 0; e < DH; e += 8) {
@@ -216,14 +254,16 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
         const int buf = (int)((jj + j) & 1);
         mbar_wait(&s_full[buf], (uint32_t)(((jj + j) >> 1) & 1));
         tc_fence_after();
-        // pass 1: row maximum of this tile
+        // pass 1: row maximum of this tile (keys >= n_valid are padding: only the MHA instantiation has any)
+        const int lim = MHA ? p.n_valid - j * AT_KT : AT_KT;
         float mx = m;
 #pragma unroll 1
         for (int c0 = 0; c0 < AT_KT; c0 += 32) {
           uint32_t r[32];
           tmem_ld32(t_lane + (uint32_t)(buf * 128 + c0), r);
 #pragma unroll
-          for (int k = 0; k < 32; ++k) mx = fmaxf(mx, __uint_as_float(r[k]) * p.scale_log2e);
+          for (int k = 0; k < 32; ++k)
+            if (!MHA || c0 + k < lim) mx = fmaxf(mx, __uint_as_float(r[k]) * p.scale_log2e);
         }
         const float corr = exp2f(m - mx);
         m = mx;
@@ -232,10 +272,13 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
           const int pb = (int)((jj + j - 1) & 1);
           mbar_wait(&o_full[pb], (uint32_t)(((jj + j - 1) >> 1) & 1));
           tc_fence_after();
-          uint32_t r[32];
-          tmem_ld32(t_lane + 256u + (uint32_t)(pb * DH), r);
 #pragma unroll
-          for (int e = 0; e < DH; ++e) o[e] += __uint_as_float(r[e]);
+          for (int e0 = 0; e0 < DH; e0 += 32) {
+            uint32_t r[32];
+            tmem_ld32(t_lane + 256u + (uint32_t)(pb * DH + e0), r);
+#pragma unroll
+            for (int e = 0; e < 32; ++e) o[e0 + e] += __uint_as_float(r[e]);
+          }
         }
         l *= corr;
 #pragma unroll
@@ -253,8 +296,12 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
             __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&pk);
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-              const float a = exp2f(fmaf(__uint_as_float(r[g * 8 + 2 * e]), p.scale_log2e, -m));
-              const float b = exp2f(fmaf(__uint_as_float(r[g * 8 + 2 * e + 1]), p.scale_log2e, -m));
+              float a = exp2f(fmaf(__uint_as_float(r[g * 8 + 2 * e]), p.scale_log2e, -m));
+              float b = exp2f(fmaf(__uint_as_float(r[g * 8 + 2 * e + 1]), p.scale_log2e, -m));
+              if (MHA) {
+                if (c0 + g * 8 + 2 * e >= lim) a = 0.f;
+                if (c0 + g * 8 + 2 * e + 1 >= lim) b = 0.f;
+              }
               h2[e] = __floats2bfloat162_rn(a, b);
               // sum what the tensor core will actually multiply (the bf16-rounded probabilities)
               lsum += __low2float(h2[e]) + __high2float(h2[e]);
@@ -274,10 +321,13 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
         const int pb = (int)((jj + nt - 1) & 1);
         mbar_wait(&o_full[pb], (uint32_t)(((jj + nt - 1) >> 1) & 1));
         tc_fence_after();
-        uint32_t r[32];
-        tmem_ld32(t_lane + 256u + (uint32_t)(pb * DH), r);
 #pragma unroll
-        for (int e = 0; e < DH; ++e) o[e] += __uint_as_float(r[e]);
+        for (int e0 = 0; e0 < DH; e0 += 32) {
+          uint32_t r[32];
+          tmem_ld32(t_lane + 256u + (uint32_t)(pb * DH + e0), r);
+#pragma unroll
+          for (int e = 0; e < 32; ++e) o[e0 + e] += __uint_as_float(r[e]);
+        }
       }
       tc_fence_before();
       __syncwarp();
@@ -327,6 +377,8 @@ int attn_tc_launch(const dv_attn_mqa_params& p, cudaStream_t s) {
   k.q_tiles_per_seq = p.n * p.heads / 128;
   k.total_tiles = (int64_t)p.S * k.q_tiles_per_seq;
   k.k_tiles = p.n / AT_KT;
+  k.keys_per_seq = p.n;
+  k.n_valid = p.n;
   k.q = reinterpret_cast<const __nv_bfloat16*>(p.q);
   k.out = reinterpret_cast<__nv_bfloat16*>(p.out);
   k.null_kv = p.null_kv;
@@ -356,7 +408,7 @@ int attn_tc_launch(const dv_attn_mqa_params& p, cudaStream_t s) {
   const size_t smem = 2 * 128 * DH * 2 + AT_STAGES * (AT_KT * DH * 2 + DH * AT_KT * 2) + 2 * 16384 + 256 + 1024;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(attn_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(attn_tc_kernel<32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     DV_REQUIRE(e == cudaSuccess, DV_ECUDA, "dv_attn_mqa(tcgen05): cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     attr_set = true;
   }
@@ -368,8 +420,122 @@ int attn_tc_launch(const dv_attn_mqa_params& p, cudaStream_t s) {
     if (sm_count <= 0) sm_count = 148;
   }
   const int grid = (int)(k.total_tiles < sm_count ? k.total_tiles : sm_count);
-  attn_tc_kernel<32><<<grid, AT_THREADS, smem, s>>>(mq, mk, mv, k);
+  attn_tc_kernel<32, false><<<grid, AT_THREADS, smem, s>>>(mq, mk, mv, k);
   DV_CHECK_LAUNCH("dv_attn_mqa(tcgen05)");
+  return DV_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Long-context CrossAttention core (K5, text conditioning): pack pre-pass + the <64, MHA> instantiation.
+
+// float32 conditioning K/V (dv_xattn_params addressing) -> bf16 K [B*heads][keys_pad][64] and V^T [B*heads][64][keys_pad];
+// key 0 = the learned null key/value, keys > n_ctx are zero (a zero V^T column keeps 0 * padding finite).
+__global__ void __launch_bounds__(256) xattn_pack_kernel(const dv_xattn_params p, __nv_bfloat16* __restrict__ kp,
+                                                         __nv_bfloat16* __restrict__ vtp, int keys_pad) {
+  constexpr int DH = 64;
+  __shared__ __nv_bfloat16 tile[64][DH + 2];
+  const int j0 = blockIdx.x * 64, h = blockIdx.y, b = blockIdx.z;
+  const int64_t bh = (int64_t)b * p.heads + h;
+  for (int i = threadIdx.x; i < 64 * (DH / 4); i += blockDim.x) {
+    const int j = i / (DH / 4), d = (i % (DH / 4)) * 4;
+    const int jg = j0 + j;
+    float kk[4] = {0.f, 0.f, 0.f, 0.f}, vv[4] = {0.f, 0.f, 0.f, 0.f};
+    if (jg == 0) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { kk[e] = p.null_kv[d + e]; vv[e] = p.null_kv[DH + d + e]; }
+    } else if (jg <= p.n_ctx) {
+      const float* tok = p.kv + ((int64_t)b * p.n_ctx + (jg - 1)) * p.kv_ld;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { kk[e] = tok[p.k_off + h * DH + d + e]; vv[e] = tok[p.v_off + h * DH + d + e]; }
+    }
+    __nv_bfloat162* kdst = reinterpret_cast<__nv_bfloat162*>(kp + (bh * keys_pad + jg) * DH + d);
+    kdst[0] = __floats2bfloat162_rn(kk[0], kk[1]);
+    kdst[1] = __floats2bfloat162_rn(kk[2], kk[3]);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) tile[j][d + e] = __float2bfloat16(vv[e]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 64 * DH; i += blockDim.x) {
+    const int d = i / 64, j = i % 64;
+    vtp[(bh * DH + d) * keys_pad + j0 + j] = tile[j][d];
+  }
+}
+
+static inline int xattn_keys_pad(int n_ctx) { return (n_ctx + 1 + AT_KT - 1) / AT_KT * AT_KT; }
+
+int64_t xattn_tc_workspace_bytes(const dv_xattn_params& p) {
+  if (p.dtype != DV_BF16 || p.dh != 64 || p.heads <= 0 || p.B <= 0 || p.n_ctx <= 0) return 0;
+  if (p.P <= 0 || p.P % 128) return 0;
+  if (p.B > 65535 || p.heads > 65535) return 0;
+  if ((int64_t)p.B * p.P * p.heads >= (1ll << 31)) return 0;
+  return (int64_t)p.B * p.heads * xattn_keys_pad(p.n_ctx) * 64 * 2 * 2;
+}
+
+int xattn_tc_supported(const dv_xattn_params& p) {
+  const int64_t need = xattn_tc_workspace_bytes(p);
+  return need > 0 && p.workspace && p.workspace_bytes >= need && (reinterpret_cast<uintptr_t>(p.workspace) & 127) == 0;
+}
+
+int xattn_tc_launch(const dv_xattn_params& p, cudaStream_t s) {
+  constexpr int DH = 64;
+  const int keys_pad = xattn_keys_pad(p.n_ctx);
+  __nv_bfloat16* kp = reinterpret_cast<__nv_bfloat16*>(p.workspace);
+  __nv_bfloat16* vtp = kp + (int64_t)p.B * p.heads * keys_pad * DH;
+  {
+    dim3 grid(keys_pad / 64, p.heads, p.B);
+    xattn_pack_kernel<<<grid, 256, 0, s>>>(p, kp, vtp, keys_pad);
+    DV_CHECK_LAUNCH("dv_xattn_core(pack)");
+  }
+  AttnTcParams k;
+  memset(&k, 0, sizeof(k));
+  k.n = (int)p.P; k.heads = p.heads; k.dh = DH;
+  k.q_tiles_per_seq = (int)(p.P / 128);
+  k.total_tiles = (int64_t)p.B * p.heads * k.q_tiles_per_seq;
+  k.k_tiles = keys_pad / AT_KT;
+  k.keys_per_seq = keys_pad;
+  k.n_valid = p.n_ctx + 1;
+  k.q = reinterpret_cast<const __nv_bfloat16*>(p.q);
+  k.out = reinterpret_cast<__nv_bfloat16*>(p.out);
+  k.null_kv = p.null_kv;
+  k.scale = p.scale;
+  k.scale_log2e = p.scale * 1.4426950408889634f;
+  CUtensorMap mq, mk, mv;
+  int rc;
+  {
+    uint64_t dims[3] = {(uint64_t)DH, (uint64_t)p.heads, (uint64_t)p.B * p.P};
+    uint64_t strides[2] = {(uint64_t)DH * 2, (uint64_t)p.heads * DH * 2};
+    uint32_t box[3] = {(uint32_t)DH, 1, 128};
+    if ((rc = encode_map(&mq, p.q, 3, dims, strides, box, 128)) != DV_OK) return rc;
+  }
+  {
+    uint64_t dims[2] = {(uint64_t)DH, (uint64_t)p.B * p.heads * keys_pad};
+    uint64_t strides[1] = {(uint64_t)DH * 2};
+    uint32_t box[2] = {(uint32_t)DH, AT_KT};
+    if ((rc = encode_map(&mk, kp, 2, dims, strides, box, 128)) != DV_OK) return rc;
+  }
+  {
+    uint64_t dims[3] = {(uint64_t)keys_pad, (uint64_t)DH, (uint64_t)p.B * p.heads};
+    uint64_t strides[2] = {(uint64_t)keys_pad * 2, (uint64_t)keys_pad * 2 * DH};
+    uint32_t box[3] = {64, (uint32_t)DH, 1};
+    if ((rc = encode_map(&mv, vtp, 3, dims, strides, box, 128)) != DV_OK) return rc;
+  }
+  const size_t smem = 2 * 128 * DH * 2 + AT_STAGES * (AT_KT * DH * 2 + DH * AT_KT * 2) + 2 * 16384 + 256 + 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(attn_tc_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    DV_REQUIRE(e == cudaSuccess, DV_ECUDA, "dv_xattn_core(tcgen05): cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  static int sm_count = 0;
+  if (!sm_count) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
+    if (sm_count <= 0) sm_count = 148;
+  }
+  const int grid = (int)(k.total_tiles < sm_count ? k.total_tiles : sm_count);
+  attn_tc_kernel<64, true><<<grid, AT_THREADS, smem, s>>>(mq, mk, mv, k);
+  DV_CHECK_LAUNCH("dv_xattn_core(tcgen05)");
   return DV_OK;
 }
 

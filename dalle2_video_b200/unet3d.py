@@ -919,11 +919,21 @@ class _Engine:
                                                    eps=1e-5, dtype=self.code))
         q = self._new_act(rows, inner)
         self._conv([(xn.ptr, C)], self._w(ca.to_q.weight), None, q.ptr, inner, rows, 1, 1, frames=P)
-        self._op("dv_xattn_core", L.XattnParams(q=q.ptr, out=q.ptr, kv=kv.data_ptr(),
-                                                null_kv=self._f32(ca.null_kv).data_ptr(), B=self.B, P=P, heads=heads,
-                                                dh=dh, n_ctx=n_ctx, kv_ld=kv.shape[2], k_off=idx * 2 * inner,
-                                                v_off=idx * 2 * inner + inner, scale=float(dh ** -0.5),
-                                                dtype=self.code))
+        xp = L.XattnParams(q=q.ptr, out=q.ptr, kv=kv.data_ptr(), null_kv=self._f32(ca.null_kv).data_ptr(), B=self.B,
+                           P=P, heads=heads, dh=dh, n_ctx=n_ctx, kv_ld=kv.shape[2], k_off=idx * 2 * inner,
+                           v_off=idx * 2 * inner + inner, scale=float(dh ** -0.5), dtype=self.code, workspace=None,
+                           workspace_bytes=0)
+        ws = None
+        if n_ctx + 1 > 8:
+            # long (text) context: flash kernel on tcgen05 over packed bf16 K / V^T (include/dv_b200.h, "K5 core")
+            ws_bytes = L.lib().dv_xattn_core_workspace_bytes(xp)
+            if ws_bytes > 0:
+                ws = self.pool.get(ws_bytes)
+                xp.workspace, xp.workspace_bytes = ws.data_ptr(), ws_bytes
+                self.n_tc += 1
+        self._op("dv_xattn_core", xp)
+        if ws is not None:
+            self.pool.put(ws)
         self._conv([(q.ptr, inner)], self._w(ca.to_out[0].weight), None, xn.ptr, C, rows, 1, 1, frames=P)
         self._release(q)
         self._op("dv_layernorm", L.LayerNormParams(x=xn.ptr, out=hact.ptr, residual=hact.ptr,

@@ -250,8 +250,15 @@ typedef struct {
   int k_off, v_off;
   float scale;
   dv_dtype dtype;
+  /* Optional scratch for the tcgen05 flash kernel (bf16, dh = 64, P % 128 == 0): packed bf16 K / V^T per (sample, head),
+   * keys padded to a multiple of 128.  Size it with dv_xattn_core_workspace_bytes (0 = that kernel does not take these
+   * parameters); 128-byte aligned.  With workspace == NULL the CUDA-core kernel runs (float32 parity path, short
+   * contexts).  The mid blocks of a text-conditioned Unet3D (262 context tokens, :860, :919-924) use it. */
+  void* workspace;
+  int64_t workspace_bytes;
 } dv_xattn_params;
 int dv_xattn_core(const dv_xattn_params* p, dv_stream_t stream);
+int64_t dv_xattn_core_workspace_bytes(const dv_xattn_params* p);
 
 /* ------------------------------------------------------------------------------------------------
  * K5 fused  whole CrossAttention block for a SHORT context (n_ctx + 1 null key <= 8; the 2 time + 4 video

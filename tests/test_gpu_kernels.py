@@ -256,6 +256,63 @@ def test_cross_attention_core(dtype, n_ctx):
     assert rel_err(out, ref) < (2e-5 if dtype == torch.float32 else 6e-3)
 
 
+@pytest.mark.parametrize("B,P,n_ctx", [(2, 256, 262), (1, 1024, 262), (3, 128, 127), (2, 384, 6), (1, 128, 600)])
+def test_cross_attention_core_tcgen05(B, P, n_ctx):
+    """Long-context (text) CrossAttention core on the tcgen05 flash kernel (<64, MHA> instantiation of attn_tc_kernel):
+    packed bf16 K / V^T with the null key as key 0, keys padded to 128 and masked; in place like the plan uses it."""
+    H, D = 8, 64
+    dtype = torch.bfloat16
+    q = rnd(B * P, H * D, dtype=dtype, seed=1)
+    n_layers, layer = 2, 1
+    kv = rnd(B, n_ctx, n_layers * 2 * H * D, seed=2)
+    null_kv = rnd(2, D, seed=3)
+    xp = L.XattnParams(q=ptr(q), out=ptr(q), kv=ptr(kv), null_kv=ptr(null_kv), B=B, P=P, heads=H, dh=D, n_ctx=n_ctx,
+                       kv_ld=kv.shape[-1], k_off=layer * 2 * H * D, v_off=layer * 2 * H * D + H * D, scale=D ** -0.5,
+                       dtype=code(q), workspace=None, workspace_bytes=0)
+    need = L.lib().dv_xattn_core_workspace_bytes(xp)
+    assert need == B * H * ((n_ctx + 1 + 127) // 128 * 128) * D * 2 * 2
+    ws = torch.full((need + 64,), 0x7F, dtype=torch.uint8, device=q.device)  # poison: padding must be written by the pack
+    xp.workspace, xp.workspace_bytes = ws.data_ptr(), need
+    q_in = q.clone()
+    L.call("dv_xattn_core", xp, stream())
+    k = kv[..., layer * 2 * H * D: layer * 2 * H * D + H * D].reshape(B, n_ctx, H, D).permute(0, 2, 1, 3)
+    v = kv[..., layer * 2 * H * D + H * D: (layer + 1) * 2 * H * D].reshape(B, n_ctx, H, D).permute(0, 2, 1, 3)
+    k = torch.cat((null_kv[0].expand(B, H, 1, D), k), dim=2)
+    v = torch.cat((null_kv[1].expand(B, H, 1, D), v), dim=2)
+    qh = q_in.float().reshape(B, P, H, D).permute(0, 2, 1, 3)
+    s = math.sqrt(D ** -0.5)
+    attn = ((qh * s) @ (k * s).transpose(-1, -2)).softmax(-1)
+    ref = (attn @ v).permute(0, 2, 1, 3).reshape(B * P, H * D)
+    assert bool(torch.isfinite(q.float()).all())
+    assert rel_err(q, ref) < 1e-2
+    assert bool((ws[need:] == 0x7F).all())  # stays inside the workspace it asked for
+    if n_ctx > 300:
+        return  # beyond the CUDA-core kernel's shared-memory limit
+    # the CUDA-core kernel on the same inputs agrees
+    out2 = torch.empty_like(q_in)
+    xp2 = L.XattnParams(q=ptr(q_in), out=ptr(out2), kv=ptr(kv), null_kv=ptr(null_kv), B=B, P=P, heads=H, dh=D,
+                        n_ctx=n_ctx, kv_ld=kv.shape[-1], k_off=layer * 2 * H * D, v_off=layer * 2 * H * D + H * D,
+                        scale=D ** -0.5, dtype=code(q), workspace=None, workspace_bytes=0)
+    L.call("dv_xattn_core", xp2, stream())
+    assert rel_err(q, out2.float()) < 1e-2
+
+
+def test_cross_attention_core_workspace_contract():
+    """Shapes the tcgen05 kernel does not take report 0 bytes; passing a workspace for them is an error, not a fallback."""
+    H, D = 8, 64
+    q = rnd(200, H * D, dtype=torch.bfloat16, seed=1)
+    kv = rnd(1, 262, 2 * H * D, seed=2)
+    null_kv = rnd(2, D, seed=3)
+    xp = L.XattnParams(q=ptr(q), out=ptr(q), kv=ptr(kv), null_kv=ptr(null_kv), B=1, P=200, heads=H, dh=D, n_ctx=262,
+                       kv_ld=kv.shape[-1], k_off=0, v_off=H * D, scale=D ** -0.5, dtype=code(q), workspace=None,
+                       workspace_bytes=0)
+    assert L.lib().dv_xattn_core_workspace_bytes(xp) == 0   # P % 128 != 0
+    ws = torch.empty(1 << 20, dtype=torch.uint8, device=q.device)
+    xp.workspace, xp.workspace_bytes = ws.data_ptr(), ws.numel()
+    with pytest.raises(L.DvError):
+        L.call("dv_xattn_core", xp, stream())
+
+
 # ------------------------------------------------------------------ K6
 @pytest.mark.parametrize("dtype", DT)
 @pytest.mark.parametrize("S,n,H,D,bias", [(2, 300, 16, 32, False), (5, 16, 16, 32, True), (1, 65, 4, 64, False)])
