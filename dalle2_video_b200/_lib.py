@@ -111,7 +111,12 @@ class InitConvParams(C.Structure):
 
 class ToOutParams(C.Structure):
     _fields_ = [("x", vp), ("w", vp), ("bias", vp), ("out", vp), ("B", i32), ("P", i64), ("C", i32), ("Cout", i32),
-                ("dtype", i32)]
+                ("dtype", i32), ("extra", vp), ("Cextra", i32)]
+
+
+class ResizeNearestParams(C.Structure):
+    _fields_ = [("in_", vp), ("out", vp), ("planes", i64), ("Hin", i32), ("Win", i32), ("Hout", i32), ("Wout", i32),
+                ("clamp", i32), ("lo", f32), ("hi", f32)]
 
 
 f64p = vp
@@ -152,7 +157,7 @@ class AttnMqaBwdParams(C.Structure):
 
 class QSampleParams(C.Structure):
     _fields_ = [("video", vp), ("noise", vp), ("times", vp), ("sqrt_ac", vp), ("sqrt_1mac", vp), ("out", vp),
-                ("n", i64), ("per_sample", i64), ("normalize", i32)]
+                ("n", i64), ("per_sample", i64), ("normalize", i32), ("unnormalize", i32)]
 
 
 class MseLossParams(C.Structure):
@@ -195,7 +200,7 @@ ENTRY_POINTS = {
     "dv_attn_mqa": AttnMqaParams, "dv_attn_temporal": AttnTemporalParams,
     "dv_time_embed": TimeEmbedParams, "dv_linear_small": LinearSmallParams,
     "dv_cond_tokens": CondTokensParams, "dv_to_out": ToOutParams, "dv_im2col_init": Im2colParams,
-    "dv_init_conv": InitConvParams,
+    "dv_init_conv": InitConvParams, "dv_resize_nearest": ResizeNearestParams,
     # training step (a16)
     "dv_conv_wgrad": ConvWgradParams, "dv_colsum": ColsumParams, "dv_gn_bwd_reduce": GnBwdParams,
     "dv_gn_bwd_apply": GnBwdParams, "dv_layernorm_bwd": LayerNormBwdParams, "dv_xattn_core_bwd": XattnBwdParams,

@@ -150,8 +150,9 @@ __global__ void __launch_bounds__(128) cond_tokens_kernel(dv_cond_tokens_params 
 // to_out: thread per position, weights in shared memory, output planes written coalesced.
 template <typename T, int CO>
 __global__ void __launch_bounds__(256) to_out_kernel(dv_to_out_params p) {
-  extern __shared__ float w[];  // [CO][C]
-  for (int i = threadIdx.x; i < CO * p.C; i += blockDim.x) w[i] = p.w[i];
+  extern __shared__ float w[];  // [CO][C + Cextra]
+  const int ldw = p.C + p.Cextra;
+  for (int i = threadIdx.x; i < CO * ldw; i += blockDim.x) w[i] = p.w[i];
   __syncthreads();
   const int b = blockIdx.y;
   const int64_t pos = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -166,7 +167,12 @@ __global__ void __launch_bounds__(256) to_out_kernel(dv_to_out_params p) {
 #pragma unroll
     for (int o = 0; o < CO; ++o)
 #pragma unroll
-      for (int k = 0; k < 8; ++k) acc[o] = fmaf(v[k], w[o * p.C + c + k], acc[o]);
+      for (int k = 0; k < 8; ++k) acc[o] = fmaf(v[k], w[o * ldw + c + k], acc[o]);
+  }
+  for (int c = 0; c < p.Cextra; ++c) {
+    const float v = p.extra[((int64_t)b * p.Cextra + c) * p.P + pos];
+#pragma unroll
+    for (int o = 0; o < CO; ++o) acc[o] = fmaf(v, w[o * ldw + p.C + c], acc[o]);
   }
 #pragma unroll
   for (int o = 0; o < CO; ++o) p.out[((int64_t)b * CO + o) * p.P + pos] = acc[o];
@@ -225,7 +231,8 @@ extern "C" int dv_to_out(const dv_to_out_params* p, dv_stream_t stream) {
   DV_REQUIRE(p->Cout == 3 || p->Cout == 6, DV_EUNSUPPORTED, "dv_to_out: channels_out must be 3 or 6 (got %d)", p->Cout);
   DV_REQUIRE(aligned16(p->x), DV_EALIGN, "dv_to_out: x must be 16-byte aligned");
   dim3 grid((unsigned)((p->P + 255) / 256), p->B);
-  const size_t smem = sizeof(float) * p->Cout * p->C;
+  DV_REQUIRE(p->Cextra >= 0 && (p->Cextra == 0 || p->extra), DV_EINVAL, "dv_to_out: Cextra > 0 needs extra");
+  const size_t smem = sizeof(float) * p->Cout * (p->C + p->Cextra);
   cudaStream_t s = as_stream(stream);
 #define DV_TO_OUT(T, CO) to_out_kernel<T, CO><<<grid, 256, smem, s>>>(*p)
   if (p->dtype == DV_F32) { if (p->Cout == 3) DV_TO_OUT(float, 3); else DV_TO_OUT(float, 6); }

@@ -25,16 +25,27 @@ __global__ void gn_stats_kernel(dv_gn_stats_params p, int rows_per_block, int rp
   for (int i = threadIdx.x; i < p.groups * 2; i += blockDim.x) sred[i] = 0.0;
   __syncthreads();
   const T* x = reinterpret_cast<const T*>(p.x) + (int64_t)b * p.P * p.C;
-  float s1 = 0.f, s2 = 0.f;
+  float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
   for (int64_t r = r0 + rl; r < r1; r += rpi) {
     float v[4];
     load4(x + r * p.C + c4 * 4, v);
 #pragma unroll
-    for (int k = 0; k < 4; ++k) { s1 += v[k]; s2 += v[k] * v[k]; }
+    for (int k = 0; k < 4; ++k) { s1[k] += v[k]; s2[k] += v[k] * v[k]; }
   }
-  const int grp = (c4 * 4) / (p.C / p.groups);
-  atomicAdd(&sred[grp * 2 + 0], (double)s1);
-  atomicAdd(&sred[grp * 2 + 1], (double)s2);
+  const int cpg = p.C / p.groups;
+  if (cpg % 4 == 0) {
+    const int grp = (c4 * 4) / cpg;
+    atomicAdd(&sred[grp * 2 + 0], (double)((s1[0] + s1[1]) + (s1[2] + s1[3])));
+    atomicAdd(&sred[grp * 2 + 1], (double)((s2[0] + s2[1]) + (s2[2] + s2[3])));
+  } else {
+    // narrow groups (1, 2, 6 ... channels: the dim-8 / dim-16 super-resolution unets): the quad straddles groups
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int grp = (c4 * 4 + k) / cpg;
+      atomicAdd(&sred[grp * 2 + 0], (double)s1[k]);
+      atomicAdd(&sred[grp * 2 + 1], (double)s2[k]);
+    }
+  }
   __syncthreads();
   for (int i = threadIdx.x; i < p.groups * 2; i += blockDim.x)
     atomicAdd(&p.stats[(int64_t)b * p.groups * 2 + i], sred[i]);
@@ -211,8 +222,8 @@ extern "C" int dv_gn_stats(const dv_gn_stats_params* p, dv_stream_t stream) {
   DV_REQUIRE(p && p->x && p->stats, DV_EINVAL, "dv_gn_stats: null pointer");
   DV_REQUIRE(p->B > 0 && p->P > 0 && p->C > 0 && p->groups > 0 && p->C % p->groups == 0, DV_EINVAL,
              "dv_gn_stats: bad dimensions");
-  DV_REQUIRE((p->C / p->groups) % 4 == 0 && p->C <= 1024, DV_EUNSUPPORTED,
-             "dv_gn_stats: needs C/groups %% 4 == 0 and C <= 1024 (C=%d groups=%d)", p->C, p->groups);
+  DV_REQUIRE(p->C % 4 == 0 && p->C <= 1024, DV_EUNSUPPORTED,
+             "dv_gn_stats: needs C %% 4 == 0 and C <= 1024 (C=%d groups=%d)", p->C, p->groups);
   DV_REQUIRE(aligned16(p->x), DV_EALIGN, "dv_gn_stats: x must be 16-byte aligned");
   const int c4n = p->C / 4;
   int rpi = 256 / c4n;

@@ -21,7 +21,25 @@ __global__ void q_sample_kernel(dv_q_sample_params p) {
   const int b = (int)(i / p.per_sample);
   const int64_t t = p.times[b];
   const float x0 = p.normalize ? 2.0f * p.video[i] - 1.0f : p.video[i];
-  p.out[i] = p.sqrt_ac[t] * x0 + p.sqrt_1mac[t] * p.noise[i];
+  const float xt = p.sqrt_ac[t] * x0 + p.sqrt_1mac[t] * p.noise[i];
+  p.out[i] = p.unnormalize ? (xt + 1.0f) * 0.5f : xt;
+}
+
+// Per-frame nearest resize (F.interpolate(mode="nearest") index rule) + optional clamp; one thread per output pixel.
+__global__ void __launch_bounds__(256) resize_nearest_kernel(dv_resize_nearest_params p) {
+  const int64_t per = (int64_t)p.Hout * p.Wout;
+  const int64_t total = p.planes * per;
+  const float sh = (float)p.Hin / (float)p.Hout, sw = (float)p.Win / (float)p.Wout;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t pl = i / per;
+    const int r = (int)(i - pl * per);
+    const int oy = r / p.Wout, ox = r - oy * p.Wout;
+    const int iy = min((int)floorf((float)oy * sh), p.Hin - 1);
+    const int ix = min((int)floorf((float)ox * sw), p.Win - 1);
+    float v = p.in[(pl * p.Hin + iy) * p.Win + ix];
+    if (p.clamp) v = fminf(fmaxf(v, p.lo), p.hi);
+    p.out[i] = v;
+  }
 }
 
 __global__ void __launch_bounds__(256) mse_loss_kernel(dv_mse_loss_params p) {
@@ -178,6 +196,20 @@ extern "C" int dv_q_sample(const dv_q_sample_params* p, dv_stream_t stream) {
   DV_REQUIRE(p->n > 0 && p->per_sample > 0 && p->n % p->per_sample == 0, DV_EINVAL, "dv_q_sample: bad sizes");
   q_sample_kernel<<<(unsigned)((p->n + 255) / 256), 256, 0, as_stream(stream)>>>(*p);
   DV_CHECK_LAUNCH("dv_q_sample");
+  return DV_OK;
+}
+
+extern "C" int dv_resize_nearest(const dv_resize_nearest_params* p, dv_stream_t stream) {
+  using namespace dv;
+  DV_REQUIRE(p && p->in && p->out, DV_EINVAL, "dv_resize_nearest: null pointer");
+  DV_REQUIRE(p->planes > 0 && p->Hin > 0 && p->Win > 0 && p->Hout > 0 && p->Wout > 0, DV_EINVAL,
+             "dv_resize_nearest: bad sizes");
+  DV_REQUIRE(p->in != p->out, DV_EINVAL, "dv_resize_nearest: in place is not supported");
+  const int64_t total = p->planes * p->Hout * p->Wout;
+  int64_t blocks = (total + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  resize_nearest_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(*p);
+  DV_CHECK_LAUNCH("dv_resize_nearest");
   return DV_OK;
 }
 

@@ -47,6 +47,72 @@ def _pad_tuple(t, length, fill=None):
     return t if len(t) >= length else (*t, *((fill,) * (length - len(t))))
 
 
+def resize_video_to(video, target_frame_size, clamp_range=None):
+    """temporal_apply(resize_image_to, video, size, clamp_range=..., nearest=True) (:2090-2095, :2130-2136; the only mode
+    the cascade uses) through dv_resize_nearest.  Same-size input is returned as is, unclamped, like the reference."""
+    if video.shape[-1] == target_frame_size:
+        return video
+    if not video.is_cuda:
+        raise L.DvError("resize_video_to needs a CUDA tensor: there is no CPU path")
+    b, c, t, h, w = video.shape
+    src = video.contiguous().float()
+    out = torch.empty(b, c, t, target_frame_size, target_frame_size, device=video.device, dtype=torch.float32)
+    L.call("dv_resize_nearest", L.ResizeNearestParams(
+        in_=src.data_ptr(), out=out.data_ptr(), planes=b * c * t, Hin=h, Win=w, Hout=target_frame_size,
+        Wout=target_frame_size, clamp=int(clamp_range is not None), lo=float(clamp_range[0]) if clamp_range else 0.0,
+        hi=float(clamp_range[1]) if clamp_range else 0.0), torch.cuda.current_stream(video.device).cuda_stream)
+    return out.to(video.dtype)
+
+
+class LowresVideoConditioner:
+    """Reference: dalle2_video.py:1044-1166.  At sampling time only the per-frame nearest resize and the optional
+    Imagen-style noise augmentation are used (:2126-2147); both run as native kernels.  The training-time blur
+    (kornia gaussian_blur2d, random) is outside the accelerated path."""
+
+    def __init__(self, downsample_first=True, use_blur=True, blur_prob=0.5, blur_sigma=0.6, blur_kernel_size=3,
+                 use_noise=False, input_video_range=None, normalize_video=True):
+        self.downsample_first, self.input_video_range = downsample_first, input_video_range
+        self.use_blur, self.blur_prob, self.blur_sigma, self.blur_kernel_size = use_blur, blur_prob, blur_sigma, \
+            blur_kernel_size
+        self.use_noise = use_noise
+        self._normalize = normalize_video
+        self.noise_scheduler = NoiseScheduler(beta_schedule="linear", timesteps=1000, loss_type="l2") if use_noise \
+            else None
+
+    def noise_video(self, cond_fmap, noise_levels=None, noise=None):
+        """unnormalize(q_sample(normalize(cond_fmap), t, randn_like)) (:1075-1090) as one dv_q_sample launch."""
+        assert self.noise_scheduler is not None
+        dev = cond_fmap.device
+        if not cond_fmap.is_cuda:
+            raise L.DvError("LowresVideoConditioner.noise_video needs a CUDA tensor: there is no CPU path")
+        sched = self.noise_scheduler.to(dev)
+        batch = cond_fmap.shape[0]
+        if noise_levels is None:
+            noise_levels = sched.sample_random_times(batch)
+        noise = torch.randn_like(cond_fmap) if noise is None else noise
+        src, nz = cond_fmap.contiguous().float(), noise.contiguous().float()
+        out = torch.empty_like(src)
+        levels = noise_levels.to(device=dev, dtype=torch.int64).contiguous()
+        L.call("dv_q_sample", L.QSampleParams(
+            video=src.data_ptr(), noise=nz.data_ptr(), times=levels.data_ptr(),
+            sqrt_ac=sched.sqrt_alphas_cumprod.data_ptr(), sqrt_1mac=sched.sqrt_one_minus_alphas_cumprod.data_ptr(),
+            out=out.data_ptr(), n=src.numel(), per_sample=src.numel() // batch, normalize=int(self._normalize),
+            unnormalize=int(self._normalize)), torch.cuda.current_stream(dev).cuda_stream)
+        return out, noise_levels
+
+    def __call__(self, cond_fmap, *, target_frame_size, downsample_frame_size=None, should_blur=True, **kwargs):
+        if self.use_blur and should_blur:
+            raise NotImplementedError("the training-time blur augmentation (kornia gaussian_blur2d) is outside the "
+                                      "accelerated path")
+        if self.downsample_first and downsample_frame_size is not None:
+            cond_fmap = resize_video_to(cond_fmap, downsample_frame_size, clamp_range=self.input_video_range)
+        cond_fmap = resize_video_to(cond_fmap, target_frame_size, clamp_range=self.input_video_range)
+        levels = None
+        if self.use_noise:
+            cond_fmap, levels = self.noise_video(cond_fmap)
+        return cond_fmap, levels
+
+
 class VideoDecoder(nn.Module):
     def __init__(self, unet, *, clip=None, frame_size=None, channels=3, vae=tuple(), timesteps=1000,
                  sample_timesteps=None, video_cond_drop_prob=0.1, text_cond_drop_prob=0.5, loss_type="l2",
@@ -73,9 +139,18 @@ class VideoDecoder(nn.Module):
 
         unets = _cast_tuple(unet)
         self.num_unets = len(unets)
-        if self.num_unets != 1:
-            raise NotImplementedError("cascades (super-resolution unets with low-res conditioning) are the next "
-                                      "scope row (SURVEY.md §8f N2); this build accelerates the base decoder")
+        num_unets = self.num_unets
+        # low-resolution conditioning options per unet (reference :1309-1325)
+        as_tuple = lambda v: tuple(v) if isinstance(v, (tuple, list)) else (v,) * (num_unets - 1)  # noqa: E731
+        use_noise_for_lowres_cond = as_tuple(use_noise_for_lowres_cond)
+        use_blur_for_lowres_cond = as_tuple(use_blur_for_lowres_cond)
+        if len(use_noise_for_lowres_cond) < num_unets:
+            use_noise_for_lowres_cond = (False, *use_noise_for_lowres_cond)
+        if len(use_blur_for_lowres_cond) < num_unets:
+            use_blur_for_lowres_cond = (False, *use_blur_for_lowres_cond)
+        assert not use_noise_for_lowres_cond[0], "first unet will never need low res noise conditioning"
+        assert not use_blur_for_lowres_cond[0], "first unet will never need low res blur conditioning"
+        assert num_unets == 1 or all((n or b) for n, b in zip(use_noise_for_lowres_cond[1:], use_blur_for_lowres_cond[1:]))
         if len(_cast_tuple(vae)) > 0:
             raise NotImplementedError("latent diffusion (VQGanVAE) is outside the accelerated path")
         self.unconditional = unconditional
@@ -87,13 +162,14 @@ class VideoDecoder(nn.Module):
 
         self.unets = nn.ModuleList([])
         self.vaes = nn.ModuleList([])
-        for ind, (one_unet, one_vae, lv) in enumerate(zip(unets, vaes, learned_variance)):
+        for ind, (one_unet, one_vae, lv, lowres_noise_cond) in enumerate(zip(unets, vaes, learned_variance,
+                                                                            use_noise_for_lowres_cond)):
             assert isinstance(one_unet, Unet3D)
             is_first = ind == 0
             ch_out = one_vae.encoded_dim * (1 if not lv else 2)
             # same call as the reference (:1347-1355) — may re-instantiate the unet with fresh weights
             one_unet = one_unet.cast_model_parameters(
-                lowres_cond=not is_first, lowres_noise_cond=False,
+                lowres_cond=not is_first, lowres_noise_cond=lowres_noise_cond,
                 cond_on_image_embeds=not unconditional and is_first,
                 cond_on_text_encodings=not unconditional and one_unet.cond_on_text_encodings,
                 channels=one_vae.encoded_dim, channels_out=ch_out)
@@ -122,7 +198,17 @@ class VideoDecoder(nn.Module):
         self.predict_x_start = _cast_tuple(predict_x_start, len(unets))
         self.predict_v = _cast_tuple(predict_v, len(unets))
         self.input_video_range = (-1.0 if not auto_normalize_video else 0.0, 1.0)
-        self.lowres_conds = [None]
+        # cascading ddpm (reference :1435-1461)
+        lowres_conditions = tuple(u.lowres_cond for u in self.unets)
+        assert lowres_conditions == (False, *((True,) * (num_unets - 1))), \
+            "the first unet must be unconditioned (by low resolution image), and the rest of the unets must have " \
+            "`lowres_cond` set to True"
+        self.lowres_conds = [None if i == 0 else LowresVideoConditioner(
+            downsample_first=lowres_downsample_first, use_blur=ub, use_noise=un, blur_prob=blur_prob,
+            blur_sigma=blur_sigma, blur_kernel_size=blur_kernel_size, input_video_range=self.input_video_range,
+            normalize_video=auto_normalize_video)
+            for i, (un, ub) in enumerate(zip(use_noise_for_lowres_cond, use_blur_for_lowres_cond))]
+        self.lowres_noise_sample_level = lowres_noise_sample_level
         self.video_cond_drop_prob = video_cond_drop_prob
         self.text_cond_drop_prob = text_cond_drop_prob
         self.can_classifier_guidance = video_cond_drop_prob > 0.0 or text_cond_drop_prob > 0.0
@@ -158,10 +244,17 @@ class VideoDecoder(nn.Module):
                                       "(chunk on dim=2, SURVEY.md F5); construct with learned_variance=False")
         if predict_x_start or predict_v:
             raise NotImplementedError("only epsilon-prediction is accelerated")
-        if lowres_cond_vid is not None or lowres_noise_level is not None:
-            raise NotImplementedError("low-resolution conditioning is outside the accelerated path")
         if self.use_dynamic_thres:
             raise NotImplementedError("dynamic thresholding (quantile) is outside the accelerated path")
+
+    def _set_lowres(self, eng, unet, lowres_cond_vid, lowres_noise_level, is_latent_diffusion, rep):
+        """`lowres_cond_vid = maybe(self.normalize_video)(lowres_cond_vid)` (:1704-1705, :1808-1809), then into the plan's
+        conditioning planes (for both halves of a CFG batch: the reference passes it to the null forward too, :683-692)."""
+        assert not (unet.lowres_cond and lowres_cond_vid is None), "low resolution conditioning image must be present"
+        if lowres_cond_vid is not None and not is_latent_diffusion:
+            lowres_cond_vid = self.normalize_video(lowres_cond_vid)
+        eng.set_lowres(rep(lowres_cond_vid) if lowres_cond_vid is not None else None,
+                       rep(lowres_noise_level) if lowres_noise_level is not None else None)
 
     @torch.no_grad()
     def p_sample_loop_ddpm(self, unet, shape, video_embed, noise_scheduler, predict_x_start=False, predict_v=False,
@@ -190,6 +283,7 @@ class VideoDecoder(nn.Module):
         ones = torch.ones(b, dtype=torch.uint8, device=device)
         keep = torch.cat((ones, torch.zeros_like(ones))) if cfg else ones
         rep = (lambda t: torch.cat((t, t), dim=0)) if cfg else (lambda t: t)
+        self._set_lowres(eng, unet, lowres_cond_vid, lowres_noise_level, is_latent_diffusion, rep)
         eng.set_conditioning(rep(video_embed) if video_embed is not None else None,
                              rep(text_encodings) if use_text else None, keep, keep)
         eng.set_time_source(True)
@@ -302,6 +396,7 @@ class VideoDecoder(nn.Module):
         ones = torch.ones(b, dtype=torch.uint8, device=device)
         keep = torch.cat((ones, torch.zeros_like(ones))) if cfg else ones
         rep = (lambda t: torch.cat((t, t), dim=0)) if cfg else (lambda t: t)
+        self._set_lowres(eng, unet, lowres_cond_vid, lowres_noise_level, is_latent_diffusion, rep)
         eng.set_conditioning(rep(video_embed) if video_embed is not None else None,
                              rep(text_encodings) if use_text else None, keep, keep)
         eng.set_time_source(True)
@@ -389,7 +484,9 @@ class VideoDecoder(nn.Module):
         assert not (cond_scale != 1.0 and not self.can_classifier_guidance)
         if model_output is None:
             model_output = unet.forward_with_cond_scale(x, t, video_embed=video_embed, text_encodings=text_encodings,
-                                                        cond_scale=cond_scale, self_cond=self_cond)
+                                                        cond_scale=cond_scale, self_cond=self_cond,
+                                                        lowres_cond_video=lowres_cond_vid,
+                                                        lowres_noise_level=lowres_noise_level)
         x_start = noise_scheduler.predict_start_from_noise(x, t=t, noise=model_output)
         if clip_denoised:
             x_start = x_start.clamp(-1.0, 1.0)
@@ -404,7 +501,8 @@ class VideoDecoder(nn.Module):
         kernel when all samples share the timestep, else through the table gathers."""
         self._check_native(predict_x_start, predict_v, learned_variance, lowres_cond_vid, lowres_noise_level)
         eps = unet.forward_with_cond_scale(x, t, video_embed=video_embed, text_encodings=text_encodings,
-                                           cond_scale=cond_scale, self_cond=self_cond)
+                                           cond_scale=cond_scale, self_cond=self_cond,
+                                           lowres_cond_video=lowres_cond_vid, lowres_noise_level=lowres_noise_level)
         if noise is None:
             noise = torch.randn_like(x)
         t0 = int(t[0])
@@ -431,7 +529,9 @@ class VideoDecoder(nn.Module):
     def sample(self, video=None, video_embed=None, text=None, text_encodings=None, batch_size=1, cond_scale=1.0,
                start_at_unet_number=1, stop_at_unet_number=None, distributed=False, one_unet_in_gpu_at_time=True,
                cuda="cuda", **loop_kwargs):
-        """Reference: dalle2_video.py:2053-2186 (single base unet)."""
+        """Reference: dalle2_video.py:2053-2186: the cascade driver.  Each unet after the first is conditioned on the
+        previous stage's output, resized per frame (nearest) to its own resolution and optionally noised at
+        `lowres_noise_sample_level` (:2126-2147)."""
         assert self.unconditional or video_embed is not None, \
             "image embed must be present on sampling from decoder unless if trained unconditionally"
         if not self.unconditional:
@@ -441,21 +541,43 @@ class VideoDecoder(nn.Module):
             "text or text encodings must be passed into decoder if specified"
         assert not (not self.condition_on_text_encodings and text_encodings is not None), \
             "decoder specified not to be conditioned on text, yet it is presented"
-        assert start_at_unet_number == 1, "only the base unet is built"
         if self.frame_numbers is None:
             raise TypeError("frame_numbers must be given (the reference zips over it, SURVEY.md Q13)")
+        vid = None
+        if start_at_unet_number > 1:
+            assert video is not None, "image must be passed in if starting at unet number > 1"
+            assert video.shape[0] == batch_size, \
+                "image must have batch size of {} if starting at unet number > 1".format(batch_size)
+            vid = resize_video_to(video.to(self.device), self.frame_sizes[start_at_unet_number - 2])
+        cond_scale = _cast_tuple(cond_scale, self.num_unets)
         was_training = self.training
         self.eval()
         try:
-            unet, vae = self.unets[0], self.vaes[0]
-            sched = self.noise_schedulers[0]
-            frame_size = vae.get_encoded_fmap_size(self.frame_sizes[0])
-            shape = (batch_size, vae.encoded_dim, self.frame_numbers[0], frame_size, frame_size)
-            vid = self.p_sample_loop(unet, shape, video_embed=video_embed, text_encodings=text_encodings,
-                                     cond_scale=_cast_tuple(cond_scale, 1)[0], predict_x_start=self.predict_x_start[0],
-                                     predict_v=self.predict_v[0], learned_variance=self.learned_variance[0],
-                                     clip_denoised=True, noise_scheduler=sched, timesteps=self.sample_timesteps[0],
-                                     **loop_kwargs)
+            for (unet_number, unet, vae, channel, frame_size, frame_number, predict_x_start, predict_v, learned_variance,
+                 noise_scheduler, lowres_cond, sample_timesteps, unet_cond_scale) in zip(
+                    range(1, self.num_unets + 1), self.unets, self.vaes, self.sample_channels, self.frame_sizes,
+                    self.frame_numbers, self.predict_x_start, self.predict_v, self.learned_variance,
+                    self.noise_schedulers, self.lowres_conds, self.sample_timesteps, cond_scale):
+                if unet_number < start_at_unet_number:
+                    continue
+                lowres_cond_vid = lowres_noise_level = None
+                if unet.lowres_cond:
+                    lowres_cond_vid = resize_video_to(vid, frame_size, clamp_range=self.input_video_range)
+                    if lowres_cond.use_noise:
+                        lowres_noise_level = torch.full((batch_size,), int(self.lowres_noise_sample_level * 1000),
+                                                        dtype=torch.long, device=self.device)
+                        nf = loop_kwargs.get("noise_fn")   # parity hook: the augmentation draw comes first (:2145)
+                        aug = nf(tuple(lowres_cond_vid.shape), -1).to(self.device) if nf is not None else None
+                        lowres_cond_vid, _ = lowres_cond.noise_video(lowres_cond_vid, lowres_noise_level, noise=aug)
+                frame_size = vae.get_encoded_fmap_size(frame_size)
+                shape = (batch_size, vae.encoded_dim, frame_number, frame_size, frame_size)
+                vid = self.p_sample_loop(unet, shape, video_embed=video_embed, text_encodings=text_encodings,
+                                         cond_scale=unet_cond_scale, predict_x_start=predict_x_start,
+                                         predict_v=predict_v, learned_variance=learned_variance, clip_denoised=True,
+                                         lowres_cond_vid=lowres_cond_vid, lowres_noise_level=lowres_noise_level,
+                                         noise_scheduler=noise_scheduler, timesteps=sample_timesteps, **loop_kwargs)
+                if stop_at_unet_number is not None and stop_at_unet_number == unet_number:
+                    break
         finally:
             self.train(was_training)
         return vid

@@ -182,8 +182,7 @@ class Unet3D(nn.Module):
         unsupported = dict(sparse_attn=sparse_attn, cosine_sim_cross_attn=cosine_sim_cross_attn,
                            cosine_sim_self_attn=cosine_sim_self_attn, cross_embed_downsample=cross_embed_downsample,
                            memory_efficient=memory_efficient, combine_upsample_fmaps=combine_upsample_fmaps,
-                           resnet_weight_standardization=resnet_weight_standardization,
-                           lowres_noise_cond=lowres_noise_cond)
+                           resnet_weight_standardization=resnet_weight_standardization)
         bad = [k for k, v in unsupported.items() if v]
         if bad or not pixel_shuffle_upsample or final_conv_ksize != 1:
             raise NotImplementedError(f"Unet3D(b200): options outside the accelerated hot path: "
@@ -231,7 +230,10 @@ class Unet3D(nn.Module):
                 "text_embed_dim must be given to the unet if cond_on_text_encodings is True"
             self.text_to_cond = nn.Linear(text_embed_dim, cond_dim)
             self.text_embed_dim = text_embed_dim
-        self.to_lowres_noise_cond = None
+        # low-resolution noise-level conditioning (:391-402); index 0 / 2 are parameter-free (SinusoidalPosEmb, GELU)
+        self.to_lowres_noise_cond = (nn.Sequential(nn.Identity(), nn.Linear(dim, time_cond_dim), nn.GELU(),
+                                                   nn.Linear(time_cond_dim, time_cond_dim))
+                                     if lowres_noise_cond else None)
 
         self.cond_on_text_encodings = cond_on_text_encodings
         self.cond_on_video_embeds = cond_on_video_embeds
@@ -378,8 +380,14 @@ class Unet3D(nn.Module):
                 disable_checkpoint=False, self_cond=None):
         if not x.is_cuda:
             raise L.DvError("Unet3D(b200).forward needs CUDA tensors: there is no CPU path")
-        if self.lowres_cond or lowres_cond_video is not None or lowres_noise_level is not None:
-            raise NotImplementedError("low-resolution conditioning (cascade stage 2) is outside the accelerated path")
+        assert not (self.lowres_cond and lowres_cond_video is None), \
+            "low resolution conditioning image must be present"
+        if lowres_cond_video is not None and not self.lowres_cond:
+            raise L.DvError("lowres_cond_video was passed to a Unet3D built with lowres_cond=False (its init_conv / "
+                            "to_out have no channels for it)")
+        if lowres_noise_level is not None:
+            assert self.to_lowres_noise_cond is not None, \
+                "lowres_noise_cond must be set to True on instantiation of the unet in order to conditiong on lowres noise"
         b = x.shape[0]
         if self.self_cond:
             sc = self_cond if self_cond is not None else torch.zeros_like(x)
@@ -394,6 +402,7 @@ class Unet3D(nn.Module):
         eng = self.engine(b, x.shape[2], x.shape[3], x.shape[4], self._resolve_dtype(), x.device, n_text)
         keep_v = _prob_mask(b, 1 - video_cond_drop_prob, x.device)
         keep_t = _prob_mask(b, 1 - text_cond_drop_prob, x.device)
+        eng.set_lowres(lowres_cond_video, lowres_noise_level)
         eng.set_conditioning(video_embed, text_encodings if use_text else None, keep_v, keep_t)
         eng.x_in.copy_(x)
         eng.time_in.copy_(time)
@@ -468,6 +477,13 @@ class _Engine:
         u = unet
         cin = u.channels * (1 + int(u.self_cond))
         self.x_in = torch.zeros(B, cin, T, H, W, **f32)
+        # cascade stage >= 2 (:744-746): the init conv sees cat(x, lowres_cond_video).  The sampler state stays a
+        # contiguous (B,c,T,H,W) tensor; x_cat is refreshed from it every step, its lowres planes once per call.
+        self.lowres_in = torch.zeros(B, u.channels, T, H, W, **f32) if u.lowres_cond else None
+        self.x_cat = torch.zeros(B, cin + u.channels, T, H, W, **f32) if u.lowres_cond else None
+        self.cin = cin
+        self.lowres_level = torch.zeros(B, dtype=torch.int64, device=device)
+        self.use_lowres_noise = False
         self.time_in = torch.zeros(B, dtype=torch.int64, device=device)
         self.t_dev = torch.zeros(1, dtype=torch.int32, device=device)
         self.use_t_dev = False
@@ -484,6 +500,9 @@ class _Engine:
         t = t.detach().to(device=self.device, dtype=self.dtype).contiguous()
         self.keep.append(t)
         return t
+
+    def _x_src(self):
+        return self.x_cat if self.x_cat is not None else self.x_in
 
     def _zeros(self, *shape, dtype=torch.float32):
         t = torch.zeros(*shape, dtype=dtype, device=self.device)
@@ -521,7 +540,7 @@ class _Engine:
                          dtype=self.code if dtype_code is None else dtype_code, impl=self.impl)
         Ho, Wo = (H // 2, W // 2) if mode == L.CONV_UNSHUFFLE else (H, W)
         rows_per_sample = (frames or self.T) * Ho * Wo
-        separate_stats = stats is not None and rows_per_sample % 64 != 0
+        separate_stats = stats is not None and (rows_per_sample % 64 != 0 or (Cout // groups) % 4 != 0)
         if separate_stats:
             p.stats = None
         if L.lib().dv_conv_uses_tcgen05(p):
@@ -657,6 +676,23 @@ class _Engine:
         lin = u.to_time_tokens[0]
         self._linear(hid.data_ptr(), self._f32(lin.weight), self._f32(lin.bias), time_tok.data_ptr(), B, 1, nt * cond,
                      tcd, tcd, 0, nt * cond, 0)
+        # low-resolution noise-level embedding (:393-402, :765-768): step-invariant, so it is folded into the static part
+        # of t.  t_comb = to_lowres_noise_cond(level) + t_static, refreshed by set_conditioning.
+        self._lowres_noise_ops, self._t_static, self._t_comb = None, t_static, None
+        if u.to_lowres_noise_cond is not None:
+            sin2, hid2 = self._zeros(B, dim), self._zeros(B, tcd)
+            self._t_comb = self._zeros(B, tcd)
+            saved, self.static_ops = self.static_ops, []
+            self._op("dv_time_embed", L.TimeEmbedParams(time=self.lowres_level.data_ptr(), t_dev=None,
+                                                        freqs=freqs.data_ptr(), out=sin2.data_ptr(), B=B, dim=dim),
+                     static=True)
+            l1, l2 = u.to_lowres_noise_cond[1], u.to_lowres_noise_cond[3]
+            self._linear(sin2.data_ptr(), self._f32(l1.weight), self._f32(l1.bias), hid2.data_ptr(), B, 1, tcd, dim,
+                         dim, 0, tcd, 0, post=L.ACT_GELU, static=True)
+            self._linear(hid2.data_ptr(), self._f32(l2.weight), self._f32(l2.bias), self._t_comb.data_ptr(), B, 1, tcd,
+                         tcd, tcd, 0, tcd, 0, accum=t_static.data_ptr() if t_static is not None else None, static=True)
+            self._lowres_noise_ops, self.static_ops = self.static_ops, saved
+            t_static = self._t_comb
         lin = u.to_time_cond[0]
         self._linear(hid.data_ptr(), self._f32(lin.weight), self._f32(lin.bias), t_emb.data_ptr(), B, 1, tcd, tcd, tcd,
                      0, tcd, 0, accum=t_static.data_ptr() if t_static is not None else None)
@@ -681,13 +717,13 @@ class _Engine:
             coff = 0
             for conv, k in zip(u.init_conv.convs, u.init_conv.kernel_sizes):
                 co = conv.weight.shape[0]
-                self._conv([(self.x_in.data_ptr(), conv.weight.shape[1])], self._w(self._pack_conv(conv.weight)),
+                self._conv([(self._x_src().data_ptr(), conv.weight.shape[1])], self._w(self._pack_conv(conv.weight)),
                            self._f32(conv.bias), x0.ptr, co, n_img, H, W, k=k, mode=L.CONV_NCDHW_F32_IN,
                            out_ld=u.init_dim, out_coff=coff)
                 coff += co
         else:
             conv = u.init_conv
-            self._conv([(self.x_in.data_ptr(), conv.weight.shape[1])], self._w(self._pack_conv(conv.weight)),
+            self._conv([(self._x_src().data_ptr(), conv.weight.shape[1])], self._w(self._pack_conv(conv.weight)),
                        self._f32(conv.bias), x0.ptr, u.init_dim, n_img, H, W, k=conv.kernel_size[1],
                        mode=L.CONV_NCDHW_F32_IN)
         x0.refs += 1  # `r = x.clone()` (:751): kept for the head, never copied
@@ -763,7 +799,9 @@ class _Engine:
         wo = self._f32(u.to_out.weight.reshape(u.channels_out, -1))
         self._op("dv_to_out", L.ToOutParams(x=x.ptr, w=wo.data_ptr(), bias=self._f32(u.to_out.bias).data_ptr(),
                                             out=self.eps.data_ptr(), B=B, P=P, C=x.C, Cout=u.channels_out,
-                                            dtype=self.code))
+                                            dtype=self.code,
+                                            extra=self.lowres_in.data_ptr() if u.lowres_cond else None,
+                                            Cextra=u.channels if u.lowres_cond else 0))
         self.final_act = x  # kept alive
 
     def _init_conv_as_gemm(self, x0, n_img, H, W):
@@ -797,7 +835,7 @@ class _Engine:
             co0 += co
         wp = torch.zeros(u.init_dim, kpad)
         wp[:, :ktot] = wfull.reshape(u.init_dim, ktot)
-        fused = L.InitConvParams(x=self.x_in.data_ptr(), weight=None, bias=None, out=x0.ptr, B=self.B, C=cin, T=self.T, H=H,
+        fused = L.InitConvParams(x=self._x_src().data_ptr(), weight=None, bias=None, out=x0.ptr, B=self.B, C=cin, T=self.T, H=H,
                                  W=W, k=kmax, Kpad=kpad, Cout=u.init_dim, dtype=self.code)
         if self.u.fuse_init_conv and L.lib().dv_init_conv_supported(fused):
             # one kernel: the im2col tiles are built in shared memory and never reach HBM (include/dv_b200.h, "K4 fused")
@@ -807,7 +845,7 @@ class _Engine:
             self.n_tc += 1
             return True
         patches = self.pool.get(rows * kpad * self.esz)
-        self._op("dv_im2col_init", L.Im2colParams(x=self.x_in.data_ptr(), out=patches.data_ptr(), B=self.B, C=cin,
+        self._op("dv_im2col_init", L.Im2colParams(x=self._x_src().data_ptr(), out=patches.data_ptr(), B=self.B, C=cin,
                                                   T=self.T, H=H, W=W, k=kmax, Kpad=kpad, dtype=self.code, layout=1))
         self._conv([(patches.data_ptr(), kpad)], self._w(wp), self._f32(torch.cat(bfull)), x0.ptr, u.init_dim, rows,
                    1, 1, frames=self.T * H * W)
@@ -1011,6 +1049,28 @@ class _Engine:
         stream = torch.cuda.current_stream(self.device).cuda_stream
         for name, p in self.static_ops:
             L.call(name, p, stream)
+        if self.use_lowres_noise:
+            for name, p in self._lowres_noise_ops:   # t += to_lowres_noise_cond(level) (:765-768), step-invariant
+                L.call(name, p, stream)
+        elif self._t_comb is not None:
+            if self._t_static is not None:
+                self._t_comb.copy_(self._t_static)
+            else:
+                self._t_comb.zero_()
+
+    def set_lowres(self, lowres_cond_video, lowres_noise_level=None):
+        """Cascade stage >= 2: the low-resolution conditioning video (already at this unet's resolution) and, for a
+        lowres_noise_cond unet, its augmentation noise level (:744-746, :765-768, :949-950).  Call before
+        set_conditioning (the noise-level embedding is one of the static conditioning ops)."""
+        if self.lowres_in is not None:
+            assert lowres_cond_video is not None, "low resolution conditioning image must be present"
+            self.lowres_in.copy_(lowres_cond_video)
+            self.x_cat[:, self.cin:].copy_(self.lowres_in)
+        self.use_lowres_noise = lowres_noise_level is not None
+        if self.use_lowres_noise:
+            if self._lowres_noise_ops is None:
+                raise L.DvError("lowres_noise_level was passed to a Unet3D built with lowres_noise_cond=False")
+            self.lowres_level.copy_(lowres_noise_level)
 
     def set_time_source(self, use_t_dev: bool):
         """Per-sample int64 `time_in` (Unet3D.forward) or the device step counter `t_dev` (sampler graph)."""
@@ -1021,6 +1081,8 @@ class _Engine:
         """Enqueue one forward on the current stream: eps <- Unet3D(x_in, time)."""
         stream = torch.cuda.current_stream(self.device).cuda_stream
         self.stats.zero_()
+        if self.x_cat is not None:
+            self.x_cat[:, : self.cin].copy_(self.x_in)
         for name, p in self.ops:
             L.call(name, p, stream)
 

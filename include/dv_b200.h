@@ -419,8 +419,28 @@ typedef struct {
   int64_t P;
   int C, Cout;
   dv_dtype dtype;
+  /* Cascade stage >= 2 (:949-952): the head sees cat(x, lowres_cond_video).  extra: float32 (B,Cextra,T,H,W) planes
+   * [B][Cextra][P] (the low-resolution conditioning video as the caller holds it) or NULL; w is then [Cout][C + Cextra]. */
+  const float* extra;
+  int Cextra;
 } dv_to_out_params;
 int dv_to_out(const dv_to_out_params* p, dv_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Per-frame nearest-neighbour resize of a float32 (B,C,T,H,W) video, the only mode the cascade uses:
+ * temporal_apply(resize_image_to, vid, size, clamp_range=..., nearest=True)  (:2090-2095, :2130-2136; resize_image_to is
+ * dalle2_pytorch 1.14.2 = F.interpolate(mode="nearest") then clamp).  Source index = min(floor(dst * (in/out)), in-1)
+ * with the ratio in float32, as ATen computes it.  planes = B*C*T.
+ */
+typedef struct {
+  const float* in;   /* [planes][Hin][Win]  */
+  float* out;        /* [planes][Hout][Wout] */
+  int64_t planes;
+  int Hin, Win, Hout, Wout;
+  int clamp;         /* 0: none; 1: clamp to [lo, hi] */
+  float lo, hi;
+} dv_resize_nearest_params;
+int dv_resize_nearest(const dv_resize_nearest_params* p, dv_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * K4 fused: CrossEmbedLayer3D (dalle2_video/dalle2_video.py:208-244, built :320-327) as ONE tcgen05 kernel: the
@@ -544,6 +564,7 @@ typedef struct {
   const float* sqrt_ac; const float* sqrt_1mac; float* out;
   int64_t n, per_sample;
   int normalize;
+  int unnormalize;   /* 1: out = (x_t + 1) / 2 — LowresVideoConditioner.noise_video (:1075-1090) */
 } dv_q_sample_params;
 int dv_q_sample(const dv_q_sample_params* p, dv_stream_t stream);
 

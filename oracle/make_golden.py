@@ -109,5 +109,66 @@ def main():
     print("sample text cfg", tuple(vid.shape), float(vid.mean()))
 
 
+CASCADE_U1 = dict(dim=32, video_embed_dim=512, dim_mults=(1, 2), cond_on_video_embeds=True)
+CASCADE_U2 = dict(dim=16, video_embed_dim=512, dim_mults=(1, 2), cond_on_video_embeds=True)
+
+
+def cascade():
+    """Scope row N2 (cascade stage 2): `python -m oracle.make_golden cascade`.  Adds the two-unet fixtures without
+    touching the others: a forward of a lowres_cond + lowres_noise_cond Unet3D, and VideoDecoder.sample over a
+    (16 -> 32 px) cascade with and without the Imagen-style noise augmentation of the conditioning video."""
+    ref = reference.load()
+    with open(os.path.join(GOLDEN, "state_dict_layouts.json")) as f:
+        layouts = json.load(f)
+
+    # forward fixture: x ++ lowres video into the init conv, noise-level embedding added to t, lowres video into to_out
+    kw = dict(CASCADE_U2, lowres_cond=True, lowres_noise_cond=True)
+    torch.manual_seed(0)
+    unet = ref.Unet3D(**kw).eval()
+    layouts["cascade_u2_noise"] = shapes_of(unet)
+    unet.load_state_dict(synth_state_dict(layouts["cascade_u2_noise"], seed=9), strict=True)
+    g = torch.Generator().manual_seed(41)
+    x = torch.randn(2, 3, 4, 32, 32, generator=g)
+    low = torch.rand(2, 3, 4, 32, 32, generator=g) * 2 - 1
+    emb = torch.randn(2, 512, generator=g)
+    t = torch.tensor([3, 17])
+    level = torch.tensor([200, 200])
+    with torch.no_grad():
+        eps = unet(x, t, video_embed=emb, lowres_cond_video=low, lowres_noise_level=level)
+    torch.save({"x": x, "lowres_cond_video": low, "video_embed": emb, "times": t, "lowres_noise_level": level,
+                "eps": eps, "unet_kwargs": kw, "weight_seed": 9}, os.path.join(GOLDEN, "unet3d_lowres.pt"))
+    print("forward lowres", tuple(eps.shape), float(eps.abs().mean()))
+    layouts["cascade_u2"] = shapes_of(ref.Unet3D(**dict(CASCADE_U2, lowres_cond=True)))
+
+    for use_noise in (False, True):
+        torch.manual_seed(0)
+        u1, u2 = ref.Unet3D(**CASCADE_U1), ref.Unet3D(**CASCADE_U2)
+        dec = ref.VideoDecoder((u1, u2), frame_sizes=(16, 32), frame_numbers=(4, 4), timesteps=50,
+                               learned_variance=False, use_noise_for_lowres_cond=use_noise)
+        assert dec.unets[1].lowres_cond and dec.unets[1].lowres_noise_cond == use_noise
+        dec.unets[0].load_state_dict(synth_state_dict(layouts["tiny"], seed=7), strict=True)
+        key = "cascade_u2_noise" if use_noise else "cascade_u2"
+        assert shapes_of(dec.unets[1]) == layouts[key]
+        dec.unets[1].load_state_dict(synth_state_dict(layouts[key], seed=9), strict=True)
+        emb = torch.randn(2, 512, generator=torch.Generator().manual_seed(51))
+        torch.manual_seed(777)
+        stage1 = dec.sample(video_embed=emb, stop_at_unet_number=1, one_unet_in_gpu_at_time=False)
+        torch.manual_seed(777)
+        vid = dec.sample(video_embed=emb, one_unet_in_gpu_at_time=False)
+        assert bool(torch.isfinite(vid).all())
+        torch.save({"video_embed": emb, "sample": vid, "stage1": stage1, "timesteps": 50, "sample_seed": 777,
+                    "weight_seeds": (7, 9), "use_noise": use_noise, "frame_sizes": (16, 32), "frames": 4,
+                    "unet_kwargs": (CASCADE_U1, CASCADE_U2)},
+                   os.path.join(GOLDEN, f"sample_cascade_{'noise' if use_noise else 'plain'}.pt"))
+        print("cascade", use_noise, tuple(vid.shape), float(vid.mean()), float(stage1.mean()))
+
+    with open(os.path.join(GOLDEN, "state_dict_layouts.json"), "w") as f:
+        json.dump(layouts, f, indent=0, sort_keys=True)
+
+
 if __name__ == "__main__":
-    main()
+    import sys
+    if len(sys.argv) > 1 and sys.argv[1] == "cascade":
+        cascade()
+    else:
+        main()

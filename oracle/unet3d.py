@@ -42,6 +42,7 @@ class UnetConfig:
     attn_dim_head: int = 32
     attn_heads: int = 16
     lowres_cond: bool = False
+    lowres_noise_cond: bool = False
     self_cond: bool = False
     attend_at_middle: bool = True
     cond_on_text_encodings: bool = False
@@ -220,7 +221,8 @@ def _pixel_shuffle_up(sd, p, x):
 
 # ----------------------------------------------------------------------------- the denoiser
 def unet3d_forward(sd, cfg: UnetConfig, x, time, *, video_embed=None, text_encodings=None,
-                   lowres_cond_video=None, self_cond=None, drop_video=False, drop_text=False):
+                   lowres_cond_video=None, lowres_noise_level=None, self_cond=None, drop_video=False,
+                   drop_text=False):
     """Unet3D.forward with drop probabilities restricted to {0,1} (``drop_*`` booleans), which is all the
     sampling path uses (dalle2_video.py:683-692); no RNG is consumed (prob_mask_like p∈{0,1})."""
     b = x.shape[0]
@@ -256,6 +258,12 @@ def unet3d_forward(sd, cfg: UnetConfig, x, time, *, video_embed=None, text_encod
     time_tokens = F.linear(hid, sd["to_time_tokens.0.weight"], sd["to_time_tokens.0.bias"]).reshape(
         b, cfg.num_time_tokens, cond_dim)
     t = F.linear(hid, sd["to_time_cond.0.weight"], sd["to_time_cond.0.bias"])
+
+    # low-resolution noise-level conditioning (:765-768; module :393-402)
+    if lowres_noise_level is not None:
+        lv = lowres_noise_level.type_as(x)
+        h2 = F.gelu(F.linear(_sinusoidal(lv, dim), sd["to_lowres_noise_cond.1.weight"], sd["to_lowres_noise_cond.1.bias"]))
+        t = t + F.linear(h2, sd["to_lowres_noise_cond.3.weight"], sd["to_lowres_noise_cond.3.bias"])
 
     keep_v = torch.full((b,), not drop_video, dtype=torch.bool, device=x.device)
     keep_t = torch.full((b, 1, 1), not drop_text, dtype=torch.bool, device=x.device)
@@ -373,18 +381,56 @@ def ddpm_posterior_step(sched: NoiseScheduler, x, t_int: int, pred_noise, noise,
 
 
 def p_sample_loop_ddpm(sd, cfg, sched: NoiseScheduler, shape, *, video_embed, text_encodings=None,
-                       cond_scale=1.0, generator=None, clip_denoised=True, record=None):
-    """dalle2_video.py:1666-1755.  RNG contract: one randn(shape) then one randn per step (also at t=0)."""
+                       cond_scale=1.0, generator=None, clip_denoised=True, record=None, lowres_cond_vid=None,
+                       lowres_noise_level=None):
+    """dalle2_video.py:1666-1755.  RNG contract: one randn(shape) then one randn per step (also at t=0).
+    `lowres_cond_vid` arrives in [0,1] and is normalised here (:1704-1705)."""
     vid = torch.randn(shape, generator=generator)
+    kw = {}
+    if lowres_cond_vid is not None:
+        kw = dict(lowres_cond_video=lowres_cond_vid * 2 - 1, lowres_noise_level=lowres_noise_level)
     for t_int in reversed(range(sched.num_timesteps)):
         times = torch.full((shape[0],), t_int, dtype=torch.long)
         eps = forward_with_cond_scale(sd, cfg, vid, times, video_embed=video_embed,
-                                      text_encodings=text_encodings, cond_scale=cond_scale)
+                                      text_encodings=text_encodings, cond_scale=cond_scale, **kw)
         noise = torch.randn(shape, generator=generator)
         vid, _ = ddpm_posterior_step(sched, vid, t_int, eps, noise, clip_denoised)
         if record is not None:
             record(t_int, eps, vid)
     return (vid + 1) * 0.5
+
+
+def resize_nearest(video, size, clamp_range=None):
+    """temporal_apply(resize_image_to, video, size, clamp_range=, nearest=True) (:2090-2095, :2130-2136): per-frame
+    F.interpolate(mode="nearest"); a same-size input is returned as is (no clamp), as upstream resize_image_to does."""
+    if video.shape[-1] == size:
+        return video
+    b, c, t, h, w = video.shape
+    out = F.interpolate(video.transpose(1, 2).reshape(b * t, c, h, w), size, mode="nearest")
+    out = out.reshape(b, t, c, size, size).transpose(1, 2)
+    return out.clamp(*clamp_range) if clamp_range is not None else out
+
+
+def sample_cascade(sds, cfgs, scheds, frame_sizes, frame_number, *, video_embed, generator=None, noise_sched=None,
+                   lowres_noise_sample_level=0.2, use_noise=None, input_video_range=(0.0, 1.0)):
+    """VideoDecoder.sample over a cascade (dalle2_video.py:2053-2186) for pixel-space unets with auto-normalisation:
+    stage k > 1 is conditioned on stage k-1's [0,1] output resized to its resolution and, when `use_noise[k]`, noised
+    at level int(lowres_noise_sample_level * 1000) of a 1000-step linear schedule (:1075-1090, :2138-2147).
+    RNG order: per stage [randn_like(lowres) if noised], randn(shape), one randn per step."""
+    b = video_embed.shape[0]
+    vid = None
+    use_noise = use_noise or [False] * len(sds)
+    for k, (sd, cfg, sched, size) in enumerate(zip(sds, cfgs, scheds, frame_sizes)):
+        low = level = None
+        if cfg.lowres_cond:
+            low = resize_nearest(vid, size, clamp_range=input_video_range)
+            if use_noise[k]:
+                level = torch.full((b,), int(lowres_noise_sample_level * 1000), dtype=torch.long)
+                noise = torch.randn(low.shape, generator=generator)
+                low = (noise_sched.q_sample(low * 2 - 1, t=level, noise=noise) + 1) * 0.5
+        vid = p_sample_loop_ddpm(sd, cfg, sched, (b, 3, frame_number, size, size), video_embed=video_embed,
+                                 generator=generator, lowres_cond_vid=low, lowres_noise_level=level)
+    return vid
 
 
 def ddim_time_pairs(total_timesteps, timesteps):

@@ -186,7 +186,8 @@ def test_conv_rejects_bad_arguments():
 
 # ------------------------------------------------------------------ K2
 @pytest.mark.parametrize("dtype", DT)
-@pytest.mark.parametrize("C,G,with_ss,with_res", [(32, 8, True, False), (96, 8, False, True), (64, 8, True, True)])
+@pytest.mark.parametrize("C,G,with_ss,with_res", [(32, 8, True, False), (96, 8, False, True), (64, 8, True, True),
+                                                  (8, 8, True, True), (16, 8, True, False), (48, 8, False, True)])
 def test_groupnorm_stats_apply(dtype, C, G, with_ss, with_res):
     B, T, H, W = 2, 3, 8, 8
     P = T * H * W

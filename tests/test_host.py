@@ -83,8 +83,17 @@ def test_decoder_construction_and_quirks():
     assert d.can_classifier_guidance
     with pytest.raises(AssertionError):
         d.sample(video_embed=torch.zeros(1, 512), text_encodings=torch.zeros(1, 4, 64))
-    with pytest.raises(NotImplementedError):
-        VideoDecoder((u, u), frame_sizes=(32, 64), frame_numbers=(8, 8))
+    # cascades (scope row N2): the second unet is re-instantiated with lowres conditioning (:1347-1355), schedules are
+    # cosine then linear (:1376-1383), one LowresVideoConditioner per super-resolution unet (:1438-1459)
+    c = VideoDecoder((u, Unet3D(**dict(CASES["tiny"], dim=16))), frame_sizes=(32, 64), frame_numbers=(8, 8), timesteps=50,
+                     learned_variance=False, use_noise_for_lowres_cond=True)
+    assert c.unets[0] is u and c.unets[1].lowres_cond and c.unets[1].lowres_noise_cond
+    assert c.unets[1].init_conv.convs[0].weight.shape[1] == 6 and c.unets[1].to_out.weight.shape[1] == 16 + 3
+    assert "to_lowres_noise_cond.3.weight" in c.unets[1].state_dict()
+    assert c.lowres_conds[0] is None and c.lowres_conds[1].use_noise
+    assert torch.allclose(c.noise_schedulers[1].betas[-1], torch.tensor(0.02 * 1000 / 50, dtype=torch.float32))
+    with pytest.raises(AssertionError):
+        VideoDecoder((u, u), frame_sizes=(32, 64), frame_numbers=(8, 8), use_blur_for_lowres_cond=False)
     # strided (DDIM) sampling dispatches to the native loop, which — like every product path — refuses to run on CPU
     from dalle2_video_b200._lib import DvError
     with pytest.raises(DvError):

@@ -7,7 +7,8 @@ import torch
 
 from conftest import golden
 from oracle import primitives as P
-from oracle.unet3d import UnetConfig, ddpm_coefficients, forward_with_cond_scale, p_sample_loop_ddpm
+from oracle.unet3d import (UnetConfig, ddpm_coefficients, forward_with_cond_scale, p_sample_loop_ddpm, resize_nearest,
+                           sample_cascade, unet3d_forward)
 from oracle.weights import synth_state_dict
 
 
@@ -46,6 +47,44 @@ def test_text_cfg_sampler_matches_reference_fixture(layouts):
         vid = p_sample_loop_ddpm(sd, cfg, sched, tuple(g["sample"].shape), video_embed=g["video_embed"],
                                  text_encodings=g["text_encodings"], cond_scale=g["cond_scale"])
     assert float((vid - g["sample"]).abs().max()) < 1e-3
+
+
+def test_lowres_conditioned_forward_matches_reference_fixture(layouts):
+    # scope row N2: lowres video into init conv and to_out, noise-level embedding into t (:744-746, :765-768, :949-950)
+    g = golden("unet3d_lowres.pt")
+    sd = synth_state_dict(layouts["cascade_u2_noise"], seed=g["weight_seed"])
+    with torch.no_grad():
+        out = unet3d_forward(sd, UnetConfig(**g["unet_kwargs"]), g["x"], g["times"], video_embed=g["video_embed"],
+                             lowres_cond_video=g["lowres_cond_video"], lowres_noise_level=g["lowres_noise_level"])
+    rel = float((out - g["eps"]).norm() / g["eps"].norm())
+    assert rel < 1e-5, rel
+
+
+@pytest.mark.parametrize("kind", ["plain", "noise"])
+def test_cascade_sampler_matches_reference_fixture(kind, layouts):
+    g = golden(f"sample_cascade_{kind}.pt")
+    k1, k2 = g["unet_kwargs"]
+    use_noise = g["use_noise"]
+    cfgs = [UnetConfig(**k1), UnetConfig(**dict(k2, lowres_cond=True, lowres_noise_cond=use_noise))]
+    sds = [synth_state_dict(layouts["tiny"], seed=g["weight_seeds"][0]),
+           synth_state_dict(layouts["cascade_u2_noise" if use_noise else "cascade_u2"], seed=g["weight_seeds"][1])]
+    # beta schedules of a 2-unet decoder: cosine, linear (:1376-1383)
+    scheds = [P.NoiseScheduler(beta_schedule=s, timesteps=g["timesteps"], loss_type="l2") for s in ("cosine", "linear")]
+    aug = P.NoiseScheduler(beta_schedule="linear", timesteps=1000, loss_type="l2")
+    torch.manual_seed(g["sample_seed"])
+    with torch.no_grad():
+        vid = sample_cascade(sds, cfgs, scheds, g["frame_sizes"], g["frames"], video_embed=g["video_embed"],
+                             noise_sched=aug, use_noise=[False, use_noise])
+    assert vid.shape == g["sample"].shape
+    assert float((vid - g["sample"]).abs().max()) < 1e-3
+
+
+def test_resize_nearest_is_per_frame_interpolate():
+    v = torch.rand(2, 3, 4, 16, 16) * 1.5 - 0.25
+    up = resize_nearest(v, 32, clamp_range=(0.0, 1.0))
+    assert up.shape == (2, 3, 4, 32, 32)
+    assert torch.equal(up[..., ::2, ::2], v.clamp(0, 1)) and torch.equal(up[..., 1::2, 1::2], v.clamp(0, 1))
+    assert resize_nearest(v, 16, clamp_range=(0.0, 1.0)) is v   # same size: returned unclamped, as upstream
 
 
 def test_schedule_tables_match_reference_fixture():
