@@ -124,7 +124,7 @@ f64p = vp
 
 class ConvWgradParams(C.Structure):
     _fields_ = [("src0", vp), ("src1", vp), ("dy", vp), ("dw", vp), ("n_img", i32), ("H", i32), ("W", i32), ("C0", i32),
-                ("C1", i32), ("Cout", i32), ("kh", i32), ("kw", i32), ("mode", i32), ("dtype", i32)]
+                ("C1", i32), ("Cout", i32), ("kh", i32), ("kw", i32), ("mode", i32), ("dtype", i32), ("impl", i32)]
 
 
 class ColsumParams(C.Structure):
@@ -209,7 +209,7 @@ ENTRY_POINTS = {
     "dv_add": AddParams, "dv_cast_f32_bf16": CastParams, "dv_sumsq": SumsqParams, "dv_adamw": AdamwParams,
 }
 PLAIN_SYMBOLS = ("dv_version", "dv_last_error_string", "dv_device_sm_count", "dv_conv_uses_tcgen05",
-                 "dv_attn_mqa_workspace_bytes", "dv_xattn_core_workspace_bytes", "dv_attn_temporal_uses_mma", "dv_attn_mqa_bwd_workspace_bytes", "dv_init_conv_supported")
+                 "dv_attn_mqa_workspace_bytes", "dv_xattn_core_workspace_bytes", "dv_conv_wgrad_uses_tcgen05", "dv_attn_temporal_uses_mma", "dv_attn_mqa_bwd_workspace_bytes", "dv_init_conv_supported")
 
 _lib = None
 _SYNC_EACH = bool(os.environ.get("DV_SYNC_EACH"))
@@ -243,6 +243,8 @@ def lib():
         _lib.dv_conv_uses_tcgen05.restype = i32
         _lib.dv_attn_mqa_workspace_bytes.argtypes = [C.POINTER(AttnMqaParams)]
         _lib.dv_attn_mqa_workspace_bytes.restype = i64
+        _lib.dv_conv_wgrad_uses_tcgen05.argtypes = [C.POINTER(ConvWgradParams)]
+        _lib.dv_conv_wgrad_uses_tcgen05.restype = i32
         _lib.dv_xattn_core_workspace_bytes.argtypes = [C.POINTER(XattnParams)]
         _lib.dv_xattn_core_workspace_bytes.restype = i64
         _lib.dv_attn_temporal_uses_mma.argtypes = [C.POINTER(AttnTemporalParams)]

@@ -177,7 +177,14 @@ __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ x, fl
   for (int c = threadIdx.x; c < C; c += blockDim.x) atomicAdd(out + c, part[c]);
 }
 
+int wgrad_tc_supported(const dv_conv_wgrad_params& p);
+int wgrad_tc_launch(const dv_conv_wgrad_params& p, cudaStream_t s);
+
 }  // namespace dv
+
+extern "C" int dv_conv_wgrad_uses_tcgen05(const dv_conv_wgrad_params* p) {
+  return p && p->impl != 1 && dv::wgrad_tc_supported(*p) ? 1 : 0;
+}
 
 extern "C" int dv_conv_wgrad(const dv_conv_wgrad_params* p, dv_stream_t stream) {
   using namespace dv;
@@ -188,6 +195,11 @@ extern "C" int dv_conv_wgrad(const dv_conv_wgrad_params* p, dv_stream_t stream) 
   DV_REQUIRE(p->dtype == DV_BF16, DV_EUNSUPPORTED, "dv_conv_wgrad: bf16 activations only");
   DV_REQUIRE(p->C0 % 8 == 0 && p->C1 % 8 == 0 && p->Cout % 8 == 0, DV_EALIGN, "dv_conv_wgrad: channel counts must be multiples of 8");
   DV_REQUIRE(aligned16(p->src0) && aligned16(p->src1) && aligned16(p->dy), DV_EALIGN, "dv_conv_wgrad: pointers must be 16-byte aligned");
+  {
+    const bool tc_ok = wgrad_tc_supported(*p) != 0;
+    if (p->impl == 2) DV_REQUIRE(tc_ok, DV_EUNSUPPORTED, "dv_conv_wgrad: the tcgen05 kernel does not take these parameters");
+    if (tc_ok && p->impl != 1) return wgrad_tc_launch(*p, as_stream(stream));
+  }
   int Ho = p->H, Wo = p->W, taps;
   if (p->mode == DV_CONV_UNSHUFFLE) {
     DV_REQUIRE(p->H % 2 == 0 && p->W % 2 == 0 && p->C1 == 0, DV_EINVAL, "dv_conv_wgrad: unshuffle needs even H, W and one source");

@@ -485,8 +485,11 @@ typedef struct {
   int kh, kw;
   int mode;          /* DV_CONV_NORMAL or DV_CONV_UNSHUFFLE */
   dv_dtype dtype;    /* DV_BF16 */
+  int impl;          /* 0: auto (tcgen05 when the shape fits: channels % 64, 64-position TMA boxes); 1: the mma.sync
+                        kernel; 2: tcgen05 or DV_EUNSUPPORTED */
 } dv_conv_wgrad_params;
 int dv_conv_wgrad(const dv_conv_wgrad_params* p, dv_stream_t stream);
+int dv_conv_wgrad_uses_tcgen05(const dv_conv_wgrad_params* p);
 
 /* out[c] += sum_rows x[row][c]  (bias gradients) */
 typedef struct {

@@ -50,6 +50,53 @@ def test_conv_wgrad_matches_autograd(B, T, H, W, C0, C1, Co, k):
     assert rel_err(db, dy.float().sum(0)) < 1e-4
 
 
+@pytest.mark.parametrize("n_img,H,W,C0,C1,Co,k", [
+    (4, 16, 16, 64, 0, 64, 3),        # 9 X blocks (odd): 5 pairs in 2 groups, one padded half
+    (4, 8, 8, 128, 64, 128, 3),       # two sources, 27 blocks
+    (4, 8, 8, 64, 0, 192, 1),         # N = 192, a single (padded) pair
+    (2, 64, 64, 64, 64, 64, 3),       # 64-wide rows: one image row per stage
+    (3, 128, 128, 64, 0, 64, 3),      # rows wider than a stage (two boxes per row)
+    (8, 8, 8, 512, 256, 512, 3),      # Cout > 256: two N chunks
+    (16, 4, 4, 64, 0, 128, 3),        # images smaller than a stage: 4 images per box
+    (512, 1, 1, 128, 0, 256, 1),      # linear layer (to_q / to_out of the attention blocks)
+    (2, 32, 32, 128, 64, 128, 3),
+])
+def test_conv_wgrad_tcgen05_matches_autograd(n_img, H, W, C0, C1, Co, k):
+    """The tcgen05 weight-gradient kernel (MN-major UMMA operands straight from channels-last TMA boxes) against torch
+    autograd and against the mma.sync kernel on the same inputs."""
+    rows = n_img * H * W
+    x0 = rnd(rows, C0, dtype=torch.bfloat16, seed=1)
+    x1 = rnd(rows, C1, dtype=torch.bfloat16, seed=2) if C1 else None
+    dy = rnd(rows, Co, dtype=torch.bfloat16, seed=3)
+    out = {}
+    for impl in (2, 1):
+        dw = torch.zeros(Co, k * k * (C0 + C1), device=dev())
+        p = L.ConvWgradParams(src0=ptr(x0), src1=ptr(x1), dy=ptr(dy), dw=ptr(dw), n_img=n_img, H=H, W=W, C0=C0, C1=C1,
+                              Cout=Co, kh=k, kw=k, mode=L.CONV_NORMAL, dtype=L.DV_BF16, impl=impl)
+        assert L.lib().dv_conv_wgrad_uses_tcgen05(p) == (1 if impl == 2 else 0)
+        L.call("dv_conv_wgrad", p, stream())
+        out[impl] = dw
+    xin = x0 if x1 is None else torch.cat((x0, x1), dim=1)
+    xin = xin.float().reshape(n_img, H, W, -1).permute(0, 3, 1, 2)
+    w = torch.zeros(Co, C0 + C1, k, k, device=dev(), requires_grad=True)
+    y = F.conv2d(xin, w, padding=k // 2)
+    y.backward(dy.float().reshape(n_img, H, W, Co).permute(0, 3, 1, 2))
+    ref = w.grad.permute(0, 2, 3, 1).reshape(Co, -1)  # K order [tap][cin]
+    assert rel_err(out[2], ref) < 2e-3, rel_err(out[2], ref)
+    assert rel_err(out[2], out[1]) < 2e-3
+
+
+def test_conv_wgrad_tcgen05_contract():
+    x = rnd(64 * 8 * 8, 32, dtype=torch.bfloat16, seed=1)
+    dy = rnd(64 * 8 * 8, 64, dtype=torch.bfloat16, seed=2)
+    dw = torch.zeros(64, 9 * 32, device=dev())
+    p = L.ConvWgradParams(src0=ptr(x), src1=None, dy=ptr(dy), dw=ptr(dw), n_img=64, H=8, W=8, C0=32, C1=0, Cout=64, kh=3,
+                          kw=3, mode=L.CONV_NORMAL, dtype=L.DV_BF16, impl=2)
+    assert L.lib().dv_conv_wgrad_uses_tcgen05(p) == 0      # 32 input channels: not a 64-channel box
+    with pytest.raises(L.DvError):
+        L.call("dv_conv_wgrad", p, stream())
+
+
 def test_conv_wgrad_unshuffle_matches_autograd():
     n_img, H, W, C, Co = 4, 16, 16, 64, 128
     x = rnd(n_img * H * W, C, dtype=torch.bfloat16, seed=1)
