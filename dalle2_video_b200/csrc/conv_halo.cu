@@ -40,6 +40,7 @@ struct HaloParams {
   int total_tiles;
   uint32_t wp_magic;  // (off * wp_magic) >> 16 == off / Wp for off < Wp + 256 (checked on the host)
   const float* bias;
+  const __nv_bfloat16* add;  // optional [rows][BN] tensor added to the result (gradient accumulation of the training plan)
   __nv_bfloat16* out;
   double* stats;
   int groups, out_ld, out_coff;
@@ -330,7 +331,17 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
             const int row = idx >> 3, chunk = idx & 7;
             const int gp = rp[row];
             if (gp >= 0) {
-              const uint4 val = *reinterpret_cast<const uint4*>(sbuf + row * 128 + ((chunk ^ (row & 7)) * 16));
+              uint4 val = *reinterpret_cast<const uint4*>(sbuf + row * 128 + ((chunk ^ (row & 7)) * 16));
+              if (p.add) {
+                const uint4 av = *reinterpret_cast<const uint4*>(p.add + (int64_t)gp * p.BN + s0 + chunk * 8);
+                __nv_bfloat162* hv = reinterpret_cast<__nv_bfloat162*>(&val);
+                const __nv_bfloat162* ha = reinterpret_cast<const __nv_bfloat162*>(&av);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const float2 a = __bfloat1622float2(hv[e]), b = __bfloat1622float2(ha[e]);
+                  hv[e] = __floats2bfloat162_rn(a.x + b.x, a.y + b.y);
+                }
+              }
               *reinterpret_cast<uint4*>(p.out + (int64_t)gp * p.out_ld + p.out_coff + s0 + chunk * 8) = val;
             }
           }
@@ -386,7 +397,7 @@ static size_t halo_smem(int Wp, int BN, int n_chunks, int* a_stage_bytes, int* a
 
 int conv_halo_supported(const dv_conv_params& p) {
   if (p.dtype != DV_BF16 || p.mode != DV_CONV_NORMAL || p.kh != 3 || p.kw != 3 || p.pad != 1) return 0;
-  if (p.epilogue != DV_EPI_STORE || p.add) return 0;
+  if (p.epilogue != DV_EPI_STORE || (p.add && p.stats)) return 0;
   if (p.Cout != 64 && p.Cout != 128) return 0;
   if (p.C0 % TC_BK || p.C1 % TC_BK) return 0;
   if (p.W < 32 || p.W > 128 || p.H < 8) return 0;
@@ -418,6 +429,7 @@ int conv_halo_launch(const dv_conv_params& p, cudaStream_t s) {
   for (int off = 0; off < h.Wp + HL_TILE_Q; ++off)
     DV_REQUIRE((int)(((uint32_t)off * h.wp_magic) >> 16) == off / h.Wp, DV_EUNSUPPORTED, "dv_conv_igemm(halo): division magic");
   h.bias = p.bias;
+  h.add = reinterpret_cast<const __nv_bfloat16*>(p.add);
   h.out = reinterpret_cast<__nv_bfloat16*>(p.out);
   h.stats = p.stats;
   h.groups = p.groups;

@@ -54,99 +54,102 @@ __global__ void gn_stats_kernel(dv_gn_stats_params p, int rows_per_block, int rp
 // ---------------------------------------------------------------- GroupNorm apply
 // grid (chunks, B); per-(b,c) affine folded into two fp32 coefficients held in shared memory.
 template <typename T>
-__global__ void __launch_bounds__(256) gn_apply_kernel(dv_gn_apply_params p, int rows_per_block) {
+__global__ void __launch_bounds__(256, 2) gn_apply_kernel(dv_gn_apply_params p, int64_t rows_per_block) {
   extern __shared__ float coef[];  // [2][C]
-  const int b = blockIdx.y;
+  // flat decomposition over all B*P rows: every CTA streams the same number of rows (one balanced wave whatever the
+  // batch), recomputing the per-(b,c) coefficients whenever its range crosses into the next sample
+  const int64_t total = (int64_t)p.B * p.P;
+  const int64_t g0 = (int64_t)blockIdx.x * rows_per_block;
+  int64_t g1 = g0 + rows_per_block;
+  if (g1 > total) g1 = total;
   const int cpg = p.C / p.groups;
   const double cnt = (double)p.P * cpg;
-  for (int c = threadIdx.x; c < p.C; c += blockDim.x) {
-    const int g = c / cpg;
-    const double s1 = p.stats[((int64_t)b * p.groups + g) * 2 + 0];
-    const double s2 = p.stats[((int64_t)b * p.groups + g) * 2 + 1];
-    const double mean = s1 / cnt;
-    double var = s2 / cnt - mean * mean;
-    if (var < 0.0) var = 0.0;
-    const float rstd = (float)(1.0 / sqrt(var + (double)p.eps));
-    float a = rstd * p.gamma[c];
-    float d = p.beta[c] - (float)mean * a;
-    if (p.scale) {
-      const float sc = 1.0f + p.scale[(int64_t)b * p.ss_ld + c];
-      a *= sc;
-      d = d * sc + p.shift[(int64_t)b * p.ss_ld + c];
-    }
-    coef[c] = a;
-    coef[p.C + c] = d;
-  }
-  __syncthreads();
   const int c8n = p.C / 8;
-  const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
-  int64_t r1 = r0 + rows_per_block;
-  if (r1 > p.P) r1 = p.P;
-  const int64_t base = (int64_t)b * p.P * p.C;
-  const T* x = reinterpret_cast<const T*>(p.x) + base;
-  const T* res = p.residual ? reinterpret_cast<const T*>(p.residual) + base : nullptr;
-  T* out = reinterpret_cast<T*>(p.out) + base;
-  const int nvec = (int)((r1 - r0) * c8n);  // vectors of 8 channels in this block's rows (rows are contiguous)
-  const int64_t vbase = r0 * c8n;
-  const T* xb = x + vbase * 8;
-  const T* rb = res ? res + vbase * 8 : nullptr;
-  T* ob = out + vbase * 8;
-  const int cmod0 = (int)(vbase % c8n);
-  constexpr int U = DV_GN_UNROLL;  // independent 16-byte loads in flight per thread and stream
-  if ((int)blockDim.x % c8n == 0) {
-    // the channel vector of a thread never changes (stride blockDim.x is a multiple of C/8): coefficients in registers
-    const int c = ((cmod0 + (int)threadIdx.x) % c8n) * 8;
-    float ca[8], cd[8];
+  constexpr int U = sizeof(T) == 4 ? DV_GN_UNROLL / 2 : DV_GN_UNROLL;  // independent loads in flight per thread and stream
+  for (int64_t seg0 = g0; seg0 < g1;) {
+    const int b = (int)(seg0 / p.P);
+    int64_t seg1 = (int64_t)(b + 1) * p.P;
+    if (seg1 > g1) seg1 = g1;
+    __syncthreads();  // the previous segment is done with coef
+    for (int c = threadIdx.x; c < p.C; c += blockDim.x) {
+      const int g = c / cpg;
+      const double s1 = p.stats[((int64_t)b * p.groups + g) * 2 + 0];
+      const double s2 = p.stats[((int64_t)b * p.groups + g) * 2 + 1];
+      const double mean = s1 / cnt;
+      double var = s2 / cnt - mean * mean;
+      if (var < 0.0) var = 0.0;
+      const float rstd = (float)(1.0 / sqrt(var + (double)p.eps));
+      float a = rstd * p.gamma[c];
+      float d = p.beta[c] - (float)mean * a;
+      if (p.scale) {
+        const float sc = 1.0f + p.scale[(int64_t)b * p.ss_ld + c];
+        a *= sc;
+        d = d * sc + p.shift[(int64_t)b * p.ss_ld + c];
+      }
+      coef[c] = a;
+      coef[p.C + c] = d;
+    }
+    __syncthreads();
+    const int nvec = (int)((seg1 - seg0) * c8n);  // vectors of 8 channels in this segment (rows are contiguous)
+    const T* xb = reinterpret_cast<const T*>(p.x) + seg0 * p.C;
+    const T* rb = p.residual ? reinterpret_cast<const T*>(p.residual) + seg0 * p.C : nullptr;
+    T* ob = reinterpret_cast<T*>(p.out) + seg0 * p.C;
+    if ((int)blockDim.x % c8n == 0) {
+      // the channel vector of a thread never changes (stride blockDim.x is a multiple of C/8): coefficients in registers
+      const int c = ((int)threadIdx.x % c8n) * 8;
+      float ca[8], cd[8];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) { ca[k] = coef[c + k]; cd[k] = coef[p.C + c + k]; }
-    // Little's law on B200 wants ~64 KB of loads in flight per SM: U raw 16/32-byte vectors per thread and stream are
-    // issued back to back (kept packed in registers), then unpacked, transformed and stored one by one.
-    constexpr int VW = sizeof(T) * 8 / 16;  // uint4 words per 8-element vector (1 for bf16, 2 for fp32)
-    for (int i0 = threadIdx.x; i0 < nvec; i0 += (int)blockDim.x * U) {
-      uint4 xr[U][VW], rraw[U][VW];
+      for (int k = 0; k < 8; ++k) { ca[k] = coef[c + k]; cd[k] = coef[p.C + c + k]; }
+      // Little's law on B200 wants ~64 KB of loads in flight per SM: U raw 16/32-byte vectors per thread and stream are
+      // issued back to back (kept packed in registers), then unpacked, transformed and stored one by one.
+      constexpr int VW = sizeof(T) * 8 / 16;  // uint4 words per 8-element vector (1 for bf16, 2 for fp32)
+      for (int i0 = threadIdx.x; i0 < nvec; i0 += (int)blockDim.x * U) {
+        uint4 xr[U][VW], rraw[U][VW];
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int i = i0 + u * (int)blockDim.x;
-        if (i < nvec) {
+        for (int u = 0; u < U; ++u) {
+          const int i = i0 + u * (int)blockDim.x;
+          if (i < nvec) {
 #pragma unroll
-          for (int w = 0; w < VW; ++w) {
-            xr[u][w] = reinterpret_cast<const uint4*>(xb + (int64_t)i * 8)[w];
-            if (rb) rraw[u][w] = reinterpret_cast<const uint4*>(rb + (int64_t)i * 8)[w];
+            for (int w = 0; w < VW; ++w) {
+              xr[u][w] = reinterpret_cast<const uint4*>(xb + (int64_t)i * 8)[w];
+              if (rb) rraw[u][w] = reinterpret_cast<const uint4*>(rb + (int64_t)i * 8)[w];
+            }
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int i = i0 + u * (int)blockDim.x;
+          if (i < nvec) {
+            float v[8], rr[8];
+            load8(reinterpret_cast<const T*>(&xr[u][0]), v);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v[k] = silu_f(fmaf(v[k], ca[k], cd[k]));
+            if (rb) {
+              load8(reinterpret_cast<const T*>(&rraw[u][0]), rr);
+#pragma unroll
+              for (int k = 0; k < 8; ++k) v[k] += rr[k];
+            }
+            store8(ob + (int64_t)i * 8, v);
           }
         }
       }
+    } else {
+      for (int i = threadIdx.x; i < nvec; i += (int)blockDim.x) {
+        const int c = (i % c8n) * 8;
+        float v[8];
+        load8(xb + (int64_t)i * 8, v);
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int i = i0 + u * (int)blockDim.x;
-        if (i < nvec) {
-          float v[8], rr[8];
-          load8(reinterpret_cast<const T*>(&xr[u][0]), v);
+        for (int k = 0; k < 8; ++k) v[k] = silu_f(fmaf(v[k], coef[c + k], coef[p.C + c + k]));
+        if (rb) {
+          float rr[8];
+          load8(rb + (int64_t)i * 8, rr);
 #pragma unroll
-          for (int k = 0; k < 8; ++k) v[k] = silu_f(fmaf(v[k], ca[k], cd[k]));
-          if (rb) {
-            load8(reinterpret_cast<const T*>(&rraw[u][0]), rr);
-#pragma unroll
-            for (int k = 0; k < 8; ++k) v[k] += rr[k];
-          }
-          store8(ob + (int64_t)i * 8, v);
+          for (int k = 0; k < 8; ++k) v[k] += rr[k];
         }
+        store8(ob + (int64_t)i * 8, v);
       }
     }
-  } else {
-    for (int i = threadIdx.x; i < nvec; i += (int)blockDim.x) {
-      const int c = ((cmod0 + i) % c8n) * 8;
-      float v[8];
-      load8(xb + (int64_t)i * 8, v);
-#pragma unroll
-      for (int k = 0; k < 8; ++k) v[k] = silu_f(fmaf(v[k], coef[c + k], coef[p.C + c + k]));
-      if (rb) {
-        float rr[8];
-        load8(rb + (int64_t)i * 8, rr);
-#pragma unroll
-        for (int k = 0; k < 8; ++k) v[k] += rr[k];
-      }
-      store8(ob + (int64_t)i * 8, v);
-    }
+    seg0 = seg1;
   }
 }
 
@@ -252,23 +255,24 @@ extern "C" int dv_gn_apply(const dv_gn_apply_params* p, dv_stream_t stream) {
   DV_REQUIRE(p->C % 8 == 0 && p->C <= 4096, DV_EUNSUPPORTED, "dv_gn_apply: needs C %% 8 == 0 and C <= 4096 (C=%d)", p->C);
   DV_REQUIRE(aligned16(p->x) && aligned16(p->out) && aligned16(p->residual), DV_EALIGN,
              "dv_gn_apply: tensors must be 16-byte aligned");
-  // one resident wave: ~2 CTAs per SM in total, so the per-CTA coefficient prologue is paid once, not per wave
+  // one resident wave: 2 CTAs per SM (120 registers x 256 threads), every CTA the same share of the B*P rows
   static int ctas_per_sm = 0;
   if (!ctas_per_sm) {
     const char* e = getenv("DV_GN_CTAS_PER_SM");  // tuning aid
     ctas_per_sm = e ? atoi(e) : 2;
     if (ctas_per_sm < 1) ctas_per_sm = 2;
   }
-  int chunks = (148 * ctas_per_sm + p->B - 1) / p->B;
-  int64_t rpb = (p->P + chunks - 1) / chunks;
-  if (rpb < 1) rpb = 1;
-  chunks = (int)((p->P + rpb - 1) / rpb);
-  dim3 grid(chunks, p->B);
+  const int64_t total = (int64_t)p->B * p->P;
+  DV_REQUIRE(p->P * (int64_t)(p->C / 8) < (1ll << 31), DV_EUNSUPPORTED, "dv_gn_apply: sample too large for 32-bit vector indices");
+  int64_t ctas = 148 * ctas_per_sm;
+  int64_t rpb = (total + ctas - 1) / ctas;
+  if (rpb < 32) rpb = 32;
+  ctas = (total + rpb - 1) / rpb;
   const size_t smem = sizeof(float) * 2 * p->C;
   if (p->dtype == DV_F32)
-    gn_apply_kernel<float><<<grid, 256, smem, as_stream(stream)>>>(*p, (int)rpb);
+    gn_apply_kernel<float><<<(unsigned)ctas, 256, smem, as_stream(stream)>>>(*p, rpb);
   else
-    gn_apply_kernel<__nv_bfloat16><<<grid, 256, smem, as_stream(stream)>>>(*p, (int)rpb);
+    gn_apply_kernel<__nv_bfloat16><<<(unsigned)ctas, 256, smem, as_stream(stream)>>>(*p, rpb);
   DV_CHECK_LAUNCH("dv_gn_apply");
   return DV_OK;
 }

@@ -500,6 +500,8 @@ HALO_CASES = [
     dict(B=1, T=4, H=32, W=32, C=(128, 64), Co=128, stats=True),     # 32x32, N=128
     dict(B=3, T=2, H=32, W=32, C=(64,), Co=64, stats=True),
     dict(B=1, T=2, H=16, W=64, C=(64,), Co=64),                      # non-square
+    dict(B=2, T=2, H=64, W=64, C=(64,), Co=64, add=True),            # + residual (gradient accumulation of the dgrad)
+    dict(B=1, T=2, H=32, W=32, C=(128,), Co=128, add=True),
 ]
 
 
@@ -515,10 +517,13 @@ def test_conv_streaming_halo_matches_conv3d(case):
     G = 8
     stats = torch.zeros(B, G, 2, dtype=torch.float64, device=dev()) if case.get("stats") else None
     out = torch.full((rows, Co), 9.0, dtype=dtype, device=dev())
-    conv(xs, wp, bias, out, n_img=B * T, frames=T, H=H, W=W, k=3, stats=stats, groups=G, impl=3)
+    add = rnd(rows, Co, dtype=dtype, seed=22) if case.get("add") else None
+    conv(xs, wp, bias, out, n_img=B * T, frames=T, H=H, W=W, k=3, stats=stats, groups=G, add=add, impl=3)
     xin = torch.cat([cl_to_ncdhw(x, B, T, H, W) for x in xs], dim=1)
     w_ref = wp.float().reshape(Co, 3, 3, cin).permute(0, 3, 1, 2)[:, :, None]
     ref = ncdhw_to_cl(F.conv3d(xin, w_ref, bias, padding=(0, 1, 1)))
+    if add is not None:
+        ref = ref + add.float()
     assert rel_err(out, ref) < 1e-2
     if stats is not None:
         yq = ref.to(dtype).float().reshape(B, -1, G, Co // G)
@@ -526,7 +531,7 @@ def test_conv_streaming_halo_matches_conv3d(case):
         assert rel_err(stats[..., 1], s2) < 2e-3
         assert float((stats[..., 0] - s1).abs().max()) < 2e-2 * float(s2.max().sqrt())
     out2 = torch.empty_like(out)
-    conv(xs, wp, bias, out2, n_img=B * T, frames=T, H=H, W=W, k=3, impl=2)
+    conv(xs, wp, bias, out2, n_img=B * T, frames=T, H=H, W=W, k=3, add=add, impl=2)
     assert rel_err(out, out2) < 6e-3
 
 
