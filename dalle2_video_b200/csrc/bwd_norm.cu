@@ -13,7 +13,7 @@
 namespace dv {
 
 __device__ __forceinline__ float silu_grad(float v) {
-  const float s = 1.0f / (1.0f + __expf(-v));
+  const float s = __fdividef(1.0f, 1.0f + __expf(-v));  // 2 ulp; keeps the streaming loop off the IEEE-division path
   return s * (1.0f + v * (1.0f - s));
 }
 
@@ -166,6 +166,156 @@ __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(dv_gn_bwd_params p, i
   }
 }
 
+// ---------------------------------------------------------------- streaming versions (C/8 divides 256)
+// Same math with the per-channel coefficients of a thread's fixed 8-channel vector held in registers and U raw 16-byte
+// loads per stream in flight (the gn_apply recipe: ~64 KB of loads in flight per SM).  The sums use
+//   sum g*xh = rs * sum g*x - mr * sum g     and     dx = w*g - x*k2 - k1,  k2 = rs*cm2,  k1 = cm1 - mr*cm2
+// so the inner loops need (a, d) resp. (a, d, w, k1, k2) per channel.
+constexpr int GNB_U = 4;
+
+template <typename T>
+__global__ void __launch_bounds__(256, 2) gn_bwd_reduce_fast_kernel(dv_gn_bwd_params p, int64_t rows_per_block) {
+  extern __shared__ float sm[];  // [4][C] coefficients a, d, rs, mr, then [C][2] partial sums
+  float* ca = sm; float* cd = sm + p.C; float* crs = sm + 2 * p.C; float* cmr = sm + 3 * p.C;
+  float* sred = sm + 4 * p.C;
+  const int b = blockIdx.y;
+  for (int c = threadIdx.x; c < p.C; c += blockDim.x) {
+    const GnCoef k = gn_coef(p, b, c);
+    ca[c] = k.a; cd[c] = k.d; crs[c] = k.rs; cmr[c] = k.mr;
+    sred[2 * c] = 0.f; sred[2 * c + 1] = 0.f;
+  }
+  __syncthreads();
+  const int c8n = p.C / 8;
+  const int c = ((int)threadIdx.x % c8n) * 8;
+  float a[8], d[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { a[j] = ca[c + j]; d[j] = cd[c + j]; }
+  const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
+  const int64_t r1 = r0 + rows_per_block < p.P ? r0 + rows_per_block : p.P;
+  const int64_t off = ((int64_t)b * p.P + r0) * p.C;
+  const T* x = reinterpret_cast<const T*>(p.x) + off;
+  const T* dy = reinterpret_cast<const T*>(p.dy) + off;
+  const int nvec = (int)((r1 - r0) * c8n);
+  constexpr int VW = sizeof(T) * 8 / 16;
+  float s1[8], sx[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { s1[j] = 0.f; sx[j] = 0.f; }
+  for (int i0 = threadIdx.x; i0 < nvec; i0 += 256 * GNB_U) {
+    uint4 xr[GNB_U][VW], gr[GNB_U][VW];
+#pragma unroll
+    for (int u = 0; u < GNB_U; ++u) {
+      const int i = i0 + u * 256;
+      if (i < nvec) {
+#pragma unroll
+        for (int w = 0; w < VW; ++w) {
+          xr[u][w] = reinterpret_cast<const uint4*>(x + (int64_t)i * 8)[w];
+          gr[u][w] = reinterpret_cast<const uint4*>(dy + (int64_t)i * 8)[w];
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < GNB_U; ++u) {
+      const int i = i0 + u * 256;
+      if (i < nvec) {
+        float xv[8], gv[8];
+        load8(reinterpret_cast<const T*>(&xr[u][0]), xv);
+        load8(reinterpret_cast<const T*>(&gr[u][0]), gv);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float g = gv[j] * silu_grad(fmaf(xv[j], a[j], d[j]));
+          s1[j] += g;
+          sx[j] = fmaf(g, xv[j], sx[j]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    atomicAdd(&sred[(c + j) * 2 + 0], s1[j]);
+    atomicAdd(&sred[(c + j) * 2 + 1], crs[c + j] * sx[j] - cmr[c + j] * s1[j]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * p.C; i += blockDim.x) atomicAdd(&p.sums[(int64_t)b * p.C * 2 + i], sred[i]);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256, 2) gn_bwd_apply_fast_kernel(dv_gn_bwd_params p, int64_t rows_per_block) {
+  extern __shared__ float sm[];  // [5][C]: a, d, w, k1, k2  (+ [C] rs scratch)
+  float* ca = sm; float* cd = sm + p.C; float* cw = sm + 2 * p.C; float* ck1 = sm + 3 * p.C; float* ck2 = sm + 4 * p.C;
+  float* crs = sm + 5 * p.C; float* cmr = sm + 6 * p.C;
+  __shared__ float gsum[64][2];
+  const int b = blockIdx.y;
+  const int cpg = p.C / p.groups;
+  if (threadIdx.x < 2 * p.groups) gsum[threadIdx.x >> 1][threadIdx.x & 1] = 0.f;
+  __syncthreads();
+  for (int c = threadIdx.x; c < p.C; c += blockDim.x) {
+    const GnCoef k = gn_coef(p, b, c);
+    ca[c] = k.a; cd[c] = k.d; crs[c] = k.rs; cmr[c] = k.mr;
+    const float sc = p.scale ? 1.0f + p.scale[(int64_t)b * p.ss_ld + c] : 1.0f;
+    const float gw = p.gamma[c] * sc;
+    cw[c] = gw * k.rs;
+    atomicAdd(&gsum[c / cpg][0], gw * p.sums[((int64_t)b * p.C + c) * 2 + 0]);
+    atomicAdd(&gsum[c / cpg][1], gw * p.sums[((int64_t)b * p.C + c) * 2 + 1]);
+  }
+  __syncthreads();
+  const float inv_cnt = 1.0f / ((float)p.P * (float)cpg);
+  for (int c = threadIdx.x; c < p.C; c += blockDim.x) {
+    const float m1 = crs[c] * gsum[c / cpg][0] * inv_cnt, m2 = crs[c] * gsum[c / cpg][1] * inv_cnt;
+    ck2[c] = crs[c] * m2;
+    ck1[c] = m1 - cmr[c] * m2;
+  }
+  __syncthreads();
+  const int c8n = p.C / 8;
+  const int c = ((int)threadIdx.x % c8n) * 8;
+  float a[8], d[8], w[8], k1[8], k2[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { a[j] = ca[c + j]; d[j] = cd[c + j]; w[j] = cw[c + j]; k1[j] = ck1[c + j]; k2[j] = ck2[c + j]; }
+  const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
+  const int64_t r1 = r0 + rows_per_block < p.P ? r0 + rows_per_block : p.P;
+  const int64_t off = ((int64_t)b * p.P + r0) * p.C;
+  const T* x = reinterpret_cast<const T*>(p.x) + off;
+  const T* dy = reinterpret_cast<const T*>(p.dy) + off;
+  T* dx = reinterpret_cast<T*>(p.dx) + off;
+  const int nvec = (int)((r1 - r0) * c8n);
+  constexpr int VW = sizeof(T) * 8 / 16;
+  for (int i0 = threadIdx.x; i0 < nvec; i0 += 256 * GNB_U) {
+    uint4 xr[GNB_U][VW], gr[GNB_U][VW], pr[GNB_U][VW];
+#pragma unroll
+    for (int u = 0; u < GNB_U; ++u) {
+      const int i = i0 + u * 256;
+      if (i < nvec) {
+#pragma unroll
+        for (int q = 0; q < VW; ++q) {
+          xr[u][q] = reinterpret_cast<const uint4*>(x + (int64_t)i * 8)[q];
+          gr[u][q] = reinterpret_cast<const uint4*>(dy + (int64_t)i * 8)[q];
+          if (p.accumulate) pr[u][q] = reinterpret_cast<const uint4*>(dx + (int64_t)i * 8)[q];
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < GNB_U; ++u) {
+      const int i = i0 + u * 256;
+      if (i < nvec) {
+        float xv[8], gv[8], o[8];
+        load8(reinterpret_cast<const T*>(&xr[u][0]), xv);
+        load8(reinterpret_cast<const T*>(&gr[u][0]), gv);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float g = gv[j] * silu_grad(fmaf(xv[j], a[j], d[j]));
+          o[j] = fmaf(w[j], g, -k1[j]) - xv[j] * k2[j];
+        }
+        if (p.accumulate) {
+          float prev[8];
+          load8(reinterpret_cast<const T*>(&pr[u][0]), prev);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] += prev[j];
+        }
+        store8(dx + (int64_t)i * 8, o);
+      }
+    }
+  }
+}
+
 // ---------------------------------------------------------------- LayerNorm backward (gain only), one warp per row
 //   y = xh * g ;  h = dy*g ;  dx = rstd * (h - mean(h) - xh*mean(h*xh)) ;  dg += sum_rows dy*xh
 template <typename T, int MAXV>
@@ -270,6 +420,20 @@ extern "C" int dv_gn_bwd_reduce(const dv_gn_bwd_params* p, dv_stream_t stream) {
   using namespace dv;
   int rc = gn_bwd_check(p, "dv_gn_bwd_reduce");
   if (rc != DV_OK) return rc;
+  cudaStream_t s = as_stream(stream);
+  const bool fast = 256 % (p->C / 8) == 0 && p->P * (int64_t)(p->C / 8) < (1ll << 31) && p->dtype == DV_BF16;
+  if (fast) {
+    // one resident wave of 2 CTAs per SM, every CTA the same number of rows
+    int chunks = (148 * 2) / p->B;
+    if (chunks < 1) chunks = 1;
+    int64_t rpb = (p->P + chunks - 1) / chunks;
+    if (rpb < 32) rpb = 32;
+    chunks = (int)((p->P + rpb - 1) / rpb);
+    dim3 grid(chunks, p->B);
+    gn_bwd_reduce_fast_kernel<__nv_bfloat16><<<grid, 256, sizeof(float) * 6 * p->C, s>>>(*p, rpb);
+    DV_CHECK_LAUNCH("dv_gn_bwd_reduce");
+    return DV_OK;
+  }
   const int c4n = p->C / 4;
   int rpi = 256 / c4n;
   if (rpi < 1) rpi = 1;
@@ -280,8 +444,8 @@ extern "C" int dv_gn_bwd_reduce(const dv_gn_bwd_params* p, dv_stream_t stream) {
   chunks = (int)((p->P + rpb - 1) / rpb);
   dim3 grid(chunks, p->B);
   const size_t smem = sizeof(float) * 2 * p->C;
-  if (p->dtype == DV_F32) gn_bwd_reduce_kernel<float><<<grid, threads, smem, as_stream(stream)>>>(*p, (int)rpb, rpi);
-  else gn_bwd_reduce_kernel<__nv_bfloat16><<<grid, threads, smem, as_stream(stream)>>>(*p, (int)rpb, rpi);
+  if (p->dtype == DV_F32) gn_bwd_reduce_kernel<float><<<grid, threads, smem, s>>>(*p, (int)rpb, rpi);
+  else gn_bwd_reduce_kernel<__nv_bfloat16><<<grid, threads, smem, s>>>(*p, (int)rpb, rpi);
   DV_CHECK_LAUNCH("dv_gn_bwd_reduce");
   return DV_OK;
 }
@@ -295,6 +459,17 @@ extern "C" int dv_gn_bwd_apply(const dv_gn_bwd_params* p, dv_stream_t stream) {
   cudaStream_t s = as_stream(stream);
   gn_bwd_params_kernel<<<(p->C + 127) / 128, 128, 0, s>>>(*p);
   DV_CHECK_LAUNCH("dv_gn_bwd_apply(params)");
+  if (256 % (p->C / 8) == 0 && p->P * (int64_t)(p->C / 8) < (1ll << 31) && p->dtype == DV_BF16) {
+    int chunks = (148 * 2) / p->B;
+    if (chunks < 1) chunks = 1;
+    int64_t rpb = (p->P + chunks - 1) / chunks;
+    if (rpb < 32) rpb = 32;
+    chunks = (int)((p->P + rpb - 1) / rpb);
+    dim3 grid(chunks, p->B);
+    gn_bwd_apply_fast_kernel<__nv_bfloat16><<<grid, 256, sizeof(float) * 7 * p->C, s>>>(*p, rpb);
+    DV_CHECK_LAUNCH("dv_gn_bwd_apply");
+    return DV_OK;
+  }
   int chunks = (148 * 2 + p->B - 1) / p->B;
   int64_t rpb = (p->P + chunks - 1) / chunks;
   if (rpb < 1) rpb = 1;
