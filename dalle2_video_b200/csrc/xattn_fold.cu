@@ -94,7 +94,7 @@ __device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, uint64_t* ba
 __device__ __forceinline__ void xf_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
 template <int NK>
-__global__ void __launch_bounds__(XF_THREADS, 1)
+__global__ void __launch_bounds__(XF_THREADS, 2)
 xattn_fold_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_mq,
                   const __grid_constant__ CUtensorMap map_u, const __grid_constant__ CUtensorMap map_out,
                   const XfoldParams p) {
@@ -401,7 +401,7 @@ extern "C" int dv_xattn_fold(const dv_xattn_fold_params* p, dv_stream_t stream) 
   k.C = p->C;
   k.chunks = p->C / 64;
   k.NB = p->C < 256 ? p->C : 256;
-  k.xs = p->C <= 256 ? 2 : 1;
+  k.xs = p->C == 128 ? 1 : 2;  // C = 128: one x stage lets two CTAs share an SM, which hides more than the prefetch did
   k.heads = p->heads;
   k.nk = p->nk;
   k.tiles_per_sample = p->P / TC_BM;
@@ -449,7 +449,11 @@ extern "C" int dv_xattn_fold(const dv_xattn_fold_params* p, dv_stream_t stream) 
     cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
     if (sm_count <= 0) sm_count = 148;
   }
-  int gx = sm_count / p->B;
+  // the per-tile chain (LN statistics -> MMA 1 -> softmax -> MMA 2 -> LN -> store) is serial within a CTA: two CTAs per
+  // SM overlap two chains whenever shared memory (and TMEM: C columns each) allow it
+  const uint32_t tmem_cols = p->C < 64 ? 64u : (uint32_t)p->C;
+  const int per_sm = (2 * (smem + 1024) <= 227 * 1024 && 2 * tmem_cols <= 512) ? 2 : 1;
+  int gx = per_sm * sm_count / p->B;
   if (gx < 1) gx = 1;
   if (gx > k.tiles_per_sample) gx = (int)k.tiles_per_sample;
   DV_REQUIRE(p->B <= 65535, DV_EUNSUPPORTED, "dv_xattn_fold: more than 65535 samples per launch");
