@@ -239,11 +239,11 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
       const int n0 = g.R0 / p.Hp1, y0r = g.R0 - n0 * p.Hp1;
       if (p.stats && cur_sample >= 0 && sample != cur_sample) flush_stats(cur_sample);
       cur_sample = sample;
-      { HL_T0(); mbar_wait(&tmem_full[acc], acc_phase); HL_ACC(w_f); }
-      tc_fence_after();
+      // which output position does each accumulator row of this thread hold?
+      // row m of the tile is Q0 + m: at most 8 padded rows below R0, at most one frame boundary crossed
+      int pos_u[2];
+#pragma unroll
       for (int u = 0; u < 2; ++u) {
-        // which output position does this accumulator row hold?
-        // row m of the tile is Q0 + m: at most 8 padded rows below R0, at most one frame boundary crossed
         const int off = g.x0r + u * 128 + row_in_sub;
         const int dR = (int)(((uint32_t)off * p.wp_magic) >> 16);
         const int xx = off - dR * p.Wp - 1;
@@ -251,7 +251,24 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
         if (yr >= p.Hp1) { yr -= p.Hp1; ++n; }
         const int yy = yr - 1;
         const bool valid = xx >= 0 && xx < p.W && yy >= 0 && n < (sample + 1) * p.frames;
-        const int pos = valid ? (n * p.H + yy) * p.W + xx : -1;
+        pos_u[u] = valid ? (n * p.H + yy) * p.W + xx : -1;
+      }
+      // residual (gradient accumulation): this thread's 32 channels of the NEXT chunk are fetched one chunk ahead, the
+      // first one before the accumulator wait, so the global-load latency hides behind the MMAs / the previous chunk
+      uint4 addv[4];
+      auto load_add = [&](int u, int s0) {
+        if (p.add && pos_u[u] >= 0) {
+          const uint4* a = reinterpret_cast<const uint4*>(p.add + (int64_t)pos_u[u] * p.BN + s0 + wg * 32);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) addv[j] = a[j];
+        }
+      };
+      load_add(0, 0);
+      { HL_T0(); mbar_wait(&tmem_full[acc], acc_phase); HL_ACC(w_f); }
+      tc_fence_after();
+      for (int u = 0; u < 2; ++u) {
+        const int pos = pos_u[u];
+        const bool valid = pos >= 0;
         const uint32_t t_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((acc * 2 + u) * p.BN);
         for (int s0 = 0; s0 < p.BN; s0 += 64) {
           const int c0 = s0 + wg * 32;
@@ -265,6 +282,23 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
             v[j + 1] = valid ? __uint_as_float(r[j + 1]) + bb.y : 0.f;
             v[j + 2] = valid ? __uint_as_float(r[j + 2]) + bb.z : 0.f;
             v[j + 3] = valid ? __uint_as_float(r[j + 3]) + bb.w : 0.f;
+          }
+          if (p.add) {
+            if (valid) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const __nv_bfloat162* ha = reinterpret_cast<const __nv_bfloat162*>(&addv[j]);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const float2 a = __bfloat1622float2(ha[e]);
+                  v[j * 8 + 2 * e] += a.x;
+                  v[j * 8 + 2 * e + 1] += a.y;
+                }
+              }
+            }
+            // next chunk of this thread: (u, s0 + 64) or (u + 1, 0)
+            if (s0 + 64 < p.BN) load_add(u, s0 + 64);
+            else if (u == 0) load_add(1, 0);
           }
           if (p.stats) {
             float w8[8];
@@ -331,17 +365,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
             const int row = idx >> 3, chunk = idx & 7;
             const int gp = rp[row];
             if (gp >= 0) {
-              uint4 val = *reinterpret_cast<const uint4*>(sbuf + row * 128 + ((chunk ^ (row & 7)) * 16));
-              if (p.add) {
-                const uint4 av = *reinterpret_cast<const uint4*>(p.add + (int64_t)gp * p.BN + s0 + chunk * 8);
-                __nv_bfloat162* hv = reinterpret_cast<__nv_bfloat162*>(&val);
-                const __nv_bfloat162* ha = reinterpret_cast<const __nv_bfloat162*>(&av);
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  const float2 a = __bfloat1622float2(hv[e]), b = __bfloat1622float2(ha[e]);
-                  hv[e] = __floats2bfloat162_rn(a.x + b.x, a.y + b.y);
-                }
-              }
+              const uint4 val = *reinterpret_cast<const uint4*>(sbuf + row * 128 + ((chunk ^ (row & 7)) * 16));
               *reinterpret_cast<uint4*>(p.out + (int64_t)gp * p.out_ld + p.out_coff + s0 + chunk * 8) = val;
             }
           }
