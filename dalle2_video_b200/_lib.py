@@ -106,7 +106,7 @@ class Im2colParams(C.Structure):
 
 class InitConvParams(C.Structure):
     _fields_ = [("x", vp), ("weight", vp), ("bias", vp), ("out", vp), ("B", i32), ("C", i32), ("T", i32), ("H", i32),
-                ("W", i32), ("k", i32), ("Kpad", i32), ("Cout", i32), ("dtype", i32)]
+                ("W", i32), ("k", i32), ("Kpad", i32), ("Cout", i32), ("dtype", i32), ("layout", i32)]
 
 
 class ToOutParams(C.Structure):

@@ -250,8 +250,12 @@ static size_t init_conv_smem(const dv_init_conv_params& p, int n_chunks, int rpt
   return w + 1024 + IC_STAGES * 16384 + win + p.Cout * 4 + 256 + 1024;
 }
 
+bool init_conv_rs_ok(const dv_init_conv_params& p);
+int init_conv_rs_launch(const dv_init_conv_params& p, cudaStream_t s);
+
 static bool init_conv_ok(const dv_init_conv_params& p) {
-  if (p.dtype != DV_BF16) return false;
+  if (p.layout == 1) return init_conv_rs_ok(p);
+  if (p.dtype != DV_BF16 || p.layout != 0) return false;
   if (p.k != 15 && p.k != 7 && p.k != 3 && p.k != 5 && p.k != 9 && p.k != 11 && p.k != 13) return false;
   if (p.W != 32 && p.W != 64 && p.W != 128) return false;
   const int rpt = 128 / p.W;
@@ -278,6 +282,7 @@ extern "C" int dv_init_conv(const dv_init_conv_params* p, dv_stream_t stream) {
              "dv_init_conv: needs bf16, W in {32,64,128}, H %% (128/W) == 0, Cout in {32,64}, weights resident in shared memory "
              "(got W=%d H=%d C=%d k=%d Cout=%d Kpad=%d)", p->W, p->H, p->C, p->k, p->Cout, p->Kpad);
   DV_REQUIRE(aligned16(p->weight) && aligned16(p->out), DV_EALIGN, "dv_init_conv: weight / out must be 16-byte aligned");
+  if (p->layout == 1) return init_conv_rs_launch(*p, as_stream(stream));
   InitConvParams k;
   memset(&k, 0, sizeof(k));
   k.x = p->x; k.bias = p->bias; k.out = reinterpret_cast<__nv_bfloat16*>(p->out);

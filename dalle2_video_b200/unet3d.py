@@ -835,8 +835,19 @@ class _Engine:
             co0 += co
         wp = torch.zeros(u.init_dim, kpad)
         wp[:, :ktot] = wfull.reshape(u.init_dim, ktot)
+        # preferred: the row-shift kernel (dx is a tap; K = (c, dy) <= 64): weight [dx][Cout][64]
+        rs = L.InitConvParams(x=self._x_src().data_ptr(), weight=None, bias=None, out=x0.ptr, B=self.B, C=cin, T=self.T, H=H,
+                              W=W, k=kmax, Kpad=64, Cout=u.init_dim, dtype=self.code, layout=1)
+        if self.u.fuse_init_conv and L.lib().dv_init_conv_supported(rs):
+            wrs = torch.zeros(kmax, u.init_dim, 64)
+            wrs[:, :, :cin * kmax] = wfull[:, :, :, :kmax].permute(3, 0, 1, 2).reshape(kmax, u.init_dim, cin * kmax)
+            rs.weight = self._w(wrs).data_ptr()
+            rs.bias = self._f32(torch.cat(bfull)).data_ptr()
+            self._op("dv_init_conv", rs)
+            self.n_tc += 1
+            return True
         fused = L.InitConvParams(x=self._x_src().data_ptr(), weight=None, bias=None, out=x0.ptr, B=self.B, C=cin, T=self.T, H=H,
-                                 W=W, k=kmax, Kpad=kpad, Cout=u.init_dim, dtype=self.code)
+                                 W=W, k=kmax, Kpad=kpad, Cout=u.init_dim, dtype=self.code, layout=0)
         if self.u.fuse_init_conv and L.lib().dv_init_conv_supported(fused):
             # one kernel: the im2col tiles are built in shared memory and never reach HBM (include/dv_b200.h, "K4 fused")
             fused.weight = self._w(wp).data_ptr()

@@ -457,9 +457,12 @@ typedef struct {
   void* out;
   int B, C, T, H, W;
   int k;      /* largest (odd) kernel size, <= 15 */
-  int Kpad;   /* row length of `weight`, multiple of 64, >= ceil(C*k/4)*64 */
+  int Kpad;   /* row length of `weight`, multiple of 64, >= ceil(C*k/4)*64 (layout 0); 64 (layout 1) */
   int Cout;
   dv_dtype dtype;
+  int layout; /* 0: weight [Cout][Kpad], K = (c*k + dy)*16 + dx — im2col tiles expanded in shared memory (init_conv_tc.cu).
+                 1: weight [k (dx)][Cout][64], K = c*k + dy — the "row-shift" kernel (init_conv_rs.cu): dx is a tap applied
+                    as a row offset into a [padded pixel][(c,dy)] matrix built once per tile; needs C*k <= 64 */
 } dv_init_conv_params;
 int dv_init_conv(const dv_init_conv_params* p, dv_stream_t stream);
 int dv_init_conv_supported(const dv_init_conv_params* p);

@@ -652,7 +652,48 @@ def test_fused_init_conv_matches_cross_embed(B, T, H, W, dim):
     assert torch.equal(out, out2)
 
 
+@pytest.mark.parametrize("B,T,H,W,dim,C,ks", [(2, 3, 64, 64, 64, 3, (3, 7, 15)), (1, 2, 32, 32, 32, 3, (3, 7, 15)),
+                                               (3, 2, 16, 16, 64, 3, (3, 7, 15)), (1, 3, 20, 48, 64, 3, (3, 7, 15)),
+                                               (2, 2, 32, 32, 64, 6, (3, 7)), (1, 1, 7, 24, 32, 4, (3, 5, 9))])
+def test_row_shift_init_conv_matches_cross_embed(B, T, H, W, dim, C, ks):
+    """dv_init_conv layout 1 (init_conv_rs.cu: dx as a tap over a [padded pixel][(c,dy)] matrix) vs the parallel Conv3d of
+    CrossEmbedLayer3D (/root/reference/dalle2_video/dalle2_video.py:208-244), incl. ragged last tiles (H % rows-per-tile),
+    widths that are not powers of two and the 6-channel input of a low-resolution-conditioned unet."""
+    n = len(ks)
+    scales = [dim // 2 ** (i + 1) for i in range(n - 1)]
+    scales.append(dim - sum(scales))
+    x = rnd(B, C, T, H, W, seed=1)
+    ws = [rnd(co, C, 1, k, k, seed=10 + i, scale=(C * k * k) ** -0.5) for i, (k, co) in enumerate(zip(ks, scales))]
+    bs = [rnd(co, seed=20 + i) for i, co in enumerate(scales)]
+    kmax = max(ks)
+    wfull = torch.zeros(dim, C, kmax, kmax, device=dev())
+    co0 = 0
+    for w, k in zip(ws, ks):
+        o = (kmax - k) // 2
+        wfull[co0:co0 + w.shape[0], :, o:o + k, o:o + k] = w[:, :, 0]
+        co0 += w.shape[0]
+    wrs = torch.zeros(kmax, dim, 64, device=dev())
+    wrs[:, :, :C * kmax] = wfull.permute(3, 0, 1, 2).reshape(kmax, dim, C * kmax)   # [dx][co][c*k + dy]
+    wrs = wrs.to(torch.bfloat16).contiguous()
+    bias = torch.cat(bs)
+    out = torch.full((B * T * H * W, dim), 7.0, device=dev(), dtype=torch.bfloat16)
+    p = L.InitConvParams(x=ptr(x), weight=ptr(wrs), bias=ptr(bias), out=ptr(out), B=B, C=C, T=T, H=H, W=W, k=kmax, Kpad=64,
+                         Cout=dim, dtype=L.DV_BF16, layout=1)
+    assert L.lib().dv_init_conv_supported(p) == 1
+    L.call("dv_init_conv", p, stream())
+    xb = x.to(torch.bfloat16).float()
+    ref = torch.cat([F.conv3d(xb, w.to(torch.bfloat16).float(), b, padding=(0, k // 2, k // 2)) for w, b, k in zip(ws, bs, ks)], dim=1)
+    assert rel_err(cl_to_ncdhw(out, B, T, H, W), ref) < TOL[torch.bfloat16]
+    out2 = torch.empty_like(out)
+    p.out = ptr(out2)
+    L.call("dv_init_conv", p, stream())
+    assert torch.equal(out, out2)
+
+
 def test_fused_init_conv_rejects_unsupported_shapes():
+    q = L.InitConvParams(x=1 << 20, weight=1 << 20, bias=None, out=1 << 20, B=1, C=6, T=1, H=8, W=64, k=15, Kpad=64, Cout=64,
+                         dtype=L.DV_BF16, layout=1)
+    assert L.lib().dv_init_conv_supported(q) == 0    # C*k = 90 > 64 K slots
     p = L.InitConvParams(x=1 << 20, weight=1 << 20, bias=None, out=1 << 20, B=1, C=3, T=1, H=8, W=48, k=15, Kpad=768, Cout=64,
                          dtype=L.DV_BF16)
     assert L.lib().dv_init_conv_supported(p) == 0
