@@ -15,7 +15,7 @@ namespace dv {
 // grid (ceil(P/128), heads, B), 128 threads: thread = one token of this (sample, head).
 template <typename T, int DH, int NKMAX>
 __global__ void __launch_bounds__(128) xattn_bwd_kernel(dv_xattn_bwd_params p) {
-  extern __shared__ float smem[];
+  extern __shared__ __align__(16) float smem[];
   const int nk = p.n_ctx + 1;
   float* ks = smem;                        // [nk][DH]
   float* vs = ks + nk * DH;                // [nk][DH]
@@ -57,10 +57,13 @@ __global__ void __launch_bounds__(128) xattn_bwd_kernel(dv_xattn_bwd_params p) {
     dp[j] = 0.f;
     if (j < nk) {
       float d = 0.f, g = 0.f;
+      // K / V rows are read as float4 (one LDS.128 per four FMAs: the kernel is shared-memory-instruction bound)
 #pragma unroll
-      for (int e = 0; e < DH; ++e) {
-        d = fmaf(q[e], ks[j * DH + e], d);
-        g = fmaf(dO[e], vs[j * DH + e], g);
+      for (int e = 0; e < DH; e += 4) {
+        const float4 kk = *reinterpret_cast<const float4*>(ks + j * DH + e);
+        const float4 vv = *reinterpret_cast<const float4*>(vs + j * DH + e);
+        d = fmaf(q[e], kk.x, d); d = fmaf(q[e + 1], kk.y, d); d = fmaf(q[e + 2], kk.z, d); d = fmaf(q[e + 3], kk.w, d);
+        g = fmaf(dO[e], vv.x, g); g = fmaf(dO[e + 1], vv.y, g); g = fmaf(dO[e + 2], vv.z, g); g = fmaf(dO[e + 3], vv.w, g);
       }
       s[j] = d * p.scale;
       dp[j] = g;
@@ -84,7 +87,11 @@ __global__ void __launch_bounds__(128) xattn_bwd_kernel(dv_xattn_bwd_params p) {
     ds_s[t * NKMAX + j] = dsj;
     if (j < nk) {
 #pragma unroll
-      for (int e = 0; e < DH; ++e) dq[e] = fmaf(dsj, ks[j * DH + e], dq[e]);
+      for (int e = 0; e < DH; e += 4) {
+        const float4 kk = *reinterpret_cast<const float4*>(ks + j * DH + e);
+        dq[e] = fmaf(dsj, kk.x, dq[e]); dq[e + 1] = fmaf(dsj, kk.y, dq[e + 1]);
+        dq[e + 2] = fmaf(dsj, kk.z, dq[e + 2]); dq[e + 3] = fmaf(dsj, kk.w, dq[e + 3]);
+      }
     }
   }
   if (active) {
@@ -108,10 +115,23 @@ __global__ void __launch_bounds__(128) xattn_bwd_kernel(dv_xattn_bwd_params p) {
   for (int j = 0; j < NKMAX; ++j) { dk[j] = 0.f; dv[j] = 0.f; }
   for (int r = half; r < 128; r += SL) {
     const float qv = q_s[r * (DH + 1) + d], ov = do_s[r * (DH + 1) + d];
+    if constexpr (NKMAX % 4 == 0) {
+      // broadcast rows of dS / P as float4
 #pragma unroll
-    for (int j = 0; j < NKMAX; ++j) {
-      dk[j] = fmaf(ds_s[r * NKMAX + j], qv, dk[j]);
-      dv[j] = fmaf(p_s[r * NKMAX + j], ov, dv[j]);
+      for (int j = 0; j < NKMAX; j += 4) {
+        const float4 a = *reinterpret_cast<const float4*>(ds_s + r * NKMAX + j);
+        const float4 c = *reinterpret_cast<const float4*>(p_s + r * NKMAX + j);
+        dk[j] = fmaf(a.x, qv, dk[j]); dk[j + 1] = fmaf(a.y, qv, dk[j + 1]);
+        dk[j + 2] = fmaf(a.z, qv, dk[j + 2]); dk[j + 3] = fmaf(a.w, qv, dk[j + 3]);
+        dv[j] = fmaf(c.x, ov, dv[j]); dv[j + 1] = fmaf(c.y, ov, dv[j + 1]);
+        dv[j + 2] = fmaf(c.z, ov, dv[j + 2]); dv[j + 3] = fmaf(c.w, ov, dv[j + 3]);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < NKMAX; ++j) {
+        dk[j] = fmaf(ds_s[r * NKMAX + j], qv, dk[j]);
+        dv[j] = fmaf(p_s[r * NKMAX + j], ov, dv[j]);
+      }
     }
   }
 #pragma unroll
@@ -184,7 +204,10 @@ __global__ void __launch_bounds__(128) attn_mqa_bwd_dq_kernel(dv_attn_mqa_bwd_pa
       for (int j = 0; j < nt; ++j) {
         float d = 0.f;
 #pragma unroll
-        for (int e = 0; e < DH; ++e) d = fmaf(q[e], ks[j * DH + e], d);
+        for (int e = 0; e < DH; e += 4) {  // float4 rows: one LDS.128 per four FMAs (shared-memory-instruction bound loop)
+          const float4 kk = *reinterpret_cast<const float4*>(ks + j * DH + e);
+          d = fmaf(q[e], kk.x, d); d = fmaf(q[e + 1], kk.y, d); d = fmaf(q[e + 2], kk.z, d); d = fmaf(q[e + 3], kk.w, d);
+        }
         d *= p.scale;
         if (pass == 0) {
           const float mn = fmaxf(m, d);
@@ -194,10 +217,17 @@ __global__ void __launch_bounds__(128) attn_mqa_bwd_dq_kernel(dv_attn_mqa_bwd_pa
           const float pj = __expf(d - lse);
           float g = 0.f;
 #pragma unroll
-          for (int e = 0; e < DH; ++e) g = fmaf(dO[e], vs[j * DH + e], g);
+          for (int e = 0; e < DH; e += 4) {
+            const float4 vv = *reinterpret_cast<const float4*>(vs + j * DH + e);
+            g = fmaf(dO[e], vv.x, g); g = fmaf(dO[e + 1], vv.y, g); g = fmaf(dO[e + 2], vv.z, g); g = fmaf(dO[e + 3], vv.w, g);
+          }
           const float dsj = pj * (g - D) * p.scale;
 #pragma unroll
-          for (int e = 0; e < DH; ++e) dq[e] = fmaf(dsj, ks[j * DH + e], dq[e]);
+          for (int e = 0; e < DH; e += 4) {
+            const float4 kk = *reinterpret_cast<const float4*>(ks + j * DH + e);
+            dq[e] = fmaf(dsj, kk.x, dq[e]); dq[e + 1] = fmaf(dsj, kk.y, dq[e + 1]);
+            dq[e + 2] = fmaf(dsj, kk.z, dq[e + 2]); dq[e + 3] = fmaf(dsj, kk.w, dq[e + 3]);
+          }
         }
       }
     }
@@ -221,8 +251,8 @@ __global__ void __launch_bounds__(128) attn_mqa_bwd_dq_kernel(dv_attn_mqa_bwd_pa
 constexpr int BQT = 32;  // (query, head) pairs per shared tile
 template <typename T, int DH>
 __global__ void __launch_bounds__(128) attn_mqa_bwd_dkv_kernel(dv_attn_mqa_bwd_params p, int pairs_per_chunk) {
-  __shared__ float q_s[BQT * DH];
-  __shared__ float do_s[BQT * DH];
+  __shared__ __align__(16) float q_s[BQT * DH];
+  __shared__ __align__(16) float do_s[BQT * DH];
   __shared__ float st_s[BQT * 2];
   const int64_t s = blockIdx.z;
   const int nk = p.n + 1;
@@ -268,17 +298,24 @@ __global__ void __launch_bounds__(128) attn_mqa_bwd_dkv_kernel(dv_attn_mqa_bwd_p
     if (active) {
       for (int r = 0; r < nt; ++r) {
         float d = 0.f, g = 0.f;
+        float4 qv[DH / 4], ov[DH / 4];   // the (query, head) row, broadcast to every key thread as float4
 #pragma unroll
-        for (int e = 0; e < DH; ++e) {
-          d = fmaf(q_s[r * DH + e], k[e], d);
-          g = fmaf(do_s[r * DH + e], v[e], g);
+        for (int e = 0; e < DH / 4; ++e) {
+          qv[e] = *reinterpret_cast<const float4*>(q_s + r * DH + 4 * e);
+          ov[e] = *reinterpret_cast<const float4*>(do_s + r * DH + 4 * e);
+          d = fmaf(qv[e].x, k[4 * e], d); d = fmaf(qv[e].y, k[4 * e + 1], d);
+          d = fmaf(qv[e].z, k[4 * e + 2], d); d = fmaf(qv[e].w, k[4 * e + 3], d);
+          g = fmaf(ov[e].x, v[4 * e], g); g = fmaf(ov[e].y, v[4 * e + 1], g);
+          g = fmaf(ov[e].z, v[4 * e + 2], g); g = fmaf(ov[e].w, v[4 * e + 3], g);
         }
         const float pj = __expf(d * p.scale - st_s[r * 2]);
         const float dsj = pj * (g - st_s[r * 2 + 1]) * p.scale;
 #pragma unroll
-        for (int e = 0; e < DH; ++e) {
-          dv[e] = fmaf(pj, do_s[r * DH + e], dv[e]);
-          dk[e] = fmaf(dsj, q_s[r * DH + e], dk[e]);
+        for (int e = 0; e < DH / 4; ++e) {
+          dv[4 * e] = fmaf(pj, ov[e].x, dv[4 * e]); dv[4 * e + 1] = fmaf(pj, ov[e].y, dv[4 * e + 1]);
+          dv[4 * e + 2] = fmaf(pj, ov[e].z, dv[4 * e + 2]); dv[4 * e + 3] = fmaf(pj, ov[e].w, dv[4 * e + 3]);
+          dk[4 * e] = fmaf(dsj, qv[e].x, dk[4 * e]); dk[4 * e + 1] = fmaf(dsj, qv[e].y, dk[4 * e + 1]);
+          dk[4 * e + 2] = fmaf(dsj, qv[e].z, dk[4 * e + 2]); dk[4 * e + 3] = fmaf(dsj, qv[e].w, dk[4 * e + 3]);
         }
       }
     }
