@@ -73,7 +73,7 @@ class XattnFoldParams(C.Structure):
 class AttnMqaParams(C.Structure):
     _fields_ = [("q", vp), ("kv", vp), ("out", vp), ("null_kv", vp), ("bias", vp), ("workspace", vp),
                 ("workspace_bytes", i64), ("S", i64), ("n", i32), ("heads", i32), ("dh", i32), ("scale", f32),
-                ("dtype", i32), ("impl", i32)]
+                ("dtype", i32), ("impl", i32), ("lse", vp)]
 
 
 class AttnTemporalParams(C.Structure):
@@ -152,7 +152,7 @@ class XattnBwdParams(C.Structure):
 class AttnMqaBwdParams(C.Structure):
     _fields_ = [("q", vp), ("kv", vp), ("out", vp), ("dout", vp), ("dq", vp), ("dkv", vp), ("null_kv", vp),
                 ("dnull_kv", vp), ("rowstats", vp), ("S", i64), ("n", i32), ("heads", i32), ("dh", i32),
-                ("scale", f32), ("dtype", i32)]
+                ("scale", f32), ("dtype", i32), ("lse", vp), ("impl", i32)]
 
 
 class QSampleParams(C.Structure):

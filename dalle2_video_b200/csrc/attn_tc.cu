@@ -40,6 +40,7 @@ struct AttnTcParams {
   const __nv_bfloat16* q;
   __nv_bfloat16* out;
   const float* null_kv;
+  float* lse;           // optional (MQA): log2-domain log-sum-exp per (query, head) row
   float scale_log2e;    // scale * log2(e)
   float scale;
 };
@@ -333,6 +334,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
       __syncwarp();
       if (lane == 0) mbar_arrive(&q_free[t & 1]);  // this Q buffer may be refilled
       const float inv = 1.0f / l;
+      if (!MHA && p.lse) p.lse[grow] = m + log2f(l);
       __nv_bfloat16* orow = p.out + grow * DH;
 #pragma unroll
       for (int e = 0; e < DH; e += 8) {
@@ -382,6 +384,7 @@ int attn_tc_launch(const dv_attn_mqa_params& p, cudaStream_t s) {
   k.q = reinterpret_cast<const __nv_bfloat16*>(p.q);
   k.out = reinterpret_cast<__nv_bfloat16*>(p.out);
   k.null_kv = p.null_kv;
+  k.lse = p.lse;
   k.scale = p.scale;
   k.scale_log2e = p.scale * 1.4426950408889634f;
   CUtensorMap mq, mk, mv;

@@ -331,6 +331,10 @@ __global__ void __launch_bounds__(128) attn_mqa_bwd_dkv_kernel(dv_attn_mqa_bwd_p
   }
 }
 
+int attn_bwd_tc_supported(const dv_attn_mqa_bwd_params& p);
+int64_t attn_bwd_tc_workspace_bytes(const dv_attn_mqa_bwd_params& p);
+int attn_bwd_tc_launch(const dv_attn_mqa_bwd_params& p, cudaStream_t s);
+
 }  // namespace dv
 
 extern "C" int dv_xattn_core_bwd(const dv_xattn_bwd_params* p, dv_stream_t stream) {
@@ -361,7 +365,14 @@ extern "C" int dv_xattn_core_bwd(const dv_xattn_bwd_params* p, dv_stream_t strea
 
 extern "C" int64_t dv_attn_mqa_bwd_workspace_bytes(const dv_attn_mqa_bwd_params* p) {
   if (!p) return 0;
-  return (int64_t)p->S * p->n * p->heads * 2 * (int64_t)sizeof(float);
+  const int64_t cuda_core = (int64_t)p->S * p->n * p->heads * 2 * (int64_t)sizeof(float);
+  // the tcgen05 path keeps D and a float32 dq accumulator there; sized for it whenever the shape could take that path
+  // (the caller may attach `lse` after sizing the workspace)
+  dv_attn_mqa_bwd_params q = *p;
+  static const float dummy = 0.f;
+  q.lse = &dummy;
+  const int64_t tc = dv::attn_bwd_tc_supported(q) ? dv::attn_bwd_tc_workspace_bytes(q) : 0;
+  return tc > cuda_core ? tc : cuda_core;
 }
 
 extern "C" int dv_attn_mqa_bwd(const dv_attn_mqa_bwd_params* p, dv_stream_t stream) {
@@ -373,6 +384,11 @@ extern "C" int dv_attn_mqa_bwd(const dv_attn_mqa_bwd_params* p, dv_stream_t stre
   DV_REQUIRE(aligned16(p->q) && aligned16(p->kv) && aligned16(p->out) && aligned16(p->dout) && aligned16(p->dq), DV_EALIGN,
              "dv_attn_mqa_bwd: tensors must be 16-byte aligned");
   cudaStream_t s = as_stream(stream);
+  {
+    const bool tc_ok = attn_bwd_tc_supported(*p) != 0;
+    if (p->impl == 2) DV_REQUIRE(tc_ok, DV_EUNSUPPORTED, "dv_attn_mqa_bwd: the tcgen05 kernel does not take these parameters (bf16, dh 32, n %% 128 == 0, lse from the forward)");
+    if (tc_ok && p->impl != 1) return attn_bwd_tc_launch(*p, s);
+  }
   const int64_t npairs = (int64_t)p->n * p->heads;
   dim3 g1((unsigned)((npairs + 127) / 128), (unsigned)p->S);
   int chunks = (int)((148 * 4 + p->S * ((p->n + 128) / 128) - 1) / (p->S * ((p->n + 128) / 128)));

@@ -307,6 +307,12 @@ class _TrainPlan:
             ws = torch.empty(ws_bytes, dtype=torch.uint8, device=self.device)
             self.keep.append(ws)
             ap.workspace, ap.workspace_bytes = ws.data_ptr(), ws_bytes
+        lse = None
+        if ws_bytes > 0:
+            # the tcgen05 forward also writes the log2-domain row log-sum-exp: the tensor-core backward starts from it
+            lse = torch.empty(x.rows * heads, device=self.device)
+            self.keep.append(lse)
+            ap.lse = lse.data_ptr()
         self.fwd.append(("dv_attn_mqa", ap))
         gnk = self._galloc(2, dh)
         self.grad_map.append((at.null_kv, lambda: self._g(gnk)))
@@ -317,7 +323,8 @@ class _TrainPlan:
         def backward():
             bp = L.AttnMqaBwdParams(q=q.ptr, kv=kvb.ptr, out=o.ptr, dout=o.grad.data_ptr(), dq=None, dkv=dkv32.data_ptr(),
                                     null_kv=nk.data_ptr(), dnull_kv=self._gptr(gnk), rowstats=None, S=B, n=P, heads=heads,
-                                    dh=dh, scale=float(1.0 / dh), dtype=self.code)
+                                    dh=dh, scale=float(1.0 / dh), dtype=self.code,
+                                    lse=lse.data_ptr() if lse is not None else None, impl=0)
             rs = torch.empty(L.lib().dv_attn_mqa_bwd_workspace_bytes(bp) // 4, device=self.device)
             self.keep.append(rs)
             dq, r1 = self._grad_target(q)

@@ -325,6 +325,9 @@ typedef struct {
   float scale;
   dv_dtype dtype;
   int impl;             /* 0 auto, 1 force CUDA-core kernel, 2 force tcgen05 kernel */
+  float* lse;           /* optional [S][n*heads] float32: log2-domain log-sum-exp of every (query, head) row
+                           (max + log2(sum), logits scaled by scale*log2(e)), written by the tcgen05 kernel only — what
+                           the tensor-core backward (dv_attn_mqa_bwd) starts from; NULL = not wanted */
 } dv_attn_mqa_params;
 int dv_attn_mqa(const dv_attn_mqa_params* p, dv_stream_t stream);
 /* scratch the tcgen05 path needs for these params (0 if it does not apply: bias, fp32, dh != 32, n % 128 != 0) */
@@ -560,6 +563,10 @@ typedef struct {
   int64_t S; int n, heads, dh;
   float scale;
   dv_dtype dtype;
+  const float* lse;     /* optional: the log2-domain row log-sum-exp dv_attn_mqa wrote (dv_attn_mqa_params.lse).  With it
+                           (bf16, dh 32, n % 128 == 0, 128 % heads == 0) the tcgen05 flash backward runs; NULL = the
+                           CUDA-core kernels, which recompute the row statistics */
+  int impl;             /* 0 auto, 1 CUDA-core kernels, 2 tcgen05 or DV_EUNSUPPORTED */
 } dv_attn_mqa_bwd_params;
 int dv_attn_mqa_bwd(const dv_attn_mqa_bwd_params* p, dv_stream_t stream);
 int64_t dv_attn_mqa_bwd_workspace_bytes(const dv_attn_mqa_bwd_params* p);

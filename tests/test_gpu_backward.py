@@ -246,6 +246,53 @@ def test_attn_mqa_backward_matches_autograd(dtype, S, n, heads):
     assert rel_err(dkv, kvr.grad) < tol and rel_err(dnull, null_kv.grad) < tol
 
 
+@pytest.mark.parametrize("S,n,heads", [(1, 128, 16), (2, 256, 16), (1, 1024, 16), (3, 128, 4)])
+def test_attn_mqa_backward_tcgen05_matches_autograd(S, n, heads):
+    """Flash backward on tcgen05 (attn_bwd_tc.cu): starts from the forward kernel's log-sum-exp, P^T / dS^T products read
+    the probability tiles MN-major.  Against torch autograd and the CUDA-core kernels on the same inputs."""
+    dtype, dh = torch.bfloat16, 32
+    q = rnd(S, n, heads * dh, dtype=dtype, seed=1, scale=2.0)
+    kv = rnd(S, n, 2 * dh, dtype=dtype, seed=2, scale=2.0)
+    dout = rnd(S, n, heads * dh, dtype=dtype, seed=3)
+    null_kv = rnd(2, dh, seed=4).requires_grad_()
+    scale = 1.0 / dh
+    qr, kvr = q.float().clone().requires_grad_(), kv.float().clone().requires_grad_()
+    qh = qr.reshape(S, n, heads, dh).permute(0, 2, 1, 3)
+    k = torch.cat((null_kv[0].expand(S, 1, dh), kvr[..., :dh]), dim=1)
+    v = torch.cat((null_kv[1].expand(S, 1, dh), kvr[..., dh:]), dim=1)
+    logits = torch.einsum("bhid,bjd->bhij", qh, k) * scale
+    ref = torch.einsum("bhij,bjd->bhid", logits.softmax(-1), v).permute(0, 2, 1, 3).reshape(S, n, heads * dh)
+    ref.backward(dout.float())
+    # forward through the tcgen05 kernel: out and the row log-sum-exp (log2 domain)
+    out = torch.empty_like(q)
+    lse = torch.empty(S, n * heads, device=dev())
+    fp = L.AttnMqaParams(q=ptr(q), kv=ptr(kv), out=ptr(out), null_kv=ptr(null_kv.detach()), bias=None, workspace=None,
+                         workspace_bytes=0, S=S, n=n, heads=heads, dh=dh, scale=scale, dtype=code(q), impl=2, lse=ptr(lse))
+    wsf = torch.empty(L.lib().dv_attn_mqa_workspace_bytes(fp), dtype=torch.uint8, device=dev())
+    fp.workspace, fp.workspace_bytes = ptr(wsf), wsf.numel()
+    L.call("dv_attn_mqa", fp, stream())
+    lse_ref = torch.logsumexp(logits.detach(), dim=-1).permute(0, 2, 1).reshape(S, n * heads) * math.log2(math.e)
+    assert float((lse - lse_ref).abs().max()) < 2e-2
+    res = {}
+    for impl in (2, 1):
+        dq = torch.empty_like(q)
+        dkv, dnull = torch.zeros(S, n, 2 * dh, device=dev()), torch.zeros(2, dh, device=dev())
+        p = L.AttnMqaBwdParams(q=ptr(q), kv=ptr(kv), out=ptr(out), dout=ptr(dout), dq=ptr(dq), dkv=ptr(dkv),
+                               null_kv=ptr(null_kv.detach()), dnull_kv=ptr(dnull), rowstats=None, S=S, n=n, heads=heads,
+                               dh=dh, scale=scale, dtype=code(q), lse=ptr(lse), impl=impl)
+        ws = torch.empty(L.lib().dv_attn_mqa_bwd_workspace_bytes(p) // 4, device=dev())
+        p.rowstats = ptr(ws)
+        L.call("dv_attn_mqa_bwd", p, stream())
+        res[impl] = (dq, dkv, dnull)
+    tol = TOL[dtype]
+    dq, dkv, dnull = res[2]
+    assert rel_err(dq, qr.grad) < tol, rel_err(dq, qr.grad)
+    assert rel_err(dkv[..., dh:], kvr.grad[..., dh:]) < tol, ("dv", rel_err(dkv[..., dh:], kvr.grad[..., dh:]))
+    assert rel_err(dkv[..., :dh], kvr.grad[..., :dh]) < tol, ("dk", rel_err(dkv[..., :dh], kvr.grad[..., :dh]))
+    assert rel_err(dnull, null_kv.grad) < tol
+    assert rel_err(dq, res[1][0].float()) < tol and rel_err(dkv, res[1][1]) < tol
+
+
 # ------------------------------------------------------------------ small passes
 @pytest.mark.parametrize("dtype", DT)
 def test_silu_shuffle_forward_and_backward(dtype):
