@@ -146,7 +146,7 @@ class LayerNormBwdParams(C.Structure):
 class XattnBwdParams(C.Structure):
     _fields_ = [("q", vp), ("dout", vp), ("dq", vp), ("kv", vp), ("dkv", vp), ("null_kv", vp), ("dnull_kv", vp),
                 ("B", i32), ("P", i64), ("heads", i32), ("dh", i32), ("n_ctx", i32), ("kv_ld", i64), ("k_off", i32),
-                ("v_off", i32), ("scale", f32), ("dtype", i32)]
+                ("v_off", i32), ("scale", f32), ("dtype", i32), ("impl", i32)]
 
 
 class AttnMqaBwdParams(C.Structure):

@@ -188,6 +188,8 @@ int attn_tc_launch(const dv_attn_mqa_params& p, cudaStream_t s);
 int64_t xattn_tc_workspace_bytes(const dv_xattn_params& p);
 int xattn_tc_supported(const dv_xattn_params& p);
 int xattn_tc_launch(const dv_xattn_params& p, cudaStream_t s);
+int xattn_fwd_short_supported(const dv_xattn_params& p);
+int xattn_fwd_short_launch(const dv_xattn_params& p, cudaStream_t s);
 
 }  // namespace dv
 
@@ -206,6 +208,12 @@ extern "C" int dv_xattn_core(const dv_xattn_params* p, dv_stream_t stream) {
   DV_REQUIRE(p->B > 0 && p->P > 0 && p->heads > 0 && p->n_ctx > 0, DV_EINVAL, "dv_xattn_core: bad dimensions");
   DV_REQUIRE(p->dh == 64, DV_EUNSUPPORTED, "dv_xattn_core: only dim_head=64 is built (got %d)", p->dh);
   DV_REQUIRE(aligned16(p->q) && aligned16(p->out), DV_EALIGN, "dv_xattn_core: q/out must be 16-byte aligned");
+  {
+    // short contexts (<= 16 keys incl. the null key): the tcgen05 kernel that keeps the keys in shared memory; needs no
+    // workspace.  DV_XATTN_DISABLE_SHORT_TC (debug aid) falls back to the CUDA-core kernel.
+    static const bool short_off = getenv("DV_XATTN_DISABLE_SHORT_TC") != nullptr;
+    if (!short_off && xattn_fwd_short_supported(*p)) return xattn_fwd_short_launch(*p, as_stream(stream));
+  }
   if (p->workspace) {
     DV_REQUIRE(xattn_tc_supported(*p), DV_EUNSUPPORTED,
                "dv_xattn_core: a workspace was passed but the tcgen05 kernel does not take these parameters "

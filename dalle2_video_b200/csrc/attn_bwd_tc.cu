@@ -344,6 +344,539 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Backward of the K5 core (CrossAttention over a SHORT context: n_ctx + 1 <= 16 keys per head, dh = 64) on tcgen05.
+// CTA = (sample, head, range of 128-token tiles); the keys are padded to 16 and live in shared memory for the whole CTA.
+//   MMA 1/2   S = Q K^T, dP = dO V^T                    (M=128 tokens, N=16 keys, K=64; K-major SW128)  -> TMEM [0,16), [16,32)
+//   threads   one token each: softmax over the valid keys (all keys are in the tile: no saved statistics needed),
+//             D = sum_j p_j dP_j, dS = scale p (dP - D); writes ONE 64-byte row [P(16) | dS(16)] (SWIZZLE_64B)
+//   MMA 3     [dV^T ; dK^T] += [dO ; Q]^T [P | dS]       (M=128 = two 64-channel atoms: the dO tile and the Q tile, LBO = their
+//             distance; N=32; K=128 tokens; all MN-major): the diagonal blocks of D are dV^T and dK^T      -> TMEM [32,64)
+//   MMA 4     dQ = dS K                                   (M=128 tokens, N=64, K=16 keys: one MMA; B = K tile MN-major) -> [64,128)
+//   threads   dQ rows -> bf16, stored (each (token, head) belongs to exactly one CTA: no atomics)
+// 128 TMEM columns and ~80 KB of shared memory per CTA: two CTAs per SM overlap their serial chains.
+constexpr int XB_THREADS = 192;
+constexpr int XB_STAGES = 2;
+
+struct XattnBwdTcParams {
+  dv_xattn_bwd_params a;     // pointers, offsets, scale
+  int tiles_per_seq;         // P / 128
+  int splits;
+};
+
+__global__ void __launch_bounds__(XB_THREADS, 2)
+xattn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_do,
+                    const XattnBwdTcParams pp) {
+  const dv_xattn_bwd_params& p = pp.a;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  constexpr int T_BYTES = 128 * 128;           // one [128 tokens][64] bf16 tile
+  uint8_t* k_s = smem;                         // [16 keys][128 B] SW128
+  uint8_t* v_s = k_s + 2048;
+  uint8_t* pd_s = v_s + 2048;                  // [128 tokens][64 B] = P(16) | dS(16), SW64   (8 KB)
+  uint8_t* qd_s = pd_s + 8192;                 // XB_STAGES x (dO_i, Q_i)   (dO first: the pair is ONE MN-major A operand)
+  qd_s = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(qd_s) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(qd_s + XB_STAGES * 2 * T_BYTES);
+  uint64_t* qd_full = bars;                    // [XB_STAGES]
+  uint64_t* qd_empty = qd_full + XB_STAGES;    // [XB_STAGES]
+  uint64_t* s_full = qd_empty + XB_STAGES;
+  uint64_t* p_ready = s_full + 1;              // 4 arrivals
+  uint64_t* dq_full = p_ready + 1;
+  uint64_t* dq_free = dq_full + 1;             // 4 arrivals
+  uint64_t* acc_done = dq_free + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_done + 1);
+  constexpr uint32_t C_S = 0, C_KV = 32, C_DQ = 64;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int split = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int nk = p.n_ctx + 1;
+  const int t_begin = pp.tiles_per_seq * split / pp.splits, t_end = pp.tiles_per_seq * (split + 1) / pp.splits;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_q);
+    tma_prefetch_desc(&map_do);
+    for (int s = 0; s < XB_STAGES; ++s) { mbar_init(&qd_full[s], 1); mbar_init(&qd_empty[s], 1); }
+    mbar_init(s_full, 1);
+    mbar_init(p_ready, 4);
+    mbar_init(dq_full, 1);
+    mbar_init(dq_free, 4);
+    mbar_init(acc_done, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(128u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  // K / V tiles: 16 key rows x 64 channels, bf16, SWIZZLE_128B; key 0 = the null key, rows >= nk zero
+  for (int i = threadIdx.x; i < 2 * 16 * 8; i += blockDim.x) {
+    const int which = i >> 7, j = (i >> 3) & 15, c8 = i & 7;
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = 0.f;
+    if (j == 0) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] = p.null_kv[which * 64 + c8 * 8 + e];
+    } else if (j < nk) {
+      const float* row = p.kv + ((int64_t)b * p.n_ctx + (j - 1)) * p.kv_ld + (which ? p.v_off : p.k_off) + h * 64 + c8 * 8;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] = row[e];
+    }
+    uint4 pk;
+    __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&pk);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) h2[e] = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
+    *reinterpret_cast<uint4*>((which ? v_s : k_s) + j * 128 + ((c8 ^ (j & 7)) * 16)) = pk;
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================================================================ TMA producer
+    if (elect_one()) {
+      int st = 0;
+      uint32_t ph = 0;
+      for (int t = t_begin; t < t_end; ++t) {
+        mbar_wait(&qd_empty[st], ph ^ 1);
+        uint8_t* dst = qd_s + st * 2 * T_BYTES;
+        mbar_expect_tx(&qd_full[st], 2 * T_BYTES);
+        const int tok = (int)((int64_t)b * p.P + (int64_t)t * 128);
+        asm volatile(
+            "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+            ::"r"(smem_u32(dst)), "l"(&map_do), "r"(smem_u32(&qd_full[st])), "r"(0), "r"(h), "r"(tok) : "memory");
+        asm volatile(
+            "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+            ::"r"(smem_u32(dst + T_BYTES)), "l"(&map_q), "r"(smem_u32(&qd_full[st])), "r"(0), "r"(h), "r"(tok) : "memory");
+        if (++st == XB_STAGES) { st = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================================================ MMA issuer
+    const uint32_t idesc_s = make_idesc_major(16, 0, 0);    // S, dP
+    const uint32_t idesc_t = make_idesc_major(32, 1, 1);    // [dV^T ; dK^T]
+    const uint32_t idesc_q = make_idesc_major(64, 0, 1);    // dQ
+    int st = 0;
+    uint32_t ph = 0;
+    for (int t = t_begin; t < t_end; ++t) {
+      const int it = t - t_begin;
+      mbar_wait(&qd_full[st], ph);
+      tc_fence_after();
+      const uint32_t do_a = smem_u32(qd_s + st * 2 * T_BYTES), q_a = do_a + T_BYTES;
+      if (elect_one()) {
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk)
+          umma_f16(tmem_base + C_S, make_smem_desc(q_a) + (uint64_t)(kk * 2), make_smem_desc(smem_u32(k_s)) + (uint64_t)(kk * 2),
+                   idesc_s, kk != 0);
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk)
+          umma_f16(tmem_base + C_S + 16, make_smem_desc(do_a) + (uint64_t)(kk * 2),
+                   make_smem_desc(smem_u32(v_s)) + (uint64_t)(kk * 2), idesc_s, kk != 0);
+        umma_commit(s_full);
+      }
+      __syncwarp();
+      mbar_wait(p_ready, (uint32_t)(it & 1));
+      if (it > 0) mbar_wait(dq_free, (uint32_t)((it - 1) & 1));
+      tc_fence_after();
+      if (elect_one()) {
+        // A = (dO tile, Q tile) as two 64-channel MN-major atoms; B = the [P | dS] rows (32 wide, MN-major SW64); K = tokens
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {
+          const uint64_t ad = make_desc_mn_sw128_b(do_a + (uint32_t)(kk * 2048), (uint32_t)T_BYTES);
+          const uint64_t bd = make_desc_mn_sw64(smem_u32(pd_s) + (uint32_t)(kk * 1024));
+          umma_f16(tmem_base + C_KV, ad, bd, idesc_t, (it | kk) != 0);
+        }
+        // dQ = dS K: A = the dS half of the rows (K-major SW64, 32 bytes in), B = K tile rows taken MN-major; K = 16 keys
+        {
+          const uint64_t ad = make_smem_desc_sw64(smem_u32(pd_s)) + 2;   // + 32 bytes: columns 16..31 of the [P | dS] rows
+          const uint64_t bd = make_desc_mn_sw128_b(smem_u32(k_s), 128u);
+          umma_f16(tmem_base + C_DQ, ad, bd, idesc_q, 0u);
+        }
+        umma_commit(&qd_empty[st]);
+        umma_commit(dq_full);
+        if (t + 1 == t_end) umma_commit(acc_done);
+      }
+      __syncwarp();
+      if (++st == XB_STAGES) { st = 0; ph ^= 1; }
+    }
+  } else if (t_begin < t_end) {
+    // ================================================================ token threads
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
+    __nv_bfloat16* dqp = reinterpret_cast<__nv_bfloat16*>(p.dq);
+    for (int t = t_begin; t < t_end; ++t) {
+      const int it = t - t_begin;
+      mbar_wait(s_full, (uint32_t)(it & 1));
+      tc_fence_after();
+      uint32_t r[32];
+      tmem_ld32(t_lane + C_S, r);   // S in [0,16), dP in [16,32)
+      float pd[32];                       // [0,16) probabilities, [16,32) dS: one 64-byte row of the B operand
+      float* pr = pd; float* ds = pd + 16;
+      float m = -CUDART_INF_F;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        pr[j] = __uint_as_float(r[j]) * p.scale;
+        if (j < nk) m = fmaxf(m, pr[j]);
+      }
+      float l = 0.f;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) { pr[j] = j < nk ? __expf(pr[j] - m) : 0.f; l += pr[j]; }
+      const float inv = 1.0f / l;
+      float D = 0.f;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) { pr[j] *= inv; D = fmaf(pr[j], __uint_as_float(r[16 + j]), D); }
+#pragma unroll
+      for (int j = 0; j < 16; ++j) ds[j] = pr[j] * (__uint_as_float(r[16 + j]) - D) * p.scale;
+      // the previous [P | dS] rows were consumed by the MMAs whose commit is dq_full (waited at the end of the last pass)
+      {
+        uint8_t* prow = pd_s + row * 64;
+        const int sw = (row >> 1) & 3;   // SWIZZLE_64B: 16-byte chunk index ^ address bits [7,9)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint4 pk;
+          __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&pk);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) h2[e] = __floats2bfloat162_rn(pd[c * 8 + 2 * e], pd[c * 8 + 2 * e + 1]);
+          *reinterpret_cast<uint4*>(prow + ((c ^ sw) * 16)) = pk;
+        }
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_ready);
+      mbar_wait(dq_full, (uint32_t)(it & 1));
+      tc_fence_after();
+      {
+        const int64_t tok = (int64_t)b * p.P + (int64_t)t * 128 + row;
+        __nv_bfloat16* dst = dqp + (tok * p.heads + h) * 64;
+#pragma unroll
+        for (int c0 = 0; c0 < 64; c0 += 32) {
+          uint32_t rq[32];
+          tmem_ld32(t_lane + C_DQ + (uint32_t)c0, rq);
+#pragma unroll
+          for (int e = 0; e < 32; e += 8) {
+            float v[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v[k] = __uint_as_float(rq[e + k]);
+            store8(dst + c0 + e, v);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(dq_free);
+    }
+    // [dV^T ; dK^T]: lanes 0..63 = channel d of dO (columns 0..15 = dV^T[d][j]), lanes 64..127 = channel d of Q (columns
+    // 16..31 = dK^T[d][j])
+    mbar_wait(acc_done, 0);
+    tc_fence_after();
+    {
+      uint32_t rk[32];
+      tmem_ld32(t_lane + C_KV, rk);
+      const int is_k = row >> 6, d = row & 63;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        if (j < nk) {
+          const float g = __uint_as_float(is_k ? rk[16 + j] : rk[j]);
+          if (j == 0) atomicAdd(p.dnull_kv + (is_k ? 0 : 64) + d, g);
+          else atomicAdd(p.dkv + ((int64_t)b * p.n_ctx + (j - 1)) * p.kv_ld + (is_k ? p.k_off : p.v_off) + h * 64 + d, g);
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(128u) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Forward of the K5 core for the same short contexts (<= 16 keys, dh = 64): the subset of the kernel above.
+//   MMA 1  S = Q K^T (N = 16)  ->  threads: softmax, P as bf16 into 64-byte rows  ->  MMA 2  O = P V (N = 64, K = 16, one MMA;
+//   B = V tile rows taken MN-major)  ->  threads: O rows -> bf16.  In place (out == q) is fine: a tile's Q is in shared
+//   memory before its O is written, and tiles do not overlap.
+struct XattnFwdTcParams {
+  dv_xattn_params a;
+  int tiles_per_seq, splits;
+};
+
+__global__ void __launch_bounds__(XB_THREADS, 2)
+xattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const XattnFwdTcParams pp) {
+  const dv_xattn_params& p = pp.a;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  constexpr int T_BYTES = 128 * 128;
+  constexpr int STAGES = 3;
+  uint8_t* k_s = smem;
+  uint8_t* v_s = k_s + 2048;
+  uint8_t* p_s = v_s + 2048;                   // [128 tokens][64 B]: P(16) | zeros, SW64
+  uint8_t* q_s = p_s + 8192;
+  q_s = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(q_s) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(q_s + STAGES * T_BYTES);
+  uint64_t* q_full = bars;                     // [STAGES]
+  uint64_t* q_empty = q_full + STAGES;         // [STAGES]
+  uint64_t* s_full = q_empty + STAGES;
+  uint64_t* p_ready = s_full + 1;              // 4 arrivals
+  uint64_t* o_full = p_ready + 1;
+  uint64_t* o_free = o_full + 1;               // 4 arrivals
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_free + 1);
+  constexpr uint32_t C_S = 0, C_O = 64;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int split = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int nk = p.n_ctx + 1;
+  const int t_begin = pp.tiles_per_seq * split / pp.splits, t_end = pp.tiles_per_seq * (split + 1) / pp.splits;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_q);
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&q_full[s], 1); mbar_init(&q_empty[s], 1); }
+    mbar_init(s_full, 1);
+    mbar_init(p_ready, 4);
+    mbar_init(o_full, 1);
+    mbar_init(o_free, 4);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(128u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  for (int i = threadIdx.x; i < 2 * 16 * 8; i += blockDim.x) {
+    const int which = i >> 7, j = (i >> 3) & 15, c8 = i & 7;
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = 0.f;
+    if (j == 0) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] = p.null_kv[which * 64 + c8 * 8 + e];
+    } else if (j < nk) {
+      const float* row = p.kv + ((int64_t)b * p.n_ctx + (j - 1)) * p.kv_ld + (which ? p.v_off : p.k_off) + h * 64 + c8 * 8;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] = row[e];
+    }
+    uint4 pk;
+    __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&pk);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) h2[e] = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
+    *reinterpret_cast<uint4*>((which ? v_s : k_s) + j * 128 + ((c8 ^ (j & 7)) * 16)) = pk;
+  }
+  for (int i = threadIdx.x; i < 8192 / 16; i += blockDim.x) reinterpret_cast<uint4*>(p_s)[i] = make_uint4(0u, 0u, 0u, 0u);
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      int st = 0;
+      uint32_t ph = 0;
+      for (int t = t_begin; t < t_end; ++t) {
+        mbar_wait(&q_empty[st], ph ^ 1);
+        mbar_expect_tx(&q_full[st], T_BYTES);
+        const int tok = (int)((int64_t)b * p.P + (int64_t)t * 128);
+        asm volatile(
+            "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+            ::"r"(smem_u32(q_s + st * T_BYTES)), "l"(&map_q), "r"(smem_u32(&q_full[st])), "r"(0), "r"(h), "r"(tok) : "memory");
+        if (++st == STAGES) { st = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    const uint32_t idesc_s = make_idesc_major(16, 0, 0);
+    const uint32_t idesc_o = make_idesc_major(64, 0, 1);
+    int st = 0;
+    uint32_t ph = 0;
+    for (int t = t_begin; t < t_end; ++t) {
+      const int it = t - t_begin;
+      mbar_wait(&q_full[st], ph);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t q_a = smem_u32(q_s + st * T_BYTES);
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk)
+          umma_f16(tmem_base + C_S, make_smem_desc(q_a) + (uint64_t)(kk * 2), make_smem_desc(smem_u32(k_s)) + (uint64_t)(kk * 2),
+                   idesc_s, kk != 0);
+        umma_commit(&q_empty[st]);   // Q is only needed for S
+        umma_commit(s_full);
+      }
+      __syncwarp();
+      mbar_wait(p_ready, (uint32_t)(it & 1));
+      if (it > 0) mbar_wait(o_free, (uint32_t)((it - 1) & 1));
+      tc_fence_after();
+      if (elect_one()) {
+        umma_f16(tmem_base + C_O, make_smem_desc_sw64(smem_u32(p_s)), make_desc_mn_sw128_b(smem_u32(v_s), 128u), idesc_o, 0u);
+        umma_commit(o_full);
+      }
+      __syncwarp();
+      if (++st == STAGES) { st = 0; ph ^= 1; }
+    }
+  } else if (t_begin < t_end) {
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
+    __nv_bfloat16* outp = reinterpret_cast<__nv_bfloat16*>(p.out);
+    for (int t = t_begin; t < t_end; ++t) {
+      const int it = t - t_begin;
+      mbar_wait(s_full, (uint32_t)(it & 1));
+      tc_fence_after();
+      uint32_t r[32];
+      tmem_ld32(t_lane + C_S, r);   // 16 logits (+ 16 unused columns)
+      float pr[16];
+      float m = -CUDART_INF_F;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        pr[j] = __uint_as_float(r[j]) * p.scale;
+        if (j < nk) m = fmaxf(m, pr[j]);
+      }
+      float l = 0.f;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) { pr[j] = j < nk ? __expf(pr[j] - m) : 0.f; l += pr[j]; }
+      const float inv = 1.0f / l;
+      // the previous P rows were consumed by the MMA whose commit is o_full (waited at the end of the last pass)
+      {
+        uint8_t* prow = p_s + row * 64;
+        const int sw = (row >> 1) & 3;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          uint4 pk;
+          __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&pk);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) h2[e] = __floats2bfloat162_rn(pr[c * 8 + 2 * e] * inv, pr[c * 8 + 2 * e + 1] * inv);
+          *reinterpret_cast<uint4*>(prow + ((c ^ sw) * 16)) = pk;
+        }
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_ready);
+      mbar_wait(o_full, (uint32_t)(it & 1));
+      tc_fence_after();
+      {
+        const int64_t tok = (int64_t)b * p.P + (int64_t)t * 128 + row;
+        __nv_bfloat16* dst = outp + (tok * p.heads + h) * 64;
+#pragma unroll
+        for (int c0 = 0; c0 < 64; c0 += 32) {
+          uint32_t ro[32];
+          tmem_ld32(t_lane + C_O + (uint32_t)c0, ro);
+#pragma unroll
+          for (int e = 0; e < 32; e += 8) {
+            float v[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v[k] = __uint_as_float(ro[e + k]);
+            store8(dst + c0 + e, v);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(o_free);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(128u) : "memory");
+  }
+}
+
+int xattn_fwd_short_supported(const dv_xattn_params& p) {
+  if (p.dtype != DV_BF16 || p.dh != 64 || p.n_ctx + 1 > 16 || p.n_ctx < 1) return 0;
+  if (p.P <= 0 || p.P % 128 || p.heads <= 0 || p.heads > 65535 || p.B > 65535) return 0;
+  if ((int64_t)p.B * p.P >= (1ll << 31)) return 0;
+  if ((reinterpret_cast<uintptr_t>(p.q) | reinterpret_cast<uintptr_t>(p.out)) & 15) return 0;
+  return 1;
+}
+
+int xattn_fwd_short_launch(const dv_xattn_params& p, cudaStream_t s) {
+  XattnFwdTcParams k;
+  memset(&k, 0, sizeof(k));
+  k.a = p;
+  k.tiles_per_seq = (int)(p.P / 128);
+  static int sm_count = 0;
+  if (!sm_count) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
+    if (sm_count <= 0) sm_count = 148;
+  }
+  int splits = 2 * sm_count / (p.B * p.heads);
+  if (splits < 1) splits = 1;
+  if (splits > k.tiles_per_seq) splits = k.tiles_per_seq;
+  k.splits = splits;
+  CUtensorMap mq;
+  {
+    uint64_t dims[3] = {64, (uint64_t)p.heads, (uint64_t)p.B * p.P};
+    uint64_t strides[2] = {128, (uint64_t)p.heads * 128};
+    uint32_t box[3] = {64, 1, 128};
+    int rc = encode_map(&mq, p.q, 3, dims, strides, box, 128);
+    if (rc != DV_OK) return rc;
+  }
+  const size_t smem = 2048 + 2048 + 8192 + 1024 + 3 * 16384 + 256 + 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(xattn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    DV_REQUIRE(e == cudaSuccess, DV_ECUDA, "dv_xattn_core(tcgen05, short): cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  dim3 grid((unsigned)splits, (unsigned)p.heads, (unsigned)p.B);
+  xattn_fwd_tc_kernel<<<grid, XB_THREADS, smem, s>>>(mq, k);
+  DV_CHECK_LAUNCH("dv_xattn_core(tcgen05, short)");
+  return DV_OK;
+}
+
+int xattn_bwd_tc_supported(const dv_xattn_bwd_params& p) {
+  if (p.dtype != DV_BF16 || p.dh != 64 || p.n_ctx + 1 > 16 || p.n_ctx < 1) return 0;
+  if (p.P <= 0 || p.P % 128 || p.heads <= 0 || p.heads > 65535 || p.B > 65535) return 0;
+  if ((int64_t)p.B * p.P >= (1ll << 31)) return 0;
+  return 1;
+}
+
+int xattn_bwd_tc_launch(const dv_xattn_bwd_params& p, cudaStream_t s) {
+  XattnBwdTcParams k;
+  memset(&k, 0, sizeof(k));
+  k.a = p;
+  k.tiles_per_seq = (int)(p.P / 128);
+  static int sm_count = 0;
+  if (!sm_count) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
+    if (sm_count <= 0) sm_count = 148;
+  }
+  int splits = 2 * sm_count / (p.B * p.heads);
+  if (splits < 1) splits = 1;
+  if (splits > k.tiles_per_seq) splits = k.tiles_per_seq;
+  k.splits = splits;
+  CUtensorMap mq, mdo;
+  int rc;
+  {
+    uint64_t dims[3] = {64, (uint64_t)p.heads, (uint64_t)p.B * p.P};
+    uint64_t strides[2] = {128, (uint64_t)p.heads * 128};
+    uint32_t box[3] = {64, 1, 128};
+    if ((rc = encode_map(&mq, p.q, 3, dims, strides, box, 128)) != DV_OK) return rc;
+    if ((rc = encode_map(&mdo, p.dout, 3, dims, strides, box, 128)) != DV_OK) return rc;
+  }
+  const size_t smem = 2048 + 2048 + 8192 + 1024 + XB_STAGES * 2 * 16384 + 256 + 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(xattn_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    DV_REQUIRE(e == cudaSuccess, DV_ECUDA, "dv_xattn_core_bwd(tcgen05): cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  dim3 grid((unsigned)splits, (unsigned)p.heads, (unsigned)p.B);
+  xattn_bwd_tc_kernel<<<grid, XB_THREADS, smem, s>>>(mq, mdo, k);
+  DV_CHECK_LAUNCH("dv_xattn_core_bwd(tcgen05)");
+  return DV_OK;
+}
+
 // ---------------------------------------------------------------------------------------------------------- host side
 int attn_bwd_tc_supported(const dv_attn_mqa_bwd_params& p) {
   if (p.dtype != DV_BF16 || p.dh != AB_DH || !p.lse) return 0;

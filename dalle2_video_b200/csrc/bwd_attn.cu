@@ -331,6 +331,8 @@ __global__ void __launch_bounds__(128) attn_mqa_bwd_dkv_kernel(dv_attn_mqa_bwd_p
   }
 }
 
+int xattn_bwd_tc_supported(const dv_xattn_bwd_params& p);
+int xattn_bwd_tc_launch(const dv_xattn_bwd_params& p, cudaStream_t s);
 int attn_bwd_tc_supported(const dv_attn_mqa_bwd_params& p);
 int64_t attn_bwd_tc_workspace_bytes(const dv_attn_mqa_bwd_params& p);
 int attn_bwd_tc_launch(const dv_attn_mqa_bwd_params& p, cudaStream_t s);
@@ -343,6 +345,11 @@ extern "C" int dv_xattn_core_bwd(const dv_xattn_bwd_params* p, dv_stream_t strea
              "dv_xattn_core_bwd: null pointer");
   DV_REQUIRE(p->B > 0 && p->P > 0 && p->heads > 0 && p->n_ctx > 0, DV_EINVAL, "dv_xattn_core_bwd: bad dimensions");
   DV_REQUIRE(p->dh == 64, DV_EUNSUPPORTED, "dv_xattn_core_bwd: only dim_head=64 is built (got %d)", p->dh);
+  {
+    const bool tc_ok = xattn_bwd_tc_supported(*p) != 0 && aligned16(p->q) && aligned16(p->dout) && aligned16(p->dq);
+    if (p->impl == 2) DV_REQUIRE(tc_ok, DV_EUNSUPPORTED, "dv_xattn_core_bwd: the tcgen05 kernel does not take these parameters (bf16, dh 64, P %% 128 == 0, <= 16 keys)");
+    if (tc_ok && p->impl != 1) return xattn_bwd_tc_launch(*p, as_stream(stream));
+  }
   DV_REQUIRE(p->n_ctx + 1 <= 8, DV_EUNSUPPORTED,
              "dv_xattn_core_bwd: contexts longer than 7 tokens (text conditioning) have no backward kernel yet (n_ctx=%d)", p->n_ctx);
   DV_REQUIRE(aligned16(p->q) && aligned16(p->dout) && aligned16(p->dq), DV_EALIGN, "dv_xattn_core_bwd: tensors must be 16-byte aligned");

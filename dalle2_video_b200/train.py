@@ -276,7 +276,8 @@ class _TrainPlan:
         nk = self._f32(lambda: ca.null_kv.detach().float())
         common = dict(B=self.B, P=P, heads=heads, dh=dh, n_ctx=n_ctx, kv_ld=kv.shape[2], k_off=idx * 2 * inner,
                       v_off=idx * 2 * inner + inner, scale=float(dh ** -0.5), dtype=self.code)
-        self.fwd.append(("dv_xattn_core", L.XattnParams(q=q.ptr, out=o.ptr, kv=kv.data_ptr(), null_kv=nk.data_ptr(), **common)))
+        xp = L.XattnParams(q=q.ptr, out=o.ptr, kv=kv.data_ptr(), null_kv=nk.data_ptr(), workspace=None, workspace_bytes=0, **common)
+        self.fwd.append(("dv_xattn_core", xp))   # <= 16 keys: the shared-memory-resident tcgen05 kernel (no workspace)
         gnk = self._galloc(2, dh)
         self.grad_map.append((ca.null_kv, lambda: self._g(gnk)))
 

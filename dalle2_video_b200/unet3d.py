@@ -973,8 +973,9 @@ class _Engine:
                            v_off=idx * 2 * inner + inner, scale=float(dh ** -0.5), dtype=self.code, workspace=None,
                            workspace_bytes=0)
         ws = None
-        if n_ctx + 1 > 8:
-            # long (text) context: flash kernel on tcgen05 over packed bf16 K / V^T (include/dv_b200.h, "K5 core")
+        if n_ctx + 1 > 16:
+            # long (text) context: flash kernel on tcgen05 over packed bf16 K / V^T (include/dv_b200.h, "K5 core"); short
+            # contexts take the shared-memory-resident tcgen05 kernel inside dv_xattn_core, which needs no workspace
             ws_bytes = L.lib().dv_xattn_core_workspace_bytes(xp)
             if ws_bytes > 0:
                 ws = self.pool.get(ws_bytes)

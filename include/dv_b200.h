@@ -550,6 +550,7 @@ typedef struct {
   int64_t kv_ld; int k_off, v_off;
   float scale;
   dv_dtype dtype;
+  int impl;   /* 0 auto (tcgen05 for bf16, dh 64, P % 128 == 0, n_ctx + 1 <= 16), 1 CUDA-core kernel, 2 tcgen05 or error */
 } dv_xattn_bwd_params;
 int dv_xattn_core_bwd(const dv_xattn_bwd_params* p, dv_stream_t stream);
 

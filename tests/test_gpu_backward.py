@@ -216,6 +216,46 @@ def test_xattn_core_backward_matches_autograd(dtype):
     assert rel_err(dkv, kv.grad) < max(tol, 2e-4) and rel_err(dnull, null_kv.grad) < max(tol, 2e-4)
 
 
+@pytest.mark.parametrize("B,P,heads,n_ctx", [(2, 256, 8, 6), (1, 1024, 8, 6), (3, 128, 4, 2), (2, 384, 8, 15)])
+def test_xattn_core_backward_tcgen05_matches_autograd(B, P, heads, n_ctx):
+    """tcgen05 backward of the short-context CrossAttention core (attn_bwd_tc.cu::xattn_bwd_tc_kernel) against torch autograd
+    and the CUDA-core kernel."""
+    dtype, dh, n_layers = torch.bfloat16, 64, 2
+    inner = heads * dh
+    q = rnd(B, P, inner, dtype=dtype, seed=1)
+    dout = rnd(B, P, inner, dtype=dtype, seed=2)
+    kv = rnd(B, n_ctx, n_layers * 2 * inner, seed=3).requires_grad_()
+    null_kv = rnd(2, dh, seed=4).requires_grad_()
+    k_off, v_off = 2 * inner, 3 * inner
+    qr = q.float().clone().requires_grad_()
+    qh = qr.reshape(B, P, heads, dh).permute(0, 2, 1, 3)
+    k = kv[..., k_off:k_off + inner].reshape(B, n_ctx, heads, dh).permute(0, 2, 1, 3)
+    v = kv[..., v_off:v_off + inner].reshape(B, n_ctx, heads, dh).permute(0, 2, 1, 3)
+    k = torch.cat((null_kv[0].expand(B, heads, 1, dh), k), dim=2)
+    v = torch.cat((null_kv[1].expand(B, heads, 1, dh), v), dim=2)
+    scale = dh ** -0.5
+    out = ((qh @ k.transpose(-1, -2)) * scale).softmax(-1) @ v
+    out.permute(0, 2, 1, 3).reshape(B, P, inner).backward(dout.float())
+    res = {}
+    for impl in ((2, 1) if n_ctx + 1 <= 8 else (2,)):
+        dq = torch.full_like(q, 7.0)
+        dkv, dnull = torch.zeros_like(kv), torch.zeros_like(null_kv)
+        L.call("dv_xattn_core_bwd", L.XattnBwdParams(q=ptr(q), dout=ptr(dout), dq=ptr(dq), kv=ptr(kv.detach()), dkv=ptr(dkv),
+                                                      null_kv=ptr(null_kv.detach()), dnull_kv=ptr(dnull), B=B, P=P,
+                                                      heads=heads, dh=dh, n_ctx=n_ctx, kv_ld=kv.shape[-1], k_off=k_off,
+                                                      v_off=v_off, scale=scale, dtype=code(q), impl=impl), stream())
+        res[impl] = (dq, dkv, dnull)
+    tol = TOL[dtype]
+    dq, dkv, dnull = res[2]
+    assert rel_err(dq, qr.grad) < tol, rel_err(dq, qr.grad)
+    assert rel_err(dkv[..., v_off:v_off + inner], kv.grad[..., v_off:v_off + inner]) < tol, "dv"
+    assert rel_err(dkv[..., k_off:k_off + inner], kv.grad[..., k_off:k_off + inner]) < tol, "dk"
+    assert rel_err(dnull, null_kv.grad) < tol
+    assert float(dkv[..., :k_off].abs().max()) == 0.0          # other layers' slots untouched
+    if 1 in res:
+        assert rel_err(dq, res[1][0].float()) < tol and rel_err(dkv, res[1][1]) < tol
+
+
 @pytest.mark.parametrize("dtype", DT)
 @pytest.mark.parametrize("S,n,heads", [(2, 192, 16), (1, 70, 4)])
 def test_attn_mqa_backward_matches_autograd(dtype, S, n, heads):
