@@ -329,7 +329,7 @@ def run_gpu_arm(args):
                                              "algorithmic_bytes": 2.0 * 2 * B * FRAMES * SIZE * SIZE * 64},
                          "traffic": traffic,
                          "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant launch shape, "
-                                         "one ncu --set full capture (profiles/r01_ncu_full_s3_summary.txt); null for batches "
+                                         "one ncu --set full capture (profiles/ncu_traffic.json names the summaries); null for batches "
                                          "that were not captured"},
             "cpu_baseline": cpu,
         }
