@@ -114,6 +114,14 @@ class ToOutParams(C.Structure):
                 ("dtype", i32), ("extra", vp), ("Cextra", i32)]
 
 
+class PatchifyParams(C.Structure):
+    _fields_ = [("x", vp), ("out", vp), ("frames", i64), ("C", i32), ("H", i32), ("W", i32), ("patch", i32)]
+
+
+class MhaSmallParams(C.Structure):
+    _fields_ = [("qkv", vp), ("out", vp), ("S", i64), ("n", i32), ("heads", i32), ("dh", i32), ("scale", f32)]
+
+
 class ResizeNearestParams(C.Structure):
     _fields_ = [("in_", vp), ("out", vp), ("planes", i64), ("Hin", i32), ("Win", i32), ("Hout", i32), ("Wout", i32),
                 ("clamp", i32), ("lo", f32), ("hi", f32)]
@@ -201,6 +209,7 @@ ENTRY_POINTS = {
     "dv_time_embed": TimeEmbedParams, "dv_linear_small": LinearSmallParams,
     "dv_cond_tokens": CondTokensParams, "dv_to_out": ToOutParams, "dv_im2col_init": Im2colParams,
     "dv_init_conv": InitConvParams, "dv_resize_nearest": ResizeNearestParams,
+    "dv_patchify": PatchifyParams, "dv_mha_small": MhaSmallParams,
     # training step (a16)
     "dv_conv_wgrad": ConvWgradParams, "dv_colsum": ColsumParams, "dv_gn_bwd_reduce": GnBwdParams,
     "dv_gn_bwd_apply": GnBwdParams, "dv_layernorm_bwd": LayerNormBwdParams, "dv_xattn_core_bwd": XattnBwdParams,

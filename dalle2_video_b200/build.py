@@ -8,7 +8,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libdv_b200.so")
-SOURCES = ["api.cu", "ddpm_step.cu", "conv_simt.cu", "conv_tc.cu", "conv_halo.cu", "norm.cu", "attention.cu", "attn_tc.cu", "attn_temporal.cu", "xattn_fold.cu", "cond.cu", "im2col.cu", "init_conv_tc.cu", "init_conv_rs.cu", "bwd_conv.cu", "wgrad_tc.cu", "bwd_norm.cu", "bwd_attn.cu", "attn_bwd_tc.cu", "train_misc.cu"]
+SOURCES = ["api.cu", "ddpm_step.cu", "conv_simt.cu", "conv_tc.cu", "conv_halo.cu", "norm.cu", "attention.cu", "attn_tc.cu", "attn_temporal.cu", "xattn_fold.cu", "cond.cu", "im2col.cu", "init_conv_tc.cu", "init_conv_rs.cu", "bwd_conv.cu", "wgrad_tc.cu", "bwd_norm.cu", "bwd_attn.cu", "attn_bwd_tc.cu", "train_misc.cu", "vivit.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-shared", "-Xcompiler", "-fPIC", "--threads", "0"]
 

@@ -212,8 +212,10 @@ static int launch_ln(const dv_layernorm_params& p, cudaStream_t s) {
     layernorm_kernel<T, 1><<<blocks, wpb * 32, 0, s>>>(p);
   else if (p.C <= 512)
     layernorm_kernel<T, 4><<<blocks, wpb * 32, 0, s>>>(p);
-  else
+  else if (p.C <= 1024)
     layernorm_kernel<T, 8><<<blocks, wpb * 32, 0, s>>>(p);
+  else
+    layernorm_kernel<T, 32><<<blocks, wpb * 32, 0, s>>>(p);   // up to 4096 channels (ViViT's flattened to_out LayerNorm)
   DV_CHECK_LAUNCH("dv_layernorm");
   return DV_OK;
 }
@@ -280,8 +282,8 @@ extern "C" int dv_gn_apply(const dv_gn_apply_params* p, dv_stream_t stream) {
 extern "C" int dv_layernorm(const dv_layernorm_params* p, dv_stream_t stream) {
   using namespace dv;
   DV_REQUIRE(p && p->x && p->out && p->g, DV_EINVAL, "dv_layernorm: null pointer");
-  DV_REQUIRE(p->rows > 0 && p->C > 0 && p->C % 4 == 0 && p->C <= 1024, DV_EUNSUPPORTED,
-             "dv_layernorm: needs C %% 4 == 0 and C <= 1024 (C=%d)", p->C);
+  DV_REQUIRE(p->rows > 0 && p->C > 0 && p->C % 4 == 0 && p->C <= 4096, DV_EUNSUPPORTED,
+             "dv_layernorm: needs C %% 4 == 0 and C <= 4096 (C=%d)", p->C);
   DV_REQUIRE(aligned16(p->x) && aligned16(p->out) && aligned16(p->residual), DV_EALIGN,
              "dv_layernorm: tensors must be 16-byte aligned");
   if (p->dtype == DV_BF16) DV_REQUIRE(p->C % 8 == 0, DV_EALIGN, "dv_layernorm: bf16 rows need C %% 8 == 0");

@@ -471,6 +471,30 @@ int dv_init_conv(const dv_init_conv_params* p, dv_stream_t stream);
 int dv_init_conv_supported(const dv_init_conv_params* p);
 
 /* ================================================================================================
+ * N4 — ViViT video-encoder forward (/root/reference/dalle2_video/video_encoder.py:99-169).
+ * float32.  The Linears / GELU / residual adds run on dv_linear_small, the LayerNorms on dv_layernorm.
+ */
+/* Rearrange "b t c (h p1) (w p2) -> b t (h w) (p1 p2 c)" (:121-123): x (frames, C, H, W) -> out [frames*h*w][patch*patch*C] */
+typedef struct {
+  const float* x;
+  float* out;
+  int64_t frames;   /* b*t */
+  int C, H, W, patch;
+} dv_patchify_params;
+int dv_patchify(const dv_patchify_params* p, dv_stream_t stream);
+
+/* Attention.forward between to_qkv and to_out (:58-69): out[s][i][h*dh+d] = softmax_j(scale q_i.k_j) v_j per (sequence, head);
+ * qkv: [S][n][3*heads*dh] = q | k | v, each (heads dh) as the reference chunks and rearranges them. */
+typedef struct {
+  const float* qkv;
+  float* out;       /* [S][n][heads*dh] */
+  int64_t S;
+  int n, heads, dh;
+  float scale;
+} dv_mha_small_params;
+int dv_mha_small(const dv_mha_small_params* p, dv_stream_t stream);
+
+/* ================================================================================================
  * a16 — decoder TRAINING step (/root/reference/dalle2_video/dalle2_video.py:1908-2006,
  * dalle2_video/trainer.py:322-365, :247-274).  The reference gets its backward pass from torch autograd over the
  * modules above; these entry points are the hand-written backward of each forward kernel.  The data-gradient of a

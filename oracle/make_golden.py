@@ -166,9 +166,54 @@ def cascade():
         json.dump(layouts, f, indent=0, sort_keys=True)
 
 
+VIVIT_CASES = {
+    # the reference's own encoder class on small shapes (same block structure as configs/celebv-text.yaml:31-36)
+    "small": dict(kw=dict(frame_size=32, patch_size=8, num_frames=25, dim=64, depth=2, heads=3, in_channels=3), batch=2),
+    # dim 512 / depth 2 as shipped; 50 frames of 56x56 (4x4 patches of 14) keep the fixture small; to_out LayerNorm over 1024
+    "dim512": dict(kw=dict(frame_size=56, patch_size=14, num_frames=50, dim=512, depth=2, heads=3, in_channels=3), batch=1),
+}
+
+
+def vivit():
+    """Scope row N4: `python -m oracle.make_golden vivit`.  Runs the reference's ViViT (dalle2_video/video_encoder.py,
+    imported from where it lies: it needs only torch + einops) on seeded inputs with synthetic weights; the fixture keeps
+    the state_dict layout, the seeds and the output (inputs are regenerated from the seed)."""
+    import importlib.util
+    path = os.path.join(reference.REFERENCE_ROOT, "dalle2_video", "video_encoder.py")
+    spec = importlib.util.spec_from_file_location("_reference_video_encoder", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    for name, case in VIVIT_CASES.items():
+        torch.manual_seed(0)
+        enc = mod.ViViT(**case["kw"]).eval()
+        layout = shapes_of(enc)
+        sd = synth_state_dict(layout, seed=13)
+        enc.load_state_dict(sd, strict=True)
+        kw = case["kw"]
+        g = torch.Generator().manual_seed(61)
+        x = torch.randn(case["batch"], kw["num_frames"], 3, kw["frame_size"], kw["frame_size"], generator=g)
+        with torch.no_grad():
+            out = enc(x.clone())
+        assert bool(torch.isfinite(out).all())
+        torch.save({"kwargs": kw, "layout": layout, "weight_seed": 13, "input_seed": 61, "batch": case["batch"],
+                    "out": out}, os.path.join(GOLDEN, f"vivit_{name}.pt"))
+        print("vivit", name, tuple(out.shape), float(out.abs().mean()))
+
+
+def vivit_fixture_inputs(g):
+    """Weights and input of a vivit_*.pt fixture, regenerated from its seeds (shared by the CPU and GPU tests)."""
+    sd = synth_state_dict(g["layout"], seed=g["weight_seed"])
+    kw = g["kwargs"]
+    gen = torch.Generator().manual_seed(g["input_seed"])
+    x = torch.randn(g["batch"], kw["num_frames"], 3, kw["frame_size"], kw["frame_size"], generator=gen)
+    return sd, x
+
+
 if __name__ == "__main__":
     import sys
-    if len(sys.argv) > 1 and sys.argv[1] == "cascade":
+    if len(sys.argv) > 1 and sys.argv[1] == "vivit":
+        vivit()
+    elif len(sys.argv) > 1 and sys.argv[1] == "cascade":
         cascade()
     else:
         main()
