@@ -318,8 +318,10 @@ __global__ void __launch_bounds__(256, 2) gn_bwd_apply_fast_kernel(dv_gn_bwd_par
 
 // ---------------------------------------------------------------- LayerNorm backward (gain only), one warp per row
 //   y = xh * g ;  h = dy*g ;  dx = rstd * (h - mean(h) - xh*mean(h*xh)) ;  dg += sum_rows dy*xh
-template <typename T, int MAXV>
+template <typename T, int MAXV, int R>
 __global__ void __launch_bounds__(256) layernorm_bwd_kernel(dv_layernorm_bwd_params p) {
+  // R rows per warp and iteration: their loads are issued together and their four reduction chains interleave, so the
+  // per-row latency (global loads + 4 dependent warp reductions) is shared by R rows
   __shared__ float sdg[1024];  // per-CTA reduction of dg before the global atomics
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
@@ -330,64 +332,88 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(dv_layernorm_bwd_par
   for (int i = 0; i < MAXV; ++i)
 #pragma unroll
     for (int k = 0; k < 4; ++k) dg[i][k] = 0.f;
-  for (int64_t row = (int64_t)blockIdx.x * wpb + (threadIdx.x >> 5); row < p.rows; row += (int64_t)gridDim.x * wpb) {
-    const T* x = reinterpret_cast<const T*>(p.x) + row * p.C;
-    const T* dy = reinterpret_cast<const T*>(p.dy) + row * p.C;
-    float v[MAXV][4], h[MAXV][4];
-    float s = 0.f;
+  const float invC = 1.0f / (float)p.C;
+  for (int64_t row0 = ((int64_t)blockIdx.x * wpb + (threadIdx.x >> 5)) * R; row0 < p.rows;
+       row0 += (int64_t)gridDim.x * wpb * R) {
+    float v[R][MAXV][4], h[R][MAXV][4];
+    float s[R];
 #pragma unroll
-    for (int i = 0; i < MAXV; ++i) {
-      const int c = (i * 32 + lane) * 4;
-      if (c < p.C) {
-        load4(x + c, v[i]);
-        load4(dy + c, h[i]);
-        s += v[i][0] + v[i][1] + v[i][2] + v[i][3];
-      }
-    }
-    const float mean = warp_sum(s) / (float)p.C;
-    float q = 0.f;
+    for (int r = 0; r < R; ++r) {
+      s[r] = 0.f;
+      const bool live = row0 + r < p.rows;
+      const T* x = reinterpret_cast<const T*>(p.x) + (row0 + r) * p.C;
+      const T* dy = reinterpret_cast<const T*>(p.dy) + (row0 + r) * p.C;
 #pragma unroll
-    for (int i = 0; i < MAXV; ++i) {
-      const int c = (i * 32 + lane) * 4;
-      if (c < p.C) {
+      for (int i = 0; i < MAXV; ++i) {
+        const int c = (i * 32 + lane) * 4;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) { const float d = v[i][k] - mean; q += d * d; }
-      }
-    }
-    const float rstd = rsqrtf(warp_sum(q) / (float)p.C + p.eps);
-    float m1 = 0.f, m2 = 0.f;
-#pragma unroll
-    for (int i = 0; i < MAXV; ++i) {
-      const int c = (i * 32 + lane) * 4;
-      if (c < p.C) {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const float xh = (v[i][k] - mean) * rstd;
-          dg[i][k] = fmaf(h[i][k], xh, dg[i][k]);
-          h[i][k] *= p.g[c + k];
-          v[i][k] = xh;
-          m1 += h[i][k];
-          m2 = fmaf(h[i][k], xh, m2);
+        for (int k = 0; k < 4; ++k) { v[r][i][k] = 0.f; h[r][i][k] = 0.f; }
+        if (live && c < p.C) {
+          load4(x + c, v[r][i]);
+          load4(dy + c, h[r][i]);
+          s[r] += v[r][i][0] + v[r][i][1] + v[r][i][2] + v[r][i][3];
         }
       }
     }
-    m1 = warp_sum(m1) / (float)p.C;
-    m2 = warp_sum(m2) / (float)p.C;
-    T* dx = reinterpret_cast<T*>(p.dx) + row * p.C;
+    float mean[R], q[R];
 #pragma unroll
-    for (int i = 0; i < MAXV; ++i) {
-      const int c = (i * 32 + lane) * 4;
-      if (c < p.C) {
-        float o[4];
+    for (int r = 0; r < R; ++r) mean[r] = warp_sum(s[r]) * invC;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) o[k] = rstd * (h[i][k] - m1 - v[i][k] * m2);
-        if (p.accumulate) {
-          float prev[4];
-          load4(dx + c, prev);
+    for (int r = 0; r < R; ++r) {
+      q[r] = 0.f;
 #pragma unroll
-          for (int k = 0; k < 4; ++k) o[k] += prev[k];
+      for (int i = 0; i < MAXV; ++i) {
+        const int c = (i * 32 + lane) * 4;
+        if (c < p.C) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) { const float d = v[r][i][k] - mean[r]; q[r] += d * d; }
         }
-        store4(dx + c, o);
+      }
+    }
+    float rstd[R], m1[R], m2[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) rstd[r] = rsqrtf(warp_sum(q[r]) * invC + p.eps);
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      m1[r] = 0.f; m2[r] = 0.f;
+      const bool live = row0 + r < p.rows;
+#pragma unroll
+      for (int i = 0; i < MAXV; ++i) {
+        const int c = (i * 32 + lane) * 4;
+        if (live && c < p.C) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float xh = (v[r][i][k] - mean[r]) * rstd[r];
+            dg[i][k] = fmaf(h[r][i][k], xh, dg[i][k]);
+            h[r][i][k] *= p.g[c + k];
+            v[r][i][k] = xh;
+            m1[r] += h[r][i][k];
+            m2[r] = fmaf(h[r][i][k], xh, m2[r]);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) { m1[r] = warp_sum(m1[r]) * invC; m2[r] = warp_sum(m2[r]) * invC; }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      if (row0 + r >= p.rows) continue;
+      T* dx = reinterpret_cast<T*>(p.dx) + (row0 + r) * p.C;
+#pragma unroll
+      for (int i = 0; i < MAXV; ++i) {
+        const int c = (i * 32 + lane) * 4;
+        if (c < p.C) {
+          float o[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) o[k] = rstd[r] * (h[r][i][k] - m1[r] - v[r][i][k] * m2[r]);
+          if (p.accumulate) {
+            float prev[4];
+            load4(dx + c, prev);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) o[k] += prev[k];
+          }
+          store4(dx + c, o);
+        }
       }
     }
   }
@@ -490,14 +516,17 @@ extern "C" int dv_layernorm_bwd(const dv_layernorm_bwd_params* p, dv_stream_t st
   DV_REQUIRE(aligned16(p->x) && aligned16(p->dy) && aligned16(p->dx), DV_EALIGN, "dv_layernorm_bwd: tensors must be 16-byte aligned");
   if (p->dtype == DV_BF16) DV_REQUIRE(p->C % 8 == 0, DV_EALIGN, "dv_layernorm_bwd: bf16 rows need C %% 8 == 0");
   const int wpb = 8;
-  int64_t blocks = (p->rows + wpb - 1) / wpb;
-  if (blocks > 148 * 4) blocks = 148 * 4;
   cudaStream_t s = as_stream(stream);
-#define DV_LNB(T, V) layernorm_bwd_kernel<T, V><<<(unsigned)blocks, wpb * 32, 0, s>>>(*p)
+#define DV_LNB(T, V, R)                                                   \
+  do {                                                                    \
+    int64_t blocks = (p->rows + wpb * R - 1) / (wpb * R);                 \
+    if (blocks > 148 * 4) blocks = 148 * 4;                               \
+    layernorm_bwd_kernel<T, V, R><<<(unsigned)blocks, wpb * 32, 0, s>>>(*p); \
+  } while (0)
   if (p->dtype == DV_F32) {
-    if (p->C <= 128) DV_LNB(float, 1); else if (p->C <= 512) DV_LNB(float, 4); else DV_LNB(float, 8);
+    if (p->C <= 128) DV_LNB(float, 1, 4); else if (p->C <= 512) DV_LNB(float, 4, 2); else DV_LNB(float, 8, 1);
   } else {
-    if (p->C <= 128) DV_LNB(__nv_bfloat16, 1); else if (p->C <= 512) DV_LNB(__nv_bfloat16, 4); else DV_LNB(__nv_bfloat16, 8);
+    if (p->C <= 128) DV_LNB(__nv_bfloat16, 1, 4); else if (p->C <= 512) DV_LNB(__nv_bfloat16, 4, 2); else DV_LNB(__nv_bfloat16, 8, 1);
   }
 #undef DV_LNB
   DV_CHECK_LAUNCH("dv_layernorm_bwd");
