@@ -65,6 +65,13 @@ class XattnFoldPrepParams(C.Structure):
                 ("v_off", i32), ("scale", f32)]
 
 
+XATTN_FOLD_PREP_MAX = 24  # DV_XATTN_FOLD_PREP_MAX
+
+
+class XattnFoldPrepMultiParams(C.Structure):
+    _fields_ = [("layers", C.POINTER(XattnFoldPrepParams)), ("count", i32)]
+
+
 class XattnFoldParams(C.Structure):
     _fields_ = [("x", vp), ("out", vp), ("mq", vp), ("u", vp), ("cs", vp), ("g2", vp), ("B", i32), ("P", i64),
                 ("C", i32), ("heads", i32), ("nk", i32), ("eps_in", f32), ("eps_out", f32)]
@@ -205,6 +212,7 @@ ENTRY_POINTS = {
     "dv_ddpm_step": DdpmStepParams, "dv_ddim_step": DdimStepParams, "dv_conv_igemm": ConvParams, "dv_gn_apply": GnApplyParams,
     "dv_gn_stats": GnStatsParams, "dv_layernorm": LayerNormParams, "dv_xattn_core": XattnParams,
     "dv_xattn_fold_prep": XattnFoldPrepParams, "dv_xattn_fold": XattnFoldParams,
+    "dv_xattn_fold_prep_multi": XattnFoldPrepMultiParams,
     "dv_attn_mqa": AttnMqaParams, "dv_attn_temporal": AttnTemporalParams,
     "dv_time_embed": TimeEmbedParams, "dv_linear_small": LinearSmallParams,
     "dv_cond_tokens": CondTokensParams, "dv_to_out": ToOutParams, "dv_im2col_init": Im2colParams,

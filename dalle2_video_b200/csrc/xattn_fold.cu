@@ -14,63 +14,93 @@
 namespace dv {
 
 // ------------------------------------------------------------------------------------------ prep
-// grid (C/64, heads, B), block (64, 2): y = 0 builds 64 columns of Mq for one head, y = 1 the matching rows of U.
-// The d loop is unrolled 8x so that eight independent weight loads are in flight per thread (latency-bound kernel).
-__global__ void __launch_bounds__(128) xattn_fold_prep_kernel(dv_xattn_fold_prep_params p) {
-  __shared__ float ks[8][64];
-  __shared__ float vs[8][64];
-  const int h = blockIdx.y, b = blockIdx.z, nk = p.n_ctx + 1, inner = p.heads * p.dh;
+// block (64, 2) = 64 channels of one head: y = 0 builds the Mq columns, y = 1 the matching rows of U.  A thread keeps its
+// 64 weights (one per head dimension) in registers and walks the samples b0..b1-1 — the weights are read once per block,
+// not once per sample (the kernel used to be one latency-bound block per sample).
+__device__ __forceinline__ void xattn_fold_prep_body(const dv_xattn_fold_prep_params& p, int b0, int b1) {
+  __shared__ float kvs[2][8][64];   // [k | v][key][d] of the current sample
+  const int h = blockIdx.y, nk = p.n_ctx + 1, inner = p.heads * 64;
   const int tid = threadIdx.y * 64 + threadIdx.x;
-  for (int i = tid; i < nk * p.dh; i += 128) {
-    const int j = i / p.dh, d = i % p.dh;
-    if (j == 0) {
-      ks[0][d] = p.null_kv[d];
-      vs[0][d] = p.null_kv[p.dh + d];
-    } else {
-      const float* row = p.kv + ((int64_t)b * p.n_ctx + (j - 1)) * p.kv_ld;
-      ks[j][d] = row[p.k_off + h * p.dh + d];
-      vs[j][d] = row[p.v_off + h * p.dh + d];
-    }
-  }
-  __syncthreads();
   const int c = blockIdx.x * 64 + threadIdx.x;
-  if (c >= p.C) return;
-  float acc[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  const bool valid = c < p.C;
+  const int cc = valid ? c : 0;
+  float wreg[64];
   if (threadIdx.y == 0) {
-    const float* w = p.wq + (int64_t)(h * p.dh) * p.C + c;  // Wq[h*dh + d][c]: coalesced over c
-    for (int d0 = 0; d0 < p.dh; d0 += 8) {
-      float wv[8];
+    const float* w = p.wq + (int64_t)(h * 64) * p.C + cc;   // Wq[h*dh + d][c]: coalesced over c
 #pragma unroll
-      for (int e = 0; e < 8; ++e) wv[e] = __ldg(w + (int64_t)(d0 + e) * p.C);
-#pragma unroll
-      for (int e = 0; e < 8; ++e)
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-          if (j < nk) acc[j] = fmaf(ks[j][d0 + e], wv[e], acc[j]);
-    }
-    const float gs = p.scale * p.g[c];
-    __nv_bfloat16* mq = reinterpret_cast<__nv_bfloat16*>(p.mq) + (int64_t)b * 64 * p.C;
-#pragma unroll
-    for (int j = 0; j < 8; ++j)
-      if (j < nk) mq[(int64_t)(h * nk + j) * p.C + c] = __float2bfloat16_rn(gs * acc[j]);
+    for (int d = 0; d < 64; ++d) wreg[d] = __ldg(w + (int64_t)d * p.C);
   } else {
-    const float4* w = reinterpret_cast<const float4*>(p.wout + (int64_t)c * inner + h * p.dh);  // Wout[c][h*dh + d]
-    for (int d0 = 0; d0 < p.dh; d0 += 8) {
-      const float4 w0 = __ldg(w + d0 / 4), w1 = __ldg(w + d0 / 4 + 1);
-      const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+    const float4* w = reinterpret_cast<const float4*>(p.wout + (int64_t)cc * inner + h * 64);  // Wout[c][h*dh + d]
 #pragma unroll
-      for (int e = 0; e < 8; ++e)
+    for (int d = 0; d < 16; ++d) {
+      const float4 t = __ldg(w + d);
+      wreg[4 * d] = t.x; wreg[4 * d + 1] = t.y; wreg[4 * d + 2] = t.z; wreg[4 * d + 3] = t.w;
+    }
+  }
+  const float gs = p.scale * p.g[cc];
+  for (int b = b0; b < b1; ++b) {
+    __syncthreads();
+    for (int i = tid; i < nk * 64; i += 128) {
+      const int j = i >> 6, d = i & 63;
+      if (j == 0) {
+        kvs[0][0][d] = p.null_kv[d];
+        kvs[1][0][d] = p.null_kv[64 + d];
+      } else {
+        const float* row = p.kv + ((int64_t)b * p.n_ctx + (j - 1)) * p.kv_ld;
+        kvs[0][j][d] = row[p.k_off + h * 64 + d];
+        kvs[1][j][d] = row[p.v_off + h * 64 + d];
+      }
+    }
+    __syncthreads();
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    const float (*src)[64] = kvs[threadIdx.y];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (j < nk) {
+#pragma unroll
+        for (int d = 0; d < 64; d += 4) {
+          const float4 t = *reinterpret_cast<const float4*>(&src[j][d]);
+          acc[j] = fmaf(t.x, wreg[d], acc[j]); acc[j] = fmaf(t.y, wreg[d + 1], acc[j]);
+          acc[j] = fmaf(t.z, wreg[d + 2], acc[j]); acc[j] = fmaf(t.w, wreg[d + 3], acc[j]);
+        }
+      }
+    }
+    if (valid) {
+      if (threadIdx.y == 0) {
+        __nv_bfloat16* mq = reinterpret_cast<__nv_bfloat16*>(p.mq) + (int64_t)b * 64 * p.C;
 #pragma unroll
         for (int j = 0; j < 8; ++j)
-          if (j < nk) acc[j] = fmaf(vs[j][d0 + e], wv[e], acc[j]);
-    }
-    __nv_bfloat16* u = reinterpret_cast<__nv_bfloat16*>(p.u) + (int64_t)b * p.C * 64;
+          if (j < nk) mq[(int64_t)(h * nk + j) * p.C + c] = __float2bfloat16_rn(gs * acc[j]);
+      } else {
+        __nv_bfloat16* u = reinterpret_cast<__nv_bfloat16*>(p.u) + (int64_t)b * p.C * 64;
 #pragma unroll
-    for (int j = 0; j < 8; ++j)
-      if (j < nk) u[(int64_t)c * 64 + h * nk + j] = __float2bfloat16_rn(acc[j]);
+        for (int j = 0; j < 8; ++j)
+          if (j < nk) u[(int64_t)c * 64 + h * nk + j] = __float2bfloat16_rn(acc[j]);
+      }
+    }
   }
+}
+
+constexpr int XF_PREP_SAMPLES = 8;   // samples per block
+__global__ void __launch_bounds__(128) xattn_fold_prep_kernel(dv_xattn_fold_prep_params p) {
+  const int b0 = blockIdx.z * XF_PREP_SAMPLES;
+  xattn_fold_prep_body(p, b0, min(b0 + XF_PREP_SAMPLES, p.B));
+}
+
+// every folded layer of one denoising step in ONE launch: blockIdx.z = layer * sample-groups + group (the per-layer
+// kernels are latency-bound 20 us launches; 12 of them per step)
+struct XfoldPrepMulti {
+  dv_xattn_fold_prep_params layer[DV_XATTN_FOLD_PREP_MAX];
+  int count;
+};
+__global__ void __launch_bounds__(128) xattn_fold_prep_multi_kernel(const __grid_constant__ XfoldPrepMulti m) {
+  const int groups = (m.layer[0].B + XF_PREP_SAMPLES - 1) / XF_PREP_SAMPLES;
+  const int li = blockIdx.z / groups, b0 = (blockIdx.z - li * groups) * XF_PREP_SAMPLES;
+  const dv_xattn_fold_prep_params& p = m.layer[li];
+  if ((int)blockIdx.x * 64 >= p.C || (int)blockIdx.y >= p.heads) return;
+  xattn_fold_prep_body(p, b0, min(b0 + XF_PREP_SAMPLES, p.B));
 }
 
 // ------------------------------------------------------------------------------------------ main kernel
@@ -378,9 +408,36 @@ extern "C" int dv_xattn_fold_prep(const dv_xattn_fold_prep_params* p, dv_stream_
   DV_REQUIRE(p->B > 0 && p->C > 0 && p->heads > 0 && p->dh == 64 && p->n_ctx >= 0 && p->n_ctx <= 7, DV_EUNSUPPORTED,
              "dv_xattn_fold_prep: needs dim_head 64 and at most 7 context tokens");
   DV_REQUIRE(p->heads * (p->n_ctx + 1) <= 64, DV_EUNSUPPORTED, "dv_xattn_fold_prep: heads*(n_ctx+1) must be <= 64");
-  dim3 grid((p->C + 63) / 64, p->heads, p->B);
+  dim3 grid((p->C + 63) / 64, p->heads, (p->B + XF_PREP_SAMPLES - 1) / XF_PREP_SAMPLES);
   xattn_fold_prep_kernel<<<grid, dim3(64, 2), 0, as_stream(stream)>>>(*p);
   DV_CHECK_LAUNCH("dv_xattn_fold_prep");
+  return DV_OK;
+}
+
+extern "C" int dv_xattn_fold_prep_multi(const dv_xattn_fold_prep_multi_params* mp, dv_stream_t stream) {
+  using namespace dv;
+  DV_REQUIRE(mp && mp->layers && mp->count > 0 && mp->count <= DV_XATTN_FOLD_PREP_MAX, DV_EINVAL,
+             "dv_xattn_fold_prep_multi: 1..%d layers", DV_XATTN_FOLD_PREP_MAX);
+  XfoldPrepMulti m;
+  memset(&m, 0, sizeof(m));
+  m.count = mp->count;
+  int cmax = 0, hmax = 0;
+  for (int i = 0; i < mp->count; ++i) {
+    const dv_xattn_fold_prep_params* p = &mp->layers[i];
+    DV_REQUIRE(p->kv && p->null_kv && p->wq && p->wout && p->g && p->mq && p->u, DV_EINVAL, "dv_xattn_fold_prep_multi: null pointer");
+    DV_REQUIRE(aligned16(p->wout) && (p->heads * p->dh) % 4 == 0, DV_EALIGN, "dv_xattn_fold_prep_multi: wout must be 16-byte aligned");
+    DV_REQUIRE(p->B > 0 && p->B == mp->layers[0].B && p->C > 0 && p->heads > 0 && p->dh == 64 && p->n_ctx >= 0 && p->n_ctx <= 7 &&
+                   p->heads * (p->n_ctx + 1) <= 64,
+               DV_EUNSUPPORTED, "dv_xattn_fold_prep_multi: every layer needs the same B, dim_head 64, <= 7 context tokens");
+    m.layer[i] = *p;
+    if (p->C > cmax) cmax = p->C;
+    if (p->heads > hmax) hmax = p->heads;
+  }
+  const int groups = (mp->layers[0].B + XF_PREP_SAMPLES - 1) / XF_PREP_SAMPLES;
+  DV_REQUIRE((int64_t)mp->count * groups <= 65535, DV_EUNSUPPORTED, "dv_xattn_fold_prep_multi: too many (layer, sample group) blocks");
+  dim3 grid((cmax + 63) / 64, hmax, mp->count * groups);
+  xattn_fold_prep_multi_kernel<<<grid, dim3(64, 2), 0, as_stream(stream)>>>(m);
+  DV_CHECK_LAUNCH("dv_xattn_fold_prep_multi");
   return DV_OK;
 }
 

@@ -708,6 +708,7 @@ class _Engine:
         self._gn_i = 0
 
         # ---- the network
+        self._fold_preps, prep_at = [], len(self.ops)   # folded cross-attention matrices: built for all layers at once
         n_img, P = B * T, T * H * W
         rows = B * P
         x0 = self._new_act(rows, u.init_dim)
@@ -803,6 +804,14 @@ class _Engine:
                                             extra=self.lowres_in.data_ptr() if u.lowres_cond else None,
                                             Cextra=u.channels if u.lowres_cond else 0))
         self.final_act = x  # kept alive
+        # one launch builds the per-sample folded matrices of every short-context cross-attention layer (they depend on the
+        # step's time tokens only); it runs right after the conditioning prologue
+        for i in range(0, len(self._fold_preps), L.XATTN_FOLD_PREP_MAX):
+            chunk = self._fold_preps[i:i + L.XATTN_FOLD_PREP_MAX]
+            arr = (L.XattnFoldPrepParams * len(chunk))(*chunk)
+            self.keep.append(arr)
+            self.ops.insert(prep_at, ("dv_xattn_fold_prep_multi", L.XattnFoldPrepMultiParams(layers=arr, count=len(chunk))))
+            prep_at += 1
 
     def _init_conv_as_gemm(self, x0, n_img, H, W):
         """CrossEmbedLayer3D as im2col + ONE tensor-core GEMM (bf16 only): the 3x3 / 7x7 windows are centred
@@ -951,7 +960,7 @@ class _Engine:
             mq = self._zeros(self.B, 64, C, dtype=torch.bfloat16)
             uu = self._zeros(self.B, C, 64, dtype=torch.bfloat16)
             cs = self._zeros(self.B, 64)
-            self._op("dv_xattn_fold_prep", L.XattnFoldPrepParams(
+            self._fold_preps.append(L.XattnFoldPrepParams(
                 kv=kv.data_ptr(), null_kv=self._f32(ca.null_kv).data_ptr(), wq=self._f32(ca.to_q.weight).data_ptr(),
                 wout=self._f32(ca.to_out[0].weight).data_ptr(), g=self._f32(ca.norm.g).data_ptr(), mq=mq.data_ptr(),
                 u=uu.data_ptr(), cs=cs.data_ptr(), B=self.B, C=C, heads=heads, dh=dh, n_ctx=n_ctx, kv_ld=kv.shape[2],

@@ -287,6 +287,13 @@ typedef struct {
   float scale;
 } dv_xattn_fold_prep_params;
 int dv_xattn_fold_prep(const dv_xattn_fold_prep_params* p, dv_stream_t stream);
+/* the same for every folded layer of a denoising step in ONE launch (the per-layer launches are latency bound) */
+#define DV_XATTN_FOLD_PREP_MAX 24
+typedef struct {
+  const dv_xattn_fold_prep_params* layers;  /* host array, copied into the kernel arguments */
+  int count;                                 /* <= DV_XATTN_FOLD_PREP_MAX, same B in every layer */
+} dv_xattn_fold_prep_multi_params;
+int dv_xattn_fold_prep_multi(const dv_xattn_fold_prep_multi_params* p, dv_stream_t stream);
 
 typedef struct {
   const void* x;    /* bf16 [B][P][C] */
