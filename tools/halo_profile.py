@@ -7,7 +7,7 @@ prof = torch.zeros(148, 16, dtype=torch.int64, device="cuda")
 os.environ["DV_HALO_PROFILE"] = hex(prof.data_ptr())
 from gpu_util import conv
 dev = torch.device("cuda:0")
-B, T, H, W, C, Co = 8, 16, 64, 64, 64, 64
+B, T, H, W, C, Co = int(os.environ.get("HB", "32")), 16, 64, 64, 64, 64
 rows = B * T * H * W
 x = torch.randn(rows, C, device=dev).bfloat16()
 w = (torch.randn(Co, 9 * C, device=dev) / math.sqrt(9 * C)).bfloat16()
