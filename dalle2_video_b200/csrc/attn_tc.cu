@@ -26,7 +26,9 @@
 
 namespace dv {
 
-constexpr int AT_THREADS = 192;  // warp 0 TMA, warp 1 MMA, warps 2-5 softmax (one (query, head) row per thread)
+constexpr int AT_THREADS = 320;  // warp 0 TMA, warp 1 MMA, warps 2-9 softmax: two threads per (query, head) row, each owning
+                                 // 64 of the tile's 128 keys and half of the output columns (one warp per scheduler could
+                                 // not hide the exp2 / TMEM-load latency: the kernel ran at 1/3 of its MUFU bound)
 constexpr int AT_KT = 128;       // keys per tile
 constexpr int AT_STAGES = 3;
 
@@ -97,6 +99,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
   uint64_t* p_ready = s_full + 2;           // 1 (4 arrivals)
   uint64_t* o_full = p_ready + 1;           // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 2);
+  float* xch = reinterpret_cast<float*>(tmem_slot + 4);   // [2 buffers][2 halves][128 rows]: row maxima / sums of the two column halves
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr uint32_t TMEM_COLS = 512;  // S: 2 x 128, Ot: 2 x DH (at 256, 256 + DH)
@@ -106,10 +109,10 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
     tma_prefetch_desc(&map_q);
     tma_prefetch_desc(&map_k);
     tma_prefetch_desc(&map_vt);
-    for (int a = 0; a < 2; ++a) { mbar_init(&q_full[a], 1); mbar_init(&q_free[a], 4); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&q_full[a], 1); mbar_init(&q_free[a], 8); }
     for (int s = 0; s < AT_STAGES; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(&s_full[a], 1); mbar_init(&o_full[a], 1); }
-    mbar_init(p_ready, 4);
+    mbar_init(p_ready, 8);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -206,10 +209,13 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
       jj += nt;
     }
   } else {
-    // ================================================================ softmax / output: one (query, head) row per thread
+    // ================================================================ softmax / output: two threads per (query, head) row
     const int q = warp & 3;
+    const int half = (warp - 2) >> 2;          // keys [64*half, 64*half + 64) of every tile, output columns [OH*half, +OH)
     const int row = q * 32 + lane;
+    constexpr int OH = DH / 2;
     const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
+    auto pair_bar = []() { asm volatile("bar.sync 2, 256;" ::: "memory"); };
     int t = 0;
     int64_t jj = 0;
     for (int64_t tile = tile_begin; tile < tile_end; ++tile, ++t) {
@@ -224,48 +230,67 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
       } else {
         grow = tile * 128 + row;
       }
-      float o[DH];
-      float m, l;
+      float o[OH];
+      float m, l;   // m: running row maximum (identical in both threads of a row); l: this thread's share of the row sum
       if (MHA) {
         // the null key / value are key 0 of the packed K / V^T blocks: plain online-softmax start
         m = -CUDART_INF_F;
         l = 0.f;
 #pragma unroll
-        for (int e = 0; e < DH; ++e) o[e] = 0.f;
+        for (int e = 0; e < OH; ++e) o[e] = 0.f;
       } else {
         // null key / value initialise the online softmax (logit of key 0 = scale * q . k_null)
-        l = 1.0f;
-        float qv[DH];
+        l = half ? 0.f : 1.0f;
+        float d = 0.f;
 #pragma unroll
         for (int e = 0; e < DH; e += 8) {
           float tmp[8];
           load8(p.q + grow * DH + e, tmp);
 #pragma unroll
-          for (int k = 0; k < 8; ++k) qv[e + k] = tmp[k];
+          for (int k = 0; k < 8; ++k) d = fmaf(tmp[k], __ldg(p.null_kv + e + k), d);
         }
-        float d = 0.f;
 #pragma unroll
-        for (int e = 0; e < DH; ++e) {
-          d = fmaf(qv[e], __ldg(p.null_kv + e), d);
-          o[e] = __ldg(p.null_kv + DH + e);
-        }
+        for (int e = 0; e < OH; ++e) o[e] = __ldg(p.null_kv + DH + half * OH + e);
         m = d * p.scale_log2e;  // running max in the log2 domain
       }
+      auto fold_o = [&](int pb) {   // o += this thread's columns of the P.V result of S buffer pb
+        if (DH == 64) {
+          uint32_t r[32];
+          tmem_ld32(t_lane + 256u + (uint32_t)(pb * DH + half * 32), r);
+#pragma unroll
+          for (int e = 0; e < OH; ++e) o[e] += __uint_as_float(r[e % 32]);
+        } else {
+          uint32_t r[16];
+          tmem_ld16_nowait(t_lane + 256u + (uint32_t)(pb * DH + half * 16), r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int e = 0; e < OH; ++e) o[e] += __uint_as_float(r[e % 16]);
+        }
+      };
       for (int j = 0; j < nt; ++j) {
         const int buf = (int)((jj + j) & 1);
         mbar_wait(&s_full[buf], (uint32_t)(((jj + j) >> 1) & 1));
         tc_fence_after();
-        // pass 1: row maximum of this tile (keys >= n_valid are padding: only the MHA instantiation has any)
-        const int lim = MHA ? p.n_valid - j * AT_KT : AT_KT;
+        // pass 1: maximum of this thread's 64 keys (keys >= n_valid are padding: only the MHA instantiation has any)
+        const int lim = MHA ? p.n_valid - j * AT_KT - half * 64 : 64;
+        // the thread's 64 logits are read from TMEM ONCE and stay in registers for both passes (TMEM reads, not MUFU, bounded
+        // the two-pass version: 2 x 64 KB per key tile at ~64 B/clk)
         float mx = m;
-#pragma unroll 1
-        for (int c0 = 0; c0 < AT_KT; c0 += 32) {
-          uint32_t r[32];
-          tmem_ld32(t_lane + (uint32_t)(buf * 128 + c0), r);
+        uint32_t sr[2][32];
+        tmem_ld32_nowait(t_lane + (uint32_t)(buf * 128 + half * 64), sr[0]);
+        tmem_ld32_nowait(t_lane + (uint32_t)(buf * 128 + half * 64 + 32), sr[1]);
+        tmem_ld_wait();
+#pragma unroll
+        for (int c = 0; c < 2; ++c)
 #pragma unroll
           for (int k = 0; k < 32; ++k)
-            if (!MHA || c0 + k < lim) mx = fmaxf(mx, __uint_as_float(r[k]) * p.scale_log2e);
-        }
+            if (!MHA || c * 32 + k < lim) mx = fmaxf(mx, __uint_as_float(sr[c][k]) * p.scale_log2e);
+        // the row maximum is the larger of the two halves' (exchange buffers alternate: a slot is rewritten two tiles later,
+        // after the barrier of the tile in between)
+        float* xb = xch + buf * 256;
+        xb[half * 128 + row] = mx;
+        pair_bar();
+        mx = fmaxf(mx, xb[(half ^ 1) * 128 + row]);
         const float corr = exp2f(m - mx);
         m = mx;
         // the previous tile's P.V must have completed before P is overwritten; fold its result in now
@@ -273,32 +298,25 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
           const int pb = (int)((jj + j - 1) & 1);
           mbar_wait(&o_full[pb], (uint32_t)(((jj + j - 1) >> 1) & 1));
           tc_fence_after();
-#pragma unroll
-          for (int e0 = 0; e0 < DH; e0 += 32) {
-            uint32_t r[32];
-            tmem_ld32(t_lane + 256u + (uint32_t)(pb * DH + e0), r);
-#pragma unroll
-            for (int e = 0; e < 32; ++e) o[e0 + e] += __uint_as_float(r[e]);
-          }
+          fold_o(pb);
         }
         l *= corr;
 #pragma unroll
-        for (int e = 0; e < DH; ++e) o[e] *= corr;
-        // pass 2: P = exp2(s*c - m) -> bf16 -> shared memory (two 64-key SWIZZLE_128B blocks)
+        for (int e = 0; e < OH; ++e) o[e] *= corr;
+        // pass 2: P = exp2(s*c - m) -> bf16 -> this thread's 64-key SWIZZLE_128B block
         float lsum = 0.f;
-#pragma unroll 1
-        for (int c0 = 0; c0 < AT_KT; c0 += 32) {
-          uint32_t r[32];
-          tmem_ld32(t_lane + (uint32_t)(buf * 128 + c0), r);
-          uint8_t* prow = p_s + (c0 / 64) * 16384 + row * 128;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          const int c0 = c * 32;
+          uint8_t* prow = p_s + half * 16384 + row * 128;
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
             uint4 pk;
             __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&pk);
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-              float a = exp2f(fmaf(__uint_as_float(r[g * 8 + 2 * e]), p.scale_log2e, -m));
-              float b = exp2f(fmaf(__uint_as_float(r[g * 8 + 2 * e + 1]), p.scale_log2e, -m));
+              float a = exp2f(fmaf(__uint_as_float(sr[c][g * 8 + 2 * e]), p.scale_log2e, -m));
+              float b = exp2f(fmaf(__uint_as_float(sr[c][g * 8 + 2 * e + 1]), p.scale_log2e, -m));
               if (MHA) {
                 if (c0 + g * 8 + 2 * e >= lim) a = 0.f;
                 if (c0 + g * 8 + 2 * e + 1 >= lim) b = 0.f;
@@ -307,7 +325,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
               // sum what the tensor core will actually multiply (the bf16-rounded probabilities)
               lsum += __low2float(h2[e]) + __high2float(h2[e]);
             }
-            const int chunk = ((c0 % 64) / 8 + g) ^ (row & 7);
+            const int chunk = (c0 / 8 + g) ^ (row & 7);
             *reinterpret_cast<uint4*>(prow + chunk * 16) = pk;
           }
         }
@@ -322,22 +340,21 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
         const int pb = (int)((jj + nt - 1) & 1);
         mbar_wait(&o_full[pb], (uint32_t)(((jj + nt - 1) >> 1) & 1));
         tc_fence_after();
-#pragma unroll
-        for (int e0 = 0; e0 < DH; e0 += 32) {
-          uint32_t r[32];
-          tmem_ld32(t_lane + 256u + (uint32_t)(pb * DH + e0), r);
-#pragma unroll
-          for (int e = 0; e < 32; ++e) o[e0 + e] += __uint_as_float(r[e]);
-        }
+        fold_o(pb);
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&q_free[t & 1]);  // this Q buffer may be refilled
+      // total row sum = the two halves' shares
+      float* xb = xch + 512 + (t & 1) * 256;
+      xb[half * 128 + row] = l;
+      pair_bar();
+      l += xb[(half ^ 1) * 128 + row];
       const float inv = 1.0f / l;
-      if (!MHA && p.lse) p.lse[grow] = m + log2f(l);
-      __nv_bfloat16* orow = p.out + grow * DH;
+      if (!MHA && p.lse && half == 0) p.lse[grow] = m + log2f(l);
+      __nv_bfloat16* orow = p.out + grow * DH + half * OH;
 #pragma unroll
-      for (int e = 0; e < DH; e += 8) {
+      for (int e = 0; e < OH; e += 8) {
         float tmp[8];
 #pragma unroll
         for (int k = 0; k < 8; ++k) tmp[k] = o[e + k] * inv;
@@ -408,7 +425,7 @@ int attn_tc_launch(const dv_attn_mqa_params& p, cudaStream_t s) {
     uint32_t box[3] = {64, (uint32_t)DH, 1};
     if ((rc = encode_map(&mv, vt, 3, dims, strides, box, 128)) != DV_OK) return rc;
   }
-  const size_t smem = 2 * 128 * DH * 2 + AT_STAGES * (AT_KT * DH * 2 + DH * AT_KT * 2) + 2 * 16384 + 256 + 1024;
+  const size_t smem = 2 * 128 * DH * 2 + AT_STAGES * (AT_KT * DH * 2 + DH * AT_KT * 2) + 2 * 16384 + 256 + 4096 + 1024;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(attn_tc_kernel<32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -522,7 +539,7 @@ int xattn_tc_launch(const dv_xattn_params& p, cudaStream_t s) {
     uint32_t box[3] = {64, (uint32_t)DH, 1};
     if ((rc = encode_map(&mv, vtp, 3, dims, strides, box, 128)) != DV_OK) return rc;
   }
-  const size_t smem = 2 * 128 * DH * 2 + AT_STAGES * (AT_KT * DH * 2 + DH * AT_KT * 2) + 2 * 16384 + 256 + 1024;
+  const size_t smem = 2 * 128 * DH * 2 + AT_STAGES * (AT_KT * DH * 2 + DH * AT_KT * 2) + 2 * 16384 + 256 + 4096 + 1024;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(attn_tc_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
