@@ -13,6 +13,6 @@ from .parallel import shard_rows
 from .scheduler import NoiseScheduler
 from .train import VideoDecoderTrainer
 from .unet3d import Unet3D
-from .video_encoder import ViViT
+from .vivit import ViViT
 
 __all__ = ["Unet3D", "VideoDecoder", "NoiseScheduler", "NullVQGanVAE", "shard_rows", "AttentionBlock", "VideoDecoderTrainer", "ViViT"]

@@ -9,7 +9,7 @@ import pytest
 import torch
 
 from conftest import golden
-from dalle2_video_b200.video_encoder import ViViT
+from dalle2_video_b200.vivit import ViViT
 from oracle import reference
 from oracle.make_golden import vivit_fixture_inputs
 from oracle.vivit import vivit_forward
