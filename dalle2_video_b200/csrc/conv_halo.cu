@@ -45,6 +45,7 @@ struct HaloParams {
   double* stats;
   int groups, out_ld, out_coff;
   int direct_store;  // epilogue rows stored straight from registers instead of through the staging transpose
+  int pair;          // BN == 64: taps dx=-1 and dx=0 of a filter row share ONE N=128 MMA (see the MMA issuer); tile stride 255
   long long* prof;  // optional [grid][16] cycle counters (debug, DV_HALO_PROFILE env)
 };
 
@@ -73,7 +74,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t tmem_cols = (uint32_t)(4 * p.BN);  // 256 or 512
+  const uint32_t tmem_cols = p.pair ? 512u : (uint32_t)(4 * p.BN);  // 256 or 512 (pair mode: 2 buffers x 2 sub-tiles x 128)
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_a0);
@@ -108,7 +109,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
     TileGeo g;
     g.sample = tile / p.tiles_per_sample;
     const int j = tile - g.sample * p.tiles_per_sample;
-    g.q0 = (g.sample * p.frames * p.Hp1 + 1) * p.Wp + 1 + j * HL_TILE_Q;
+    g.q0 = (g.sample * p.frames * p.Hp1 + 1) * p.Wp + 1 + j * (p.pair ? HL_TILE_Q - 1 : HL_TILE_Q);
     g.R0 = g.q0 / p.Wp;
     g.x0r = g.q0 - g.R0 * p.Wp;
     g.r_lo = g.R0 - (g.x0r >= 1 ? 1 : 2);          // padded row of Q0 - Wp - 1
@@ -168,7 +169,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
       const int row_off = tile_geo(tile).row_off;
       { HL_T0(); mbar_wait(&tmem_empty[acc], acc_phase ^ 1); HL_ACC(w_t); }
       tc_fence_after();
-      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 2 * p.BN);
+      const uint32_t d_tmem = tmem_base + (uint32_t)(p.pair ? acc * 256 : acc * 2 * p.BN);
       for (int ch = 0; ch < n_chunks; ++ch) {
         { HL_T0(); mbar_wait(&full_a[sa], pa); HL_ACC(w_a); }
         tc_fence_after();
@@ -180,7 +181,36 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
           const int sbi = p.b_resident ? ch * 3 + g3 : sb;
           if (!p.b_resident || first_tile) { HL_T0(); mbar_wait(&full_b[sbi], p.b_resident ? 0u : pb); HL_ACC(w_b); }
           tc_fence_after();
-          if (elect_one()) {
+          if (p.pair) {
+            // Tap pairing (BN = 64): the N = 64 MMA is bounded by its 4 KB A-operand read, so the taps dx = -1 and dx = 0 of
+            // this filter row share ONE N = 128 MMA: their weight tiles are adjacent in the stage ([tap0 ; tap1] is a
+            // [128][64] K-major tile), A is the dx = -1 view.  Columns [0,64) are the usual dx = -1 term of output row m;
+            // columns [64,128) are the dx = 0 term of output row m - 1 (the same A row is one pixel further right for it),
+            // which the epilogue adds back one row up.  dx = +1 stays an N = 64 MMA into columns [0,64).
+            if (elect_one()) {
+              const uint64_t b_desc0 = make_smem_desc(smem_u32(b_ring + (size_t)sbi * b_bytes));
+              const uint32_t idesc128 = make_idesc(128);
+              const int shift_m = (g3 - 1) * p.Wp - 1, shift_p = (g3 - 1) * p.Wp + 1;
+#pragma unroll
+              for (int u = 0; u < 2; ++u) {
+                const uint64_t a_m = a_desc0 + (uint64_t)(int64_t)((shift_m + u * 128) * 8);
+                const uint64_t a_p = a_desc0 + (uint64_t)(int64_t)((shift_p + u * 128) * 8);
+#pragma unroll
+                for (int kk = 0; kk < TC_BK / 16; ++kk)
+                  umma_f16(d_tmem + (uint32_t)(u * 128), a_m + (uint64_t)(kk * 2), b_desc0 + (uint64_t)(kk * 2), idesc128,
+                           (ch | g3 | kk) != 0);
+#pragma unroll
+                for (int kk = 0; kk < TC_BK / 16; ++kk)
+                  umma_f16(d_tmem + (uint32_t)(u * 128), a_p + (uint64_t)(kk * 2),
+                           b_desc0 + (uint64_t)(2 * p.BN * 8) + (uint64_t)(kk * 2), idesc, 1u);
+              }
+              if (!p.b_resident) umma_commit(&empty_b[sbi]);
+              if (g3 == 2) {
+                umma_commit(&empty_a[sa]);
+                if (ch == n_chunks - 1) umma_commit(&tmem_full[acc]);
+              }
+            }
+          } else if (elect_one()) {
             const uint64_t b_desc0 = make_smem_desc(smem_u32(b_ring + (size_t)sbi * b_bytes));
 #pragma unroll
             for (int t3 = 0; t3 < 3; ++t3) {
@@ -251,7 +281,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
         int yr = y0r + dR, n = n0;
         if (yr >= p.Hp1) { yr -= p.Hp1; ++n; }
         const int yy = yr - 1;
-        const bool valid = xx >= 0 && xx < p.W && yy >= 0 && n < (sample + 1) * p.frames;
+        const bool valid = xx >= 0 && xx < p.W && yy >= 0 && n < (sample + 1) * p.frames &&
+                           !(p.pair && u == 1 && row_in_sub == 127);   // pair mode: row 255 only feeds row 254
         pos_u[u] = valid ? (n * p.H + yy) * p.W + xx : -1;
       }
       // residual (gradient accumulation): this thread's 32 channels of the NEXT chunk are fetched one chunk ahead, the
@@ -267,14 +298,42 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
       load_add(0, 0);
       { HL_T0(); mbar_wait(&tmem_full[acc], acc_phase); HL_ACC(w_f); }
       tc_fence_after();
-      for (int u = 0; u < 2; ++u) {
+      if (p.pair) {
+        // phase 1: columns [64,128) of accumulator row M belong to output row M - 1: hand them over through shared
+        // memory (bf16, [256 rows][64 channels], 16-byte chunks XOR-swizzled by row)
+        hl_epi_bar();   // the previous tile's readers are done with the exchange buffer
+        uint32_t rx[2][32];
+        tmem_ld32_nowait(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 256 + 64 + wg * 32), rx[0]);
+        tmem_ld32_nowait(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 256 + 128 + 64 + wg * 32), rx[1]);
+        tmem_ld_wait();
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int M = u * 128 + row_in_sub;
+          const uint32_t (&r)[32] = rx[u];
+          if (M >= 1) {
+            uint8_t* xrow = stage_out + (size_t)(M - 1) * 128;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint4 pk;
+              __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&pk);
+#pragma unroll
+              for (int e = 0; e < 4; ++e)
+                h[e] = __floats2bfloat162_rn(__uint_as_float(r[j * 8 + 2 * e]), __uint_as_float(r[j * 8 + 2 * e + 1]));
+              *reinterpret_cast<uint4*>(xrow + (((wg * 4 + j) ^ ((M - 1) & 7)) * 16)) = pk;
+            }
+          }
+        }
+        hl_epi_bar();
+      }
+      auto t_addr = [&](int u, int s0) {
+        return tmem_base + ((uint32_t)(q * 32) << 16) +
+               (uint32_t)((p.pair ? acc * 256 + u * 128 : (acc * 2 + u) * p.BN) + s0 + wg * 32);
+      };
+      auto process_chunk = [&](int u, int s0, const uint32_t (&r)[32]) {
         const int pos = pos_u[u];
         const bool valid = pos >= 0;
-        const uint32_t t_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((acc * 2 + u) * p.BN);
-        for (int s0 = 0; s0 < p.BN; s0 += 64) {
+        {
           const int c0 = s0 + wg * 32;
-          uint32_t r[32];
-          tmem_ld32(t_base + (uint32_t)c0, r);
           float v[32];
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
@@ -283,6 +342,21 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
             v[j + 1] = valid ? __uint_as_float(r[j + 1]) + bb.y : 0.f;
             v[j + 2] = valid ? __uint_as_float(r[j + 2]) + bb.z : 0.f;
             v[j + 3] = valid ? __uint_as_float(r[j + 3]) + bb.w : 0.f;
+          }
+          if (p.pair && valid) {
+            const int M = u * 128 + row_in_sub;
+            const uint8_t* xrow = stage_out + (size_t)M * 128;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint4 xv = *reinterpret_cast<const uint4*>(xrow + (((wg * 4 + j) ^ (M & 7)) * 16));
+              const __nv_bfloat162* hx = reinterpret_cast<const __nv_bfloat162*>(&xv);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float2 a = __bfloat1622float2(hx[e]);
+                v[j * 8 + 2 * e] += a.x;
+                v[j * 8 + 2 * e + 1] += a.y;
+              }
+            }
           }
           if (p.add) {
             if (valid) {
@@ -358,7 +432,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
                 reinterpret_cast<uint4*>(dst)[j] = pk;
               }
             }
-            continue;
+            return;
           }
           // transpose through shared memory: rows -> coalesced 16-byte stores of the valid rows
           uint8_t* sbuf = stage_out + buf * 16384;
@@ -390,10 +464,30 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
           if (p.out_bufs == 2) buf ^= 1;
           else hl_epi_bar();  // single staging buffer: everyone has copied out before it is rewritten
         }
+      };
+      if (p.direct_store && p.BN == 64) {
+        // both sub-tiles' accumulator rows go to registers first: one TMEM round trip per tile, and the accumulator is
+        // handed back to the MMA warp BEFORE the bias / statistics / store work (which no longer touches TMEM)
+        uint32_t r0[32], r1[32];
+        tmem_ld32_nowait(t_addr(0, 0), r0);
+        tmem_ld32_nowait(t_addr(1, 0), r1);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+        process_chunk(0, 0, r0);
+        process_chunk(1, 0, r1);
+      } else {
+        for (int u = 0; u < 2; ++u)
+          for (int s0 = 0; s0 < p.BN; s0 += 64) {
+            uint32_t r[32];
+            tmem_ld32(t_addr(u, s0), r);
+            process_chunk(u, s0, r);
+          }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty[acc]);
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
     if (p.stats && cur_sample >= 0) flush_stats(cur_sample);
@@ -465,7 +559,19 @@ int conv_halo_launch(const dv_conv_params& p, cudaStream_t s) {
   const size_t smem = halo_smem(h.Wp, h.BN, h.c0_chunks + h.c1_chunks, &h.a_stage_bytes, &h.a_stages, &h.b_stages,
                                 &h.out_bufs, &h.b_resident);
   const int64_t span = ((int64_t)p.frames * h.Hp1 - 2) * h.Wp + p.W;
-  h.tiles_per_sample = (int)((span + HL_TILE_Q - 1) / HL_TILE_Q);
+  {
+    static int pr = -1, ds = -1;
+    if (pr < 0) { const char* e = getenv("DV_HALO_PAIR"); pr = e ? atoi(e) : 1; }   // 0 off, 1 auto, 2 every BN = 64 layer
+    if (ds < 0) { const char* e = getenv("DV_HALO_DIRECT_STORE"); ds = e ? (atoi(e) != 0) : 1; }
+    h.direct_store = ds;
+    // tap pairing needs the 32 KB staging area as its exchange buffer, i.e. the direct-store epilogue.  Measured at B=32
+    // (tools/halo_profile.py): the MMA warp's time per tile drops 5020 -> 4450 cycles, but the epilogue grows (exchange,
+    // two barriers, twice the TMEM reads) to ~7500 per tile — so it only pays where the MMA work per tile is at least
+    // doubled, i.e. >= 2 input chunks (128 -> 64 @64x64: 1.38 -> 1.27 ms); one-chunk layers keep the plain issue order
+    h.pair = pr && ds && p.Cout == 64 && h.out_bufs == 2 && (pr >= 2 || h.c0_chunks + h.c1_chunks >= 2);
+  }
+  const int stride = h.pair ? HL_TILE_Q - 1 : HL_TILE_Q;
+  h.tiles_per_sample = (int)((span + stride - 1) / stride);
   h.total_tiles = (p.n_img / p.frames) * h.tiles_per_sample;
   h.wp_magic = (uint32_t)((65536 + h.Wp - 1) / h.Wp);
   for (int off = 0; off < h.Wp + HL_TILE_Q; ++off)
@@ -477,11 +583,6 @@ int conv_halo_launch(const dv_conv_params& p, cudaStream_t s) {
   h.groups = p.groups;
   h.out_ld = p.out_ld ? p.out_ld : p.Cout;
   h.out_coff = p.out_coff;
-  {
-    static int ds = -1;
-    if (ds < 0) { const char* e = getenv("DV_HALO_DIRECT_STORE"); ds = e ? (atoi(e) != 0) : 1; }
-    h.direct_store = ds;
-  }
   {
     // debug: DV_HALO_PROFILE=<device pointer as hex> makes every CTA dump its wait-cycle counters there
     static long long* prof = nullptr;

@@ -15,7 +15,7 @@ bias = torch.randn(Co, device=dev)
 out = torch.empty(rows, Co, device=dev, dtype=torch.bfloat16)
 stats = torch.zeros(B, 8, 2, dtype=torch.float64, device=dev)
 for _ in range(3):
-    conv([x], w, bias, out, n_img=B * T, frames=T, H=H, W=W, k=3, stats=stats, groups=8, impl=3)
+    conv([x], w, bias, out, n_img=B * T, frames=T, H=H, W=W, k=3, stats=None if os.environ.get("NOSTATS") else stats, groups=8, impl=3)
 torch.cuda.synchronize()
 p = prof.float().mean(0).tolist()
 tiles = p[11]
