@@ -28,7 +28,7 @@ import torch.nn.functional as F
 from torch import nn
 
 from . import _lib as L
-from .parallel import allreduce_mean_
+from .parallel import GradBuckets, allreduce_mean_
 from .unet3d import Unet3D, _CrossAttn, _CrossEmbed, _prob_mask
 
 
@@ -81,7 +81,11 @@ class _TrainPlan:
         self.keep = []
         self.refresh = []        # (dst tensor, producer()) pairs re-evaluated when the weights change
         self.grad_map = []       # (parameter, producer() -> gradient in the parameter's shape)
+        self.grad_owner = []     # per grad_map entry: index of the tape closure whose launches complete that gradient
         self.gbufs = []          # float32 gradient accumulators (zeroed once per step)
+        self.bwd_marks = []      # (tape index, first launch in self.bwd) in backward order
+        self.segments = None     # [(first launch, end launch, [grad_map indices])] when the backward is split (data parallel)
+        self.on_segment = None   # callback(segment index) after a segment's gradients are in the .grad buffers
         self.use_cuda_graph = True
         self._graphs = {}
         self.stats_slots = 0
@@ -107,6 +111,11 @@ class _TrainPlan:
         """float32 gradient accumulator in a kernel layout (zeroed once per step); returns its index."""
         self.gbufs.append(torch.zeros(*shape, device=self.device))
         return len(self.gbufs) - 1
+
+    def _gmap(self, entry):
+        """Register (parameter, producer); remembers which tape closure (= backward position) finishes that gradient."""
+        self.grad_map.append(entry)
+        self.grad_owner.append(len(self.tape))
 
     def _g(self, idx):
         return self.gbufs[idx]
@@ -156,9 +165,9 @@ class _TrainPlan:
                                                             groups=groups, dtype=self.code)))
         gw = self._galloc(Co, kh * kw * ctot)
         gb = self._galloc(Co) if bias_fn is not None else None
-        self.grad_map.append((param_w, lambda: from5(unpack_wgrad(self._g(gw), Co, ctot, kh, kw))))
+        self._gmap((param_w, lambda: from5(unpack_wgrad(self._g(gw), Co, ctot, kh, kw))))
         if gb is not None:
-            self.grad_map.append((param_b, (lambda: self._g(gb)) if bias_unperm is None else (lambda: bias_unperm(self._g(gb)))))
+            self._gmap((param_b, (lambda: self._g(gb)) if bias_unperm is None else (lambda: bias_unperm(self._g(gb)))))
         if mode == L.CONV_UNSHUFFLE:
             wd = [self._w(lambda: pack_fwd(w5_fn()).t().contiguous())]       # [(s1,s2,c)][co]: rows in pixel-shuffle order
         else:
@@ -219,8 +228,8 @@ class _TrainPlan:
             gamma=gamma.data_ptr(), beta=beta.data_ptr(), scale=sc, shift=sh, ss_ld=self.ss_total, B=B, P=P, C=C,
             groups=G, eps=float(norm.eps), dtype=self.code)))
         gg, gbt = self._galloc(C), self._galloc(C)
-        self.grad_map.append((norm.weight, lambda: self._g(gg)))
-        self.grad_map.append((norm.bias, lambda: self._g(gbt)))
+        self._gmap((norm.weight, lambda: self._g(gg)))
+        self._gmap((norm.bias, lambda: self._g(gbt)))
         sums = torch.zeros(B, C, 2, device=self.device)
         self.zero_each_step.append(sums)
 
@@ -248,7 +257,7 @@ class _TrainPlan:
         self.fwd.append(("dv_layernorm", L.LayerNormParams(x=x.ptr, out=out.ptr, residual=residual.ptr if residual is not None else None,
                                                            g=gt.data_ptr(), beta=None, rows=x.rows, C=x.C, eps=eps, dtype=self.code)))
         gg = self._galloc(x.C)
-        self.grad_map.append((g, lambda: self._g(gg)))
+        self._gmap((g, lambda: self._g(gg)))
 
         def backward():
             dy = out.grad.data_ptr()
@@ -279,7 +288,7 @@ class _TrainPlan:
         xp = L.XattnParams(q=q.ptr, out=o.ptr, kv=kv.data_ptr(), null_kv=nk.data_ptr(), workspace=None, workspace_bytes=0, **common)
         self.fwd.append(("dv_xattn_core", xp))   # <= 16 keys: the shared-memory-resident tcgen05 kernel (no workspace)
         gnk = self._galloc(2, dh)
-        self.grad_map.append((ca.null_kv, lambda: self._g(gnk)))
+        self._gmap((ca.null_kv, lambda: self._g(gnk)))
 
         def backward():
             dst, ready = self._grad_target(q)
@@ -316,7 +325,7 @@ class _TrainPlan:
             ap.lse = lse.data_ptr()
         self.fwd.append(("dv_attn_mqa", ap))
         gnk = self._galloc(2, dh)
-        self.grad_map.append((at.null_kv, lambda: self._g(gnk)))
+        self._gmap((at.null_kv, lambda: self._g(gnk)))
         dkv32 = torch.zeros(x.rows, 2 * dh, device=self.device)
         self.keep.append(dkv32)
         self.zero_each_step.append(dkv32)
@@ -433,9 +442,9 @@ class _TrainPlan:
         co0 = 0
         for conv, k in zip(convs, ks):
             co, o = conv.weight.shape[0], (kmax - k) // 2
-            self.grad_map.append((conv.weight, lambda co0=co0, co=co, o=o, k=k: self._g(gw0)[co0:co0 + co, :ktot].reshape(
+            self._gmap((conv.weight, lambda co0=co0, co=co, o=o, k=k: self._g(gw0)[co0:co0 + co, :ktot].reshape(
                 co, cin, kmax, 16)[:, :, o:o + k, o:o + k][:, :, None]))
-            self.grad_map.append((conv.bias, lambda co0=co0, co=co: self._g(gb0)[co0:co0 + co]))
+            self._gmap((conv.bias, lambda co0=co0, co=co: self._g(gb0)[co0:co0 + co]))
             co0 += co
 
         def init_backward():
@@ -495,15 +504,17 @@ class _TrainPlan:
         self.fwd.append(("dv_to_out", L.ToOutParams(x=x.ptr, w=wo.data_ptr(), bias=bo.data_ptr(), out=self.eps.data_ptr(), B=B,
                                                     P=P, C=x.C, Cout=co, dtype=self.code)))
         gwo, gbo = self._galloc(co, x.C), self._galloc(co)
-        self.grad_map.append((u.to_out.weight, lambda: self._g(gwo).reshape(u.to_out.weight.shape)))
-        self.grad_map.append((u.to_out.bias, lambda: self._g(gbo)))
+        self._gmap((u.to_out.weight, lambda: self._g(gwo).reshape(u.to_out.weight.shape)))
+        self._gmap((u.to_out.bias, lambda: self._g(gbo)))
         dst, _ = self._grad_target(x)
         self.bwd.append(("dv_to_out_bwd", L.ToOutBwdParams(x=x.ptr, w=wo.data_ptr(), deps=self.deps.data_ptr(), dx=dst,
                                                            dw=self._gptr(gwo), db=self._gptr(gbo), B=B, P=P, C=x.C, Cout=co,
                                                            dtype=self.code)))
         # ---- backward launch list: replay the tape in reverse
-        for fn in reversed(self.tape):
-            fn()
+        self.bwd_marks.append((len(self.tape), 0))   # the head's launches (dv_to_out_bwd) come first
+        for i in reversed(range(len(self.tape))):
+            self.bwd_marks.append((i, len(self.bwd)))
+            self.tape[i]()
 
     def _upsample(self, up, x: _Var, n_img, h, w):
         """PixelShuffleUpsample3D.forward (:64-78): 1x1 conv -> SiLU -> PixelShuffle(2); rows ordered [(i,j)][c]."""
@@ -572,11 +583,53 @@ class _TrainPlan:
         for name, p in self.fwd:
             L.call(name, p, stream)
 
-    def _backward_body(self):
+    def _backward_body(self, lo=0, hi=None):
         stream = torch.cuda.current_stream(self.device).cuda_stream
-        torch._foreach_zero_(self.gbufs + self.zero_each_step)
-        for name, p in self.bwd:
+        if lo == 0:
+            torch._foreach_zero_(self.gbufs + self.zero_each_step)
+        for name, p in self.bwd[lo:hi]:
             L.call(name, p, stream)
+
+    def split_backward(self, bucket_bytes=32 << 20, tail_bytes=2 << 20):
+        """Cut the backward launch list into segments so a data-parallel trainer can start the all-reduce of a bucket
+        of gradients while the rest of the backward still runs.  Cuts fall on tape boundaries:
+        after every `bucket_bytes` of finished parameter gradients, plus one cut where only `tail_bytes` remain (the
+        high-resolution layers at the end of the backward hold little weight but most of the time, so the last big
+        bucket travels under them).  Returns the number of segments; each segment is captured as its own CUDA graph."""
+        by_owner = {}
+        for idx, ((prm, _), owner) in enumerate(zip(self.grad_map, self.grad_owner)):
+            by_owner.setdefault(owner, []).append(idx)
+        nbytes = lambda ids: sum(self.grad_map[i][0].numel() * 4 for i in ids)
+        remaining = nbytes(range(len(self.grad_map)))
+        segs, start, ids, acc, tail_cut = [], 0, [], 0, False
+        for k, (tape_idx, first) in enumerate(self.bwd_marks):
+            end = self.bwd_marks[k + 1][1] if k + 1 < len(self.bwd_marks) else len(self.bwd)
+            mine = by_owner.get(tape_idx, [])
+            ids += mine
+            acc += nbytes(mine)
+            remaining -= nbytes(mine)
+            last = k + 1 == len(self.bwd_marks)
+            cut_tail = not tail_cut and remaining <= tail_bytes and acc > 0
+            if last or ((acc >= bucket_bytes or cut_tail) and end > start):
+                segs.append((start, end, ids))
+                tail_cut = tail_cut or cut_tail
+                start, ids, acc = end, [], 0
+        assert segs[-1][1] == len(self.bwd) and sum(len(s[2]) for s in segs) == len(self.grad_map)
+        self.segments = segs
+        for key in [k for k in self._graphs if k == "bwd" or (isinstance(k, tuple) and k[0] == "bwd")]:
+            del self._graphs[key]
+        return len(segs)
+
+    def apply_grads(self, ids=None):
+        """Move finished gradients from the kernel-layout accumulators into the parameters' .grad (DDP-hook style)."""
+        with torch.no_grad():
+            for i in (range(len(self.grad_map)) if ids is None else ids):
+                prm, fn = self.grad_map[i]
+                g = fn()
+                if prm.grad is None:
+                    prm.grad = g.reshape(prm.shape).to(prm.dtype).clone()
+                else:
+                    prm.grad.add_(g.reshape(prm.shape))
 
     def _replay(self, key, body):
         """Eager on the first call (module loading, function attributes); captured into a CUDA graph on the second and
@@ -607,7 +660,25 @@ class _TrainPlan:
         self._replay("fwd", self._forward_body)
 
     def run_backward(self):
-        self._replay("bwd", self._backward_body)
+        """Backward launches + gradients into .grad.  Split plans run segment by segment and call on_segment(i) after
+        segment i's gradients are final, which is where the trainer starts that bucket's all-reduce."""
+        if self.segments is None:
+            self._replay("bwd", self._backward_body)
+            self.apply_grads()
+            return
+        for i, (lo, hi, ids) in enumerate(self.segments):
+            self._replay(("bwd", i), lambda lo=lo, hi=hi: self._backward_body(lo, hi))
+            self.apply_grads(ids)
+            if self.on_segment is not None:
+                self.on_segment(i)
+
+    def graphs_ready(self):
+        """True once every backward graph has been captured (or graphs are off): nothing will synchronise the device
+        or capture during run_backward any more."""
+        if not self.use_cuda_graph:
+            return True
+        keys = ["bwd"] if self.segments is None else [("bwd", i) for i in range(len(self.segments))]
+        return all(isinstance(self._graphs.get(k), torch.cuda.CUDAGraph) for k in keys)
 
 
 class _PlanFunction(torch.autograd.Function):
@@ -636,13 +707,6 @@ class _PlanFunction(torch.autograd.Function):
         L.call("dv_mse_loss", L.MseLossParams(pred=plan.eps.data_ptr(), target=noise.data_ptr(), dpred=plan.deps.data_ptr(),
                                               loss=scratch.data_ptr(), n=noise.numel(), grad_scale=float(grad_out)), stream)
         plan.run_backward()
-        with torch.no_grad():
-            for prm, fn in plan.grad_map:
-                g = fn()
-                if prm.grad is None:
-                    prm.grad = g.reshape(prm.shape).to(prm.dtype).clone()
-                else:
-                    prm.grad.add_(g.reshape(prm.shape))
         return (None, None, plan.dss.clone(), *[plan.dkv[k].clone() for k in plan.kv_kinds])
 
 
@@ -678,7 +742,8 @@ class VideoDecoderTrainer(nn.Module):
     two launches (dv_sumsq, dv_adamw per weight-decay group).  get_optimizer semantics: AdamW,
     betas (0.9, 0.99), parameters with ndim < 2 excluded from weight decay when group_wd_params."""
 
-    def __init__(self, decoder, lr=1e-4, wd=1e-2, eps=1e-8, max_grad_norm=0.5, group_wd_params=True, betas=(0.9, 0.99), **_):
+    def __init__(self, decoder, lr=1e-4, wd=1e-2, eps=1e-8, max_grad_norm=0.5, group_wd_params=True, betas=(0.9, 0.99),
+                 overlap_allreduce=False, bucket_bytes=32 << 20, **_):
         super().__init__()
         self.decoder = decoder
         self.lr, self.wd, self.eps, self.betas = lr, wd, eps, betas
@@ -707,12 +772,50 @@ class VideoDecoderTrainer(nn.Module):
         self._groups = [(0, nd, wd), (nd, n - nd, 0.0)]
         self.register_buffer("steps", torch.tensor([0]))
         self._sumsq = torch.zeros(1, dtype=torch.float64, device=dev)
+        self._params = ordered
+        self.overlap_allreduce, self.bucket_bytes, self.min_bucket_bytes = overlap_allreduce, bucket_bytes, 4 << 20
+        self._buckets, self._bucket_plan, self._overlap_live = None, None, False
         unet._engines.clear()  # every plan (and captured graph) built before the parameters moved into the flat buffer is stale
 
+    def _overlap_setup(self, plan):
+        """Split the plan's backward and map every slice of the flat gradient buffer to the segment that finishes it."""
+        if plan is self._bucket_plan:
+            return
+        nseg = plan.split_backward(self.bucket_bytes)
+        seg_of = {}
+        for s, (_, _, ids) in enumerate(plan.segments):
+            for i in ids:
+                prm = plan.grad_map[i][0]
+                seg_of[id(prm)] = max(seg_of.get(id(prm), 0), s)
+        base = self.flat_g.data_ptr()
+        items = [((p.grad.data_ptr() - base) // 4, p.numel(), seg_of.get(id(p), nseg)) for p in self._params]
+        self._buckets = GradBuckets(self.flat_g, items, nseg, min_bytes=self.min_bucket_bytes)
+        plan.on_segment = self._on_segment
+        self._bucket_plan = plan
+
+    def _on_segment(self, i):
+        if self._overlap_live:
+            self._buckets.launch(i)
+
     def forward(self, video, video_embed, unet_number=None, **kwargs):
+        """loss + backward + gradient averaging.  Data parallel: ONE all-reduce of the flat gradient buffer after the
+        backward (default), or with overlap_allreduce=True in buckets that start as soon as the backward segment
+        producing them has run (parallel.GradBuckets; the first two steps — eager warm-up, graph capture — still reduce
+        after the backward).  The default is the measured winner: the backward's conv kernels are persistent with one
+        CTA per SM and a static tile split, so every SM NCCL holds while they run costs a second wave — 25.0 vs 24.1 ms
+        per step at 2 GPUs (profiles/r01_train_2gpu_overlap_ab.json)."""
         loss = self.decoder(video, video_embed=video_embed, unet_number=unet_number, **kwargs)
-        loss.backward()
-        allreduce_mean_(self.flat_g)
+        import torch.distributed as dist
+        data_parallel = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+        plan = getattr(self.decoder.unets[0], "_train_plan_last", None)
+        if data_parallel and self.overlap_allreduce and plan is not None:
+            self._overlap_setup(plan)
+            self._overlap_live = plan.graphs_ready()
+            loss.backward()
+            self._buckets.finish()
+        else:
+            loss.backward()
+            allreduce_mean_(self.flat_g)
         return loss.item()
 
     @torch.no_grad()

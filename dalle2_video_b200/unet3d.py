@@ -372,6 +372,7 @@ class Unet3D(nn.Module):
         if pl is None:
             pl = _TrainPlan(self, batch, frames, height, width, device)
             self._engines[key] = pl
+        self._train_plan_last = pl
         return pl
 
     @torch.no_grad()

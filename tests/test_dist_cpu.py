@@ -97,3 +97,74 @@ def test_data_parallel_gradient_allreduce_equals_full_batch_gloo_world2():
         p.join(timeout=60)
         assert p.exitcode == 0
     assert err < 1e-5, err
+
+
+def test_grad_buckets_partition_and_merge():
+    """Bucket construction (no process group): the buckets tile the flat buffer exactly, each is ready no earlier than
+    every parameter inside it, small runs are merged, and parameters nobody claims wait for finish()."""
+    from dalle2_video_b200.parallel import GradBuckets
+    sizes = [300, 5, 5000, 7000, 3, 2, 9000, 40, 6000]
+    segs = [4, 9, 3, 3, 2, 2, 1, 0, 0]       # backward finishes the tail of the buffer first; item 1 arrives via autograd
+    items, off = [], 0
+    for n, s in zip(sizes, segs):
+        items.append((off, n, s))
+        off += n
+    flat = torch.zeros(off + 17)             # 17 trailing elements no parameter owns
+    gb = GradBuckets(flat, items, n_segments=5, min_bytes=4 * 1000)
+    assert gb.buckets[0][0] == 0 and gb.buckets[-1][1] == flat.numel()
+    assert all(a[1] == b[0] for a, b in zip(gb.buckets, gb.buckets[1:]))
+    for lo, hi, seg in gb.buckets:
+        inside = [min(s, 5) for (o, n, s) in items if o < hi and o + n > lo]
+        assert seg >= max(inside or [5])
+        assert (hi - lo) * 4 >= 4000 or seg == 5   # only buckets that wait for finish() anyway may stay small
+    assert len(gb.buckets) <= 5
+
+
+def _bucket_worker(rank, world, port, q):
+    import sys
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from dalle2_video_b200.parallel import GradBuckets, allreduce_mean_
+    g = torch.Generator().manual_seed(100 + rank)
+    sizes, segs = [4096, 64, 8192, 2048, 16, 4096], [3, 3, 2, 1, 0, 0]
+    items, off = [], 0
+    for n, s in zip(sizes, segs):
+        items.append((off, n, s))
+        off += n
+    flat = torch.zeros(off)
+    gb = GradBuckets(flat, items, n_segments=3, min_bytes=1024)
+    final = torch.randn(off, generator=g)
+    want = allreduce_mean_(final.clone())
+    for seg in range(3):                      # "backward": segment `seg` fills in the slices it owns, then launches
+        for o, n, s in items:
+            if s == seg:
+                flat[o:o + n] = final[o:o + n]
+        gb.launch(seg)
+    for o, n, s in items:                     # late arrivals (the prologue parameters of the trainer)
+        if s == 3:
+            flat[o:o + n] = final[o:o + n]
+    gb.finish()
+    first = float((flat - want).abs().max())
+    flat.copy_(final)                         # second step on the same object: state was reset by finish()
+    for seg in range(3):
+        gb.launch(seg)
+    gb.finish()
+    if rank == 0:
+        q.put(max(first, float((flat - want).abs().max())))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_bucketed_overlapped_allreduce_equals_one_allreduce_gloo_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 33500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_bucket_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    err = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert err < 1e-6, err

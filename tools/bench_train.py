@@ -32,6 +32,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--size", type=int, default=SIZE)
     ap.add_argument("--frames", type=int, default=FRAMES)
+    ap.add_argument("--overlap", action="store_true", help="all-reduce in buckets launched under the backward instead of once after it")
     args = ap.parse_args()
     import torch.distributed as dist
     from dalle2_video_b200 import Unet3D, VideoDecoder, VideoDecoderTrainer
@@ -48,7 +49,7 @@ def main():
     unet = Unet3D(**UNET_KW)
     torch.nn.init.normal_(unet.to_out.weight, std=0.02)
     dec = VideoDecoder(unet, frame_size=args.size, frame_numbers=(args.frames,), timesteps=1000, learned_variance=False).to(dev)
-    trainer = VideoDecoderTrainer(dec, lr=3e-4, wd=1e-2, max_grad_norm=0.5)
+    trainer = VideoDecoderTrainer(dec, lr=3e-4, wd=1e-2, max_grad_norm=0.5, overlap_allreduce=args.overlap)
     B = args.batch
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
     video = torch.rand(B, 3, args.frames, args.size, args.size, device=dev, generator=g)
@@ -79,6 +80,7 @@ def main():
     plan = dec.unets[0].train_plan(B, args.frames, args.size, args.size, dev)
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
     torch.cuda.synchronize()
+    trainer._overlap_live = False   # this extra step reduces in one piece after the backward so the phases separate
     ev[0].record()
     loss = dec(video, video_embed=emb)
     ev[1].record()
@@ -106,7 +108,13 @@ def main():
             "scaling": "weak", "dtype": "bf16", "data": "synthetic",
             "config": {"workload": "config4: decoder training step (p_losses + backward + clip + AdamW), Unet3D dim64 "
                                    f"mults(1,2,4,8), 3x{args.frames}x{args.size}x{args.size}", "batch_per_gpu": B,
-                       "parallelism": f"data-parallel x{world}, one NCCL all-reduce of the flat fp32 gradient per step"},
+                       "parallelism": f"data-parallel x{world}, NCCL all-reduce of the flat fp32 gradient once per step, "
+                                      + ("in buckets launched under the backward" if trainer._buckets is not None
+                                         else "one call after the backward")},
+            "allreduce": None if trainer._buckets is None else {
+                "backward_segments": len(plan.segments),
+                "segment_launches": [hi - lo for lo, hi, _ in plan.segments],
+                "buckets_mb_by_ready_segment": [[round((hi - lo) * 4 / 2 ** 20, 2), seg] for lo, hi, seg in trainer._buckets.buckets]},
             "model_tflops": value * GFLOP_PER_SAMPLE / 1e3 * (args.frames * args.size ** 2) / (FRAMES * SIZE ** 2),
             "frac_of_sustained_peak_per_gpu": value * GFLOP_PER_SAMPLE / 1e3 * (args.frames * args.size ** 2) / (FRAMES * SIZE ** 2) / world / peak,
             "phases_last_step": phases, "grad_bytes": int(trainer.flat_g.numel() * 4),
