@@ -22,13 +22,25 @@ vp, i32, i64, f32 = C.c_void_p, C.c_int, C.c_int64, C.c_float
 class DdpmStepParams(C.Structure):
     _fields_ = [("x_t", vp), ("eps", vp), ("eps_null", vp), ("noise", vp), ("out", vp), ("unnormalize_out", vp),
                 ("coef", vp), ("t_dev", vp), ("t_host", i32), ("t_dev_decrement", i32), ("num_timesteps", i32),
-                ("n", i64), ("cond_scale", f32), ("clip_denoised", i32), ("eps_dtype", i32)]
+                ("n", i64), ("cond_scale", f32), ("clip_denoised", i32), ("eps_dtype", i32),
+                ("objective", i32), ("coef_v", vp), ("thres", vp), ("per_sample", i64)]
 
 
 class DdimStepParams(C.Structure):
     _fields_ = [("x_t", vp), ("eps", vp), ("eps_null", vp), ("noise", vp), ("out", vp), ("unnormalize_out", vp),
                 ("coef", vp), ("step_dev", vp), ("t_dev", vp), ("times", vp), ("step_host", i32), ("n_pairs", i32),
-                ("advance", i32), ("n", i64), ("cond_scale", f32), ("clip_denoised", i32), ("eps_dtype", i32)]
+                ("advance", i32), ("n", i64), ("cond_scale", f32), ("clip_denoised", i32), ("eps_dtype", i32),
+                ("objective", i32), ("coef_v", vp), ("thres", vp), ("per_sample", i64)]
+
+
+class X0ThresholdParams(C.Structure):
+    _fields_ = [("x_t", vp), ("eps", vp), ("eps_null", vp), ("coef", vp), ("coef_v", vp), ("idx_dev", vp),
+                ("idx_host", i32), ("rows", i32), ("thres", vp), ("workspace", vp), ("workspace_bytes", i64),
+                ("n", i64), ("per_sample", i64), ("cond_scale", f32), ("quantile", f32), ("objective", i32),
+                ("eps_dtype", i32)]
+
+
+OBJ_EPS, OBJ_X_START, OBJ_V = 0, 1, 2
 
 
 class ConvParams(C.Structure):
@@ -172,7 +184,8 @@ class AttnMqaBwdParams(C.Structure):
 
 class QSampleParams(C.Structure):
     _fields_ = [("video", vp), ("noise", vp), ("times", vp), ("sqrt_ac", vp), ("sqrt_1mac", vp), ("out", vp),
-                ("n", i64), ("per_sample", i64), ("normalize", i32), ("unnormalize", i32)]
+                ("n", i64), ("per_sample", i64), ("normalize", i32), ("unnormalize", i32), ("target", vp),
+                ("objective", i32)]
 
 
 class MseLossParams(C.Structure):
@@ -209,7 +222,7 @@ class AdamwParams(C.Structure):
 
 # every symbol include/dv_b200.h declares: name -> params struct (None for the plain helpers)
 ENTRY_POINTS = {
-    "dv_ddpm_step": DdpmStepParams, "dv_ddim_step": DdimStepParams, "dv_conv_igemm": ConvParams, "dv_gn_apply": GnApplyParams,
+    "dv_ddpm_step": DdpmStepParams, "dv_ddim_step": DdimStepParams, "dv_x0_threshold": X0ThresholdParams, "dv_conv_igemm": ConvParams, "dv_gn_apply": GnApplyParams,
     "dv_gn_stats": GnStatsParams, "dv_layernorm": LayerNormParams, "dv_xattn_core": XattnParams,
     "dv_xattn_fold_prep": XattnFoldPrepParams, "dv_xattn_fold": XattnFoldParams,
     "dv_xattn_fold_prep_multi": XattnFoldPrepMultiParams,
@@ -226,7 +239,8 @@ ENTRY_POINTS = {
     "dv_add": AddParams, "dv_cast_f32_bf16": CastParams, "dv_sumsq": SumsqParams, "dv_adamw": AdamwParams,
 }
 PLAIN_SYMBOLS = ("dv_version", "dv_last_error_string", "dv_device_sm_count", "dv_conv_uses_tcgen05",
-                 "dv_attn_mqa_workspace_bytes", "dv_xattn_core_workspace_bytes", "dv_conv_wgrad_uses_tcgen05", "dv_attn_temporal_uses_mma", "dv_attn_mqa_bwd_workspace_bytes", "dv_init_conv_supported")
+                 "dv_attn_mqa_workspace_bytes", "dv_xattn_core_workspace_bytes", "dv_conv_wgrad_uses_tcgen05", "dv_attn_temporal_uses_mma", "dv_attn_mqa_bwd_workspace_bytes", "dv_init_conv_supported",
+                 "dv_x0_threshold_workspace_bytes")
 
 _lib = None
 _SYNC_EACH = bool(os.environ.get("DV_SYNC_EACH"))
@@ -262,6 +276,8 @@ def lib():
         _lib.dv_attn_mqa_workspace_bytes.restype = i64
         _lib.dv_conv_wgrad_uses_tcgen05.argtypes = [C.POINTER(ConvWgradParams)]
         _lib.dv_conv_wgrad_uses_tcgen05.restype = i32
+        _lib.dv_x0_threshold_workspace_bytes.argtypes = [i64, i64]
+        _lib.dv_x0_threshold_workspace_bytes.restype = i64
         _lib.dv_xattn_core_workspace_bytes.argtypes = [C.POINTER(XattnParams)]
         _lib.dv_xattn_core_workspace_bytes.restype = i64
         _lib.dv_attn_temporal_uses_mma.argtypes = [C.POINTER(AttnTemporalParams)]

@@ -23,6 +23,10 @@ __global__ void q_sample_kernel(dv_q_sample_params p) {
   const float x0 = p.normalize ? 2.0f * p.video[i] - 1.0f : p.video[i];
   const float xt = p.sqrt_ac[t] * x0 + p.sqrt_1mac[t] * p.noise[i];
   p.out[i] = p.unnormalize ? (xt + 1.0f) * 0.5f : xt;
+  if (p.target) {
+    if (p.objective == DV_OBJ_X_START) p.target[i] = x0;
+    else if (p.objective == DV_OBJ_V) p.target[i] = p.sqrt_ac[t] * p.noise[i] - p.sqrt_1mac[t] * x0;
+  }
 }
 
 // Per-frame nearest resize (F.interpolate(mode="nearest") index rule) + optional clamp; one thread per output pixel.

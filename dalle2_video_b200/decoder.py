@@ -242,10 +242,56 @@ class VideoDecoder(nn.Module):
         if learned_variance:
             raise NotImplementedError("learned_variance=True is broken for (b,c,t,h,w) tensors in the reference too "
                                       "(chunk on dim=2, SURVEY.md F5); construct with learned_variance=False")
-        if predict_x_start or predict_v:
-            raise NotImplementedError("only epsilon-prediction is accelerated")
-        if self.use_dynamic_thres:
-            raise NotImplementedError("dynamic thresholding (quantile) is outside the accelerated path")
+
+    def _x0_options(self, ns, rows_t, predict_x_start, predict_v, clip_denoised, x, eps_ptr, eps_null_ptr, coef, idx_dev,
+                    b, n, cond_scale, device):
+        """Objective + dynamic-threshold arguments shared by the two fused step kernels (:1589-1598, :1847-1860).
+        rows_t = the timestep of every row of `coef` (all of them for DDPM, the pair starts for DDIM).  Returns the extra
+        keyword arguments of the step params, the dv_x0_threshold params to launch before the step (or None), and the
+        tensors that must stay alive while the step graph is."""
+        objective = L.OBJ_V if predict_v else L.OBJ_X_START if predict_x_start else L.OBJ_EPS
+        keep = []
+        extra = dict(objective=objective, coef_v=None, thres=None, per_sample=n // b)
+        if predict_v:
+            idx = rows_t.to(ns.sqrt_alphas_cumprod.device)
+            coef_v = torch.stack((ns.sqrt_alphas_cumprod[idx], ns.sqrt_one_minus_alphas_cumprod[idx]),
+                                 dim=1).float().contiguous().to(device)
+            keep.append(coef_v)
+            extra["coef_v"] = coef_v.data_ptr()
+        thr = None
+        if self.use_dynamic_thres and clip_denoised:
+            nbytes = L.lib().dv_x0_threshold_workspace_bytes(n, n // b)
+            ws = torch.zeros(nbytes, dtype=torch.uint8, device=device)   # zero on entry, every call leaves it zero
+            thres = torch.ones(b, device=device)
+            keep += [ws, thres]
+            extra["thres"] = thres.data_ptr()
+            thr = L.X0ThresholdParams(
+                x_t=x.data_ptr(), eps=eps_ptr, eps_null=eps_null_ptr, coef=coef.data_ptr(), coef_v=extra["coef_v"],
+                idx_dev=idx_dev, idx_host=0, rows=coef.shape[0], thres=thres.data_ptr(), workspace=ws.data_ptr(),
+                workspace_bytes=nbytes, n=n, per_sample=n // b, cond_scale=float(cond_scale),
+                quantile=float(self.dynamic_thres_percentile), objective=objective, eps_dtype=L.DV_F32)
+        return extra, thr, keep
+
+    def dynamic_threshold(self, x):
+        """Reference: dalle2_video.py:1531-1549.  Static clamp to [-1, 1], or (use_dynamic_thres) clamp to the per-sample
+        quantile of |x| found by the radix-select kernel (dv_x0_threshold), then divide by it."""
+        if not self.use_dynamic_thres:
+            return x.clamp(-1.0, 1.0)
+        if not x.is_cuda:
+            raise L.DvError("VideoDecoder(b200).dynamic_threshold needs a CUDA tensor: there is no CPU path")
+        xc = x.contiguous().float()
+        b, n = xc.shape[0], xc.numel()
+        nbytes = L.lib().dv_x0_threshold_workspace_bytes(n, n // b)
+        ws = torch.zeros(nbytes, dtype=torch.uint8, device=x.device)
+        thres = torch.empty(b, device=x.device)
+        coef = torch.zeros(1, 5, device=x.device)
+        L.call("dv_x0_threshold", L.X0ThresholdParams(
+            x_t=xc.data_ptr(), eps=xc.data_ptr(), eps_null=None, coef=coef.data_ptr(), coef_v=None, idx_dev=None,
+            idx_host=0, rows=1, thres=thres.data_ptr(), workspace=ws.data_ptr(), workspace_bytes=nbytes, n=n,
+            per_sample=n // b, cond_scale=1.0, quantile=float(self.dynamic_thres_percentile), objective=L.OBJ_X_START,
+            eps_dtype=L.DV_F32), torch.cuda.current_stream(x.device).cuda_stream)
+        s = thres.view(-1, *((1,) * (x.ndim - 1)))
+        return x.clamp(-s, s) / s
 
     def _set_lowres(self, eng, unet, lowres_cond_vid, lowres_noise_level, is_latent_diffusion, rep):
         """`lowres_cond_vid = maybe(self.normalize_video)(lowres_cond_vid)` (:1704-1705, :1808-1809), then into the plan's
@@ -305,10 +351,17 @@ class VideoDecoder(nn.Module):
             noise=noise.data_ptr(), out=x.data_ptr(), unnormalize_out=result.data_ptr(), coef=coef.data_ptr(),
             t_dev=eng.t_dev.data_ptr(), t_host=0, t_dev_decrement=1, num_timesteps=steps, n=n,
             cond_scale=float(cond_scale), clip_denoised=int(bool(clip_denoised)), eps_dtype=L.DV_F32)
+        extra, thr_params, _alive = self._x0_options(
+            noise_scheduler, torch.arange(steps), predict_x_start, predict_v, clip_denoised, x, params.eps, params.eps_null,
+            coef, eng.t_dev.data_ptr(), b, n, cond_scale, device)
+        for k, v in extra.items():
+            setattr(params, k, v)
         stream_of = lambda: torch.cuda.current_stream(device).cuda_stream  # noqa: E731
 
         def one_step():
             eng.run()
+            if thr_params is not None:
+                L.call("dv_x0_threshold", thr_params, stream_of())
             L.call("dv_ddpm_step", params, stream_of())
             if cfg:
                 eng.x_in[b:].copy_(x)
@@ -431,10 +484,17 @@ class VideoDecoder(nn.Module):
             step_dev=step_dev.data_ptr(), t_dev=eng.t_dev.data_ptr(), times=times_dev.data_ptr(), step_host=0,
             n_pairs=n_pairs, advance=1, n=n, cond_scale=float(cond_scale), clip_denoised=int(bool(clip_denoised)),
             eps_dtype=L.DV_F32)
+        extra, thr_params, _alive = self._x0_options(
+            noise_scheduler, t_idx, predict_x_start, predict_v, clip_denoised, x, params.eps, params.eps_null, coef,
+            step_dev.data_ptr(), b, n, cond_scale, device)
+        for k, v in extra.items():
+            setattr(params, k, v)
         stream_of = lambda: torch.cuda.current_stream(device).cuda_stream  # noqa: E731
 
         def one_step():
             eng.run()
+            if thr_params is not None:
+                L.call("dv_x0_threshold", thr_params, stream_of())
             L.call("dv_ddim_step", params, stream_of())
             if cfg:
                 eng.x_in[b:].copy_(x)
@@ -479,7 +539,7 @@ class VideoDecoder(nn.Module):
     def p_mean_variance(self, unet, x, t, video_embed, noise_scheduler, text_encodings=None, lowres_cond_vid=None,
                         self_cond=None, clip_denoised=True, predict_x_start=False, predict_v=False,
                         learned_variance=False, cond_scale=1.0, model_output=None, lowres_noise_level=None):
-        """Reference: dalle2_video.py:1551-1618 (epsilon prediction, fixed variance)."""
+        """Reference: dalle2_video.py:1551-1618 (eps / x_start / v objectives, static or dynamic clamp, fixed variance)."""
         self._check_native(predict_x_start, predict_v, learned_variance, lowres_cond_vid, lowres_noise_level)
         assert not (cond_scale != 1.0 and not self.can_classifier_guidance)
         if model_output is None:
@@ -487,9 +547,14 @@ class VideoDecoder(nn.Module):
                                                         cond_scale=cond_scale, self_cond=self_cond,
                                                         lowres_cond_video=lowres_cond_vid,
                                                         lowres_noise_level=lowres_noise_level)
-        x_start = noise_scheduler.predict_start_from_noise(x, t=t, noise=model_output)
+        if predict_v:
+            x_start = noise_scheduler.predict_start_from_v(x, t=t, v=model_output)
+        elif predict_x_start:
+            x_start = model_output
+        else:
+            x_start = noise_scheduler.predict_start_from_noise(x, t=t, noise=model_output)
         if clip_denoised:
-            x_start = x_start.clamp(-1.0, 1.0)
+            x_start = self.dynamic_threshold(x_start)
         mean, var, logvar = noise_scheduler.q_posterior(x_start=x_start, x_t=x, t=t)
         return mean, var, logvar, x_start
 
@@ -506,7 +571,8 @@ class VideoDecoder(nn.Module):
         if noise is None:
             noise = torch.randn_like(x)
         t0 = int(t[0])
-        if bool((t == t0).all()):
+        plain = not (predict_x_start or predict_v or (self.use_dynamic_thres and clip_denoised))
+        if plain and bool((t == t0).all()):
             sched = noise_scheduler
             coef = sched.coef_table().to(x.device)
             out = torch.empty_like(x)
@@ -520,7 +586,8 @@ class VideoDecoder(nn.Module):
             x_start = sched.predict_start_from_noise(x, t=t, noise=eps)
             return out, (x_start.clamp(-1.0, 1.0) if clip_denoised else x_start)
         mean, _, logvar, x_start = self.p_mean_variance(unet, x, t, video_embed, noise_scheduler, model_output=eps,
-                                                        clip_denoised=clip_denoised)
+                                                        clip_denoised=clip_denoised, predict_x_start=predict_x_start,
+                                                        predict_v=predict_v)
         nonzero = (1 - (t == 0).float()).reshape(x.shape[0], *((1,) * (x.ndim - 1)))
         return mean + nonzero * (0.5 * logvar).exp() * noise, x_start
 
@@ -604,5 +671,6 @@ class VideoDecoder(nn.Module):
             raise NotImplementedError("per-frame nearest resizing (resize_image_to) is outside the accelerated path: pass "
                                       f"videos at the training resolution ({size})")
         times = torch.randint(0, sched.num_timesteps, (b,), device=video.device, dtype=torch.long)
-        loss = p_losses(self, unet, video, times, video_embed=video_embed, noise_scheduler=sched)
+        loss = p_losses(self, unet, video, times, video_embed=video_embed, noise_scheduler=sched,
+                        predict_x_start=self.predict_x_start[unet_number - 1], predict_v=self.predict_v[unet_number - 1])
         return (loss, None) if return_lowres_cond_video else loss

@@ -710,9 +710,11 @@ class _PlanFunction(torch.autograd.Function):
         return (None, None, plan.dss.clone(), *[plan.dkv[k].clone() for k in plan.kv_kinds])
 
 
-def p_losses(decoder, unet: Unet3D, x_start, times, *, video_embed, noise_scheduler, noise=None, is_latent_diffusion=False):
-    """VideoDecoder.p_losses (:1908-2006) for epsilon prediction with the l2 loss; returns a scalar loss tensor whose
-    .backward() runs the native backward plan."""
+def p_losses(decoder, unet: Unet3D, x_start, times, *, video_embed, noise_scheduler, noise=None, is_latent_diffusion=False,
+             predict_x_start=False, predict_v=False):
+    """VideoDecoder.p_losses (:1908-2006) with the l2 loss; the regression target is the noise, x_start or v
+    (:1990-1995, written by dv_q_sample next to x_t).  Returns a scalar loss tensor whose .backward() runs the native
+    backward plan."""
     if not x_start.is_cuda:
         raise L.DvError("VideoDecoder(b200).forward needs CUDA tensors: there is no CPU path")
     B, C, T, H, W = x_start.shape
@@ -723,16 +725,19 @@ def p_losses(decoder, unet: Unet3D, x_start, times, *, video_embed, noise_schedu
     stream = torch.cuda.current_stream(dev).cuda_stream
     x_start = x_start.contiguous().float()
     noise = noise.contiguous().float()
+    objective = L.OBJ_V if predict_v else L.OBJ_X_START if predict_x_start else L.OBJ_EPS
+    target = noise if objective == L.OBJ_EPS else torch.empty_like(noise)
     L.call("dv_q_sample", L.QSampleParams(
         video=x_start.data_ptr(), noise=noise.data_ptr(), times=times.data_ptr(),
         sqrt_ac=noise_scheduler.sqrt_alphas_cumprod.data_ptr(),
         sqrt_1mac=noise_scheduler.sqrt_one_minus_alphas_cumprod.data_ptr(), out=plan.x_in.data_ptr(), n=x_start.numel(),
-        per_sample=x_start.numel() // B, normalize=0 if is_latent_diffusion else 1), stream)
+        per_sample=x_start.numel() // B, normalize=0 if is_latent_diffusion else 1,
+        target=target.data_ptr() if target is not noise else None, objective=objective), stream)
     # prob_mask_like draws (reference :772-778): video mask, then text mask (drawn even without text conditioning)
     keep_v = _prob_mask(B, 1 - decoder.video_cond_drop_prob, dev)
     _prob_mask(B, 1 - decoder.text_cond_drop_prob, dev)
     outs = plan.prologue(times, video_embed.float(), keep_v)
-    return _PlanFunction.apply(plan, noise, outs["ss"], *[outs[k] for k in plan.kv_kinds])
+    return _PlanFunction.apply(plan, target, outs["ss"], *[outs[k] for k in plan.kv_kinds])
 
 
 class VideoDecoderTrainer(nn.Module):

@@ -75,6 +75,12 @@ typedef struct {
   float cond_scale;
   int clip_denoised;
   dv_dtype eps_dtype;
+  /* objective and dynamic thresholding (zero / NULL = epsilon prediction with the static clamp above) */
+  int objective;         /* DV_OBJ_EPS | DV_OBJ_X_START (x0 = pred, :1592) | DV_OBJ_V (x0 = sqrt_ac*x_t - sqrt_1mac*pred, :1590) */
+  const float* coef_v;   /* [T][2] {sqrt_alphas_cumprod, sqrt_one_minus_alphas_cumprod}; required for DV_OBJ_V */
+  const float* thres;    /* [n / per_sample] s_b >= 1 from dv_x0_threshold: x0 = clamp(x0, -s_b, s_b) / s_b
+                            (VideoDecoder.dynamic_threshold :1531-1549); NULL = clamp to [-1, 1] */
+  int64_t per_sample;    /* elements per sample (multiple of 4), needed with thres */
 } dv_ddpm_step_params;
 int dv_ddpm_step(const dv_ddpm_step_params* p, dv_stream_t stream);
 
@@ -99,8 +105,42 @@ typedef struct {
   float cond_scale;
   int clip_denoised;
   dv_dtype eps_dtype;
+  int objective;         /* as dv_ddpm_step_params (:1847-1857) */
+  const float* coef_v;   /* [n_pairs][2] {sqrt_alphas_cumprod[t], sqrt_one_minus_alphas_cumprod[t]} per pair */
+  const float* thres;    /* [n / per_sample] or NULL */
+  int64_t per_sample;
 } dv_ddim_step_params;
 int dv_ddim_step(const dv_ddim_step_params* p, dv_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K7c  dynamic threshold of the predicted x0 (VideoDecoder.dynamic_threshold, dalle2_video/dalle2_video.py:1531-1549,
+ * Imagen's improved clamping under classifier-free guidance):
+ *     s_b = max(1, quantile(|x0_b|, q))       torch.quantile, 'linear' interpolation, over all elements of sample b
+ * x0 is formed exactly as the step kernels form it (objective, CFG blend, row `idx` of `coef` / `coef_v`), so the step
+ * that follows clamps the same numbers.  Exact selection, no sort: |x0| is written once to the workspace while a
+ * histogram of the top 11 bits of its float pattern is built; two more passes over the workspace refine the two order
+ * statistics floor(r), ceil(r) of r = q*(per_sample-1) (computed in float32 like torch) by 10 bits each; a last launch
+ * interpolates and clears the histograms.  4 launches, ~16 B of HBM/L2 traffic per element.
+ * The workspace must be zero-filled before the first call; every call leaves it zero-filled again.
+ */
+#define DV_OBJ_EPS 0
+#define DV_OBJ_X_START 1
+#define DV_OBJ_V 2
+typedef struct {
+  const float* x_t; const void* eps; const void* eps_null;
+  const float* coef;     /* [rows][5]; columns 0,1 = sqrt_recip_alphas_cumprod, sqrt_recipm1_alphas_cumprod (both step tables) */
+  const float* coef_v;   /* [rows][2] or NULL (DV_OBJ_V) */
+  const int* idx_dev;    /* device row index (the DDPM t_dev or the DDIM step_dev) or NULL */
+  int idx_host, rows;
+  float* thres;          /* [B] out */
+  void* workspace; int64_t workspace_bytes;
+  int64_t n, per_sample; /* n = B * per_sample, per_sample a multiple of 4 */
+  float cond_scale, quantile;
+  int objective;
+  dv_dtype eps_dtype;
+} dv_x0_threshold_params;
+int dv_x0_threshold(const dv_x0_threshold_params* p, dv_stream_t stream);
+int64_t dv_x0_threshold_workspace_bytes(int64_t n, int64_t per_sample);
 
 /* ------------------------------------------------------------------------------------------------
  * K1 / K3 / K4  implicit-GEMM convolution over channels-last activations.
@@ -610,6 +650,10 @@ typedef struct {
   int64_t n, per_sample;
   int normalize;
   int unnormalize;   /* 1: out = (x_t + 1) / 2 — LowresVideoConditioner.noise_video (:1075-1090) */
+  float* target;     /* optional [n]: the regression target of p_losses (:1990-1995) for `objective`:
+                        DV_OBJ_X_START -> x_start (after normalize), DV_OBJ_V -> sqrt_ac*noise - sqrt_1mac*x_start
+                        (NoiseScheduler.calculate_v); NULL or DV_OBJ_EPS -> nothing is written (the target is `noise`) */
+  int objective;
 } dv_q_sample_params;
 int dv_q_sample(const dv_q_sample_params* p, dv_stream_t stream);
 

@@ -166,6 +166,48 @@ def cascade():
         json.dump(layouts, f, indent=0, sort_keys=True)
 
 
+OBJECTIVE_CASES = {
+    # name: (decoder kwargs, cond_scale)
+    "v": (dict(predict_v=True), 1.0),
+    "x_start": (dict(predict_x_start=True), 1.0),
+    "dyn": (dict(use_dynamic_thres=True, dynamic_thres_percentile=0.9), 1.0),
+    "v_dyn_cfg": (dict(predict_v=True, use_dynamic_thres=True, dynamic_thres_percentile=0.95, video_cond_drop_prob=0.1), 2.5),
+}
+
+
+def objectives():
+    """`python -m oracle.make_golden objectives`: the sampler and the training loss of the reference VideoDecoder for
+    the x_start / v objectives and for dynamic thresholding (dalle2_video.py:1531-1549, 1589-1598, 1990-1995), tiny Unet3D,
+    12 steps at 4x16x16.  Noise draws follow torch.manual_seed(sample_seed) on the CPU, as in the other sample fixtures."""
+    ref = reference.load()
+    with open(os.path.join(GOLDEN, "state_dict_layouts.json")) as f:
+        layouts = json.load(f)
+    out = {}
+    for name, (kw, cond_scale) in OBJECTIVE_CASES.items():
+        torch.manual_seed(0)
+        unet = ref.Unet3D(**CASES["tiny"]["unet"])
+        dec = ref.VideoDecoder(unet, frame_size=16, frame_numbers=(4,), timesteps=12, learned_variance=False, **kw)
+        dec.unets[0].load_state_dict(synth_state_dict(layouts["tiny"], seed=7), strict=True)
+        dec.eval()
+        emb = torch.randn(2, 512, generator=torch.Generator().manual_seed(21))
+        torch.manual_seed(4242)
+        vid = dec.sample(video_embed=emb, cond_scale=cond_scale)
+        assert bool(torch.isfinite(vid).all())
+        # training loss with explicit times / noise (conditioning dropout off so no RNG enters)
+        dec.video_cond_drop_prob, dec.text_cond_drop_prob = 0.0, 0.0
+        g = torch.Generator().manual_seed(77)
+        video = torch.rand(2, 3, 4, 16, 16, generator=g)
+        noise = torch.randn(2, 3, 4, 16, 16, generator=g)
+        times = torch.tensor([2, 9])
+        loss = dec.p_losses(dec.unets[0], video, times, video_embed=emb, noise_scheduler=dec.noise_schedulers[0], noise=noise,
+                            predict_x_start=dec.predict_x_start[0], predict_v=dec.predict_v[0])
+        out[name] = {"decoder_kwargs": kw, "cond_scale": cond_scale, "sample": vid, "loss": float(loss)}
+        print("objective", name, float(vid.mean()), float(vid.std()), float(loss))
+    torch.save({"cases": out, "video_embed_seed": 21, "sample_seed": 4242, "weight_seed": 7, "timesteps": 12,
+                "shape": (2, 3, 4, 16, 16), "loss_input_seed": 77, "loss_times": (2, 9)},
+               os.path.join(GOLDEN, "sample_objectives.pt"))
+
+
 VIVIT_CASES = {
     # the reference's own encoder class on small shapes (same block structure as configs/celebv-text.yaml:31-36)
     "small": dict(kw=dict(frame_size=32, patch_size=8, num_frames=25, dim=64, depth=2, heads=3, in_channels=3), batch=2),
@@ -215,5 +257,7 @@ if __name__ == "__main__":
         vivit()
     elif len(sys.argv) > 1 and sys.argv[1] == "cascade":
         cascade()
+    elif len(sys.argv) > 1 and sys.argv[1] == "objectives":
+        objectives()
     else:
         main()

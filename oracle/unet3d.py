@@ -368,13 +368,35 @@ def ddpm_coefficients(sched: NoiseScheduler):
                         sched.posterior_log_variance_clipped), dim=-1)
 
 
-def ddpm_posterior_step(sched: NoiseScheduler, x, t_int: int, pred_noise, noise, clip_denoised=True):
-    """predict x0 from eps, static clamp, posterior mean, add noise (dalle2_video.py:1591-1600, 1657-1662)."""
+def dynamic_threshold(x, percentile=None):
+    """VideoDecoder.dynamic_threshold (dalle2_video.py:1531-1549): static clamp to [-1, 1] (percentile None) or the
+    per-sample threshold s = max(1, quantile(|x|, percentile)) followed by clamp(-s, s) / s."""
+    s = 1.0
+    if percentile is not None:
+        s = torch.quantile(x.flatten(1).abs(), percentile, dim=-1)
+        s.clamp_(min=1.0)
+        s = s.view(-1, *((1,) * (x.ndim - 1)))
+    return x.clamp(-s, s) / s
+
+
+def x_start_from(sched: NoiseScheduler, x, t, pred, objective="eps"):
+    """The three objectives of p_mean_variance (dalle2_video.py:1589-1595)."""
+    if objective == "v":
+        return sched.predict_start_from_v(x, t=t, v=pred)
+    if objective == "x_start":
+        return pred
+    return sched.predict_start_from_noise(x, t=t, noise=pred)
+
+
+def ddpm_posterior_step(sched: NoiseScheduler, x, t_int: int, pred_noise, noise, clip_denoised=True, objective="eps",
+                        dynamic_thres_percentile=None):
+    """predict x0 (eps / x_start / v objective), static or dynamic clamp, posterior mean, add noise
+    (dalle2_video.py:1589-1600, 1657-1662)."""
     b = x.shape[0]
     t = torch.full((b,), t_int, dtype=torch.long, device=x.device)
-    x0 = sched.predict_start_from_noise(x, t=t, noise=pred_noise)
+    x0 = x_start_from(sched, x, t, pred_noise, objective)
     if clip_denoised:
-        x0 = x0.clamp(-1.0, 1.0) / 1.0
+        x0 = dynamic_threshold(x0, dynamic_thres_percentile)
     mean, _, logvar = sched.q_posterior(x_start=x0, x_t=x, t=t)
     nonzero = (1 - (t == 0).float()).reshape(b, 1, 1, 1, 1)
     return mean + nonzero * (0.5 * logvar).exp() * noise, x0
@@ -382,9 +404,10 @@ def ddpm_posterior_step(sched: NoiseScheduler, x, t_int: int, pred_noise, noise,
 
 def p_sample_loop_ddpm(sd, cfg, sched: NoiseScheduler, shape, *, video_embed, text_encodings=None,
                        cond_scale=1.0, generator=None, clip_denoised=True, record=None, lowres_cond_vid=None,
-                       lowres_noise_level=None):
+                       lowres_noise_level=None, objective="eps", dynamic_thres_percentile=None):
     """dalle2_video.py:1666-1755.  RNG contract: one randn(shape) then one randn per step (also at t=0).
-    `lowres_cond_vid` arrives in [0,1] and is normalised here (:1704-1705)."""
+    `lowres_cond_vid` arrives in [0,1] and is normalised here (:1704-1705).  `objective` = eps | x_start | v
+    (predict_x_start / predict_v), `dynamic_thres_percentile` = the decoder's percentile when use_dynamic_thres."""
     vid = torch.randn(shape, generator=generator)
     kw = {}
     if lowres_cond_vid is not None:
@@ -394,7 +417,7 @@ def p_sample_loop_ddpm(sd, cfg, sched: NoiseScheduler, shape, *, video_embed, te
         eps = forward_with_cond_scale(sd, cfg, vid, times, video_embed=video_embed,
                                       text_encodings=text_encodings, cond_scale=cond_scale, **kw)
         noise = torch.randn(shape, generator=generator)
-        vid, _ = ddpm_posterior_step(sched, vid, t_int, eps, noise, clip_denoised)
+        vid, _ = ddpm_posterior_step(sched, vid, t_int, eps, noise, clip_denoised, objective, dynamic_thres_percentile)
         if record is not None:
             record(t_int, eps, vid)
     return (vid + 1) * 0.5
@@ -441,7 +464,8 @@ def ddim_time_pairs(total_timesteps, timesteps):
 
 
 def p_sample_loop_ddim(sd, cfg, sched: NoiseScheduler, shape, *, video_embed, timesteps, eta=0.0, text_encodings=None,
-                       cond_scale=1.0, generator=None, clip_denoised=True, record=None):
+                       cond_scale=1.0, generator=None, clip_denoised=True, record=None, objective="eps",
+                       dynamic_thres_percentile=None):
     """Arithmetic of the reference's p_sample_loop_ddim (dalle2_video.py:1757-1889) for epsilon prediction.  The reference
     method is unreachable as shipped (it passes image_embed= / lowres_cond_img= to a Unet3D that takes video_embed=,
     SURVEY.md F5): PARITY UNPINNED against the reference, this restates its math with the keyword fixed.
@@ -454,9 +478,9 @@ def p_sample_loop_ddim(sd, cfg, sched: NoiseScheduler, shape, *, video_embed, ti
         t = torch.full((shape[0],), time, dtype=torch.long)
         pred = forward_with_cond_scale(sd, cfg, vid, t, video_embed=video_embed, text_encodings=text_encodings,
                                        cond_scale=cond_scale)
-        x_start = sched.predict_start_from_noise(vid, t=t, noise=pred)
+        x_start = x_start_from(sched, vid, t, pred, objective)
         if clip_denoised:
-            x_start = x_start.clamp(-1.0, 1.0) / 1.0
+            x_start = dynamic_threshold(x_start, dynamic_thres_percentile)
         pred_noise = sched.predict_noise_from_start(vid, t=t, x0=x_start)
         c1 = eta * ((1 - alpha / alpha_next) * (1 - alpha_next) / (1 - alpha)).sqrt()
         c2 = ((1 - alpha_next) - torch.square(c1)).sqrt()

@@ -164,3 +164,177 @@ def test_ddim_sampling_matches_oracle_loop(eta, graph, layouts):
                                  generator=torch.Generator().manual_seed(21))
     err = float((vid.cpu() - ref).abs().max())
     assert err < 2e-3, err
+
+
+# ------------------------------------------------------------------ x_start / v objectives and dynamic thresholding
+def _x0_ref(s, objective, x, t, pred):
+    tt = torch.full((x.shape[0],), t, device=x.device)
+    if objective == 2:
+        return s.predict_start_from_v(x, tt, pred)
+    return pred if objective == 1 else s.predict_start_from_noise(x, tt, pred)
+
+
+@pytest.mark.parametrize("objective", [0, 1, 2])
+@pytest.mark.parametrize("case", ["small", "headline", "ties", "below_one", "cfg_bf16"])
+def test_x0_threshold_kernel_matches_torch_quantile(objective, case):
+    """dv_x0_threshold = max(1, torch.quantile(|x0|, q)) per sample, exact order statistics by radix selection."""
+    from dalle2_video_b200 import NoiseScheduler
+    from dalle2_video_b200 import _lib as L
+    from gpu_util import ptr, stream
+    dev = torch.device("cuda:0")
+    s = NoiseScheduler(beta_schedule="cosine", timesteps=100, loss_type="l2").to(dev)
+    shape = {"small": (3, 3, 2, 8, 8), "headline": (4, 3, 16, 64, 64)}.get(case, (2, 3, 4, 16, 16))
+    g = torch.Generator().manual_seed(10 * ["small", "headline", "ties", "below_one", "cfg_bf16"].index(case) + objective)
+    x, pred, pred0 = (torch.randn(shape, generator=g).to(dev) * 1.7 for _ in range(3))
+    if case == "ties":
+        x, pred = (x * 4).round() / 4, (pred * 4).round() / 4          # many equal |x0| values around the cut
+    if case == "below_one":
+        x, pred = x * 0.05, pred * 0.05
+    cfg = case == "cfg_bf16"
+    scale = 3.0 if cfg else 1.0
+    if cfg:
+        pred, pred0 = pred.bfloat16(), pred0.bfloat16()
+    t = 37
+    coef = s.coef_table().to(dev)
+    coef_v = torch.stack((s.sqrt_alphas_cumprod, s.sqrt_one_minus_alphas_cumprod), dim=1).float().contiguous().to(dev)
+    n, b = x.numel(), shape[0]
+    nbytes = L.lib().dv_x0_threshold_workspace_bytes(n, n // b)
+    assert nbytes == n * 4 + b * (2048 + 4096) * 4
+    ws = torch.zeros(nbytes, dtype=torch.uint8, device=dev)
+    for q in (0.0, 0.5, 0.9, 0.95, 0.999, 1.0):
+        thres = torch.full((b,), -1.0, device=dev)
+        L.call("dv_x0_threshold", L.X0ThresholdParams(
+            x_t=ptr(x), eps=ptr(pred), eps_null=ptr(pred0) if cfg else None, coef=ptr(coef), coef_v=ptr(coef_v), idx_dev=None,
+            idx_host=t, rows=100, thres=ptr(thres), workspace=ptr(ws), workspace_bytes=nbytes, n=n, per_sample=n // b,
+            cond_scale=scale, quantile=q, objective=objective, eps_dtype=L.DV_BF16 if cfg else L.DV_F32), stream())
+        e = pred.float()
+        if cfg:
+            e = pred0.float() + (e - pred0.float()) * scale
+        x0 = _x0_ref(s, objective, x, t, e)
+        want = torch.quantile(x0.flatten(1).abs(), q, dim=-1).clamp(min=1.0)
+        # the kernel forms x0 with FMA contraction, torch with two rounded products: allow a few ulp of |x0|
+        assert torch.allclose(thres, want, rtol=2e-6, atol=1e-6), (q, thres, want)
+        assert int(ws[n * 4:].max()) == 0, "the histograms must be left zero-filled"
+    if case == "below_one":
+        assert float(thres.max()) == 1.0
+
+
+def test_x0_threshold_argument_checks():
+    from dalle2_video_b200 import _lib as L
+    from gpu_util import ptr, stream
+    dev = torch.device("cuda:0")
+    x = torch.zeros(2, 64, device=dev)
+    coef, thres = torch.zeros(4, 5, device=dev), torch.zeros(2, device=dev)
+    ws = torch.zeros(L.lib().dv_x0_threshold_workspace_bytes(128, 64), dtype=torch.uint8, device=dev)
+    base = dict(x_t=ptr(x), eps=ptr(x), eps_null=None, coef=ptr(coef), coef_v=None, idx_dev=None, idx_host=0, rows=4,
+                thres=ptr(thres), workspace=ptr(ws), workspace_bytes=ws.numel(), n=128, per_sample=64, cond_scale=1.0,
+                quantile=0.9, objective=0, eps_dtype=L.DV_F32)
+    L.call("dv_x0_threshold", L.X0ThresholdParams(**base), stream())
+    for bad in (dict(objective=2), dict(quantile=1.5), dict(per_sample=6), dict(idx_host=4), dict(workspace_bytes=16),
+                dict(objective=7)):
+        with pytest.raises(L.DvError):
+            L.call("dv_x0_threshold", L.X0ThresholdParams(**dict(base, **bad)), stream())
+    assert L.lib().dv_x0_threshold_workspace_bytes(100, 7) == -1
+
+
+@pytest.mark.parametrize("objective", [1, 2])
+@pytest.mark.parametrize("dynamic", [False, True])
+def test_step_kernels_with_objective_and_threshold_match_reference_arithmetic(objective, dynamic):
+    from dalle2_video_b200 import NoiseScheduler
+    from dalle2_video_b200 import _lib as L
+    from gpu_util import ptr, rel_err, stream
+    dev = torch.device("cuda:0")
+    s = NoiseScheduler(beta_schedule="cosine", timesteps=100, loss_type="l2").to(dev)
+    g = torch.Generator().manual_seed(3)
+    shape = (3, 3, 4, 8, 8)
+    x, pred, noise = (torch.randn(shape, generator=g).to(dev) * 1.5 for _ in range(3))
+    thres = torch.tensor([1.0, 1.7, 2.9], device=dev)
+    sv = thres.view(-1, 1, 1, 1, 1) if dynamic else 1.0
+    coef_v = torch.stack((s.sqrt_alphas_cumprod, s.sqrt_one_minus_alphas_cumprod), dim=1).float().contiguous().to(dev)
+    extra = dict(objective=objective, coef_v=ptr(coef_v), thres=ptr(thres) if dynamic else None, per_sample=x.numel() // 3)
+    t = 41
+    tt = torch.full((3,), t, device=dev)
+    x0 = _x0_ref(s, objective, x, t, pred)
+    x0 = x0.clamp(-sv, sv) / sv if dynamic else x0.clamp(-1, 1)
+    mean, _, logvar = s.q_posterior(x_start=x0, x_t=x, t=tt)
+    ref = mean + (0.5 * logvar).exp() * noise
+    out = torch.empty_like(x)
+    L.call("dv_ddpm_step", L.DdpmStepParams(
+        x_t=ptr(x), eps=ptr(pred), eps_null=None, noise=ptr(noise), out=ptr(out), unnormalize_out=None,
+        coef=ptr(s.coef_table().to(dev)), t_dev=None, t_host=t, t_dev_decrement=0, num_timesteps=100, n=x.numel(),
+        cond_scale=1.0, clip_denoised=1, eps_dtype=L.DV_F32, **extra), stream())
+    assert rel_err(out, ref) < 2e-6
+    # DDIM with the same x0
+    pairs = VideoDecoder.ddim_time_pairs(100, 10)
+    i = 3
+    t, tn = pairs[i]
+    tt = torch.full((3,), t, device=dev)
+    alpha, alpha_next = s.alphas_cumprod[t], s.alphas_cumprod[tn]
+    c1 = 0.5 * ((1 - alpha / alpha_next) * (1 - alpha_next) / (1 - alpha)).sqrt()
+    c2 = ((1 - alpha_next) - torch.square(c1)).sqrt()
+    x0 = _x0_ref(s, objective, x, t, pred)
+    x0 = x0.clamp(-sv, sv) / sv if dynamic else x0.clamp(-1, 1)
+    ref = x0 * alpha_next.sqrt() + c1 * noise + c2 * s.predict_noise_from_start(x, tt, x0)
+    coef = torch.zeros(len(pairs), 5, device=dev)
+    coef[i] = torch.stack((s.sqrt_recip_alphas_cumprod[t], s.sqrt_recipm1_alphas_cumprod[t], alpha_next.sqrt(), c1, c2))
+    cv = torch.zeros(len(pairs), 2, device=dev)
+    cv[i] = coef_v[t]
+    L.call("dv_ddim_step", L.DdimStepParams(
+        x_t=ptr(x), eps=ptr(pred), eps_null=None, noise=ptr(noise), out=ptr(out), unnormalize_out=None, coef=ptr(coef),
+        step_dev=None, t_dev=None, times=None, step_host=i, n_pairs=len(pairs), advance=0, n=x.numel(), cond_scale=1.0,
+        clip_denoised=1, eps_dtype=L.DV_F32, **dict(extra, coef_v=ptr(cv))), stream())
+    assert rel_err(out, ref) < 5e-6
+
+
+@pytest.mark.parametrize("name", ["v", "x_start", "dyn", "v_dyn_cfg"])
+@pytest.mark.parametrize("graph", [False, True])
+def test_sample_with_objectives_and_dynamic_threshold_matches_reference_fixture(name, graph, layouts):
+    g = golden("sample_objectives.pt")
+    case = g["cases"][name]
+    u = Unet3D(**TINY)
+    u.load_state_dict(synth_state_dict(layouts["tiny"], seed=g["weight_seed"]), strict=True)
+    d = VideoDecoder(u, frame_size=16, frame_numbers=(4,), timesteps=g["timesteps"], learned_variance=False,
+                     **case["decoder_kwargs"]).cuda()
+    d.use_cuda_graph = graph
+    emb = torch.randn(2, 512, generator=torch.Generator().manual_seed(g["video_embed_seed"]))
+    vid = d.sample(video_embed=emb.cuda(), cond_scale=case["cond_scale"], noise_fn=cpu_noise(g["sample_seed"]))
+    assert d.last_launch_stats["graph"] == graph
+    err = float((vid.cpu() - case["sample"]).abs().max())
+    assert err < 2e-3, err
+
+
+def test_ddim_with_v_objective_and_dynamic_threshold_matches_oracle_loop(layouts):
+    from oracle.primitives import NoiseScheduler as OracleScheduler
+    from oracle.unet3d import UnetConfig, p_sample_loop_ddim
+    sd = synth_state_dict(layouts["tiny"], seed=7)
+    u = Unet3D(**TINY)
+    u.load_state_dict(sd, strict=True)
+    d = VideoDecoder(u, frame_size=16, frame_numbers=(4,), timesteps=100, sample_timesteps=10, learned_variance=False,
+                     ddim_sampling_eta=0.3, predict_v=True, use_dynamic_thres=True, dynamic_thres_percentile=0.9).cuda()
+    emb = torch.randn(2, 512, generator=torch.Generator().manual_seed(4))
+    vid = d.sample(video_embed=emb.cuda(), noise_fn=cpu_noise(33))
+    with torch.no_grad():
+        ref = p_sample_loop_ddim(sd, UnetConfig(**TINY), OracleScheduler(beta_schedule="cosine", timesteps=100, loss_type="l2"),
+                                 (2, 3, 4, 16, 16), video_embed=emb, timesteps=10, eta=0.3,
+                                 generator=torch.Generator().manual_seed(33), objective="v", dynamic_thres_percentile=0.9)
+    err = float((vid.cpu() - ref).abs().max())
+    assert err < 2e-3, err
+
+
+def test_p_mean_variance_and_dynamic_threshold_method(layouts):
+    """The per-step API (p_mean_variance / dynamic_threshold) follows the same objective and clamp as the fused loop."""
+    d = decoder(TINY, layouts["tiny"], 20, 16, 4)
+    d.use_dynamic_thres, d.dynamic_thres_percentile = True, 0.8
+    g = torch.Generator().manual_seed(8)
+    x = (torch.randn(2, 3, 4, 16, 16, generator=g) * 2).cuda()
+    got = d.dynamic_threshold(x)
+    s = torch.quantile(x.flatten(1).abs(), 0.8, dim=-1).clamp(min=1.0).view(-1, 1, 1, 1, 1)
+    assert torch.allclose(got, x.clamp(-s, s) / s, rtol=1e-6, atol=1e-6)
+    emb = torch.randn(2, 512, generator=g).cuda()
+    t = torch.tensor([5, 5]).cuda()
+    sched = d.noise_schedulers[0]
+    out = d.unets[0](x, t, video_embed=emb)
+    mean, _, _, x_start = d.p_mean_variance(d.unets[0], x, t, emb, sched, predict_v=True)
+    xs = sched.predict_start_from_v(x, t, out)
+    s = torch.quantile(xs.flatten(1).abs(), 0.8, dim=-1).clamp(min=1.0).view(-1, 1, 1, 1, 1)
+    assert torch.allclose(x_start, xs.clamp(-s, s) / s, rtol=1e-4, atol=1e-5)

@@ -161,11 +161,16 @@ def test_split_backward_gives_the_same_gradients_and_fires_segments_in_order():
     assert all(a[1] == b[0] for a, b in zip(plan.segments, plan.segments[1:]))
     for a, b in zip(whole, parts):
         assert a.keys() == b.keys()
+        # same launches in the same order; the fp32 atomics of the attention / norm reductions reorder from run to run
+        # and the bf16 activations downstream amplify that to a few 1e-3 (a few 1e-2 on the smallest gradients) — a
+        # dropped or misplaced segment would be an O(1) error in the tensors it owns
+        num = sum(float((a[k] - b[k]).pow(2).sum()) for k in a)
+        den = sum(float(a[k].pow(2).sum()) for k in a)
+        assert (num / den) ** 0.5 < 1e-2, (num / den) ** 0.5
         for k in a:
-            # same launches in the same order; the fp32 atomics of the attention / norm reductions reorder from run to
-            # run and the bf16 activations downstream amplify that to a few 1e-3 by the first layer — a dropped or
-            # misplaced segment would be an O(1) error
-            assert float((a[k] - b[k]).norm()) <= 2e-2 * float(a[k].norm()) + 1e-9, k
+            if float(a[k].norm()) > 1e-7:
+                cos = float(F.cosine_similarity(a[k].flatten(), b[k].flatten(), dim=0))
+                assert cos > 0.995, (k, cos)
     # bucket map over a flat buffer laid out like the trainer's
     prms = [p for p in plan.u.parameters()]
     seg_of = {}
@@ -182,3 +187,29 @@ def test_split_backward_gives_the_same_gradients_and_fires_segments_in_order():
         assert seg >= max(s for (o, n, s) in items if o < hi and o + n > lo)
     early = sum(hi - lo for lo, hi, seg in gb.buckets if seg < nseg - 1)
     assert early > 0.8 * off, (early, off)   # most of the gradient travels before the last segment has run
+
+
+@pytest.mark.parametrize("name", ["v", "x_start"])
+def test_training_loss_of_x_start_and_v_objectives_matches_reference_fixture(name, layouts):
+    """p_losses target selection (:1990-1995) — dv_q_sample writes x_start / v next to x_t; loss against the reference's
+    own p_losses on the same video, noise and timesteps (bf16 activations: 2 %)."""
+    from conftest import golden
+    g = golden("sample_objectives.pt")
+    case = g["cases"][name]
+    kw, _ = CASES["tiny"]
+    u = Unet3D(**kw)
+    u.load_state_dict(synth_state_dict(layouts["tiny"], seed=g["weight_seed"]), strict=True)
+    dec = VideoDecoder(u, frame_size=16, frame_numbers=(4,), timesteps=g["timesteps"], learned_variance=False,
+                       video_cond_drop_prob=0.0, text_cond_drop_prob=0.0, **case["decoder_kwargs"]).cuda()
+    emb = torch.randn(2, 512, generator=torch.Generator().manual_seed(g["video_embed_seed"]))
+    gen = torch.Generator().manual_seed(g["loss_input_seed"])
+    video, noise = torch.rand(g["shape"], generator=gen), torch.randn(g["shape"], generator=gen)
+    times = torch.tensor(g["loss_times"])
+    loss = p_losses(dec, dec.unets[0], video.cuda(), times.cuda(), video_embed=emb.cuda(),
+                    noise_scheduler=dec.noise_schedulers[0], noise=noise.cuda(),
+                    predict_x_start=dec.predict_x_start[0], predict_v=dec.predict_v[0])
+    assert abs(float(loss) - case["loss"]) < 2e-2 * case["loss"], (float(loss), case["loss"])
+    loss.backward()
+    grads = [p.grad for p in dec.unets[0].parameters() if p.grad is not None]
+    assert len(grads) > 100 and all(bool(torch.isfinite(gr).all()) for gr in grads)
+    assert float(dec.unets[0].to_out.weight.grad.abs().max()) > 0
