@@ -23,14 +23,14 @@ class DdpmStepParams(C.Structure):
     _fields_ = [("x_t", vp), ("eps", vp), ("eps_null", vp), ("noise", vp), ("out", vp), ("unnormalize_out", vp),
                 ("coef", vp), ("t_dev", vp), ("t_host", i32), ("t_dev_decrement", i32), ("num_timesteps", i32),
                 ("n", i64), ("cond_scale", f32), ("clip_denoised", i32), ("eps_dtype", i32),
-                ("objective", i32), ("coef_v", vp), ("thres", vp), ("per_sample", i64)]
+                ("objective", i32), ("coef_v", vp), ("thres", vp), ("per_sample", i64), ("x0_out", vp)]
 
 
 class DdimStepParams(C.Structure):
     _fields_ = [("x_t", vp), ("eps", vp), ("eps_null", vp), ("noise", vp), ("out", vp), ("unnormalize_out", vp),
                 ("coef", vp), ("step_dev", vp), ("t_dev", vp), ("times", vp), ("step_host", i32), ("n_pairs", i32),
                 ("advance", i32), ("n", i64), ("cond_scale", f32), ("clip_denoised", i32), ("eps_dtype", i32),
-                ("objective", i32), ("coef_v", vp), ("thres", vp), ("per_sample", i64)]
+                ("objective", i32), ("coef_v", vp), ("thres", vp), ("per_sample", i64), ("x0_out", vp)]
 
 
 class X0ThresholdParams(C.Structure):

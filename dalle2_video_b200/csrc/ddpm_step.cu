@@ -34,7 +34,7 @@ __global__ void __launch_bounds__(256) ddpm_step_kernel(dv_ddpm_step_params p) {
   const int64_t n4 = p.n >> 2;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
-    float x[4], e[4], z[4], o[4];
+    float x[4], e[4], z[4], o[4], xs[4];
     load4(p.x_t + 4 * i, x);
     load4(eps + 4 * i, e);
     load4(p.noise + 4 * i, z);
@@ -49,10 +49,12 @@ __global__ void __launch_bounds__(256) ddpm_step_kernel(dv_ddpm_step_params p) {
     for (int k = 0; k < 4; ++k) {
       float x0 = form_x0(p.objective, x[k], e[k], c0, c1, va, vb);
       if (p.clip_denoised) x0 = clip_x0(x0, s_thr, dyn);
+      xs[k] = x0;
       const float mean = c2 * x0 + c3 * x[k];
       o[k] = mean + sigma * z[k];
     }
     store4(p.out + 4 * i, o);
+    if (p.x0_out) store4(p.x0_out + 4 * i, xs);
     if (unnorm) {
 #pragma unroll
       for (int k = 0; k < 4; ++k) o[k] = (o[k] + 1.0f) * 0.5f;
@@ -80,7 +82,7 @@ __global__ void __launch_bounds__(256) ddim_step_kernel(dv_ddim_step_params p) {
   const int64_t n4 = p.n >> 2;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
-    float x[4], e[4], z[4] = {0.f, 0.f, 0.f, 0.f}, o[4];
+    float x[4], e[4], z[4] = {0.f, 0.f, 0.f, 0.f}, o[4], xs[4];
     load4(p.x_t + 4 * i, x);
     load4(eps + 4 * i, e);
     if (!last) load4(p.noise + 4 * i, z);
@@ -96,10 +98,12 @@ __global__ void __launch_bounds__(256) ddim_step_kernel(dv_ddim_step_params p) {
       const float rx = r0 * x[k];
       float x0 = p.objective == DV_OBJ_EPS ? rx - r1 * e[k] : form_x0(p.objective, x[k], e[k], r0, r1, va, vb);
       if (p.clip_denoised) x0 = clip_x0(x0, s_thr, dyn);
+      xs[k] = x0;
       const float pn = (rx - x0) * inv_r1;
       o[k] = x0 * a + c1 * z[k] + c2 * pn;
     }
     store4(p.out + 4 * i, o);
+    if (p.x0_out) store4(p.x0_out + 4 * i, xs);
     if (unnorm) {
 #pragma unroll
       for (int k = 0; k < 4; ++k) o[k] = (o[k] + 1.0f) * 0.5f;
@@ -299,7 +303,7 @@ extern "C" int dv_ddpm_step(const dv_ddpm_step_params* p, dv_stream_t stream) {
   DV_REQUIRE(p->t_dev || (p->t_host >= 0 && p->t_host < p->num_timesteps), DV_EINVAL,
              "dv_ddpm_step: t=%d outside [0,%d)", p->t_host, p->num_timesteps);
   DV_REQUIRE(aligned16(p->x_t) && aligned16(p->noise) && aligned16(p->out) && aligned16(p->eps) &&
-                 aligned16(p->eps_null) && aligned16(p->unnormalize_out),
+                 aligned16(p->eps_null) && aligned16(p->unnormalize_out) && aligned16(p->x0_out),
              DV_EALIGN, "dv_ddpm_step: pointers must be 16-byte aligned");
   DV_REQUIRE(p->eps_dtype == DV_F32 || p->eps_dtype == DV_BF16, DV_EINVAL, "dv_ddpm_step: bad eps_dtype");
   DV_REQUIRE(p->objective >= DV_OBJ_EPS && p->objective <= DV_OBJ_V, DV_EINVAL, "dv_ddpm_step: bad objective %d", p->objective);
@@ -331,7 +335,7 @@ extern "C" int dv_ddim_step(const dv_ddim_step_params* p, dv_stream_t stream) {
              "dv_ddim_step: step %d outside [0,%d)", p->step_host, p->n_pairs);
   DV_REQUIRE(!p->advance || (p->step_dev && p->t_dev && p->times), DV_EINVAL, "dv_ddim_step: advance needs step_dev, t_dev and times");
   DV_REQUIRE(aligned16(p->x_t) && aligned16(p->noise) && aligned16(p->out) && aligned16(p->eps) && aligned16(p->eps_null) &&
-                 aligned16(p->unnormalize_out),
+                 aligned16(p->unnormalize_out) && aligned16(p->x0_out),
              DV_EALIGN, "dv_ddim_step: pointers must be 16-byte aligned");
   DV_REQUIRE(p->eps_dtype == DV_F32 || p->eps_dtype == DV_BF16, DV_EINVAL, "dv_ddim_step: bad eps_dtype");
   DV_REQUIRE(p->objective >= DV_OBJ_EPS && p->objective <= DV_OBJ_V, DV_EINVAL, "dv_ddim_step: bad objective %d", p->objective);

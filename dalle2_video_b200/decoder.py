@@ -272,6 +272,25 @@ class VideoDecoder(nn.Module):
                 quantile=float(self.dynamic_thres_percentile), objective=objective, eps_dtype=L.DV_F32)
         return extra, thr, keep
 
+    @staticmethod
+    def _state_buffers(unet, eng, shape, cfg, device):
+        """Where the sampler state lives.  Plain unets: x IS the first half of the plan's input (updated in place).
+        Self-conditioned unets (:738-740, :1727): the plan's input is cat(x, previous clipped x_start), so the state and
+        the x_start written by the step kernel are separate tensors and `feed()` assembles the input before each
+        forward (for both halves of a CFG batch).  Returns (feed or None, x, x0buf or None)."""
+        b, c = shape[0], shape[1]
+        if not unet.self_cond:
+            return None, eng.x_in[:b], None
+        x = torch.empty(shape, device=device)
+        x0buf = torch.zeros(shape, device=device)   # `default(self_cond, zeros_like(x))` on the first step
+
+        def feed():
+            eng.x_in[:b, :c].copy_(x)
+            eng.x_in[:b, c:].copy_(x0buf)
+            if cfg:
+                eng.x_in[b:].copy_(eng.x_in[:b])
+        return feed, x, x0buf
+
     def dynamic_threshold(self, x):
         """Reference: dalle2_video.py:1531-1549.  Static clamp to [-1, 1], or (use_dynamic_thres) clamp to the per-sample
         quantile of |x| found by the radix-select kernel (dv_x0_threshold), then divide by it."""
@@ -339,9 +358,9 @@ class VideoDecoder(nn.Module):
         coef = noise_scheduler.coef_table().to(device)
         draw = (lambda i: noise_fn(shape, i).to(device)) if noise_fn is not None else \
             (lambda i: torch.randn(shape, device=device))
-        x = eng.x_in[:b]
+        feed, x, x0buf = self._state_buffers(unet, eng, shape, cfg, device)
         x.copy_(draw(0))
-        if cfg:
+        if cfg and feed is None:
             eng.x_in[b:].copy_(x)
         noise = torch.empty(shape, device=device)
         result = torch.empty(shape, device=device)
@@ -356,14 +375,17 @@ class VideoDecoder(nn.Module):
             coef, eng.t_dev.data_ptr(), b, n, cond_scale, device)
         for k, v in extra.items():
             setattr(params, k, v)
+        params.x0_out = x0buf.data_ptr() if x0buf is not None else None
         stream_of = lambda: torch.cuda.current_stream(device).cuda_stream  # noqa: E731
 
         def one_step():
+            if feed is not None:
+                feed()
             eng.run()
             if thr_params is not None:
                 L.call("dv_x0_threshold", thr_params, stream_of())
             L.call("dv_ddpm_step", params, stream_of())
-            if cfg:
+            if cfg and feed is None:
                 eng.x_in[b:].copy_(x)
 
         eng.t_dev.fill_(steps - 1)
@@ -376,7 +398,9 @@ class VideoDecoder(nn.Module):
             one_step()
             torch.cuda.synchronize(device)
             x.copy_(saved)
-            if cfg:
+            if x0buf is not None:
+                x0buf.zero_()
+            if cfg and feed is None:
                 eng.x_in[b:].copy_(x)
             eng.t_dev.fill_(steps - 1)
             graph = torch.cuda.CUDAGraph()
@@ -471,9 +495,9 @@ class VideoDecoder(nn.Module):
         n = b * c * T * H * W
         draw = (lambda i: noise_fn(shape, i).to(device)) if noise_fn is not None else \
             (lambda i: torch.randn(shape, device=device))
-        x = eng.x_in[:b]
+        feed, x, x0buf = self._state_buffers(unet, eng, shape, cfg, device)
         x.copy_(draw(0))
-        if cfg:
+        if cfg and feed is None:
             eng.x_in[b:].copy_(x)
         noise = torch.zeros(shape, device=device)
         result = torch.empty(shape, device=device)
@@ -489,14 +513,17 @@ class VideoDecoder(nn.Module):
             step_dev.data_ptr(), b, n, cond_scale, device)
         for k, v in extra.items():
             setattr(params, k, v)
+        params.x0_out = x0buf.data_ptr() if x0buf is not None else None
         stream_of = lambda: torch.cuda.current_stream(device).cuda_stream  # noqa: E731
 
         def one_step():
+            if feed is not None:
+                feed()
             eng.run()
             if thr_params is not None:
                 L.call("dv_x0_threshold", thr_params, stream_of())
             L.call("dv_ddim_step", params, stream_of())
-            if cfg:
+            if cfg and feed is None:
                 eng.x_in[b:].copy_(x)
 
         def rewind():
@@ -510,7 +537,9 @@ class VideoDecoder(nn.Module):
             one_step()                      # warm-up outside capture, then rewind
             torch.cuda.synchronize(device)
             x.copy_(saved)
-            if cfg:
+            if x0buf is not None:
+                x0buf.zero_()
+            if cfg and feed is None:
                 eng.x_in[b:].copy_(x)
             rewind()
             graph = torch.cuda.CUDAGraph()

@@ -22,6 +22,7 @@ Text conditioning and the extensions (temporal conv / attention) have no backwar
 from __future__ import annotations
 
 import math
+import random
 
 import torch
 import torch.nn.functional as F
@@ -72,8 +73,8 @@ class _TrainPlan:
             raise NotImplementedError("training with text conditioning has no backward kernels yet (long-context cross attention)")
         if u.temporal_conv or any(u._stage_temporal_attn) or u.attn_mode != "joint":
             raise NotImplementedError("the extensions (temporal conv / attention, factorised attention) have no backward kernels")
-        if u.lowres_cond or u.self_cond or u.skip_connect_scale != 1.0:
-            raise NotImplementedError("lowres / self conditioning and scaled skip connections are outside the training plan")
+        if u.lowres_cond or u.skip_connect_scale != 1.0:
+            raise NotImplementedError("lowres conditioning and scaled skip connections are outside the training plan")
         self.u, self.B, self.T, self.H, self.W, self.device = u, B, T, H, W, device
         self.code = L.DV_BF16
         L.lib()
@@ -408,7 +409,7 @@ class _TrainPlan:
         n_img, P = B * T, T * H * W
         rows = B * P
         # ---- inputs: x_t (B,3,T,H,W) float32 -> CrossEmbedLayer3D as im2col + one GEMM (patches are kept for the wgrad)
-        self.x_in = torch.zeros(B, u.channels, T, H, W, device=dev)
+        self.x_in = torch.zeros(B, u.channels * (1 + int(u.self_cond)), T, H, W, device=dev)   # cat(x_t, self_cond), :738-740
         if not isinstance(u.init_conv, _CrossEmbed):
             raise NotImplementedError("training plan: init_cross_embed=False is not built")
         convs, ks = list(u.init_conv.convs), list(u.init_conv.kernel_sizes)
@@ -727,12 +728,21 @@ def p_losses(decoder, unet: Unet3D, x_start, times, *, video_embed, noise_schedu
     noise = noise.contiguous().float()
     objective = L.OBJ_V if predict_v else L.OBJ_X_START if predict_x_start else L.OBJ_EPS
     target = noise if objective == L.OBJ_EPS else torch.empty_like(noise)
+    x_t = torch.empty_like(x_start) if unet.self_cond else plan.x_in
     L.call("dv_q_sample", L.QSampleParams(
         video=x_start.data_ptr(), noise=noise.data_ptr(), times=times.data_ptr(),
         sqrt_ac=noise_scheduler.sqrt_alphas_cumprod.data_ptr(),
-        sqrt_1mac=noise_scheduler.sqrt_one_minus_alphas_cumprod.data_ptr(), out=plan.x_in.data_ptr(), n=x_start.numel(),
+        sqrt_1mac=noise_scheduler.sqrt_one_minus_alphas_cumprod.data_ptr(), out=x_t.data_ptr(), n=x_start.numel(),
         per_sample=x_start.numel() // B, normalize=0 if is_latent_diffusion else 1,
         target=target.data_ptr() if target is not noise else None, objective=objective), stream)
+    if unet.self_cond:
+        # self-conditioning (:1969-1976): half of the time a no-grad first pass (no conditioning dropout) predicts the
+        # network output that is concatenated to x_t; `random.random()` is the reference's draw
+        plan.x_in[:, :C].copy_(x_t)
+        if random.random() < 0.5:
+            plan.x_in[:, C:].copy_(unet(x_t, times, video_embed=video_embed))
+        else:
+            plan.x_in[:, C:].zero_()
     # prob_mask_like draws (reference :772-778): video mask, then text mask (drawn even without text conditioning)
     keep_v = _prob_mask(B, 1 - decoder.video_cond_drop_prob, dev)
     _prob_mask(B, 1 - decoder.text_cond_drop_prob, dev)

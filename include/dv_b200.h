@@ -81,6 +81,8 @@ typedef struct {
   const float* thres;    /* [n / per_sample] s_b >= 1 from dv_x0_threshold: x0 = clamp(x0, -s_b, s_b) / s_b
                             (VideoDecoder.dynamic_threshold :1531-1549); NULL = clamp to [-1, 1] */
   int64_t per_sample;    /* elements per sample (multiple of 4), needed with thres */
+  float* x0_out;         /* optional [n]: the clipped x_start, p_sample's second return value (:1656) — what a
+                            self-conditioned Unet3D receives on the next step (:1727) */
 } dv_ddpm_step_params;
 int dv_ddpm_step(const dv_ddpm_step_params* p, dv_stream_t stream);
 
@@ -109,6 +111,7 @@ typedef struct {
   const float* coef_v;   /* [n_pairs][2] {sqrt_alphas_cumprod[t], sqrt_one_minus_alphas_cumprod[t]} per pair */
   const float* thres;    /* [n / per_sample] or NULL */
   int64_t per_sample;
+  float* x0_out;         /* optional [n]: the clipped x_start (self-conditioning, :1830) */
 } dv_ddim_step_params;
 int dv_ddim_step(const dv_ddim_step_params* p, dv_stream_t stream);
 

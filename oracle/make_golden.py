@@ -203,6 +203,35 @@ def objectives():
                             predict_x_start=dec.predict_x_start[0], predict_v=dec.predict_v[0])
         out[name] = {"decoder_kwargs": kw, "cond_scale": cond_scale, "sample": vid, "loss": float(loss)}
         print("objective", name, float(vid.mean()), float(vid.std()), float(loss))
+    # self-conditioning (Unet3D(self_cond=True), :738-740; the loop feeds the previous step's clipped x_start, :1727):
+    # DDPM sampling, and one training loss with the no-grad first pass forced on (random.random() < 0.5, :1971)
+    import random
+    kw_sc = dict(CASES["tiny"]["unet"], self_cond=True)
+    torch.manual_seed(0)
+    unet = ref.Unet3D(**kw_sc)
+    layouts["tiny_self_cond"] = shapes_of(unet)
+    dec = ref.VideoDecoder(unet, frame_size=16, frame_numbers=(4,), timesteps=12, learned_variance=False)
+    dec.unets[0].load_state_dict(synth_state_dict(layouts["tiny_self_cond"], seed=7), strict=True)
+    dec.eval()
+    emb = torch.randn(2, 512, generator=torch.Generator().manual_seed(21))
+    torch.manual_seed(4242)
+    vid = dec.sample(video_embed=emb)
+    dec.video_cond_drop_prob, dec.text_cond_drop_prob = 0.0, 0.0
+    g = torch.Generator().manual_seed(77)
+    video, noise = torch.rand(2, 3, 4, 16, 16, generator=g), torch.randn(2, 3, 4, 16, 16, generator=g)
+    losses = {}
+    for seed, label in ((1, "with_first_pass"), (2, "without_first_pass")):
+        random.seed(seed)
+        took = random.random() < 0.5
+        random.seed(seed)
+        assert took == (label == "with_first_pass"), (seed, took)
+        losses[label] = float(dec.p_losses(dec.unets[0], video, torch.tensor([2, 9]), video_embed=emb,
+                                           noise_scheduler=dec.noise_schedulers[0], noise=noise))
+    out["self_cond"] = {"decoder_kwargs": {}, "unet_kwargs": kw_sc, "cond_scale": 1.0, "sample": vid, "loss": losses,
+                        "python_random_seeds": {"with_first_pass": 1, "without_first_pass": 2}}
+    print("self_cond", float(vid.mean()), float(vid.std()), losses)
+    with open(os.path.join(GOLDEN, "state_dict_layouts.json"), "w") as f:
+        json.dump(layouts, f, indent=0, sort_keys=True)
     torch.save({"cases": out, "video_embed_seed": 21, "sample_seed": 4242, "weight_seed": 7, "timesteps": 12,
                 "shape": (2, 3, 4, 16, 16), "loss_input_seed": 77, "loss_times": (2, 9)},
                os.path.join(GOLDEN, "sample_objectives.pt"))

@@ -412,12 +412,15 @@ def p_sample_loop_ddpm(sd, cfg, sched: NoiseScheduler, shape, *, video_embed, te
     kw = {}
     if lowres_cond_vid is not None:
         kw = dict(lowres_cond_video=lowres_cond_vid * 2 - 1, lowres_noise_level=lowres_noise_level)
+    x_start = None   # self-conditioning: the previous step's clipped x_start (:1727), zeros on the first step (:739)
     for t_int in reversed(range(sched.num_timesteps)):
         times = torch.full((shape[0],), t_int, dtype=torch.long)
+        if cfg.self_cond:
+            kw["self_cond"] = x_start
         eps = forward_with_cond_scale(sd, cfg, vid, times, video_embed=video_embed,
                                       text_encodings=text_encodings, cond_scale=cond_scale, **kw)
         noise = torch.randn(shape, generator=generator)
-        vid, _ = ddpm_posterior_step(sched, vid, t_int, eps, noise, clip_denoised, objective, dynamic_thres_percentile)
+        vid, x_start = ddpm_posterior_step(sched, vid, t_int, eps, noise, clip_denoised, objective, dynamic_thres_percentile)
         if record is not None:
             record(t_int, eps, vid)
     return (vid + 1) * 0.5
@@ -472,12 +475,14 @@ def p_sample_loop_ddim(sd, cfg, sched: NoiseScheduler, shape, *, video_embed, ti
     RNG contract: randn(shape), then one randn per step except the last (:1870)."""
     alphas = sched.alphas_cumprod
     vid = torch.randn(shape, generator=generator)
+    x_start = None   # self-conditioning (:1830)
     for time, time_next in ddim_time_pairs(sched.num_timesteps, timesteps):
         is_last = time_next == 0
         alpha, alpha_next = alphas[time], alphas[time_next]
         t = torch.full((shape[0],), time, dtype=torch.long)
+        kw = dict(self_cond=x_start) if cfg.self_cond else {}
         pred = forward_with_cond_scale(sd, cfg, vid, t, video_embed=video_embed, text_encodings=text_encodings,
-                                       cond_scale=cond_scale)
+                                       cond_scale=cond_scale, **kw)
         x_start = x_start_from(sched, vid, t, pred, objective)
         if clip_denoised:
             x_start = dynamic_threshold(x_start, dynamic_thres_percentile)

@@ -338,3 +338,45 @@ def test_p_mean_variance_and_dynamic_threshold_method(layouts):
     xs = sched.predict_start_from_v(x, t, out)
     s = torch.quantile(xs.flatten(1).abs(), 0.8, dim=-1).clamp(min=1.0).view(-1, 1, 1, 1, 1)
     assert torch.allclose(x_start, xs.clamp(-s, s) / s, rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize("graph", [False, True])
+def test_self_conditioned_sampling_matches_reference_fixture(graph, layouts):
+    """Unet3D(self_cond=True): the step kernel's x0_out (clipped x_start) is the next step's self_cond (:1727, :738-740)."""
+    g = golden("sample_objectives.pt")
+    case = g["cases"]["self_cond"]
+    u = Unet3D(**case["unet_kwargs"])
+    u.load_state_dict(synth_state_dict(layouts["tiny_self_cond"], seed=g["weight_seed"]), strict=True)
+    d = VideoDecoder(u, frame_size=16, frame_numbers=(4,), timesteps=g["timesteps"], learned_variance=False).cuda()
+    d.use_cuda_graph = graph
+    emb = torch.randn(2, 512, generator=torch.Generator().manual_seed(g["video_embed_seed"]))
+    vid = d.sample(video_embed=emb.cuda(), noise_fn=cpu_noise(g["sample_seed"]))
+    assert d.last_launch_stats["graph"] == graph
+    err = float((vid.cpu() - case["sample"]).abs().max())
+    assert err < 2e-3, err
+
+
+def test_self_conditioned_cfg_and_ddim_match_oracle_loops(layouts):
+    from oracle.primitives import NoiseScheduler as OracleScheduler
+    from oracle.unet3d import UnetConfig, p_sample_loop_ddim, p_sample_loop_ddpm
+    kw = dict(TINY, self_cond=True)
+    sd = synth_state_dict(layouts["tiny_self_cond"], seed=7)
+    emb = torch.randn(2, 512, generator=torch.Generator().manual_seed(4))
+    # 8 steps: with random weights the self-conditioning feedback doubles a 1e-4 difference every ~2 steps under a 2x
+    # guidance gain (measured per step with tools/diag_sc.py), so longer chains test chaos, not the kernels
+    for sample_steps in (None, 5):
+        u = Unet3D(**kw)
+        u.load_state_dict(sd, strict=True)
+        d = VideoDecoder(u, frame_size=16, frame_numbers=(4,), timesteps=8, sample_timesteps=sample_steps,
+                         learned_variance=False, video_cond_drop_prob=0.1, ddim_sampling_eta=0.4).cuda()
+        vid = d.sample(video_embed=emb.cuda(), cond_scale=2.0, noise_fn=cpu_noise(55))
+        sched = OracleScheduler(beta_schedule="cosine", timesteps=8, loss_type="l2")
+        with torch.no_grad():
+            if sample_steps is None:
+                ref = p_sample_loop_ddpm(sd, UnetConfig(**kw), sched, (2, 3, 4, 16, 16), video_embed=emb, cond_scale=2.0,
+                                         generator=torch.Generator().manual_seed(55))
+            else:
+                ref = p_sample_loop_ddim(sd, UnetConfig(**kw), sched, (2, 3, 4, 16, 16), video_embed=emb, timesteps=5, eta=0.4,
+                                         cond_scale=2.0, generator=torch.Generator().manual_seed(55))
+        err = float((vid.cpu() - ref).abs().max())
+        assert err < 2e-3, (sample_steps, err)

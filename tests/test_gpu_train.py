@@ -213,3 +213,28 @@ def test_training_loss_of_x_start_and_v_objectives_matches_reference_fixture(nam
     grads = [p.grad for p in dec.unets[0].parameters() if p.grad is not None]
     assert len(grads) > 100 and all(bool(torch.isfinite(gr).all()) for gr in grads)
     assert float(dec.unets[0].to_out.weight.grad.abs().max()) > 0
+
+
+@pytest.mark.parametrize("label", ["with_first_pass", "without_first_pass"])
+def test_self_conditioned_training_loss_matches_reference_fixture(label, layouts):
+    """p_losses with Unet3D(self_cond=True) (:1969-1983): `random.random() < 0.5` decides whether a no-grad first pass
+    supplies the self-conditioning planes; both branches against the reference's loss (bf16: 2 %)."""
+    import random
+    from conftest import golden
+    g = golden("sample_objectives.pt")
+    case = g["cases"]["self_cond"]
+    u = Unet3D(**case["unet_kwargs"])
+    u.load_state_dict(synth_state_dict(layouts["tiny_self_cond"], seed=g["weight_seed"]), strict=True)
+    dec = VideoDecoder(u, frame_size=16, frame_numbers=(4,), timesteps=g["timesteps"], learned_variance=False,
+                       video_cond_drop_prob=0.0, text_cond_drop_prob=0.0).cuda()
+    emb = torch.randn(2, 512, generator=torch.Generator().manual_seed(g["video_embed_seed"]))
+    gen = torch.Generator().manual_seed(g["loss_input_seed"])
+    video, noise = torch.rand(g["shape"], generator=gen), torch.randn(g["shape"], generator=gen)
+    random.seed(case["python_random_seeds"][label])
+    loss = p_losses(dec, dec.unets[0], video.cuda(), torch.tensor(g["loss_times"]).cuda(), video_embed=emb.cuda(),
+                    noise_scheduler=dec.noise_schedulers[0], noise=noise.cuda())
+    want = case["loss"][label]
+    assert abs(float(loss) - want) < 2e-2 * want, (float(loss), want)
+    loss.backward()
+    gw = dec.unets[0].init_conv.convs[0].weight.grad
+    assert gw is not None and gw.shape[1] == 6 and float(gw[:, 3:].abs().max()) > 0 or label == "without_first_pass"

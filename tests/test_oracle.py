@@ -219,3 +219,29 @@ def test_training_target_of_each_objective_matches_reference_loss(name, layouts)
     target = {"eps": noise, "x_start": x0, "v": sched.calculate_v(x0, times, noise)}[objective]
     loss = float(F.mse_loss(pred, target, reduction="none").flatten(1).mean(1).mean())
     assert abs(loss - case["loss"]) < 1e-5 * max(1.0, case["loss"]), (loss, case["loss"])
+
+
+def test_self_conditioned_sampler_and_loss_match_reference_fixture(layouts):
+    # Unet3D(self_cond=True): cat(x, self_cond) into the init conv (:738-740); the loop passes the previous clipped x_start
+    # (:1727); p_losses runs a no-grad first pass with probability 1/2 (:1969-1976)
+    import torch.nn.functional as F
+    g = golden("sample_objectives.pt")
+    case = g["cases"]["self_cond"]
+    cfg = UnetConfig(**case["unet_kwargs"])
+    sd = synth_state_dict(layouts["tiny_self_cond"], seed=g["weight_seed"])
+    sched = P.NoiseScheduler(beta_schedule="cosine", timesteps=g["timesteps"], loss_type="l2")
+    emb = torch.randn(2, 512, generator=torch.Generator().manual_seed(g["video_embed_seed"]))
+    torch.manual_seed(g["sample_seed"])
+    with torch.no_grad():
+        vid = p_sample_loop_ddpm(sd, cfg, sched, tuple(g["shape"]), video_embed=emb)
+    assert float((vid - case["sample"]).abs().max()) < 1e-3
+    gen = torch.Generator().manual_seed(g["loss_input_seed"])
+    video, noise = torch.rand(g["shape"], generator=gen), torch.randn(g["shape"], generator=gen)
+    times = torch.tensor(g["loss_times"])
+    x_t = sched.q_sample(video * 2 - 1, times, noise)
+    with torch.no_grad():
+        first = unet3d_forward(sd, cfg, x_t, times, video_embed=emb)
+        for label, sc in (("with_first_pass", first), ("without_first_pass", None)):
+            pred = unet3d_forward(sd, cfg, x_t, times, video_embed=emb, self_cond=sc)
+            loss = float(F.mse_loss(pred, noise, reduction="none").flatten(1).mean(1).mean())
+            assert abs(loss - case["loss"][label]) < 1e-5 * case["loss"][label], (label, loss)
