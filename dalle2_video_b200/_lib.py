@@ -189,7 +189,11 @@ class QSampleParams(C.Structure):
 
 
 class MseLossParams(C.Structure):
-    _fields_ = [("pred", vp), ("target", vp), ("dpred", vp), ("loss", vp), ("n", i64), ("grad_scale", f32)]
+    _fields_ = [("pred", vp), ("target", vp), ("dpred", vp), ("loss", vp), ("n", i64), ("grad_scale", f32),
+                ("kind", i32), ("sample_weight", vp), ("per_sample", i64)]
+
+
+LOSS_KINDS = {"l2": 0, "l1": 1, "huber": 2}
 
 
 class ToOutBwdParams(C.Structure):

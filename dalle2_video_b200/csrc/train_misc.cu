@@ -49,11 +49,23 @@ __global__ void __launch_bounds__(256) resize_nearest_kernel(dv_resize_nearest_p
 __global__ void __launch_bounds__(256) mse_loss_kernel(dv_mse_loss_params p) {
   __shared__ double red[8];
   double acc = 0.0;
-  const float k = 2.0f * p.grad_scale / (float)p.n;
+  const float k = p.grad_scale / (float)p.n;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < p.n; i += (int64_t)gridDim.x * blockDim.x) {
     const float d = p.pred[i] - p.target[i];
-    acc += (double)d * d;
-    if (p.dpred) p.dpred[i] = k * d;
+    const float w = p.sample_weight ? p.sample_weight[i / p.per_sample] : 1.0f;
+    float f, df;
+    if (p.kind == DV_LOSS_L2) {
+      f = d * d;
+      df = 2.0f * d;
+    } else if (p.kind == DV_LOSS_L1 || fabsf(d) >= 1.0f) {
+      f = fabsf(d) - (p.kind == DV_LOSS_HUBER ? 0.5f : 0.0f);
+      df = d > 0.0f ? 1.0f : (d < 0.0f ? -1.0f : 0.0f);
+    } else {
+      f = 0.5f * d * d;
+      df = d;
+    }
+    acc += (double)w * f;
+    if (p.dpred) p.dpred[i] = k * w * df;
   }
   for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
@@ -221,6 +233,9 @@ extern "C" int dv_mse_loss(const dv_mse_loss_params* p, dv_stream_t stream) {
   using namespace dv;
   DV_REQUIRE(p && p->pred && p->target && p->loss, DV_EINVAL, "dv_mse_loss: null pointer");
   DV_REQUIRE(p->n > 0, DV_EINVAL, "dv_mse_loss: bad size");
+  DV_REQUIRE(p->kind >= DV_LOSS_L2 && p->kind <= DV_LOSS_HUBER, DV_EINVAL, "dv_mse_loss: bad kind %d", p->kind);
+  DV_REQUIRE(!p->sample_weight || (p->per_sample > 0 && p->n % p->per_sample == 0), DV_EINVAL,
+             "dv_mse_loss: sample_weight needs per_sample dividing n");
   int64_t blocks = (p->n + 255) / 256;
   if (blocks > 148 * 8) blocks = 148 * 8;
   mse_loss_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(*p);

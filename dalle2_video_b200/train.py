@@ -695,8 +695,12 @@ class _PlanFunction(torch.autograd.Function):
         plan.run_forward()
         loss = torch.zeros(1, dtype=torch.float64, device=plan.device)
         stream = torch.cuda.current_stream(plan.device).cuda_stream
+        kind, weight = plan.loss_opts
+        ctx.loss_kw = dict(kind=kind, sample_weight=weight.data_ptr() if weight is not None else None,
+                           per_sample=noise.numel() // plan.B)
+        ctx.weight = weight
         L.call("dv_mse_loss", L.MseLossParams(pred=plan.eps.data_ptr(), target=noise.data_ptr(), dpred=None,
-                                              loss=loss.data_ptr(), n=noise.numel(), grad_scale=1.0), stream)
+                                              loss=loss.data_ptr(), n=noise.numel(), grad_scale=1.0, **ctx.loss_kw), stream)
         ctx.plan, ctx.noise = plan, noise
         return loss[0].float()
 
@@ -706,7 +710,8 @@ class _PlanFunction(torch.autograd.Function):
         stream = torch.cuda.current_stream(plan.device).cuda_stream
         scratch = torch.zeros(1, dtype=torch.float64, device=plan.device)
         L.call("dv_mse_loss", L.MseLossParams(pred=plan.eps.data_ptr(), target=noise.data_ptr(), dpred=plan.deps.data_ptr(),
-                                              loss=scratch.data_ptr(), n=noise.numel(), grad_scale=float(grad_out)), stream)
+                                              loss=scratch.data_ptr(), n=noise.numel(), grad_scale=float(grad_out),
+                                              **ctx.loss_kw), stream)
         plan.run_backward()
         return (None, None, plan.dss.clone(), *[plan.dkv[k].clone() for k in plan.kv_kinds])
 
@@ -746,6 +751,9 @@ def p_losses(decoder, unet: Unet3D, x_start, times, *, video_embed, noise_schedu
     # prob_mask_like draws (reference :772-778): video mask, then text mask (drawn even without text conditioning)
     keep_v = _prob_mask(B, 1 - decoder.video_cond_drop_prob, dev)
     _prob_mask(B, 1 - decoder.text_cond_drop_prob, dev)
+    # loss_fn (l1 / l2 / huber) and p2 reweighting (:1997-2003) are applied inside dv_mse_loss
+    weight = noise_scheduler.p2_loss_weight[times].float().contiguous() if noise_scheduler.has_p2_loss_reweighting else None
+    plan.loss_opts = (L.LOSS_KINDS[noise_scheduler.loss_type], weight)
     outs = plan.prologue(times, video_embed.float(), keep_v)
     return _PlanFunction.apply(plan, target, outs["ss"], *[outs[k] for k in plan.kv_kinds])
 

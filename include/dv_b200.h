@@ -660,10 +660,19 @@ typedef struct {
 } dv_q_sample_params;
 int dv_q_sample(const dv_q_sample_params* p, dv_stream_t stream);
 
-/* *loss += mean((pred-target)^2) (double, caller zeroes); dpred = grad_scale * 2 (pred-target) / n (or NULL) */
+/* The loss of p_losses (:1997-2003): *loss += mean_b( w_b * mean_i f(pred - target) ) (double, caller zeroes) and
+ * dpred = grad_scale * w_b * f'(pred - target) / n (or NULL).
+ *   kind DV_LOSS_L2: f = d^2 (F.mse_loss)   DV_LOSS_L1: |d| (F.l1_loss)   DV_LOSS_HUBER: F.smooth_l1_loss, beta 1
+ *   sample_weight[b] = NoiseScheduler.p2_loss_weight[times[b]] (p2_reweigh_loss) or NULL for w_b = 1. */
+#define DV_LOSS_L2 0
+#define DV_LOSS_L1 1
+#define DV_LOSS_HUBER 2
 typedef struct {
   const float* pred; const float* target; float* dpred; double* loss;
   int64_t n; float grad_scale;
+  int kind;
+  const float* sample_weight;   /* [n / per_sample] or NULL */
+  int64_t per_sample;           /* needed with sample_weight */
 } dv_mse_loss_params;
 int dv_mse_loss(const dv_mse_loss_params* p, dv_stream_t stream);
 

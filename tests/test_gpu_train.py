@@ -238,3 +238,49 @@ def test_self_conditioned_training_loss_matches_reference_fixture(label, layouts
     loss.backward()
     gw = dec.unets[0].init_conv.convs[0].weight.grad
     assert gw is not None and gw.shape[1] == 6 and float(gw[:, 3:].abs().max()) > 0 or label == "without_first_pass"
+
+
+@pytest.mark.parametrize("kind", ["l2", "l1", "huber"])
+@pytest.mark.parametrize("weighted", [False, True])
+def test_loss_kernel_kinds_and_p2_weights_match_torch_autograd(kind, weighted):
+    """dv_mse_loss = noise_scheduler.loss_fn(pred, target, 'none') -> per-sample mean -> p2_reweigh_loss -> mean (:1997-2003)."""
+    from dalle2_video_b200 import _lib as L
+    from gpu_util import ptr, stream
+    g = torch.Generator().manual_seed(5)
+    pred = (torch.randn(3, 3, 4, 8, 8, generator=g) * 1.5).cuda().requires_grad_()
+    target = torch.randn(3, 3, 4, 8, 8, generator=g).cuda()
+    w = torch.tensor([0.3, 1.0, 2.5]).cuda() if weighted else None
+    fn = {"l2": F.mse_loss, "l1": F.l1_loss, "huber": F.smooth_l1_loss}[kind]
+    per = fn(pred, target, reduction="none").flatten(1).mean(1)
+    ref = (per * w if weighted else per).mean()
+    ref.backward()
+    loss = torch.zeros(1, dtype=torch.float64, device="cuda")
+    dpred = torch.empty_like(target)
+    L.call("dv_mse_loss", L.MseLossParams(pred=ptr(pred), target=ptr(target), dpred=ptr(dpred), loss=ptr(loss), n=pred.numel(),
+                                          grad_scale=0.7, kind=L.LOSS_KINDS[kind], sample_weight=ptr(w) if weighted else None,
+                                          per_sample=pred.numel() // 3), stream())
+    assert abs(float(loss) - float(ref)) < 1e-5 * float(ref)
+    assert rel_err(dpred, 0.7 * pred.grad) < 1e-5
+
+
+def test_huber_loss_with_p2_reweighting_through_the_decoder(layouts):
+    kw, _ = CASES["tiny"]
+    u = Unet3D(**kw)
+    sd = synth_state_dict(layouts["tiny"], seed=7)
+    u.load_state_dict(sd, strict=True)
+    dec = VideoDecoder(u, frame_size=16, frame_numbers=(4,), timesteps=100, learned_variance=False, loss_type="huber",
+                       p2_loss_weight_gamma=1.0, video_cond_drop_prob=0.0, text_cond_drop_prob=0.0).cuda()
+    g = torch.Generator().manual_seed(3)
+    shape = (2, 3, 4, 16, 16)
+    video, noise, emb = torch.rand(shape, generator=g), torch.randn(shape, generator=g), torch.randn(2, 512, generator=g)
+    times = torch.tensor([7, 63])
+    sched = OracleScheduler(beta_schedule="cosine", timesteps=100, loss_type="huber", p2_loss_weight_gamma=1.0)
+    with torch.no_grad():
+        pred = unet3d_forward(sd, UnetConfig(**kw), sched.q_sample(2 * video - 1, times, noise), times, video_embed=emb)
+    per = F.smooth_l1_loss(pred, noise, reduction="none").flatten(1).mean(1)
+    ref = float(sched.p2_reweigh_loss(per, times).mean())
+    loss = p_losses(dec, dec.unets[0], video.cuda(), times.cuda(), video_embed=emb.cuda(),
+                    noise_scheduler=dec.noise_schedulers[0], noise=noise.cuda())
+    assert abs(float(loss) - ref) < 2e-2 * ref, (float(loss), ref)
+    loss.backward()
+    assert float(dec.unets[0].to_out.weight.grad.abs().max()) > 0
