@@ -188,6 +188,11 @@ class QSampleParams(C.Structure):
                 ("objective", i32)]
 
 
+class GaussianBlurParams(C.Structure):
+    _fields_ = [("in_", vp), ("out", vp), ("planes", i64), ("H", i32), ("W", i32), ("k", i32), ("wy", f32 * 16),
+                ("wx", f32 * 16)]
+
+
 class MseLossParams(C.Structure):
     _fields_ = [("pred", vp), ("target", vp), ("dpred", vp), ("loss", vp), ("n", i64), ("grad_scale", f32),
                 ("kind", i32), ("sample_weight", vp), ("per_sample", i64)]
@@ -198,7 +203,7 @@ LOSS_KINDS = {"l2": 0, "l1": 1, "huber": 2}
 
 class ToOutBwdParams(C.Structure):
     _fields_ = [("x", vp), ("w", vp), ("deps", vp), ("dx", vp), ("dw", vp), ("db", vp), ("B", i32), ("P", i64),
-                ("C", i32), ("Cout", i32), ("dtype", i32)]
+                ("C", i32), ("Cout", i32), ("dtype", i32), ("extra", vp), ("Cextra", i32)]
 
 
 class SiluShuffleParams(C.Structure):
@@ -238,7 +243,7 @@ ENTRY_POINTS = {
     # training step (a16)
     "dv_conv_wgrad": ConvWgradParams, "dv_colsum": ColsumParams, "dv_gn_bwd_reduce": GnBwdParams,
     "dv_gn_bwd_apply": GnBwdParams, "dv_layernorm_bwd": LayerNormBwdParams, "dv_xattn_core_bwd": XattnBwdParams,
-    "dv_attn_mqa_bwd": AttnMqaBwdParams, "dv_q_sample": QSampleParams, "dv_mse_loss": MseLossParams,
+    "dv_attn_mqa_bwd": AttnMqaBwdParams, "dv_q_sample": QSampleParams, "dv_gaussian_blur": GaussianBlurParams, "dv_mse_loss": MseLossParams,
     "dv_to_out_bwd": ToOutBwdParams, "dv_silu_shuffle": SiluShuffleParams, "dv_silu_shuffle_bwd": SiluShuffleParams,
     "dv_add": AddParams, "dv_cast_f32_bf16": CastParams, "dv_sumsq": SumsqParams, "dv_adamw": AdamwParams,
 }

@@ -46,6 +46,31 @@ __global__ void __launch_bounds__(256) resize_nearest_kernel(dv_resize_nearest_p
   }
 }
 
+// Per-frame Gaussian blur with reflect borders (kornia gaussian_blur2d semantics); one thread per output pixel.
+__global__ void __launch_bounds__(256) gaussian_blur_kernel(dv_gaussian_blur_params p) {
+  const int64_t per = (int64_t)p.H * p.W, total = p.planes * per;
+  const int r = p.k / 2;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t pl = i / per;
+    const int rem = (int)(i - pl * per);
+    const int y = rem / p.W, x = rem - y * p.W;
+    const float* src = p.in + pl * per;
+    float acc = 0.f;
+    for (int a = 0; a < p.k; ++a) {
+      int yy = y + a - r;
+      yy = yy < 0 ? -yy : (yy >= p.H ? 2 * (p.H - 1) - yy : yy);
+      float row = 0.f;
+      for (int b = 0; b < p.k; ++b) {
+        int xx = x + b - r;
+        xx = xx < 0 ? -xx : (xx >= p.W ? 2 * (p.W - 1) - xx : xx);
+        row = fmaf(p.wx[b], src[yy * p.W + xx], row);
+      }
+      acc = fmaf(p.wy[a], row, acc);
+    }
+    p.out[i] = acc;
+  }
+}
+
 __global__ void __launch_bounds__(256) mse_loss_kernel(dv_mse_loss_params p) {
   __shared__ double red[8];
   double acc = 0.0;
@@ -82,12 +107,15 @@ template <typename T, int CO>
 __global__ void __launch_bounds__(256) to_out_bwd_kernel(dv_to_out_bwd_params p) {
   const int lane = threadIdx.x & 31;
   const int nci = p.C / 32;
-  float w[CO][8], dw[CO][8], db[CO];
+  const int ld = p.C + p.Cextra;   // row length of w / dw
+  const bool has_extra = p.extra != nullptr && lane < p.Cextra;
+  float w[CO][8], dw[CO][8], db[CO], dwe[CO];
 #pragma unroll
   for (int o = 0; o < CO; ++o) {
     db[o] = 0.f;
+    dwe[o] = 0.f;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { dw[o][i] = 0.f; w[o][i] = i < nci ? p.w[o * p.C + lane + 32 * i] : 0.f; }
+    for (int i = 0; i < 8; ++i) { dw[o][i] = 0.f; w[o][i] = i < nci ? p.w[o * ld + lane + 32 * i] : 0.f; }
   }
   const int64_t total = (int64_t)p.B * p.P;
   const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
@@ -96,6 +124,11 @@ __global__ void __launch_bounds__(256) to_out_bwd_kernel(dv_to_out_bwd_params p)
     float de[CO];
 #pragma unroll
     for (int o = 0; o < CO; ++o) { de[o] = p.deps[(b * CO + o) * p.P + pos]; db[o] += de[o]; }
+    if (has_extra) {   // lane j < Cextra owns the weight-gradient column of extra plane j
+      const float ev = p.extra[(b * p.Cextra + lane) * p.P + pos];
+#pragma unroll
+      for (int o = 0; o < CO; ++o) dwe[o] = fmaf(de[o], ev, dwe[o]);
+    }
     const T* x = reinterpret_cast<const T*>(p.x) + r * p.C;
     T* dx = reinterpret_cast<T*>(p.dx) + r * p.C;
 #pragma unroll
@@ -113,7 +146,8 @@ __global__ void __launch_bounds__(256) to_out_bwd_kernel(dv_to_out_bwd_params p)
   for (int o = 0; o < CO; ++o) {
 #pragma unroll
     for (int i = 0; i < 8; ++i)
-      if (i < nci) atomicAdd(p.dw + o * p.C + lane + 32 * i, dw[o][i]);
+      if (i < nci) atomicAdd(p.dw + o * ld + lane + 32 * i, dw[o][i]);
+    if (has_extra) atomicAdd(p.dw + o * ld + p.C + lane, dwe[o]);
     if (lane == 0) atomicAdd(p.db + o, db[o]);
   }
 }
@@ -229,6 +263,19 @@ extern "C" int dv_resize_nearest(const dv_resize_nearest_params* p, dv_stream_t 
   return DV_OK;
 }
 
+extern "C" int dv_gaussian_blur(const dv_gaussian_blur_params* p, dv_stream_t stream) {
+  using namespace dv;
+  DV_REQUIRE(p && p->in && p->out && p->in != p->out, DV_EINVAL, "dv_gaussian_blur: null pointer or in-place call");
+  DV_REQUIRE(p->planes > 0 && p->H > 0 && p->W > 0, DV_EINVAL, "dv_gaussian_blur: bad sizes");
+  DV_REQUIRE(p->k >= 1 && p->k <= 15 && (p->k & 1), DV_EUNSUPPORTED, "dv_gaussian_blur: kernel size %d (odd, <= 15)", p->k);
+  DV_REQUIRE(p->k / 2 < p->H && p->k / 2 < p->W, DV_EINVAL, "dv_gaussian_blur: reflect padding needs k/2 < H, W");
+  int64_t blocks = (p->planes * p->H * p->W + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  gaussian_blur_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(*p);
+  DV_CHECK_LAUNCH("dv_gaussian_blur");
+  return DV_OK;
+}
+
 extern "C" int dv_mse_loss(const dv_mse_loss_params* p, dv_stream_t stream) {
   using namespace dv;
   DV_REQUIRE(p && p->pred && p->target && p->loss, DV_EINVAL, "dv_mse_loss: null pointer");
@@ -249,6 +296,8 @@ extern "C" int dv_to_out_bwd(const dv_to_out_bwd_params* p, dv_stream_t stream) 
   DV_REQUIRE(p->B > 0 && p->P > 0 && p->C > 0 && p->C % 32 == 0 && p->C <= 256, DV_EUNSUPPORTED,
              "dv_to_out_bwd: needs C %% 32 == 0 and C <= 256 (C=%d)", p->C);
   DV_REQUIRE(p->Cout == 3 || p->Cout == 6, DV_EUNSUPPORTED, "dv_to_out_bwd: channels_out must be 3 or 6 (got %d)", p->Cout);
+  DV_REQUIRE((p->extra == nullptr) == (p->Cextra == 0) && p->Cextra >= 0 && p->Cextra <= 32, DV_EINVAL,
+             "dv_to_out_bwd: extra / Cextra mismatch (Cextra=%d, at most 32)", p->Cextra);
   const unsigned blocks = 148 * 8;
   cudaStream_t s = as_stream(stream);
 #define DV_TOB(T, CO) to_out_bwd_kernel<T, CO><<<blocks, 256, 0, s>>>(*p)

@@ -12,6 +12,7 @@ device memory; classifier-free guidance runs cond+uncond as one 2B batch instead
 """
 from __future__ import annotations
 
+import random
 from contextlib import nullcontext
 
 import torch
@@ -66,8 +67,8 @@ def resize_video_to(video, target_frame_size, clamp_range=None):
 
 class LowresVideoConditioner:
     """Reference: dalle2_video.py:1044-1166.  At sampling time only the per-frame nearest resize and the optional
-    Imagen-style noise augmentation are used (:2126-2147); both run as native kernels.  The training-time blur
-    (kornia gaussian_blur2d, random) is outside the accelerated path."""
+    Imagen-style noise augmentation are used (:2126-2147); in training also the random Gaussian blur (:1135-1144).  All
+    three run as native kernels."""
 
     def __init__(self, downsample_first=True, use_blur=True, blur_prob=0.5, blur_sigma=0.6, blur_kernel_size=3,
                  use_noise=False, input_video_range=None, normalize_video=True):
@@ -100,12 +101,37 @@ class LowresVideoConditioner:
             unnormalize=int(self._normalize)), torch.cuda.current_stream(dev).cuda_stream)
         return out, noise_levels
 
-    def __call__(self, cond_fmap, *, target_frame_size, downsample_frame_size=None, should_blur=True, **kwargs):
-        if self.use_blur and should_blur:
-            raise NotImplementedError("the training-time blur augmentation (kornia gaussian_blur2d) is outside the "
-                                      "accelerated path")
+    @staticmethod
+    def blur_image(cond_fmap, blur_sigma, blur_kernel_size):
+        """Reference: dalle2_video.py:1091-1112 (kornia gaussian_blur2d per frame, reflect borders) as one dv_gaussian_blur
+        launch.  Tuples draw a random sigma / kernel size with Python's `random`, as the reference does."""
+        if isinstance(blur_sigma, tuple):
+            blur_sigma = random.uniform(*map(float, blur_sigma))
+        if isinstance(blur_kernel_size, tuple):
+            lo, hi = map(int, blur_kernel_size)
+            blur_kernel_size = random.randrange(lo, hi + 1)
+        if not cond_fmap.is_cuda:
+            raise L.DvError("LowresVideoConditioner.blur_image needs a CUDA tensor: there is no CPU path")
+        k = int(blur_kernel_size)
+        d = torch.arange(k, dtype=torch.float32) - k // 2
+        w = torch.exp(-d.pow(2) / (2.0 * float(blur_sigma) ** 2))
+        w = (w / w.sum()).tolist() + [0.0] * (16 - k)
+        src = cond_fmap.contiguous().float()
+        out = torch.empty_like(src)
+        b, c, t, h, wd = src.shape
+        arr = (L.C.c_float * 16)(*w)
+        L.call("dv_gaussian_blur", L.GaussianBlurParams(in_=src.data_ptr(), out=out.data_ptr(), planes=b * c * t, H=h, W=wd, k=k,
+                                                        wy=arr, wx=arr), torch.cuda.current_stream(src.device).cuda_stream)
+        return out.to(cond_fmap.dtype)
+
+    def __call__(self, cond_fmap, *, target_frame_size, downsample_frame_size=None, should_blur=True, blur_sigma=None,
+                 blur_kernel_size=None, **kwargs):
         if self.downsample_first and downsample_frame_size is not None:
             cond_fmap = resize_video_to(cond_fmap, downsample_frame_size, clamp_range=self.input_video_range)
+        # blur is only applied 50% of the time (:1135-1144)
+        if self.use_blur and should_blur and random.random() < self.blur_prob:
+            cond_fmap = self.blur_image(cond_fmap, blur_sigma if blur_sigma is not None else self.blur_sigma,
+                                        blur_kernel_size if blur_kernel_size is not None else self.blur_kernel_size)
         cond_fmap = resize_video_to(cond_fmap, target_frame_size, clamp_range=self.input_video_range)
         levels = None
         if self.use_noise:
@@ -209,6 +235,7 @@ class VideoDecoder(nn.Module):
             normalize_video=auto_normalize_video)
             for i, (un, ub) in enumerate(zip(use_noise_for_lowres_cond, use_blur_for_lowres_cond))]
         self.lowres_noise_sample_level = lowres_noise_sample_level
+        self.random_crop_sizes = _pad_tuple(_cast_tuple(random_crop_sizes), len(self.unets), None)
         self.video_cond_drop_prob = video_cond_drop_prob
         self.text_cond_drop_prob = text_cond_drop_prob
         self.can_classifier_guidance = video_cond_drop_prob > 0.0 or text_cond_drop_prob > 0.0
@@ -696,10 +723,19 @@ class VideoDecoder(nn.Module):
         b, c, t, h, w = video.shape
         assert c == self.channels
         size = self.frame_sizes[unet_number - 1]
-        if h != size or w != size:
-            raise NotImplementedError("per-frame nearest resizing (resize_image_to) is outside the accelerated path: pass "
-                                      f"videos at the training resolution ({size})")
+        assert h >= size and w >= size
+        if self.random_crop_sizes[unet_number - 1] is not None:
+            raise NotImplementedError("random_crop_sizes (kornia RandomCrop) is outside the accelerated path")
         times = torch.randint(0, sched.num_timesteps, (b,), device=video.device, dtype=torch.long)
+        # cascade stage >= 2 (:2245-2258): the conditioning video is the training video taken down to the previous
+        # stage's resolution and back up (per-frame nearest), optionally noise-augmented at one random level per batch
+        conditioner = self.lowres_conds[unet_number - 1]
+        lowres_cond_video = lowres_noise_level = None
+        if conditioner is not None:
+            lowres_cond_video, lowres_noise_level = conditioner(
+                video, target_frame_size=size, downsample_frame_size=self.frame_sizes[unet_number - 2])
+        video = resize_video_to(video, size)
         loss = p_losses(self, unet, video, times, video_embed=video_embed, noise_scheduler=sched,
-                        predict_x_start=self.predict_x_start[unet_number - 1], predict_v=self.predict_v[unet_number - 1])
-        return (loss, None) if return_lowres_cond_video else loss
+                        predict_x_start=self.predict_x_start[unet_number - 1], predict_v=self.predict_v[unet_number - 1],
+                        lowres_cond_video=lowres_cond_video, lowres_noise_level=lowres_noise_level)
+        return (loss, lowres_cond_video) if return_lowres_cond_video else loss

@@ -73,8 +73,8 @@ class _TrainPlan:
             raise NotImplementedError("training with text conditioning has no backward kernels yet (long-context cross attention)")
         if u.temporal_conv or any(u._stage_temporal_attn) or u.attn_mode != "joint":
             raise NotImplementedError("the extensions (temporal conv / attention, factorised attention) have no backward kernels")
-        if u.lowres_cond or u.skip_connect_scale != 1.0:
-            raise NotImplementedError("lowres conditioning and scaled skip connections are outside the training plan")
+        if u.skip_connect_scale != 1.0:
+            raise NotImplementedError("scaled skip connections are outside the training plan")
         self.u, self.B, self.T, self.H, self.W, self.device = u, B, T, H, W, device
         self.code = L.DV_BF16
         L.lib()
@@ -409,7 +409,10 @@ class _TrainPlan:
         n_img, P = B * T, T * H * W
         rows = B * P
         # ---- inputs: x_t (B,3,T,H,W) float32 -> CrossEmbedLayer3D as im2col + one GEMM (patches are kept for the wgrad)
-        self.x_in = torch.zeros(B, u.channels * (1 + int(u.self_cond)), T, H, W, device=dev)   # cat(x_t, self_cond), :738-740
+        # cat(x_t, self_cond, lowres_cond_video) in the reference's order (:738-746)
+        self.x_in = torch.zeros(B, u.channels * (1 + int(u.self_cond) + int(u.lowres_cond)), T, H, W, device=dev)
+        # the head sees the low-resolution video again (:949-952): a contiguous copy in the layout dv_to_out reads
+        self.lowres_in = torch.zeros(B, u.channels, T, H, W, device=dev) if u.lowres_cond else None
         if not isinstance(u.init_conv, _CrossEmbed):
             raise NotImplementedError("training plan: init_cross_embed=False is not built")
         convs, ks = list(u.init_conv.convs), list(u.init_conv.kernel_sizes)
@@ -502,15 +505,16 @@ class _TrainPlan:
         self.deps = torch.zeros(B, co, P, device=dev)
         wo = self._f32(lambda: u.to_out.weight.detach().float().reshape(co, -1))
         bo = self._f32(lambda: u.to_out.bias.detach().float())
+        extra = dict(extra=self.lowres_in.data_ptr() if u.lowres_cond else None, Cextra=u.channels if u.lowres_cond else 0)
         self.fwd.append(("dv_to_out", L.ToOutParams(x=x.ptr, w=wo.data_ptr(), bias=bo.data_ptr(), out=self.eps.data_ptr(), B=B,
-                                                    P=P, C=x.C, Cout=co, dtype=self.code)))
-        gwo, gbo = self._galloc(co, x.C), self._galloc(co)
+                                                    P=P, C=x.C, Cout=co, dtype=self.code, **extra)))
+        gwo, gbo = self._galloc(co, x.C + extra["Cextra"]), self._galloc(co)
         self._gmap((u.to_out.weight, lambda: self._g(gwo).reshape(u.to_out.weight.shape)))
         self._gmap((u.to_out.bias, lambda: self._g(gbo)))
         dst, _ = self._grad_target(x)
         self.bwd.append(("dv_to_out_bwd", L.ToOutBwdParams(x=x.ptr, w=wo.data_ptr(), deps=self.deps.data_ptr(), dx=dst,
                                                            dw=self._gptr(gwo), db=self._gptr(gbo), B=B, P=P, C=x.C, Cout=co,
-                                                           dtype=self.code)))
+                                                           dtype=self.code, **extra)))
         # ---- backward launch list: replay the tape in reverse
         self.bwd_marks.append((len(self.tape), 0))   # the head's launches (dv_to_out_bwd) come first
         for i in reversed(range(len(self.tape))):
@@ -540,7 +544,7 @@ class _TrainPlan:
         return out
 
     # -------------------------------------------------------------- conditioning prologue (torch autograd, see module doc)
-    def prologue(self, time, video_embed, keep_v):
+    def prologue(self, time, video_embed, keep_v, lowres_noise_level=None):
         u, B = self.u, self.B
         cond, nt = u.cond_dim, u.num_time_tokens
         half = u.dim // 2
@@ -551,6 +555,11 @@ class _TrainPlan:
         hid = F.gelu(u.to_time_hiddens[1](emb))
         time_tokens = u.to_time_tokens[0](hid).reshape(B, nt, cond)
         t = u.to_time_cond[0](hid)
+        if lowres_noise_level is not None:   # t = t + to_lowres_noise_cond(level) (:765-768): SinusoidalPosEmb, Linear, GELU, Linear
+            assert u.to_lowres_noise_cond is not None, \
+                "lowres_noise_cond must be set to True on instantiation of the unet in order to conditiong on lowres noise"
+            al = lowres_noise_level.to(torch.float32)[:, None] * freqs[None, :]
+            t = t + u.to_lowres_noise_cond[3](F.gelu(u.to_lowres_noise_cond[1](torch.cat((al.sin(), al.cos()), dim=-1))))
         keep = keep_v.bool()
         if u.to_video_hiddens is not None:
             vh = F.gelu(u.to_video_hiddens[0](video_embed))
@@ -717,7 +726,7 @@ class _PlanFunction(torch.autograd.Function):
 
 
 def p_losses(decoder, unet: Unet3D, x_start, times, *, video_embed, noise_scheduler, noise=None, is_latent_diffusion=False,
-             predict_x_start=False, predict_v=False):
+             predict_x_start=False, predict_v=False, lowres_cond_video=None, lowres_noise_level=None):
     """VideoDecoder.p_losses (:1908-2006) with the l2 loss; the regression target is the noise, x_start or v
     (:1990-1995, written by dv_q_sample next to x_t).  Returns a scalar loss tensor whose .backward() runs the native
     backward plan."""
@@ -733,28 +742,41 @@ def p_losses(decoder, unet: Unet3D, x_start, times, *, video_embed, noise_schedu
     noise = noise.contiguous().float()
     objective = L.OBJ_V if predict_v else L.OBJ_X_START if predict_x_start else L.OBJ_EPS
     target = noise if objective == L.OBJ_EPS else torch.empty_like(noise)
-    x_t = torch.empty_like(x_start) if unet.self_cond else plan.x_in
+    assert not (unet.lowres_cond and lowres_cond_video is None), "low resolution conditioning image must be present"
+    if lowres_cond_video is not None and not unet.lowres_cond:
+        raise L.DvError("lowres_cond_video was passed to a Unet3D built with lowres_cond=False")
+    multi_plane = unet.self_cond or unet.lowres_cond
+    x_t = torch.empty_like(x_start) if multi_plane else plan.x_in
     L.call("dv_q_sample", L.QSampleParams(
         video=x_start.data_ptr(), noise=noise.data_ptr(), times=times.data_ptr(),
         sqrt_ac=noise_scheduler.sqrt_alphas_cumprod.data_ptr(),
         sqrt_1mac=noise_scheduler.sqrt_one_minus_alphas_cumprod.data_ptr(), out=x_t.data_ptr(), n=x_start.numel(),
         per_sample=x_start.numel() // B, normalize=0 if is_latent_diffusion else 1,
         target=target.data_ptr() if target is not noise else None, objective=objective), stream)
+    if multi_plane:
+        plan.x_in[:, :C].copy_(x_t)
+    lowres_kw = {}
+    if unet.lowres_cond:
+        # `lowres_cond_video = maybe(self.normalize_video)(lowres_cond_video)` (:1946-1948); last planes of the init conv
+        # input (:744-746) and again beside the last feature map at the head (:949-952)
+        low = lowres_cond_video.float()
+        plan.lowres_in.copy_(low if is_latent_diffusion else low * 2 - 1)
+        plan.x_in[:, -C:].copy_(plan.lowres_in)
+        lowres_kw = dict(lowres_cond_video=plan.lowres_in, lowres_noise_level=lowres_noise_level)
     if unet.self_cond:
         # self-conditioning (:1969-1976): half of the time a no-grad first pass (no conditioning dropout) predicts the
         # network output that is concatenated to x_t; `random.random()` is the reference's draw
-        plan.x_in[:, :C].copy_(x_t)
         if random.random() < 0.5:
-            plan.x_in[:, C:].copy_(unet(x_t, times, video_embed=video_embed))
+            plan.x_in[:, C:2 * C].copy_(unet(x_t, times, video_embed=video_embed, **lowres_kw))
         else:
-            plan.x_in[:, C:].zero_()
+            plan.x_in[:, C:2 * C].zero_()
     # prob_mask_like draws (reference :772-778): video mask, then text mask (drawn even without text conditioning)
     keep_v = _prob_mask(B, 1 - decoder.video_cond_drop_prob, dev)
     _prob_mask(B, 1 - decoder.text_cond_drop_prob, dev)
     # loss_fn (l1 / l2 / huber) and p2 reweighting (:1997-2003) are applied inside dv_mse_loss
     weight = noise_scheduler.p2_loss_weight[times].float().contiguous() if noise_scheduler.has_p2_loss_reweighting else None
     plan.loss_opts = (L.LOSS_KINDS[noise_scheduler.loss_type], weight)
-    outs = plan.prologue(times, video_embed.float(), keep_v)
+    outs = plan.prologue(times, video_embed.float(), keep_v, lowres_noise_level)
     return _PlanFunction.apply(plan, target, outs["ss"], *[outs[k] for k in plan.kv_kinds])
 
 

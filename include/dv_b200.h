@@ -646,6 +646,19 @@ typedef struct {
 int dv_attn_mqa_bwd(const dv_attn_mqa_bwd_params* p, dv_stream_t stream);
 int64_t dv_attn_mqa_bwd_workspace_bytes(const dv_attn_mqa_bwd_params* p);
 
+/* Per-frame Gaussian blur of the low-resolution conditioning video in training (LowresVideoConditioner.blur_image,
+ * dalle2_video/dalle2_video.py:1091-1112 -> kornia.filters.gaussian_blur2d, an un-vendored dependency: PARITY UNPINNED
+ * against kornia itself, pinned against the oracle's restatement with F.pad(mode="reflect") + F.conv2d).
+ *   out[p][y][x] = sum_{i,j} wy[i] wx[j] in[p][reflect(y + i - k/2)][reflect(x + j - k/2)]
+ * wy / wx: the normalised 1-D kernels exp(-d^2 / (2 sigma^2)) / sum, built by the caller (k odd, <= 15). */
+typedef struct {
+  const float* in; float* out;   /* [planes][H][W], not in place */
+  int64_t planes;
+  int H, W, k;
+  float wy[16], wx[16];
+} dv_gaussian_blur_params;
+int dv_gaussian_blur(const dv_gaussian_blur_params* p, dv_stream_t stream);
+
 /* x_t = sqrt_ac[t_b] * (normalize ? 2 v - 1 : v) + sqrt_1mac[t_b] * noise   (NoiseScheduler.q_sample) */
 typedef struct {
   const float* video; const float* noise; const int64_t* times;
@@ -676,11 +689,14 @@ typedef struct {
 } dv_mse_loss_params;
 int dv_mse_loss(const dv_mse_loss_params* p, dv_stream_t stream);
 
-/* Backward of dv_to_out: deps [B][Cout][P] float32 -> dx [B][P][C] (=), dw [Cout][C] and db [Cout] (+=). */
+/* Backward of dv_to_out: deps [B][Cout][P] float32 -> dx [B][P][C] (=), dw [Cout][C + Cextra] and db [Cout] (+=).
+ * With `extra` (the low-resolution conditioning planes [B][Cextra][P] the forward concatenated, :949-952) w and dw have
+ * C + Cextra columns and the last Cextra columns of dw receive sum_pos deps * extra; extra itself gets no gradient. */
 typedef struct {
   const void* x; const float* w; const float* deps; void* dx; float* dw; float* db;
   int B; int64_t P; int C, Cout;
   dv_dtype dtype;
+  const float* extra; int Cextra;
 } dv_to_out_bwd_params;
 int dv_to_out_bwd(const dv_to_out_bwd_params* p, dv_stream_t stream);
 

@@ -166,6 +166,45 @@ def cascade():
         json.dump(layouts, f, indent=0, sort_keys=True)
 
 
+def cascade_train():
+    """`python -m oracle.make_golden cascade_train`: the training loss of the SECOND unet of a (16 -> 32 px) cascade through
+    the reference's own VideoDecoder.p_losses (:1908-2006) with explicit timesteps / noise / conditioning video, with and
+    without the noise-level conditioning; the conditioning video itself comes from the reference's LowresVideoConditioner
+    (nearest down + up, no blur, no noise: deterministic), which pins the resize path of VideoDecoder.forward too."""
+    ref = reference.load()
+    with open(os.path.join(GOLDEN, "state_dict_layouts.json")) as f:
+        layouts = json.load(f)
+    out = {}
+    for use_noise in (False, True):
+        kw2 = dict(CASCADE_U1, lowres_cond=True)   # dim 32 second stage (the sampling fixtures use a dim-16 one)
+        torch.manual_seed(0)
+        u1, u2 = ref.Unet3D(**CASCADE_U1), ref.Unet3D(**kw2)
+        dec = ref.VideoDecoder((u1, u2), frame_sizes=(16, 32), frame_numbers=(4, 4), timesteps=50, learned_variance=False,
+                               use_noise_for_lowres_cond=use_noise,   # (the reference insists on blur or noise, :1325;
+                               video_cond_drop_prob=0.0, text_cond_drop_prob=0.0)   # p_losses itself uses neither)
+        key = "cascade_train_u2_noise" if use_noise else "cascade_train_u2"
+        layouts[key] = shapes_of(dec.unets[1])
+        dec.unets[1].load_state_dict(synth_state_dict(layouts[key], seed=11), strict=True)
+        g = torch.Generator().manual_seed(91)
+        video = torch.rand(2, 3, 4, 32, 32, generator=g)
+        noise = torch.randn(2, 3, 4, 32, 32, generator=g)
+        emb = torch.randn(2, 512, generator=g)
+        times = torch.tensor([4, 31])
+        cond = ref.LowresVideoConditioner(downsample_first=True, use_blur=False, use_noise=False,
+                                          input_video_range=dec.input_video_range)
+        low, _ = cond(video, target_frame_size=32, downsample_frame_size=16)
+        level = torch.tensor([150, 150]) if use_noise else None
+        loss = dec.p_losses(dec.unets[1], video, times, video_embed=emb, noise_scheduler=dec.noise_schedulers[1],
+                            lowres_cond_video=low, noise=noise, lowres_noise_level=level)
+        out[key] = {"loss": float(loss), "lowres_cond_video": low, "lowres_noise_level": level,
+                    "unet_kwargs": dict(kw2, lowres_noise_cond=use_noise)}
+        print("cascade train", use_noise, float(loss), float(low.mean()))
+    torch.save({"cases": out, "input_seed": 91, "weight_seed": 11, "times": (4, 31), "timesteps": 50,
+                "shape": (2, 3, 4, 32, 32)}, os.path.join(GOLDEN, "cascade_train.pt"))
+    with open(os.path.join(GOLDEN, "state_dict_layouts.json"), "w") as f:
+        json.dump(layouts, f, indent=0, sort_keys=True)
+
+
 OBJECTIVE_CASES = {
     # name: (decoder kwargs, cond_scale)
     "v": (dict(predict_v=True), 1.0),
@@ -286,6 +325,8 @@ if __name__ == "__main__":
         vivit()
     elif len(sys.argv) > 1 and sys.argv[1] == "cascade":
         cascade()
+    elif len(sys.argv) > 1 and sys.argv[1] == "cascade_train":
+        cascade_train()
     elif len(sys.argv) > 1 and sys.argv[1] == "objectives":
         objectives()
     else:

@@ -437,6 +437,23 @@ def resize_nearest(video, size, clamp_range=None):
     return out.clamp(*clamp_range) if clamp_range is not None else out
 
 
+def gaussian_blur_frames(video, kernel_size, sigma):
+    """LowresVideoConditioner.blur_image (:1091-1112) = kornia.filters.gaussian_blur2d applied per frame.  kornia is an
+    un-vendored dependency that is not installed: PARITY UNPINNED against kornia itself; this restates its documented
+    algorithm — normalised 1-D kernel exp(-d^2 / (2 sigma^2)) over d = arange(k) - k // 2, outer product, 'reflect'
+    border, depthwise correlation."""
+    import torch.nn.functional as F
+    b, c, t, h, w = video.shape
+    d = torch.arange(kernel_size, dtype=torch.float32) - kernel_size // 2
+    k1 = torch.exp(-d.pow(2) / (2.0 * sigma ** 2))
+    k1 = k1 / k1.sum()
+    k2 = torch.outer(k1, k1)[None, None]
+    frames = video.permute(0, 2, 1, 3, 4).reshape(b * t * c, 1, h, w)
+    r = kernel_size // 2
+    out = F.conv2d(F.pad(frames, (r, r, r, r), mode="reflect"), k2)
+    return out.reshape(b, t, c, h, w).permute(0, 2, 1, 3, 4).contiguous()
+
+
 def sample_cascade(sds, cfgs, scheds, frame_sizes, frame_number, *, video_embed, generator=None, noise_sched=None,
                    lowres_noise_sample_level=0.2, use_noise=None, input_video_range=(0.0, 1.0)):
     """VideoDecoder.sample over a cascade (dalle2_video.py:2053-2186) for pixel-space unets with auto-normalisation:

@@ -284,3 +284,111 @@ def test_huber_loss_with_p2_reweighting_through_the_decoder(layouts):
     assert abs(float(loss) - ref) < 2e-2 * ref, (float(loss), ref)
     loss.backward()
     assert float(dec.unets[0].to_out.weight.grad.abs().max()) > 0
+
+
+@pytest.mark.parametrize("key", ["cascade_train_u2", "cascade_train_u2_noise"])
+def test_cascade_stage2_training_matches_reference_loss_and_oracle_gradients(key, layouts):
+    """Training the second unet of a cascade (scope rows a16 x N2): lowres planes into the init conv (:744-746) and the head
+    (:949-952, dv_to_out_bwd `extra`), noise-level conditioning into t (:765-768).  Loss against the reference's own
+    p_losses, gradients against torch autograd through the oracle."""
+    from conftest import golden
+    from dalle2_video_b200.decoder import LowresVideoConditioner
+    g = golden("cascade_train.pt")
+    case = g["cases"][key]
+    kw = case["unet_kwargs"]
+    use_noise = case["lowres_noise_level"] is not None
+    sd = synth_state_dict(layouts[key], seed=g["weight_seed"])
+    u1, u2 = Unet3D(**CASES["tiny"][0]), Unet3D(**kw)
+    dec = VideoDecoder((u1, u2), frame_sizes=(16, 32), frame_numbers=(4, 4), timesteps=g["timesteps"], learned_variance=False,
+                       use_noise_for_lowres_cond=use_noise, video_cond_drop_prob=0.0, text_cond_drop_prob=0.0).cuda()
+    dec.unets[1].load_state_dict(sd, strict=True)   # after construction: the decoder re-instantiates its unets (quirk Q1)
+    gen = torch.Generator().manual_seed(g["input_seed"])
+    video, noise = torch.rand(g["shape"], generator=gen), torch.randn(g["shape"], generator=gen)
+    emb, times = torch.randn(2, 512, generator=gen), torch.tensor(g["times"])
+    cond = LowresVideoConditioner(downsample_first=True, use_blur=False, use_noise=False, input_video_range=(0.0, 1.0))
+    low, _ = cond(video.cuda(), target_frame_size=32, downsample_frame_size=16)
+    assert torch.equal(low.cpu(), case["lowres_cond_video"])
+    level = case["lowres_noise_level"]
+    loss = p_losses(dec, dec.unets[1], video.cuda(), times.cuda(), video_embed=emb.cuda(), noise_scheduler=dec.noise_schedulers[1],
+                    noise=noise.cuda(), lowres_cond_video=low, lowres_noise_level=level.cuda() if use_noise else None)
+    assert abs(float(loss) - case["loss"]) < 2e-2 * case["loss"], (float(loss), case["loss"])
+    loss.backward()
+    # oracle autograd on the same inputs
+    sdg = {k: v.clone().requires_grad_() for k, v in sd.items()}
+    sched = OracleScheduler(beta_schedule="linear", timesteps=g["timesteps"], loss_type="l2")   # last unet: linear (:1376-1385)
+    pred = unet3d_forward(sdg, UnetConfig(**kw), sched.q_sample(2 * video - 1, times, noise), times, video_embed=emb,
+                          lowres_cond_video=case["lowres_cond_video"] * 2 - 1, lowres_noise_level=level)
+    F.mse_loss(pred, noise, reduction="none").flatten(1).mean(1).mean().backward()
+    got = dict(dec.unets[1].named_parameters())
+    num = den = 0.0
+    for k, v in sdg.items():
+        if v.grad is None:
+            continue
+        gg = got[k].grad.float().cpu()
+        num += float((gg - v.grad).pow(2).sum())
+        den += float(v.grad.pow(2).sum())
+        if v.grad.numel() >= 256 and float(v.grad.norm()) > 1e-6:
+            cos = float(F.cosine_similarity(gg.flatten(), v.grad.flatten(), dim=0))
+            assert cos >= 0.98, (k, cos)
+    assert (num / den) ** 0.5 < 8e-2
+    for k in ["to_out.weight"] + (["to_lowres_noise_cond.3.weight"] if use_noise else []):
+        assert rel_err(got[k].grad, sdg[k].grad) < 8e-2, k
+    wg, rg = got["to_out.weight"].grad.float().cpu(), sdg["to_out.weight"].grad
+    assert rel_err(wg[:, -3:], rg[:, -3:]) < 5e-2    # the columns fed by the low-resolution planes
+    ig, irg = got["init_conv.convs.0.weight"].grad.float().cpu(), sdg["init_conv.convs.0.weight"].grad
+    assert ig.shape[1] == 6 and rel_err(ig[:, 3:], irg[:, 3:]) < 8e-2
+
+
+def test_cascade_stage2_trainer_steps_through_decoder_forward(layouts):
+    """VideoDecoder.forward(unet_number=2) builds the conditioning video itself (nearest down / up + noise augmentation at a
+    random level, :2245-2258) from a video larger than the stage's frame size; a few optimiser steps reduce the loss."""
+    kw = dict(CASES["tiny"][0], lowres_cond=True)
+    u1, u2 = Unet3D(**CASES["tiny"][0]), Unet3D(**kw)
+    dec = VideoDecoder((u1, u2), frame_sizes=(16, 32), frame_numbers=(4, 4), timesteps=100, learned_variance=False,
+                       use_noise_for_lowres_cond=True, video_cond_drop_prob=0.0, text_cond_drop_prob=0.0).cuda()
+    torch.nn.init.normal_(dec.unets[1].to_out.weight, std=0.02)
+    g = torch.Generator().manual_seed(2)
+    video, emb = torch.rand(2, 3, 4, 64, 64, generator=g).cuda(), torch.randn(2, 512, generator=g).cuda()
+    loss, low = dec(video, video_embed=emb, unet_number=2, return_lowres_cond_video=True)
+    assert low.shape == (2, 3, 4, 32, 32) and bool(torch.isfinite(loss))
+    loss.backward()
+    params = [p for p in dec.unets[1].parameters() if p.grad is not None]
+    opt = torch.optim.AdamW(params, lr=3e-4)
+    losses = []
+    for _ in range(10):
+        for p in params:
+            p.grad = None
+        torch.manual_seed(11)
+        loss = dec(video, video_embed=emb, unet_number=2)
+        loss.backward()
+        opt.step()
+        dec.unets[1].invalidate_cache()
+        losses.append(float(loss))
+    assert losses[-1] < 0.9 * losses[0], losses
+
+
+@pytest.mark.parametrize("k,sigma,shape", [(3, 0.6, (2, 3, 4, 16, 16)), (5, 1.3, (1, 3, 2, 9, 20)), (1, 0.6, (1, 3, 1, 8, 8))])
+def test_gaussian_blur_kernel_matches_oracle_restatement(k, sigma, shape):
+    from dalle2_video_b200.decoder import LowresVideoConditioner
+    from oracle.unet3d import gaussian_blur_frames
+    x = torch.rand(shape, generator=torch.Generator().manual_seed(k))
+    got = LowresVideoConditioner.blur_image(x.cuda(), sigma, k)
+    assert rel_err(got, gaussian_blur_frames(x, k, sigma)) < 1e-6
+    if k == 1:
+        assert torch.equal(got.cpu(), x)
+
+
+def test_lowres_conditioner_blurs_half_of_the_time_like_the_reference():
+    import random
+    from dalle2_video_b200.decoder import LowresVideoConditioner
+    from oracle.unet3d import gaussian_blur_frames, resize_nearest
+    x = torch.rand(2, 3, 2, 32, 32, generator=torch.Generator().manual_seed(0))
+    cond = LowresVideoConditioner(downsample_first=True, use_blur=True, use_noise=False, input_video_range=(0.0, 1.0))
+    for seed, blurred in ((1, True), (2, False)):   # random.random() = 0.134 / 0.956 against blur_prob 0.5 (:1138)
+        random.seed(seed)
+        got, levels = cond(x.cuda(), target_frame_size=32, downsample_frame_size=16)
+        low = resize_nearest(x, 16, clamp_range=(0.0, 1.0))
+        if blurred:
+            low = gaussian_blur_frames(low, 3, 0.6)
+        want = resize_nearest(low, 32, clamp_range=(0.0, 1.0))
+        assert levels is None and rel_err(got, want) < 1e-6, seed

@@ -245,3 +245,27 @@ def test_self_conditioned_sampler_and_loss_match_reference_fixture(layouts):
             pred = unet3d_forward(sd, cfg, x_t, times, video_embed=emb, self_cond=sc)
             loss = float(F.mse_loss(pred, noise, reduction="none").flatten(1).mean(1).mean())
             assert abs(loss - case["loss"][label]) < 1e-5 * case["loss"][label], (label, loss)
+
+
+@pytest.mark.parametrize("key", ["cascade_train_u2", "cascade_train_u2_noise"])
+def test_cascade_stage2_training_loss_matches_reference_fixture(key, layouts):
+    # p_losses of the second unet (:1908-2006): normalised lowres video into init conv and head, noise level into t
+    import torch.nn.functional as F
+    from oracle.unet3d import resize_nearest
+    g = golden("cascade_train.pt")
+    case = g["cases"][key]
+    cfg = UnetConfig(**case["unet_kwargs"])
+    sd = synth_state_dict(layouts[key], seed=g["weight_seed"])
+    # the last unet of a cascade trains on the LINEAR schedule by default (:1376-1385)
+    sched = P.NoiseScheduler(beta_schedule="linear", timesteps=g["timesteps"], loss_type="l2")
+    gen = torch.Generator().manual_seed(g["input_seed"])
+    video, noise = torch.rand(g["shape"], generator=gen), torch.randn(g["shape"], generator=gen)
+    emb = torch.randn(2, 512, generator=gen)
+    times = torch.tensor(g["times"])
+    low = resize_nearest(resize_nearest(video, 16, clamp_range=(0.0, 1.0)), 32, clamp_range=(0.0, 1.0))
+    assert torch.equal(low, case["lowres_cond_video"])
+    with torch.no_grad():
+        pred = unet3d_forward(sd, cfg, sched.q_sample(video * 2 - 1, times, noise), times, video_embed=emb,
+                              lowres_cond_video=low * 2 - 1, lowres_noise_level=case["lowres_noise_level"])
+    loss = float(F.mse_loss(pred, noise, reduction="none").flatten(1).mean(1).mean())
+    assert abs(loss - case["loss"]) < 1e-5 * case["loss"], (loss, case["loss"])
