@@ -71,6 +71,14 @@ __device__ __forceinline__ void tma_load_3d_at(const CUtensorMap* map, uint64_t*
       : "memory");
 }
 
+// One MUFU.EX2: exp2f() without -use_fast_math wraps it in a range test and two multiplies per element to keep
+// denormal results, which a softmax probability never needs (results below 2^-126 flush to zero).
+__device__ __forceinline__ float ex2_ftz(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 template <int DH>
 __device__ __forceinline__ uint64_t qk_desc(uint32_t saddr) {
   return DH == 32 ? make_smem_desc_sw64(saddr) : make_smem_desc(saddr);  // 64-byte rows vs 128-byte rows
@@ -89,15 +97,16 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
   constexpr int STAGE_BYTES = K_BYTES + VT_BYTES;
   uint8_t* q_s = smem;                                   // 2 x [128][ROWB] SWIZZLE_64B (double-buffered)
   uint8_t* kv_s = q_s + 2 * Q_BYTES;                     // ring
-  uint8_t* p_s = kv_s + AT_STAGES * STAGE_BYTES;         // [2 blocks][128 rows][128 B] SWIZZLE_128B
-  uint64_t* bars = reinterpret_cast<uint64_t*>(p_s + 2 * 16384);
+  uint8_t* p_s = kv_s + AT_STAGES * STAGE_BYTES;         // [2 buffers][2 blocks][128 rows][128 B] SWIZZLE_128B: P_j is
+                                                         // written while P_{j-1}.V_{j-1} is still in flight
+  uint64_t* bars = reinterpret_cast<uint64_t*>(p_s + 4 * 16384);
   uint64_t* q_full = bars;            // [2]
   uint64_t* q_free = bars + 2;        // [2] (4 arrivals each)
   uint64_t* kv_full = bars + 4;       // [AT_STAGES]
   uint64_t* kv_empty = kv_full + AT_STAGES;
   uint64_t* s_full = kv_empty + AT_STAGES;  // [2]
-  uint64_t* p_ready = s_full + 2;           // 1 (4 arrivals)
-  uint64_t* o_full = p_ready + 1;           // [2]
+  uint64_t* p_ready = s_full + 2;           // [2] (8 arrivals each), one per P buffer
+  uint64_t* o_full = p_ready + 2;           // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 2);
   float* xch = reinterpret_cast<float*>(tmem_slot + 4);   // [2 buffers][2 halves][128 rows]: row maxima / sums of the two column halves
 
@@ -112,7 +121,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
     for (int a = 0; a < 2; ++a) { mbar_init(&q_full[a], 1); mbar_init(&q_free[a], 8); }
     for (int s = 0; s < AT_STAGES; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(&s_full[a], 1); mbar_init(&o_full[a], 1); }
-    mbar_init(p_ready, 8);
+    for (int a = 0; a < 2; ++a) mbar_init(&p_ready[a], 8);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -189,14 +198,15 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
       issue_s(0);
       for (int j = 0; j < nt; ++j) {
         if (j + 1 < nt) issue_s(j + 1);  // S buffer (jj+j+1)&1 was drained before p_ready(j-1)
-        mbar_wait(p_ready, (uint32_t)((jj + j) & 1));
+        const int pbuf = (int)((jj + j) & 1);
+        mbar_wait(&p_ready[pbuf], (uint32_t)(((jj + j) >> 1) & 1));
         tc_fence_after();
         if (elect_one()) {
           const uint32_t vbase = smem_u32(kv_s + st_pv * STAGE_BYTES + K_BYTES);
           const uint32_t d = tmem_base + 256u + (uint32_t)(((jj + j) & 1) * DH);
 #pragma unroll
           for (int kk = 0; kk < AT_KT / 16; ++kk) {
-            const uint64_t pd = make_smem_desc(smem_u32(p_s) + (uint32_t)(kk / 4) * 16384u) + (uint64_t)((kk % 4) * 2);
+            const uint64_t pd = make_smem_desc(smem_u32(p_s) + (uint32_t)(pbuf * 2 + kk / 4) * 16384u) + (uint64_t)((kk % 4) * 2);
             const uint64_t vd = make_smem_desc(vbase + (uint32_t)(kk / 4) * (VT_BYTES / 2)) + (uint64_t)((kk % 4) * 2);
             umma_f16(d, pd, vd, idesc_o, kk != 0);
           }
@@ -253,18 +263,18 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
         for (int e = 0; e < OH; ++e) o[e] = __ldg(p.null_kv + DH + half * OH + e);
         m = d * p.scale_log2e;  // running max in the log2 domain
       }
-      auto fold_o = [&](int pb) {   // o += this thread's columns of the P.V result of S buffer pb
+      auto fold_o = [&](int pb, float w) {   // o += w * this thread's columns of the P.V result of S buffer pb
         if (DH == 64) {
           uint32_t r[32];
           tmem_ld32(t_lane + 256u + (uint32_t)(pb * DH + half * 32), r);
 #pragma unroll
-          for (int e = 0; e < OH; ++e) o[e] += __uint_as_float(r[e % 32]);
+          for (int e = 0; e < OH; ++e) o[e] = fmaf(__uint_as_float(r[e % 32]), w, o[e]);
         } else {
           uint32_t r[16];
           tmem_ld16_nowait(t_lane + 256u + (uint32_t)(pb * DH + half * 16), r);
           tmem_ld_wait();
 #pragma unroll
-          for (int e = 0; e < OH; ++e) o[e] += __uint_as_float(r[e % 16]);
+          for (int e = 0; e < OH; ++e) o[e] = fmaf(__uint_as_float(r[e % 16]), w, o[e]);
         }
       };
       for (int j = 0; j < nt; ++j) {
@@ -275,16 +285,21 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
         const int lim = MHA ? p.n_valid - j * AT_KT - half * 64 : 64;
         // the thread's 64 logits are read from TMEM ONCE and stay in registers for both passes (TMEM reads, not MUFU, bounded
         // the two-pass version: 2 x 64 KB per key tile at ~64 B/clk)
-        float mx = m;
         uint32_t sr[2][32];
         tmem_ld32_nowait(t_lane + (uint32_t)(buf * 128 + half * 64), sr[0]);
         tmem_ld32_nowait(t_lane + (uint32_t)(buf * 128 + half * 64 + 32), sr[1]);
         tmem_ld_wait();
+        // maximum of the raw logits, scaled once (scale > 0); eight independent chains instead of one of 64 dependent FMNMX
+        float rw[8];
+#pragma unroll
+        for (int a = 0; a < 8; ++a) rw[a] = -CUDART_INF_F;
 #pragma unroll
         for (int c = 0; c < 2; ++c)
 #pragma unroll
           for (int k = 0; k < 32; ++k)
-            if (!MHA || c * 32 + k < lim) mx = fmaxf(mx, __uint_as_float(sr[c][k]) * p.scale_log2e);
+            if (!MHA || c * 32 + k < lim) rw[k & 7] = fmaxf(rw[k & 7], __uint_as_float(sr[c][k]));
+        const float raw = fmaxf(fmaxf(fmaxf(rw[0], rw[1]), fmaxf(rw[2], rw[3])), fmaxf(fmaxf(rw[4], rw[5]), fmaxf(rw[6], rw[7])));
+        float mx = fmaxf(m, raw * p.scale_log2e);
         // the row maximum is the larger of the two halves' (exchange buffers alternate: a slot is rewritten two tiles later,
         // after the barrier of the tile in between)
         float* xb = xch + buf * 256;
@@ -293,13 +308,6 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
         mx = fmaxf(mx, xb[(half ^ 1) * 128 + row]);
         const float corr = exp2f(m - mx);
         m = mx;
-        // the previous tile's P.V must have completed before P is overwritten; fold its result in now
-        if (j > 0) {
-          const int pb = (int)((jj + j - 1) & 1);
-          mbar_wait(&o_full[pb], (uint32_t)(((jj + j - 1) >> 1) & 1));
-          tc_fence_after();
-          fold_o(pb);
-        }
         l *= corr;
 #pragma unroll
         for (int e = 0; e < OH; ++e) o[e] *= corr;
@@ -308,22 +316,24 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
           const int c0 = c * 32;
-          uint8_t* prow = p_s + half * 16384 + row * 128;
+          uint8_t* prow = p_s + (buf * 2 + half) * 16384 + row * 128;
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
             uint4 pk;
             __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&pk);
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-              float a = exp2f(fmaf(__uint_as_float(sr[c][g * 8 + 2 * e]), p.scale_log2e, -m));
-              float b = exp2f(fmaf(__uint_as_float(sr[c][g * 8 + 2 * e + 1]), p.scale_log2e, -m));
+              float a = ex2_ftz(fmaf(__uint_as_float(sr[c][g * 8 + 2 * e]), p.scale_log2e, -m));
+              float b = ex2_ftz(fmaf(__uint_as_float(sr[c][g * 8 + 2 * e + 1]), p.scale_log2e, -m));
               if (MHA) {
                 if (c0 + g * 8 + 2 * e >= lim) a = 0.f;
                 if (c0 + g * 8 + 2 * e + 1 >= lim) b = 0.f;
               }
               h2[e] = __floats2bfloat162_rn(a, b);
-              // sum what the tensor core will actually multiply (the bf16-rounded probabilities)
-              lsum += __low2float(h2[e]) + __high2float(h2[e]);
+              // the row sum takes the fp32 probabilities (their bf16 rounding, which is what the tensor core multiplies,
+              // differs by <= 2^-9 relative with random sign: far below the bf16 output rounding, and two issue slots
+              // per pair cheaper than unpacking)
+              lsum += a + b;
             }
             const int chunk = (c0 / 8 + g) ^ (row & 7);
             *reinterpret_cast<uint4*>(prow + chunk * 16) = pk;
@@ -333,14 +343,23 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(p_ready);
+        if (lane == 0) mbar_arrive(&p_ready[buf]);
+        // P is double-buffered, so the wait for the PREVIOUS tile's P.V sits here, after this tile's exponentials: the MMA
+        // had a whole pass to finish.  Its result was computed against the old maximum: fold it in with this tile's corr.
+        // (Also frees P buffer buf^1 and accumulator buf^1 for tile j+1.)
+        if (j > 0) {
+          const int pb = buf ^ 1;
+          mbar_wait(&o_full[pb], (uint32_t)(((jj + j - 1) >> 1) & 1));
+          tc_fence_after();
+          fold_o(pb, corr);
+        }
       }
       // last tile's P.V
       {
         const int pb = (int)((jj + nt - 1) & 1);
         mbar_wait(&o_full[pb], (uint32_t)(((jj + nt - 1) >> 1) & 1));
         tc_fence_after();
-        fold_o(pb);
+        fold_o(pb, 1.0f);
       }
       tc_fence_before();
       __syncwarp();
@@ -425,7 +444,7 @@ int attn_tc_launch(const dv_attn_mqa_params& p, cudaStream_t s) {
     uint32_t box[3] = {64, (uint32_t)DH, 1};
     if ((rc = encode_map(&mv, vt, 3, dims, strides, box, 128)) != DV_OK) return rc;
   }
-  const size_t smem = 2 * 128 * DH * 2 + AT_STAGES * (AT_KT * DH * 2 + DH * AT_KT * 2) + 2 * 16384 + 256 + 4096 + 1024;
+  const size_t smem = 2 * 128 * DH * 2 + AT_STAGES * (AT_KT * DH * 2 + DH * AT_KT * 2) + 4 * 16384 + 256 + 4096 + 1024;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(attn_tc_kernel<32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -539,7 +558,7 @@ int xattn_tc_launch(const dv_xattn_params& p, cudaStream_t s) {
     uint32_t box[3] = {64, (uint32_t)DH, 1};
     if ((rc = encode_map(&mv, vtp, 3, dims, strides, box, 128)) != DV_OK) return rc;
   }
-  const size_t smem = 2 * 128 * DH * 2 + AT_STAGES * (AT_KT * DH * 2 + DH * AT_KT * 2) + 2 * 16384 + 256 + 4096 + 1024;
+  const size_t smem = 2 * 128 * DH * 2 + AT_STAGES * (AT_KT * DH * 2 + DH * AT_KT * 2) + 4 * 16384 + 256 + 4096 + 1024;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(attn_tc_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
