@@ -290,8 +290,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
           __nv_bfloat162* dh2 = reinterpret_cast<__nv_bfloat162*>(&dk);
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            const float pa = exp2f(fmaf(__uint_as_float(rs[g * 8 + 2 * e]), p.scale_log2e, -lse));
-            const float pb = exp2f(fmaf(__uint_as_float(rs[g * 8 + 2 * e + 1]), p.scale_log2e, -lse));
+            const float pa = ex2_ftz(fmaf(__uint_as_float(rs[g * 8 + 2 * e]), p.scale_log2e, -lse));
+            const float pb = ex2_ftz(fmaf(__uint_as_float(rs[g * 8 + 2 * e + 1]), p.scale_log2e, -lse));
             const float da = pa * (__uint_as_float(rp[g * 8 + 2 * e]) - D) * p.scale;
             const float db = pb * (__uint_as_float(rp[g * 8 + 2 * e + 1]) - D) * p.scale;
             ph2[e] = __floats2bfloat162_rn(pa, pb);

@@ -71,14 +71,6 @@ __device__ __forceinline__ void tma_load_3d_at(const CUtensorMap* map, uint64_t*
       : "memory");
 }
 
-// One MUFU.EX2: exp2f() without -use_fast_math wraps it in a range test and two multiplies per element to keep
-// denormal results, which a softmax probability never needs (results below 2^-126 flush to zero).
-__device__ __forceinline__ float ex2_ftz(float x) {
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-
 template <int DH>
 __device__ __forceinline__ uint64_t qk_desc(uint32_t saddr) {
   return DH == 32 ? make_smem_desc_sw64(saddr) : make_smem_desc(saddr);  // 64-byte rows vs 128-byte rows

@@ -197,8 +197,8 @@ __global__ void __launch_bounds__(TA_THREADS, 4) attn_temporal_kernel(const dv_a
           for (int half = 0; half < 2; ++half) {
             const int j = kk * 2 + half;
             if (j < NKT) {
-              pa[kk][half * 2] = pack_bf16(exp2f(s[j][0] - m0), exp2f(s[j][1] - m0));
-              pa[kk][half * 2 + 1] = pack_bf16(exp2f(s[j][2] - m1), exp2f(s[j][3] - m1));
+              pa[kk][half * 2] = pack_bf16(ex2_ftz(s[j][0] - m0), ex2_ftz(s[j][1] - m0));
+              pa[kk][half * 2 + 1] = pack_bf16(ex2_ftz(s[j][2] - m1), ex2_ftz(s[j][3] - m1));
               l0 += bf16_pair_sum(pa[kk][half * 2]);
               l1 += bf16_pair_sum(pa[kk][half * 2 + 1]);
             } else {

@@ -87,6 +87,14 @@ __device__ __forceinline__ void store8(__nv_bfloat16* p, const float (&v)[8]) {
 }
 
 // x * sigmoid(x); __fdividef (2 ulp) keeps the streaming kernels off the IEEE-division slow path
+// One MUFU.EX2: exp2f() without -use_fast_math wraps it in a range test and two multiplies per element to keep
+// denormal results, which a softmax probability never needs (results below 2^-126 flush to zero).
+__device__ __forceinline__ float ex2_ftz(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 __device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
 __device__ __forceinline__ float gelu_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 

@@ -1,3 +1,7 @@
+"""Per-step error growth of the sampler against the CPU oracle loop, with and without self-conditioning and classifier-free
+guidance (tiny Unet3D, 4x16x16, fp32).  Shows that the first step agrees to ~1e-4 in every mode and that the self-conditioning
+feedback amplifies that difference step by step under guidance (random weights): the reason the self-conditioned CFG parity
+test uses a 6-step chain.  Measurement tool, not a product path.  Usage: python tools/diag_sc.py"""
 import json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
