@@ -134,27 +134,38 @@ def test_library_builds_loads_and_exports_every_declared_symbol(built_lib):
     assert isinstance(lib.dv_last_error_string(), bytes)
 
 
-def test_abi_struct_sizes_match_header(built_lib):
-    # A C compile of the header gives the authoritative sizes; ctypes mirrors must agree field for field.
+def test_abi_struct_layouts_match_header(built_lib):
+    """Every parameter struct of include/dv_b200.h against its ctypes mirror: a C compile of the header gives the
+    authoritative sizeof and the offsetof of every field; the mirrors must agree field for field (same names, `in_` for
+    the C field `in`)."""
     import subprocess
     import tempfile
-    names = {"dv_ddpm_step_params": "DdpmStepParams", "dv_conv_params": "ConvParams",
-             "dv_gn_apply_params": "GnApplyParams", "dv_gn_stats_params": "GnStatsParams",
-             "dv_layernorm_params": "LayerNormParams", "dv_xattn_params": "XattnParams",
-             "dv_attn_mqa_params": "AttnMqaParams", "dv_time_embed_params": "TimeEmbedParams",
-             "dv_linear_small_params": "LinearSmallParams", "dv_cond_tokens_params": "CondTokensParams",
-             "dv_to_out_params": "ToOutParams", "dv_im2col_params": "Im2colParams",
-             "dv_xattn_fold_prep_params": "XattnFoldPrepParams", "dv_xattn_fold_params": "XattnFoldParams"}
-    src = '#include <stdio.h>\n#include "dv_b200.h"\nint main(){' + "".join(
-        f'printf("{c} %zu\\n", sizeof({c}));' for c in names) + "return 0;}"
+    header = open(os.path.join(ROOT, "include", "dv_b200.h")).read()
+    takes = dict(re.findall(r"^int\s+(dv_\w+)\s*\(\s*const\s+(dv_\w+)\s*\*", header, flags=re.M))
+    pairs = {}   # C struct -> ctypes class
+    for fn, cls in built_lib.ENTRY_POINTS.items():
+        assert fn in takes, f"{fn}: no `int {fn}(const <struct>* ...)` declaration in the header"
+        pairs[takes[fn]] = cls
+    assert len(pairs) >= 30
+    lines = []
+    for cname, cls in pairs.items():
+        lines.append(f'printf("{cname} sizeof %zu\\n", sizeof({cname}));')
+        for field, _ in cls._fields_:
+            lines.append(f'printf("{cname} {field} %zu\\n", offsetof({cname}, {field.rstrip("_")}));')
+    src = '#include <stdio.h>\n#include <stddef.h>\n#include "dv_b200.h"\nint main(){' + "".join(lines) + "return 0;}"
     with tempfile.TemporaryDirectory() as d:
         open(os.path.join(d, "s.c"), "w").write(src)
         subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), os.path.join(d, "s.c"), "-o",
                                os.path.join(d, "s")])
         out = subprocess.check_output([os.path.join(d, "s")], text=True)
+    checked = 0
     for line in out.strip().splitlines():
-        c, size = line.split()
-        assert ctypes.sizeof(getattr(built_lib, names[c])) == int(size), c
+        cname, what, value = line.split()
+        cls = pairs[cname]
+        got = ctypes.sizeof(cls) if what == "sizeof" else getattr(cls, what).offset
+        assert got == int(value), (cname, what, got, int(value))
+        checked += 1
+    assert checked > 300
 
 
 def test_null_params_return_error_code_not_crash(built_lib):
