@@ -780,24 +780,13 @@ def p_losses(decoder, unet: Unet3D, x_start, times, *, video_embed, noise_schedu
     return _PlanFunction.apply(plan, target, outs["ss"], *[outs[k] for k in plan.kv_kinds])
 
 
-class VideoDecoderTrainer(nn.Module):
-    """The optimiser half of the reference's VideoDecoderTrainer (/root/reference/dalle2_video/trainer.py:40-365) for a
-    single-unet decoder: forward() = loss + backward (+ gradient all-reduce when torch.distributed is initialised, the
-    only collective of the training config), update() = clip_grad_norm_ + AdamW + zero_grad on flat fp32 buffers with
-    two launches (dv_sumsq, dv_adamw per weight-decay group).  get_optimizer semantics: AdamW,
-    betas (0.9, 0.99), parameters with ndim < 2 excluded from weight decay when group_wd_params."""
+class _UnetOptState:
+    """Flat fp32 parameter / gradient / Adam-moment buffers of ONE unet (param.data and param.grad become views)."""
 
-    def __init__(self, decoder, lr=1e-4, wd=1e-2, eps=1e-8, max_grad_norm=0.5, group_wd_params=True, betas=(0.9, 0.99),
-                 overlap_allreduce=False, bucket_bytes=32 << 20, **_):
-        super().__init__()
-        self.decoder = decoder
-        self.lr, self.wd, self.eps, self.betas = lr, wd, eps, betas
-        self.max_grad_norm = max_grad_norm
-        unet = decoder.unets[0]
-        params = [p for p in decoder.parameters() if p.requires_grad]
+    def __init__(self, unet, wd, group_wd_params):
+        params = [p for p in unet.parameters() if p.requires_grad]
         decay = [p for p in params if p.ndim >= 2 or not group_wd_params]
         no_decay = [p for p in params if not (p.ndim >= 2 or not group_wd_params)]
-        self._groups = []
         dev = params[0].device
         ordered = decay + no_decay
         n = sum(p.numel() for p in ordered)
@@ -814,17 +803,51 @@ class VideoDecoderTrainer(nn.Module):
                 p.grad = self.flat_g[off:off + k].view(p.shape)
                 off += k
         nd = sum(p.numel() for p in decay)
-        self._groups = [(0, nd, wd), (nd, n - nd, 0.0)]
-        self.register_buffer("steps", torch.tensor([0]))
-        self._sumsq = torch.zeros(1, dtype=torch.float64, device=dev)
-        self._params = ordered
-        self.overlap_allreduce, self.bucket_bytes, self.min_bucket_bytes = overlap_allreduce, bucket_bytes, 4 << 20
-        self._buckets, self._bucket_plan, self._overlap_live = None, None, False
+        self.groups = [(0, nd, wd), (nd, n - nd, 0.0)]
+        self.sumsq = torch.zeros(1, dtype=torch.float64, device=dev)
+        self.params = ordered
+        self.buckets, self.bucket_plan = None, None
         unet._engines.clear()  # every plan (and captured graph) built before the parameters moved into the flat buffer is stale
 
-    def _overlap_setup(self, plan):
+
+class VideoDecoderTrainer(nn.Module):
+    """The optimiser half of the reference's VideoDecoderTrainer (/root/reference/dalle2_video/trainer.py:40-365):
+    forward(unet_number) = loss + backward of that unet (+ gradient all-reduce when torch.distributed is initialised, the
+    only collective of the training config), update(unet_number) = clip_grad_norm_ + AdamW + zero_grad on that unet's flat
+    fp32 buffers with two launches (dv_sumsq, dv_adamw per weight-decay group).  One optimiser state and one step counter
+    per unet, as the reference keeps optim{i} / steps[i] (:60-110, :240-274).  get_optimizer semantics:
+    AdamW, betas (0.9, 0.99), parameters with ndim < 2 excluded from weight decay when group_wd_params."""
+
+    def __init__(self, decoder, lr=1e-4, wd=1e-2, eps=1e-8, max_grad_norm=0.5, group_wd_params=True, betas=(0.9, 0.99),
+                 overlap_allreduce=False, bucket_bytes=32 << 20, **_):
+        super().__init__()
+        self.decoder = decoder
+        self.num_unets = len(decoder.unets)
+        self.lr, self.wd, self.eps, self.betas = lr, wd, eps, betas
+        self.max_grad_norm = max_grad_norm
+        self._opt = [_UnetOptState(u, wd, group_wd_params) for u in decoder.unets]
+        self.register_buffer("steps", torch.tensor([0] * self.num_unets))
+        self.overlap_allreduce, self.bucket_bytes, self.min_bucket_bytes = overlap_allreduce, bucket_bytes, 4 << 20
+        self._overlap_live, self._live_state = False, None
+
+    # the first unet's buffers under their old names (single-unet callers, tools/bench_train.py)
+    flat_p = property(lambda self: self._opt[0].flat_p)
+    flat_g = property(lambda self: self._opt[0].flat_g)
+    exp_avg = property(lambda self: self._opt[0].exp_avg)
+    exp_avg_sq = property(lambda self: self._opt[0].exp_avg_sq)
+    _buckets = property(lambda self: self._opt[0].buckets)
+
+    def validate_and_return_unet_number(self, unet_number=None):
+        """Reference: trainer.py (dalle2_pytorch DecoderTrainer): the unet must be named when there are several."""
+        if self.num_unets == 1:
+            unet_number = 1 if unet_number is None else unet_number
+        assert unet_number is not None and 1 <= unet_number <= self.num_unets, \
+            f"unet number should be in between 1 and {self.num_unets}"
+        return unet_number
+
+    def _overlap_setup(self, st, plan):
         """Split the plan's backward and map every slice of the flat gradient buffer to the segment that finishes it."""
-        if plan is self._bucket_plan:
+        if plan is st.bucket_plan:
             return
         nseg = plan.split_backward(self.bucket_bytes)
         seg_of = {}
@@ -832,15 +855,15 @@ class VideoDecoderTrainer(nn.Module):
             for i in ids:
                 prm = plan.grad_map[i][0]
                 seg_of[id(prm)] = max(seg_of.get(id(prm), 0), s)
-        base = self.flat_g.data_ptr()
-        items = [((p.grad.data_ptr() - base) // 4, p.numel(), seg_of.get(id(p), nseg)) for p in self._params]
-        self._buckets = GradBuckets(self.flat_g, items, nseg, min_bytes=self.min_bucket_bytes)
+        base = st.flat_g.data_ptr()
+        items = [((p.grad.data_ptr() - base) // 4, p.numel(), seg_of.get(id(p), nseg)) for p in st.params]
+        st.buckets = GradBuckets(st.flat_g, items, nseg, min_bytes=self.min_bucket_bytes)
         plan.on_segment = self._on_segment
-        self._bucket_plan = plan
+        st.bucket_plan = plan
 
     def _on_segment(self, i):
-        if self._overlap_live:
-            self._buckets.launch(i)
+        if self._overlap_live and self._live_state is not None:
+            self._live_state.buckets.launch(i)
 
     def forward(self, video, video_embed, unet_number=None, **kwargs):
         """loss + backward + gradient averaging.  Data parallel: ONE all-reduce of the flat gradient buffer after the
@@ -848,40 +871,46 @@ class VideoDecoderTrainer(nn.Module):
         producing them has run (parallel.GradBuckets; the first two steps — eager warm-up, graph capture — still reduce
         after the backward).  The default is the measured winner: the backward's conv kernels are persistent with one
         CTA per SM and a static tile split, so every SM NCCL holds while they run costs a second wave — 25.0 vs 24.1 ms
-        per step at 2 GPUs (profiles/r01_train_2gpu_overlap_ab.json, DESIGN.md section 11)."""
+        per step at 2 GPUs (profiles/r01_train_2gpu_overlap_ab.json, DESIGN.md section 10)."""
+        unet_number = self.validate_and_return_unet_number(unet_number)
+        st, unet = self._opt[unet_number - 1], self.decoder.unets[unet_number - 1]
         loss = self.decoder(video, video_embed=video_embed, unet_number=unet_number, **kwargs)
         import torch.distributed as dist
         data_parallel = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
-        plan = getattr(self.decoder.unets[0], "_train_plan_last", None)
+        plan = getattr(unet, "_train_plan_last", None)
         if data_parallel and self.overlap_allreduce and plan is not None:
-            self._overlap_setup(plan)
-            self._overlap_live = plan.graphs_ready()
+            self._overlap_setup(st, plan)
+            self._overlap_live, self._live_state = plan.graphs_ready(), st
             loss.backward()
-            self._buckets.finish()
+            st.buckets.finish()
+            self._overlap_live = False
         else:
+            self._overlap_live = False
             loss.backward()
-            allreduce_mean_(self.flat_g)
+            allreduce_mean_(st.flat_g)
         return loss.item()
 
     @torch.no_grad()
     def update(self, unet_number=None):
-        dev = self.flat_p.device
+        unet_number = self.validate_and_return_unet_number(unet_number)
+        st = self._opt[unet_number - 1]
+        dev = st.flat_p.device
         stream = torch.cuda.current_stream(dev).cuda_stream
-        step = int(self.steps[0]) + 1
-        self._sumsq.zero_()
+        step = int(self.steps[unet_number - 1]) + 1
+        st.sumsq.zero_()
         use_clip = self.max_grad_norm is not None
         if use_clip:
-            L.call("dv_sumsq", L.SumsqParams(x=self.flat_g.data_ptr(), out=self._sumsq.data_ptr(), n=self.flat_g.numel()), stream)
+            L.call("dv_sumsq", L.SumsqParams(x=st.flat_g.data_ptr(), out=st.sumsq.data_ptr(), n=st.flat_g.numel()), stream)
         b1, b2 = self.betas
-        for off, n, wd in self._groups:
+        for off, n, wd in st.groups:
             if n == 0:
                 continue
             L.call("dv_adamw", L.AdamwParams(
-                param=self.flat_p.data_ptr() + off * 4, grad=self.flat_g.data_ptr() + off * 4,
-                exp_avg=self.exp_avg.data_ptr() + off * 4, exp_avg_sq=self.exp_avg_sq.data_ptr() + off * 4,
-                grad_sumsq=self._sumsq.data_ptr() if use_clip else None, n=n, lr=self.lr, beta1=b1, beta2=b2, eps=self.eps,
+                param=st.flat_p.data_ptr() + off * 4, grad=st.flat_g.data_ptr() + off * 4,
+                exp_avg=st.exp_avg.data_ptr() + off * 4, exp_avg_sq=st.exp_avg_sq.data_ptr() + off * 4,
+                grad_sumsq=st.sumsq.data_ptr() if use_clip else None, n=n, lr=self.lr, beta1=b1, beta2=b2, eps=self.eps,
                 weight_decay=wd, bias_correction1=1 - b1 ** step, bias_correction2=1 - b2 ** step,
                 max_grad_norm=float(self.max_grad_norm or 0.0)), stream)
-        self.flat_g.zero_()
-        self.steps += 1
-        self.decoder.unets[0].invalidate_cache()  # sampler plans hold packed copies of the old weights
+        st.flat_g.zero_()
+        self.steps[unet_number - 1] += 1
+        self.decoder.unets[unet_number - 1].invalidate_cache()  # sampler plans hold packed copies of the old weights

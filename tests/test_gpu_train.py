@@ -392,3 +392,37 @@ def test_lowres_conditioner_blurs_half_of_the_time_like_the_reference():
             low = gaussian_blur_frames(low, 3, 0.6)
         want = resize_nearest(low, 32, clamp_range=(0.0, 1.0))
         assert levels is None and rel_err(got, want) < 1e-6, seed
+
+
+def test_trainer_keeps_one_optimiser_state_per_unet(layouts):
+    """VideoDecoderTrainer.forward / update take the unet number (reference trainer.py:240-274, :322-365): training the
+    second unet of a cascade leaves the first one bit-identical (no weight decay, no Adam step on it), each unet has its
+    own step counter, and the unet must be named when there are several."""
+    kw = CASES["tiny"][0]
+    u1, u2 = Unet3D(**kw), Unet3D(**dict(kw, lowres_cond=True))
+    dec = VideoDecoder((u1, u2), frame_sizes=(16, 32), frame_numbers=(4, 4), timesteps=100, learned_variance=False,
+                       use_noise_for_lowres_cond=True, use_blur_for_lowres_cond=False).cuda()
+    torch.nn.init.normal_(dec.unets[1].to_out.weight, std=0.02)
+    torch.nn.init.normal_(dec.unets[0].to_out.weight, std=0.02)
+    trainer = VideoDecoderTrainer(dec, lr=3e-4, wd=1e-2, max_grad_norm=0.5)
+    g = torch.Generator().manual_seed(2)
+    video, emb = torch.rand(2, 3, 4, 32, 32, generator=g).cuda(), torch.randn(2, 512, generator=g).cuda()
+    with pytest.raises(AssertionError):
+        trainer(video, video_embed=emb)
+    before1 = [p.detach().clone() for p in dec.unets[0].parameters()]
+    before2 = [p.detach().clone() for p in dec.unets[1].parameters()]
+    losses = []
+    for _ in range(8):
+        torch.manual_seed(5)
+        losses.append(trainer(video, video_embed=emb, unet_number=2))
+        trainer.update(unet_number=2)
+    assert trainer.steps.tolist() == [0, 8]
+    assert losses[-1] < 0.95 * losses[0], losses
+    assert all(torch.equal(a, b) for a, b in zip(before1, dec.unets[0].parameters()))
+    assert any(not torch.equal(a, b) for a, b in zip(before2, dec.unets[1].parameters()))
+    after2 = [p.detach().clone() for p in dec.unets[1].parameters()]
+    trainer(video, video_embed=emb, unet_number=1)   # the first stage resizes the 32 px video down to its 16 px itself
+    trainer.update(unet_number=1)
+    assert trainer.steps.tolist() == [1, 8]
+    assert all(torch.equal(a, b) for a, b in zip(after2, dec.unets[1].parameters()))
+    assert any(not torch.equal(a, b) for a, b in zip(before1, dec.unets[0].parameters()))
