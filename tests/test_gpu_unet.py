@@ -83,3 +83,23 @@ def test_zero_init_to_out_gives_exact_zero():
     u = Unet3D(dim=32, video_embed_dim=512, dim_mults=(1, 2), cond_on_video_embeds=True).cuda()
     y = u(torch.randn(1, 3, 8, 32, 32).cuda(), torch.tensor([5]).cuda(), video_embed=torch.randn(1, 512).cuda())
     assert float(y.abs().max()) == 0.0  # SURVEY.md F6 anchor
+
+
+@pytest.mark.parametrize("shape", [(1, 3, 1, 16, 16), (3, 3, 3, 16, 32), (2, 3, 5, 32, 16), (1, 3, 2, 8, 8), (5, 3, 2, 4, 4),
+                                   (1, 3, 7, 24, 40)])
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, FP32_TOL), (torch.bfloat16, BF16_TOL)])
+def test_forward_on_ragged_shapes_matches_oracle(shape, dtype, tol, layouts):
+    """Edge shapes the fixtures do not hold: a single frame, odd batch / frame counts, non-square frames, frame sides that
+    are not a multiple of 8 or 16 (24 x 40), and the smallest frames the two-stage topology admits (4 x 4 -> 2 x 2)."""
+    kw = dict(dim=32, video_embed_dim=512, dim_mults=(1, 2), cond_on_video_embeds=True)
+    sd = synth_state_dict(layouts["tiny"], seed=5)
+    u = make_unet(kw, layouts["tiny"], seed=5)
+    u.compute_dtype = dtype
+    g = torch.Generator().manual_seed(sum(shape))
+    x, emb = torch.randn(shape, generator=g), torch.randn(shape[0], 512, generator=g)
+    t = torch.randint(0, 1000, (shape[0],), generator=g)
+    with torch.no_grad():
+        ref = unet3d_forward(sd, UnetConfig(**kw), x, t, video_embed=emb)
+    out = u(x.cuda(), t.cuda(), video_embed=emb.cuda())
+    assert out.shape == ref.shape
+    assert rel_err(out, ref) < tol
