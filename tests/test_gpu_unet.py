@@ -103,3 +103,27 @@ def test_forward_on_ragged_shapes_matches_oracle(shape, dtype, tol, layouts):
     out = u(x.cuda(), t.cuda(), video_embed=emb.cuda())
     assert out.shape == ref.shape
     assert rel_err(out, ref) < tol
+
+
+def test_text_padding_rows_and_truncation_match_oracle(layouts):
+    """Text edge cases (:787-815): all-zero rows are padding and get the null text embedding, an all-padding sample is
+    legal, and encodings longer than max_text_len are truncated."""
+    kw = dict(dim=32, video_embed_dim=512, dim_mults=(1, 2), cond_on_video_embeds=True,
+              cond_on_text_encodings=True, text_embed_dim=64, max_text_len=6)
+    u = Unet3D(**kw)
+    lay = {k: list(v.shape) for k, v in u.state_dict().items()}
+    sd = synth_state_dict(lay, seed=3)
+    u.load_state_dict(sd, strict=True)
+    u = u.cuda()
+    g = torch.Generator().manual_seed(2)
+    x, emb = torch.randn(3, 3, 2, 16, 16, generator=g), torch.randn(3, 512, generator=g)
+    t = torch.tensor([10, 500, 990])
+    for n_text in (1, 4, 9):          # 9 > max_text_len = 6: truncated
+        txt = torch.randn(3, n_text, 64, generator=g)
+        if n_text > 1:
+            txt[0, n_text // 2:] = 0.0   # trailing padding
+            txt[1] = 0.0                 # a sample with no text at all
+        with torch.no_grad():
+            ref = unet3d_forward(sd, UnetConfig(**kw), x, t, video_embed=emb, text_encodings=txt)
+        out = u(x.cuda(), t.cuda(), video_embed=emb.cuda(), text_encodings=txt.cuda())
+        assert rel_err(out, ref) < FP32_TOL, n_text
