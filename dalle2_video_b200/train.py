@@ -871,7 +871,7 @@ class VideoDecoderTrainer(nn.Module):
         producing them has run (parallel.GradBuckets; the first two steps — eager warm-up, graph capture — still reduce
         after the backward).  The default is the measured winner: the backward's conv kernels are persistent with one
         CTA per SM and a static tile split, so every SM NCCL holds while they run costs a second wave — 25.0 vs 24.1 ms
-        per step at 2 GPUs (profiles/r01_train_2gpu_overlap_ab.json)."""
+        per step at 2 GPUs, 25.6 vs 24.3 ms at 8 (profiles/r01_train_{2,8}gpu_overlap_ab.json)."""
         unet_number = self.validate_and_return_unet_number(unet_number)
         st, unet = self._opt[unet_number - 1], self.decoder.unets[unet_number - 1]
         loss = self.decoder(video, video_embed=video_embed, unet_number=unet_number, **kwargs)
