@@ -73,8 +73,6 @@ class _TrainPlan:
             raise NotImplementedError("training with text conditioning has no backward kernels yet (long-context cross attention)")
         if u.temporal_conv or any(u._stage_temporal_attn) or u.attn_mode != "joint":
             raise NotImplementedError("the extensions (temporal conv / attention, factorised attention) have no backward kernels")
-        if u.skip_connect_scale != 1.0:
-            raise NotImplementedError("scaled skip connections are outside the training plan")
         self.u, self.B, self.T, self.H, self.W, self.device = u, B, T, H, W, device
         self.code = L.DV_BF16
         L.lib()
@@ -202,9 +200,27 @@ class _TrainPlan:
         self.tape.append(backward)
         return out
 
-    def _std_conv(self, srcs, conv: nn.Conv3d, n_img, h, w, k, stats=None, groups=0):
-        return self._conv(srcs, lambda: conv.weight.detach().float(), lambda: conv.bias.detach().float(), conv.weight,
-                          lambda g5: g5, conv.bias, conv.weight.shape[0], n_img, h, w, k=k, stats=stats, groups=groups)
+    def _std_conv(self, srcs, conv: nn.Conv3d, n_img, h, w, k, stats=None, groups=0, skip_scale=1.0):
+        """`skip_scale`: the second source is a skip connection the reference multiplies by skip_connect_scale before the
+        concat (:926-928, :945).  The factor is folded into that source's weight columns, so the forward and the
+        data-gradient use the scaled weights as they are and the weight gradient of those columns gets the factor back."""
+        c0, scaled = srcs[0].C, skip_scale != 1.0 and len(srcs) > 1
+
+        def w5():
+            wt = conv.weight.detach().float()
+            if scaled:
+                wt = wt.clone()
+                wt[:, c0:] *= skip_scale
+            return wt
+
+        def from5(g5):
+            if scaled:
+                g5 = g5.clone()
+                g5[:, c0:] *= skip_scale
+            return g5
+
+        return self._conv(srcs, w5, lambda: conv.bias.detach().float(), conv.weight, from5, conv.bias,
+                          conv.weight.shape[0], n_img, h, w, k=k, stats=stats, groups=groups)
 
     def _linear(self, src, lin_weight: nn.Parameter, rows):
         """bias-free nn.Linear on a [rows][K] activation, as a 1x1 convolution (to_q / to_kv / to_out projections)."""
@@ -349,14 +365,14 @@ class _TrainPlan:
         y = self._linear(o, at.to_out[0].weight, x.rows)
         return self._layernorm(y, at.to_out[1].g, residual=x)
 
-    def _resblock(self, m, srcs, h, w):
-        """ResnetBlock3D.forward (:172-205)."""
+    def _resblock(self, m, srcs, h, w, skip_scale=1.0):
+        """ResnetBlock3D.forward (:172-205); skip_scale applies to srcs[1] (see _std_conv)."""
         B, T = self.B, self.T
         n_img, P = B * T, T * h * w
         off = self.ss_off[id(m)]
         G = m.groups
         st1 = self._next_stats()
-        h1r = self._std_conv(srcs, m.block1.project, n_img, h, w, 3, stats=st1, groups=G)
+        h1r = self._std_conv(srcs, m.block1.project, n_img, h, w, 3, stats=st1, groups=G, skip_scale=skip_scale)
         h1 = self._gn_block(h1r, st1, m.block1.norm, off, None, P)
         if m.cross_attn is not None:
             h1 = self._cross_attention(m, h1, P)
@@ -365,7 +381,7 @@ class _TrainPlan:
         if isinstance(m.res_conv, nn.Identity):
             res = srcs[0]
         else:
-            res = self._std_conv(srcs, m.res_conv, n_img, h, w, 1)
+            res = self._std_conv(srcs, m.res_conv, n_img, h, w, 1, skip_scale=skip_scale)
         return self._gn_block(h2r, st2, m.block2.norm, None, res, P)
 
     # -------------------------------------------------------------- plan construction
@@ -488,9 +504,9 @@ class _TrainPlan:
         x = self._self_attention(u.mid_attn.fn.fn, x, T * h * w)
         x = self._resblock(u.mid_block2, [x], h, w)
         for s, st in enumerate(u.ups):
-            x = self._resblock(st[0], [x, hiddens.pop()], h, w)
+            x = self._resblock(st[0], [x, hiddens.pop()], h, w, skip_scale=u.skip_connect_scale)
             for m in st[1]:
-                x = self._resblock(m, [x, hiddens.pop()], h, w)
+                x = self._resblock(m, [x, hiddens.pop()], h, w, skip_scale=u.skip_connect_scale)
             if not isinstance(st[2], nn.Identity):
                 x = self._self_attention(st[2].fn.fn, x, T * h * w)
             up = st[3]

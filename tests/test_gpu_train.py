@@ -453,3 +453,31 @@ def test_training_on_ragged_shapes_matches_oracle_autograd(shape):
         if rg.numel() >= 256 and float(rg.norm()) > 1e-6:
             assert float(F.cosine_similarity(gg.flatten(), rg.flatten(), dim=0)) >= 0.98, k
     assert (num / den) ** 0.5 < 8e-2, (num / den) ** 0.5
+
+
+def test_training_with_scaled_skip_connections_matches_oracle_autograd(layouts):
+    """scale_skip_connection=True (:926-928, :945): the 2^-0.5 factor on the skip half of every up-block concat is folded
+    into the weight columns of that source for forward / data-gradient and restored on the weight gradient."""
+    kw = dict(CASES["tiny"][0], scale_skip_connection=True)
+    shape = (2, 3, 4, 16, 16)
+    dec, sd = build(kw, shape[2], shape[3])
+    g = torch.Generator().manual_seed(13)
+    video, noise = torch.rand(shape, generator=g), torch.randn(shape, generator=g)
+    emb, times = torch.randn(2, 512, generator=g), torch.tensor([11, 80])
+    ref_loss, ref_grads = oracle_loss_and_grads(sd, kw, video, times, noise, emb)
+    plain_loss, _ = oracle_loss_and_grads(sd, CASES["tiny"][0], video, times, noise, emb)
+    assert abs(ref_loss - plain_loss) > 1e-3 * plain_loss   # the option changes the function
+    unet = dec.unets[0]
+    loss = p_losses(dec, unet, video.cuda(), times.cuda(), video_embed=emb.cuda(), noise_scheduler=dec.noise_schedulers[0],
+                    noise=noise.cuda())
+    assert abs(float(loss) - ref_loss) < 2e-2 * ref_loss, (float(loss), ref_loss)
+    loss.backward()
+    got = {k: p.grad for k, p in unet.named_parameters()}
+    num = den = 0.0
+    for k, rg in ref_grads.items():
+        gg = got[k].float().cpu()
+        num += float((gg - rg).pow(2).sum())
+        den += float(rg.pow(2).sum())
+        if rg.numel() >= 256 and float(rg.norm()) > 1e-6:
+            assert float(F.cosine_similarity(gg.flatten(), rg.flatten(), dim=0)) >= 0.98, k
+    assert (num / den) ** 0.5 < 8e-2, (num / den) ** 0.5
