@@ -217,7 +217,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
     const int row = q * 32 + lane;
     constexpr int OH = DH / 2;
     const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
-    auto pair_bar = []() { asm volatile("bar.sync 2, 256;" ::: "memory"); };
+    // the two warps that share a row group (lane quarter q) meet on their own named barrier: the four pairs drift freely
+    auto pair_bar = [q]() { asm volatile("bar.sync %0, 64;" ::"r"(2 + q) : "memory"); };
     int t = 0;
     int64_t jj = 0;
     for (int64_t tile = tile_begin; tile < tile_end; ++tile, ++t) {
