@@ -176,3 +176,38 @@ def test_null_params_return_error_code_not_crash(built_lib):
     assert b"null pointer" in lib.dv_last_error_string()
     c = built_lib.ConvParams()
     assert lib.dv_conv_igemm(ctypes.byref(c), None) == -1
+
+
+def test_trainer_flat_buffers_are_per_unet_views():
+    """Host logic of VideoDecoderTrainer (no kernels run): every unet gets its own flat parameter / gradient / moment
+    buffers, param.data and param.grad alias them, weight-decay groups split at ndim >= 2, and the unet must be named when
+    there are several (reference trainer.py:60-110, validate_and_return_unet_number)."""
+    import pytest
+    import torch
+    from dalle2_video_b200 import Unet3D, VideoDecoder, VideoDecoderTrainer
+    kw = dict(dim=16, video_embed_dim=32, dim_mults=(1, 2), cond_on_video_embeds=True)
+    dec = VideoDecoder((Unet3D(**kw), Unet3D(**dict(kw, lowres_cond=True))), frame_sizes=(8, 16), frame_numbers=(2, 2),
+                       timesteps=10, learned_variance=False, use_noise_for_lowres_cond=True)
+    tr = VideoDecoderTrainer(dec)
+    assert tr.num_unets == 2 and tr.steps.tolist() == [0, 0]
+    for st, unet in zip(tr._opt, dec.unets):
+        n = sum(p.numel() for p in unet.parameters())
+        assert st.flat_p.numel() == st.flat_g.numel() == st.exp_avg.numel() == st.exp_avg_sq.numel() == n
+        lo, hi = st.flat_p.data_ptr(), st.flat_p.data_ptr() + 4 * n
+        assert all(lo <= p.data_ptr() < hi for p in unet.parameters())
+        glo = st.flat_g.data_ptr()
+        assert all(glo <= p.grad.data_ptr() < glo + 4 * n for p in unet.parameters())
+        (o0, n0, wd0), (o1, n1, wd1) = st.groups
+        assert o0 == 0 and o1 == n0 and n0 + n1 == n and wd0 > 0 and wd1 == 0.0
+        assert n1 == sum(p.numel() for p in unet.parameters() if p.ndim < 2)
+        w = next(p for p in unet.parameters() if p.ndim >= 2)
+        st.flat_p.zero_()
+        assert float(w.detach().abs().max()) == 0.0   # a view, not a copy
+    assert tr._opt[0].flat_p.data_ptr() != tr._opt[1].flat_p.data_ptr()
+    assert tr.validate_and_return_unet_number(2) == 2
+    with pytest.raises(AssertionError):
+        tr.validate_and_return_unet_number(None)
+    with pytest.raises(AssertionError):
+        tr.validate_and_return_unet_number(3)
+    single = VideoDecoderTrainer(VideoDecoder(Unet3D(**kw), frame_size=8, frame_numbers=(2,), timesteps=10, learned_variance=False))
+    assert single.validate_and_return_unet_number(None) == 1
