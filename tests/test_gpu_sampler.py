@@ -381,3 +381,24 @@ def test_self_conditioned_cfg_and_ddim_match_oracle_loops(layouts):
                                          cond_scale=2.0, generator=torch.Generator().manual_seed(55))
         err = float((vid.cpu() - ref).abs().max())
         assert err < 3e-3, (sample_steps, err)
+
+
+def test_unconditional_decoder_samples_from_batch_size_alone(layouts):
+    """VideoDecoder(unconditional=True).sample(batch_size=n) (:2072-2076): no video embedding anywhere; against the oracle
+    loop with video_embed=None on the same weights and noise."""
+    from oracle.primitives import NoiseScheduler as OracleScheduler
+    from oracle.unet3d import UnetConfig, p_sample_loop_ddpm
+    kw = dict(dim=32, dim_mults=(1, 2), cond_on_video_embeds=False)
+    u = Unet3D(**kw)
+    lay = {k: list(v.shape) for k, v in u.state_dict().items()}
+    d = VideoDecoder(u, frame_size=16, frame_numbers=(4,), timesteps=8, learned_variance=False, unconditional=True).cuda()
+    lay = {k: list(v.shape) for k, v in d.unets[0].state_dict().items()}
+    sd = synth_state_dict(lay, seed=7)
+    d.unets[0].load_state_dict(sd, strict=True)
+    vid = d.sample(batch_size=2, noise_fn=cpu_noise(77))
+    assert vid.shape == (2, 3, 4, 16, 16)
+    with torch.no_grad():
+        ref = p_sample_loop_ddpm(sd, UnetConfig(**kw), OracleScheduler(beta_schedule="cosine", timesteps=8, loss_type="l2"),
+                                 (2, 3, 4, 16, 16), video_embed=None, generator=torch.Generator().manual_seed(77))
+    err = float((vid.cpu() - ref).abs().max())
+    assert err < 2e-3, err
