@@ -276,6 +276,52 @@ def objectives():
                os.path.join(GOLDEN, "sample_objectives.pt"))
 
 
+class _DdimKwargAdapter:
+    """The reference's p_sample_loop_ddim (:1757-1889) calls `unet.forward_with_cond_scale(..., image_embed=,
+    lowres_cond_img=)`, names its own Unet3D does not take, so the method cannot run as shipped.  This
+    adapter only renames those two keywords; the loop that runs — time pairs, x_start, clipping, pred_noise, c1 / c2, the
+    noise draws — is the reference's own code, unmodified."""
+
+    def __init__(self, unet):
+        self.unet, self.self_cond = unet, unet.self_cond
+
+    def forward_with_cond_scale(self, x, t, *, image_embed=None, lowres_cond_img=None, **kw):
+        return self.unet.forward_with_cond_scale(x, t, video_embed=image_embed, lowres_cond_video=lowres_cond_img, **kw)
+
+
+DDIM_CASES = {
+    "eta0": (dict(ddim_sampling_eta=0.0), 1.0),
+    "eta07": (dict(ddim_sampling_eta=0.7), 1.0),
+    "v_dyn_cfg": (dict(ddim_sampling_eta=0.3, predict_v=True, use_dynamic_thres=True, dynamic_thres_percentile=0.9,
+                       video_cond_drop_prob=0.1), 2.0),
+}
+
+
+def ddim():
+    """`python -m oracle.make_golden ddim`: the reference's own DDIM loop (through _DdimKwargAdapter) on the tiny Unet3D,
+    100 training steps sampled in 12 — pins scope row N1, which until now rested on a restatement only."""
+    ref = reference.load()
+    with open(os.path.join(GOLDEN, "state_dict_layouts.json")) as f:
+        layouts = json.load(f)
+    out = {}
+    for name, (kw, cond_scale) in DDIM_CASES.items():
+        torch.manual_seed(0)
+        unet = ref.Unet3D(**CASES["tiny"]["unet"])
+        dec = ref.VideoDecoder(unet, frame_size=16, frame_numbers=(4,), timesteps=100, learned_variance=False, **kw)
+        dec.unets[0].load_state_dict(synth_state_dict(layouts["tiny"], seed=7), strict=True)
+        dec.eval()
+        emb = torch.randn(2, 512, generator=torch.Generator().manual_seed(21))
+        torch.manual_seed(999)
+        vid = dec.p_sample_loop_ddim(_DdimKwargAdapter(dec.unets[0]), (2, 3, 4, 16, 16), emb,
+                                     noise_scheduler=dec.noise_schedulers[0], timesteps=12, cond_scale=cond_scale,
+                                     predict_x_start=dec.predict_x_start[0], predict_v=dec.predict_v[0])
+        assert bool(torch.isfinite(vid).all())
+        out[name] = {"decoder_kwargs": kw, "cond_scale": cond_scale, "sample": vid}
+        print("ddim", name, float(vid.mean()), float(vid.std()))
+    torch.save({"cases": out, "video_embed_seed": 21, "sample_seed": 999, "weight_seed": 7, "timesteps": 100,
+                "sample_timesteps": 12, "shape": (2, 3, 4, 16, 16)}, os.path.join(GOLDEN, "sample_ddim.pt"))
+
+
 VIVIT_CASES = {
     # the reference's own encoder class on small shapes (same block structure as configs/celebv-text.yaml:31-36)
     "small": dict(kw=dict(frame_size=32, patch_size=8, num_frames=25, dim=64, depth=2, heads=3, in_channels=3), batch=2),
@@ -325,6 +371,8 @@ if __name__ == "__main__":
         vivit()
     elif len(sys.argv) > 1 and sys.argv[1] == "cascade":
         cascade()
+    elif len(sys.argv) > 1 and sys.argv[1] == "ddim":
+        ddim()
     elif len(sys.argv) > 1 and sys.argv[1] == "cascade_train":
         cascade_train()
     elif len(sys.argv) > 1 and sys.argv[1] == "objectives":

@@ -488,7 +488,8 @@ def p_sample_loop_ddim(sd, cfg, sched: NoiseScheduler, shape, *, video_embed, ti
                        dynamic_thres_percentile=None):
     """Arithmetic of the reference's p_sample_loop_ddim (dalle2_video.py:1757-1889) for epsilon prediction.  The reference
     method is unreachable as shipped (it passes image_embed= / lowres_cond_img= to a Unet3D that takes video_embed=,
-    SURVEY.md F5): PARITY UNPINNED against the reference, this restates its math with the keyword fixed.
+    SURVEY.md F5), so it is pinned through tests/golden/sample_ddim.pt: oracle/make_golden.py `ddim` ran the reference's own
+    loop behind an adapter that renames those two keywords and nothing else.
     RNG contract: randn(shape), then one randn per step except the last (:1870)."""
     alphas = sched.alphas_cumprod
     vid = torch.randn(shape, generator=generator)

@@ -402,3 +402,21 @@ def test_unconditional_decoder_samples_from_batch_size_alone(layouts):
                                  (2, 3, 4, 16, 16), video_embed=None, generator=torch.Generator().manual_seed(77))
     err = float((vid.cpu() - ref).abs().max())
     assert err < 2e-3, err
+
+
+@pytest.mark.parametrize("name", ["eta0", "eta07", "v_dyn_cfg"])
+@pytest.mark.parametrize("graph", [False, True])
+def test_ddim_sampling_matches_the_references_own_loop(name, graph, layouts):
+    """Row N1 against fixtures produced by the reference's p_sample_loop_ddim itself (see oracle/make_golden.py `ddim`)."""
+    g = golden("sample_ddim.pt")
+    case = g["cases"][name]
+    u = Unet3D(**TINY)
+    u.load_state_dict(synth_state_dict(layouts["tiny"], seed=g["weight_seed"]), strict=True)
+    d = VideoDecoder(u, frame_size=16, frame_numbers=(4,), timesteps=g["timesteps"], sample_timesteps=g["sample_timesteps"],
+                     learned_variance=False, **case["decoder_kwargs"]).cuda()
+    d.use_cuda_graph = graph
+    emb = torch.randn(2, 512, generator=torch.Generator().manual_seed(g["video_embed_seed"]))
+    vid = d.sample(video_embed=emb.cuda(), cond_scale=case["cond_scale"], noise_fn=cpu_noise(g["sample_seed"]))
+    assert d.last_launch_stats["graph"] == graph
+    err = float((vid.cpu() - case["sample"]).abs().max())
+    assert err < 2e-3, err

@@ -269,3 +269,24 @@ def test_cascade_stage2_training_loss_matches_reference_fixture(key, layouts):
                               lowres_cond_video=low * 2 - 1, lowres_noise_level=case["lowres_noise_level"])
     loss = float(F.mse_loss(pred, noise, reduction="none").flatten(1).mean(1).mean())
     assert abs(loss - case["loss"]) < 1e-5 * case["loss"], (loss, case["loss"])
+
+
+@pytest.mark.parametrize("name", ["eta0", "eta07", "v_dyn_cfg"])
+def test_ddim_loop_matches_the_references_own_loop(name, layouts):
+    """Scope row N1 pinned by the reference itself: oracle/make_golden.py `ddim` ran the reference's p_sample_loop_ddim
+    (:1757-1889) through an adapter that only renames the two keywords its Unet3D does not take."""
+    from oracle.unet3d import p_sample_loop_ddim
+    g = golden("sample_ddim.pt")
+    case = g["cases"][name]
+    kw = case["decoder_kwargs"]
+    cfg = UnetConfig(dim=32, video_embed_dim=512, dim_mults=(1, 2), cond_on_video_embeds=True)
+    sd = synth_state_dict(layouts["tiny"], seed=g["weight_seed"])
+    sched = P.NoiseScheduler(beta_schedule="cosine", timesteps=g["timesteps"], loss_type="l2")
+    emb = torch.randn(2, 512, generator=torch.Generator().manual_seed(g["video_embed_seed"]))
+    torch.manual_seed(g["sample_seed"])
+    with torch.no_grad():
+        vid = p_sample_loop_ddim(sd, cfg, sched, tuple(g["shape"]), video_embed=emb, timesteps=g["sample_timesteps"],
+                                 eta=kw["ddim_sampling_eta"], cond_scale=case["cond_scale"],
+                                 objective="v" if kw.get("predict_v") else "eps",
+                                 dynamic_thres_percentile=kw.get("dynamic_thres_percentile"))
+    assert float((vid - case["sample"]).abs().max()) < 1e-3
