@@ -211,3 +211,18 @@ def test_trainer_flat_buffers_are_per_unet_views():
         tr.validate_and_return_unet_number(3)
     single = VideoDecoderTrainer(VideoDecoder(Unet3D(**kw), frame_size=8, frame_numbers=(2,), timesteps=10, learned_variance=False))
     assert single.validate_and_return_unet_number(None) == 1
+
+
+def test_ddim_time_pairs_known_answers_and_edges():
+    """Host half of row N1 (dalle2_video.py:1796-1799): linspace(0, T, S + 2)[:-1] truncated to int, reversed, equal
+    neighbours dropped.  T=100 / S=12 is the spacing of tests/golden/sample_ddim.pt."""
+    from oracle.unet3d import ddim_time_pairs as oracle_pairs
+    pairs = VideoDecoder.ddim_time_pairs(100, 12)
+    assert pairs == [(92, 84), (84, 76), (76, 69), (69, 61), (61, 53), (53, 46), (46, 38), (38, 30), (30, 23), (23, 15),
+                     (15, 7), (7, 0)]
+    for T, S in ((1000, 50), (1000, 250), (1000, 999), (50, 50), (50, 7), (10, 1), (4, 9)):
+        pairs = VideoDecoder.ddim_time_pairs(T, S)
+        assert pairs == oracle_pairs(T, S)
+        assert 1 <= len(pairs) <= S and pairs[-1][1] == 0 and pairs[0][0] < T
+        assert all(a > b for a, b in pairs)                                   # S > T: repeated times are skipped
+        assert all(p[1] == q[0] for p, q in zip(pairs, pairs[1:]))            # a chain: every step starts where the last ended
