@@ -226,3 +226,15 @@ def test_ddim_time_pairs_known_answers_and_edges():
         assert 1 <= len(pairs) <= S and pairs[-1][1] == 0 and pairs[0][0] < T
         assert all(a > b for a, b in pairs)                                   # S > T: repeated times are skipped
         assert all(p[1] == q[0] for p, q in zip(pairs, pairs[1:]))            # a chain: every step starts where the last ended
+
+
+def test_integration_index_names_every_declared_entry_point():
+    """INTEGRATION.md §4 maps each C-ABI symbol to the reference lines it stands in for; a symbol added to the header
+    without a row there (or a row for a symbol that no longer exists) fails here."""
+    header = open(os.path.join(ROOT, "include", "dv_b200.h")).read()
+    declared = set(re.findall(r"^(?:int|int64_t|const char\*)\s+(dv_\w+)\s*\(", header, flags=re.M))
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    index = doc[doc.index("## 4. Entry-point index"):]
+    rows = [ln.split("|")[1] for ln in index.splitlines() if ln.startswith("| `dv_")]
+    indexed = set(re.findall(r"`(dv_\w+)`", " ".join(rows)))
+    assert indexed == declared, (sorted(declared - indexed), sorted(indexed - declared))
