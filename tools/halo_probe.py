@@ -1,7 +1,7 @@
 """Bring-up probe for the streaming-halo conv (run under `timeout` on the GPU box)."""
 import math, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
 import torch
 from gpu_util import conv, rel_err
 from test_gpu_kernels import HALO_CASES, rnd, dev
