@@ -65,13 +65,15 @@ def resize_video_to(video, target_frame_size, clamp_range=None):
     return out.to(video.dtype)
 
 
-class LowresVideoConditioner:
+class LowresVideoConditioner(nn.Module):
     """Reference: dalle2_video.py:1044-1166.  At sampling time only the per-frame nearest resize and the optional
     Imagen-style noise augmentation are used (:2126-2147); in training also the random Gaussian blur (:1135-1144).  All
-    three run as native kernels."""
+    three run as native kernels.  An nn.Module like the reference's, so that `decoder.state_dict()` carries the
+    `lowres_conds.N.noise_scheduler.*` buffers and the scheduler follows `decoder.to()`."""
 
     def __init__(self, downsample_first=True, use_blur=True, blur_prob=0.5, blur_sigma=0.6, blur_kernel_size=3,
                  use_noise=False, input_video_range=None, normalize_video=True):
+        super().__init__()
         self.downsample_first, self.input_video_range = downsample_first, input_video_range
         self.use_blur, self.blur_prob, self.blur_sigma, self.blur_kernel_size = use_blur, blur_prob, blur_sigma, \
             blur_kernel_size
@@ -124,8 +126,8 @@ class LowresVideoConditioner:
                                                         wy=arr, wx=arr), torch.cuda.current_stream(src.device).cuda_stream)
         return out.to(cond_fmap.dtype)
 
-    def __call__(self, cond_fmap, *, target_frame_size, downsample_frame_size=None, should_blur=True, blur_sigma=None,
-                 blur_kernel_size=None, **kwargs):
+    def forward(self, cond_fmap, *, target_frame_size, downsample_frame_size=None, should_blur=True, blur_sigma=None,
+                blur_kernel_size=None, **kwargs):
         if self.downsample_first and downsample_frame_size is not None:
             cond_fmap = resize_video_to(cond_fmap, downsample_frame_size, clamp_range=self.input_video_range)
         # blur is only applied 50% of the time (:1135-1144)
@@ -229,11 +231,11 @@ class VideoDecoder(nn.Module):
         assert lowres_conditions == (False, *((True,) * (num_unets - 1))), \
             "the first unet must be unconditioned (by low resolution image), and the rest of the unets must have " \
             "`lowres_cond` set to True"
-        self.lowres_conds = [None if i == 0 else LowresVideoConditioner(
+        self.lowres_conds = nn.ModuleList([None if i == 0 else LowresVideoConditioner(
             downsample_first=lowres_downsample_first, use_blur=ub, use_noise=un, blur_prob=blur_prob,
             blur_sigma=blur_sigma, blur_kernel_size=blur_kernel_size, input_video_range=self.input_video_range,
             normalize_video=auto_normalize_video)
-            for i, (un, ub) in enumerate(zip(use_noise_for_lowres_cond, use_blur_for_lowres_cond))]
+            for i, (un, ub) in enumerate(zip(use_noise_for_lowres_cond, use_blur_for_lowres_cond))])
         self.lowres_noise_sample_level = lowres_noise_sample_level
         self.random_crop_sizes = _pad_tuple(_cast_tuple(random_crop_sizes), len(self.unets), None)
         self.video_cond_drop_prob = video_cond_drop_prob

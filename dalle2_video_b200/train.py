@@ -88,6 +88,7 @@ class _TrainPlan:
         self.use_cuda_graph = True
         self._graphs = {}
         self.stats_slots = 0
+        self.generation = 0
         self._build()
 
     # -------------------------------------------------------------- buffers
@@ -718,6 +719,8 @@ class _PlanFunction(torch.autograd.Function):
         for kind, t in zip(plan.kv_kinds, kv):
             plan.kv[kind].copy_(t)
         plan.run_forward()
+        plan.generation += 1    # the plan owns ONE set of activation buffers: a backward must follow its own forward
+        ctx.generation = plan.generation
         loss = torch.zeros(1, dtype=torch.float64, device=plan.device)
         stream = torch.cuda.current_stream(plan.device).cuda_stream
         kind, weight = plan.loss_opts
@@ -732,6 +735,10 @@ class _PlanFunction(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_out):
         plan, noise = ctx.plan, ctx.noise
+        if ctx.generation != plan.generation:
+            raise L.DvError("backward through a stale training plan: another forward of the same shape ran since this "
+                            "loss was computed and overwrote the plan's activations — call backward() on each loss "
+                            "before the next forward (gradient accumulation: loss_i.backward() per micro-batch)")
         stream = torch.cuda.current_stream(plan.device).cuda_stream
         scratch = torch.zeros(1, dtype=torch.float64, device=plan.device)
         L.call("dv_mse_loss", L.MseLossParams(pred=plan.eps.data_ptr(), target=noise.data_ptr(), dpred=plan.deps.data_ptr(),
@@ -799,31 +806,58 @@ def p_losses(decoder, unet: Unet3D, x_start, times, *, video_embed, noise_schedu
 class _UnetOptState:
     """Flat fp32 parameter / gradient / Adam-moment buffers of ONE unet (param.data and param.grad become views)."""
 
+    # parameters no training path reaches (text conditioning has no backward here and raises): torch.optim.AdamW skips
+    # parameters whose .grad is None — no weight decay, no moments — so they sit outside the stepped ranges
+    NEVER_GRAD = ("null_text_embed", "text_to_cond.")
+
     def __init__(self, unet, wd, group_wd_params):
-        params = [p for p in unet.parameters() if p.requires_grad]
-        decay = [p for p in params if p.ndim >= 2 or not group_wd_params]
-        no_decay = [p for p in params if not (p.ndim >= 2 or not group_wd_params)]
+        named = [(n, p) for n, p in unet.named_parameters() if p.requires_grad]
+        dead = {id(p) for n, p in named if n.startswith(self.NEVER_GRAD)}
+        params = [p for _, p in named]
+        is_decay = lambda p: p.ndim >= 2 or not group_wd_params  # noqa: E731
+        decay = [p for p in params if is_decay(p) and id(p) not in dead]
+        decay_dead = [p for p in params if is_decay(p) and id(p) in dead]
+        no_decay = [p for p in params if not is_decay(p) and id(p) not in dead]
+        no_decay_dead = [p for p in params if not is_decay(p) and id(p) in dead]
         dev = params[0].device
-        ordered = decay + no_decay
+        ordered = decay + decay_dead + no_decay + no_decay_dead
         n = sum(p.numel() for p in ordered)
         self.flat_p = torch.empty(n, device=dev)
         self.flat_g = torch.zeros(n, device=dev)
         self.exp_avg = torch.zeros(n, device=dev)
         self.exp_avg_sq = torch.zeros(n, device=dev)
         off = 0
+        self.offsets = []
         with torch.no_grad():
             for p in ordered:
                 k = p.numel()
                 self.flat_p[off:off + k].copy_(p.detach().reshape(-1))
                 p.data = self.flat_p[off:off + k].view(p.shape)
                 p.grad = self.flat_g[off:off + k].view(p.shape)
+                self.offsets.append(off)
                 off += k
-        nd = sum(p.numel() for p in decay)
-        self.groups = [(0, nd, wd), (nd, n - nd, 0.0)]
+        numel = lambda ps: sum(p.numel() for p in ps)  # noqa: E731
+        nd, ndd, nn_ = numel(decay), numel(decay_dead), numel(no_decay)
+        self.groups = [(0, nd, wd), (nd + ndd, nn_, 0.0)]
         self.sumsq = torch.zeros(1, dtype=torch.float64, device=dev)
         self.params = ordered
         self.buckets, self.bucket_plan = None, None
         unet._engines.clear()  # every plan (and captured graph) built before the parameters moved into the flat buffer is stale
+
+    def rebind_grads(self):
+        """param.grad must stay a view of flat_g (the all-reduce and dv_adamw read the flat buffer).  A
+        `zero_grad(set_to_none=True)` (torch's default) or an assignment detaches it: re-attach, keeping the meaning —
+        a None gradient reads as zero, a foreign tensor is copied in."""
+        for p, off in zip(self.params, self.offsets):
+            view = self.flat_g[off:off + p.numel()].view(p.shape)
+            g = p.grad
+            if g is None:
+                view.zero_()
+            elif g.data_ptr() != view.data_ptr() or g.shape != view.shape:
+                view.copy_(g)
+            else:
+                continue
+            p.grad = view
 
 
 class VideoDecoderTrainer(nn.Module):
@@ -834,14 +868,33 @@ class VideoDecoderTrainer(nn.Module):
     per unet, as the reference keeps optim{i} / steps[i] (:60-110, :240-274).  get_optimizer semantics:
     AdamW, betas (0.9, 0.99), parameters with ndim < 2 excluded from weight decay when group_wd_params."""
 
-    def __init__(self, decoder, lr=1e-4, wd=1e-2, eps=1e-8, max_grad_norm=0.5, group_wd_params=True, betas=(0.9, 0.99),
-                 overlap_allreduce=False, bucket_bytes=32 << 20, **_):
+    def __init__(self, decoder, accelerator=None, dataloaders=None, use_ema=False, lr=1e-4, wd=1e-2, eps=1e-8,
+                 warmup_steps=None, cosine_decay_max_steps=None, max_grad_norm=0.5, amp=False, group_wd_params=True,
+                 betas=(0.9, 0.99), overlap_allreduce=False, bucket_bytes=32 << 20, **kwargs):
         super().__init__()
+        import warnings
+        # Reference keywords (trainer.py:10-25).  What is outside the accelerated path is rejected or named, never
+        # silently dropped: EMA copies (ema_pytorch), accelerate objects and dataloaders belong to the trainer plumbing
+        # SURVEY.md section 2 keeps out of scope; `amp` is moot (the native step always computes in bf16 with fp32
+        # master weights and statistics).
+        if use_ema:
+            raise NotImplementedError("VideoDecoderTrainer(b200): use_ema=True is not supported (EMA weight copies are "
+                                      "outside the accelerated training step; the shipped config sets use_ema: False, "
+                                      "/root/reference/configs/celebv-text.yaml:73) — pass use_ema=False")
+        ignored = [k for k, v in dict(accelerator=accelerator, dataloaders=dataloaders, **kwargs).items() if v is not None]
+        if ignored:
+            warnings.warn(f"VideoDecoderTrainer(b200): keyword(s) {ignored} have no effect here (no accelerate / "
+                          "dataloader / EMA plumbing behind the native training step)", stacklevel=2)
+        self.use_ema, self.amp = False, amp
         self.decoder = decoder
         self.num_unets = len(decoder.unets)
         self.lr, self.wd, self.eps, self.betas = lr, wd, eps, betas
+        # LinearWarmup dampening and CosineAnnealingLR (trainer.py:78-90, :262-268) as a host-side factor on lr
+        self.warmup_steps, self.cosine_decay_max_steps = warmup_steps, cosine_decay_max_steps
         self.max_grad_norm = max_grad_norm
-        self._opt = [_UnetOptState(u, wd, group_wd_params) for u in decoder.unets]
+        per_unet = lambda v, i: (v[i] if isinstance(v, (tuple, list)) else v)  # noqa: E731
+        self._opt = [_UnetOptState(u, per_unet(wd, i), group_wd_params) for i, u in enumerate(decoder.unets)]
+        self.sync_replicas()
         self.register_buffer("steps", torch.tensor([0] * self.num_unets))
         self.overlap_allreduce, self.bucket_bytes, self.min_bucket_bytes = overlap_allreduce, bucket_bytes, 4 << 20
         self._overlap_live, self._live_state = False, None
@@ -881,8 +934,33 @@ class VideoDecoderTrainer(nn.Module):
         if self._overlap_live and self._live_state is not None:
             self._live_state.buckets.launch(i)
 
-    def forward(self, video, video_embed, unet_number=None, **kwargs):
-        """loss + backward + gradient averaging.  Data parallel: ONE all-reduce of the flat gradient buffer after the
+    def sync_replicas(self):
+        """Data parallel: every rank starts from rank 0's weights (what accelerate.prepare / DDP's constructor broadcast
+        gives the reference, trainer.py:117-124).  Without it ranks built under different RNG states would average
+        gradients of different models.  The noise-schedule buffers are deterministic and need no broadcast."""
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+            return
+        for st in self._opt:
+            dist.broadcast(st.flat_p, src=0)
+
+    def current_lr(self, unet_number=None):
+        """lr x LinearWarmup dampening x CosineAnnealingLR factor for the NEXT optimiser step of that unet."""
+        unet_number = self.validate_and_return_unet_number(unet_number)
+        step = int(self.steps[unet_number - 1])   # optimiser steps already taken
+        pick = lambda v: (v[unet_number - 1] if isinstance(v, (tuple, list)) else v)  # noqa: E731
+        lr, warm, tmax = pick(self.lr), pick(self.warmup_steps), pick(self.cosine_decay_max_steps)
+        if tmax is not None:
+            lr = lr * (1 + math.cos(math.pi * step / tmax)) / 2
+        if warm is not None:
+            lr = lr * min(1.0, (step + 1) / warm)
+        return lr
+
+    def forward(self, video, video_embed, unet_number=None, max_batch_size=None, **kwargs):
+        """loss + backward + gradient averaging.  Like the reference (trainer.py:322-365): the batch is processed in
+        chunks of `max_batch_size` (loss scaled by the chunk's share, gradients accumulating), and the backward and the
+        all-reduce only run in training mode with gradients enabled — an eval() / no_grad() pass returns the loss
+        and leaves the gradient buffer untouched.  Data parallel: ONE all-reduce of the flat gradient buffer after the
         backward (default), or with overlap_allreduce=True in buckets that start as soon as the backward segment
         producing them has run (parallel.GradBuckets; the first two steps — eager warm-up, graph capture — still reduce
         after the backward).  The default is the measured winner: the backward's conv kernels are persistent with one
@@ -890,21 +968,37 @@ class VideoDecoderTrainer(nn.Module):
         per step at 2 GPUs, 25.6 vs 24.3 ms at 8 (profiles/r01_train_{2,8}gpu_overlap_ab.json)."""
         unet_number = self.validate_and_return_unet_number(unet_number)
         st, unet = self._opt[unet_number - 1], self.decoder.unets[unet_number - 1]
-        loss = self.decoder(video, video_embed=video_embed, unet_number=unet_number, **kwargs)
         import torch.distributed as dist
         data_parallel = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
-        plan = getattr(unet, "_train_plan_last", None)
-        if data_parallel and self.overlap_allreduce and plan is not None:
-            self._overlap_setup(st, plan)
-            self._overlap_live, self._live_state = plan.graphs_ready(), st
-            loss.backward()
-            st.buckets.finish()
-            self._overlap_live = False
-        else:
-            self._overlap_live = False
-            loss.backward()
-            allreduce_mean_(st.flat_g)
-        return loss.item()
+        backprop = self.training and torch.is_grad_enabled()
+        if backprop:
+            st.rebind_grads()
+        n = video.shape[0]
+        size = n if max_batch_size is None else max(1, min(int(max_batch_size), n))
+        bounds = [(lo, min(lo + size, n)) for lo in range(0, n, size)]
+        chunked = lambda v, lo, hi: v[lo:hi] if torch.is_tensor(v) and v.ndim > 0 and v.shape[0] == n else v  # noqa: E731
+        total = 0.0
+        for ci, (lo, hi) in enumerate(bounds):
+            last = ci == len(bounds) - 1
+            ckw = {k: chunked(v, lo, hi) for k, v in kwargs.items()}
+            loss = self.decoder(video[lo:hi], video_embed=chunked(video_embed, lo, hi), unet_number=unet_number, **ckw)
+            loss = loss * ((hi - lo) / n)
+            total += loss.item()
+            if not backprop:
+                continue
+            plan = getattr(unet, "_train_plan_last", None)
+            if data_parallel and self.overlap_allreduce and plan is not None and last and len(bounds) == 1:
+                self._overlap_setup(st, plan)
+                self._overlap_live, self._live_state = plan.graphs_ready(), st
+                loss.backward()
+                st.buckets.finish()
+                self._overlap_live = False
+            else:
+                self._overlap_live = False
+                loss.backward()
+                if last:
+                    allreduce_mean_(st.flat_g)
+        return total
 
     @torch.no_grad()
     def update(self, unet_number=None):
@@ -918,13 +1012,15 @@ class VideoDecoderTrainer(nn.Module):
         if use_clip:
             L.call("dv_sumsq", L.SumsqParams(x=st.flat_g.data_ptr(), out=st.sumsq.data_ptr(), n=st.flat_g.numel()), stream)
         b1, b2 = self.betas
+        lr = self.current_lr(unet_number)
+        pick = lambda v: (v[unet_number - 1] if isinstance(v, (tuple, list)) else v)  # noqa: E731
         for off, n, wd in st.groups:
             if n == 0:
                 continue
             L.call("dv_adamw", L.AdamwParams(
                 param=st.flat_p.data_ptr() + off * 4, grad=st.flat_g.data_ptr() + off * 4,
                 exp_avg=st.exp_avg.data_ptr() + off * 4, exp_avg_sq=st.exp_avg_sq.data_ptr() + off * 4,
-                grad_sumsq=st.sumsq.data_ptr() if use_clip else None, n=n, lr=self.lr, beta1=b1, beta2=b2, eps=self.eps,
+                grad_sumsq=st.sumsq.data_ptr() if use_clip else None, n=n, lr=lr, beta1=b1, beta2=b2, eps=pick(self.eps),
                 weight_decay=wd, bias_correction1=1 - b1 ** step, bias_correction2=1 - b2 ** step,
                 max_grad_norm=float(self.max_grad_norm or 0.0)), stream)
         st.flat_g.zero_()

@@ -369,8 +369,14 @@ class Unet3D(nn.Module):
         from .train import _TrainPlan
         key = ("train", batch, frames, height, width, str(device))
         pl = self._engines.get(key)
+        # the plan's captured graphs bake in the parameters' storage pointers: unet.to(...) / .float() / a re-flattening
+        # optimiser moves them, and a stale plan would read freed memory
+        sig = tuple(p.data_ptr() for p in self.parameters())
+        if pl is not None and pl.param_signature != sig:
+            pl = None
         if pl is None:
             pl = _TrainPlan(self, batch, frames, height, width, device)
+            pl.param_signature = sig
             self._engines[key] = pl
         self._train_plan_last = pl
         return pl

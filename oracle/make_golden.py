@@ -363,6 +363,21 @@ def vivit_fixture_inputs(g):
     gen = torch.Generator().manual_seed(g["input_seed"])
     x = torch.randn(g["batch"], kw["num_frames"], 3, kw["frame_size"], kw["frame_size"], generator=gen)
     return sd, x
+def decoder_layout():
+    """`python -m oracle.make_golden decoder_layout`: key -> shape of the reference's own two-unet
+    `VideoDecoder.state_dict()` (with and without the noise augmentation of the conditioning video, whose conditioner
+    owns a NoiseScheduler: `lowres_conds.1.noise_scheduler.*`), so a reference decoder checkpoint loads strict=True."""
+    ref = reference.load()
+    out = {}
+    for use_noise in (False, True):
+        torch.manual_seed(0)
+        u1, u2 = ref.Unet3D(**CASCADE_U1), ref.Unet3D(**CASCADE_U2)
+        dec = ref.VideoDecoder((u1, u2), frame_sizes=(16, 32), frame_numbers=(4, 4), timesteps=50,
+                               learned_variance=False, use_noise_for_lowres_cond=use_noise)
+        out["noise" if use_noise else "plain"] = shapes_of(dec)
+    with open(os.path.join(GOLDEN, "decoder_state_dict_layouts.json"), "w") as f:
+        json.dump(out, f, indent=0, sort_keys=True)
+    print({k: len(v) for k, v in out.items()})
 
 
 if __name__ == "__main__":
@@ -377,5 +392,7 @@ if __name__ == "__main__":
         cascade_train()
     elif len(sys.argv) > 1 and sys.argv[1] == "objectives":
         objectives()
+    elif len(sys.argv) > 1 and sys.argv[1] == "decoder_layout":
+        decoder_layout()
     else:
         main()

@@ -1,0 +1,89 @@
+"""-m gpu, needs >= 2 GPUs (skipped otherwise; run with `gpurun --gpus 2`): the one collective of the path — the NCCL
+all-reduce of the flat gradient in the data-parallel training config (reference: accelerate-DDP,
+/root/reference/dalle2_video/trainer.py:117-124, :360) — gives the 1-GPU step on the concatenated batch."""
+import os
+
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+from conftest import ROOT
+
+pytestmark = pytest.mark.gpu
+
+KW = dict(dim=32, video_embed_dim=512, dim_mults=(1, 2), cond_on_video_embeds=True)
+SHAPE = (4, 3, 4, 16, 16)
+
+
+def _inputs():
+    g = torch.Generator().manual_seed(3)
+    video, noise = torch.rand(SHAPE, generator=g), torch.randn(SHAPE, generator=g)
+    emb, times = torch.randn(SHAPE[0], 512, generator=g), torch.tensor([7, 63, 21, 90])
+    return video, noise, emb, times
+
+
+def _flat_grad_after_step(dev, rows, seed, world_seed_offset=0):
+    """p_losses on `rows` of the fixed batch + backward + gradient averaging + one AdamW update; returns (grad, params)."""
+    import json
+    from dalle2_video_b200 import Unet3D, VideoDecoder, VideoDecoderTrainer
+    from dalle2_video_b200.parallel import allreduce_mean_
+    from dalle2_video_b200.train import p_losses
+    from oracle.weights import synth_state_dict
+    torch.manual_seed(seed + world_seed_offset)          # ranks construct under different RNG states on purpose
+    u = Unet3D(**KW)
+    if world_seed_offset == 0:
+        lay = json.load(open(os.path.join(ROOT, "tests", "golden", "state_dict_layouts.json")))["tiny"]
+        u.load_state_dict(synth_state_dict(lay, seed=5), strict=True)
+    dec = VideoDecoder(u, frame_size=SHAPE[3], frame_numbers=(SHAPE[2],), timesteps=100, learned_variance=False,
+                       video_cond_drop_prob=0.0, text_cond_drop_prob=0.0).to(dev)
+    trainer = VideoDecoderTrainer(dec, lr=3e-4, wd=1e-2, max_grad_norm=0.5)   # broadcasts rank 0's weights
+    video, noise, emb, times = (t[rows].to(dev) for t in _inputs())
+    loss = p_losses(dec, dec.unets[0], video, times, video_embed=emb, noise_scheduler=dec.noise_schedulers[0], noise=noise)
+    loss.backward()
+    allreduce_mean_(trainer.flat_g)
+    grad = trainer.flat_g.clone()
+    trainer.update()
+    return float(loss), grad, trainer.flat_p.clone()
+
+
+def _worker(rank, world, port, q):
+    import sys
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    per = SHAPE[0] // world
+    loss, grad, params = _flat_grad_after_step(dev, slice(rank * per, (rank + 1) * per), seed=0, world_seed_offset=rank)
+    losses = [None] * world
+    dist.all_gather_object(losses, loss)
+    if rank == 0:
+        q.put((losses, grad.cpu(), params.cpu()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_two_rank_nccl_step_equals_one_gpu_step_on_the_concatenated_batch():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 37500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    losses, grad2, params2 = q.get(timeout=600)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    loss1, grad1, params1 = _flat_grad_after_step(torch.device("cuda", 0), slice(0, SHAPE[0]), seed=0)
+    grad1, params1 = grad1.cpu(), params1.cpu()
+    # equal shards: mean of the shard losses / gradients = full-batch loss / gradient.  Every op is per-sample, so the
+    # only differences are fp32 summation orders (atomics in the weight-gradient and norm reductions)
+    assert abs(sum(losses) / 2 - loss1) < 1e-4 * abs(loss1), (losses, loss1)
+    rel = float((grad2 - grad1).norm() / grad1.norm())
+    assert rel < 2e-3, rel
+    # rank 1 was constructed under another seed: after the constructor's broadcast and the averaged step both replicas
+    # hold the 1-GPU result
+    assert float((params2 - params1).abs().max()) < 1e-5 + 2 * 3e-4, float((params2 - params1).abs().max())
+    assert float((params2 - params1).norm() / params1.norm()) < 1e-4

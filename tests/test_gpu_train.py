@@ -481,3 +481,53 @@ def test_training_with_scaled_skip_connections_matches_oracle_autograd(layouts):
         if rg.numel() >= 256 and float(rg.norm()) > 1e-6:
             assert float(F.cosine_similarity(gg.flatten(), rg.flatten(), dim=0)) >= 0.98, k
     assert (num / den) ** 0.5 < 8e-2, (num / den) ** 0.5
+
+
+def test_eval_and_no_grad_forward_leave_the_gradient_buffer_untouched_and_chunks_run():
+    """trainer.py:322-365: the backward runs only `if self.training`; `max_batch_size` splits the batch, each chunk's
+    loss scaled by its share.  A validation pass must not leak gradients into the next update()."""
+    kw, shape = CASES["tiny"]
+    dec, _ = build(kw, shape[2], shape[3])
+    trainer = VideoDecoderTrainer(dec, lr=3e-4)
+    g = torch.Generator().manual_seed(9)
+    video = torch.rand((4, *shape[1:]), generator=g).cuda()
+    emb = torch.randn(4, 512, generator=g).cuda()
+    trainer.eval()
+    l_eval = trainer(video, video_embed=emb)
+    assert l_eval > 0 and float(trainer.flat_g.abs().max()) == 0.0
+    trainer.train()
+    with torch.no_grad():
+        trainer(video, video_embed=emb)
+    assert float(trainer.flat_g.abs().max()) == 0.0
+    before = trainer.flat_p.clone()
+    trainer.update()                                   # all-zero gradient: Adam moves nothing but the decayed weights
+    assert float((trainer.flat_p - before).abs().max()) < 1e-5
+    dec.zero_grad()                                    # set_to_none=True detaches .grad from the flat buffer
+    l_chunk = trainer(video, video_embed=emb, max_batch_size=3)   # chunks of 3 + 1: two plans, gradients accumulate
+    assert l_chunk > 0 and float(trainer.flat_g.abs().max()) > 0
+    w = dec.unets[0].to_time_cond[0].weight
+    base = trainer.flat_g.data_ptr()
+    assert base <= w.grad.data_ptr() < base + trainer.flat_g.numel() * 4
+    trainer.update()
+    assert float((trainer.flat_p - before).abs().max()) > 1e-5
+
+
+def test_backward_through_a_plan_whose_buffers_were_overwritten_raises():
+    """One plan per shape owns one set of activations: (l1 + l2).backward() over two forwards of the same shape would
+    back-propagate l1 through l2's activations — it must fail loudly instead."""
+    from dalle2_video_b200 import _lib as L
+    kw, shape = CASES["tiny"]
+    dec, _ = build(kw, shape[2], shape[3])
+    g = torch.Generator().manual_seed(1)
+    video, emb = torch.rand(shape, generator=g).cuda(), torch.randn(shape[0], 512, generator=g).cuda()
+    l1 = dec(video, video_embed=emb)
+    l2 = dec(video, video_embed=emb)
+    with pytest.raises(L.DvError):
+        l1.backward()
+    l2.backward()                                      # the most recent forward is still valid
+    # moving the parameters (a new optimiser flattening, .to(), .float()) rebuilds the plan instead of replaying graphs
+    unet = dec.unets[0]
+    plan_a = unet.train_plan(shape[0], shape[2], shape[3], shape[4], video.device)
+    VideoDecoderTrainer(dec)
+    plan_b = unet.train_plan(shape[0], shape[2], shape[3], shape[4], video.device)
+    assert plan_a is not plan_b

@@ -29,6 +29,24 @@ def test_state_dict_layout_matches_reference(name, layouts):
     assert {k: list(v.shape) for k, v in sd.items()} == layouts[name]
 
 
+@pytest.mark.parametrize("use_noise", [False, True])
+def test_decoder_state_dict_layout_matches_reference(use_noise):
+    """A reference two-unet decoder checkpoint loads strict=True: the conditioner of a super-resolution unet is a module
+    whose NoiseScheduler buffers appear as `lowres_conds.1.noise_scheduler.*` (dalle2_video.py:1438-1459).  Fixture:
+    `python -m oracle.make_golden decoder_layout` (the reference's own VideoDecoder.state_dict())."""
+    import json
+    u1 = dict(dim=32, video_embed_dim=512, dim_mults=(1, 2), cond_on_video_embeds=True)
+    u2 = dict(dim=16, video_embed_dim=512, dim_mults=(1, 2), cond_on_video_embeds=True)
+    dec = VideoDecoder((Unet3D(**u1), Unet3D(**u2)), frame_sizes=(16, 32), frame_numbers=(4, 4), timesteps=50,
+                       learned_variance=False, use_noise_for_lowres_cond=use_noise)
+    ref = json.load(open(os.path.join(ROOT, "tests", "golden", "decoder_state_dict_layouts.json")))
+    ref = ref["noise" if use_noise else "plain"]
+    sd = dec.state_dict()
+    assert {k: list(v.shape) for k, v in sd.items()} == ref
+    assert any(k.startswith("lowres_conds.1.noise_scheduler.") for k in sd) == use_noise
+    dec.load_state_dict({k: torch.zeros(v) for k, v in ref.items()}, strict=True)
+
+
 @pytest.mark.skipif(not reference.available(), reason="/root/reference not mounted")
 def test_same_seed_gives_reference_init():
     ref = reference.load()
@@ -198,7 +216,10 @@ def test_trainer_flat_buffers_are_per_unet_views():
         glo = st.flat_g.data_ptr()
         assert all(glo <= p.grad.data_ptr() < glo + 4 * n for p in unet.parameters())
         (o0, n0, wd0), (o1, n1, wd1) = st.groups
-        assert o0 == 0 and o1 == n0 and n0 + n1 == n and wd0 > 0 and wd1 == 0.0
+        # the stepped ranges leave out null_text_embed (never reached by a training path; torch's AdamW skips
+        # parameters without a gradient): max_text_len x cond_dim values in the decayed group
+        dead = unet.null_text_embed.numel()
+        assert o0 == 0 and o1 == n0 + dead and n0 + n1 == n - dead and wd0 > 0 and wd1 == 0.0
         assert n1 == sum(p.numel() for p in unet.parameters() if p.ndim < 2)
         w = next(p for p in unet.parameters() if p.ndim >= 2)
         st.flat_p.zero_()
