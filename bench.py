@@ -84,40 +84,68 @@ def build_model(device, dtype, seed=0):
 
 
 # ---------------------------------------------------------------------------------------------- CPU arm
-def cpu_reference_step_time(n_steps, warmup, threads=None):
-    """The reference's algorithm for this path on the host cores: the oracle restatement (oracle/unet3d.py; the
-    reference itself cannot travel to the GPU box) — one denoise step = Unet3D forward + posterior update, B=1."""
-    import torch
-    from oracle.primitives import NoiseScheduler
-    from oracle.unet3d import UnetConfig, ddpm_posterior_step, unet3d_forward
+def _synth_weights():
     from oracle.weights import synth_state_dict
     from dalle2_video_b200 import Unet3D
+    shapes = {k: list(v.shape) for k, v in Unet3D(**UNET_KW).state_dict().items()}
+    return synth_state_dict(shapes, seed=0)
+
+
+def cpu_reference_step_time(n_steps, warmup, threads=None):
+    """The reference's CPU implementation of the path on the host cores, one denoise step at B=1 in fp32 with all host
+    threads: `VideoDecoder.p_sample` of the UNMODIFIED reference package when it is present (baseline/_ref, installed
+    from /root/reference — its Unet3D / VideoDecoder code over oracle/primitives.py's restatement of the un-installable
+    dalle2-pytorch symbols; kind "reference"), else the oracle restatement of the same step (oracle/unet3d.py; kind
+    "port").  Returns (seconds per step, threads, kind, description)."""
+    import torch
+    from oracle import reference
     threads = threads or os.cpu_count() or 1
     torch.set_num_threads(threads)
-    shapes = {k: list(v.shape) for k, v in Unet3D(**UNET_KW).state_dict().items()}
-    sd = synth_state_dict(shapes, seed=0)
-    cfg = UnetConfig(**UNET_KW)
-    sched = NoiseScheduler(beta_schedule="cosine", timesteps=TIMESTEPS, loss_type="l2")
+    sd = _synth_weights()
     g = torch.Generator().manual_seed(0)
     x = torch.randn(1, 3, FRAMES, SIZE, SIZE, generator=g)
     emb = torch.randn(1, 512, generator=g)
     times = []
-    with torch.no_grad():
-        for i in range(warmup + n_steps):
-            t = TIMESTEPS - 1 - i
-            t0 = time.perf_counter()
-            eps = unet3d_forward(sd, cfg, x, torch.tensor([t]), video_embed=emb)
-            x, _ = ddpm_posterior_step(sched, x, t, eps, torch.randn(x.shape, generator=g))
-            if i >= warmup:
-                times.append(time.perf_counter() - t0)
-    return sum(times) / len(times), threads
+    if reference.available():
+        ref = reference.load()
+        dec = ref.VideoDecoder(ref.Unet3D(**UNET_KW), frame_size=SIZE, frame_numbers=(FRAMES,), timesteps=TIMESTEPS,
+                               learned_variance=False)
+        dec.unets[0].load_state_dict(sd, strict=True)   # after construction: VideoDecoder re-instantiates its unets (F4)
+        dec.eval()
+        unet, sched = dec.unets[0], dec.noise_schedulers[0]
+        torch.manual_seed(0)
+        with torch.no_grad():
+            for i in range(warmup + n_steps):
+                t = torch.full((1,), TIMESTEPS - 1 - i, dtype=torch.long)
+                t0 = time.perf_counter()
+                x, _ = dec.p_sample(unet, x, t, video_embed=emb, noise_scheduler=sched)
+                if i >= warmup:
+                    times.append(time.perf_counter() - t0)
+        kind = "reference"
+        what = (f"the reference's own VideoDecoder.p_sample (unmodified package from {reference.REFERENCE_ROOT}, "
+                "dalle2-pytorch symbols restated in oracle/primitives.py)")
+    else:
+        from oracle.primitives import NoiseScheduler
+        from oracle.unet3d import UnetConfig, ddpm_posterior_step, unet3d_forward
+        cfg = UnetConfig(**UNET_KW)
+        sched = NoiseScheduler(beta_schedule="cosine", timesteps=TIMESTEPS, loss_type="l2")
+        with torch.no_grad():
+            for i in range(warmup + n_steps):
+                t = TIMESTEPS - 1 - i
+                t0 = time.perf_counter()
+                eps = unet3d_forward(sd, cfg, x, torch.tensor([t]), video_embed=emb)
+                x, _ = ddpm_posterior_step(sched, x, t, eps, torch.randn(x.shape, generator=g))
+                if i >= warmup:
+                    times.append(time.perf_counter() - t0)
+        kind, what = "port", "oracle restatement of the reference Unet3D + DDPM update (oracle/unet3d.py)"
+    return sum(times) / len(times), threads, kind, what
 
 
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    sec, threads = cpu_reference_step_time(args.steps, args.warmup)
+    sec, threads, kind, what = cpu_reference_step_time(args.steps, args.warmup)
     val = 1.0 / sec
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
@@ -125,9 +153,9 @@ def run_reference_arm(args):
             "config": {"workload": "config2: Unet3D dim64 mults(1,2,4,8) 3x16x64x64, 1000-step cosine DDPM, one p_sample step",
                        "batch_per_step": 1},
             "frames_per_sec": val * FRAMES,
-            "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
-                             "sample": f"{args.steps} denoise steps at batch 1 after {args.warmup} warm-up, oracle restatement "
-                                       "of the reference Unet3D + DDPM update, fp32, torch CPU"},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": kind,
+                             "sample": f"{args.steps} denoise steps at batch 1 after {args.warmup} warm-up: {what}, fp32, "
+                                       "torch CPU, all host threads"},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -173,6 +201,119 @@ def profile_conv_family(eng, iters=3):
             total += sum(a.elapsed_time(b) for a, b, _ in evs) * 1e-3
             dom_sec += sum(a.elapsed_time(b) for a, b, d in evs if d) * 1e-3
     return flops, total / iters, len(convs), tc, dom_sec / iters / max(dom_n, 1), dom_flops, dom_n
+
+
+def gpu_eager_baseline(dev, B, steps=3):
+    """"the real kernel to beat" — the reference formulation as plain torch eager ops on the SAME
+    GPU (the oracle restatement moved to cuda: every conv / GroupNorm / attention is a cuDNN / cuBLAS / ATen kernel),
+    bf16 autocast, the bench's batch.  A reported baseline leg like cpu_baseline: measurement only, after the timed
+    regions of the product path, never part of them."""
+    import torch
+    from oracle.primitives import NoiseScheduler
+    from oracle.unet3d import UnetConfig, ddpm_posterior_step, unet3d_forward
+    sd = {k: v.to(dev) for k, v in _synth_weights().items()}
+    cfg = UnetConfig(**UNET_KW)
+    sched = NoiseScheduler(beta_schedule="cosine", timesteps=TIMESTEPS, loss_type="l2").to(dev)
+    while B >= 1:
+        try:
+            x = torch.randn(B, 3, FRAMES, SIZE, SIZE, device=dev)
+            emb = torch.randn(B, 512, device=dev)
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+            with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+                for i in range(1 + steps):
+                    if i == 1:
+                        torch.cuda.synchronize()
+                        ev[0].record()
+                    t = TIMESTEPS - 1 - i
+                    eps = unet3d_forward(sd, cfg, x, torch.full((B,), t, device=dev), video_embed=emb)
+                    x, _ = ddpm_posterior_step(sched, x, t, eps.float(), torch.randn_like(x))
+                ev[1].record()
+            torch.cuda.synchronize()
+            sec = ev[0].elapsed_time(ev[1]) * 1e-3 / steps
+            return {"value": B / sec, "unit": UNIT, "ms_per_step": sec * 1e3, "batch": B, "steps": steps,
+                    "dtype": "bf16 autocast", "kind": "torch eager (cuDNN / cuBLAS / ATen) on the same GPU, oracle "
+                    "restatement of the reference Unet3D + DDPM update"}
+        except torch.OutOfMemoryError:
+            torch.cuda.empty_cache()
+            B //= 2
+    return None
+
+
+def train_block(dev, world, rank, B, steps, warmup):
+    """BASELINE.json configs[3] / SURVEY.md row a16 + section 8e: the decoder training step (q_sample, Unet3D forward,
+    loss, native backward, NCCL all-reduce of the flat fp32 gradient — the ONE collective of the path — clip 0.5 + AdamW),
+    bf16 activations, synthetic 16x64x64 videos, B per GPU, data-parallel over the ranks.  Timed like the headline
+    (events, barrier + synchronize on both sides, max over ranks).  The exposed all-reduce time is the difference to the
+    same steps with the collective skipped."""
+    import torch
+    import torch.distributed as dist
+    from dalle2_video_b200 import Unet3D, VideoDecoder, VideoDecoderTrainer
+    from dalle2_video_b200 import _lib as L
+    from dalle2_video_b200 import train as T
+    torch.manual_seed(1 + rank)                       # replicas are synchronised by the trainer, not by the seed
+    unet = Unet3D(**UNET_KW)
+    torch.nn.init.normal_(unet.to_out.weight, std=0.02)
+    dec = VideoDecoder(unet, frame_size=SIZE, frame_numbers=(FRAMES,), timesteps=TIMESTEPS, learned_variance=False).to(dev)
+    trainer = VideoDecoderTrainer(dec, lr=3e-4, wd=1e-2, max_grad_norm=0.5)
+    g = torch.Generator(device=dev).manual_seed(4321 + rank)
+    video = torch.rand(B, 3, FRAMES, SIZE, SIZE, device=dev, generator=g)
+    emb = torch.randn(B, 512, device=dev, generator=g)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(n):
+        barrier()
+        c0 = L.launch_count
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            losses.append(trainer(video, video_embed=emb))
+            trainer.update()
+        e1.record()
+        barrier()
+        sec = e0.elapsed_time(e1) * 1e-3
+        if world > 1:
+            t = torch.tensor([sec], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            sec = float(t[0])
+        return sec, L.launch_count - c0
+
+    losses = []
+    for _ in range(max(warmup, 3)):                   # eager, graph capture, first replay
+        losses.append(trainer(video, video_embed=emb))
+        trainer.update()
+    sec, launches = timed(steps)
+    exposed = None
+    if world > 1:
+        real = T.allreduce_mean_
+        T.allreduce_mean_ = lambda flat: flat         # same steps without the collective
+        try:
+            sec_local, _ = timed(steps)
+        finally:
+            T.allreduce_mean_ = real
+        trainer.sync_replicas()
+        exposed = (sec - sec_local) / steps * 1e3
+    value = world * B * steps / sec
+    pk = peaks()
+    out = {"metric": "decoder_train_samples_per_sec_16x64x64", "value": value, "unit": "samples/s",
+           "ms_per_step": sec / steps * 1e3, "steps": steps, "batch_per_gpu": B, "n_gpus": world, "dtype": "bf16",
+           "scaling": "weak", "higher_is_better": True,
+           "collective": None if world == 1 else "NCCL all-reduce (sum, then divide by the world size) of the flat fp32 "
+                                                 "gradient buffer, one call per step after the backward",
+           "allreduce_exposed_ms": exposed, "grad_bytes": int(trainer.flat_g.numel() * 4),
+           "grad_bytes_if_bf16": int(trainer.flat_g.numel() * 2),
+           "model_tflops": value * 3 * GFLOP_PER_SAMPLE_STEP / 1e3,
+           "frac_of_sustained_peak_per_gpu": value * 3 * GFLOP_PER_SAMPLE_STEP / 1e3 / world / pk["bf16_sustained"],
+           "gpu_launches": int(launches), "loss_first": losses[0], "loss_last": losses[-1],
+           "mem_gb": torch.cuda.max_memory_allocated(dev) / 1e9,
+           "workload": "config4: VideoDecoderTrainer.forward (p_losses + backward + gradient all-reduce) + update (clip "
+                       "0.5, AdamW), Unet3D dim64 mults(1,2,4,8), 3x16x64x64, 875 GFLOP per sample (3 x 291.8)"}
+    del trainer, dec, unet
+    torch.cuda.empty_cache()
+    return out
 
 
 def run_gpu_arm(args):
@@ -281,9 +422,22 @@ def run_gpu_arm(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         elapsed, e2e_elapsed = float(t[0]), float(t[1])
 
+    conv_profile = profile_conv_family(eng) if rank == 0 else None
+    ws_gb = eng.pool.total / 1e9
+    # the extra legs need the memory of the sampling plan (and must not disturb it while it is timed)
+    del graph, eng, params
+    unet._engines.clear()
+    torch.cuda.empty_cache()
+    train = None
+    if not args.no_train:
+        train = train_block(dev, world, rank, args.train_batch, max(3, min(args.steps, 10)), 3)
+    eager = None
+    if rank == 0 and world == 1 and not args.no_eager_baseline:
+        eager = gpu_eager_baseline(dev, B)
+
     if rank == 0:
         pk = peaks()
-        flops, conv_sec, n_conv, n_tc, dom_sec, dom_flops, dom_n = profile_conv_family(eng)
+        flops, conv_sec, n_conv, n_tc, dom_sec, dom_flops, dom_n = conv_profile
         traffic = None
         tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
         if os.path.isfile(tp):
@@ -291,13 +445,11 @@ def run_gpu_arm(args):
         achieved = flops / conv_sec / 1e12
         value = world * B * args.steps / elapsed
         e2e_val = world * B * e2e_steps / e2e_elapsed
-        ws_gb = eng.pool.total / 1e9
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
-            sec, threads = cpu_reference_step_time(3, 1)
-            cpu = {"value": 1.0 / sec, "unit": UNIT, "cores": threads, "kind": "port",
-                   "sample": "3 denoise steps at batch 1 after 1 warm-up (oracle restatement of the reference Unet3D + "
-                             "DDPM update, fp32, torch CPU, all host threads)"}
+            sec, threads, kind, what = cpu_reference_step_time(3, 1)
+            cpu = {"value": 1.0 / sec, "unit": UNIT, "cores": threads, "kind": kind,
+                   "sample": f"3 denoise steps at batch 1 after 1 warm-up: {what}, fp32, torch CPU, all host threads"}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": elapsed / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -317,21 +469,31 @@ def run_gpu_arm(args):
             "gpu_launches": int(launches_per_step * args.steps),
             "launches_per_step": int(launches_per_step),
             "clocks": sampler.summary(),
-            "roofline": {"bound": "tensor", "kernel": "dv_conv_igemm (all launches of one step)", "achieved": achieved,
+            "roofline": {"bound": "tensor",
+                         "kernel": "dv_conv_igemm (all launches of one step: the 3x3 / 1x1 convolutions AND the q / kv / out "
+                                   "projections of the attention blocks, which run through the same entry point — 259.4 "
+                                   "GFLOP per sample against SURVEY B.2's 253-255 for conv + 1x1 alone)",
+                         "achieved": achieved,
                          "peak": pk["bf16_sustained"], "unit": "TFLOP/s", "frac": achieved / pk["bf16_sustained"],
-                         "peak_source": pk["source"] + " bf16_tflops_sustained (kernel timed inside the step)",
+                         "peak_burst": pk["bf16_tflops"], "frac_burst": achieved / pk["bf16_tflops"],
+                         "peak_source": pk["source"] + " bf16_tflops_sustained (kernel timed inside the step); frac_burst "
+                                        "is against the burst figure — MEASURED_PEAKS' sustained number was taken at a lower "
+                                        "SM clock than this bench settles at, so both are reported",
                          "algorithmic_gflop_per_step": flops / 1e9, "conv_ms_per_step": conv_sec * 1e3,
                          "launches": n_conv, "tcgen05_launches": n_tc,
                          "dominant_launch": {"kernel": "conv_halo_kernel 3x3 64->64 @64x64 (dv_conv_igemm)", "launches_per_step": dom_n,
                                              "algorithmic_gflop": dom_flops / 1e9, "avg_ms": dom_sec * 1e3,
                                              "achieved": dom_flops / dom_sec / 1e12 if dom_sec else None,
                                              "frac": dom_flops / dom_sec / 1e12 / pk["bf16_sustained"] if dom_sec else None,
+                                             "frac_burst": dom_flops / dom_sec / 1e12 / pk["bf16_tflops"] if dom_sec else None,
                                              "algorithmic_bytes": 2.0 * 2 * B * FRAMES * SIZE * SIZE * 64},
                          "traffic": traffic,
                          "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant launch shape, "
                                          "one ncu --set full capture (profiles/ncu_traffic.json names the summaries); null for batches "
                                          "that were not captured"},
             "cpu_baseline": cpu,
+            "gpu_eager_baseline": eager,
+            "train": train,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -347,6 +509,9 @@ def main():
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-eager-baseline", action="store_true", help="skip the torch-eager-on-the-same-GPU leg (N=1 only)")
+    ap.add_argument("--no-train", action="store_true", help="skip the config-4 (data-parallel training step) block")
+    ap.add_argument("--train-batch", type=int, default=16, help="videos per GPU in the training block")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3

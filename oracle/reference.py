@@ -1,8 +1,12 @@
 """ORACLE helper — loads the reference's OWN Unet3D / VideoDecoder code (unmodified, from
 /root/reference/dalle2_video/dalle2_video.py) on top of the restated primitives.
 
-Only available where /root/reference is mounted (this container); never on the GPU box.
-Used by oracle/make_golden.py and by CPU tests that cross-check the restatement.
+Search order: $DV_REFERENCE_ROOT, /root/reference (this container only), then <repo>/baseline/_ref — the
+unmodified reference package installed there with
+    python -m pip install --no-index --no-build-isolation --no-deps --target baseline/_ref <copy of /root/reference>
+(git-ignored, but it travels to the GPU box, where /root/reference does not exist).
+Used by oracle/make_golden.py, by CPU tests that cross-check the restatement, and by `bench.py --impl reference` /
+the `cpu_baseline` leg (kind "reference"); never by the product package.
 """
 from __future__ import annotations
 
@@ -10,10 +14,20 @@ import importlib.util
 import os
 import sys
 
-REFERENCE_ROOT = os.environ.get("DV_REFERENCE_ROOT", "/root/reference")
 _SHIM = os.path.join(os.path.dirname(os.path.abspath(__file__)), "shim")
 _REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 _cached = None
+
+
+def _find_root():
+    roots = [os.environ.get("DV_REFERENCE_ROOT"), "/root/reference", os.path.join(_REPO, "baseline", "_ref")]
+    for r in roots:
+        if r and os.path.isfile(os.path.join(r, "dalle2_video", "dalle2_video.py")):
+            return r
+    return os.environ.get("DV_REFERENCE_ROOT", "/root/reference")
+
+
+REFERENCE_ROOT = _find_root()
 
 
 def available() -> bool:

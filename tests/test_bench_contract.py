@@ -28,14 +28,15 @@ def test_reference_arm_line_on_the_host_cores():
     assert d["impl"] == "reference" and d["value"] > 0 and d["unit"] == "sample-steps/s"
     assert d["config"]["workload"].startswith("config2") and "model" not in d["config"]
     cb = d["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
+    from oracle import reference
+    assert cb["kind"] == ("reference" if reference.available() else "port") and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["vs_baseline"] is None
 
 
 @pytest.mark.gpu
 def test_b200_arm_line_carries_roofline_e2e_clocks_and_launch_count():
-    d = run_bench("--steps", "3", "--warmup", "3", "--batch", "4", "--no-cpu-baseline")
+    d = run_bench("--steps", "3", "--warmup", "3", "--batch", "4", "--no-cpu-baseline", "--no-eager-baseline", "--train-batch", "2")
     assert BASE_KEYS | {"roofline", "clocks", "gpu_launches"} <= set(d)
     assert d["n_gpus"] == 1 and d["steps"] == 3 and d["warmup"] == 3 and d["dtype"] == "bf16" and d["data"] == "synthetic"
     assert d["metric"] == "unet3d_denoise_sample_steps_per_sec_16x64x64" and d["higher_is_better"] is True
@@ -45,3 +46,7 @@ def test_b200_arm_line_carries_roofline_e2e_clocks_and_launch_count():
     e = d["e2e"]
     assert e["value"] > 0 and e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] > 0 and e["value"] <= d["value"] * 1.05
     assert d["gpu_launches"] > 0 and d["clocks"]["sm_mhz"] > 0
+    assert abs(r["frac_burst"] - r["achieved"] / r["peak_burst"]) < 1e-6
+    t = d["train"]   # BASELINE.json configs[3]: the data-parallel training step, the one place the path has a collective
+    assert t["value"] > 0 and t["unit"] == "samples/s" and t["batch_per_gpu"] == 2 and t["gpu_launches"] > 0
+    assert t["collective"] is None and t["allreduce_exposed_ms"] is None   # one GPU: nothing to reduce
