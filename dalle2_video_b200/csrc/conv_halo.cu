@@ -28,6 +28,13 @@ namespace dv {
 
 constexpr int HL_EPI_WARPS = 8;
 constexpr int HL_THREADS = 64 + 32 * HL_EPI_WARPS;
+// PRE variant: 20 warps = 5 warpgroups, roles aligned to warpgroups so that each can re-balance its registers with
+// setmaxnreg: WG0 = TMA (weights), MMA, two idle warps; WG1-2 = the eight epilogue warps; WG3-4 = eight transform warps.
+// Launched at 96 registers per thread; then WG0 keeps 40, the epilogue warpgroups take 144 and the transform warpgroups 72
+// (per scheduler: 40 + 144 + 144 + 72 + 72 = 472 x 32 <= the 480 x 32 of the launch allocation).
+constexpr int HL_XF_WARPS = 8;
+constexpr int HL_THREADS_PRE = 128 + 32 * HL_EPI_WARPS + 32 * HL_XF_WARPS;   // 640
+constexpr int HL_PRE_EPI_WARP0 = 4;
 constexpr int HL_TILE_Q = 256;
 
 struct HaloParams {
@@ -47,15 +54,32 @@ struct HaloParams {
   int direct_store;  // epilogue rows stored straight from registers instead of through the staging transpose
   int pair;          // BN == 64: taps dx=-1 and dx=0 of a filter row share ONE N=128 MMA (see the MMA issuer); tile stride 255
   long long* prof;  // optional [grid][16] cycle counters (debug, DV_HALO_PROFILE env)
+  // PRE variant (fused K2 on the load path): the input is the RAW output of the previous convolution; GroupNorm finalize +
+  // (1+scale)/shift + SiLU are applied while the activation window is brought into shared memory
+  const __nv_bfloat16* pre_src;   // [n_img][H][W][C0]
+  const double* pre_stats;        // [B][pre_groups][2] (sum, sum of squares) of pre_src
+  const float* pre_gamma;
+  const float* pre_beta;
+  const float* pre_scale;         // element (b,c) at pre_scale[b*pre_ss_ld + c], or NULL
+  const float* pre_shift;
+  int pre_ss_ld, pre_groups;
+  float pre_eps;
+  int pre_debug;   // timing experiments (DV_HALO_PRE_DEBUG): 1 no global loads, 2 no math, 4 no shared stores
 };
 
 __device__ __forceinline__ void hl_epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 #define HL_T0() const long long t0__ = clock64()
 #define HL_ACC(var) var += clock64() - t0__
 
-__global__ void __launch_bounds__(HL_THREADS, 1)
-conv_halo_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
-                 const __grid_constant__ CUtensorMap map_b, const HaloParams p) {
+// PRE = false: warp 0 brings activation windows and weights in by TMA.
+// PRE = true : the activation window is produced by ten extra "transform" warps instead: 16-byte global loads of the raw
+//   tensor (zeros for padding), y = SiLU(x*a[c] + d[c]) with the per-(sample, channel) GroupNorm / scale-shift coefficients
+//   in registers, 16-byte stores at the SWIZZLE_128B position the UMMA descriptor expects (chunk ^ (row & 7); the stage is
+//   1024-byte aligned).  Shared-memory traffic is the same as with TMA (one write of the window) — the operand reads of the
+//   N = 64 MMAs own that port — and the standalone gn_apply pass (one HBM read + write of the tensor) disappears.
+template <bool PRE>
+__device__ __forceinline__ void conv_halo_body(const CUtensorMap& map_a0, const CUtensorMap& map_a1, const CUtensorMap& map_b,
+                                               const HaloParams& p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const uint32_t b_bytes = (uint32_t)p.BN * 128 * 3;  // one weight stage = the three taps of one filter row
@@ -65,7 +89,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
   int* rowpos = reinterpret_cast<int*>(stage_out + p.out_bufs * 16384);  // 2 x [128] output row of each staged row (-1: discard)
   float* bias_s = reinterpret_cast<float*>(rowpos + 256);                   // [128]
   float* sred = bias_s + 128;                                               // [64]
-  uint64_t* full_a = reinterpret_cast<uint64_t*>(sred + 64);
+  float* coef_s = sred + 64;                                                // PRE: [2][128] half-coefficients of the current sample
+  uint64_t* full_a = reinterpret_cast<uint64_t*>(coef_s + (PRE ? 256 : 0));
   uint64_t* empty_a = full_a + p.a_stages;
   uint64_t* full_b = empty_a + p.a_stages;
   uint64_t* empty_b = full_b + p.b_stages;
@@ -74,13 +99,18 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // PRE: the producer / MMA / epilogue warps share their schedulers with the transform warps, which are the busiest role
+  auto wait = [](uint64_t* bar, uint32_t parity) {
+    if (PRE) mbar_wait_backoff(bar, parity);
+    else mbar_wait(bar, parity);
+  };
   const uint32_t tmem_cols = p.pair ? 512u : (uint32_t)(4 * p.BN);  // 256 or 512 (pair mode: 2 buffers x 2 sub-tiles x 128)
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_a0);
     tma_prefetch_desc(&map_a1);
     tma_prefetch_desc(&map_b);
-    for (int s = 0; s < p.a_stages; ++s) { mbar_init(&full_a[s], 1); mbar_init(&empty_a[s], 1); }
+    for (int s = 0; s < p.a_stages; ++s) { mbar_init(&full_a[s], PRE ? HL_XF_WARPS : 1); mbar_init(&empty_a[s], 1); }
     for (int s = 0; s < p.b_stages; ++s) { mbar_init(&full_b[s], 1); mbar_init(&empty_b[s], 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], HL_EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -97,6 +127,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const int epi_warp0 = PRE ? HL_PRE_EPI_WARP0 : 2;
+  const bool is_epi = warp >= epi_warp0 && warp < epi_warp0 + HL_EPI_WARPS;
 
   const int per_cta = (p.total_tiles + (int)gridDim.x - 1) / (int)gridDim.x;
   const int tile_begin = (int)blockIdx.x * per_cta;
@@ -117,6 +149,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
     return g;
   };
 
+  if (PRE && warp < HL_PRE_EPI_WARP0) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");   // WG0, one instruction for all four warps
   if (warp == 0) {
     // ================================================================ TMA producer
     if (elect_one()) {
@@ -131,18 +164,20 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
           const int src = ch >= p.c0_chunks;
           const int c = src ? ch - p.c0_chunks : ch;
           const CUtensorMap* map = src ? &map_a1 : &map_a0;
-          { HL_T0(); mbar_wait(&empty_a[sa], pa ^ 1); HL_ACC(w_a); }
-          uint8_t* dst = a_ring + (size_t)sa * p.a_stage_bytes;
-          mbar_expect_tx(&full_a[sa], (uint32_t)(p.NR * p.Wp * 128));
-          int n = n_lo, yr = y_lo;
-          for (int r = 0; r < p.NR; ++r) {
-            tma_load_5d(map, &full_a[sa], dst + (size_t)r * p.Wp * 128, c * TC_BK, -1, yr - 1, n, 0);
-            if (++yr == p.Hp1) { yr = 0; ++n; }
+          if (!PRE) {
+            { HL_T0(); mbar_wait(&empty_a[sa], pa ^ 1); HL_ACC(w_a); }
+            uint8_t* dst = a_ring + (size_t)sa * p.a_stage_bytes;
+            mbar_expect_tx(&full_a[sa], (uint32_t)(p.NR * p.Wp * 128));
+            int n = n_lo, yr = y_lo;
+            for (int r = 0; r < p.NR; ++r) {
+              tma_load_5d(map, &full_a[sa], dst + (size_t)r * p.Wp * 128, c * TC_BK, -1, yr - 1, n, 0);
+              if (++yr == p.Hp1) { yr = 0; ++n; }
+            }
+            if (++sa == p.a_stages) { sa = 0; pa ^= 1; }
           }
-          if (++sa == p.a_stages) { sa = 0; pa ^= 1; }
           if (!p.b_resident || tile == tile_begin) {
             for (int g3 = 0; g3 < 3; ++g3) {
-              { HL_T0(); mbar_wait(&empty_b[sb], pb ^ 1); HL_ACC(w_b); }
+              { HL_T0(); wait(&empty_b[sb], pb ^ 1); HL_ACC(w_b); }
               mbar_expect_tx(&full_b[sb], b_bytes);
               for (int t3 = 0; t3 < 3; ++t3)
                 tma_load_2d(&map_b, &full_b[sb], b_ring + (size_t)sb * b_bytes + (size_t)t3 * p.BN * 128,
@@ -167,11 +202,11 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
     const long long tstart = clock64();
     for (int tile = tile_begin; tile < tile_end; ++tile) {
       const int row_off = tile_geo(tile).row_off;
-      { HL_T0(); mbar_wait(&tmem_empty[acc], acc_phase ^ 1); HL_ACC(w_t); }
+      { HL_T0(); wait(&tmem_empty[acc], acc_phase ^ 1); HL_ACC(w_t); }
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + (uint32_t)(p.pair ? acc * 256 : acc * 2 * p.BN);
       for (int ch = 0; ch < n_chunks; ++ch) {
-        { HL_T0(); mbar_wait(&full_a[sa], pa); HL_ACC(w_a); }
+        { HL_T0(); wait(&full_a[sa], pa); HL_ACC(w_a); }
         tc_fence_after();
         // descriptor of window row `row_off` (the tile's first output) in this stage; taps and sub-tiles are
         // constant offsets in 16-byte units added to the low word
@@ -179,7 +214,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
         const bool first_tile = tile == tile_begin;
         for (int g3 = 0; g3 < 3; ++g3) {
           const int sbi = p.b_resident ? ch * 3 + g3 : sb;
-          if (!p.b_resident || first_tile) { HL_T0(); mbar_wait(&full_b[sbi], p.b_resident ? 0u : pb); HL_ACC(w_b); }
+          if (!p.b_resident || first_tile) { HL_T0(); wait(&full_b[sbi], p.b_resident ? 0u : pb); HL_ACC(w_b); }
           tc_fence_after();
           if (p.pair) {
             // Tap pairing (BN = 64): the N = 64 MMA is bounded by its 4 KB A-operand read, so the taps dx = -1 and dx = 0 of
@@ -244,9 +279,166 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
       p.prof[blockIdx.x * 16 + 6] = w_a;
       p.prof[blockIdx.x * 16 + 7] = w_b;
     }
-  } else {
+  } else if (PRE && warp >= HL_PRE_EPI_WARP0 + HL_EPI_WARPS) {
+    // ================================================================ input transform (PRE only, 8 warps)
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
+    // Items of 16 bytes (8 channels of one window pixel).  Measured on B200 (tools/halo_profile.py, ncu source view): a
+    // transform warp sustains only ~0.2 instructions per cycle whatever the instruction mix (fixed-latency dependencies;
+    // fp32 vs packed-bf16 math, 16- vs 32-byte items, 4 vs 12 loads in flight all landed within 10 % of each other), so
+    // the lever is warps per scheduler: 2 here instead of 1-1.5, which setmaxnreg makes affordable.  The steps are
+    // branch-free (predicated loads / stores, selects for the padding zeros), the window cursor advances incrementally,
+    // and the loop-invariants are pinned in registers (the compiler otherwise re-reads kernel parameters from the constant
+    // bank in every step: 28 k -> 12 k cycles per tile).
+    constexpr int XT = 32 * HL_XF_WARPS;
+    const int tw = warp - (HL_PRE_EPI_WARP0 + HL_EPI_WARPS);   // transform warp 0..7
+    const int tt = tw * 32 + lane;
+    const int j = lane & 7;                     // this thread's 16 bytes = channels [8 j, 8 j + 8) of the K chunk
+    const int lp = lane >> 3;                   // pixel inside the warp's group of 4 consecutive window pixels
+    const int C = p.c0_chunks * TC_BK;
+    const int cpg = C / p.pre_groups;
+    const double cnt = (double)p.frames * p.H * p.W * cpg;
+    const uint32_t coef_u32 = smem_u32(coef_s);
+    // Work units = half rows of the window (whole rows would leave warps idle when NR is not a multiple of 8): unit v is
+    // row v >> 1, columns [half * HWc, ...) with HWc = ceil(Wp / 2) rounded up to 4; a warp walks units tw, tw + 8, ... in
+    // groups of 4 pixels.  The row state (frame row, memory row, validity) is warp-uniform and computed once per unit;
+    // per item only the column advances.
+    const int HWc = ((p.Wp + 1) / 2 + 3) & ~3;
+    const int n_units = 2 * p.NR;
+    int sa = 0, cur_sample = -1;
+    uint32_t pa = 0;
+    long long w_e = 0;
+    const long long tstart = clock64();
+    for (int tile = tile_begin; tile < tile_end; ++tile) {
+      const TileGeo g = tile_geo(tile);
+      if (g.sample != cur_sample) {
+        // y = SiLU(x*a + d) = h*tanh(h) + h with h = x*(a/2) + d/2: the halved coefficients of this sample
+        asm volatile("bar.sync 2, %0;" ::"n"(XT) : "memory");
+        for (int c = tt; c < C; c += XT) {
+          const int grp = c / cpg;
+          const double s1 = p.pre_stats[((int64_t)g.sample * p.pre_groups + grp) * 2 + 0];
+          const double s2 = p.pre_stats[((int64_t)g.sample * p.pre_groups + grp) * 2 + 1];
+          const double mean = s1 / cnt;
+          double var = s2 / cnt - mean * mean;
+          if (var < 0.0) var = 0.0;
+          const float rstd = (float)(1.0 / sqrt(var + (double)p.pre_eps));
+          float a = rstd * p.pre_gamma[c];
+          float d = p.pre_beta[c] - (float)mean * a;
+          if (p.pre_scale) {
+            const float sc = 1.0f + p.pre_scale[(int64_t)g.sample * p.pre_ss_ld + c];
+            a *= sc;
+            d = d * sc + p.pre_shift[(int64_t)g.sample * p.pre_ss_ld + c];
+          }
+          coef_s[c] = 0.5f * a;
+          coef_s[128 + c] = 0.5f * d;
+        }
+        asm volatile("bar.sync 2, %0;" ::"n"(XT) : "memory");
+        cur_sample = g.sample;
+      }
+      const int n_lo = g.r_lo / p.Hp1, y_lo = g.r_lo - n_lo * p.Hp1;
+      const int mrow0 = n_lo * p.H + y_lo - 1;
+      for (int ch = 0; ch < p.c0_chunks; ++ch) {
+        float ca[8], cd[8];
+        {
+          const uint32_t ca_addr = coef_u32 + (uint32_t)(ch * TC_BK + j * 8) * 4u;
+#pragma unroll
+          for (int q4 = 0; q4 < 2; ++q4) {
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                         : "=f"(ca[4 * q4]), "=f"(ca[4 * q4 + 1]), "=f"(ca[4 * q4 + 2]), "=f"(ca[4 * q4 + 3]) : "r"(ca_addr + 16u * q4));
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                         : "=f"(cd[4 * q4]), "=f"(cd[4 * q4 + 1]), "=f"(cd[4 * q4 + 2]), "=f"(cd[4 * q4 + 3]) : "r"(ca_addr + 512u + 16u * q4));
+          }
+        }
+        { HL_T0(); mbar_wait(&empty_a[sa], pa ^ 1); HL_ACC(w_e); }
+        const uint32_t dst = smem_u32(a_ring + (size_t)sa * p.a_stage_bytes);   // 1024-byte aligned: swizzle phase = pix & 7
+        const __nv_bfloat16* src = p.pre_src + ch * TC_BK + j * 8;
+        int kW = p.W, kWp = p.Wp, kC = C, kHp1 = p.Hp1, kRows = p.n_img * p.H, kNU = n_units, kHWc = HWc, kY = y_lo,
+            kM0 = mrow0, dbg = p.pre_debug;
+        asm volatile("" : "+r"(kW), "+r"(kWp), "+r"(kC), "+r"(kHp1), "+r"(kRows), "+r"(kNU), "+r"(kHWc), "+r"(kY), "+r"(kM0),
+                     "+r"(dbg));
+        // Software pipeline over units: the body below is IUMAX straight-line steps; step `it` first transforms and
+        // stores item `it` of the PREVIOUS unit (its load was issued one whole unit ago: IUMAX items of distance), then
+        // issues the load of item `it` of the current unit into the same registers.  Row state is warp-uniform and
+        // computed once per unit; nothing inside the steps branches or reads kernel parameters.
+        constexpr int IUMAX = 9;   // host-checked: ceil(ceil(Wp / 2) / 4) <= 9, i.e. W <= 70
+        uint4 raw[IUMAX];
+#pragma unroll
+        for (int u = 0; u < IUMAX; ++u) raw[u] = make_uint4(0u, 0u, 0u, 0u);
+        uint32_t okm_prev = 0, sbase_prev = 0, sw0_prev = 0, sw1_prev = 0;
+        int xleft_prev = 0;   // xend - xq0 of the previous unit: item `it` lies inside its unit iff 4*it < xleft
+        for (int unit = tw;; unit += HL_XF_WARPS) {
+          // ---- state of this unit (uniform except for lp / j)
+          const bool live = unit < kNU;
+          const int r = unit >> 1, half = unit & 1;
+          int yr = kY + r, cross = 0;
+          if (yr >= kHp1) { yr -= kHp1; cross = 1; }
+          if (yr >= kHp1) { yr -= kHp1; cross = 2; }
+          const int mrow = kM0 + r - cross;
+          const bool rowok = live && yr != 0 && mrow < kRows;
+          const int xq0 = half * kHWc + lp;
+          const int xleft = live ? (half ? kWp : kHWc) - xq0 : 0;
+          const __nv_bfloat16* ptr0 = src + (int64_t)(mrow * kW + xq0 - 1) * kC;
+          const int pix0 = r * kWp + xq0;
+          const uint32_t sbase = dst + (uint32_t)pix0 * 128u;
+          const uint32_t sw0 = (uint32_t)((j ^ (pix0 & 7)) << 4), sw1 = sw0 ^ 64u;   // items advance 4 pixels: bit 2 of the phase toggles
+          uint32_t okm = 0;
+#pragma unroll
+          for (int it = 0; it < IUMAX; ++it) {
+            // ---- finish item `it` of the previous unit
+            {
+              const bool ok = (okm_prev >> it) & 1u;   // padding stays exactly zero (SiLU(d) != 0)
+              uint4 o;
+              const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw[it]);
+              __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float2 xv = __bfloat1622float2(h2[e]);
+                const float h0 = fmaf(xv.x, ca[2 * e], cd[2 * e]), h1 = fmaf(xv.y, ca[2 * e + 1], cd[2 * e + 1]);
+                float t0, t1;
+                asm("tanh.approx.f32 %0, %1;" : "=f"(t0) : "f"(h0));
+                asm("tanh.approx.f32 %0, %1;" : "=f"(t1) : "f"(h1));
+                o2[e] = __floats2bfloat162_rn(fmaf(h0, t0, h0), fmaf(h1, t1, h1));
+              }
+              o.x = ok ? o.x : 0u; o.y = ok ? o.y : 0u; o.z = ok ? o.z : 0u; o.w = ok ? o.w : 0u;
+              asm volatile(
+                  "{\n\t"
+                  ".reg .pred p;\n\t"
+                  "setp.ne.b32 p, %5, 0;\n\t"
+                  "@p st.shared.v4.b32 [%0], {%1, %2, %3, %4};\n\t"
+                  "}" ::"r"(sbase_prev + (uint32_t)(it * 512) + ((it & 1) ? sw1_prev : sw0_prev)),
+                  "r"(o.x), "r"(o.y), "r"(o.z), "r"(o.w), "r"((uint32_t)(4 * it < xleft_prev && !(dbg & 4)))
+                  : "memory");
+            }
+            // ---- issue item `it` of this unit
+            {
+              const bool ok = rowok && 4 * it < xleft && (unsigned)(xq0 + 4 * it - 1) < (unsigned)kW;
+              asm volatile(
+                  "{\n\t"
+                  ".reg .pred p;\n\t"
+                  "setp.ne.b32 p, %5, 0;\n\t"
+                  "@p ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];\n\t"
+                  "}"
+                  : "+r"(raw[it].x), "+r"(raw[it].y), "+r"(raw[it].z), "+r"(raw[it].w)
+                  : "l"(ptr0 + 4 * it * kC), "r"((uint32_t)(ok && !(dbg & 1))));
+              okm |= (uint32_t)ok << it;
+            }
+          }
+          okm_prev = okm; sbase_prev = sbase; sw0_prev = sw0; sw1_prev = sw1; xleft_prev = xleft;
+          if (!live) break;   // the iteration after the last unit only drained the pipeline
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&full_a[sa]);
+        if (++sa == p.a_stages) { sa = 0; pa ^= 1; }
+      }
+    }
+    if (p.prof && tt == 0) {
+      p.prof[blockIdx.x * 16 + 12] = clock64() - tstart;
+      p.prof[blockIdx.x * 16 + 13] = w_e;
+    }
+  } else if (is_epi) {
     // ================================================================ epilogue (8 warps)
-    const int ew = warp - 2, wg = ew >> 2, q = warp & 3;
+    if (PRE) asm volatile("setmaxnreg.inc.sync.aligned.u32 144;");
+    const int ew = warp - epi_warp0, wg = ew >> 2, q = warp & 3;
     const int row_in_sub = q * 32 + lane;
     const int et = ew * 32 + lane;
     int acc = 0;
@@ -296,7 +488,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
         }
       };
       load_add(0, 0);
-      { HL_T0(); mbar_wait(&tmem_full[acc], acc_phase); HL_ACC(w_f); }
+      { HL_T0(); wait(&tmem_full[acc], acc_phase); HL_ACC(w_f); }
       tc_fence_after();
       if (p.pair) {
         // phase 1: columns [64,128) of accumulator row M belong to output row M - 1: hand them over through shared
@@ -507,15 +699,27 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
   }
 }
 
+__global__ void __launch_bounds__(HL_THREADS, 1)
+conv_halo_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
+                 const __grid_constant__ CUtensorMap map_b, const __grid_constant__ HaloParams p) {
+  conv_halo_body<false>(map_a0, map_a1, map_b, p);
+}
+// 640 threads x 96 registers at launch; the warpgroups then re-balance with setmaxnreg (see HL_XF_WARPS)
+__global__ void __launch_bounds__(HL_THREADS_PRE, 1)
+conv_halo_pre_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
+                     const __grid_constant__ CUtensorMap map_b, const __grid_constant__ HaloParams p) {
+  conv_halo_body<true>(map_a0, map_a1, map_b, p);
+}
+
 // ------------------------------------------------------------------------------------------ host side
 static int halo_nr(int Wp) { return (HL_TILE_Q + 2 * Wp + 2 + Wp - 2) / Wp + 1; }
 
 static size_t halo_smem(int Wp, int BN, int n_chunks, int* a_stage_bytes, int* a_stages, int* b_stages, int* out_bufs,
-                        int* resident) {
+                        int* resident, bool pre = false) {
   const int a = (halo_nr(Wp) * Wp * 128 + 1023) / 1024 * 1024;
   const int bstage = 3 * BN * 128;
   const int limit = 227 * 1024 - 1024;  // minus alignment slack
-  const int misc = 2 * 128 * 8 + 128 * 4 + 64 * 4 + 1024;
+  const int misc = 2 * 128 * 8 + 128 * 4 + 64 * 4 + 1024 + (pre ? 1024 : 0);
   // two activation-window stages (measured: a third does not help), double-buffered output staging when it fits,
   // the rest for weight stages (one stage = three taps); if ALL weights fit they are loaded once and stay resident
   int as = 2, ob = 2;
@@ -544,8 +748,16 @@ int conv_halo_supported(const dv_conv_params& p) {
   if (p.stats) {
     if (p.groups <= 0 || p.Cout % p.groups || (p.Cout / p.groups) % 8 || p.groups > 32) return 0;
   }
+  const bool pre = p.pre_stats != nullptr;
+  if (pre) {
+    // fused input GroupNorm: one bf16 source of at most 128 channels whose groups do not straddle 8-channel vectors
+    if (p.C1 || p.C0 > 128 || !p.pre_gamma || !p.pre_beta || (!p.pre_scale) != (!p.pre_shift)) return 0;
+    if (p.pre_groups <= 0 || p.C0 % p.pre_groups) return 0;
+    if ((int64_t)p.n_img * p.H * p.W * p.C0 >= (1ll << 31)) return 0;   // 32-bit element indices in the transform warps
+    if (p.W > 70) return 0;                                                // half a window row = at most 9 groups of 4 pixels
+  }
   int a, as, bs, ob, res;
-  halo_smem(p.W + 2, p.Cout, (p.C0 + p.C1) / TC_BK, &a, &as, &bs, &ob, &res);
+  halo_smem(p.W + 2, p.Cout, (p.C0 + p.C1) / TC_BK, &a, &as, &bs, &ob, &res, pre);
   return bs >= 2;
 }
 
@@ -556,8 +768,16 @@ int conv_halo_launch(const dv_conv_params& p, cudaStream_t s) {
   h.c0_chunks = p.C0 / TC_BK; h.c1_chunks = p.C1 / TC_BK;
   h.BN = p.Cout;
   h.NR = halo_nr(h.Wp);
+  const bool pre = p.pre_stats != nullptr;
   const size_t smem = halo_smem(h.Wp, h.BN, h.c0_chunks + h.c1_chunks, &h.a_stage_bytes, &h.a_stages, &h.b_stages,
-                                &h.out_bufs, &h.b_resident);
+                                &h.out_bufs, &h.b_resident, pre);
+  if (pre) {
+    h.pre_src = reinterpret_cast<const __nv_bfloat16*>(p.src0);
+    h.pre_stats = p.pre_stats; h.pre_gamma = p.pre_gamma; h.pre_beta = p.pre_beta;
+    h.pre_scale = p.pre_scale; h.pre_shift = p.pre_shift;
+    h.pre_ss_ld = p.pre_ss_ld; h.pre_groups = p.pre_groups; h.pre_eps = p.pre_eps;
+    if (const char* e = getenv("DV_HALO_PRE_DEBUG")) h.pre_debug = atoi(e);
+  }
   const int64_t span = ((int64_t)p.frames * h.Hp1 - 2) * h.Wp + p.W;
   {
     static int pr = -1, ds = -1;
@@ -574,7 +794,8 @@ int conv_halo_launch(const dv_conv_params& p, cudaStream_t s) {
   h.tiles_per_sample = (int)((span + stride - 1) / stride);
   h.total_tiles = (p.n_img / p.frames) * h.tiles_per_sample;
   h.wp_magic = (uint32_t)((65536 + h.Wp - 1) / h.Wp);
-  for (int off = 0; off < h.Wp + HL_TILE_Q; ++off)
+  const int magic_range = h.Wp + HL_TILE_Q > h.NR * h.Wp ? h.Wp + HL_TILE_Q : h.NR * h.Wp;  // epilogue rows / window pixels
+  for (int off = 0; off < magic_range; ++off)
     DV_REQUIRE((int)(((uint32_t)off * h.wp_magic) >> 16) == off / h.Wp, DV_EUNSUPPORTED, "dv_conv_igemm(halo): division magic");
   h.bias = p.bias;
   h.add = reinterpret_cast<const __nv_bfloat16*>(p.add);
@@ -628,11 +849,16 @@ int conv_halo_launch(const dv_conv_params& p, cudaStream_t s) {
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(conv_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(conv_halo_pre_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     DV_REQUIRE(e == cudaSuccess, DV_ECUDA, "dv_conv_igemm(halo): cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     attr_set = true;
   }
   const int grid = h.total_tiles < sm_count ? h.total_tiles : sm_count;
-  conv_halo_kernel<<<grid, HL_THREADS, smem, s>>>(ma0, ma1, mb, h);
+  if (pre)
+    conv_halo_pre_kernel<<<grid, HL_THREADS_PRE, smem, s>>>(ma0, ma1, mb, h);
+  else
+    conv_halo_kernel<<<grid, HL_THREADS, smem, s>>>(ma0, ma1, mb, h);
   DV_CHECK_LAUNCH("dv_conv_igemm(halo)");
   return DV_OK;
 }

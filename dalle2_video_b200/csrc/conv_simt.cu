@@ -302,6 +302,15 @@ extern "C" int dv_conv_uses_tcgen05(const dv_conv_params* pin) {
   return dv::conv_tc_supported(*p) || (dv::halo_enabled() && dv::conv_halo_supported(*p));
 }
 
+extern "C" int dv_conv_pre_norm_supported(const dv_conv_params* pin) {
+  dv::ConvGeom g;
+  if (!pin || !pin->pre_stats) return 0;
+  dv_conv_params q = *pin;
+  if (q.mode != DV_CONV_NORMAL || q.impl == 1 || q.impl == 2) return 0;
+  if (dv::validate_conv(&q, &g) != DV_OK) return 0;
+  return dv::halo_enabled() && dv::conv_halo_supported(q);
+}
+
 extern "C" int dv_conv_igemm(const dv_conv_params* pin, dv_stream_t stream) {
   using namespace dv;
   ConvGeom g;
@@ -321,6 +330,9 @@ extern "C" int dv_conv_igemm(const dv_conv_params* pin, dv_stream_t stream) {
   if (p.impl == 2) DV_REQUIRE(tc_ok, DV_EUNSUPPORTED, "dv_conv_igemm: tcgen05 path does not support this shape");
   if (p.impl == 3) DV_REQUIRE(halo_ok, DV_EUNSUPPORTED, "dv_conv_igemm: streaming-halo path does not support this shape");
   if (p.impl == 3 || (p.impl == 0 && halo_ok && halo_enabled())) return conv_halo_launch(p, s);
+  DV_REQUIRE(!p.pre_stats, DV_EUNSUPPORTED,
+             "dv_conv_igemm: the fused input GroupNorm (pre_stats) needs the streaming-halo kernel (3x3, one bf16 source of "
+             "64 / 128 channels, Cout 64 / 128, W >= 32); ask dv_conv_pre_norm_supported first");
   if (tc_ok && p.impl != 1) return conv_tc_launch(p, s);
   return (p.dtype == DV_F32) ? launch_simt<float>(p, g, s) : launch_simt<__nv_bfloat16>(p, g, s);
 }

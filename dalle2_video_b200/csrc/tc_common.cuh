@@ -32,6 +32,24 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "}" ::"r"(smem_u32(bar)), "r"(parity)
       : "memory");
 }
+// The same wait for a warp that shares its scheduler with a busy compute warp: a failed probe sleeps instead of
+// re-probing at once, so the spin does not take issue slots from the warp everybody is waiting for.
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity) {
+  uint32_t done;
+  for (;;) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (done) break;
+    __nanosleep(40);
+  }
+}
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred = 0;
   asm volatile(

@@ -11,6 +11,7 @@ non-CUDA tensor raises.
 from __future__ import annotations
 
 import math
+import os
 from functools import partial
 
 import torch
@@ -310,6 +311,10 @@ class Unet3D(nn.Module):
         self.compute_dtype = None  # None: follow autocast (bf16) else fp32; or torch.float32 / torch.bfloat16
         self.fuse_short_context_attention = True  # bf16: folded single-kernel CrossAttention for <= 7 keys
         self.fuse_init_conv = True                # bf16: CrossEmbedLayer3D as one tcgen05 kernel (no im2col in HBM)
+        # bf16: block1's GroupNorm / scale-shift / SiLU applied on the load path of block2's convolution instead of a
+        # standalone dv_gn_apply pass (dv_conv_params.pre_*).  Correct and tested, but OFF by default: measured on B200 the
+        # transform warps cost the convolution more than the HBM pass it removes
+        self.fuse_input_norm = os.environ.get("DV_FUSE_INPUT_NORM", "0") != "0"
         self._engines = {}
         self._param_version = None
 
@@ -536,15 +541,17 @@ class _Engine:
 
     # -------------------------------------------------------------- conv / gemm
     def _conv(self, srcs, weight, bias, out_ptr, Cout, n_img, H, W, *, k=1, mode=L.CONV_NORMAL, epilogue=L.EPI_STORE,
-              stats=None, groups=0, add=None, out_ld=0, out_coff=0, dtype_code=None, frames=None):
-        """srcs: list of (ptr, C).  Falls back to a separate statistics pass when the fused one does not apply."""
+              stats=None, groups=0, add=None, out_ld=0, out_coff=0, dtype_code=None, frames=None, pre=None):
+        """srcs: list of (ptr, C).  Falls back to a separate statistics pass when the fused one does not apply.
+        `pre`: GroupNorm + scale/shift + SiLU of the (raw) input on the load path (dv_conv_params.pre_*); the caller
+        checked dv_conv_pre_norm_supported."""
         p = L.ConvParams(src0=srcs[0][0], src1=srcs[1][0] if len(srcs) > 1 else None, weight=weight.data_ptr(),
                          bias=bias.data_ptr() if bias is not None else None, add=add, out=out_ptr, stats=stats,
                          n_img=n_img, frames=frames or self.T, H=H, W=W, C0=srcs[0][1],
                          C1=srcs[1][1] if len(srcs) > 1 else 0, Cout=Cout, kh=k,
                          kw=1 if mode == L.CONV_TEMPORAL else k, pad=k // 2, mode=mode,
                          epilogue=epilogue, groups=groups, out_ld=out_ld, out_coff=out_coff,
-                         dtype=self.code if dtype_code is None else dtype_code, impl=self.impl)
+                         dtype=self.code if dtype_code is None else dtype_code, impl=self.impl, **(pre or {}))
         Ho, Wo = (H // 2, W // 2) if mode == L.CONV_UNSHUFFLE else (H, W)
         rows_per_sample = (frames or self.T) * Ho * Wo
         separate_stats = stats is not None and (rows_per_sample % 64 != 0 or (Cout // groups) % 4 != 0)
@@ -899,16 +906,24 @@ class _Engine:
 
         h1, st1 = self._block_convs(m.block1, src_list, self._pack_conv(m.block1.project.weight, skip_scale, c0),
                                     rows, Co, n_img, h, w, G)
-        self._op("dv_gn_apply", L.GnApplyParams(
-            x=h1.ptr, out=h1.ptr, residual=None, stats=st1, gamma=self._f32(m.block1.norm.weight).data_ptr(),
-            beta=self._f32(m.block1.norm.bias).data_ptr(), scale=self.ss.data_ptr() + off * 4,
-            shift=self.ss.data_ptr() + (off + Co) * 4, ss_ld=self.ss_total, B=B, P=P, C=Co, groups=G,
-            eps=float(m.block1.norm.eps), dtype=self.code))
+        # block1's GroupNorm + (1+scale)/shift + SiLU (:125-131).  Its result has exactly one consumer: when that consumer
+        # can apply it on its own load path the standalone pass (one HBM read + write of the tensor) is not launched
+        norm1 = dict(stats=st1, gamma=self._f32(m.block1.norm.weight).data_ptr(),
+                     beta=self._f32(m.block1.norm.bias).data_ptr(), scale=self.ss.data_ptr() + off * 4,
+                     shift=self.ss.data_ptr() + (off + Co) * 4, ss_ld=self.ss_total, groups=G,
+                     eps=float(m.block1.norm.eps))
+        pre = None
+        if m.cross_attn is None:
+            pre = self._pre_norm_for_conv(m.block2, norm1, h1, Co, n_img, h, w, G)
+        if pre is None and not (m.cross_attn is not None and self._cross_attention_takes_norm(m, h1, P)):
+            self._op("dv_gn_apply", L.GnApplyParams(x=h1.ptr, out=h1.ptr, residual=None, B=B, P=P, C=Co, dtype=self.code,
+                                                    **norm1))
+            norm1 = None
         if m.cross_attn is not None:
-            self._cross_attention(m, h1, rows, P)
+            self._cross_attention(m, h1, rows, P, pre_norm=norm1)
 
         h2, st2 = self._block_convs(m.block2, [(h1.ptr, Co)], self._pack_conv(m.block2.project.weight), rows, Co,
-                                    n_img, h, w, G)
+                                    n_img, h, w, G, pre=pre)
         self._release(h1)
         if isinstance(m.res_conv, nn.Identity):
             assert len(srcs) == 1
@@ -931,14 +946,31 @@ class _Engine:
             self._release(a)
         return h2
 
-    def _block_convs(self, blk: _Block, src_list, wpacked, rows, Co, n_img, h, w, G):
+    def _pre_norm_for_conv(self, blk: _Block, norm, src: _Act, Co, n_img, h, w, G):
+        """dv_conv_params.pre_* for blk.project reading the raw tensor `src`, or None when the kernel that would run this
+        convolution cannot apply the normalisation on its load path."""
+        if self.dtype != torch.bfloat16 or not self.u.fuse_input_norm:
+            return None
+        pre = dict(pre_stats=norm["stats"], pre_gamma=norm["gamma"], pre_beta=norm["beta"], pre_scale=norm["scale"],
+                   pre_shift=norm["shift"], pre_ss_ld=norm["ss_ld"], pre_groups=norm["groups"], pre_eps=norm["eps"])
+        temporal = getattr(blk, "temporal", None)
+        probe = L.ConvParams(src0=src.ptr, src1=None, weight=1 << 20, bias=None, add=None, out=1 << 20,
+                             stats=None if temporal is not None else 1 << 20, n_img=n_img, frames=self.T, H=h, W=w, C0=src.C,
+                             C1=0, Cout=Co, kh=3, kw=3, pad=1, mode=L.CONV_NORMAL, epilogue=L.EPI_STORE, groups=G, out_ld=0,
+                             out_coff=0, dtype=self.code, impl=self.impl, **pre)
+        return pre if L.lib().dv_conv_pre_norm_supported(probe) else None
+
+    def _cross_attention_takes_norm(self, m, hact, P):
+        return False
+
+    def _block_convs(self, blk: _Block, src_list, wpacked, rows, Co, n_img, h, w, G, pre=None):
         """Block3D.project (:107,124) [+ the extension's (3,1,1) frame conv]; the LAST conv accumulates the
         GroupNorm statistics.  Returns (activation, statistics slot)."""
         st = self._next_stats()
         temporal = getattr(blk, "temporal", None)
         a = self._new_act(rows, Co)
         self._conv(src_list, self._w(wpacked), self._f32(blk.project.bias), a.ptr, Co, n_img, h, w, k=3,
-                   stats=None if temporal is not None else st, groups=G)
+                   stats=None if temporal is not None else st, groups=G, pre=pre)
         if temporal is None:
             return a, st
         b = self._new_act(rows, Co)
@@ -952,8 +984,9 @@ class _Engine:
     def _ss_off(self, m):
         return self._ss_offsets[id(m)]
 
-    def _cross_attention(self, m: _ResBlock, hact: _Act, rows, P):
-        """h = CrossAttention(h, ctx) + h (:192-201), in place on `hact`."""
+    def _cross_attention(self, m: _ResBlock, hact: _Act, rows, P, pre_norm=None):
+        """h = CrossAttention(h, ctx) + h (:192-201), in place on `hact`.  `pre_norm`: the block's first GroupNorm /
+        scale-shift / SiLU has NOT been applied to `hact` yet and is this kernel's job (_cross_attention_takes_norm)."""
         ca = m.cross_attn
         C, heads, dh = hact.C, ca.heads, ca.dim_head
         inner = heads * dh

@@ -195,8 +195,28 @@ typedef struct {
   int out_coff;       /* first output channel inside the row */
   dv_dtype dtype;     /* activations + weights */
   int impl;
+  /* Fused K2 on the LOAD path (optional; pre_stats == NULL: off).  src0 is then the RAW output of the previous
+   * convolution and the kernel applies that Block3D's GroupNorm finalize + `x * (scale + 1) + shift` + SiLU
+   * (:125-131) while it brings the activation window into shared memory:
+   *   src0'[n][y][x][c] = SiLU( ((src0 - mean_g) * rstd_g * gamma_c + beta_c) * (1 + scale_bc) + shift_bc )
+   * with (mean, rstd) from pre_stats = double[B][pre_groups][2] (sum, sum of squares over the sample's C0/groups x
+   * positions, as dv_conv_igemm / dv_gn_stats accumulate them).  The zero padding of the convolution is applied AFTER
+   * the transform, as in the reference (the conv pads the normalised tensor).  Removes one dv_gn_apply pass (an HBM read
+   * + write of the tensor) when the normalised tensor has this convolution as its only consumer — block1 -> block2 of a
+   * ResnetBlock3D without cross-attention (:172-205).  Only the streaming-halo kernel takes it:
+   * dv_conv_pre_norm_supported(p) tells; dv_conv_igemm returns DV_EUNSUPPORTED otherwise (never silently ignores it). */
+  const double* pre_stats;
+  const float* pre_gamma;  /* [C0] */
+  const float* pre_beta;   /* [C0] */
+  const float* pre_scale;  /* element (b,c) at pre_scale[b*pre_ss_ld + c], or NULL (then pre_shift NULL too) */
+  const float* pre_shift;
+  int pre_ss_ld;
+  int pre_groups;
+  float pre_eps;
 } dv_conv_params;
 int dv_conv_igemm(const dv_conv_params* p, dv_stream_t stream);
+/* 1 if dv_conv_igemm(impl=auto) accepts these params WITH the fused input GroupNorm (pre_* fields set) */
+int dv_conv_pre_norm_supported(const dv_conv_params* p);
 /* 1 if dv_conv_igemm(impl=auto) would take the tcgen05 path for these params */
 int dv_conv_uses_tcgen05(const dv_conv_params* p);
 

@@ -102,10 +102,14 @@ def test_config3_full_size_text_and_guidance_matches_oracle(layouts, dtype, tol)
     assert rel_err(got, want) < (tol if dtype == torch.float32 else 2 * tol)
 
 
-def test_bench_batch_rows_equal_small_batch_rows_bf16(layouts):
+def test_bench_batch_rows_against_small_batches_and_oracle_bf16(layouts):
     """B = 64 (the bench's batch: 4.2 M positions per 64² layer, the padded 32-bit index space of conv_halo, two-source
-    convs, flat-grid GroupNorm apply) against the same rows run two at a time."""
-    u, _ = make(CONFIG2, layouts["config2"])
+    convs, flat-grid GroupNorm apply) against the same rows run two at a time, and rows 0 / 63 against the fp32 oracle.
+    bf16 forwards are not bit-reproducible: the GroupNorm partial sums are fp32 shared-memory atomics whose order varies,
+    a 1e-7 change of a statistic flips a few bf16 roundings and those flips grow to the bf16 noise floor within a few
+    layers — measured run-to-run 5e-3 at ANY batch (tools/diag/batch_rows.py), the same size as bf16-vs-fp32.  An
+    indexing error at large batch is an O(1) difference; the convolution itself is checked bit-for-bit below."""
+    u, sd = make(CONFIG2, layouts["config2"])
     u.compute_dtype = torch.bfloat16
     B = 64
     g = torch.Generator(device="cuda").manual_seed(31)
@@ -119,8 +123,52 @@ def test_bench_batch_rows_equal_small_batch_rows_bf16(layouts):
         small = u(x[lo:lo + 2], t[lo:lo + 2], video_embed=emb[lo:lo + 2])
         worst = max(worst, rel_err(big[lo:lo + 2], small))
     print(f"B=64 rows vs B=2 rows, bf16: worst pair rel-err {worst:.3e}")
-    # same kernels, same arithmetic per sample; only the order of the fp64 GroupNorm partial sums differs
-    assert worst < 2e-3, worst
+    assert worst < 2e-2, worst
+    for row in (0, B - 1):
+        with torch.no_grad():
+            ref = unet3d_forward(sd, UnetConfig(**CONFIG2), x[row:row + 1].cpu(), t[row:row + 1].cpu(),
+                                 video_embed=emb[row:row + 1].cpu())
+        err = rel_err(big[row:row + 1], ref)
+        print(f"B=64 row {row} vs fp32 oracle: {err:.3e}")
+        assert err < BF16_TOL, (row, err)
+
+
+@pytest.mark.parametrize("cin", [(64,), (64, 64)])
+def test_conv_halo_at_the_bench_batch_is_bit_equal_to_small_batches(cin):
+    """The dominant kernel at the bench's size: 3x3 (64 | 64+64) -> 64 at 64x64, 64 videos x 16 frames = 4.2 M output
+    positions in one launch, against the same convolution launched on 2 videos at a time.  The convolution has no
+    order-dependent arithmetic (one accumulator per output, fixed K order), so the outputs must be IDENTICAL; the
+    GroupNorm partial sums (fp32 / fp64 atomics) agree to rounding."""
+    import math
+    from dalle2_video_b200 import _lib as L
+    from gpu_util import conv
+    B, T, H, W, Co, G = 64, FRAMES, SIZE, SIZE, 64, 8
+    rows = B * T * H * W
+    g = torch.Generator(device="cuda").manual_seed(5)
+    xs = [torch.randn(rows, c, device="cuda", generator=g).to(torch.bfloat16) for c in cin]
+    ctot = sum(cin)
+    wp = (torch.randn(Co, 9 * ctot, device="cuda", generator=g) / math.sqrt(9 * ctot)).to(torch.bfloat16)
+    bias = torch.randn(Co, device="cuda", generator=g)
+    out = torch.zeros(rows, Co, dtype=torch.bfloat16, device="cuda")
+    stats = torch.zeros(B, G, 2, dtype=torch.float64, device="cuda")
+    p = conv(xs, wp, bias, out, n_img=B * T, frames=T, H=H, W=W, k=3, stats=stats, groups=G)
+    assert L.lib().dv_conv_uses_tcgen05(p)
+    per = rows // B
+    small = torch.zeros(2 * per, Co, dtype=torch.bfloat16, device="cuda")
+    st2 = torch.zeros(2, G, 2, dtype=torch.float64, device="cuda")
+    for lo in range(0, B, 2):
+        small.zero_()
+        st2.zero_()
+        conv([a[lo * per:(lo + 2) * per] for a in xs], wp, bias, small, n_img=2 * T, frames=T, H=H, W=W, k=3, stats=st2,
+             groups=G)
+        assert torch.equal(out[lo * per:(lo + 2) * per], small), lo
+        assert float(((stats[lo:lo + 2] - st2) / st2.abs().clamp_min(1.0)).abs().max()) < 1e-5, lo
+    # and the first / last video against torch's own convolution in fp32 on the same bf16 operands
+    w4 = wp.float().reshape(Co, 3, 3, ctot).permute(0, 3, 1, 2)
+    for b in (0, B - 1):
+        xin = torch.cat([a[b * per:(b + 1) * per].float() for a in xs], dim=1).reshape(T, H, W, ctot).permute(0, 3, 1, 2)
+        ref = torch.nn.functional.conv2d(xin, w4, bias, padding=1).permute(0, 2, 3, 1).reshape(per, Co)
+        assert rel_err(out[b * per:(b + 1) * per], ref) < 5e-3, b
 
 
 @pytest.fixture(scope="module")

@@ -535,6 +535,75 @@ def test_conv_streaming_halo_matches_conv3d(case):
     assert rel_err(out, out2) < 6e-3
 
 
+PRE_CASES = [
+    dict(B=2, T=3, H=64, W=64, C=64, Co=64, ss=True, stats=True),     # the production shape: block1 -> block2 at 64x64
+    dict(B=3, T=2, H=32, W=32, C=64, Co=64, ss=True, stats=True),     # sample boundaries inside tiles
+    dict(B=1, T=2, H=32, W=32, C=128, Co=128, ss=True, stats=True),   # two K chunks, per-chunk coefficients
+    dict(B=2, T=1, H=16, W=32, C=64, Co=128, ss=False),               # no scale/shift, non-square, N = 128
+    dict(B=1, T=5, H=8, W=32, C=64, Co=64, ss=True, G=64),            # one channel per group; windows span 3 frames
+]
+
+
+@pytest.mark.parametrize("case", PRE_CASES)
+def test_conv_streaming_halo_with_groupnorm_on_the_load_path(case):
+    """dv_conv_params.pre_*: conv3x3(SiLU(GroupNorm(x)*(1+scale)+shift)) in ONE launch (transform warps feed the MMA
+    operand window) against (a) F.group_norm / F.silu / F.conv3d in fp32 and (b) dv_gn_apply followed by the plain
+    streaming-halo convolution — Block3D.forward -> Block3D.project of the next block (dalle2_video.py:112-133, :172-205)."""
+    dtype = torch.bfloat16
+    B, T, H, W, C, Co = (case[x] for x in ("B", "T", "H", "W", "C", "Co"))
+    G = case.get("G", 8)
+    P, rows = T * H * W, B * T * H * W
+    x = rnd(rows, C, dtype=dtype, seed=1, scale=1.7) + 0.3
+    gamma, beta = rnd(C, seed=2) * 0.2 + 1, rnd(C, seed=3) * 0.2
+    ss = rnd(B, 2 * C + 8, seed=4) * 0.3
+    stats_in = torch.zeros(B, G, 2, dtype=torch.float64, device=dev())
+    L.call("dv_gn_stats", L.GnStatsParams(x=ptr(x), stats=ptr(stats_in), B=B, P=P, C=C, groups=G, dtype=code(x)), stream())
+    wp = rnd(Co, 9 * C, seed=20, scale=1 / math.sqrt(C * 9)).to(dtype)
+    bias = rnd(Co, seed=21)
+    scale_ptr = ss.data_ptr() + 16 if case["ss"] else None
+    shift_ptr = ss.data_ptr() + 16 + 4 * C if case["ss"] else None
+    pre = dict(pre_stats=ptr(stats_in), pre_gamma=ptr(gamma), pre_beta=ptr(beta), pre_scale=scale_ptr, pre_shift=shift_ptr,
+               pre_ss_ld=2 * C + 8, pre_groups=G, pre_eps=1e-5)
+    stats = torch.zeros(B, 8, 2, dtype=torch.float64, device=dev()) if case.get("stats") else None
+    out = torch.full((rows, Co), 9.0, dtype=dtype, device=dev())
+    p = conv([x], wp, bias, out, n_img=B * T, frames=T, H=H, W=W, k=3, stats=stats, groups=8, pre=pre)
+    assert L.lib().dv_conv_pre_norm_supported(p)
+    # (a) fp32 statement of the reference ops
+    y = F.group_norm(cl_to_ncdhw(x, B, T, H, W), G, gamma, beta, eps=1e-5)
+    if case["ss"]:
+        sc, sh = ss[:, 4:4 + C], ss[:, 4 + C:4 + 2 * C]
+        y = y * (sc[:, :, None, None, None] + 1) + sh[:, :, None, None, None]
+    y = F.silu(y)
+    w_ref = wp.float().reshape(Co, 3, 3, C).permute(0, 3, 1, 2)[:, :, None]
+    ref = ncdhw_to_cl(F.conv3d(y, w_ref, bias, padding=(0, 1, 1)))
+    assert rel_err(out, ref) < 1e-2, rel_err(out, ref)
+    # (b) the two-launch form it replaces
+    xa = torch.empty_like(x)
+    L.call("dv_gn_apply", L.GnApplyParams(x=ptr(x), out=ptr(xa), residual=None, stats=ptr(stats_in), gamma=ptr(gamma),
+                                          beta=ptr(beta), scale=scale_ptr, shift=shift_ptr, ss_ld=2 * C + 8, B=B, P=P, C=C,
+                                          groups=G, eps=1e-5, dtype=code(x)), stream())
+    out2 = torch.empty_like(out)
+    stats2 = torch.zeros_like(stats) if stats is not None else None
+    conv([xa], wp, bias, out2, n_img=B * T, frames=T, H=H, W=W, k=3, stats=stats2, groups=8, impl=3)
+    assert rel_err(out, out2) < 6e-3, rel_err(out, out2)
+    if stats is not None:
+        assert rel_err(stats[..., 1], stats2[..., 1]) < 2e-3
+        assert float((stats[..., 0] - stats2[..., 0]).abs().max()) < 2e-2 * float(stats2[..., 1].max().sqrt())
+
+
+def test_conv_pre_norm_is_refused_where_no_kernel_applies_it():
+    """The fused input GroupNorm is never silently dropped: shapes outside the streaming-halo kernel are an error."""
+    x = rnd(2 * 8 * 8, 256, dtype=torch.bfloat16, seed=1)
+    wp = rnd(256, 9 * 256, seed=2, scale=0.02).to(torch.bfloat16)
+    out = torch.empty(2 * 8 * 8, 256, dtype=torch.bfloat16, device=dev())
+    st = torch.zeros(1, 8, 2, dtype=torch.float64, device=dev())
+    g = rnd(256, seed=3)
+    pre = dict(pre_stats=ptr(st), pre_gamma=ptr(g), pre_beta=ptr(g), pre_scale=None, pre_shift=None, pre_ss_ld=0, pre_groups=8,
+               pre_eps=1e-5)
+    with pytest.raises(L.DvError):
+        conv([x], wp, None, out, n_img=2, frames=2, H=8, W=8, k=3, pre=pre)
+
+
 @pytest.mark.parametrize("C,P,B,n_ctx", [(64, 256, 2, 6), (128, 1024, 1, 6), (256, 384, 3, 6), (64, 128, 2, 2)])
 def test_fused_folded_cross_attention_block(C, P, B, n_ctx):
     """dv_xattn_fold_prep + dv_xattn_fold == CrossAttention(x, ctx) + x of the reference (dalle2_video.py:192-201)."""
