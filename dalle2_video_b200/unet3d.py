@@ -728,6 +728,21 @@ class _Engine:
         x0 = self._new_act(rows, u.init_dim)
         if isinstance(u.init_conv, _CrossEmbed) and self._init_conv_as_gemm(x0, n_img, H, W):
             pass
+        elif isinstance(u.init_conv, _CrossEmbed) and any(c.weight.shape[0] % 4 for c in u.init_conv.convs):
+            # channel slices narrower than the 4-channel store vector (dim 8 of the shipped super-resolution unet: 4 + 2 + 2,
+            # configs/celebv-text.yaml:55-57): the 3x3 / 7x7 windows are centred sub-windows of the largest one, so the layer
+            # is ONE convolution with the smaller filters zero-padded (same sums, a few more zero products)
+            convs, ks = list(u.init_conv.convs), list(u.init_conv.kernel_sizes)
+            kmax, ci = max(ks), convs[0].weight.shape[1]
+            wfull = torch.zeros(u.init_dim, ci, 1, kmax, kmax)
+            co0 = 0
+            for conv, k in zip(convs, ks):
+                co, o = conv.weight.shape[0], (kmax - k) // 2
+                wfull[co0:co0 + co, :, :, o:o + k, o:o + k] = conv.weight.detach().cpu()
+                co0 += co
+            self._conv([(self._x_src().data_ptr(), ci)], self._w(self._pack_conv(wfull)),
+                       self._f32(torch.cat([c.bias.detach().cpu() for c in convs])), x0.ptr, u.init_dim, n_img, H, W, k=kmax,
+                       mode=L.CONV_NCDHW_F32_IN)
         elif isinstance(u.init_conv, _CrossEmbed):
             coff = 0
             for conv, k in zip(u.init_conv.convs, u.init_conv.kernel_sizes):

@@ -62,6 +62,8 @@ def test_training_loss_and_gradients_match_oracle_autograd(case):
     assert not missing, missing
     num = den = 0.0
     worst = (1.0, None)
+    total = sum(float(rg.pow(2).sum()) for rg in ref_grads.values()) ** 0.5
+    ratios = []
     for k, rg in ref_grads.items():
         gg = got[k].float().cpu()
         assert gg.shape == rg.shape, k
@@ -71,8 +73,14 @@ def test_training_loss_and_gradients_match_oracle_autograd(case):
             cos = float(F.cosine_similarity(gg.flatten(), rg.flatten(), dim=0))
             if cos < worst[0]:
                 worst = (cos, k)
+        if float(rg.norm()) > 1e-3 * total:   # every tensor that carries a visible share of the gradient
+            ratios.append((float(gg.norm() / rg.norm()), k))
     assert worst[0] >= 0.98, worst
     assert (num / den) ** 0.5 < 8e-2, (num / den) ** 0.5
+    # a mis-scaled tensor (a dropped factor in one backward kernel) keeps its cosine: bound every tensor's norm as well
+    lo, hi = min(ratios), max(ratios)
+    print(f"{case}: total rel-L2 {(num / den) ** 0.5:.3e}, worst cosine {worst}, norm ratio range {lo} .. {hi} over {len(ratios)} tensors")
+    assert 0.85 < lo[0] and hi[0] < 1.15, (lo, hi)
 
 
 def test_dropped_video_conditioning_routes_gradients_to_the_null_embeddings():

@@ -25,9 +25,24 @@ def describe(name, p):
         return f"xattn P{p.P} nctx{p.n_ctx}"
     if name == "dv_attn_mqa":
         return f"attn_mqa n{p.n} S{p.S}"
+    if name == "dv_xattn_fold":
+        return f"xattn_fold P{p.P} C{p.C} nk{p.nk}"
     if name == "dv_linear_small":
         return f"linear_small M{p.M1 * p.M2} N{p.N} K{p.K}"
     return name
+
+
+def hbm_bytes(name, p, B):
+    """Algorithmic HBM bytes of the bandwidth-bound ops (bf16 / fp32 element size from the op's dtype field)."""
+    if name == "dv_gn_apply":
+        esz = 2 if p.dtype == L.DV_BF16 else 4
+        return p.B * p.P * p.C * esz * (3 if p.residual else 2)
+    if name == "dv_xattn_fold":
+        return p.B * p.P * p.C * 2 * 2
+    if name == "dv_layernorm":
+        esz = 2 if p.dtype == L.DV_BF16 else 4
+        return p.rows * p.C * esz * (3 if p.residual else 2)
+    return 0
 
 
 def main():
@@ -48,7 +63,7 @@ def main():
     eng.x_in.normal_()
     eng.time_in.fill_(500)
     stream = torch.cuda.current_stream().cuda_stream
-    acc = defaultdict(lambda: [0, 0.0, 0.0])
+    acc = defaultdict(lambda: [0, 0.0, 0.0, 0.0])
     for it in range(a.iters + 1):
         evs = []
         eng.stats.zero_()
@@ -67,15 +82,20 @@ def main():
             acc[k][1] += e0.elapsed_time(e1)
             if name == "dv_conv_igemm":
                 acc[k][2] += bench.conv_flops(p)
+            hbm = hbm_bytes(name, p, B)
+            if hbm:
+                acc[k][3] += hbm
     rows = []
     total = sum(v[1] for v in acc.values()) / a.iters
-    for k, (n, ms, fl) in sorted(acc.items(), key=lambda kv: -kv[1][1]):
+    for k, (n, ms, fl, by) in sorted(acc.items(), key=lambda kv: -kv[1][1]):
         ms_step = ms / a.iters
         tf = fl / (ms * 1e-3) / 1e12 if fl else 0.0
-        rows.append(dict(op=k, launches=n // a.iters, ms_per_step=ms_step, share=ms_step / total, tflops=tf))
+        rows.append(dict(op=k, launches=n // a.iters, ms_per_step=ms_step, share=ms_step / total, tflops=tf,
+                         algorithmic_tb_per_s=by / (ms * 1e-3) / 1e12 if by else 0.0))
     print(f"total {total:.3f} ms per forward at batch {B} ({total / B:.3f} ms/sample)")
     for r in rows:
-        print(f"{r['ms_per_step']:8.3f} ms {100 * r['share']:5.1f}%  x{r['launches']:<3d} {r['tflops']:7.1f} TF  {r['op']}")
+        rate = f"{r['tflops']:7.1f} TF" if r["tflops"] else (f"{r['algorithmic_tb_per_s']:5.2f} TB/s" if r["algorithmic_tb_per_s"] else " " * 10)
+        print(f"{r['ms_per_step']:8.3f} ms {100 * r['share']:5.1f}%  x{r['launches']:<3d} {rate}  {r['op']}")
     if a.json:
         json.dump(dict(batch=B, dtype=a.dtype, total_ms=total, rows=rows), open(a.json, "w"), indent=1)
 
