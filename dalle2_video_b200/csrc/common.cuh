@@ -96,6 +96,14 @@ __device__ __forceinline__ float ex2_ftz(float x) {
 }
 
 __device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
+// SiLU of 2h from h: x*sigmoid(x) = h*tanh(h) + h with h = x/2 — ONE MUFU op per element instead of two (ex2 + rcp).
+// tanh.approx.f32 is good to 2^-11 relative: below the 2^-9 rounding of a bf16 result, not of a float32 one, so only the
+// bf16 streaming kernels use it (the MUFU pipe, 16 ops/clk/SM, is what holds them below the HBM rate).
+__device__ __forceinline__ float silu_from_half_arg(float h) {
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+  return fmaf(h, t, h);
+}
 __device__ __forceinline__ float gelu_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 
 __device__ __forceinline__ float warp_sum(float v) {

@@ -715,16 +715,18 @@ conv_halo_pre_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_co
 static int halo_nr(int Wp) { return (HL_TILE_Q + 2 * Wp + 2 + Wp - 2) / Wp + 1; }
 
 static size_t halo_smem(int Wp, int BN, int n_chunks, int* a_stage_bytes, int* a_stages, int* b_stages, int* out_bufs,
-                        int* resident, bool pre = false) {
+                        int* resident, bool pre = false, bool staging = true) {
   const int a = (halo_nr(Wp) * Wp * 128 + 1023) / 1024 * 1024;
   const int bstage = 3 * BN * 128;
   const int limit = 227 * 1024 - 1024;  // minus alignment slack
   const int misc = 2 * 128 * 8 + 128 * 4 + 64 * 4 + 1024 + (pre ? 1024 : 0);
   // two activation-window stages (measured: a third does not help), double-buffered output staging when it fits,
   // the rest for weight stages (one stage = three taps); if ALL weights fit they are loaded once and stay resident
-  int as = 2, ob = 2;
+  // (the direct-store epilogue without tap pairing never touches the staging area: its 32 KB go to the weights, which
+  // makes the 64 -> 64 @64x64 layers weight-resident — no per-tile weight traffic from L2, no weight barriers)
+  int as = 2, ob = staging ? 2 : 0;
   int bs = (limit - as * a - ob * 16384 - misc) / bstage;
-  if (bs < 2) { ob = 1; bs = (limit - as * a - ob * 16384 - misc) / bstage; }
+  if (bs < 2 && ob == 2) { ob = 1; bs = (limit - as * a - ob * 16384 - misc) / bstage; }
   *resident = bs >= 3 * n_chunks;
   if (*resident) bs = 3 * n_chunks;
   if (bs > 6 && !*resident) bs = 6;
@@ -769,8 +771,18 @@ int conv_halo_launch(const dv_conv_params& p, cudaStream_t s) {
   h.BN = p.Cout;
   h.NR = halo_nr(h.Wp);
   const bool pre = p.pre_stats != nullptr;
+  static int pr = -1, ds = -1, res_w = -1;
+  if (pr < 0) { const char* e = getenv("DV_HALO_PAIR"); pr = e ? atoi(e) : 1; }   // 0 off, 1 auto, 2 every BN = 64 layer
+  if (ds < 0) { const char* e = getenv("DV_HALO_DIRECT_STORE"); ds = e ? (atoi(e) != 0) : 1; }
+  if (res_w < 0) { const char* e = getenv("DV_HALO_NO_STAGING"); res_w = e ? (atoi(e) != 0) : 1; }
+  // tap pairing needs the 32 KB staging area as its exchange buffer, i.e. the direct-store epilogue.  Measured at B=32
+  // (tools/halo_profile.py): the MMA warp's time per tile drops 5020 -> 4450 cycles, but the epilogue grows (exchange,
+  // two barriers, twice the TMEM reads) to ~7500 per tile — so it only pays where the MMA work per tile is at least
+  // doubled, i.e. >= 2 input chunks (128 -> 64 @64x64: 1.38 -> 1.27 ms); one-chunk layers keep the plain issue order
+  const bool want_pair = pr && ds && p.Cout == 64 && (pr >= 2 || h.c0_chunks + h.c1_chunks >= 2);
+  const bool staging = !ds || want_pair || !res_w;
   const size_t smem = halo_smem(h.Wp, h.BN, h.c0_chunks + h.c1_chunks, &h.a_stage_bytes, &h.a_stages, &h.b_stages,
-                                &h.out_bufs, &h.b_resident, pre);
+                                &h.out_bufs, &h.b_resident, pre, staging);
   if (pre) {
     h.pre_src = reinterpret_cast<const __nv_bfloat16*>(p.src0);
     h.pre_stats = p.pre_stats; h.pre_gamma = p.pre_gamma; h.pre_beta = p.pre_beta;
@@ -779,17 +791,8 @@ int conv_halo_launch(const dv_conv_params& p, cudaStream_t s) {
     if (const char* e = getenv("DV_HALO_PRE_DEBUG")) h.pre_debug = atoi(e);
   }
   const int64_t span = ((int64_t)p.frames * h.Hp1 - 2) * h.Wp + p.W;
-  {
-    static int pr = -1, ds = -1;
-    if (pr < 0) { const char* e = getenv("DV_HALO_PAIR"); pr = e ? atoi(e) : 1; }   // 0 off, 1 auto, 2 every BN = 64 layer
-    if (ds < 0) { const char* e = getenv("DV_HALO_DIRECT_STORE"); ds = e ? (atoi(e) != 0) : 1; }
-    h.direct_store = ds;
-    // tap pairing needs the 32 KB staging area as its exchange buffer, i.e. the direct-store epilogue.  Measured at B=32
-    // (tools/halo_profile.py): the MMA warp's time per tile drops 5020 -> 4450 cycles, but the epilogue grows (exchange,
-    // two barriers, twice the TMEM reads) to ~7500 per tile — so it only pays where the MMA work per tile is at least
-    // doubled, i.e. >= 2 input chunks (128 -> 64 @64x64: 1.38 -> 1.27 ms); one-chunk layers keep the plain issue order
-    h.pair = pr && ds && p.Cout == 64 && h.out_bufs == 2 && (pr >= 2 || h.c0_chunks + h.c1_chunks >= 2);
-  }
+  h.direct_store = ds;
+  h.pair = want_pair && h.out_bufs == 2;
   const int stride = h.pair ? HL_TILE_Q - 1 : HL_TILE_Q;
   h.tiles_per_sample = (int)((span + stride - 1) / stride);
   h.total_tiles = (p.n_img / p.frames) * h.tiles_per_sample;

