@@ -49,7 +49,8 @@ class ConvParams(C.Structure):
                 ("kh", i32), ("kw", i32), ("pad", i32), ("mode", i32), ("epilogue", i32), ("groups", i32),
                 ("out_ld", i32), ("out_coff", i32), ("dtype", i32), ("impl", i32),
                 ("pre_stats", vp), ("pre_gamma", vp), ("pre_beta", vp), ("pre_scale", vp), ("pre_shift", vp),
-                ("pre_ss_ld", i32), ("pre_groups", i32), ("pre_eps", f32)]
+                ("pre_ss_ld", i32), ("pre_groups", i32), ("pre_eps", f32),
+                ("add_stats", vp), ("add_gamma", vp), ("add_beta", vp), ("add_groups", i32), ("add_eps", f32)]
 
 
 class GnApplyParams(C.Structure):
@@ -249,7 +250,7 @@ ENTRY_POINTS = {
     "dv_to_out_bwd": ToOutBwdParams, "dv_silu_shuffle": SiluShuffleParams, "dv_silu_shuffle_bwd": SiluShuffleParams,
     "dv_add": AddParams, "dv_cast_f32_bf16": CastParams, "dv_sumsq": SumsqParams, "dv_adamw": AdamwParams,
 }
-PLAIN_SYMBOLS = ("dv_version", "dv_last_error_string", "dv_device_sm_count", "dv_conv_uses_tcgen05", "dv_conv_pre_norm_supported",
+PLAIN_SYMBOLS = ("dv_version", "dv_last_error_string", "dv_device_sm_count", "dv_conv_uses_tcgen05", "dv_conv_pre_norm_supported", "dv_conv_add_norm_supported",
                  "dv_attn_mqa_workspace_bytes", "dv_xattn_core_workspace_bytes", "dv_conv_wgrad_uses_tcgen05", "dv_attn_temporal_uses_mma", "dv_attn_mqa_bwd_workspace_bytes", "dv_init_conv_supported",
                  "dv_x0_threshold_workspace_bytes")
 
@@ -285,6 +286,8 @@ def lib():
         _lib.dv_conv_uses_tcgen05.restype = i32
         _lib.dv_conv_pre_norm_supported.argtypes = [C.POINTER(ConvParams)]
         _lib.dv_conv_pre_norm_supported.restype = i32
+        _lib.dv_conv_add_norm_supported.argtypes = [C.POINTER(ConvParams)]
+        _lib.dv_conv_add_norm_supported.restype = i32
         _lib.dv_attn_mqa_workspace_bytes.argtypes = [C.POINTER(AttnMqaParams)]
         _lib.dv_attn_mqa_workspace_bytes.restype = i64
         _lib.dv_conv_wgrad_uses_tcgen05.argtypes = [C.POINTER(ConvWgradParams)]

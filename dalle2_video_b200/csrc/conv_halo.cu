@@ -739,7 +739,7 @@ static size_t halo_smem(int Wp, int BN, int n_chunks, int* a_stage_bytes, int* a
 
 int conv_halo_supported(const dv_conv_params& p) {
   if (p.dtype != DV_BF16 || p.mode != DV_CONV_NORMAL || p.kh != 3 || p.kw != 3 || p.pad != 1) return 0;
-  if (p.epilogue != DV_EPI_STORE || (p.add && p.stats)) return 0;
+  if (p.epilogue != DV_EPI_STORE || (p.add && p.stats) || p.add_stats) return 0;
   if (p.Cout != 64 && p.Cout != 128) return 0;
   if (p.C0 % TC_BK || p.C1 % TC_BK) return 0;
   if (p.W < 32 || p.W > 128 || p.H < 8) return 0;

@@ -313,6 +313,16 @@ extern "C" int dv_conv_pre_norm_supported(const dv_conv_params* pin) {
   return dv::halo_enabled() && dv::conv_halo_supported(q);
 }
 
+extern "C" int dv_conv_add_norm_supported(const dv_conv_params* pin) {
+  dv::ConvGeom g;
+  if (!pin || !pin->add_stats) return 0;
+  dv_conv_params q = *pin;
+  dv::rewrite_temporal(&q);
+  if (q.impl == 1 || q.impl == 3 || dv::validate_conv(&q, &g) != DV_OK) return 0;
+  if (q.impl == 0 && dv::halo_enabled() && dv::conv_halo_supported(q)) return 0;
+  return dv::conv_tc_supported(q);
+}
+
 extern "C" int dv_conv_igemm(const dv_conv_params* pin, dv_stream_t stream) {
   using namespace dv;
   ConvGeom g;
@@ -336,5 +346,8 @@ extern "C" int dv_conv_igemm(const dv_conv_params* pin, dv_stream_t stream) {
              "dv_conv_igemm: the fused input GroupNorm (pre_stats) needs the streaming-halo kernel (3x3, one bf16 source of "
              "64 / 128 channels, Cout 64 / 128, W >= 32); ask dv_conv_pre_norm_supported first");
   if (tc_ok && p.impl != 1) return conv_tc_launch(p, s);
+  DV_REQUIRE(!p.add_stats, DV_EUNSUPPORTED,
+             "dv_conv_igemm: the fused GroupNorm of the residual operand (add_stats) needs the per-tap tcgen05 kernel "
+             "(bf16, channel counts that are multiples of 64, 128-row tiles); ask dv_conv_add_norm_supported first");
   return (p.dtype == DV_F32) ? launch_simt<float>(p, g, s) : launch_simt<__nv_bfloat16>(p, g, s);
 }

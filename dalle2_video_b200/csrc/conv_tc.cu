@@ -26,6 +26,8 @@ constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;  // warp 0: TMA producer, war
 constexpr int TC_SLAB_BYTES = TC_BM * 128;           // one 128-row x 64-column bf16 output slab
 constexpr int TC_PIPE_BYTES = 192 * 1024;            // operand pipeline: 8 / 6 / 4 stages for BN = 64 / 128 / 256
 constexpr int TC_TAIL_BYTES = 2 * TC_SLAB_BYTES + 1024 /*bias*/ + 1024 /*barriers, tmem slot, partials*/;
+constexpr int TC_COEF_BYTES = 2048;                  // add_norm only: [2][256] half-coefficients of the residual's GroupNorm
+constexpr int TC_ADD_RING = 3;                       // add_norm only: slabs of the residual operand in flight (TMA ring)
 
 struct TcParams {
   // problem
@@ -43,6 +45,13 @@ struct TcParams {
   __nv_bfloat16* out;
   double* stats;
   int groups, epilogue, out_ld, out_coff;
+  // GroupNorm + SiLU of the residual operand (dv_conv_params.add_*): add_stats == nullptr: plain add
+  const double* add_stats;
+  const float* add_gamma;
+  const float* add_beta;
+  int add_groups;
+  float add_eps;
+  int add_ring;  // TC_ADD_RING when the residual operand comes in through the TMA ring (add_stats), else 0
 };
 
 // ------------------------------------------------------------------------------------------ the kernel
@@ -50,13 +59,15 @@ __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: 
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
-               const __grid_constant__ CUtensorMap map_b, const __grid_constant__ CUtensorMap map_out, const TcParams p) {
+               const __grid_constant__ CUtensorMap map_b, const __grid_constant__ CUtensorMap map_out,
+               const __grid_constant__ CUtensorMap map_add, const TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // carve: [stages x (A 16 KB | B BN*128 B)] [2 x 16 KB output slabs] [bias BN floats] [barriers ...]
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const uint32_t a_bytes = TC_BM * TC_BK * 2, b_bytes = (uint32_t)p.BN * TC_BK * 2;
   const uint32_t stage_bytes = a_bytes + b_bytes;
-  uint8_t* slab = smem + (size_t)p.stages * stage_bytes;            // 2 x (128 rows x 128 B), SWIZZLE_128B
+  uint8_t* add_ring = smem + (size_t)p.stages * stage_bytes;        // add_ring x (128 rows x 128 B), SWIZZLE_128B
+  uint8_t* slab = add_ring + (size_t)p.add_ring * TC_SLAB_BYTES;    // 2 x (128 rows x 128 B), SWIZZLE_128B
   float* bias_s = reinterpret_cast<float*>(slab + 2 * TC_SLAB_BYTES);  // [256]
   uint64_t* bars = reinterpret_cast<uint64_t*>(bias_s + 256);
   uint64_t* full_bar = bars;                 // [stages]
@@ -65,6 +76,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
   uint64_t* tmem_empty = tmem_full + 2;      // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
   float* sred = reinterpret_cast<float*>(tmem_slot + 2);  // [64] GroupNorm partials: [group-in-tile][2]
+  uint64_t* add_full = reinterpret_cast<uint64_t*>(sred + 64);  // [TC_ADD_RING]
+  float* coef_s = bias_s + 512;                           // add_norm: [2][256], after the 1 KB bias and 1 KB barrier regions
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t tmem_cols = (uint32_t)(2 * p.BN);  // 128 / 256 / 512: a power of two >= 32
@@ -74,6 +87,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     tma_prefetch_desc(&map_a1);
     tma_prefetch_desc(&map_b);
     tma_prefetch_desc(&map_out);
+    if (p.add_ring) tma_prefetch_desc(&map_add);
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -82,6 +96,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
       mbar_init(&tmem_full[a], 1);
       mbar_init(&tmem_empty[a], TC_EPI_WARPS);  // one arrival per epilogue warp
     }
+    for (int a = 0; a < TC_ADD_RING; ++a) mbar_init(&add_full[a], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -180,7 +195,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     const bool issuer = (et == 0);
     int acc = 0;
     uint32_t acc_phase = 0;
-    int cur_sample = -1, last_n_tile = -1, bias_n_tile = -1;
+    int cur_sample = -1, last_n_tile = -1, bias_n_tile = -1, coef_sample = -1;
     int slab_idx = 0;  // running slab counter -> staging buffer parity
     const int cpg = p.stats ? p.Cout / p.groups : 8;
     auto flush_stats = [&](int sample, int n_tile) {
@@ -193,26 +208,62 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
       }
       epi_bar();
     };
-    for (int64_t tile = tile_begin; tile < tile_end; ++tile) {
-      const int64_t m_tile = tile / p.n_tiles_n;
-      const int n_tile = (int)(tile % p.n_tiles_n);
-      const int64_t row0 = m_tile * TC_BM;
-      const int64_t row = row0 + row_in_tile;
-      const int sample = (int)(row0 / p.rows_per_sample);
+    // Residual operand with its GroupNorm (add_stats): work items = (tile, 64-column slab) in processing order; the
+    // [128 rows][64 channels] box of item i + TC_ADD_RING is brought into the ring slot of item i by TMA as soon as every
+    // epilogue thread has read item i — 48 KB of residual loads in flight per SM, no registers held across the wait
+    // (a register prefetch stalls on the rotation of its buffers: measured 1.5 TB/s for this operand, B200).
+    const int spt = p.BN / 64;
+    // (all tile / row indices of the epilogue fit 32 bits: the host checks rows < 2^31)
+    const uint32_t n_items = p.add_ring ? (uint32_t)(tile_end - tile_begin) * (uint32_t)spt : 0u;
+    uint32_t add_item = 0;
+    int add_slot = 0;
+    uint32_t add_phase = 0;
+    auto issue_add = [&](uint32_t item, int slot) {   // issuer thread only
+      if (item < n_items) {
+        const uint32_t t = (uint32_t)tile_begin + item / (uint32_t)spt;
+        const uint32_t mt = t / (uint32_t)p.n_tiles_n;
+        const int col = (int)(t - mt * (uint32_t)p.n_tiles_n) * p.BN + (int)(item % (uint32_t)spt) * 64;
+        mbar_expect_tx(&add_full[slot], TC_SLAB_BYTES);
+        tma_load_2d(&map_add, &add_full[slot], add_ring + (size_t)slot * TC_SLAB_BYTES, col, (int)(mt * TC_BM));
+      }
+    };
+    if (p.add_ring && issuer)
+      for (int a = 0; a < TC_ADD_RING; ++a) issue_add(a, a);
+    const uint32_t rps = (uint32_t)p.rows_per_sample;
+    for (uint32_t tile = (uint32_t)tile_begin; tile < (uint32_t)tile_end; ++tile) {
+      const uint32_t m_tile = tile / (uint32_t)p.n_tiles_n;
+      const int n_tile = (int)(tile - m_tile * (uint32_t)p.n_tiles_n);
+      const uint32_t row0 = m_tile * TC_BM;
+      const int sample = (int)(row0 / rps);
       if (p.stats && cur_sample >= 0 && (sample != cur_sample || n_tile != last_n_tile)) flush_stats(cur_sample, last_n_tile);
       cur_sample = sample;
       last_n_tile = n_tile;
-      if (n_tile != bias_n_tile) {
-        epi_bar();  // previous tile's readers are done with bias_s
+      const bool new_coef = p.add_stats && (sample != coef_sample || n_tile != bias_n_tile);
+      if (n_tile != bias_n_tile || new_coef) {
+        epi_bar();  // previous tile's readers are done with bias_s / coef_s
         if (et < p.BN) bias_s[et] = p.bias ? p.bias[n_tile * p.BN + et] : 0.f;
+        if (new_coef && et < p.BN) {
+          // SiLU(a*x + d) = h*tanh(h) + h with h = x*(a/2) + d/2 (silu_from_half_arg): the halved per-(sample, channel)
+          // coefficients of the residual's GroupNorm, the same arithmetic as gn_apply_kernel
+          const int c = n_tile * p.BN + et;
+          const int cpg_a = p.Cout / p.add_groups;
+          const double cnt = (double)p.rows_per_sample * cpg_a;
+          const double s1 = p.add_stats[((int64_t)sample * p.add_groups + c / cpg_a) * 2 + 0];
+          const double s2 = p.add_stats[((int64_t)sample * p.add_groups + c / cpg_a) * 2 + 1];
+          const double mean = s1 / cnt;
+          double var = s2 / cnt - mean * mean;
+          if (var < 0.0) var = 0.0;
+          const float rstd = (float)(1.0 / sqrt(var + (double)p.add_eps));
+          const float a = rstd * p.add_gamma[c];
+          coef_s[et] = 0.5f * a;
+          coef_s[256 + et] = 0.5f * (p.add_beta[c] - (float)mean * a);
+        }
         epi_bar();
         bias_n_tile = n_tile;
+        coef_sample = sample;
       }
-      // store coordinates of this tile
-      const int img0 = (int)(row0 / ((int64_t)p.Ho * p.Wo));
-      const int rem0 = (int)(row0 % ((int64_t)p.Ho * p.Wo));
-      const int y0 = rem0 / p.Wo, x0 = rem0 % p.Wo;
-      const __nv_bfloat16* arow = p.add ? p.add + row * p.Cout + n_tile * p.BN : nullptr;
+      const __nv_bfloat16* arow =
+          (p.add && !p.add_ring) ? p.add + (int64_t)(row0 + row_in_tile) * p.Cout + n_tile * p.BN : nullptr;
 
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
@@ -284,6 +335,28 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
             for (int e = 0; e < 8; ++e) v[j + e] += a[e];
           }
         }
+        if (p.add_ring) {
+          mbar_wait(&add_full[add_slot], add_phase);
+          const uint8_t* arow_s = add_ring + (size_t)add_slot * TC_SLAB_BYTES + row_in_tile * 128;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint4 raw = *reinterpret_cast<const uint4*>(arow_s + (((wg * 4 + j) ^ (row_in_tile & 7)) * 16));
+            float a[8];
+            load8(reinterpret_cast<const __nv_bfloat16*>(&raw), a);
+            const float4 ca0 = *reinterpret_cast<const float4*>(coef_s + c0 + 8 * j);
+            const float4 ca1 = *reinterpret_cast<const float4*>(coef_s + c0 + 8 * j + 4);
+            const float4 cd0 = *reinterpret_cast<const float4*>(coef_s + 256 + c0 + 8 * j);
+            const float4 cd1 = *reinterpret_cast<const float4*>(coef_s + 256 + c0 + 8 * j + 4);
+            v[8 * j + 0] += silu_from_half_arg(fmaf(a[0], ca0.x, cd0.x));
+            v[8 * j + 1] += silu_from_half_arg(fmaf(a[1], ca0.y, cd0.y));
+            v[8 * j + 2] += silu_from_half_arg(fmaf(a[2], ca0.z, cd0.z));
+            v[8 * j + 3] += silu_from_half_arg(fmaf(a[3], ca0.w, cd0.w));
+            v[8 * j + 4] += silu_from_half_arg(fmaf(a[4], ca1.x, cd1.x));
+            v[8 * j + 5] += silu_from_half_arg(fmaf(a[5], ca1.y, cd1.y));
+            v[8 * j + 6] += silu_from_half_arg(fmaf(a[6], ca1.z, cd1.z));
+            v[8 * j + 7] += silu_from_half_arg(fmaf(a[7], ca1.w, cd1.w));
+          }
+        }
         if (p.epilogue == DV_EPI_SHUFFLE_SILU) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = silu_f(v[j]);
@@ -293,6 +366,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
         uint8_t* sbuf = slab + (slab_idx & 1) * TC_SLAB_BYTES;
         if (issuer) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
         epi_bar();
+        if (p.add_ring) {
+          // every epilogue thread has read this item's residual slab: refill its slot with the item TC_ADD_RING ahead
+          if (issuer) issue_add(add_item + TC_ADD_RING, add_slot);
+          ++add_item;
+          if (++add_slot == TC_ADD_RING) { add_slot = 0; add_phase ^= 1; }
+        }
         {
           // row r of the slab = 128 bytes; 16-byte chunk index is XOR-swizzled with (r % 8)
           uint8_t* srow = sbuf + row_in_tile * 128;
@@ -312,6 +391,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
           const int ncol = n_tile * p.BN + s0;
           if (shuffle_out) {
             // output view (Cq, j, Wo, i, n_img*Ho): columns [ncol, ncol+64) lie inside one (i,j) block
+            const uint32_t hw = (uint32_t)(p.Ho * p.Wo);
+            const int img0 = (int)(row0 / hw);
+            const int rem0 = (int)(row0 - (uint32_t)img0 * hw);
+            const int y0 = rem0 / p.Wo, x0 = rem0 % p.Wo;
             const int cq = p.Cout / 4, qq = ncol / cq, cc = ncol % cq;
             tma_store_5d(&map_out, sbuf, p.out_coff + cc, qq & 1, x0, qq >> 1, img0 * p.Ho + y0);
           } else {
@@ -408,6 +491,7 @@ int conv_tc_supported(const dv_conv_params& p) {
   const int64_t rows = (int64_t)p.n_img * Ho * Wo;
   const int64_t rps = (int64_t)p.frames * Ho * Wo;
   if (rows % TC_BM || rps % TC_BM) return 0;
+  if (rows >= (1ll << 31) || rows / TC_BM * (p.Cout / bn) >= (1ll << 31)) return 0;   // 32-bit tile / row indices in the epilogue
   if (p.epilogue == DV_EPI_SHUFFLE_SILU || p.epilogue == DV_EPI_SHUFFLE) {
     if ((p.Cout / 4) % 64) return 0;
   }
@@ -417,6 +501,12 @@ int conv_tc_supported(const dv_conv_params& p) {
   }
   const int out_ld = p.out_ld ? p.out_ld : (p.epilogue != DV_EPI_STORE ? p.Cout / 4 : p.Cout);
   if (out_ld % 8 || p.out_coff % 8) return 0;
+  if (p.add_stats) {
+    // GroupNorm + SiLU of the residual operand: plain epilogue, statistics of whole groups
+    if (!p.add || !p.add_gamma || !p.add_beta || p.epilogue != DV_EPI_STORE) return 0;
+    if (p.add_groups <= 0 || p.Cout % p.add_groups) return 0;
+    if (bn > 128) return 0;   // the residual ring (48 KB) would leave the N = 256 pipeline two stages
+  }
   return 1;
 }
 
@@ -509,7 +599,11 @@ int conv_tc_launch(const dv_conv_params& p, cudaStream_t s) {
   t.total_tiles = t.m_tiles * t.n_tiles_n;
   t.rows_per_sample = (int64_t)p.frames * Ho * Wo;
   const int stage_bytes = TC_BM * TC_BK * 2 + t.BN * TC_BK * 2;
-  t.stages = TC_PIPE_BYTES / stage_bytes;
+  // the coefficient table of the fused residual GroupNorm comes out of the operand pipeline (the launch already uses
+  // all 227 KB); these launches are HBM-bound 1x1 convolutions, one stage less costs them nothing
+  t.add_ring = p.add_stats ? TC_ADD_RING : 0;
+  const int coef_bytes = p.add_stats ? TC_COEF_BYTES + TC_ADD_RING * TC_SLAB_BYTES : 0;
+  t.stages = (TC_PIPE_BYTES - coef_bytes) / stage_bytes;
   if (t.stages > 8) t.stages = 8;
   t.bias = p.bias;
   t.add = reinterpret_cast<const __nv_bfloat16*>(p.add);
@@ -519,6 +613,8 @@ int conv_tc_launch(const dv_conv_params& p, cudaStream_t s) {
   t.epilogue = p.epilogue;
   t.out_ld = p.out_ld;
   t.out_coff = p.out_coff;
+  t.add_stats = p.add_stats; t.add_gamma = p.add_gamma; t.add_beta = p.add_beta;
+  t.add_groups = p.add_groups; t.add_eps = p.add_eps;
 
   CUtensorMap ma0, ma1, mb;
   int rc = make_act_map(&ma0, p.src0, p.C0, p, g);
@@ -554,6 +650,14 @@ int conv_tc_launch(const dv_conv_params& p, cudaStream_t s) {
     }
     if (rc != DV_OK) return rc;
   }
+  CUtensorMap madd = mo;
+  if (t.add_ring) {
+    uint64_t dims[2] = {(uint64_t)p.Cout, (uint64_t)p.n_img * Ho * Wo};
+    uint64_t strides[1] = {(uint64_t)p.Cout * 2};
+    uint32_t box[2] = {64, TC_BM};
+    rc = encode_map(&madd, p.add, 2, dims, strides, box);
+    if (rc != DV_OK) return rc;
+  }
   static int sm_count = 0;
   if (!sm_count) {
     int dev = 0;
@@ -561,7 +665,7 @@ int conv_tc_launch(const dv_conv_params& p, cudaStream_t s) {
     cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
     if (sm_count <= 0) sm_count = 148;
   }
-  const size_t smem = (size_t)t.stages * stage_bytes + TC_TAIL_BYTES + 1024 /*alignment slack*/;
+  const size_t smem = (size_t)t.stages * stage_bytes + TC_TAIL_BYTES + coef_bytes + 1024 /*alignment slack*/;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -569,7 +673,7 @@ int conv_tc_launch(const dv_conv_params& p, cudaStream_t s) {
     attr_set = true;
   }
   const int grid = (int)(t.total_tiles < sm_count ? t.total_tiles : sm_count);
-  conv_tc_kernel<<<grid, TC_THREADS, smem, s>>>(ma0, ma1, mb, mo, t);
+  conv_tc_kernel<<<grid, TC_THREADS, smem, s>>>(ma0, ma1, mb, mo, madd, t);
   DV_CHECK_LAUNCH("dv_conv_igemm(tcgen05)");
   return DV_OK;
 }

@@ -315,6 +315,9 @@ class Unet3D(nn.Module):
         # standalone dv_gn_apply pass (dv_conv_params.pre_*).  Correct and tested, but OFF by default: measured on B200 the
         # transform warps cost the convolution more than the HBM pass it removes
         self.fuse_input_norm = os.environ.get("DV_FUSE_INPUT_NORM", "0") != "0"
+        # bf16: `h + res_conv(x)` as ONE launch — block2's GroupNorm + SiLU is applied to h in res_conv's epilogue
+        # (dv_conv_params.add_*) instead of a res_conv launch + a dv_gn_apply(+residual) pass
+        self.fuse_residual_norm = os.environ.get("DV_FUSE_RESIDUAL_NORM", "1") != "0"
         self._engines = {}
         self._param_version = None
 
@@ -541,17 +544,20 @@ class _Engine:
 
     # -------------------------------------------------------------- conv / gemm
     def _conv(self, srcs, weight, bias, out_ptr, Cout, n_img, H, W, *, k=1, mode=L.CONV_NORMAL, epilogue=L.EPI_STORE,
-              stats=None, groups=0, add=None, out_ld=0, out_coff=0, dtype_code=None, frames=None, pre=None):
+              stats=None, groups=0, add=None, out_ld=0, out_coff=0, dtype_code=None, frames=None, pre=None,
+              add_norm=None):
         """srcs: list of (ptr, C).  Falls back to a separate statistics pass when the fused one does not apply.
         `pre`: GroupNorm + scale/shift + SiLU of the (raw) input on the load path (dv_conv_params.pre_*); the caller
-        checked dv_conv_pre_norm_supported."""
+        checked dv_conv_pre_norm_supported.  `add_norm`: GroupNorm + SiLU of the residual operand `add` in the epilogue
+        (dv_conv_params.add_*); the caller checked dv_conv_add_norm_supported."""
         p = L.ConvParams(src0=srcs[0][0], src1=srcs[1][0] if len(srcs) > 1 else None, weight=weight.data_ptr(),
                          bias=bias.data_ptr() if bias is not None else None, add=add, out=out_ptr, stats=stats,
                          n_img=n_img, frames=frames or self.T, H=H, W=W, C0=srcs[0][1],
                          C1=srcs[1][1] if len(srcs) > 1 else 0, Cout=Cout, kh=k,
                          kw=1 if mode == L.CONV_TEMPORAL else k, pad=k // 2, mode=mode,
                          epilogue=epilogue, groups=groups, out_ld=out_ld, out_coff=out_coff,
-                         dtype=self.code if dtype_code is None else dtype_code, impl=self.impl, **(pre or {}))
+                         dtype=self.code if dtype_code is None else dtype_code, impl=self.impl, **(pre or {}),
+                         **(add_norm or {}))
         Ho, Wo = (H // 2, W // 2) if mode == L.CONV_UNSHUFFLE else (H, W)
         rows_per_sample = (frames or self.T) * Ho * Wo
         separate_stats = stats is not None and (rows_per_sample % 64 != 0 or (Cout // groups) % 4 != 0)
@@ -944,11 +950,27 @@ class _Engine:
             assert len(srcs) == 1
             res_ptr, res_act = srcs[0].ptr, None
         else:
-            res_act = self._new_act(rows, Co)
             wr = m.res_conv.weight.detach().reshape(Co, -1)
             if skip_scale != 1.0 and c0 is not None:
                 wr = wr.clone()
                 wr[:, c0:] *= skip_scale
+            # `h + res_conv(x)` (:203-205) with block2's GroupNorm + SiLU applied to h inside res_conv's epilogue: the
+            # standalone normalisation pass and the round trip of res_conv's output through HBM are not launched
+            add_norm = dict(add_stats=st2, add_gamma=self._f32(m.block2.norm.weight).data_ptr(),
+                            add_beta=self._f32(m.block2.norm.bias).data_ptr(), add_groups=G,
+                            add_eps=float(m.block2.norm.eps))
+            probe = L.ConvParams(src0=src_list[0][0], src1=src_list[1][0] if len(src_list) > 1 else None, weight=1 << 20,
+                                 bias=None, add=h2.ptr, out=h2.ptr, stats=None, n_img=n_img, frames=self.T, H=h, W=w,
+                                 C0=src_list[0][1], C1=src_list[1][1] if len(src_list) > 1 else 0, Cout=Co, kh=1, kw=1,
+                                 pad=0, mode=L.CONV_NORMAL, epilogue=L.EPI_STORE, groups=0, out_ld=0, out_coff=0,
+                                 dtype=self.code, impl=self.impl, **add_norm)
+            if self.u.fuse_residual_norm and L.lib().dv_conv_add_norm_supported(probe):
+                self._conv(src_list, self._w(wr), self._f32(m.res_conv.bias), h2.ptr, Co, n_img, h, w, add=h2.ptr,
+                           add_norm=add_norm)
+                for a in srcs:
+                    self._release(a)
+                return h2
+            res_act = self._new_act(rows, Co)
             self._conv(src_list, self._w(wr), self._f32(m.res_conv.bias), res_act.ptr, Co, n_img, h, w)
             res_ptr = res_act.ptr
         self._op("dv_gn_apply", L.GnApplyParams(

@@ -213,10 +213,26 @@ typedef struct {
   int pre_ss_ld;
   int pre_groups;
   float pre_eps;
+  /* Fused K2 on the RESIDUAL operand (optional; add_stats == NULL: `add` is added as it is).  `add` is then the RAW
+   * output of block2's convolution and the epilogue adds that Block3D's GroupNorm + SiLU of it (:125-131 without
+   * scale/shift):
+   *   out = conv(src0, src1) + bias + SiLU( (add - mean_g) * rstd_g * add_gamma_c + add_beta_c )
+   * i.e. ResnetBlock3D's `return h + self.res_conv(x)` (:203-205) with this launch as the res_conv: the standalone
+   * dv_gn_apply(+residual) pass and the round trip of res_conv's output through HBM disappear (the block's tail moves
+   * 4 instead of 6 tensor-sized transfers).  add_stats = double[B][add_groups][2] as accumulated by the convolution that
+   * produced `add`; `out` may alias `add`.  Only the per-tap tcgen05 kernel takes it: dv_conv_add_norm_supported(p) tells,
+   * dv_conv_igemm returns DV_EUNSUPPORTED otherwise. */
+  const double* add_stats;
+  const float* add_gamma;  /* [Cout] */
+  const float* add_beta;   /* [Cout] */
+  int add_groups;
+  float add_eps;
 } dv_conv_params;
 int dv_conv_igemm(const dv_conv_params* p, dv_stream_t stream);
 /* 1 if dv_conv_igemm(impl=auto) accepts these params WITH the fused input GroupNorm (pre_* fields set) */
 int dv_conv_pre_norm_supported(const dv_conv_params* p);
+/* 1 if dv_conv_igemm(impl=auto) accepts these params WITH the GroupNorm + SiLU of the residual operand (add_* fields set) */
+int dv_conv_add_norm_supported(const dv_conv_params* p);
 /* 1 if dv_conv_igemm(impl=auto) would take the tcgen05 path for these params */
 int dv_conv_uses_tcgen05(const dv_conv_params* p);
 

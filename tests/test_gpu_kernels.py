@@ -610,6 +610,57 @@ def test_conv_streaming_halo_with_groupnorm_on_the_load_path(case):
         assert float((stats[..., 0] - stats2[..., 0]).abs().max()) < 2e-2 * float(stats2[..., 1].max().sqrt())
 
 
+@pytest.mark.parametrize("B,T,H,W,C0,C1,Co,G", [(2, 2, 16, 16, 64, 64, 64, 8), (3, 4, 8, 8, 128, 64, 128, 8),
+                                                 (2, 2, 8, 8, 512, 256, 128, 8), (2, 1, 16, 8, 64, 0, 384, 4)])
+@pytest.mark.parametrize("in_place", [True, False])
+def test_conv_1x1_with_groupnorm_of_the_residual_in_the_epilogue(B, T, H, W, C0, C1, Co, G, in_place):
+    """dv_conv_params.add_*: res_conv(cat(x, skip)) + SiLU(GroupNorm(h)) in ONE launch — the tail of ResnetBlock3D.forward
+    (`return h + self.res_conv(x)` with h = block2's norm + act, dalle2_video.py:125-131, :203-205) — against (a)
+    F.group_norm / F.silu / F.conv3d in fp32 and (b) the two launches it replaces (1x1 conv, then dv_gn_apply with the conv's
+    output as the residual).  `out` may alias `add` (the plan runs it in place)."""
+    dtype = torch.bfloat16
+    P, rows = T * H * W, B * T * H * W
+    xs = [rnd(rows, C0, dtype=dtype, seed=1)] + ([rnd(rows, C1, dtype=dtype, seed=2)] if C1 else [])
+    hraw = rnd(rows, Co, dtype=dtype, seed=3, scale=1.7) + 0.3
+    gamma, beta = rnd(Co, seed=4) * 0.2 + 1, rnd(Co, seed=5) * 0.2
+    st = torch.zeros(B, G, 2, dtype=torch.float64, device=dev())
+    L.call("dv_gn_stats", L.GnStatsParams(x=ptr(hraw), stats=ptr(st), B=B, P=P, C=Co, groups=G, dtype=code(hraw)), stream())
+    cin = C0 + C1
+    wp = rnd(Co, cin, seed=20, scale=1 / math.sqrt(cin)).to(dtype)
+    bias = rnd(Co, seed=21)
+    add_norm = dict(add_stats=ptr(st), add_gamma=ptr(gamma), add_beta=ptr(beta), add_groups=G, add_eps=1e-5)
+    h_in = hraw.clone()
+    out = h_in if in_place else torch.full((rows, Co), 9.0, dtype=dtype, device=dev())
+    p = conv(xs, wp, bias, out, n_img=B * T, frames=T, H=H, W=W, k=1, add=h_in, pre=add_norm)
+    assert L.lib().dv_conv_add_norm_supported(p)
+    # (a) fp32 statement of the reference ops
+    hn = F.silu(F.group_norm(cl_to_ncdhw(hraw, B, T, H, W), G, gamma, beta, eps=1e-5))
+    xin = torch.cat([cl_to_ncdhw(x, B, T, H, W) for x in xs], dim=1)
+    ref = ncdhw_to_cl(hn + F.conv3d(xin, wp.float().reshape(Co, cin, 1, 1, 1), bias))
+    assert rel_err(out, ref) < 1e-2, rel_err(out, ref)
+    # (b) the two launches it replaces
+    res = torch.empty(rows, Co, dtype=dtype, device=dev())
+    conv(xs, wp, bias, res, n_img=B * T, frames=T, H=H, W=W, k=1)
+    out2 = torch.empty_like(res)
+    L.call("dv_gn_apply", L.GnApplyParams(x=ptr(hraw), out=ptr(out2), residual=ptr(res), stats=ptr(st), gamma=ptr(gamma),
+                                          beta=ptr(beta), scale=None, shift=None, ss_ld=0, B=B, P=P, C=Co, groups=G,
+                                          eps=1e-5, dtype=code(hraw)), stream())
+    assert rel_err(out, out2) < 6e-3, rel_err(out, out2)
+
+
+def test_conv_add_norm_is_refused_where_no_kernel_applies_it():
+    """Never silently dropped: fp32 (SIMT path) and 3x3 shapes that the streaming-halo kernel takes are an error."""
+    x = rnd(2 * 8 * 8, 64, seed=1)
+    wp = rnd(64, 64, seed=2, scale=0.1)
+    h = rnd(2 * 8 * 8, 64, seed=3)
+    out = torch.empty_like(h)
+    st = torch.zeros(1, 8, 2, dtype=torch.float64, device=dev())
+    g = rnd(64, seed=3)
+    add_norm = dict(add_stats=ptr(st), add_gamma=ptr(g), add_beta=ptr(g), add_groups=8, add_eps=1e-5)
+    with pytest.raises(L.DvError, match="add_stats"):
+        conv([x], wp, None, out, n_img=2, frames=2, H=8, W=8, k=1, add=h, pre=add_norm)
+
+
 def test_conv_pre_norm_is_refused_where_no_kernel_applies_it():
     """The fused input GroupNorm is never silently dropped: shapes outside the streaming-halo kernel are an error."""
     x = rnd(2 * 8 * 8, 256, dtype=torch.bfloat16, seed=1)

@@ -67,6 +67,29 @@ def test_batch_rows_are_independent(layouts):
     assert rel_err(halves, full) < 1e-5
 
 
+def test_residual_norm_in_the_res_conv_epilogue_replaces_the_standalone_pass(layouts):
+    """Unet3D.fuse_residual_norm (default on, bf16): every ResnetBlock3D with a res_conv ends in ONE launch (res_conv whose
+    epilogue adds SiLU(GroupNorm(h)), dv_conv_params.add_*) instead of res_conv + dv_gn_apply(+residual); same result as the
+    two-launch plan (dalle2_video.py:203-205)."""
+    g = golden("unet3d_headline_small.pt")
+    outs, counts = [], []
+    for fuse in (True, False):
+        u = make_unet(g["unet_kwargs"], layouts["headline_small"], g["weight_seed"])
+        u.compute_dtype = torch.bfloat16
+        u.fuse_residual_norm = fuse
+        outs.append(u(g["x"].cuda(), g["times"].cuda(), video_embed=g["video_embed"].cuda()))
+        eng = next(iter(u._engines.values()))
+        counts.append((sum(1 for n, p in eng.ops if n == "dv_gn_apply"),
+                       sum(1 for n, p in eng.ops if n == "dv_conv_igemm" and p.add_stats)))
+    n_res = sum(1 for m in u.modules() if hasattr(m, "res_conv") and not isinstance(m.res_conv, torch.nn.Identity))
+    # the res_convs with at most 128 output channels whose samples have a multiple of 128 positions (wider layers keep the
+    # two-launch form: the residual ring would take half of the N = 256 operand pipeline)
+    assert n_res >= 10 and 4 <= counts[0][1] <= n_res and counts[1][1] == 0
+    assert counts[1][0] - counts[0][0] == counts[0][1]
+    assert rel_err(outs[0], outs[1]) < 1e-2
+    assert rel_err(outs[0], g["eps"]) < BF16_TOL
+
+
 def test_weights_are_repacked_after_load_state_dict(layouts):
     kw = dict(dim=32, video_embed_dim=512, dim_mults=(1, 2), cond_on_video_embeds=True)
     u = make_unet(kw, layouts["tiny"], seed=7)

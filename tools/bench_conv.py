@@ -13,6 +13,7 @@ ap.add_argument("--C0", type=int, default=64); ap.add_argument("--C1", type=int,
 ap.add_argument("--Cout", type=int, default=64); ap.add_argument("--k", type=int, default=3)
 ap.add_argument("--impl", type=int, default=0); ap.add_argument("--iters", type=int, default=20)
 ap.add_argument("--stats", type=int, default=1)
+ap.add_argument("--add-norm", type=int, default=0, help="1: GroupNorm + SiLU of the residual operand in the epilogue (add_*), in place")
 a = ap.parse_args()
 dev = torch.device("cuda:0")
 rows = a.B * a.T * a.H * a.W
@@ -25,8 +26,18 @@ bias = torch.randn(a.Cout, device=dev)
 out = torch.empty(rows, a.Cout, device=dev, dtype=torch.bfloat16)
 stats = torch.zeros(a.B, 8, 2, dtype=torch.float64, device=dev) if a.stats else None
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+add_norm = None
+if a.add_norm:
+    gam, bet = torch.ones(a.Cout, device=dev), torch.zeros(a.Cout, device=dev)
+    ast = torch.zeros(a.B, 8, 2, dtype=torch.float64, device=dev)
+    out.normal_()
+    L.call("dv_gn_stats", L.GnStatsParams(x=out.data_ptr(), stats=ast.data_ptr(), B=a.B, P=a.T * a.H * a.W, C=a.Cout, groups=8,
+                                          dtype=L.DV_BF16), torch.cuda.current_stream().cuda_stream)
+    add_norm = dict(add_stats=ast.data_ptr(), add_gamma=gam.data_ptr(), add_beta=bet.data_ptr(), add_groups=8, add_eps=1e-5)
+    stats = None
 def run():
-    conv(xs, w, bias, out, n_img=a.B * a.T, frames=a.T, H=a.H, W=a.W, k=a.k, stats=stats, groups=8, impl=a.impl)
+    conv(xs, w, bias, out, n_img=a.B * a.T, frames=a.T, H=a.H, W=a.W, k=a.k, stats=stats, groups=8, impl=a.impl,
+         add=out if a.add_norm else None, pre=add_norm)
 for _ in range(3):
     run()
 torch.cuda.synchronize()
@@ -38,4 +49,6 @@ for _ in range(a.iters):
     tot += e0.elapsed_time(e1)
 ms = tot / a.iters
 fl = 2.0 * rows * a.Cout * a.k * a.k * cin
+nb = rows * 2 * (cin + a.Cout * (2 if a.add_norm else 1))
+print(f"  {nb / ms / 1e6:.0f} GB/s algorithmic")
 print(f"impl {a.impl} {a.H}x{a.W} C{a.C0}+{a.C1}->{a.Cout} k{a.k} B{a.B}: {ms*1e3:.1f} us  {fl/ms/1e9:.1f} TFLOP/s (L2 flushed between iterations)")
