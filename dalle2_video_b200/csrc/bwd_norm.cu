@@ -8,6 +8,8 @@
 //   dbeta  = sum_b (1+scale)*S1  dgamma = sum_b (1+scale)*S2
 //   dx     = rstd * ( gamma*(1+scale)*g_v - m1 - xh*m2 ),  m1 / m2 = group means of gamma*(1+scale)*{S1,S2} / P
 // Three launches: reduce (streams x and dy once), params (tiny), apply (streams x, dy -> dx).  HBM-bound.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace dv {
@@ -429,6 +431,131 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(dv_layernorm_bwd_par
   for (int c = threadIdx.x; c < p.C; c += blockDim.x) atomicAdd(p.dg + c, sdg[c]);
 }
 
+// Vectorised form for bf16 rows whose 16-byte vectors are a power of two (C = 64 ... 512): LPR lanes share a row (32 / LPR
+// rows per warp pass, NV vectors per lane), R passes in flight.  Two dependent reduction phases instead of four: the mean
+// first, then sum (x-m)^2, sum h and sum h (x-m) together (h = dy*g; mean(h*xh) = rstd * sum h (x-m) / C), each over LPR
+// lanes only.  Measured on B200 at rows 524288 x C 128: 1.8 TB/s with the one-warp-per-row kernel above (8-byte loads,
+// four serial 5-step shuffle chains per row).
+template <int LPR, int NV, int R>
+__global__ void __launch_bounds__(256, 2) layernorm_bwd_vec_kernel(dv_layernorm_bwd_params p) {
+  using T = __nv_bfloat16;
+  __shared__ float sdg[512];
+  constexpr int RPW = 32 / LPR;       // rows per warp pass
+  const int lane = threadIdx.x & 31, sub = lane % LPR, rsel = lane / LPR;
+  const int wpb = blockDim.x >> 5;
+  for (int c = threadIdx.x; c < p.C; c += blockDim.x) sdg[c] = 0.f;
+  __syncthreads();
+  float g[NV][8], dg[NV][8];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const float4 g0 = *reinterpret_cast<const float4*>(p.g + (i * LPR + sub) * 8);
+    const float4 g1 = *reinterpret_cast<const float4*>(p.g + (i * LPR + sub) * 8 + 4);
+    g[i][0] = g0.x; g[i][1] = g0.y; g[i][2] = g0.z; g[i][3] = g0.w;
+    g[i][4] = g1.x; g[i][5] = g1.y; g[i][6] = g1.z; g[i][7] = g1.w;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) dg[i][k] = 0.f;
+  }
+  const float invC = 1.0f / (float)p.C;
+  const int64_t stride = (int64_t)gridDim.x * wpb * RPW * R;
+  for (int64_t row0 = ((int64_t)blockIdx.x * wpb + (threadIdx.x >> 5)) * RPW * R; row0 < p.rows; row0 += stride) {
+    uint4 xr[R][NV], dr[R][NV];
+    bool live[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int64_t row = row0 + r * RPW + rsel;
+      live[r] = row < p.rows;
+      const uint4* x4 = reinterpret_cast<const uint4*>(reinterpret_cast<const T*>(p.x) + row * p.C);
+      const uint4* d4 = reinterpret_cast<const uint4*>(reinterpret_cast<const T*>(p.dy) + row * p.C);
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        xr[r][i] = live[r] ? x4[i * LPR + sub] : make_uint4(0, 0, 0, 0);
+        dr[r][i] = live[r] ? d4[i * LPR + sub] : make_uint4(0, 0, 0, 0);
+      }
+    }
+    float mean[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      float s = 0.f;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        float v[8];
+        load8(reinterpret_cast<const T*>(&xr[r][i]), v);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) s += v[k];
+      }
+      mean[r] = s;
+    }
+#pragma unroll
+    for (int o = LPR / 2; o > 0; o >>= 1)
+#pragma unroll
+      for (int r = 0; r < R; ++r) mean[r] += __shfl_xor_sync(0xffffffffu, mean[r], o);
+    float q[R], a[R], b[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      mean[r] *= invC;
+      q[r] = 0.f; a[r] = 0.f; b[r] = 0.f;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        float v[8], d[8];
+        load8(reinterpret_cast<const T*>(&xr[r][i]), v);
+        load8(reinterpret_cast<const T*>(&dr[r][i]), d);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const float c = v[k] - mean[r], h = d[k] * g[i][k];
+          q[r] = fmaf(c, c, q[r]);
+          a[r] += h;
+          b[r] = fmaf(h, c, b[r]);
+        }
+      }
+    }
+#pragma unroll
+    for (int o = LPR / 2; o > 0; o >>= 1)
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        q[r] += __shfl_xor_sync(0xffffffffu, q[r], o);
+        a[r] += __shfl_xor_sync(0xffffffffu, a[r], o);
+        b[r] += __shfl_xor_sync(0xffffffffu, b[r], o);
+      }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      if (!live[r]) continue;
+      const float rstd = rsqrtf(q[r] * invC + p.eps);
+      const float m1 = a[r] * invC, m2 = rstd * b[r] * invC;
+      T* dx = reinterpret_cast<T*>(p.dx) + (row0 + r * RPW + rsel) * p.C;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        float v[8], d[8], o[8];
+        load8(reinterpret_cast<const T*>(&xr[r][i]), v);
+        load8(reinterpret_cast<const T*>(&dr[r][i]), d);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const float xh = (v[k] - mean[r]) * rstd;
+          dg[i][k] = fmaf(d[k], xh, dg[i][k]);
+          o[k] = rstd * (d[k] * g[i][k] - m1 - xh * m2);
+        }
+        if (p.accumulate) {
+          float prev[8];
+          load8(dx + (i * LPR + sub) * 8, prev);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) o[k] += prev[k];
+        }
+        store8(dx + (i * LPR + sub) * 8, o);
+      }
+    }
+  }
+  // lanes with the same `sub` hold the same channels: fold the warp's row slots, then CTA, then global
+#pragma unroll
+  for (int i = 0; i < NV; ++i)
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+#pragma unroll
+      for (int o = 16; o >= LPR; o >>= 1) dg[i][k] += __shfl_xor_sync(0xffffffffu, dg[i][k], o);
+      if (rsel == 0) atomicAdd(&sdg[(i * LPR + sub) * 8 + k], dg[i][k]);
+    }
+  __syncthreads();
+  for (int c = threadIdx.x; c < p.C; c += blockDim.x) atomicAdd(p.dg + c, sdg[c]);
+}
+
 }  // namespace dv
 
 static int gn_bwd_check(const dv_gn_bwd_params* p, const char* who) {
@@ -523,7 +650,22 @@ extern "C" int dv_layernorm_bwd(const dv_layernorm_bwd_params* p, dv_stream_t st
     if (blocks > 148 * 4) blocks = 148 * 4;                               \
     layernorm_bwd_kernel<T, V, R><<<(unsigned)blocks, wpb * 32, 0, s>>>(*p); \
   } while (0)
-  if (p->dtype == DV_F32) {
+  static int vec_on = -1;
+  if (vec_on < 0) { const char* e = getenv("DV_LN_BWD_VEC"); vec_on = e ? atoi(e) : 1; }
+  if (p->dtype == DV_BF16 && vec_on && aligned16(p->g) && (p->C == 64 || p->C == 128 || p->C == 256 || p->C == 512)) {
+#define DV_LNV(LPR, NV, R)                                                              \
+  do {                                                                                  \
+    const int rows_per_cta = wpb * (32 / LPR) * R;                                      \
+    int64_t blocks = (p->rows + rows_per_cta - 1) / rows_per_cta;                       \
+    if (blocks > 148 * 2) blocks = 148 * 2;                                             \
+    layernorm_bwd_vec_kernel<LPR, NV, R><<<(unsigned)blocks, wpb * 32, 0, s>>>(*p);     \
+  } while (0)
+    if (p->C == 64) DV_LNV(8, 1, 2);
+    else if (p->C == 128) DV_LNV(16, 1, 2);
+    else if (p->C == 256) DV_LNV(32, 1, 2);
+    else DV_LNV(32, 2, 1);
+#undef DV_LNV
+  } else if (p->dtype == DV_F32) {
     if (p->C <= 128) DV_LNB(float, 1, 4); else if (p->C <= 512) DV_LNB(float, 4, 2); else DV_LNB(float, 8, 1);
   } else {
     if (p->C <= 128) DV_LNB(__nv_bfloat16, 1, 4); else if (p->C <= 512) DV_LNB(__nv_bfloat16, 4, 2); else DV_LNB(__nv_bfloat16, 8, 1);
