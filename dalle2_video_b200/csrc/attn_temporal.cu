@@ -12,7 +12,7 @@
 // bank-conflict free.  Several CTAs are resident per SM so the load / compute / store phases overlap across CTAs.
 #include <math_constants.h>
 
-#include "common.cuh"
+#include "tc_common.cuh"
 
 namespace dv {
 
@@ -255,6 +255,322 @@ __global__ void __launch_bounds__(TA_THREADS, 4) attn_temporal_kernel(const dv_a
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// tcgen05 form (bf16, dh = 32, T in {8, 16, 32}, heads a multiple of 128 / T).  The mma.sync kernel above spends ~200
+// warp instructions per (pixel, head) on fragment loads, quad shuffles and the null-key special case and is issue /
+// latency bound at 0.35-0.49 of the HBM rate; here ONE thread owns one (frame, head) row of a 128-row tile:
+//   tile    = the T frames x HG = 128 / T heads of one pixel: Q [128 rows][32] K-major SWIZZLE_64B, brought in by ONE 4-D
+//             TMA box (d, head, pixel, frame) of the channels-last tensor — the "(b h w) t c" rearrangement of the
+//             reference is an address pattern, never a copy;
+//   K / V   = the pixel's [T][32] tiles (two 3-D TMA boxes of the kv rows), row T of both holds the learned null key /
+//             value (written once per CTA; the TMA boxes never touch it), rows above it are zero;
+//   MMA 1     S[128][NS] = Q . K^T        (M = 128, N = NS = T + 16 rounded to 16, K = 32)          -> TMEM
+//   threads   logits * scale*log2e + bias row (registers, log2 domain), max, ex2, P (bf16, unnormalised) -> shared memory
+//   MMA 2     O[128][32] = P . V          (A = P K-major, B = V MN-major SWIZZLE_64B, K = NS)        -> TMEM
+//   threads   O / rowsum -> bf16 -> 64-byte row store.
+// No shuffles, no fragment bookkeeping: ~150 instructions per row.  Several CTAs share an SM; a CTA keeps its head group
+// (so the bias rows stay in registers) and walks pixels.
+// warp 0 drives both the TMA loads and the MMAs (no separate producer: when P of tile i is ready, the MMAs of tile i - 1
+// have retired, so its stage can be refilled without an `empty` barrier); warps 1-4 are the softmax / output threads.
+// 160 threads x <= 80 registers: five CTAs per SM (four at T = 32) keep five tile chains in flight.
+constexpr int TT_THREADS = 160;
+template <int T> struct TtCfg {
+  static constexpr int NS = T == 8 ? 16 : (T == 16 ? 32 : 48);   // keys incl. the null key, padded to the MMA granularity
+  static constexpr int P_ROW = T == 32 ? 128 : 64;               // bytes per P row (K-major, SWIZZLE_128B / SWIZZLE_64B)
+  static constexpr int STAGES = T == 32 ? 2 : 3;
+  static constexpr int CTAS = 4;
+  static constexpr int STAGE = 128 * 64 + 2 * NS * 64;
+  static constexpr int SMEM = STAGES * STAGE + 128 * P_ROW + 256 + 1024;
+};
+
+struct TemporalTcParams {
+  dv_attn_temporal_params a;
+  int hg;            // heads per tile = 128 / T
+  int tpp;           // tiles (head groups) per pixel = heads / hg
+  int64_t pixels;    // B * HW
+};
+
+__device__ __forceinline__ void tma_load_4d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_t(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+
+template <int T>
+__global__ void __launch_bounds__(TT_THREADS, TtCfg<T>::CTAS)
+attn_temporal_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_kv,
+                        const TemporalTcParams pp) {
+  constexpr int NS = TtCfg<T>::NS, P_ROW = TtCfg<T>::P_ROW, TT_STAGES = TtCfg<T>::STAGES;
+  constexpr int Q_BYTES = 128 * 64;
+  constexpr int KV_BYTES = NS * 64;                       // one of K, V
+  constexpr int STAGE = Q_BYTES + 2 * KV_BYTES;           // multiple of 1024
+  constexpr uint32_t C_S = 0, C_O = NS <= 32 ? 32 : 64;
+  constexpr uint32_t TMEM_COLS = NS <= 32 ? 64 : 128;     // x CTAs per SM <= 512
+  const dv_attn_temporal_params& p = pp.a;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* ring = smem;                                   // [TT_STAGES][Q | K | V]
+  uint8_t* p_s = ring + TT_STAGES * STAGE;                // [128][P_ROW]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(p_s + 128 * P_ROW);
+  uint64_t* full = bars;                 // [TT_STAGES]
+  uint64_t* s_full = full + TT_STAGES;
+  uint64_t* p_ready = s_full + 1;        // 4 arrivals
+  uint64_t* o_full = p_ready + 1;
+  uint64_t* o_free = o_full + 1;         // 4 arrivals
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_free + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // CTA -> (head group, pixel range): blockIdx.x = slot * tpp + head group
+  const int hgroup = (int)blockIdx.x % pp.tpp;
+  const int slot = (int)blockIdx.x / pp.tpp, slots = (int)gridDim.x / pp.tpp;
+  const int64_t per = (pp.pixels + slots - 1) / slots;
+  const int64_t pix_begin = (int64_t)slot * per;
+  const int64_t pix_end = pix_begin + per < pp.pixels ? pix_begin + per : pp.pixels;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_q);
+    tma_prefetch_desc(&map_kv);
+    for (int s = 0; s < TT_STAGES; ++s) mbar_init(&full[s], 1);
+    mbar_init(s_full, 1);
+    mbar_init(p_ready, 4);
+    mbar_init(o_full, 1);
+    mbar_init(o_free, 4);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  // rows T .. NS-1 of every K / V stage: the null key / value in row T (a multiple of 8: swizzle phase 0), zeros above.
+  // The TMA boxes cover rows 0 .. T-1 only, so this is written once.
+  for (int i = threadIdx.x; i < TT_STAGES * 2 * (NS - T) * 4; i += blockDim.x) {
+    const int c = i & 3, r = (i >> 2) % (NS - T), which = ((i >> 2) / (NS - T)) & 1, st = (i >> 2) / (2 * (NS - T));
+    uint4 pk = make_uint4(0u, 0u, 0u, 0u);
+    if (r == 0) {
+      __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&pk);
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        h2[e] = __floats2bfloat162_rn(p.null_kv[which * 32 + c * 8 + 2 * e], p.null_kv[which * 32 + c * 8 + 2 * e + 1]);
+    }
+    const int row = T + r;
+    *reinterpret_cast<uint4*>(ring + (size_t)st * STAGE + Q_BYTES + which * KV_BYTES + row * 64 + ((c ^ ((row >> 1) & 3)) * 16)) = pk;
+  }
+  for (int i = threadIdx.x; i < 128 * P_ROW / 16; i += blockDim.x) reinterpret_cast<uint4*>(p_s)[i] = make_uint4(0u, 0u, 0u, 0u);
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================================================================ driver: TMA loads + MMAs
+    const uint32_t idesc_s = make_idesc_major(NS, 0, 0);
+    const uint32_t idesc_o = make_idesc_major(32, 0, 1);
+    const int n_tiles = (int)(pix_end - pix_begin);
+    auto load_tile = [&](int i) {   // tile i of this CTA -> stage i % TT_STAGES
+      const int64_t pix = pix_begin + i;
+      const int b = (int)(pix / p.HW), hw = (int)(pix - (int64_t)b * p.HW);
+      const int st = i % TT_STAGES;
+      uint8_t* dst = ring + (size_t)st * STAGE;
+      mbar_expect_tx(&full[st], (uint32_t)(Q_BYTES + 2 * T * 64));
+      tma_load_4d(&map_q, &full[st], dst, 0, hgroup * pp.hg, hw, b * T);
+      tma_load_3d_t(&map_kv, &full[st], dst + Q_BYTES, 0, hw, b * T);
+      tma_load_3d_t(&map_kv, &full[st], dst + Q_BYTES + KV_BYTES, 32, hw, b * T);
+    };
+    auto issue_s = [&](int i) {
+      const uint32_t q_a = smem_u32(ring + (size_t)(i % TT_STAGES) * STAGE), k_a = q_a + Q_BYTES;
+#pragma unroll
+      for (int kk = 0; kk < 2; ++kk)
+        umma_f16(tmem_base + C_S, make_smem_desc_sw64(q_a) + (uint64_t)(kk * 2), make_smem_desc_sw64(k_a) + (uint64_t)(kk * 2),
+                 idesc_s, kk != 0);
+      umma_commit(s_full);
+    };
+    if (n_tiles > 0) {
+      if (elect_one())
+        for (int i = 0; i < TT_STAGES && i < n_tiles; ++i) load_tile(i);
+      __syncwarp();
+      mbar_wait(&full[0], 0u);
+      tc_fence_after();
+      if (elect_one()) issue_s(0);
+      __syncwarp();
+    }
+    for (int it = 0; it < n_tiles; ++it) {
+      mbar_wait(p_ready, (uint32_t)(it & 1));           // P written, S read out of TMEM
+      if (it > 0) mbar_wait(o_free, (uint32_t)((it - 1) & 1));
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t v_a = smem_u32(ring + (size_t)(it % TT_STAGES) * STAGE) + Q_BYTES + KV_BYTES;
+#pragma unroll
+        for (int kk = 0; kk < NS / 16; ++kk) {
+          const uint64_t ad = (T == 32 ? make_smem_desc(smem_u32(p_s)) : make_smem_desc_sw64(smem_u32(p_s))) + (uint64_t)(kk * 2);
+          umma_f16(tmem_base + C_O, ad, make_desc_mn_sw64(v_a + (uint32_t)(kk * 1024)), idesc_o, kk != 0);
+        }
+        umma_commit(o_full);
+        // P of tile `it` exists, so the output pass of tile it - 1 has begun, i.e. its MMAs have retired: its stage is free
+        if (it >= 1 && it - 1 + TT_STAGES < n_tiles) load_tile(it - 1 + TT_STAGES);
+      }
+      __syncwarp();
+      if (it + 1 < n_tiles) {
+        // the next tile's logits run under this tile's output pass
+        mbar_wait(&full[(it + 1) % TT_STAGES], (uint32_t)(((it + 1) / TT_STAGES) & 1));
+        tc_fence_after();
+        if (elect_one()) issue_s(it + 1);
+        __syncwarp();
+      }
+    }
+  } else if (pix_begin < pix_end) {
+    // ================================================================ softmax + output: one (frame, head) row per thread
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int t_row = row / pp.hg, h = hgroup * pp.hg + row % pp.hg;
+    const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
+    const float LOG2E = 1.4426950408889634f;
+    const float sl2 = p.scale * LOG2E;
+    float bl[T + 1];   // bias row in the log2 domain: [0] = null key, [1 + j] = frame j
+#pragma unroll
+    for (int j = 0; j <= T; ++j) bl[j] = p.bias ? __ldg(p.bias + ((int64_t)h * T + t_row) * (T + 1) + j) * LOG2E : 0.f;
+    __nv_bfloat16* outp = reinterpret_cast<__nv_bfloat16*>(p.out);
+    const int inner = p.heads * 32;
+    int it = 0;
+    for (int64_t pix = pix_begin; pix < pix_end; ++pix, ++it) {
+      const int b = (int)(pix / p.HW), hw = (int)(pix - (int64_t)b * p.HW);
+      mbar_wait(s_full, (uint32_t)(it & 1));
+      tc_fence_after();
+      float s[NS];
+      {
+        uint32_t r[32];
+        tmem_ld32(t_lane + C_S, r);
+#pragma unroll
+        for (int j = 0; j < (NS < 32 ? NS : 32); ++j) s[j] = __uint_as_float(r[j]);
+        if constexpr (NS > 32) {
+          uint32_t r2[16];
+          tmem_ld16_nowait(t_lane + C_S + 32, r2);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < NS - 32; ++j) s[32 + j] = __uint_as_float(r2[j]);
+        }
+      }
+      float m = fmaf(s[T], sl2, bl[0]);
+      s[T] = m;
+#pragma unroll
+      for (int j = 0; j < T; ++j) {
+        s[j] = fmaf(s[j], sl2, bl[1 + j]);
+        m = fmaxf(m, s[j]);
+      }
+      // unnormalised probabilities as the bf16 values the tensor core multiplies; the row sum uses the rounded values
+      float l = 0.f;
+      uint32_t pk[NS / 2];
+#pragma unroll
+      for (int j2 = 0; j2 < NS / 2; ++j2) {
+        const int j0 = 2 * j2, j1 = 2 * j2 + 1;
+        const float e0 = j0 <= T ? ex2_ftz(s[j0] - m) : 0.f;
+        const float e1 = j1 <= T ? ex2_ftz(s[j1] - m) : 0.f;
+        pk[j2] = pack_bf16(e0, e1);
+        l += bf16_pair_sum(pk[j2]);
+      }
+      {
+        // the previous P was consumed by the MMA whose commit is o_full (waited at the end of the last pass)
+        uint8_t* prow = p_s + row * P_ROW;
+        const int sw = P_ROW == 128 ? (row & 7) : ((row >> 1) & 3);
+#pragma unroll
+        for (int c = 0; c < NS / 8; ++c)
+          *reinterpret_cast<uint4*>(prow + ((c ^ sw) * 16)) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_ready);
+      const float inv = 1.0f / l;
+      mbar_wait(o_full, (uint32_t)(it & 1));
+      tc_fence_after();
+      {
+        uint32_t r[32];
+        tmem_ld32(t_lane + C_O, r);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(o_free);
+        const int64_t tok = ((int64_t)b * T + t_row) * p.HW + hw;
+        uint4* dst = reinterpret_cast<uint4*>(outp + tok * inner + h * 32);
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          dst[c] = make_uint4(pack_bf16(__uint_as_float(r[8 * c]) * inv, __uint_as_float(r[8 * c + 1]) * inv),
+                              pack_bf16(__uint_as_float(r[8 * c + 2]) * inv, __uint_as_float(r[8 * c + 3]) * inv),
+                              pack_bf16(__uint_as_float(r[8 * c + 4]) * inv, __uint_as_float(r[8 * c + 5]) * inv),
+                              pack_bf16(__uint_as_float(r[8 * c + 6]) * inv, __uint_as_float(r[8 * c + 7]) * inv));
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+static bool tc_kernel_ok(const dv_attn_temporal_params& p) {
+  if (p.dtype != DV_BF16 || p.dh != TA_DH) return false;
+  if (p.T != 8 && p.T != 16 && p.T != 32) return false;
+  const int hg = 128 / p.T;
+  if (p.heads % hg || p.heads > 64) return false;
+  if ((int64_t)p.B * p.T * p.HW >= (1ll << 31)) return false;
+  return true;
+}
+
+template <int T>
+static int launch_tc_kernel(const dv_attn_temporal_params& p, cudaStream_t s) {
+  TemporalTcParams k;
+  memset(&k, 0, sizeof(k));
+  k.a = p;
+  k.hg = 128 / T;
+  k.tpp = p.heads / k.hg;
+  k.pixels = (int64_t)p.B * p.HW;
+  const int inner = p.heads * TA_DH;
+  CUtensorMap mq, mkv;
+  int rc;
+  {
+    uint64_t dims[4] = {32, (uint64_t)p.heads, (uint64_t)p.HW, (uint64_t)p.B * T};
+    uint64_t strides[3] = {64, (uint64_t)inner * 2, (uint64_t)p.HW * inner * 2};
+    uint32_t box[4] = {32, (uint32_t)k.hg, 1, (uint32_t)T};
+    if ((rc = encode_map(&mq, p.q, 4, dims, strides, box, 64)) != DV_OK) return rc;
+  }
+  {
+    uint64_t dims[3] = {64, (uint64_t)p.HW, (uint64_t)p.B * T};
+    uint64_t strides[2] = {128, (uint64_t)p.HW * 128};
+    uint32_t box[3] = {32, 1, (uint32_t)T};
+    if ((rc = encode_map(&mkv, p.kv, 3, dims, strides, box, 64)) != DV_OK) return rc;
+  }
+  const size_t smem = TtCfg<T>::SMEM;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(attn_temporal_tc_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    DV_REQUIRE(e == cudaSuccess, DV_ECUDA, "dv_attn_temporal(tcgen05): cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  static int sm_count = 0;
+  if (!sm_count) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
+    if (sm_count <= 0) sm_count = 148;
+  }
+  // TtCfg::CTAS CTAs per SM (<= 128 TMEM columns, 34-45 KB of shared memory, 160 threads each); a CTA keeps one head group
+  int64_t slots = (int64_t)TtCfg<T>::CTAS * sm_count / k.tpp;
+  if (slots < 1) slots = 1;
+  if (slots > k.pixels) slots = k.pixels;
+  attn_temporal_tc_kernel<T><<<(unsigned)(slots * k.tpp), TT_THREADS, smem, s>>>(mq, mkv, k);
+  return DV_OK;
+}
+
 // Generic CUDA-core path (fp32 parity mode, any T / dim_head <= 64): one thread per (token, head), strided keys.
 template <typename TT, int DH>
 __global__ void __launch_bounds__(128) attn_temporal_simt_kernel(const dv_attn_temporal_params p) {
@@ -342,7 +658,20 @@ extern "C" int dv_attn_temporal(const dv_attn_temporal_params* p, dv_stream_t st
              "dv_attn_temporal: q/kv/out must be 16-byte aligned");
   cudaStream_t s = as_stream(stream);
   const bool ok = warp_kernel_ok(*p);
+  const bool tc_ok = tc_kernel_ok(*p);
   if (p->impl == 2) DV_REQUIRE(ok, DV_EUNSUPPORTED, "dv_attn_temporal: the mma kernel does not take these parameters");
+  if (p->impl == 3) DV_REQUIRE(tc_ok, DV_EUNSUPPORTED, "dv_attn_temporal: the tcgen05 kernel does not take these parameters");
+  if (tc_ok && (p->impl == 3 || p->impl == 0)) {
+    int rc;
+    switch (p->T) {
+      case 8: rc = launch_tc_kernel<8>(*p, s); break;
+      case 16: rc = launch_tc_kernel<16>(*p, s); break;
+      default: rc = launch_tc_kernel<32>(*p, s); break;
+    }
+    if (rc != DV_OK) return rc;
+    DV_CHECK_LAUNCH("dv_attn_temporal(tcgen05)");
+    return DV_OK;
+  }
   if (ok && p->impl != 1) {
     int rc;
     switch (p->T) {

@@ -166,4 +166,30 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw64(uint32_t saddr) {
   return d;
 }
 
+// MN-major SWIZZLE_64B (64-byte rows = 32 bf16 along MN, 8 K-rows per 512-byte group)
+__device__ __forceinline__ uint64_t make_desc_mn_sw64(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)(64 >> 4) << 16;      // LBO: next 32-element MN atom (unused: N = 32)
+  d |= (uint64_t)(512 >> 4) << 32;     // SBO: next group of 8 K-rows
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)4 << 61;              // SWIZZLE_64B
+  return d;
+}
+// MN-major SWIZZLE_128B, 64-element atoms `lbo` bytes apart
+__device__ __forceinline__ uint64_t make_desc_mn_sw128_b(uint32_t saddr, uint32_t lbo) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((lbo >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// instruction descriptor: D f32, A/B bf16, M = 128, N = bn, with per-operand major-ness (1 = MN-major)
+__device__ __forceinline__ uint32_t make_idesc_major(int bn, int a_mn, int b_mn) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) | ((uint32_t)(bn >> 3) << 17) |
+         ((uint32_t)(128 >> 4) << 24);
+}
+
 }  // namespace dv

@@ -60,6 +60,36 @@ def test_temporal_attention_mma_kernel(T, heads, use_bias):
     assert torch.equal(q2, out)
 
 
+@pytest.mark.parametrize("T,heads", [(8, 16), (16, 16), (32, 16), (16, 8), (32, 4), (8, 32)])
+@pytest.mark.parametrize("use_bias", [True, False])
+@pytest.mark.parametrize("B,HW", [(2, 64), (3, 50), (1, 1)])
+def test_temporal_attention_tcgen05_kernel(T, heads, use_bias, B, HW):
+    """impl = 3: one (frame, head) row per thread on 128-row tiles of one pixel (4-D TMA box over the channels-last tensor,
+    the null key as row T of the K / V tiles) — against the fp32 statement of upstream Attention + RelPosBias on
+    "(b h w) t c" and against the mma.sync kernel; ragged pixel counts (3 x 50 pixels, a single pixel) and in place."""
+    D = 32
+    q = rnd(B, T, HW, heads, D, dtype=torch.bfloat16, seed=1)
+    kv = rnd(B, T, HW, 2 * D, dtype=torch.bfloat16, seed=2)
+    null_kv = rnd(2, D, seed=3)
+    bias = rnd(heads, T, T + 1, seed=4) if use_bias else None
+    out = torch.full_like(q, 7.0)
+    p = L.AttnTemporalParams(q=ptr(q), kv=ptr(kv), out=ptr(out), null_kv=ptr(null_kv), bias=ptr(bias), B=B, T=T, HW=HW,
+                             heads=heads, dh=D, scale=1.0 / D, dtype=code(q), impl=3)
+    L.call("dv_attn_temporal", p, stream())
+    ref = temporal_attention_reference(q, kv, null_kv, bias, 1.0 / D)
+    assert rel_err(out, ref) < 1.2e-2, rel_err(out, ref)
+    if heads % 4 == 0 and HW % 4 == 0:
+        out2 = torch.empty_like(q)
+        p.out, p.impl = ptr(out2), 2
+        L.call("dv_attn_temporal", p, stream())
+        assert rel_err(out, out2) < 8e-3
+        p.impl = 3
+    q2 = q.clone()                      # in place (out aliases q), as the launch plan uses it
+    p.q, p.out = ptr(q2), ptr(q2)
+    L.call("dv_attn_temporal", p, stream())
+    assert torch.equal(q2, out)
+
+
 @pytest.mark.parametrize("dtype,tol", [(torch.float32, 2e-5), (torch.bfloat16, 1.2e-2)])
 @pytest.mark.parametrize("T,D", [(5, 32), (16, 64), (12, 32)])
 def test_temporal_attention_cuda_core_kernel(dtype, tol, T, D):

@@ -89,6 +89,17 @@ def sweep_case(mode, B, T, H, W, C, iters, flush, peaks, with_torch=True):
     core = [(n, p) for n, p in plan.ops if n in ("dv_attn_temporal", "dv_attn_mqa")][0]
     stream = torch.cuda.current_stream().cuda_stream
     core_ms = timed(lambda: L.call(core[0], core[1], stream), iters, flush)
+    alt = {}
+    if mode == "temporal":
+        # the same launch through the other kernels of dv_attn_temporal: 2 = warp-level mma.sync, 3 = tcgen05
+        for name, impl in (("mma_sync", 2), ("tcgen05", 3)):
+            saved = core[1].impl
+            core[1].impl = impl
+            try:
+                alt[name] = timed(lambda: L.call(core[0], core[1], stream), iters, flush)
+            except L.DvError:
+                alt[name] = None
+            core[1].impl = saved
     tokens = B * T * H * W
     inner = HEADS * DH
     nk = {"temporal": T, "factorised": H * W, "joint": T * H * W}[mode] + 1
@@ -101,6 +112,9 @@ def sweep_case(mode, B, T, H, W, C, iters, flush, peaks, with_torch=True):
            "core_frac_hbm": core_bytes / core_ms / 1e6 / peaks["hbm_gbs"], "core_TFLOPs": core_flops / core_ms / 1e9,
            "block_ms": blk_ms, "block_launches": len(plan.ops),
            "block_min_bytes_GBps": block_bytes / blk_ms / 1e6}
+    if alt:
+        rec["core_ms_by_kernel"] = alt
+        rec["core_frac_hbm_by_kernel"] = {k: (core_bytes / v / 1e6 / peaks["hbm_gbs"] if v else None) for k, v in alt.items()}
     if with_torch:
         rec["torch_ms"] = torch_arm(mode, B, T, H, W, C, block, iters, flush)
         for k, v in rec["torch_ms"].items():
@@ -117,6 +131,7 @@ def main():
     ap.add_argument("--out", default=None)
     ap.add_argument("--quick", action="store_true")
     ap.add_argument("--no-torch", action="store_true")
+    ap.add_argument("--only", default=None, help="temporal | factorised | joint")
     args = ap.parse_args()
     pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
     peaks = json.load(open(pk)) if os.path.isfile(pk) else {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}
@@ -135,6 +150,8 @@ def main():
     if not args.quick:
         cases.append(("factorised", 1, 16, 64, 64, 64))
         cases.append(("joint", 8, 16, 8, 8, 512))  # the reference's own bottleneck attention at config 2, B = 8
+    if args.only:
+        cases = [c for c in cases if c[0] == args.only]
     lines = []
     for c in cases:
         big = c[0] != "temporal" and c[3] * c[4] >= 128 * 128
