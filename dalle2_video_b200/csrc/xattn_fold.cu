@@ -107,6 +107,7 @@ __global__ void __launch_bounds__(128) xattn_fold_prep_multi_kernel(const __grid
 constexpr int XF_THREADS = 192;  // warp 0 TMA, warp 1 MMA, warps 2-5 softmax + epilogue (one token per thread)
 
 struct XfoldParams {
+  int alias_u;            // C = 512: U takes Mq's shared memory once MMA 1 has retired; one tile per CTA
   int C, chunks, NB, xs;  // channels, C/64, N of MMA 2 (min(C,256)), X stages
   int heads, nk;
   int64_t tiles, tiles_per_sample;
@@ -133,8 +134,9 @@ xattn_fold_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
   const uint32_t x_stage_bytes = (uint32_t)p.chunks * 16384;
   uint8_t* x_s = smem;                                           // [xs][chunks][128 rows x 128 B]
   uint8_t* mq_s = x_s + (size_t)p.xs * x_stage_bytes;            // [chunks][64 rows x 128 B]
-  uint8_t* u_s = mq_s + (size_t)p.chunks * 8192;                 // [C rows x 128 B]
-  uint8_t* p_s = u_s + (size_t)p.C * 128;                        // [128 rows x 128 B]  P, then output slab
+  // C = 512: x (128 KB) + Mq (64 KB) + U (64 KB) do not fit; Mq is dead once MMA 1 has retired, so U is loaded over it
+  uint8_t* u_s = p.alias_u ? mq_s : mq_s + (size_t)p.chunks * 8192;   // [C rows x 128 B]
+  uint8_t* p_s = mq_s + (size_t)p.chunks * 8192 + (p.alias_u ? 0 : (size_t)p.C * 128);  // [128 rows x 128 B]  P, then output slab
   float* cs_s = reinterpret_cast<float*>(p_s + 16384);           // [64]
   float* g2_s = cs_s + 64;                                       // [C]
   uint64_t* bars = reinterpret_cast<uint64_t*>(g2_s + p.C);
@@ -146,7 +148,9 @@ xattn_fold_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
   uint64_t* p_ready = bars + 7;
   uint64_t* y_full = bars + 8;
   uint64_t* acc_free = bars + 9;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+  uint64_t* mq_free = bars + 10;   // alias_u: MMA 1 retired (tcgen05.commit) + the column sums of Mq are taken (one arrive)
+  uint64_t* u_full = bars + 11;    // alias_u: U has landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t tmem_cols = p.C < 64 ? 64u : (uint32_t)p.C;  // 64 / 128 / 256 / 512
@@ -162,6 +166,8 @@ xattn_fold_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
     mbar_init(p_ready, 4);
     mbar_init(y_full, 1);
     mbar_init(acc_free, 4);
+    mbar_init(mq_free, 2);
+    mbar_init(u_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -189,9 +195,10 @@ xattn_fold_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
     if (elect_one()) {
       int t = 0;
       if (tile_begin < tile_end) {
-        mbar_expect_tx(w_full, (uint32_t)(p.chunks * 8192 + p.C * 128));
+        mbar_expect_tx(w_full, (uint32_t)(p.chunks * 8192 + (p.alias_u ? 0 : p.C * 128)));
         for (int c = 0; c < p.chunks; ++c) tma_load_3d(&map_mq, w_full, mq_s + (size_t)c * 8192, c * 64, 0, b);
-        for (int r0 = 0; r0 < p.C; r0 += p.NB) tma_load_3d(&map_u, w_full, u_s + (size_t)r0 * 128, 0, r0, b);
+        if (!p.alias_u)
+          for (int r0 = 0; r0 < p.C; r0 += p.NB) tma_load_3d(&map_u, w_full, u_s + (size_t)r0 * 128, 0, r0, b);
       }
       for (int64_t tile = tile_begin; tile < tile_end; ++tile, ++t) {
         const int st = t % p.xs;
@@ -200,6 +207,11 @@ xattn_fold_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
         for (int c = 0; c < p.chunks; ++c)
           tma_load_2d(&map_x, &x_full[st], x_s + (size_t)st * x_stage_bytes + (size_t)c * 16384, c * 64,
                       (int)(tile * TC_BM));
+        if (p.alias_u) {   // one tile per CTA (host): U over Mq as soon as nobody reads Mq any more
+          mbar_wait(mq_free, 0u);
+          mbar_expect_tx(u_full, (uint32_t)(p.C * 128));
+          for (int r0 = 0; r0 < p.C; r0 += p.NB) tma_load_3d(&map_u, u_full, u_s + (size_t)r0 * 128, 0, r0, b);
+        }
       }
     }
   } else if (warp == 1) {
@@ -221,9 +233,11 @@ xattn_fold_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
             umma_f16(tmem_base, ad + (uint64_t)(kk * 2), bd + (uint64_t)(kk * 2), idesc1, (c | kk) != 0);
         }
         umma_commit(s_full);
+        if (p.alias_u) umma_commit(mq_free);
       }
       __syncwarp();
       mbar_wait(p_ready, (uint32_t)(t & 1));  // P written (and the logits read out of TMEM)
+      if (p.alias_u) mbar_wait(u_full, 0u);
       tc_fence_after();
       if (elect_one()) {
         const uint64_t ad = make_smem_desc(smem_u32(p_s));
@@ -263,6 +277,7 @@ xattn_fold_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
       }
     }
     xf_bar();
+    if (p.alias_u && et == 0 && tile_begin < tile_end) mbar_arrive(mq_free);   // the generic reads of Mq are done
     for (int64_t tile = tile_begin; tile < tile_end; ++tile, ++t) {
       const int st = t % p.xs;
       const uint8_t* xrow = x_s + (size_t)st * x_stage_bytes + (size_t)row * 128;
@@ -444,8 +459,8 @@ extern "C" int dv_xattn_fold_prep_multi(const dv_xattn_fold_prep_multi_params* m
 extern "C" int dv_xattn_fold(const dv_xattn_fold_params* p, dv_stream_t stream) {
   using namespace dv;
   DV_REQUIRE(p && p->x && p->out && p->mq && p->u && p->g2, DV_EINVAL, "dv_xattn_fold: null pointer");
-  DV_REQUIRE(p->C == 64 || p->C == 128 || p->C == 256, DV_EUNSUPPORTED,
-             "dv_xattn_fold: C must be 64, 128 or 256 (got %d)", p->C);
+  DV_REQUIRE(p->C == 64 || p->C == 128 || p->C == 256 || p->C == 512, DV_EUNSUPPORTED,
+             "dv_xattn_fold: C must be 64, 128, 256 or 512 (got %d)", p->C);
   DV_REQUIRE(p->heads == 8 && (p->nk == 3 || p->nk == 7), DV_EUNSUPPORTED,
              "dv_xattn_fold: built for 8 heads and 2 or 6 context tokens (+ null key), got heads=%d nk=%d", p->heads, p->nk);
   DV_REQUIRE(p->B > 0 && p->P > 0 && p->P % TC_BM == 0, DV_EUNSUPPORTED,
@@ -458,7 +473,8 @@ extern "C" int dv_xattn_fold(const dv_xattn_fold_params* p, dv_stream_t stream) 
   k.C = p->C;
   k.chunks = p->C / 64;
   k.NB = p->C < 256 ? p->C : 256;
-  k.xs = p->C == 128 ? 1 : 2;  // C = 128: one x stage lets two CTAs share an SM, which hides more than the prefetch did
+  k.alias_u = p->C == 512;
+  k.xs = (p->C == 128 || p->C == 512) ? 1 : 2;  // C = 128: one x stage lets two CTAs share an SM, which hides more than the prefetch did
   k.heads = p->heads;
   k.nk = p->nk;
   k.tiles_per_sample = p->P / TC_BM;
@@ -489,7 +505,7 @@ extern "C" int dv_xattn_fold(const dv_xattn_fold_params* p, dv_stream_t stream) 
     uint32_t box[3] = {64, (uint32_t)k.NB, 1};
     if ((rc = encode_map(&mu, p->u, 3, dims, strides, box)) != DV_OK) return rc;
   }
-  const size_t smem = (size_t)k.xs * k.chunks * 16384 + (size_t)k.chunks * 8192 + (size_t)p->C * 128 + 16384 +
+  const size_t smem = (size_t)k.xs * k.chunks * 16384 + (size_t)k.chunks * 8192 + (k.alias_u ? 0 : (size_t)p->C * 128) + 16384 +
                      64 * 4 + (size_t)p->C * 4 + 256 + 1024;
   static bool attr_set = false;
   if (!attr_set) {
@@ -513,6 +529,8 @@ extern "C" int dv_xattn_fold(const dv_xattn_fold_params* p, dv_stream_t stream) 
   int gx = per_sm * sm_count / p->B;
   if (gx < 1) gx = 1;
   if (gx > k.tiles_per_sample) gx = (int)k.tiles_per_sample;
+  if (k.alias_u) gx = (int)k.tiles_per_sample;   // U replaces Mq after the CTA's only MMA 1
+  DV_REQUIRE(gx <= 65535 * 16, DV_EUNSUPPORTED, "dv_xattn_fold: too many tiles per sample");
   DV_REQUIRE(p->B <= 65535, DV_EUNSUPPORTED, "dv_xattn_fold: more than 65535 samples per launch");
   dim3 grid(gx, p->B);
   if (p->nk == 7)

@@ -1030,7 +1030,7 @@ class _Engine:
         kind, idx = self.kv_idx[id(m)]
         kv = self.kv[kind]
         n_ctx = kv.shape[1]
-        if (self.dtype == torch.bfloat16 and self.u.fuse_short_context_attention and C in (64, 128, 256)
+        if (self.dtype == torch.bfloat16 and self.u.fuse_short_context_attention and C in (64, 128, 256, 512)
                 and P % 128 == 0 and heads == 8 and dh == 64 and (n_ctx + 1) in (3, 7)):
             # short context (time + video tokens): the whole block is one tcgen05 kernel on per-sample folded
             # matrices (include/dv_b200.h, "K5 fused"); the matrices are rebuilt every step (time tokens change)

@@ -674,7 +674,8 @@ def test_conv_pre_norm_is_refused_where_no_kernel_applies_it():
         conv([x], wp, None, out, n_img=2, frames=2, H=8, W=8, k=3, pre=pre)
 
 
-@pytest.mark.parametrize("C,P,B,n_ctx", [(64, 256, 2, 6), (128, 1024, 1, 6), (256, 384, 3, 6), (64, 128, 2, 2)])
+@pytest.mark.parametrize("C,P,B,n_ctx", [(64, 256, 2, 6), (128, 1024, 1, 6), (256, 384, 3, 6), (64, 128, 2, 2), (512, 256, 2, 6),
+                                         (512, 1024, 3, 6), (512, 128, 2, 2)])
 def test_fused_folded_cross_attention_block(C, P, B, n_ctx):
     """dv_xattn_fold_prep + dv_xattn_fold == CrossAttention(x, ctx) + x of the reference (dalle2_video.py:192-201)."""
     from oracle.primitives import CrossAttention
