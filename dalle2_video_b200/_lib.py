@@ -77,7 +77,7 @@ class XattnParams(C.Structure):
 class XattnFoldPrepParams(C.Structure):
     _fields_ = [("kv", vp), ("null_kv", vp), ("wq", vp), ("wout", vp), ("g", vp), ("mq", vp), ("u", vp), ("cs", vp),
                 ("B", i32), ("C", i32), ("heads", i32), ("dh", i32), ("n_ctx", i32), ("kv_ld", i64), ("k_off", i32),
-                ("v_off", i32), ("scale", f32)]
+                ("v_off", i32), ("scale", f32), ("key_begin", i32), ("key_end", i32)]
 
 
 XATTN_FOLD_PREP_MAX = 24  # DV_XATTN_FOLD_PREP_MAX

@@ -20,6 +20,7 @@ namespace dv {
 __device__ __forceinline__ void xattn_fold_prep_body(const dv_xattn_fold_prep_params& p, int b0, int b1) {
   __shared__ float kvs[2][8][64];   // [k | v][key][d] of the current sample
   const int h = blockIdx.y, nk = p.n_ctx + 1, inner = p.heads * 64;
+  const int j_lo = p.key_end > p.key_begin ? p.key_begin : 0, j_hi = p.key_end > p.key_begin ? p.key_end : nk;
   const int tid = threadIdx.y * 64 + threadIdx.x;
   const int c = blockIdx.x * 64 + threadIdx.x;
   const bool valid = c < p.C;
@@ -40,7 +41,7 @@ __device__ __forceinline__ void xattn_fold_prep_body(const dv_xattn_fold_prep_pa
   const float gs = p.scale * p.g[cc];
   for (int b = b0; b < b1; ++b) {
     __syncthreads();
-    for (int i = tid; i < nk * 64; i += 128) {
+    for (int i = tid + j_lo * 64; i < j_hi * 64; i += 128) {
       const int j = i >> 6, d = i & 63;
       if (j == 0) {
         kvs[0][0][d] = p.null_kv[d];
@@ -58,7 +59,7 @@ __device__ __forceinline__ void xattn_fold_prep_body(const dv_xattn_fold_prep_pa
     const float (*src)[64] = kvs[threadIdx.y];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      if (j < nk) {
+      if (j >= j_lo && j < j_hi) {
 #pragma unroll
         for (int d = 0; d < 64; d += 4) {
           const float4 t = *reinterpret_cast<const float4*>(&src[j][d]);
@@ -72,12 +73,12 @@ __device__ __forceinline__ void xattn_fold_prep_body(const dv_xattn_fold_prep_pa
         __nv_bfloat16* mq = reinterpret_cast<__nv_bfloat16*>(p.mq) + (int64_t)b * 64 * p.C;
 #pragma unroll
         for (int j = 0; j < 8; ++j)
-          if (j < nk) mq[(int64_t)(h * nk + j) * p.C + c] = __float2bfloat16_rn(gs * acc[j]);
+          if (j >= j_lo && j < j_hi) mq[(int64_t)(h * nk + j) * p.C + c] = __float2bfloat16_rn(gs * acc[j]);
       } else {
         __nv_bfloat16* u = reinterpret_cast<__nv_bfloat16*>(p.u) + (int64_t)b * p.C * 64;
 #pragma unroll
         for (int j = 0; j < 8; ++j)
-          if (j < nk) u[(int64_t)c * 64 + h * nk + j] = __float2bfloat16_rn(acc[j]);
+          if (j >= j_lo && j < j_hi) u[(int64_t)c * 64 + h * nk + j] = __float2bfloat16_rn(acc[j]);
       }
     }
   }
@@ -423,6 +424,8 @@ extern "C" int dv_xattn_fold_prep(const dv_xattn_fold_prep_params* p, dv_stream_
   DV_REQUIRE(p->B > 0 && p->C > 0 && p->heads > 0 && p->dh == 64 && p->n_ctx >= 0 && p->n_ctx <= 7, DV_EUNSUPPORTED,
              "dv_xattn_fold_prep: needs dim_head 64 and at most 7 context tokens");
   DV_REQUIRE(p->heads * (p->n_ctx + 1) <= 64, DV_EUNSUPPORTED, "dv_xattn_fold_prep: heads*(n_ctx+1) must be <= 64");
+  DV_REQUIRE(p->key_begin >= 0 && p->key_end <= p->n_ctx + 1 && (p->key_end >= p->key_begin), DV_EINVAL,
+             "dv_xattn_fold_prep: key range [%d, %d) outside the %d keys", p->key_begin, p->key_end, p->n_ctx + 1);
   dim3 grid((p->C + 63) / 64, p->heads, (p->B + XF_PREP_SAMPLES - 1) / XF_PREP_SAMPLES);
   xattn_fold_prep_kernel<<<grid, dim3(64, 2), 0, as_stream(stream)>>>(*p);
   DV_CHECK_LAUNCH("dv_xattn_fold_prep");
@@ -444,6 +447,8 @@ extern "C" int dv_xattn_fold_prep_multi(const dv_xattn_fold_prep_multi_params* m
     DV_REQUIRE(p->B > 0 && p->B == mp->layers[0].B && p->C > 0 && p->heads > 0 && p->dh == 64 && p->n_ctx >= 0 && p->n_ctx <= 7 &&
                    p->heads * (p->n_ctx + 1) <= 64,
                DV_EUNSUPPORTED, "dv_xattn_fold_prep_multi: every layer needs the same B, dim_head 64, <= 7 context tokens");
+    DV_REQUIRE(p->key_begin >= 0 && p->key_end <= p->n_ctx + 1 && (p->key_end >= p->key_begin), DV_EINVAL,
+               "dv_xattn_fold_prep_multi: key range [%d, %d) outside the %d keys", p->key_begin, p->key_end, p->n_ctx + 1);
     m.layer[i] = *p;
     if (p->C > cmax) cmax = p->C;
     if (p->heads > hmax) hmax = p->heads;

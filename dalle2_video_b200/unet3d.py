@@ -841,11 +841,17 @@ class _Engine:
         self.final_act = x  # kept alive
         # one launch builds the per-sample folded matrices of every short-context cross-attention layer (they depend on the
         # step's time tokens only); it runs right after the conditioning prologue
+        # Only the time tokens change from step to step: the per-step launch rebuilds keys [1, 1 + num_time_tokens) of every
+        # layer, the null key and the video tokens' keys are built once per conditioning (set_conditioning's static ops)
         for i in range(0, len(self._fold_preps), L.XATTN_FOLD_PREP_MAX):
             chunk = self._fold_preps[i:i + L.XATTN_FOLD_PREP_MAX]
-            arr = (L.XattnFoldPrepParams * len(chunk))(*chunk)
-            self.keep.append(arr)
-            self.ops.insert(prep_at, ("dv_xattn_fold_prep_multi", L.XattnFoldPrepMultiParams(layers=arr, count=len(chunk))))
+            full = (L.XattnFoldPrepParams * len(chunk))(*chunk)
+            step = (L.XattnFoldPrepParams * len(chunk))(*chunk)
+            for q in step:
+                q.key_begin, q.key_end = 1, 1 + nt
+            self.keep += [full, step]
+            self._op("dv_xattn_fold_prep_multi", L.XattnFoldPrepMultiParams(layers=full, count=len(chunk)), static=True)
+            self.ops.insert(prep_at, ("dv_xattn_fold_prep_multi", L.XattnFoldPrepMultiParams(layers=step, count=len(chunk))))
             prep_at += 1
 
     def _init_conv_as_gemm(self, x0, n_img, H, W):

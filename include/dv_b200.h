@@ -364,6 +364,11 @@ typedef struct {
   int64_t kv_ld;
   int k_off, v_off;
   float scale;
+  /* keys [key_begin, key_end) of the 1 + n_ctx keys (key 0 = the null key, key 1 + j = context token j) are (re)built, the
+   * other rows of Mq / columns of U are left as they are; 0, 0 = all.  Inside a sampling loop only the time tokens change
+   * from step to step (:852-855): the host builds everything once per conditioning and keys [1, 1 + num_time_tokens)
+   * every step. */
+  int key_begin, key_end;
 } dv_xattn_fold_prep_params;
 int dv_xattn_fold_prep(const dv_xattn_fold_prep_params* p, dv_stream_t stream);
 /* the same for every folded layer of a denoising step in ONE launch (the per-layer launches are latency bound) */
