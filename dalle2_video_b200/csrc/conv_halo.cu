@@ -742,7 +742,9 @@ int conv_halo_supported(const dv_conv_params& p) {
   if (p.epilogue != DV_EPI_STORE || (p.add && p.stats) || p.add_stats) return 0;
   if (p.Cout != 64 && p.Cout != 128) return 0;
   if (p.C0 % TC_BK || p.C1 % TC_BK) return 0;
-  if (p.W < 32 || p.W > 128 || p.H < 8) return 0;
+  if (p.W < 16 || p.W > 128 || p.H < 8) return 0;
+  // the epilogue allows one frame boundary inside a tile: the <= (Wp + 254) / Wp padded rows a tile spans must fit a frame
+  if ((p.W + 2 + 254) / (p.W + 2) > p.H + 1) return 0;
   if (p.n_img % p.frames) return 0;
   if (((int64_t)p.n_img * (p.H + 1) + 2) * (p.W + 2) >= (1ll << 30)) return 0;  // 32-bit index arithmetic in the kernel
   const int out_ld = p.out_ld ? p.out_ld : p.Cout;

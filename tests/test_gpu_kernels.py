@@ -521,6 +521,9 @@ HALO_CASES = [
     dict(B=1, T=2, H=16, W=64, C=(64,), Co=64),                      # non-square
     dict(B=2, T=2, H=64, W=64, C=(64,), Co=64, add=True),            # + residual (gradient accumulation of the dgrad)
     dict(B=1, T=2, H=32, W=32, C=(128,), Co=128, add=True),
+    dict(B=2, T=3, H=16, W=16, C=(128,), Co=128, stats=True),        # 16x16: a tile spans 15 of the 17 padded rows of a frame
+    dict(B=2, T=2, H=16, W=16, C=(64, 64), Co=64, stats=True),       # 16x16, tap pairing
+    dict(B=1, T=2, H=16, W=16, C=(64,), Co=64, add=True),
 ]
 
 
