@@ -141,9 +141,11 @@ class _TrainPlan:
 
     # -------------------------------------------------------------- layers
     def _conv(self, srcs, w5_fn, bias_fn, param_w, from5, param_b, Co, n_img, h, w, *, k=1, mode=L.CONV_NORMAL, stats=None,
-              groups=0, bias_unperm=None, frames=None):
+              groups=0, bias_unperm=None, frames=None, add_norm=None):
         """One convolution / linear.  w5_fn() -> canonical [Co][Ci][1][kh][kw] float32 view of the parameter;
-        from5(g5) maps a gradient in that view back to the parameter's shape."""
+        from5(g5) maps a gradient in that view back to the parameter's shape.  `add_norm` = (raw tensor, statistics slot,
+        GroupNorm): the epilogue adds SiLU(GroupNorm(raw)) (dv_conv_params.add_*; the tail of ResnetBlock3D.forward,
+        :203-205) — d out / d conv = 1, so this op's own backward is unchanged; the caller adds the GroupNorm's."""
         ho, wo = (h // 2, w // 2) if mode == L.CONV_UNSHUFFLE else (h, w)
         rows_out = n_img * ho * wo
         kh = kw = 2 if mode == L.CONV_UNSHUFFLE else k
@@ -154,12 +156,17 @@ class _TrainPlan:
         bf = self._f32(bias_fn) if bias_fn is not None else None
         rows_per_sample = rows_out // self.B
         fused_stats = stats is not None and rows_per_sample % 64 == 0
+        an = {}
+        if add_norm is not None:
+            raw, st_ptr, norm, gamma, beta = add_norm
+            an = dict(add=raw.ptr, add_stats=st_ptr, add_gamma=gamma.data_ptr(), add_beta=beta.data_ptr(),
+                      add_groups=norm.num_groups, add_eps=float(norm.eps))
         self.fwd.append(("dv_conv_igemm", L.ConvParams(
             src0=srcs[0].ptr, src1=srcs[1].ptr if len(srcs) > 1 else None, weight=wf.data_ptr(),
-            bias=bf.data_ptr() if bf is not None else None, add=None, out=out.ptr, stats=stats if fused_stats else None,
+            bias=bf.data_ptr() if bf is not None else None, out=out.ptr, stats=stats if fused_stats else None,
             n_img=n_img, frames=frames or self.T,
             H=h, W=w, C0=cin[0], C1=cin[1] if len(srcs) > 1 else 0, Cout=Co, kh=k, kw=k, pad=k // 2, mode=mode,
-            epilogue=L.EPI_STORE, groups=groups, out_ld=0, out_coff=0, dtype=self.code, impl=0)))
+            epilogue=L.EPI_STORE, groups=groups, out_ld=0, out_coff=0, dtype=self.code, impl=0, **an)))
         if stats is not None and not fused_stats:
             self.fwd.append(("dv_gn_stats", L.GnStatsParams(x=out.ptr, stats=stats, B=self.B, P=rows_per_sample, C=Co,
                                                             groups=groups, dtype=self.code)))
@@ -201,7 +208,7 @@ class _TrainPlan:
         self.tape.append(backward)
         return out
 
-    def _std_conv(self, srcs, conv: nn.Conv3d, n_img, h, w, k, stats=None, groups=0, skip_scale=1.0):
+    def _std_conv(self, srcs, conv: nn.Conv3d, n_img, h, w, k, stats=None, groups=0, skip_scale=1.0, add_norm=None):
         """`skip_scale`: the second source is a skip connection the reference multiplies by skip_connect_scale before the
         concat (:926-928, :945).  The factor is folded into that source's weight columns, so the forward and the
         data-gradient use the scaled weights as they are and the weight gradient of those columns gets the factor back."""
@@ -221,7 +228,7 @@ class _TrainPlan:
             return g5
 
         return self._conv(srcs, w5, lambda: conv.bias.detach().float(), conv.weight, from5, conv.bias,
-                          conv.weight.shape[0], n_img, h, w, k=k, stats=stats, groups=groups)
+                          conv.weight.shape[0], n_img, h, w, k=k, stats=stats, groups=groups, add_norm=add_norm)
 
     def _linear(self, src, lin_weight: nn.Parameter, rows):
         """bias-free nn.Linear on a [rows][K] activation, as a 1x1 convolution (to_q / to_kv / to_out projections)."""
@@ -245,6 +252,15 @@ class _TrainPlan:
             x=xraw.ptr, out=out.ptr, residual=residual.ptr if residual is not None else None, stats=st_ptr,
             gamma=gamma.data_ptr(), beta=beta.data_ptr(), scale=sc, shift=sh, ss_ld=self.ss_total, B=B, P=P, C=C,
             groups=G, eps=float(norm.eps), dtype=self.code)))
+        self._gn_backward(xraw, st_ptr, norm, gamma, beta, ss_off, residual, P, out)
+        return out
+
+    def _gn_backward(self, xraw, st_ptr, norm, gamma, beta, ss_off, residual, P, out):
+        """Tape entry of out = SiLU(GroupNorm(xraw) * (1+scale) + shift) [+ residual]: gradients of xraw, gamma / beta, the
+        scale / shift rows and (a plain copy of dy) the residual."""
+        B, C, G = self.B, xraw.C, norm.num_groups
+        sc = self.ss.data_ptr() + ss_off * 4 if ss_off is not None else None
+        sh = self.ss.data_ptr() + (ss_off + C) * 4 if ss_off is not None else None
         gg, gbt = self._galloc(C), self._galloc(C)
         self._gmap((norm.weight, lambda: self._g(gg)))
         self._gmap((norm.bias, lambda: self._g(gbt)))
@@ -267,7 +283,6 @@ class _TrainPlan:
                 self._grad_add(residual, dy)
 
         self.tape.append(backward)
-        return out
 
     def _layernorm(self, x: _Var, g: nn.Parameter, residual=None, eps=1e-5):
         out = self._var(x.rows, x.C)
@@ -382,8 +397,27 @@ class _TrainPlan:
         if isinstance(m.res_conv, nn.Identity):
             res = srcs[0]
         else:
+            norm2 = m.block2.norm
+            if self.u.fuse_residual_norm and self._add_norm_ok(srcs, h2r, st2, norm2, n_img, h, w):
+                # `h + res_conv(x)` as ONE launch: block2's GroupNorm + SiLU is applied to the raw h in res_conv's epilogue
+                # (the sampler's form, unet3d._resblock); its gradient reaches res_conv unchanged — no gradient copy either
+                gamma = self._f32(lambda: norm2.weight.detach().float())
+                beta = self._f32(lambda: norm2.bias.detach().float())
+                out = self._std_conv(srcs, m.res_conv, n_img, h, w, 1, skip_scale=skip_scale,
+                                     add_norm=(h2r, st2, norm2, gamma, beta))
+                self._gn_backward(h2r, st2, norm2, gamma, beta, None, None, P, out)
+                return out
             res = self._std_conv(srcs, m.res_conv, n_img, h, w, 1, skip_scale=skip_scale)
         return self._gn_block(h2r, st2, m.block2.norm, None, res, P)
+
+    def _add_norm_ok(self, srcs, raw, st_ptr, norm, n_img, h, w):
+        probe = L.ConvParams(src0=srcs[0].ptr, src1=srcs[1].ptr if len(srcs) > 1 else None, weight=1 << 20, bias=None,
+                             add=raw.ptr, out=1 << 20, stats=None, n_img=n_img, frames=self.T, H=h, W=w, C0=srcs[0].C,
+                             C1=srcs[1].C if len(srcs) > 1 else 0, Cout=raw.C, kh=1, kw=1, pad=0, mode=L.CONV_NORMAL,
+                             epilogue=L.EPI_STORE, groups=0, out_ld=0, out_coff=0, dtype=self.code, impl=0,
+                             add_stats=st_ptr, add_gamma=1 << 20, add_beta=1 << 20, add_groups=norm.num_groups,
+                             add_eps=float(norm.eps))
+        return bool(L.lib().dv_conv_add_norm_supported(probe))
 
     # -------------------------------------------------------------- plan construction
     def _build(self):
