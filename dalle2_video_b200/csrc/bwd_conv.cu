@@ -177,6 +177,54 @@ __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ x, fl
   for (int c = threadIdx.x; c < C; c += blockDim.x) atomicAdd(out + c, part[c]);
 }
 
+// float32 parity path (and any channel count that is a multiple of 4): CTA = (position chunk, tap, 16 x 16 tile of
+// (co, ci)); 16-position slices of dY and the tap-shifted X staged in shared memory, fp32 FMAs, chunks reduced with atomics.
+template <typename T>
+__global__ void __launch_bounds__(256) conv_wgrad_simt_kernel(const dv_conv_wgrad_params p, int Ho, int Wo, int64_t rows,
+                                                              int64_t rows_per_cta, int n_ci_tiles) {
+  __shared__ float As[16][17], Bs[16][17];   // [pos][co], [pos][ci]
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;   // tx: ci (and the column a thread loads), ty: co (and the position)
+  const int tap = blockIdx.y;
+  const int co0 = (blockIdx.z / n_ci_tiles) * 16, ci0 = (blockIdx.z % n_ci_tiles) * 16;
+  const int Ct = p.C0 + p.C1;
+  int dyo, dxo;
+  if (p.mode == DV_CONV_UNSHUFFLE) { dyo = tap >> 1; dxo = tap & 1; }
+  else { dyo = tap / p.kw - (p.kh >> 1); dxo = tap % p.kw - (p.kw >> 1); }
+  const T* dy = reinterpret_cast<const T*>(p.dy);
+  const int64_t r_begin = (int64_t)blockIdx.x * rows_per_cta;
+  const int64_t r_end = r_begin + rows_per_cta < rows ? r_begin + rows_per_cta : rows;
+  float acc = 0.f;
+  for (int64_t r0 = r_begin; r0 < r_end; r0 += 16) {
+    const int64_t r = r0 + ty;
+    float a = 0.f, b = 0.f;
+    if (r < r_end) {
+      if (co0 + tx < p.Cout) a = to_f<T>(dy[r * p.Cout + co0 + tx]);
+      const int ci = ci0 + tx;
+      if (ci < Ct) {
+        const int img = (int)(r / ((int64_t)Ho * Wo));
+        const int rem = (int)(r - (int64_t)img * Ho * Wo);
+        const int oy = rem / Wo, ox = rem - oy * Wo;
+        int iy, ix;
+        if (p.mode == DV_CONV_UNSHUFFLE) { iy = 2 * oy + dyo; ix = 2 * ox + dxo; }
+        else { iy = oy + dyo; ix = ox + dxo; }
+        if ((unsigned)iy < (unsigned)p.H && (unsigned)ix < (unsigned)p.W) {
+          const int64_t pix = ((int64_t)img * p.H + iy) * p.W + ix;
+          b = ci < p.C0 ? to_f<T>(reinterpret_cast<const T*>(p.src0)[pix * p.C0 + ci])
+                        : to_f<T>(reinterpret_cast<const T*>(p.src1)[pix * p.C1 + ci - p.C0]);
+        }
+      }
+    }
+    __syncthreads();
+    As[ty][tx] = a;
+    Bs[ty][tx] = b;
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 16; ++k) acc = fmaf(As[k][ty], Bs[k][tx], acc);
+  }
+  const int taps = p.mode == DV_CONV_UNSHUFFLE ? 4 : p.kh * p.kw;
+  if (co0 + ty < p.Cout && ci0 + tx < Ct) atomicAdd(p.dw + (int64_t)(co0 + ty) * taps * Ct + tap * Ct + ci0 + tx, acc);
+}
+
 int wgrad_tc_supported(const dv_conv_wgrad_params& p);
 int wgrad_tc_launch(const dv_conv_wgrad_params& p, cudaStream_t s);
 
@@ -192,7 +240,30 @@ extern "C" int dv_conv_wgrad(const dv_conv_wgrad_params* p, dv_stream_t stream) 
   DV_REQUIRE(p->n_img > 0 && p->H > 0 && p->W > 0 && p->C0 > 0 && p->C1 >= 0 && p->Cout > 0, DV_EINVAL,
              "dv_conv_wgrad: non-positive dimension");
   DV_REQUIRE((p->C1 == 0) == (p->src1 == nullptr), DV_EINVAL, "dv_conv_wgrad: src1 / C1 mismatch");
-  DV_REQUIRE(p->dtype == DV_BF16, DV_EUNSUPPORTED, "dv_conv_wgrad: bf16 activations only");
+  DV_REQUIRE(p->dtype == DV_BF16 || p->dtype == DV_F32, DV_EINVAL, "dv_conv_wgrad: bad dtype");
+  if (p->dtype == DV_F32 || p->impl == 3) {
+    // float32 parity path (impl 3 forces it for bf16 as well)
+    DV_REQUIRE(p->mode == DV_CONV_UNSHUFFLE || (p->mode == DV_CONV_NORMAL && p->kh % 2 == 1 && p->kw % 2 == 1), DV_EUNSUPPORTED,
+               "dv_conv_wgrad: NORMAL ('same', odd kernel) or UNSHUFFLE mode only");
+    if (p->mode == DV_CONV_UNSHUFFLE)
+      DV_REQUIRE(p->H % 2 == 0 && p->W % 2 == 0 && p->C1 == 0, DV_EINVAL, "dv_conv_wgrad: unshuffle needs even H, W and one source");
+    const int Ho = p->mode == DV_CONV_UNSHUFFLE ? p->H / 2 : p->H, Wo = p->mode == DV_CONV_UNSHUFFLE ? p->W / 2 : p->W;
+    const int taps = p->mode == DV_CONV_UNSHUFFLE ? 4 : p->kh * p->kw;
+    const int64_t rows = (int64_t)p->n_img * Ho * Wo;
+    const int n_co = (p->Cout + 15) / 16, n_ci = (p->C0 + p->C1 + 15) / 16;
+    DV_REQUIRE((int64_t)n_co * n_ci <= 65535 && taps <= 65535, DV_EUNSUPPORTED, "dv_conv_wgrad: grid too large");
+    int64_t chunks = (148 * 8 + (int64_t)taps * n_co * n_ci - 1) / ((int64_t)taps * n_co * n_ci);
+    const int64_t max_chunks = (rows + 255) / 256;
+    if (chunks > max_chunks) chunks = max_chunks;
+    if (chunks < 1) chunks = 1;
+    int64_t rpc = ((rows + chunks - 1) / chunks + 15) / 16 * 16;
+    chunks = (rows + rpc - 1) / rpc;
+    dim3 grid((unsigned)chunks, (unsigned)taps, (unsigned)(n_co * n_ci));
+    if (p->dtype == DV_F32) conv_wgrad_simt_kernel<float><<<grid, 256, 0, as_stream(stream)>>>(*p, Ho, Wo, rows, rpc, n_ci);
+    else conv_wgrad_simt_kernel<__nv_bfloat16><<<grid, 256, 0, as_stream(stream)>>>(*p, Ho, Wo, rows, rpc, n_ci);
+    DV_CHECK_LAUNCH("dv_conv_wgrad(simt)");
+    return DV_OK;
+  }
   DV_REQUIRE(p->C0 % 8 == 0 && p->C1 % 8 == 0 && p->Cout % 8 == 0, DV_EALIGN, "dv_conv_wgrad: channel counts must be multiples of 8");
   DV_REQUIRE(aligned16(p->src0) && aligned16(p->src1) && aligned16(p->dy), DV_EALIGN, "dv_conv_wgrad: pointers must be 16-byte aligned");
   {

@@ -67,14 +67,18 @@ class _Var:
 
 
 class _TrainPlan:
-    def __init__(self, unet: Unet3D, B, T, H, W, device):
+    def __init__(self, unet: Unet3D, B, T, H, W, device, dtype=torch.bfloat16):
         u = unet
         if u.cond_on_text_encodings:
             raise NotImplementedError("training with text conditioning has no backward kernels yet (long-context cross attention)")
         if u.temporal_conv or any(u._stage_temporal_attn) or u.attn_mode != "joint":
             raise NotImplementedError("the extensions (temporal conv / attention, factorised attention) have no backward kernels")
         self.u, self.B, self.T, self.H, self.W, self.device = u, B, T, H, W, device
-        self.code = L.DV_BF16
+        # bf16: the production mode (tcgen05 kernels).  float32: the parity mode — every activation, weight copy and
+        # activation gradient in float32 on the CUDA-core kernels, for a per-step check against autograd at 1e-4
+        assert dtype in (torch.bfloat16, torch.float32)
+        self.dtype = dtype
+        self.code = L.dtype_code(dtype)
         L.lib()
         self.fwd, self.bwd, self.tape = [], [], []
         self.keep = []
@@ -102,7 +106,7 @@ class _TrainPlan:
         return t
 
     def _w(self, producer):
-        return self._bind(producer, torch.bfloat16)
+        return self._bind(producer, self.dtype)
 
     def _f32(self, producer):
         return self._bind(producer, torch.float32)
@@ -124,7 +128,7 @@ class _TrainPlan:
         return self.gbufs[idx].data_ptr()
 
     def _var(self, rows, C):
-        return _Var(rows, C, self.device)
+        return _Var(rows, C, self.device, self.dtype)
 
     def _grad_target(self, v: _Var):
         """(pointer to v.grad, whether it already holds a value that must be accumulated into)."""
@@ -375,7 +379,10 @@ class _TrainPlan:
             assert not r1 and not r2
             bp.dq, bp.rowstats = dq, rs.data_ptr()
             self.bwd.append(("dv_attn_mqa_bwd", bp))
-            self.bwd.append(("dv_cast_f32_bf16", L.CastParams(src=dkv32.data_ptr(), dst=dk, n=dkv32.numel())))
+            if self.dtype == torch.float32:   # parity mode: the key/value gradient stays float32 (a plain copy)
+                self.bwd.append(("dv_add", L.AddParams(a=dkv32.data_ptr(), b=None, out=dk, n=dkv32.numel(), dtype=self.code)))
+            else:
+                self.bwd.append(("dv_cast_f32_bf16", L.CastParams(src=dkv32.data_ptr(), dst=dk, n=dkv32.numel())))
 
         self.tape.append(backward)
         y = self._linear(o, at.to_out[0].weight, x.rows)
@@ -471,7 +478,7 @@ class _TrainPlan:
         assert all(k % 2 == 1 for k in ks) and kmax <= 16
         ktot = cin * kmax * 16
         kpad = (ktot + 63) // 64 * 64
-        patches = _Var(rows, kpad, dev)  # kept for the weight gradient; no data-gradient (network input)
+        patches = self._var(rows, kpad)  # kept for the weight gradient; no data-gradient (network input)
         self.fwd.append(("dv_im2col_init", L.Im2colParams(x=self.x_in.data_ptr(), out=patches.ptr, B=B, C=cin, T=T, H=H, W=W,
                                                           k=kmax, Kpad=kpad, dtype=self.code, layout=1)))
 

@@ -375,7 +375,9 @@ class Unet3D(nn.Module):
     def train_plan(self, batch, frames, height, width, device):
         """Forward + backward launch plan of the training step (dalle2_video_b200/train.py)."""
         from .train import _TrainPlan
-        key = ("train", batch, frames, height, width, str(device))
+        # bf16 unless float32 is asked for explicitly (unet.compute_dtype = torch.float32: the parity mode)
+        dtype = torch.float32 if self.compute_dtype == torch.float32 else torch.bfloat16
+        key = ("train", batch, frames, height, width, str(device), dtype)
         pl = self._engines.get(key)
         # the plan's captured graphs bake in the parameters' storage pointers: unet.to(...) / .float() / a re-flattening
         # optimiser moves them, and a stale plan would read freed memory
@@ -383,7 +385,7 @@ class Unet3D(nn.Module):
         if pl is not None and pl.param_signature != sig:
             pl = None
         if pl is None:
-            pl = _TrainPlan(self, batch, frames, height, width, device)
+            pl = _TrainPlan(self, batch, frames, height, width, device, dtype)
             pl.param_signature = sig
             self._engines[key] = pl
         self._train_plan_last = pl

@@ -600,17 +600,17 @@ int dv_mha_small(const dv_mha_small_params* p, dv_stream_t stream);
 /* dW[co][tap*(C0+C1)+ci] += sum_pos dY[pos][co] * X[pos (+) tap][ci]; dw is float32 in the packed-weight layout of
  * dv_conv_igemm and must be zeroed by the caller (results are accumulated with atomics). */
 typedef struct {
-  const void* src0;  /* forward inputs, bf16 channels-last */
+  const void* src0;  /* forward inputs, channels-last, act dtype */
   const void* src1;  /* NULL when C1 == 0 */
-  const void* dy;    /* [n_img][Ho][Wo][Cout] bf16 */
+  const void* dy;    /* [n_img][Ho][Wo][Cout] act dtype */
   float* dw;         /* [Cout][taps*(C0+C1)] */
   int n_img, H, W;   /* input spatial size (output is H/2 x W/2 in UNSHUFFLE mode) */
   int C0, C1, Cout;
   int kh, kw;
   int mode;          /* DV_CONV_NORMAL or DV_CONV_UNSHUFFLE */
-  dv_dtype dtype;    /* DV_BF16 */
+  dv_dtype dtype;    /* DV_BF16, or DV_F32 (float32 parity mode: CUDA-core kernel) */
   int impl;          /* 0: auto (tcgen05 when the shape fits: channels % 64, 64-position TMA boxes); 1: the mma.sync
-                        kernel; 2: tcgen05 or DV_EUNSUPPORTED */
+                        kernel; 2: tcgen05 or DV_EUNSUPPORTED; 3: the CUDA-core kernel (any dtype) */
 } dv_conv_wgrad_params;
 int dv_conv_wgrad(const dv_conv_wgrad_params* p, dv_stream_t stream);
 int dv_conv_wgrad_uses_tcgen05(const dv_conv_wgrad_params* p);
