@@ -623,14 +623,21 @@ class VideoDecoder(nn.Module):
         """Reference: dalle2_video.py:1620-1664.  One step with per-sample timesteps `t` (B,), through the fused
         kernel when all samples share the timestep, else through the table gathers."""
         self._check_native(predict_x_start, predict_v, learned_variance, lowres_cond_vid, lowres_noise_level)
+        # `t` may live on the host (a serving loop knows its timestep): then nothing in this call reads device memory back
+        # and the host keeps running ahead of the GPU; a device `t` costs one small read-back (the reference's own
+        # `times` tensors are device tensors, :1689)
+        t_cpu = t if not t.is_cuda else None
+        if t_cpu is not None:
+            t = t_cpu.to(x.device, non_blocking=True)
         eps = unet.forward_with_cond_scale(x, t, video_embed=video_embed, text_encodings=text_encodings,
                                            cond_scale=cond_scale, self_cond=self_cond,
                                            lowres_cond_video=lowres_cond_vid, lowres_noise_level=lowres_noise_level)
         if noise is None:
             noise = torch.randn_like(x)
-        t0 = int(t[0])
+        t_probe = t_cpu if t_cpu is not None else t
+        t0 = int(t_probe[0])
         plain = not (predict_x_start or predict_v or (self.use_dynamic_thres and clip_denoised))
-        if plain and bool((t == t0).all()):
+        if plain and bool((t_probe == t0).all()):
             sched = noise_scheduler
             coef = sched.coef_table().to(x.device)
             out = torch.empty_like(x)

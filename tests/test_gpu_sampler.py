@@ -104,6 +104,11 @@ def test_p_sample_single_step_api(layouts):
     t2 = torch.tensor([0, 9]).cuda()
     out2, _ = d.p_sample(d.unets[0], x, t2, emb, s, noise=noise)
     assert float((out2[1] - out[1]).abs().max()) < 1e-5
+    # a host-side `t` (pinned or not) gives the same step without any device read-back inside the call
+    for th in (torch.tensor([9, 9]), torch.tensor([9, 9]).pin_memory(), torch.tensor([0, 9])):
+        out3, x03 = d.p_sample(d.unets[0], x, th, emb, s, noise=noise)
+        ref3 = out if int(th[0]) == 9 else out2
+        assert out3.is_cuda and float((out3 - ref3).abs().max()) < 1e-5
 
 
 # ------------------------------------------------------------------ DDIM / strided sampling (scope row N1)
