@@ -256,7 +256,7 @@ __global__ void __launch_bounds__(TA_THREADS, 4) attn_temporal_kernel(const dv_a
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// tcgen05 form (bf16, dh = 32, T in {8, 16, 32}, heads a multiple of 128 / T).  The mma.sync kernel above spends ~200
+// tcgen05 form (bf16, dh = 32, T in {8, 16, 24, 32}, heads a multiple of 128 / T — of 4 at T = 24, where a tile is 96 rows).  The mma.sync kernel above spends ~200
 // warp instructions per (pixel, head) on fragment loads, quad shuffles and the null-key special case and is issue /
 // latency bound at 0.35-0.49 of the HBM rate; here ONE thread owns one (frame, head) row of a 128-row tile:
 //   tile    = the T frames x HG = 128 / T heads of one pixel: Q [128 rows][32] K-major SWIZZLE_64B, brought in by ONE 4-D
@@ -275,7 +275,8 @@ __global__ void __launch_bounds__(TA_THREADS, 4) attn_temporal_kernel(const dv_a
 // 160 threads x <= 80 registers: five CTAs per SM (four at T = 32) keep five tile chains in flight.
 constexpr int TT_THREADS = 160;
 template <int T> struct TtCfg {
-  static constexpr int NS = T == 8 ? 16 : (T == 16 ? 32 : 48);   // keys incl. the null key, padded to the MMA granularity
+  static constexpr int NS = T == 8 ? 16 : (T <= 24 ? 32 : 48);   // keys incl. the null key, padded to the MMA granularity
+  static constexpr int HG = T == 24 ? 4 : 128 / T;               // heads per tile (T = 24: 96 of the 128 rows are used)
   static constexpr int P_ROW = T == 32 ? 128 : 64;               // bytes per P row (K-major, SWIZZLE_128B / SWIZZLE_64B)
   static constexpr int STAGES = T == 32 ? 2 : 3;
   static constexpr int CTAS = 4;
@@ -380,7 +381,7 @@ attn_temporal_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_
       const int b = (int)(pix / p.HW), hw = (int)(pix - (int64_t)b * p.HW);
       const int st = i % TT_STAGES;
       uint8_t* dst = ring + (size_t)st * STAGE;
-      mbar_expect_tx(&full[st], (uint32_t)(Q_BYTES + 2 * T * 64));
+      mbar_expect_tx(&full[st], (uint32_t)(T * TtCfg<T>::HG * 64 + 2 * T * 64));
       tma_load_4d(&map_q, &full[st], dst, 0, hgroup * pp.hg, hw, b * T);
       tma_load_3d_t(&map_kv, &full[st], dst + Q_BYTES, 0, hw, b * T);
       tma_load_3d_t(&map_kv, &full[st], dst + Q_BYTES + KV_BYTES, 32, hw, b * T);
@@ -430,7 +431,8 @@ attn_temporal_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_
     // ================================================================ softmax + output: one (frame, head) row per thread
     const int q = warp & 3;
     const int row = q * 32 + lane;
-    const int t_row = row / pp.hg, h = hgroup * pp.hg + row % pp.hg;
+    const bool live = row < T * TtCfg<T>::HG;   // T = 24: rows 96..127 of the tile are unused (their results are never stored)
+    const int t_row = live ? row / pp.hg : 0, h = hgroup * pp.hg + (live ? row % pp.hg : 0);
     const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
     const float LOG2E = 1.4426950408889634f;
     const float sl2 = p.scale * LOG2E;
@@ -501,7 +503,7 @@ attn_temporal_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_
         uint4* dst = reinterpret_cast<uint4*>(outp + tok * inner + h * 32);
 #pragma unroll
         for (int c = 0; c < 4; ++c)
-          dst[c] = make_uint4(pack_bf16(__uint_as_float(r[8 * c]) * inv, __uint_as_float(r[8 * c + 1]) * inv),
+          if (live) dst[c] = make_uint4(pack_bf16(__uint_as_float(r[8 * c]) * inv, __uint_as_float(r[8 * c + 1]) * inv),
                               pack_bf16(__uint_as_float(r[8 * c + 2]) * inv, __uint_as_float(r[8 * c + 3]) * inv),
                               pack_bf16(__uint_as_float(r[8 * c + 4]) * inv, __uint_as_float(r[8 * c + 5]) * inv),
                               pack_bf16(__uint_as_float(r[8 * c + 6]) * inv, __uint_as_float(r[8 * c + 7]) * inv));
@@ -519,8 +521,8 @@ attn_temporal_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_
 
 static bool tc_kernel_ok(const dv_attn_temporal_params& p) {
   if (p.dtype != DV_BF16 || p.dh != TA_DH) return false;
-  if (p.T != 8 && p.T != 16 && p.T != 32) return false;
-  const int hg = 128 / p.T;
+  if (p.T != 8 && p.T != 16 && p.T != 24 && p.T != 32) return false;
+  const int hg = p.T == 24 ? 4 : 128 / p.T;
   if (p.heads % hg || p.heads > 64) return false;
   if ((int64_t)p.B * p.T * p.HW >= (1ll << 31)) return false;
   return true;
@@ -531,7 +533,7 @@ static int launch_tc_kernel(const dv_attn_temporal_params& p, cudaStream_t s) {
   TemporalTcParams k;
   memset(&k, 0, sizeof(k));
   k.a = p;
-  k.hg = 128 / T;
+  k.hg = TtCfg<T>::HG;
   k.tpp = p.heads / k.hg;
   k.pixels = (int64_t)p.B * p.HW;
   const int inner = p.heads * TA_DH;
@@ -666,6 +668,7 @@ extern "C" int dv_attn_temporal(const dv_attn_temporal_params* p, dv_stream_t st
     switch (p->T) {
       case 8: rc = launch_tc_kernel<8>(*p, s); break;
       case 16: rc = launch_tc_kernel<16>(*p, s); break;
+      case 24: rc = launch_tc_kernel<24>(*p, s); break;
       default: rc = launch_tc_kernel<32>(*p, s); break;
     }
     if (rc != DV_OK) return rc;

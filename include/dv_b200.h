@@ -431,10 +431,10 @@ int64_t dv_attn_mqa_workspace_bytes(const dv_attn_mqa_params* p);
  * (column 0 is the null key).  The channels-last buffers are read in place: the
  * sequence of pixel (b, hw) is the T rows {((b*T + t)*HW + hw)}.
  * q: [B][T][HW][heads*dh], kv: [B][T][HW][2*dh] (k then v), out like q (may alias q).
- * bf16, dh = 32, T in {8,16,32}, heads a multiple of 128 / T: tcgen05 kernel — a tile is the T frames x 128/T heads of one
+ * bf16, dh = 32, T in {8,16,24,32}, heads a multiple of 128 / T (of 4 at T = 24): tcgen05 kernel — a tile is the T frames x 128/T heads of one
  *   pixel (one 4-D TMA box of the channels-last tensor), one (frame, head) row per thread, the null key as row T of the
- *   K / V tiles; 0.75-0.77 of the measured HBM rate at T = 8 / 16 on a 1.1 GB working set (profiles/r02_kernel_sweep_*).
- * bf16, dh = 32, T in {8,16,24,32}, heads % 4 == 0: warp-level mma.sync kernel with cp.async staging (T = 24, impl = 2);
+ *   K / V tiles; 0.75 / 0.77 / 0.68 / 0.53 of the measured HBM rate at T = 8 / 16 / 24 / 32 on a 1.1-2.3 GB working set (profiles/r02_kernel_sweep_*).
+ * bf16, dh = 32, T in {8,16,24,32}, heads % 4 == 0: warp-level mma.sync kernel with cp.async staging (impl = 2);
  * anything else (fp32 parity mode, other T): CUDA-core kernel.
  */
 typedef struct {

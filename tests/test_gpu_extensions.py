@@ -60,7 +60,7 @@ def test_temporal_attention_mma_kernel(T, heads, use_bias):
     assert torch.equal(q2, out)
 
 
-@pytest.mark.parametrize("T,heads", [(8, 16), (16, 16), (32, 16), (16, 8), (32, 4), (8, 32)])
+@pytest.mark.parametrize("T,heads", [(8, 16), (16, 16), (32, 16), (16, 8), (32, 4), (8, 32), (24, 16), (24, 4)])
 @pytest.mark.parametrize("use_bias", [True, False])
 @pytest.mark.parametrize("B,HW", [(2, 64), (3, 50), (1, 1)])
 def test_temporal_attention_tcgen05_kernel(T, heads, use_bias, B, HW):
