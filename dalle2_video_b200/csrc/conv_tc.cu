@@ -51,7 +51,7 @@ struct TcParams {
   const float* add_beta;
   int add_groups;
   float add_eps;
-  int add_ring;  // TC_ADD_RING when the residual operand comes in through the TMA ring (add_stats), else 0
+  int add_ring;  // slabs of the residual operand in flight (TMA ring): TC_ADD_RING (2 at N = 256) with add_stats, else 0
 };
 
 // ------------------------------------------------------------------------------------------ the kernel
@@ -228,7 +228,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
       }
     };
     if (p.add_ring && issuer)
-      for (int a = 0; a < TC_ADD_RING; ++a) issue_add(a, a);
+      for (int a = 0; a < p.add_ring; ++a) issue_add(a, a);
     const uint32_t rps = (uint32_t)p.rows_per_sample;
     for (uint32_t tile = (uint32_t)tile_begin; tile < (uint32_t)tile_end; ++tile) {
       const uint32_t m_tile = tile / (uint32_t)p.n_tiles_n;
@@ -368,9 +368,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
         epi_bar();
         if (p.add_ring) {
           // every epilogue thread has read this item's residual slab: refill its slot with the item TC_ADD_RING ahead
-          if (issuer) issue_add(add_item + TC_ADD_RING, add_slot);
+          if (issuer) issue_add(add_item + p.add_ring, add_slot);
           ++add_item;
-          if (++add_slot == TC_ADD_RING) { add_slot = 0; add_phase ^= 1; }
+          if (++add_slot == p.add_ring) { add_slot = 0; add_phase ^= 1; }
         }
         {
           // row r of the slab = 128 bytes; 16-byte chunk index is XOR-swizzled with (r % 8)
@@ -505,7 +505,6 @@ int conv_tc_supported(const dv_conv_params& p) {
     // GroupNorm + SiLU of the residual operand: plain epilogue, statistics of whole groups
     if (!p.add || !p.add_gamma || !p.add_beta || p.epilogue != DV_EPI_STORE) return 0;
     if (p.add_groups <= 0 || p.Cout % p.add_groups) return 0;
-    if (bn > 128) return 0;   // the residual ring (48 KB) would leave the N = 256 pipeline two stages
   }
   return 1;
 }
@@ -601,8 +600,9 @@ int conv_tc_launch(const dv_conv_params& p, cudaStream_t s) {
   const int stage_bytes = TC_BM * TC_BK * 2 + t.BN * TC_BK * 2;
   // the coefficient table of the fused residual GroupNorm comes out of the operand pipeline (the launch already uses
   // all 227 KB); these launches are HBM-bound 1x1 convolutions, one stage less costs them nothing
-  t.add_ring = p.add_stats ? TC_ADD_RING : 0;
-  const int coef_bytes = p.add_stats ? TC_COEF_BYTES + TC_ADD_RING * TC_SLAB_BYTES : 0;
+  // N = 256: a 48 KB stage — two residual slabs in flight leave the operand pipeline three stages (four without the ring)
+  t.add_ring = p.add_stats ? (t.BN == 256 ? 2 : TC_ADD_RING) : 0;
+  const int coef_bytes = p.add_stats ? TC_COEF_BYTES + t.add_ring * TC_SLAB_BYTES : 0;
   t.stages = (TC_PIPE_BYTES - coef_bytes) / stage_bytes;
   if (t.stages > 8) t.stages = 8;
   t.bias = p.bias;

@@ -614,7 +614,8 @@ def test_conv_streaming_halo_with_groupnorm_on_the_load_path(case):
 
 
 @pytest.mark.parametrize("B,T,H,W,C0,C1,Co,G", [(2, 2, 16, 16, 64, 64, 64, 8), (3, 4, 8, 8, 128, 64, 128, 8),
-                                                 (2, 2, 8, 8, 512, 256, 128, 8), (2, 1, 16, 8, 64, 0, 384, 4)])
+                                                 (2, 2, 8, 8, 512, 256, 128, 8), (2, 1, 16, 8, 64, 0, 384, 4),
+                                                 (2, 2, 8, 8, 512, 256, 512, 8), (2, 4, 16, 16, 256, 128, 256, 8)])
 @pytest.mark.parametrize("in_place", [True, False])
 def test_conv_1x1_with_groupnorm_of_the_residual_in_the_epilogue(B, T, H, W, C0, C1, Co, G, in_place):
     """dv_conv_params.add_*: res_conv(cat(x, skip)) + SiLU(GroupNorm(h)) in ONE launch — the tail of ResnetBlock3D.forward
