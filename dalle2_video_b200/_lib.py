@@ -165,7 +165,7 @@ class GnBwdParams(C.Structure):
     _fields_ = [("x", vp), ("dy", vp), ("dx", vp), ("stats", vp), ("gamma", vp), ("beta", vp), ("scale", vp),
                 ("shift", vp), ("sums", vp), ("dgamma", vp), ("dbeta", vp), ("dscale", vp), ("dshift", vp),
                 ("ss_ld", i32), ("dss_ld", i32), ("B", i32), ("P", i64), ("C", i32), ("groups", i32), ("eps", f32),
-                ("accumulate", i32), ("dtype", i32)]
+                ("accumulate", i32), ("dtype", i32), ("dbias", vp)]
 
 
 class LayerNormBwdParams(C.Structure):

@@ -158,6 +158,10 @@ __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(dv_gn_bwd_params p, i
       const float xh = fmaf(xv[j], crs[c + j], -cmr[c + j]);
       o[j] = fmaf(cw[c + j], g, -cm1[c + j]) - xh * cm2[c + j];
     }
+    if (p.dbias) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) atomicAdd(&p.dbias[c + j], o[j]);   // parity path: global atomics per element
+    }
     if (p.accumulate) {
       float prev[8];
       load8(dx + (vbase + i) * 8, prev);
@@ -280,6 +284,7 @@ __global__ void __launch_bounds__(256, 2) gn_bwd_apply_fast_kernel(dv_gn_bwd_par
   T* dx = reinterpret_cast<T*>(p.dx) + off;
   const int nvec = (int)((r1 - r0) * c8n);
   constexpr int VW = sizeof(T) * 8 / 16;
+  float bsum[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // column sums of the dx this thread writes (p.dbias)
   for (int i0 = threadIdx.x; i0 < nvec; i0 += 256 * GNB_U) {
     uint4 xr[GNB_U][VW], gr[GNB_U][VW], pr[GNB_U][VW];
 #pragma unroll
@@ -305,6 +310,7 @@ __global__ void __launch_bounds__(256, 2) gn_bwd_apply_fast_kernel(dv_gn_bwd_par
         for (int j = 0; j < 8; ++j) {
           const float g = gv[j] * silu_grad(fmaf(xv[j], a[j], d[j]));
           o[j] = fmaf(w[j], g, -k1[j]) - xv[j] * k2[j];
+          bsum[j] += o[j];
         }
         if (p.accumulate) {
           float prev[8];
@@ -315,6 +321,16 @@ __global__ void __launch_bounds__(256, 2) gn_bwd_apply_fast_kernel(dv_gn_bwd_par
         store8(dx + (int64_t)i * 8, o);
       }
     }
+  }
+  if (p.dbias) {
+    // the coefficient arrays are dead: reuse ca as the CTA's [C] partial sums
+    __syncthreads();
+    for (int cc = threadIdx.x; cc < p.C; cc += blockDim.x) ca[cc] = 0.f;
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 8; ++j) atomicAdd(&ca[c + j], bsum[j]);
+    __syncthreads();
+    for (int cc = threadIdx.x; cc < p.C; cc += blockDim.x) atomicAdd(p.dbias + cc, ca[cc]);
   }
 }
 

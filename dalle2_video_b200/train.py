@@ -54,12 +54,15 @@ def unpack_wgrad(g, co, ci, kh, kw):
 
 class _Var:
     """A channels-last activation [rows][C] (bf16) and, once something back-propagates into it, its gradient."""
-    __slots__ = ("t", "rows", "C", "grad", "gready")
+    __slots__ = ("t", "rows", "C", "grad", "gready", "bias_gidx", "bias_claimed")
 
     def __init__(self, rows, C, device, dtype=torch.bfloat16):
         self.t = torch.empty(rows, C, dtype=dtype, device=device)
         self.rows, self.C = rows, C
         self.grad, self.gready = None, False
+        # a convolution output whose only consumer is a GroupNorm: that GroupNorm's backward also sums its dx over the
+        # positions (dv_gn_bwd_params.dbias), which IS the convolution's bias gradient — no dv_colsum pass
+        self.bias_gidx, self.bias_claimed = None, False
 
     @property
     def ptr(self):
@@ -138,8 +141,13 @@ class _TrainPlan:
         v.gready = True
         return v.grad.data_ptr(), ready
 
-    def _grad_add(self, v: _Var, src_ptr):
-        """v.grad (+)= the tensor at src_ptr (same shape and dtype)."""
+    def _grad_add(self, v: _Var, src_ptr, src_tensor=None):
+        """v.grad (+)= the tensor at src_ptr (same shape and dtype).  `src_tensor`: the caller's gradient buffer is dead
+        after this tape entry (it is the entry's own `out.grad`); when v has no gradient yet, v simply takes the buffer
+        over instead of receiving a copy of it."""
+        if src_tensor is not None and v.grad is None and not v.gready:
+            v.grad, v.gready = src_tensor, True
+            return
         dst, ready = self._grad_target(v)
         self.bwd.append(("dv_add", L.AddParams(a=src_ptr, b=dst if ready else None, out=dst, n=v.rows * v.C, dtype=self.code)))
 
@@ -176,6 +184,8 @@ class _TrainPlan:
                                                             groups=groups, dtype=self.code)))
         gw = self._galloc(Co, kh * kw * ctot)
         gb = self._galloc(Co) if bias_fn is not None else None
+        if stats is not None and gb is not None and add_norm is None:
+            out.bias_gidx = gb
         self._gmap((param_w, lambda: from5(unpack_wgrad(self._g(gw), Co, ctot, kh, kw))))
         if gb is not None:
             self._gmap((param_b, (lambda: self._g(gb)) if bias_unperm is None else (lambda: bias_unperm(self._g(gb)))))
@@ -190,7 +200,7 @@ class _TrainPlan:
             self.bwd.append(("dv_conv_wgrad", L.ConvWgradParams(
                 src0=srcs[0].ptr, src1=srcs[1].ptr if len(srcs) > 1 else None, dy=dy, dw=self._gptr(gw), n_img=n_img, H=h,
                 W=w, C0=cin[0], C1=cin[1] if len(srcs) > 1 else 0, Cout=Co, kh=k, kw=k, mode=mode, dtype=self.code)))
-            if gb is not None:
+            if gb is not None and not out.bias_claimed:
                 self.bwd.append(("dv_colsum", L.ColsumParams(x=dy, out=self._gptr(gb), rows=rows_out, C=Co, dtype=self.code)))
             if mode == L.CONV_UNSHUFFLE:
                 s = srcs[0]
@@ -268,6 +278,8 @@ class _TrainPlan:
         gg, gbt = self._galloc(C), self._galloc(C)
         self._gmap((norm.weight, lambda: self._g(gg)))
         self._gmap((norm.bias, lambda: self._g(gbt)))
+        if xraw.bias_gidx is not None:
+            xraw.bias_claimed = True    # this GroupNorm is the convolution output's only consumer
         sums = torch.zeros(B, C, 2, device=self.device)
         self.zero_each_step.append(sums)
 
@@ -280,11 +292,12 @@ class _TrainPlan:
                 x=xraw.ptr, dy=dy, dx=dst, stats=st_ptr, gamma=gamma.data_ptr(), beta=beta.data_ptr(), scale=sc, shift=sh,
                 sums=sums.data_ptr(), dgamma=self._gptr(gg), dbeta=self._gptr(gbt), dscale=dsc, dshift=dsh,
                 ss_ld=self.ss_total, dss_ld=self.ss_total, B=B, P=P, C=C, groups=G, eps=float(norm.eps),
-                accumulate=1 if ready else 0, dtype=self.code)
+                accumulate=1 if ready else 0, dtype=self.code,
+                dbias=self._gptr(xraw.bias_gidx) if xraw.bias_claimed else None)
             self.bwd.append(("dv_gn_bwd_reduce", bp))
             self.bwd.append(("dv_gn_bwd_apply", bp))
             if residual is not None:
-                self._grad_add(residual, dy)
+                self._grad_add(residual, dy, out.grad)
 
         self.tape.append(backward)
 
@@ -303,7 +316,7 @@ class _TrainPlan:
                                                                       rows=x.rows, C=x.C, eps=eps, accumulate=1 if ready else 0,
                                                                       dtype=self.code)))
             if residual is not None:
-                self._grad_add(residual, dy)
+                self._grad_add(residual, dy, out.grad)
 
         self.tape.append(backward)
         return out

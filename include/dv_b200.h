@@ -643,6 +643,10 @@ typedef struct {
   float eps;
   int accumulate;       /* dx += instead of dx = */
   dv_dtype dtype;
+  float* dbias;         /* optional [C], accumulated by dv_gn_bwd_apply: sum over samples and positions of THIS call's
+                           gradient wrt x (before `accumulate` adds the previous content) — the bias gradient of the
+                           convolution that produced x (Block3D.project, :107,124), which saves that convolution's
+                           dv_colsum pass over the same tensor */
 } dv_gn_bwd_params;
 int dv_gn_bwd_reduce(const dv_gn_bwd_params* p, dv_stream_t stream);
 int dv_gn_bwd_apply(const dv_gn_bwd_params* p, dv_stream_t stream);

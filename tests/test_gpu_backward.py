@@ -165,10 +165,14 @@ def test_gn_backward_matches_autograd(dtype, with_ss, B, P, C, G):
     assert rel_err(dgamma, gamma.grad) < max(tol, 2e-4) and rel_err(dbeta, beta.grad) < max(tol, 2e-4)
     if with_ss:
         assert rel_err(dss[:, :2 * C], ss.grad[:, :2 * C]) < max(tol, 2e-4)
-    # accumulate mode and in-place over dy
-    p.accumulate = 1
+    # accumulate mode and in-place over dy; with dbias the call also sums ITS gradient over samples and positions (the bias
+    # gradient of the convolution that produced x), independent of what `accumulate` adds
+    dbias = torch.zeros(C, device=dev())
+    p.accumulate, p.dbias = 1, ptr(dbias)
     L.call("dv_gn_bwd_apply", p, stream())
     assert rel_err(dx, 2 * xr.grad) < 2 * tol
+    ref_db = xr.grad.float().reshape(-1, C).sum(0)
+    assert float((dbias - ref_db).abs().max()) < max(tol, 2e-4) * float(xr.grad.float().abs().sum(0).max())
 
 
 @pytest.mark.parametrize("dtype", DT)
