@@ -580,7 +580,7 @@ struct XattnFwdTcParams {
   int tiles_per_seq, splits;
 };
 
-__global__ void __launch_bounds__(XB_THREADS, 2)
+__global__ void __launch_bounds__(XB_THREADS, 3)
 xattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const XattnFwdTcParams pp) {
   const dv_xattn_params& p = pp.a;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -769,6 +769,20 @@ int xattn_fwd_short_supported(const dv_xattn_params& p) {
   return 1;
 }
 
+// Row splits per (sample, head): the CTAs run in waves of `slots` (resident CTAs on the device), each CTA a serial chain
+// over its tiles — pick the split count that minimises waves x tiles-per-CTA (+ a small per-CTA set-up term).
+static int pick_splits(int64_t units, int tiles, int slots) {
+  int best = 1;
+  double best_cost = 1e30;
+  for (int sp = 1; sp <= 16 && sp <= tiles; ++sp) {
+    const int64_t ctas = units * sp;
+    const int64_t waves = (ctas + slots - 1) / slots;
+    const double cost = (double)waves * ((tiles + sp - 1) / sp + 1.5);
+    if (cost < best_cost - 1e-9) { best_cost = cost; best = sp; }
+  }
+  return best;
+}
+
 int xattn_fwd_short_launch(const dv_xattn_params& p, cudaStream_t s) {
   XattnFwdTcParams k;
   memset(&k, 0, sizeof(k));
@@ -781,9 +795,7 @@ int xattn_fwd_short_launch(const dv_xattn_params& p, cudaStream_t s) {
     cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
     if (sm_count <= 0) sm_count = 148;
   }
-  int splits = 2 * sm_count / (p.B * p.heads);
-  if (splits < 1) splits = 1;
-  if (splits > k.tiles_per_seq) splits = k.tiles_per_seq;
+  const int splits = pick_splits((int64_t)p.B * p.heads, k.tiles_per_seq, 3 * sm_count);   // three CTAs per SM
   k.splits = splits;
   CUtensorMap mq;
   {
@@ -825,9 +837,7 @@ int xattn_bwd_tc_launch(const dv_xattn_bwd_params& p, cudaStream_t s) {
     cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
     if (sm_count <= 0) sm_count = 148;
   }
-  int splits = 2 * sm_count / (p.B * p.heads);
-  if (splits < 1) splits = 1;
-  if (splits > k.tiles_per_seq) splits = k.tiles_per_seq;
+  const int splits = pick_splits((int64_t)p.B * p.heads, k.tiles_per_seq, 2 * sm_count);   // two CTAs per SM
   k.splits = splits;
   CUtensorMap mq, mdo;
   int rc;
