@@ -278,8 +278,8 @@ template <int T> struct TtCfg {
   static constexpr int NS = T == 8 ? 16 : (T <= 24 ? 32 : 48);   // keys incl. the null key, padded to the MMA granularity
   static constexpr int HG = T == 24 ? 4 : 128 / T;               // heads per tile (T = 24: 96 of the 128 rows are used)
   static constexpr int P_ROW = T == 32 ? 128 : 64;               // bytes per P row (K-major, SWIZZLE_128B / SWIZZLE_64B)
-  static constexpr int STAGES = T == 32 ? 2 : 3;
-  static constexpr int CTAS = 4;
+  static constexpr int STAGES = 3;
+  static constexpr int CTAS = T == 32 ? 3 : 4;   // T = 32 needs ~124 registers: three CTAs per SM without spills beat four with them (0.52 -> 0.65)
   static constexpr int STAGE = 128 * 64 + 2 * NS * 64;
   static constexpr int SMEM = STAGES * STAGE + 128 * P_ROW + 256 + 1024;
 };

@@ -433,7 +433,7 @@ int64_t dv_attn_mqa_workspace_bytes(const dv_attn_mqa_params* p);
  * q: [B][T][HW][heads*dh], kv: [B][T][HW][2*dh] (k then v), out like q (may alias q).
  * bf16, dh = 32, T in {8,16,24,32}, heads a multiple of 128 / T (of 4 at T = 24): tcgen05 kernel — a tile is the T frames x 128/T heads of one
  *   pixel (one 4-D TMA box of the channels-last tensor), one (frame, head) row per thread, the null key as row T of the
- *   K / V tiles; 0.75 / 0.77 / 0.68 / 0.53 of the measured HBM rate at T = 8 / 16 / 24 / 32 on a 1.1-2.3 GB working set (profiles/r02_kernel_sweep_*).
+ *   K / V tiles; 0.75 / 0.78 / 0.68 / 0.66 of the measured HBM rate at T = 8 / 16 / 24 / 32 on a 1.1-2.3 GB working set (profiles/r02_kernel_sweep_*).
  * bf16, dh = 32, T in {8,16,24,32}, heads % 4 == 0: warp-level mma.sync kernel with cp.async staging (impl = 2);
  * anything else (fp32 parity mode, other T): CUDA-core kernel.
  */
