@@ -222,6 +222,10 @@ class CastParams(C.Structure):
     _fields_ = [("src", vp), ("dst", vp), ("n", i64)]
 
 
+class GatherScaleParams(C.Structure):
+    _fields_ = [("src", vp), ("idx", vp), ("scale", vp), ("dst", vp), ("n", i64), ("dst_dtype", i32), ("accumulate", i32)]
+
+
 class SumsqParams(C.Structure):
     _fields_ = [("x", vp), ("out", vp), ("n", i64)]
 
@@ -248,7 +252,7 @@ ENTRY_POINTS = {
     "dv_gn_bwd_apply": GnBwdParams, "dv_layernorm_bwd": LayerNormBwdParams, "dv_xattn_core_bwd": XattnBwdParams,
     "dv_attn_mqa_bwd": AttnMqaBwdParams, "dv_q_sample": QSampleParams, "dv_gaussian_blur": GaussianBlurParams, "dv_mse_loss": MseLossParams,
     "dv_to_out_bwd": ToOutBwdParams, "dv_silu_shuffle": SiluShuffleParams, "dv_silu_shuffle_bwd": SiluShuffleParams,
-    "dv_add": AddParams, "dv_cast_f32_bf16": CastParams, "dv_sumsq": SumsqParams, "dv_adamw": AdamwParams,
+    "dv_add": AddParams, "dv_cast_f32_bf16": CastParams, "dv_gather_scale": GatherScaleParams, "dv_sumsq": SumsqParams, "dv_adamw": AdamwParams,
 }
 PLAIN_SYMBOLS = ("dv_version", "dv_last_error_string", "dv_device_sm_count", "dv_conv_uses_tcgen05", "dv_conv_pre_norm_supported", "dv_conv_add_norm_supported",
                  "dv_attn_mqa_workspace_bytes", "dv_xattn_core_workspace_bytes", "dv_conv_wgrad_uses_tcgen05", "dv_attn_temporal_uses_mma", "dv_attn_mqa_bwd_workspace_bytes", "dv_init_conv_supported",

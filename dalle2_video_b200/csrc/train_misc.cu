@@ -451,6 +451,51 @@ extern "C" int dv_add(const dv_add_params* p, dv_stream_t stream) {
   return DV_OK;
 }
 
+namespace dv {
+template <typename T>
+__global__ void __launch_bounds__(256) gather_scale_kernel(dv_gather_scale_params p) {
+  const int64_t i0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i0 >= p.n) return;
+  T* dst = reinterpret_cast<T*>(p.dst);
+  if (i0 + 4 <= p.n) {
+    const int4 id = *reinterpret_cast<const int4*>(p.idx + i0);
+    float4 sc = make_float4(1.f, 1.f, 1.f, 1.f);
+    if (p.scale) sc = *reinterpret_cast<const float4*>(p.scale + i0);
+    float v[4];
+    v[0] = id.x >= 0 ? __ldg(p.src + id.x) * sc.x : 0.f;
+    v[1] = id.y >= 0 ? __ldg(p.src + id.y) * sc.y : 0.f;
+    v[2] = id.z >= 0 ? __ldg(p.src + id.z) * sc.z : 0.f;
+    v[3] = id.w >= 0 ? __ldg(p.src + id.w) * sc.w : 0.f;
+    if (p.accumulate) {
+      float prev[4];
+      load4(dst + i0, prev);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) v[k] += prev[k];
+    }
+    store4(dst + i0, v);
+  } else {
+    for (int64_t i = i0; i < p.n; ++i) {
+      const int id = p.idx[i];
+      float v = id >= 0 ? p.src[id] * (p.scale ? p.scale[i] : 1.f) : 0.f;
+      if (p.accumulate) v += to_f<T>(dst[i]);
+      dst[i] = from_f<T>(v);
+    }
+  }
+}
+}  // namespace dv
+
+extern "C" int dv_gather_scale(const dv_gather_scale_params* p, dv_stream_t stream) {
+  using namespace dv;
+  DV_REQUIRE(p && p->src && p->idx && p->dst && p->n > 0, DV_EINVAL, "dv_gather_scale: bad arguments");
+  DV_REQUIRE(p->dst_dtype == DV_F32 || p->dst_dtype == DV_BF16, DV_EINVAL, "dv_gather_scale: bad dtype");
+  DV_REQUIRE(aligned16(p->idx) && aligned16(p->dst) && aligned16(p->scale), DV_EALIGN, "dv_gather_scale: 16-byte alignment");
+  const unsigned blocks = (unsigned)((p->n + 1023) / 1024);
+  if (p->dst_dtype == DV_F32) gather_scale_kernel<float><<<blocks, 256, 0, as_stream(stream)>>>(*p);
+  else gather_scale_kernel<__nv_bfloat16><<<blocks, 256, 0, as_stream(stream)>>>(*p);
+  DV_CHECK_LAUNCH("dv_gather_scale");
+  return DV_OK;
+}
+
 extern "C" int dv_cast_f32_bf16(const dv_cast_params* p, dv_stream_t stream) {
   using namespace dv;
   DV_REQUIRE(p && p->src && p->dst && p->n > 0, DV_EINVAL, "dv_cast_f32_bf16: bad arguments");

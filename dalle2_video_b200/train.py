@@ -22,6 +22,7 @@ Text conditioning and the extensions (temporal conv / attention) have no backwar
 from __future__ import annotations
 
 import math
+import os
 import random
 
 import torch
@@ -96,27 +97,57 @@ class _TrainPlan:
         self._graphs = {}
         self.stats_slots = 0
         self.generation = 0
+        # Arenas: every kernel-layout weight copy and every kernel-layout gradient accumulator is a view into one flat
+        # buffer per kind, so that the per-step layout conversions are ONE gather launch each (dv_gather_scale) instead
+        # of ~1000 tiny torch copies (_build_gather_tables)
+        n_params = sum(p.numel() for p in u.parameters())
+        self._arena = {
+            "w": [torch.empty(int(2.4 * n_params) + (1 << 20), dtype=dtype, device=device), 0],
+            "f": [torch.empty(n_params // 4 + (1 << 20), dtype=torch.float32, device=device), 0],
+            "g": [torch.zeros(int(1.15 * n_params) + (1 << 20), dtype=torch.float32, device=device), 0],
+        }
+        self._fused = None       # gather tables (None: per-tensor torch copies)
         self._build()
+        if os.environ.get("DV_TRAIN_FUSED_LAYOUT", "1") != "0":
+            self._build_gather_tables()
 
     # -------------------------------------------------------------- buffers
-    def _bind(self, producer, dtype):
+    def _carve(self, kind, shape):
+        """A view of `shape` into arena `kind` (256-byte aligned), or None when the arena is full."""
+        buf, used = self._arena[kind]
+        numel = 1
+        for d in shape:
+            numel *= int(d)
+        off = (used + 63) // 64 * 64
+        if off + numel > buf.numel():
+            return None, -1
+        self._arena[kind][1] = off + numel
+        return buf[off:off + numel].view(*shape), off
+
+    def _bind(self, producer, dtype, kind):
         """A persistent device tensor holding producer() (weights in a kernel layout), refreshed every step."""
         with torch.no_grad():
             src = producer()
-        t = torch.empty(src.shape, dtype=dtype, device=self.device)
-        self.refresh.append((t, producer))
+        t, off = self._carve(kind, tuple(src.shape))
+        if t is None:
+            t = torch.empty(src.shape, dtype=dtype, device=self.device)
+        self.refresh.append((t, producer, kind, off))
         self.keep.append(t)
         return t
 
     def _w(self, producer):
-        return self._bind(producer, self.dtype)
+        return self._bind(producer, self.dtype, "w")
 
     def _f32(self, producer):
-        return self._bind(producer, torch.float32)
+        return self._bind(producer, torch.float32, "f")
 
     def _galloc(self, *shape):
         """float32 gradient accumulator in a kernel layout (zeroed once per step); returns its index."""
-        self.gbufs.append(torch.zeros(*shape, device=self.device))
+        t, off = self._carve("g", shape)
+        if t is None:
+            t = torch.zeros(*shape, device=self.device)
+            self._g_outside = True
+        self.gbufs.append(t)
         return len(self.gbufs) - 1
 
     def _gmap(self, entry):
@@ -655,8 +686,150 @@ class _TrainPlan:
     # -------------------------------------------------------------- execution
     def refresh_weights(self):
         with torch.no_grad():
-            for dst, fn in self.refresh:
+            fz = self._fused
+            if fz is None:
+                for dst, fn, _, _ in self.refresh:
+                    dst.copy_(fn())
+                return
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+            torch.cat([p.detach().reshape(-1) for p in fz["params"]], out=fz["flat_src"])
+            for gp in fz["refresh_ops"]:
+                L.call("dv_gather_scale", gp, stream)
+            for dst, fn in fz["lambda_refresh"]:
                 dst.copy_(fn())
+
+    def _build_gather_tables(self):
+        """Index tables for dv_gather_scale: every refresh expression (packed / transposed / flipped / padded copies of the
+        parameters) and every gradient un-permutation is linear in its source — evaluate it on index-valued tensors
+        (source element number split into two float32-exact halves, and all-ones for the scale factor) and read off, for
+        every destination element, which source element it takes and with what factor.  Both tables are checked against
+        the torch expressions before they are used; a mismatch keeps the per-tensor path."""
+        if getattr(self, "_g_outside", False) or any(off < 0 for _, _, _, off in self.refresh):
+            return
+        u, dev = self.u, self.device
+        params = [p for p in u.parameters()]
+        n = sum(p.numel() for p in params)
+        if n >= (1 << 31) or any(p.dtype != torch.float32 for p in params):
+            return
+        offs, o = [], 0
+        for p in params:
+            offs.append(o)
+            o += p.numel()
+
+        def trace_params(make):
+            saved = [p.data for p in params]
+            try:
+                for p, off in zip(params, offs):
+                    p.data = make(off, p.numel()).view(p.shape)
+                with torch.no_grad():
+                    return [fn().detach().float().reshape(-1).clone() for _, fn, _, _ in self.refresh]
+            finally:
+                for p, d in zip(params, saved):
+                    p.data = d
+
+        ar = lambda off, k: torch.arange(off, off + k, device=dev, dtype=torch.int64)  # noqa: E731
+        hi = trace_params(lambda off, k: (ar(off, k) // 4096).float())
+        lo = trace_params(lambda off, k: (ar(off, k) % 4096).float())
+        one = trace_params(lambda off, k: torch.ones(k, device=dev))
+        zero = trace_params(lambda off, k: torch.zeros(k, device=dev))
+        tables = {}
+        for kind in ("w", "f"):
+            used = self._arena[kind][1]
+            tables[kind] = [torch.full((max(used, 4),), -1, dtype=torch.int32, device=dev), None]
+        lambda_refresh = []
+        for (dst, fn, kind, off), h, l_, sc, z in zip(self.refresh, hi, lo, one, zero):
+            if float(z.abs().max()) != 0.0:          # not linear in the parameters (a constant term): keep the expression
+                lambda_refresh.append((dst, fn))
+                continue
+            nz = sc != 0
+            safe = torch.where(nz, sc, torch.ones_like(sc))
+            idx = torch.round(h / safe).to(torch.int64) * 4096 + torch.round(l_ / safe).to(torch.int64)
+            idx = torch.where(nz, idx, torch.full_like(idx, -1))
+            tables[kind][0][off:off + idx.numel()] = idx.to(torch.int32)
+            if bool(((sc != 1) & nz).any()):
+                if tables[kind][1] is None:
+                    tables[kind][1] = torch.ones(tables[kind][0].numel(), device=dev)
+                tables[kind][1][off:off + idx.numel()] = sc
+        flat_src = torch.empty(n, device=dev)
+        refresh_ops = []
+        for kind, code in (("w", self.code), ("f", L.DV_F32)):
+            used = self._arena[kind][1]
+            if used == 0:
+                continue
+            idx_t, sc_t = tables[kind]
+            refresh_ops.append(L.GatherScaleParams(src=flat_src.data_ptr(), idx=idx_t.data_ptr(),
+                                                   scale=sc_t.data_ptr() if sc_t is not None else None,
+                                                   dst=self._arena[kind][0].data_ptr(), n=used, dst_dtype=code, accumulate=0))
+        # ---- gradients: kernel-layout accumulators (views of the "g" arena) -> parameter layout
+        g_buf, g_used = self._arena["g"]
+        by_param = {id(p): (p, off) for p, off in zip(params, offs)}
+        g_idx = torch.full((n,), -1, dtype=torch.int32, device=dev)
+        g_scale = None
+        seen, order = set(), []
+        ok = True
+
+        def trace_grads(vals):
+            g_buf[:g_used].copy_(vals)
+            with torch.no_grad():
+                return [fn().detach().float().reshape(-1).clone() for _, fn in self.grad_map]
+
+        arg = torch.arange(g_used, device=dev, dtype=torch.int64)
+        gh = trace_grads((arg // 4096).float())
+        gl = trace_grads((arg % 4096).float())
+        g1 = trace_grads(torch.ones(g_used, device=dev))
+        g0 = trace_grads(torch.zeros(g_used, device=dev))
+        for (prm, fn), h, l_, sc, z in zip(self.grad_map, gh, gl, g1, g0):
+            ent = by_param.get(id(prm))
+            if ent is None or id(prm) in seen or float(z.abs().max()) != 0.0 or h.numel() != prm.numel():
+                ok = False
+                break
+            seen.add(id(prm))
+            order.append(id(prm))
+            nz = sc != 0
+            safe = torch.where(nz, sc, torch.ones_like(sc))
+            idx = torch.round(h / safe).to(torch.int64) * 4096 + torch.round(l_ / safe).to(torch.int64)
+            idx = torch.where(nz, idx, torch.full_like(idx, -1))
+            g_idx[ent[1]:ent[1] + idx.numel()] = idx.to(torch.int32)
+            if bool(((sc != 1) & nz).any()):
+                if g_scale is None:
+                    g_scale = torch.ones(n, device=dev)
+                g_scale[ent[1]:ent[1] + idx.numel()] = sc
+        g_buf.zero_()
+        fz = dict(params=params, flat_src=flat_src, refresh_ops=refresh_ops, lambda_refresh=lambda_refresh,
+                  keep=(tables, g_idx, g_scale))
+        if ok:
+            grad_out = torch.empty(n, device=dev)
+            fz["grad_op"] = L.GatherScaleParams(src=g_buf.data_ptr(), idx=g_idx.data_ptr(),
+                                                scale=g_scale.data_ptr() if g_scale is not None else None,
+                                                dst=grad_out.data_ptr(), n=n, dst_dtype=L.DV_F32, accumulate=0)
+            fz["grad_out"] = grad_out
+            fz["grad_params"] = [by_param[i][0] for i in order]
+            fz["grad_views"] = [grad_out[by_param[i][1]:by_param[i][1] + by_param[i][0].numel()].view(by_param[i][0].shape)
+                                for i in order]
+        # ---- check both tables against the torch expressions on random data before trusting them
+        with torch.no_grad():
+            for dst, fn, _, _ in self.refresh:
+                dst.copy_(fn())
+            want = {k: self._arena[k][0][: self._arena[k][1]].clone() for k in ("w", "f")}
+            self._fused = fz
+            self.refresh_weights()
+            torch.cuda.synchronize(dev)
+            good = all(torch.equal(want[k], self._arena[k][0][: self._arena[k][1]]) for k in ("w", "f"))
+            if good and ok:
+                g_buf[:g_used].normal_()
+                ref = [fn().detach().float().reshape(-1).clone() for _, fn in self.grad_map]
+                L.call("dv_gather_scale", fz["grad_op"], torch.cuda.current_stream(dev).cuda_stream)
+                torch.cuda.synchronize(dev)
+                for (prm, _), r in zip(self.grad_map, ref):
+                    off = by_param[id(prm)][1]
+                    if not torch.equal(fz["grad_out"][off:off + r.numel()], r):
+                        ok = False
+                        break
+                g_buf.zero_()
+            if not ok:
+                fz.pop("grad_op", None)
+            if not good:
+                self._fused = None
 
     def _forward_body(self):
         stream = torch.cuda.current_stream(self.device).cuda_stream
@@ -667,7 +840,12 @@ class _TrainPlan:
     def _backward_body(self, lo=0, hi=None):
         stream = torch.cuda.current_stream(self.device).cuda_stream
         if lo == 0:
-            torch._foreach_zero_(self.gbufs + self.zero_each_step)
+            if getattr(self, "_g_outside", False):
+                torch._foreach_zero_(self.gbufs + self.zero_each_step)
+            else:
+                self._arena["g"][0][: self._arena["g"][1]].zero_()
+                if self.zero_each_step:
+                    torch._foreach_zero_(self.zero_each_step)
         for name, p in self.bwd[lo:hi]:
             L.call(name, p, stream)
 
@@ -703,6 +881,12 @@ class _TrainPlan:
 
     def apply_grads(self, ids=None):
         """Move finished gradients from the kernel-layout accumulators into the parameters' .grad (DDP-hook style)."""
+        fz = self._fused
+        if ids is None and fz is not None and "grad_op" in fz and all(p.grad is not None for p in fz["grad_params"]):
+            with torch.no_grad():
+                L.call("dv_gather_scale", fz["grad_op"], torch.cuda.current_stream(self.device).cuda_stream)
+                torch._foreach_add_([p.grad for p in fz["grad_params"]], fz["grad_views"])
+            return
         with torch.no_grad():
             for i in (range(len(self.grad_map)) if ids is None else ids):
                 prm, fn = self.grad_map[i]

@@ -763,6 +763,15 @@ typedef struct { const void* a; const void* b; void* out; int64_t n; dv_dtype dt
 int dv_add(const dv_add_params* p, dv_stream_t stream);
 typedef struct { const void* src; void* dst; int64_t n; } dv_cast_params;
 int dv_cast_f32_bf16(const dv_cast_params* p, dv_stream_t stream);
+/* dst[i] (+)= scale[i] * src[idx[i]], zero where idx[i] < 0: every kernel-layout copy of the weights (packed / transposed /
+ * tap-flipped / zero-padded forms of the float32 master parameters, refreshed each training step) in ONE launch, and the way
+ * back for the gradients (kernel-layout accumulators -> the parameters' .grad layout).  The index table is built once per
+ * plan by evaluating the layout expressions on index-valued tensors. */
+typedef struct {
+  const float* src; const int* idx; const float* scale; /* scale may be NULL (all ones) */
+  void* dst; int64_t n; dv_dtype dst_dtype; int accumulate;
+} dv_gather_scale_params;
+int dv_gather_scale(const dv_gather_scale_params* p, dv_stream_t stream);
 typedef struct { const float* x; double* out; int64_t n; } dv_sumsq_params; /* *out += sum x^2 */
 int dv_sumsq(const dv_sumsq_params* p, dv_stream_t stream);
 
