@@ -384,6 +384,318 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// MQA at dim_head 32, two Q tiles in flight per CTA ("ping-pong").  The kernel above keeps all eight softmax warps on the
+// SAME (Q tile, key tile): they wait for S together, read TMEM together, exchange the row maximum, and only then use the
+// MUFU pipe (ncu: XU 46 %, issue 42 %, ~2100 cycles per tile against 1024 of exp2).  Here the CTA owns a PAIR of Q tiles of
+// one sequence and the K / V stream is shared by both:
+//   warps 0-3 = group 0 (Q tile 2k), warps 4-7 = group 1 (Q tile 2k+1), warp 8 TMA, warp 9 MMA (warps 10-11 idle: roles are
+//   aligned to warpgroups for setmaxnreg), ONE thread per (query, head) row holding all 128
+//   logits of a key tile in registers — no exchange of row maxima, no named barrier; each scheduler holds one warp of
+//   either group, and the groups drift apart, so one group's TMEM read / maximum runs under the other's exponentials.
+//   O ACCUMULATES IN TMEM over the key tiles of a Q tile (the threads keep no output registers and do no per-tile
+//   fold; the row sum stays in a register).  The reference m of the exponentials is only raised when some row of the
+//   warp exceeds it by more than 2^PP_LAZY (the softmax is shift-invariant; P <= 2^PP_LAZY is exact enough in bf16 /
+//   fp32); then, and only then, the accumulator is rescaled in place (tcgen05.ld / st) once the P.V MMAs issued so far have
+//   retired.  The null key / value stay out of the MMAs and are added at the end with weight 2^(m_null - m).
+//   TMEM: S of group g at column 128 g (single buffer: S(j+1) is issued as soon as the group has copied S(j) to
+//   registers), P.V accumulator of group g at 256 + 64 g.
+constexpr int PP_THREADS = 384;
+constexpr int PP_STAGES = 4;
+constexpr float PP_LAZY = 5.0f;
+constexpr int PP_POLY_DEFAULT = 0;
+// template parameter POLY: of every 8 exponentials, this many are evaluated on the FMA pipe (polynomial) instead of MUFU
+
+// 2^x for x <= 0 (and moderately positive) on the FMA pipe: round-to-nearest split x = n + f, f in [-0.5, 0.5], cubic for
+// 2^f (max relative error 7.5e-5, below the bf16 rounding of P), exponent added to the bit pattern
+__device__ __forceinline__ float ex2_poly(float x) {
+  x = fmaxf(x, -125.0f);
+  const float t = x + 12582912.0f;                 // 1.5 * 2^23: the integer part lands in the low mantissa bits
+  const float f = x - (t - 12582912.0f);
+  float p = fmaf(f, 0.05517166f, 0.24261112f);     // minimax on [-0.5, 0.5]
+  p = fmaf(p, f, 0.69326099f);
+  p = fmaf(p, f, 0.99992807f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
+
+template <int POLY>
+__global__ void __launch_bounds__(PP_THREADS, 1)
+attn_mqa_pp_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
+                   const __grid_constant__ CUtensorMap map_vt, const AttnTcParams p) {
+  constexpr int DH = 32;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  constexpr int ROWB = DH * 2;
+  constexpr int Q_BYTES = 128 * ROWB;          // 8 KB
+  constexpr int K_BYTES = AT_KT * ROWB;        // 8 KB
+  constexpr int VT_BYTES = DH * AT_KT * 2;     // 8 KB: what TMA brings per stage, as two blocks of [32 rows][64 keys]
+  constexpr int PP_N = DH;
+  constexpr int VBLK = PP_N * 128;             // one 64-key block of V^T: 4 KB
+  constexpr int STAGE_BYTES = K_BYTES + 2 * VBLK;
+  uint8_t* q_s = smem;                                   // [2 pair parities][2 groups][128][64 B] SWIZZLE_64B
+  uint8_t* kv_s = q_s + 4 * Q_BYTES;                     // ring of K | V^T
+  uint8_t* p_s = kv_s + PP_STAGES * STAGE_BYTES;         // [2 groups][2 buffers][2 blocks of 64 keys][128 rows][128 B]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(p_s + 8 * 16384);
+  uint64_t* q_full = bars;                  // [4]  (pair parity, group)
+  uint64_t* q_free = bars + 4;              // [4]  4 arrivals (one per warp of the group)
+  uint64_t* kv_full = bars + 8;             // [PP_STAGES]
+  uint64_t* kv_empty = kv_full + PP_STAGES;
+  uint64_t* s_full = kv_empty + PP_STAGES;  // [2 groups]
+  uint64_t* s_drained = s_full + 2;         // [2 groups] 4 arrivals
+  uint64_t* p_ready = s_drained + 2;        // [2 groups][2 buffers] 4 arrivals
+  uint64_t* pv_done = p_ready + 4;          // [2 groups][2 buffers]: P.V of a step has retired (its P buffer is free)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr uint32_t TMEM_COLS = 512;
+
+  if (warp == 8 && lane == 0) {
+    tma_prefetch_desc(&map_q);
+    tma_prefetch_desc(&map_k);
+    tma_prefetch_desc(&map_vt);
+    for (int a = 0; a < 4; ++a) { mbar_init(&q_full[a], 1); mbar_init(&q_free[a], 4); }
+    for (int s = 0; s < PP_STAGES; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
+    for (int g = 0; g < 2; ++g) { mbar_init(&s_full[g], 1); mbar_init(&s_drained[g], 4); }
+    for (int a = 0; a < 4; ++a) { mbar_init(&p_ready[a], 4); mbar_init(&pv_done[a], 1); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 9) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int64_t pairs = p.total_tiles / 2;
+  const int64_t per_cta = (pairs + gridDim.x - 1) / gridDim.x;
+  const int64_t pair_begin = (int64_t)blockIdx.x * per_cta;
+  const int64_t pair_end = pair_begin + per_cta < pairs ? pair_begin + per_cta : pairs;
+  const int nt = p.k_tiles;
+
+  // registers: launched at 168 per thread (3 warps per scheduler); the driver warpgroup keeps 56, the softmax warpgroups
+  // take 224 (128 logits per thread live across the maximum and the exponentials)
+  if (warp >= 8) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+  if (warp == 8) {
+    // ================================================================ TMA producer
+    if (elect_one()) {
+      int st = 0;
+      uint32_t ph = 0;
+      int t = 0;
+      for (int64_t pair = pair_begin; pair < pair_end; ++pair, ++t) {
+        const int seq = (int)(pair * 2 / p.q_tiles_per_seq);   // both tiles of a pair lie in one sequence (q_tiles_per_seq even)
+        for (int g = 0; g < 2; ++g) {
+          const int qb = (t & 1) * 2 + g;
+          mbar_wait(&q_free[qb], (uint32_t)(((t >> 1) & 1) ^ 1));
+          mbar_expect_tx(&q_full[qb], Q_BYTES);
+          tma_load_2d(&map_q, &q_full[qb], q_s + qb * Q_BYTES, 0, (int)((pair * 2 + g) * 128));
+        }
+        for (int j = 0; j < nt; ++j) {
+          mbar_wait(&kv_empty[st], ph ^ 1);
+          uint8_t* dst = kv_s + st * STAGE_BYTES;
+          mbar_expect_tx(&kv_full[st], K_BYTES + VT_BYTES);
+          tma_load_2d(&map_k, &kv_full[st], dst, 0, seq * p.keys_per_seq + j * AT_KT);
+          tma_load_3d_at(&map_vt, &kv_full[st], dst + K_BYTES, j * AT_KT, 0, seq);
+          tma_load_3d_at(&map_vt, &kv_full[st], dst + K_BYTES + VBLK, j * AT_KT + 64, 0, seq);
+          if (++st == PP_STAGES) { st = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 9) {
+    // ================================================================ MMA issuer: steps = (pair, key tile), flat
+    const uint32_t idesc_s = make_idesc(AT_KT), idesc_o = make_idesc(PP_N);
+    const int64_t total = (pair_end - pair_begin) * nt;
+    // S of step s for group g: needs the step's K stage, the group's Q tile, and the group's S buffer copied out (step s-1)
+    auto issue_s = [&](int64_t s, int g) {
+      const int t = (int)(s / nt), j = (int)(s - (int64_t)t * nt);
+      const int st = (int)(s % PP_STAGES);
+      const int qb = (t & 1) * 2 + g;
+      if (j == 0) mbar_wait(&q_full[qb], (uint32_t)((t >> 1) & 1));
+      mbar_wait(&kv_full[st], (uint32_t)((s / PP_STAGES) & 1));
+      if (s > 0) mbar_wait(&s_drained[g], (uint32_t)((s - 1) & 1));
+      tc_fence_after();
+      if (elect_one()) {
+        const uint64_t qd = make_smem_desc_sw64(smem_u32(q_s + qb * Q_BYTES));
+        const uint64_t kd = make_smem_desc_sw64(smem_u32(kv_s + st * STAGE_BYTES));
+        const uint32_t d = tmem_base + (uint32_t)(g * 128);
+#pragma unroll
+        for (int kk = 0; kk < DH / 16; ++kk) umma_f16(d, qd + (uint64_t)(kk * 2), kd + (uint64_t)(kk * 2), idesc_s, kk != 0);
+        umma_commit(&s_full[g]);
+      }
+      __syncwarp();
+    };
+    auto issue_pv = [&](int64_t s, int g) {
+      const int st = (int)(s % PP_STAGES);
+      const int buf = (int)(s & 1);
+      mbar_wait(&p_ready[g * 2 + buf], (uint32_t)((s >> 1) & 1));
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t vbase = smem_u32(kv_s + st * STAGE_BYTES + K_BYTES);
+        const uint32_t pbase = smem_u32(p_s) + (uint32_t)(g * 4 + buf * 2) * 16384u;
+        const uint32_t d = tmem_base + 256u + (uint32_t)(g * 64);
+        const uint32_t first = (s % nt) == 0 ? 0u : 1u;   // the Q tile's first key tile starts the accumulator
+#pragma unroll
+        for (int kk = 0; kk < AT_KT / 16; ++kk) {
+          const uint64_t pd = make_smem_desc(pbase + (uint32_t)(kk / 4) * 16384u) + (uint64_t)((kk % 4) * 2);
+          const uint64_t vd = make_smem_desc(vbase + (uint32_t)(kk / 4) * VBLK) + (uint64_t)((kk % 4) * 2);
+          umma_f16(d, pd, vd, idesc_o, kk != 0 ? 1u : first);
+        }
+        if (g == 1) umma_commit(&kv_empty[st]);   // both groups' S and P.V of this stage have been issued before this point
+        umma_commit(&pv_done[g * 2 + buf]);
+      }
+      __syncwarp();
+    };
+    if (total > 0) {
+      issue_s(0, 0);
+      issue_s(0, 1);
+      for (int64_t s = 0; s < total; ++s) {
+        if (s + 1 < total) {
+          issue_s(s + 1, 0);
+          issue_s(s + 1, 1);
+        }
+        issue_pv(s, 0);
+        issue_pv(s, 1);
+      }
+    }
+  }
+  } else {
+    // ================================================================ softmax / output: one thread per (query, head) row
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+    const int g = warp >> 2;
+    const int q = warp & 3;                    // TMEM lane quarter this warp may read
+    const int row = q * 32 + lane;
+    const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
+    const uint32_t s_addr = t_lane + (uint32_t)(g * 128);
+    const uint32_t o_addr = t_lane + 256u + (uint32_t)(g * 64);
+    const uint32_t p_grp = smem_u32(p_s) + (uint32_t)(g * 65536 + row * 128);   // shared-window address: st.shared, not generic stores
+    const float c = p.scale_log2e;
+    int t = 0;
+    int64_t ss = 0;   // running step counter (barrier phases)
+    for (int64_t pair = pair_begin; pair < pair_end; ++pair, ++t) {
+      const int64_t grow = (pair * 2 + g) * 128 + row;
+      // the null key / value never enter the MMAs: logit of key 0 = scale * q . k_null, folded in at the end
+      float m_null;
+      {
+        float d = 0.f;
+#pragma unroll
+        for (int e = 0; e < DH; e += 8) {
+          float tmp[8];
+          load8(p.q + grow * DH + e, tmp);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) d = fmaf(tmp[k], __ldg(p.null_kv + e + k), d);
+        }
+        m_null = d * c;
+      }
+      float m = m_null;   // reference of the exponentials (log2 domain); O accumulates in TMEM against it
+      float l = 0.f;      // row sum of the probabilities (the null key is added at the end)
+      for (int j = 0; j < nt; ++j, ++ss) {
+        const int buf = (int)(ss & 1);
+        mbar_wait(&s_full[g], (uint32_t)(ss & 1));
+        tc_fence_after();
+        uint32_t sr[4][32];
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) tmem_ld32_nowait(s_addr + (uint32_t)(cc * 32), sr[cc]);
+        tmem_ld_wait();
+        // S is in registers: the MMA warp may overwrite it with the next tile's logits; after the last tile of this Q tile
+        // the Q buffer may be refilled as well
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(&s_drained[g]);
+          if (j == nt - 1) mbar_arrive(&q_free[(t & 1) * 2 + g]);
+        }
+        float rw[8];
+#pragma unroll
+        for (int a = 0; a < 8; ++a) rw[a] = -CUDART_INF_F;
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc)
+#pragma unroll
+          for (int k = 0; k < 32; ++k) rw[k & 7] = fmaxf(rw[k & 7], __uint_as_float(sr[cc][k]));
+        const float mx = c * fmaxf(fmaxf(fmaxf(rw[0], rw[1]), fmaxf(rw[2], rw[3])), fmaxf(fmaxf(rw[4], rw[5]), fmaxf(rw[6], rw[7])));
+        if (__any_sync(0xffffffffu, mx > m + PP_LAZY)) {
+          // raise the reference (rare after the first tiles): what has been accumulated in TMEM is rescaled in place.  Every
+          // P.V of this Q tile issued so far must have retired (P.V(j-1) is the last one; the MMA warp cannot issue P.V(j)
+          // before this thread's p_ready arrival below)
+          const float mn = mx > m + PP_LAZY ? mx : m;
+          const float corr = ex2_ftz(m - mn);
+          m = mn;
+          l *= corr;
+          if (j > 0) {
+            mbar_wait(&pv_done[g * 2 + (buf ^ 1)], (uint32_t)(((ss - 1) >> 1) & 1));
+            tc_fence_after();
+            uint32_t r[32];
+            tmem_ld32(o_addr, r);
+#pragma unroll
+            for (int e = 0; e < 32; ++e) r[e] = __float_as_uint(__uint_as_float(r[e]) * corr);
+            tmem_st32(o_addr, r);
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+          }
+        }
+        // P buffer `buf` was last read by P.V of step ss-2
+        if (ss >= 2) mbar_wait(&pv_done[g * 2 + buf], (uint32_t)(((ss - 2) >> 1) & 1));
+        const uint32_t prow = p_grp + (uint32_t)(buf * 32768);
+        float lsum = 0.f;
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) {
+#pragma unroll
+          for (int gq = 0; gq < 4; ++gq) {
+            uint32_t pk[4];
+            __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(pk);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float xa = fmaf(__uint_as_float(sr[cc][gq * 8 + 2 * e]), c, -m);
+              const float xb = fmaf(__uint_as_float(sr[cc][gq * 8 + 2 * e + 1]), c, -m);
+              const float a = (2 * e < POLY) ? ex2_poly(xa) : ex2_ftz(xa);
+              const float b = (2 * e + 1 < POLY) ? ex2_poly(xb) : ex2_ftz(xb);
+              h2[e] = __floats2bfloat162_rn(a, b);
+              lsum += a + b;
+            }
+            const int chunk = ((cc & 1) * 4 + gq) ^ (row & 7);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(prow + (uint32_t)((cc >> 1) * 16384 + chunk * 16)),
+                         "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3])
+                         : "memory");
+          }
+        }
+        l += lsum;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_ready[g * 2 + buf]);
+      }
+      // the Q tile's last P.V
+      mbar_wait(&pv_done[g * 2 + (int)((ss - 1) & 1)], (uint32_t)(((ss - 1) >> 1) & 1));
+      tc_fence_after();
+      uint32_t r[32];
+      tmem_ld32(o_addr, r);
+      tc_fence_before();   // the next Q tile's first P.V overwrites the accumulator; it is issued after this thread's next arrival
+      const float w0 = ex2_ftz(m_null - m);   // weight of the null key against the final reference
+      l += w0;
+      const float inv = 1.0f / l;
+      if (p.lse) p.lse[grow] = m + log2f(l);
+      __nv_bfloat16* orow = p.out + grow * DH;
+#pragma unroll
+      for (int e = 0; e < DH; e += 8) {
+        float tmp[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) tmp[k] = fmaf(w0, __ldg(p.null_kv + DH + e + k), __uint_as_float(r[e + k])) * inv;
+        store8(orow + e, tmp);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 9) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
 int attn_tc_supported(const dv_attn_mqa_params& p) {
   if (p.dtype != DV_BF16 || p.bias) return 0;
   if (p.dh != 32) return 0;
@@ -450,6 +762,25 @@ int attn_tc_launch(const dv_attn_mqa_params& p, cudaStream_t s) {
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
     if (sm_count <= 0) sm_count = 148;
+  }
+  // two Q tiles in flight per CTA whenever the tiles of a sequence pair up (DV_ATTN_MQA_PP=0: the one-tile kernel)
+  static const bool pp_off = getenv("DV_ATTN_MQA_PP") != nullptr && getenv("DV_ATTN_MQA_PP")[0] == '0';
+  if (!pp_off && k.q_tiles_per_seq % 2 == 0) {
+    const size_t smem_pp = 4 * 128 * DH * 2 + PP_STAGES * (AT_KT * DH * 2 + DH * AT_KT * 2) + 8 * 16384 + 512 + 1024;
+    static const int poly = getenv("DV_ATTN_MQA_POLY") ? atoi(getenv("DV_ATTN_MQA_POLY")) : PP_POLY_DEFAULT;
+    auto kern = poly <= 0 ? attn_mqa_pp_kernel<0> : poly == 1 ? attn_mqa_pp_kernel<1> : poly == 2 ? attn_mqa_pp_kernel<2>
+              : poly == 3 ? attn_mqa_pp_kernel<3> : attn_mqa_pp_kernel<4>;
+    static bool attr_pp = false;
+    if (!attr_pp) {
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      DV_REQUIRE(e == cudaSuccess, DV_ECUDA, "dv_attn_mqa(tcgen05, pairs): cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      attr_pp = true;
+    }
+    const int64_t pairs = k.total_tiles / 2;
+    const int grid_pp = (int)(pairs < sm_count ? pairs : sm_count);
+    kern<<<grid_pp, PP_THREADS, smem_pp, s>>>(mq, mk, mv, k);
+    DV_CHECK_LAUNCH("dv_attn_mqa(tcgen05, pairs)");
+    return DV_OK;
   }
   const int grid = (int)(k.total_tiles < sm_count ? k.total_tiles : sm_count);
   attn_tc_kernel<32, false><<<grid, AT_THREADS, smem, s>>>(mq, mk, mv, k);

@@ -742,6 +742,41 @@ def test_mqa_flash_attention_tcgen05(S, n, H):
     assert torch.equal(q2, out)
 
 
+@pytest.mark.parametrize("S,n,H,growth", [(2, 1024, 16, 8.0), (1, 512, 16, -8.0), (2, 256, 1, 0.0), (3, 128, 1, 6.0)])
+def test_mqa_flash_attention_tcgen05_reference_changes(S, n, H, growth):
+    """The two-tiles-in-flight kernel accumulates O in TMEM against a LAZILY raised reference and rescales the accumulator in
+    place when a key tile exceeds it by more than 2^5: keys whose magnitude grows (or shrinks) from tile to tile force that
+    path on every tile (or only on the first).  heads = 1 has an odd number of Q tiles per sequence at n = 128 (the
+    one-tile kernel) and an even one at n = 256.  Also checks the log2-domain row log-sum-exp the backward reads."""
+    D = 32
+    q = rnd(S * n, H * D, dtype=torch.bfloat16, seed=11)
+    kv = rnd(S * n, 2 * D, dtype=torch.bfloat16, seed=12, scale=2.0).float().reshape(S, n, 2 * D)
+    tile = torch.arange(n, device=dev()) // 128
+    f = 1.0 + abs(growth) * (tile if growth >= 0 else tile.flip(0)).float()
+    kv[:, :, :D] *= f[None, :, None]
+    kv = kv.reshape(S * n, 2 * D).to(torch.bfloat16).contiguous()
+    null_kv = rnd(2, D, seed=13)
+    out = torch.empty_like(q)
+    lse = torch.empty(S * n * H, device=dev())
+    p = L.AttnMqaParams(q=ptr(q), kv=ptr(kv), out=ptr(out), null_kv=ptr(null_kv), bias=None, workspace=None,
+                        workspace_bytes=0, S=S, n=n, heads=H, dh=D, scale=1.0 / D, dtype=code(q), impl=2)
+    p.lse = ptr(lse)
+    nbytes = L.lib().dv_attn_mqa_workspace_bytes(p)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev())
+    p.workspace, p.workspace_bytes = ptr(ws), nbytes
+    L.call("dv_attn_mqa", p, stream())
+    qh = q.float().reshape(S, n, H, D).permute(0, 2, 1, 3)
+    k, v = kv.float().reshape(S, n, 2 * D).chunk(2, dim=-1)
+    k = torch.cat((null_kv[0].expand(S, 1, D), k), dim=1)
+    v = torch.cat((null_kv[1].expand(S, 1, D), v), dim=1)
+    sim = torch.einsum("shid,sjd->shij", qh, k) / D
+    ref = torch.einsum("shij,sjd->shid", sim.softmax(-1), v).permute(0, 2, 1, 3).reshape(S * n, H * D)
+    assert torch.isfinite(out.float()).all()
+    assert rel_err(out, ref) < 1e-2
+    ref_lse = torch.logsumexp(sim, dim=-1).permute(0, 2, 1).reshape(-1) * 1.4426950408889634
+    assert float((lse - ref_lse).abs().max()) < 2e-2
+
+
 @pytest.mark.parametrize("dtype", DT)
 @pytest.mark.parametrize("k,H", [(15, 8), (7, 6), (3, 4)])
 def test_im2col_halo_layout(dtype, k, H):
