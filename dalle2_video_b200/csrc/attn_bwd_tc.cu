@@ -107,7 +107,7 @@ __global__ void __launch_bounds__(AB_THREADS, 1)
 attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_do,
                    const __grid_constant__ CUtensorMap map_kv, const AttnBwdTcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = align_smem_1024(smem_raw);
   constexpr int T_BYTES = 128 * 64;            // one [128][32] bf16 tile (64-byte rows)
   uint8_t* k_s = smem;                         // K_j
   uint8_t* v_s = k_s + T_BYTES;                // V_j
@@ -343,7 +343,7 @@ xattn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
                     const XattnBwdTcParams pp) {
   const dv_xattn_bwd_params& p = pp.a;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = align_smem_1024(smem_raw);
   constexpr int T_BYTES = 128 * 128;           // one [128 tokens][64] bf16 tile
   uint8_t* k_s = smem;                         // [16 keys][128 B] SW128
   uint8_t* v_s = k_s + 2048;
@@ -584,7 +584,7 @@ __global__ void __launch_bounds__(XB_THREADS, 3)
 xattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const XattnFwdTcParams pp) {
   const dv_xattn_params& p = pp.a;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = align_smem_1024(smem_raw);
   constexpr int T_BYTES = 128 * 128;
   constexpr int STAGES = 3;
   uint8_t* k_s = smem;

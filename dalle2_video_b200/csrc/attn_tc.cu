@@ -81,7 +81,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1)
 attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                const __grid_constant__ CUtensorMap map_vt, const AttnTcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = align_smem_1024(smem_raw);
   constexpr int ROWB = DH * 2;                 // bytes per q/k row (64 for dh=32)
   constexpr int Q_BYTES = 128 * ROWB;          // 8 KB
   constexpr int K_BYTES = AT_KT * ROWB;        // 8 KB
@@ -425,7 +425,7 @@ attn_mqa_pp_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
                    const __grid_constant__ CUtensorMap map_vt, const AttnTcParams p) {
   constexpr int DH = 32;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = align_smem_1024(smem_raw);
   constexpr int ROWB = DH * 2;
   constexpr int Q_BYTES = 128 * ROWB;          // 8 KB
   constexpr int K_BYTES = AT_KT * ROWB;        // 8 KB

@@ -316,7 +316,7 @@ attn_temporal_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_
   constexpr uint32_t TMEM_COLS = NS <= 32 ? 64 : 128;     // x CTAs per SM <= 512
   const dv_attn_temporal_params& p = pp.a;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = align_smem_1024(smem_raw);
   uint8_t* ring = smem;                                   // [TT_STAGES][Q | K | V]
   uint8_t* p_s = ring + TT_STAGES * STAGE;                // [128][P_ROW]
   uint64_t* bars = reinterpret_cast<uint64_t*>(p_s + 128 * P_ROW);

@@ -81,7 +81,7 @@ template <bool PRE>
 __device__ __forceinline__ void conv_halo_body(const CUtensorMap& map_a0, const CUtensorMap& map_a1, const CUtensorMap& map_b,
                                                const HaloParams& p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = align_smem_1024(smem_raw);
   const uint32_t b_bytes = (uint32_t)p.BN * 128 * 3;  // one weight stage = the three taps of one filter row
   uint8_t* a_ring = smem;
   uint8_t* b_ring = a_ring + (size_t)p.a_stages * p.a_stage_bytes;

@@ -38,7 +38,7 @@ __device__ __forceinline__ void rs_builder_bar() { asm volatile("bar.sync 2, 256
 __global__ void __launch_bounds__(RS_THREADS, 1)
 init_conv_rs_kernel(const __grid_constant__ CUtensorMap map_w, const InitConvRsParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = align_smem_1024(smem_raw);
   const uint32_t w_tap_bytes = (uint32_t)p.Cout * 128;
   uint8_t* w_s = smem;                                        // k taps x [Cout rows][64 K] SWIZZLE_128B
   uint8_t* v_s = w_s + ((size_t)p.k * w_tap_bytes + 1023) / 1024 * 1024;   // 2 buffers x [RS_VROWS][128 B]

@@ -44,7 +44,7 @@ __device__ __forceinline__ void builder_bar() { asm volatile("bar.sync 2, 256;" 
 __global__ void __launch_bounds__(IC_THREADS, 1)
 init_conv_tc_kernel(const __grid_constant__ CUtensorMap map_w, const InitConvParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = align_smem_1024(smem_raw);
   const uint32_t w_chunk_bytes = (uint32_t)p.Cout * 128;
   uint8_t* w_s = smem;                                             // n_chunks x [Cout rows][64 K] SWIZZLE_128B
   uint8_t* a_s = w_s + (size_t)p.n_chunks * w_chunk_bytes;         // IC_STAGES x [128 rows][64 K] SWIZZLE_128B

@@ -11,6 +11,13 @@ constexpr int TC_BK = 64;   // channels per K step (one 128-byte swizzle row)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// 1024-byte aligned start of the dynamic shared memory, by pointer arithmetic on the __shared__ array: after an integer round
+// trip (uintptr_t) the compiler no longer knows the address space and every later access becomes a generic LD.E / ST.E /
+// ATOM.E instead of LDS / STS / ATOMS
+__device__ __forceinline__ uint8_t* align_smem_1024(uint8_t* raw) {
+  return raw + ((1024u - (smem_u32(raw) & 1023u)) & 1023u);
+}
+
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }

@@ -60,7 +60,7 @@ __global__ void __launch_bounds__(WT_THREADS, 1)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constant__ CUtensorMap map_x1,
                 const __grid_constant__ CUtensorMap map_dy, const WgradTcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = align_smem_1024(smem_raw);
   const int dy_blocks = p.BN / 64;
   const int stage_bytes = (dy_blocks + 2 * p.acc) * WT_BLOCK_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.stages * stage_bytes);
@@ -229,7 +229,7 @@ __global__ void __launch_bounds__(WT_THREADS, 1)
 wgrad_halo_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constant__ CUtensorMap map_x1,
                   const __grid_constant__ CUtensorMap map_dy, const WgradHaloParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = align_smem_1024(smem_raw);
   constexpr int DY_BYTES = WH_POS * 128;
   constexpr int STAGES = 2;
   const int stage_bytes = DY_BYTES + p.win_bytes;

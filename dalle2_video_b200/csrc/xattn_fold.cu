@@ -131,7 +131,7 @@ xattn_fold_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
                   const __grid_constant__ CUtensorMap map_u, const __grid_constant__ CUtensorMap map_out,
                   const XfoldParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = align_smem_1024(smem_raw);
   const uint32_t x_stage_bytes = (uint32_t)p.chunks * 16384;
   uint8_t* x_s = smem;                                           // [xs][chunks][128 rows x 128 B]
   uint8_t* mq_s = x_s + (size_t)p.xs * x_stage_bytes;            // [chunks][64 rows x 128 B]
