@@ -133,7 +133,11 @@ class InitConvParams(C.Structure):
 
 class ToOutParams(C.Structure):
     _fields_ = [("x", vp), ("w", vp), ("bias", vp), ("out", vp), ("B", i32), ("P", i64), ("C", i32), ("Cout", i32),
-                ("dtype", i32), ("extra", vp), ("Cextra", i32)]
+                ("dtype", i32), ("extra", vp), ("Cextra", i32), ("k", i32), ("H", i32), ("W", i32)]
+
+
+class UpsampleNearest2xParams(C.Structure):
+    _fields_ = [("in_", vp), ("out", vp), ("n_img", i32), ("H", i32), ("W", i32), ("row_bytes", i32)]
 
 
 class PatchifyParams(C.Structure):
@@ -244,7 +248,7 @@ ENTRY_POINTS = {
     "dv_xattn_fold_prep_multi": XattnFoldPrepMultiParams,
     "dv_attn_mqa": AttnMqaParams, "dv_attn_temporal": AttnTemporalParams,
     "dv_time_embed": TimeEmbedParams, "dv_linear_small": LinearSmallParams,
-    "dv_cond_tokens": CondTokensParams, "dv_to_out": ToOutParams, "dv_im2col_init": Im2colParams,
+    "dv_cond_tokens": CondTokensParams, "dv_to_out": ToOutParams, "dv_upsample_nearest2x": UpsampleNearest2xParams, "dv_im2col_init": Im2colParams,
     "dv_init_conv": InitConvParams, "dv_resize_nearest": ResizeNearestParams,
     "dv_patchify": PatchifyParams, "dv_mha_small": MhaSmallParams,
     # training step (a16)

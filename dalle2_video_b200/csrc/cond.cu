@@ -178,7 +178,84 @@ __global__ void __launch_bounds__(256) to_out_kernel(dv_to_out_params p) {
   for (int o = 0; o < CO; ++o) p.out[((int64_t)b * CO + o) * p.P + pos] = acc[o];
 }
 
+// to_out with a (1, k, k) window (final_conv_ksize > 1): thread per position, weights [CO][k][k][C + Cextra] in shared
+// memory, zero padding by skipping the taps outside the frame.
+template <typename T, int CO>
+__global__ void __launch_bounds__(256) to_out_window_kernel(dv_to_out_params p) {
+  extern __shared__ float w[];
+  const int ldw = p.C + p.Cextra;
+  const int kk = p.k * p.k;
+  for (int i = threadIdx.x; i < CO * kk * ldw; i += blockDim.x) w[i] = p.w[i];
+  __syncthreads();
+  const int b = blockIdx.y;
+  const int64_t pos = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (pos >= p.P) return;
+  const int hw = p.H * p.W;
+  const int64_t frame = pos / hw;
+  const int rem = (int)(pos - frame * hw);
+  const int y = rem / p.W, x = rem - y * p.W;
+  const int r = p.k / 2;
+  float acc[CO];
+#pragma unroll
+  for (int o = 0; o < CO; ++o) acc[o] = p.bias ? p.bias[o] : 0.f;
+  for (int dy = 0; dy < p.k; ++dy) {
+    const int yy = y + dy - r;
+    if (yy < 0 || yy >= p.H) continue;
+    for (int dx = 0; dx < p.k; ++dx) {
+      const int xx = x + dx - r;
+      if (xx < 0 || xx >= p.W) continue;
+      const int64_t q = frame * hw + (int64_t)yy * p.W + xx;
+      const T* xin = reinterpret_cast<const T*>(p.x) + ((int64_t)b * p.P + q) * p.C;
+      const float* wt = w + (dy * p.k + dx) * ldw;
+      for (int c = 0; c < p.C; c += 8) {
+        float v[8];
+        load8(xin + c, v);
+#pragma unroll
+        for (int o = 0; o < CO; ++o)
+#pragma unroll
+          for (int e = 0; e < 8; ++e) acc[o] = fmaf(v[e], wt[o * kk * ldw + c + e], acc[o]);
+      }
+      for (int c = 0; c < p.Cextra; ++c) {
+        const float v = p.extra[((int64_t)b * p.Cextra + c) * p.P + q];
+#pragma unroll
+        for (int o = 0; o < CO; ++o) acc[o] = fmaf(v, wt[o * kk * ldw + p.C + c], acc[o]);
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 0; o < CO; ++o) p.out[((int64_t)b * CO + o) * p.P + pos] = acc[o];
+}
+
+// nearest x2 of channels-last rows: one thread per 16 bytes of an output pixel
+__global__ void __launch_bounds__(256) upsample_nearest2x_kernel(dv_upsample_nearest2x_params p) {
+  const int v = p.row_bytes / 16;
+  const int64_t total = (int64_t)p.n_img * (2 * p.H) * (2 * p.W) * v;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % v);
+    int64_t pix = i / v;
+    const int xo = (int)(pix % (2 * p.W));
+    pix /= 2 * p.W;
+    const int yo = (int)(pix % (2 * p.H));
+    const int64_t n = pix / (2 * p.H);
+    const int64_t src = ((n * p.H + (yo >> 1)) * p.W + (xo >> 1)) * v + c;
+    reinterpret_cast<uint4*>(p.out)[i] = __ldg(reinterpret_cast<const uint4*>(p.in) + src);
+  }
+}
+
 }  // namespace dv
+
+extern "C" int dv_upsample_nearest2x(const dv_upsample_nearest2x_params* p, dv_stream_t stream) {
+  using namespace dv;
+  DV_REQUIRE(p && p->in && p->out, DV_EINVAL, "dv_upsample_nearest2x: null pointer");
+  DV_REQUIRE(p->n_img > 0 && p->H > 0 && p->W > 0 && p->row_bytes > 0 && p->row_bytes % 16 == 0, DV_EINVAL,
+             "dv_upsample_nearest2x: bad dimensions (row_bytes %% 16)");
+  DV_REQUIRE(aligned16(p->in) && aligned16(p->out), DV_EALIGN, "dv_upsample_nearest2x: 16-byte alignment");
+  const int64_t total = (int64_t)p->n_img * 4 * p->H * p->W * (p->row_bytes / 16);
+  const int64_t blocks = (total + 255) / 256;
+  upsample_nearest2x_kernel<<<(unsigned)(blocks < 148 * 16 ? blocks : 148 * 16), 256, 0, as_stream(stream)>>>(*p);
+  DV_CHECK_LAUNCH("dv_upsample_nearest2x");
+  return DV_OK;
+}
 
 extern "C" int dv_time_embed(const dv_time_embed_params* p, dv_stream_t stream) {
   using namespace dv;
@@ -232,8 +309,20 @@ extern "C" int dv_to_out(const dv_to_out_params* p, dv_stream_t stream) {
   DV_REQUIRE(aligned16(p->x), DV_EALIGN, "dv_to_out: x must be 16-byte aligned");
   dim3 grid((unsigned)((p->P + 255) / 256), p->B);
   DV_REQUIRE(p->Cextra >= 0 && (p->Cextra == 0 || p->extra), DV_EINVAL, "dv_to_out: Cextra > 0 needs extra");
-  const size_t smem = sizeof(float) * p->Cout * (p->C + p->Cextra);
   cudaStream_t s = as_stream(stream);
+  if (p->k > 1) {
+    DV_REQUIRE(p->k % 2 == 1 && p->k <= 7, DV_EUNSUPPORTED, "dv_to_out: final_conv_ksize must be odd and <= 7 (got %d)", p->k);
+    DV_REQUIRE(p->H > 0 && p->W > 0 && p->P % ((int64_t)p->H * p->W) == 0, DV_EINVAL, "dv_to_out: P must be frames * H * W");
+    const size_t smem_w = sizeof(float) * p->Cout * p->k * p->k * (p->C + p->Cextra);
+    DV_REQUIRE(smem_w <= 48 * 1024, DV_EUNSUPPORTED, "dv_to_out: %d x %d head weights do not fit shared memory", p->k, p->k);
+#define DV_TO_OUT_W(T, CO) to_out_window_kernel<T, CO><<<grid, 256, smem_w, s>>>(*p)
+    if (p->dtype == DV_F32) { if (p->Cout == 3) DV_TO_OUT_W(float, 3); else DV_TO_OUT_W(float, 6); }
+    else { if (p->Cout == 3) DV_TO_OUT_W(__nv_bfloat16, 3); else DV_TO_OUT_W(__nv_bfloat16, 6); }
+#undef DV_TO_OUT_W
+    DV_CHECK_LAUNCH("dv_to_out(window)");
+    return DV_OK;
+  }
+  const size_t smem = sizeof(float) * p->Cout * (p->C + p->Cextra);
 #define DV_TO_OUT(T, CO) to_out_kernel<T, CO><<<grid, 256, smem, s>>>(*p)
   if (p->dtype == DV_F32) { if (p->Cout == 3) DV_TO_OUT(float, 3); else DV_TO_OUT(float, 6); }
   else { if (p->Cout == 3) DV_TO_OUT(__nv_bfloat16, 3); else DV_TO_OUT(__nv_bfloat16, 6); }

@@ -182,12 +182,17 @@ class Unet3D(nn.Module):
 
         unsupported = dict(sparse_attn=sparse_attn, cosine_sim_cross_attn=cosine_sim_cross_attn,
                            cosine_sim_self_attn=cosine_sim_self_attn, cross_embed_downsample=cross_embed_downsample,
-                           memory_efficient=memory_efficient, combine_upsample_fmaps=combine_upsample_fmaps,
+                           combine_upsample_fmaps=combine_upsample_fmaps,
                            resnet_weight_standardization=resnet_weight_standardization)
         bad = [k for k, v in unsupported.items() if v]
-        if bad or not pixel_shuffle_upsample or final_conv_ksize != 1:
-            raise NotImplementedError(f"Unet3D(b200): options outside the accelerated hot path: "
-                                      f"{bad or ['pixel_shuffle_upsample=False / final_conv_ksize!=1']}")
+        if bad:
+            raise NotImplementedError(f"Unet3D(b200): options outside the accelerated hot path: {bad}")
+        assert final_conv_ksize % 2 == 1 and final_conv_ksize <= 7, "final_conv_ksize must be odd and <= 7"
+        if memory_efficient:
+            assert not temporal_attn or not any(_cast_tuple(temporal_attn, len(dim_mults))), \
+                "memory_efficient and the temporal_attn extension are not combined"
+        self.memory_efficient, self.pixel_shuffle_upsample = memory_efficient, pixel_shuffle_upsample
+        self.final_conv_ksize = final_conv_ksize
 
         self.lowres_cond, self.self_cond = lowres_cond, self_cond
         self.lowres_noise_cond = lowres_noise_cond
@@ -265,7 +270,11 @@ class Unet3D(nn.Module):
             self.up_temporal_attns = nn.ModuleList([make_tattn(d) if f else nn.Identity()
                                                     for d, f in zip(reversed(dims_all), reversed(temporal_attn))])
 
-        self.init_resnet_block = None
+        # memory_efficient (:466-477, :499-541, :611): an initial resnet block, the downsample BEFORE each stage's blocks (which
+        # then run at the stage's output width and half its input resolution), a 1x1x1 convolution after them, and an
+        # upsample after EVERY up stage
+        self.init_resnet_block = res(init_dim, init_dim, groups=resnet_groups[0]) if memory_efficient else None
+        down = lambda a, b: nn.Sequential(nn.Identity(), nn.Conv3d(a * 4, b, 1))  # noqa: E731  Downsample3D (:19-26)
         self.downs = nn.ModuleList([])
         self.ups = nn.ModuleList([])
         skip_dims = []
@@ -273,14 +282,15 @@ class Unet3D(nn.Module):
                 zip(in_out, resnet_groups, num_resnet_blocks, self_attn)):
             is_first, is_last = ind == 0, ind >= n_stages - 1
             layer_cond = cond_dim if not is_first else None
-            skip_dims.append(d_in)
+            d_l = d_out if memory_efficient else d_in
+            skip_dims.append(d_l)
             self.downs.append(nn.ModuleList([
-                None,
-                res(d_in, d_in, groups=groups),
-                nn.ModuleList([res(d_in, d_in, cond_dim=layer_cond, groups=groups) for _ in range(nblk)]),
-                make_attn(d_in) if sattn else nn.Identity(),
+                down(d_in, d_out) if memory_efficient else None,
+                res(d_l, d_l, groups=groups),
+                nn.ModuleList([res(d_l, d_l, cond_dim=layer_cond, groups=groups) for _ in range(nblk)]),
+                make_attn(d_l) if sattn else nn.Identity(),
                 # Downsample3D = Sequential(Rearrange, Conv3d(4*dim, dim_out, 1)) (:19-26) / plain 1x1x1 conv (:537)
-                nn.Sequential(nn.Identity(), nn.Conv3d(d_in * 4, d_out, 1)) if not is_last else nn.Conv3d(d_in, d_out, 1),
+                down(d_l, d_out) if not is_last and not memory_efficient else nn.Conv3d(d_l, d_out, 1),
             ]))
 
         mid_dim = dims[-1]
@@ -297,13 +307,17 @@ class Unet3D(nn.Module):
                 res(d_out + skip, d_out, cond_dim=layer_cond, groups=groups),
                 nn.ModuleList([res(d_out + skip, d_out, cond_dim=layer_cond, groups=groups) for _ in range(nblk)]),
                 make_attn(d_out) if sattn else nn.Identity(),
-                _PixelShuffleUp(d_out, d_in) if not is_last else nn.Identity(),
+                # PixelShuffleUpsample3D (:38-78) or NearestUpsample3D = Sequential(nn.Upsample, Conv3d (1,3,3)) (:29-35)
+                (_PixelShuffleUp(d_out, d_in) if pixel_shuffle_upsample else
+                 nn.Sequential(nn.Identity(), nn.Conv3d(d_out, d_in, (1, 3, 3), padding=(0, 1, 1))))
+                if not is_last or memory_efficient else nn.Identity(),
             ]))
 
         self.upsample_combiner = nn.Identity()  # disabled combiner: parameter-free, dim_out == dim
         self.final_resnet_block = res(dim + dim, dim, groups=resnet_groups[0])
         out_dim_in = dim + (channels if lowres_cond else 0)
-        self.to_out = nn.Conv3d(out_dim_in, self.channels_out, kernel_size=(1, 1, 1))
+        self.to_out = nn.Conv3d(out_dim_in, self.channels_out, kernel_size=(1, final_conv_ksize, final_conv_ksize),
+                                padding=(0, final_conv_ksize // 2, final_conv_ksize // 2))
         nn.init.zeros_(self.to_out.weight)  # zero_init_ (:644)
         nn.init.zeros_(self.to_out.bias)
         self.checkpoint_during_training = checkpoint_during_training
@@ -375,6 +389,10 @@ class Unet3D(nn.Module):
     def train_plan(self, batch, frames, height, width, device):
         """Forward + backward launch plan of the training step (dalle2_video_b200/train.py)."""
         from .train import _TrainPlan
+        if self.memory_efficient or not self.pixel_shuffle_upsample or self.final_conv_ksize != 1:
+            raise NotImplementedError("Unet3D(b200): the training plan is built for the default layer plan only "
+                                      "(memory_efficient / pixel_shuffle_upsample=False / final_conv_ksize != 1 sample, "
+                                      "but do not train, on the native path)")
         # bf16 unless float32 is asked for explicitly (unet.compute_dtype = torch.float32: the parity mode)
         dtype = torch.float32 if self.compute_dtype == torch.float32 else torch.bfloat16
         key = ("train", batch, frames, height, width, str(device), dtype)
@@ -595,6 +613,8 @@ class _Engine:
 
         # ---- enumerate resnet blocks (for the concatenated time-MLP) and cross-attention layers
         blocks = []   # (prefix-less module, ctx kind)
+        if u.init_resnet_block is not None:
+            blocks.append((u.init_resnet_block, "c"))
         for s, st in enumerate(u.downs):
             blocks.append((st[1], "c"))
             blocks += [(m, "c") for m in st[2]]
@@ -770,7 +790,23 @@ class _Engine:
         h, w = H, W
         hiddens = []
         n_st = len(u.downs)
+
+        def unshuffle_conv(x, conv, h, w):
+            co, c4 = conv.weight.shape[0], conv.weight.shape[1]
+            ci = c4 // 4
+            # in-channel index of the reference is (c s1 s2) (:24); K order here is [s1][s2][c]
+            wp = conv.weight.detach().reshape(co, ci, 2, 2).permute(0, 2, 3, 1).reshape(co, 4 * ci)
+            y = self._new_act(B * T * (h // 2) * (w // 2), co)
+            self._conv([(x.ptr, ci)], self._w(wp), self._f32(conv.bias), y.ptr, co, n_img, h, w, mode=L.CONV_UNSHUFFLE)
+            self._release(x)
+            return y
+
+        if u.init_resnet_block is not None:
+            x = self._resblock(u.init_resnet_block, [x], h, w)
         for s, st in enumerate(u.downs):
+            if st[0] is not None:   # memory_efficient: downsample first (:898-899)
+                x = unshuffle_conv(x, st[0][1], h, w)
+                h, w = h // 2, w // 2
             x = self._resblock(st[1], [x], h, w)
             for m in st[2]:
                 x = self._resblock(m, [x], h, w)
@@ -783,15 +819,8 @@ class _Engine:
             x.refs += 1
             hiddens.append(x)
             post = st[4]
-            if s < n_st - 1:
-                conv = post[1]
-                co, c4 = conv.weight.shape[0], conv.weight.shape[1]
-                ci = c4 // 4
-                # in-channel index of the reference is (c s1 s2) (:24); K order here is [s1][s2][c]
-                wp = conv.weight.detach().reshape(co, ci, 2, 2).permute(0, 2, 3, 1).reshape(co, 4 * ci)
-                y = self._new_act(B * T * (h // 2) * (w // 2), co)
-                self._conv([(x.ptr, ci)], self._w(wp), self._f32(conv.bias), y.ptr, co, n_img, h, w,
-                           mode=L.CONV_UNSHUFFLE)
+            if isinstance(post, nn.Sequential):
+                x = unshuffle_conv(x, post[1], h, w)
                 h, w = h // 2, w // 2
             else:
                 conv = post
@@ -799,8 +828,8 @@ class _Engine:
                 y = self._new_act(B * T * h * w, co)
                 self._conv([(x.ptr, x.C)], self._w(conv.weight.detach().reshape(co, -1)), self._f32(conv.bias), y.ptr,
                            co, n_img, h, w)
-            self._release(x)
-            x = y
+                self._release(x)
+                x = y
 
         x = self._resblock(u.mid_block1, [x], h, w)
         x = self._self_attention(u.mid_attn.fn.fn, x, h, w)
@@ -819,7 +848,21 @@ class _Engine:
             if u._stage_temporal_attn[n_st - 1 - s]:
                 x = self._self_attention(u.up_temporal_attns[s], x, h, w, mode="temporal")
             up = st[3]
-            if not isinstance(up, nn.Identity):
+            if isinstance(up, nn.Sequential):
+                # NearestUpsample3D (:29-35): nearest x2 of the channels-last rows, then the (1,3,3) convolution
+                conv = up[1]
+                co, ci = conv.weight.shape[0], conv.weight.shape[1]
+                big = self._new_act(B * T * (2 * h) * (2 * w), ci)
+                self._op("dv_upsample_nearest2x", L.UpsampleNearest2xParams(
+                    in_=x.ptr, out=big.ptr, n_img=n_img, H=h, W=w, row_bytes=ci * (2 if self.dtype == torch.bfloat16 else 4)))
+                self._release(x)
+                h, w = 2 * h, 2 * w
+                y = self._new_act(B * T * h * w, co)
+                self._conv([(big.ptr, ci)], self._w(self._pack_conv(conv.weight)), self._f32(conv.bias), y.ptr, co, n_img,
+                           h, w, k=3)
+                self._release(big)
+                x = y
+            elif not isinstance(up, nn.Identity):
                 conv = up.conv
                 co4, ci = conv.weight.shape[0], conv.weight.shape[1]
                 cq = co4 // 4
@@ -834,12 +877,14 @@ class _Engine:
                 h, w = 2 * h, 2 * w
 
         x = self._resblock(u.final_resnet_block, [x, r], h, w, skip_scale=1.0)
-        wo = self._f32(u.to_out.weight.reshape(u.channels_out, -1))
+        # [Cout][C + Cextra] (1x1x1) or [Cout][k][k][C + Cextra] (final_conv_ksize > 1)
+        wo = self._f32(u.to_out.weight[:, :, 0].permute(0, 2, 3, 1).reshape(u.channels_out, -1))
         self._op("dv_to_out", L.ToOutParams(x=x.ptr, w=wo.data_ptr(), bias=self._f32(u.to_out.bias).data_ptr(),
                                             out=self.eps.data_ptr(), B=B, P=P, C=x.C, Cout=u.channels_out,
                                             dtype=self.code,
                                             extra=self.lowres_in.data_ptr() if u.lowres_cond else None,
-                                            Cextra=u.channels if u.lowres_cond else 0))
+                                            Cextra=u.channels if u.lowres_cond else 0,
+                                            k=u.final_conv_ksize, H=H, W=W))
         self.final_act = x  # kept alive
         # one launch builds the per-sample folded matrices of every short-context cross-attention layer (they depend on the
         # step's time tokens only); it runs right after the conditioning prologue

@@ -523,8 +523,22 @@ typedef struct {
    * [B][Cextra][P] (the low-resolution conditioning video as the caller holds it) or NULL; w is then [Cout][C + Cextra]. */
   const float* extra;
   int Cextra;
+  /* final_conv_ksize > 1 (:637-642: kernel (1, k, k), zero padding k/2): k odd <= 7 with the frame size H x W (P = frames *
+   * H * W per sample) and w as [Cout][k][k][C + Cextra]; k <= 1 is the 1x1x1 head (H, W unused). */
+  int k, H, W;
 } dv_to_out_params;
 int dv_to_out(const dv_to_out_params* p, dv_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * NearestUpsample3D's resampling (pixel_shuffle_upsample=False; :29-35: nn.Upsample(scale_factor=(1, 2, 2),
+ * mode="nearest") ahead of a (1,3,3) convolution, which runs through dv_conv_igemm) on channels-last activations:
+ * out[n][2y+i][2x+j][:] = in[n][y][x][:], rows of row_bytes (a multiple of 16) bytes. */
+typedef struct {
+  const void* in;   /* [n_img][H][W][row_bytes]   */
+  void* out;        /* [n_img][2H][2W][row_bytes] */
+  int n_img, H, W, row_bytes;
+} dv_upsample_nearest2x_params;
+int dv_upsample_nearest2x(const dv_upsample_nearest2x_params* p, dv_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Per-frame nearest-neighbour resize of a float32 (B,C,T,H,W) video, the only mode the cascade uses:

@@ -109,6 +109,46 @@ def main():
     print("sample text cfg", tuple(vid.shape), float(vid.mean()))
 
 
+# Off-default layer plans of Unet3D (dalle2_video.py:284-287, :443-456, :466-541, :611, :637-642): the reference's own modules
+OPTION_CASES = {
+    "memory_efficient": dict(unet=dict(dim=32, video_embed_dim=512, dim_mults=(1, 2), cond_on_video_embeds=True,
+                                       memory_efficient=True), shape=(2, 3, 4, 32, 32), times=(7, 640)),
+    "nearest_upsample": dict(unet=dict(dim=32, video_embed_dim=512, dim_mults=(1, 2, 4), cond_on_video_embeds=True,
+                                       pixel_shuffle_upsample=False), shape=(2, 3, 4, 32, 32), times=(7, 640)),
+    "final_conv3": dict(unet=dict(dim=32, video_embed_dim=512, dim_mults=(1, 2), cond_on_video_embeds=True,
+                                  final_conv_ksize=3), shape=(2, 3, 4, 32, 32), times=(7, 640)),
+    "all_three": dict(unet=dict(dim=32, video_embed_dim=512, dim_mults=(1, 2), cond_on_video_embeds=True,
+                                memory_efficient=True, pixel_shuffle_upsample=False, final_conv_ksize=3,
+                                lowres_cond=True), shape=(1, 3, 4, 32, 32), times=(311,), lowres=True),
+}
+
+
+def options():
+    """python -m oracle.make_golden options -> tests/golden/unet3d_options.pt (+ the state_dict layouts)."""
+    ref = reference.load()
+    out, layouts = {}, {}
+    for name, case in OPTION_CASES.items():
+        torch.manual_seed(0)
+        unet = ref.Unet3D(**case["unet"]).eval()
+        shapes = shapes_of(unet)
+        layouts[name] = shapes
+        sd = synth_state_dict(shapes, seed=7)
+        unet.load_state_dict(sd, strict=True)
+        g = torch.Generator().manual_seed(17)
+        x = torch.randn(case["shape"], generator=g)
+        emb = torch.randn(case["shape"][0], 512, generator=g)
+        low = torch.randn(case["shape"], generator=g) if case.get("lowres") else None
+        t = torch.tensor(case["times"], dtype=torch.long)
+        with torch.no_grad():
+            eps = unet(x, t, video_embed=emb, lowres_cond_video=low)
+        out[name] = {"x": x, "video_embed": emb, "lowres_cond_video": low, "times": t, "eps": eps,
+                     "unet_kwargs": case["unet"], "weight_seed": 7}
+        print(name, tuple(eps.shape), float(eps.abs().mean()))
+    torch.save(out, os.path.join(GOLDEN, "unet3d_options.pt"))
+    with open(os.path.join(GOLDEN, "unet3d_options_layouts.json"), "w") as f:
+        json.dump(layouts, f, indent=0, sort_keys=True)
+
+
 CASCADE_U1 = dict(dim=32, video_embed_dim=512, dim_mults=(1, 2), cond_on_video_embeds=True)
 CASCADE_U2 = dict(dim=16, video_embed_dim=512, dim_mults=(1, 2), cond_on_video_embeds=True)
 
@@ -394,5 +434,7 @@ if __name__ == "__main__":
         objectives()
     elif len(sys.argv) > 1 and sys.argv[1] == "decoder_layout":
         decoder_layout()
+    elif len(sys.argv) > 1 and sys.argv[1] == "options":
+        options()
     else:
         main()

@@ -34,6 +34,26 @@ def test_forward_matches_reference_fixture(name, dtype, tol, layouts):
     assert err < tol, err
 
 
+@pytest.mark.parametrize("name", ["memory_efficient", "nearest_upsample", "final_conv3", "all_three"])
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, FP32_TOL), (torch.bfloat16, BF16_TOL)])
+def test_off_default_layer_plans_match_reference_fixture(name, dtype, tol):
+    """memory_efficient (downsample first, initial resnet block, upsample after every up stage), NearestUpsample3D
+    (pixel_shuffle_upsample=False) and a 3x3 head (final_conv_ksize=3) — dalle2_video.py:284-287, :443-456, :466-541, :611,
+    :637-642 — against outputs of the reference's own Unet3D (`python -m oracle.make_golden options`)."""
+    import json
+    import os
+    from conftest import ROOT
+    g = golden("unet3d_options.pt")[name]
+    layout = json.load(open(os.path.join(ROOT, "tests", "golden", "unet3d_options_layouts.json")))[name]
+    u = make_unet(g["unet_kwargs"], layout, g["weight_seed"])
+    u.compute_dtype = dtype
+    low = g["lowres_cond_video"].cuda() if g["lowres_cond_video"] is not None else None
+    out = u(g["x"].cuda(), g["times"].cuda(), video_embed=g["video_embed"].cuda(), lowres_cond_video=low)
+    assert out.shape == g["eps"].shape and out.dtype == torch.float32
+    err = rel_err(out, g["eps"])
+    assert err < tol, err
+
+
 def test_forward_vs_oracle_with_drop_masks_and_per_sample_times(layouts):
     kw = dict(dim=32, video_embed_dim=512, dim_mults=(1, 2), cond_on_video_embeds=True,
               cond_on_text_encodings=True, text_embed_dim=64)

@@ -29,6 +29,31 @@ def test_state_dict_layout_matches_reference(name, layouts):
     assert {k: list(v.shape) for k, v in sd.items()} == layouts[name]
 
 
+@pytest.mark.parametrize("name", ["memory_efficient", "nearest_upsample", "final_conv3", "all_three"])
+def test_off_default_layer_plan_state_dict_layouts_match_reference(name):
+    """memory_efficient / pixel_shuffle_upsample=False / final_conv_ksize=3: same parameter names and shapes as the
+    reference's own modules (fixture: `python -m oracle.make_golden options`), and same-seed initialisation where the
+    reference is mounted."""
+    import json
+    ref_layout = json.load(open(os.path.join(ROOT, "tests", "golden", "unet3d_options_layouts.json")))[name]
+    kw = golden("unet3d_options.pt")[name]["unet_kwargs"]
+    torch.manual_seed(0)
+    sd = Unet3D(**kw).state_dict()
+    assert {k: list(v.shape) for k, v in sd.items()} == ref_layout
+    assert list(sd) == list(ref_layout) or sorted(sd) == sorted(ref_layout)
+    if reference.available():
+        torch.manual_seed(0)
+        a = reference.load().Unet3D(**kw).state_dict()
+        assert all(torch.equal(a[k], sd[k]) for k in a)
+
+
+def test_off_default_options_without_a_kernel_raise():
+    for kw in (dict(cosine_sim_cross_attn=True), dict(cosine_sim_self_attn=True), dict(cross_embed_downsample=True),
+               dict(combine_upsample_fmaps=True), dict(resnet_weight_standardization=True), dict(sparse_attn=True)):
+        with pytest.raises(NotImplementedError):
+            Unet3D(dim=32, video_embed_dim=512, dim_mults=(1, 2), cond_on_video_embeds=True, **kw)
+
+
 @pytest.mark.parametrize("use_noise", [False, True])
 def test_decoder_state_dict_layout_matches_reference(use_noise):
     """A reference two-unet decoder checkpoint loads strict=True: the conditioner of a super-resolution unet is a module
