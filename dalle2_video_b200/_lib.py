@@ -121,6 +121,15 @@ class CondTokensParams(C.Structure):
                 ("eps", f32)]
 
 
+class LinearSmallBwdParams(C.Structure):
+    _fields_ = [("fwd", LinearSmallParams), ("dy", vp), ("dz", vp), ("dw", vp), ("db", vp), ("dx", vp), ("dalt", vp)]
+
+
+class CondTokensBwdParams(C.Structure):
+    _fields_ = [("fwd", CondTokensParams), ("dc", vp), ("dmid", vp), ("dtime_tokens", vp), ("dvideo_tokens", vp),
+                ("dnull_video", vp), ("dln_w", vp), ("dln_b", vp), ("dln_mid_w", vp), ("dln_mid_b", vp)]
+
+
 class Im2colParams(C.Structure):
     _fields_ = [("x", vp), ("out", vp), ("B", i32), ("C", i32), ("T", i32), ("H", i32), ("W", i32), ("k", i32),
                 ("Kpad", i32), ("dtype", i32), ("layout", i32)]
@@ -248,7 +257,8 @@ ENTRY_POINTS = {
     "dv_xattn_fold_prep_multi": XattnFoldPrepMultiParams,
     "dv_attn_mqa": AttnMqaParams, "dv_attn_temporal": AttnTemporalParams,
     "dv_time_embed": TimeEmbedParams, "dv_linear_small": LinearSmallParams,
-    "dv_cond_tokens": CondTokensParams, "dv_to_out": ToOutParams, "dv_upsample_nearest2x": UpsampleNearest2xParams, "dv_im2col_init": Im2colParams,
+    "dv_cond_tokens": CondTokensParams, "dv_linear_small_bwd": LinearSmallBwdParams,
+    "dv_cond_tokens_bwd": CondTokensBwdParams, "dv_to_out": ToOutParams, "dv_upsample_nearest2x": UpsampleNearest2xParams, "dv_im2col_init": Im2colParams,
     "dv_init_conv": InitConvParams, "dv_resize_nearest": ResizeNearestParams,
     "dv_patchify": PatchifyParams, "dv_mha_small": MhaSmallParams,
     # training step (a16)

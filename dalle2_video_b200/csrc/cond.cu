@@ -147,6 +147,226 @@ __global__ void __launch_bounds__(128) cond_tokens_kernel(dv_cond_tokens_params 
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Backward of the prologue (training step).  Batch-sized problems (M <= a few hundred rows): plain CUDA-core kernels.
+__device__ __forceinline__ float act_grad(float v, int act) {   // d act(v) / d v
+  if (act == DV_ACT_SILU) {
+    const float sg = 1.0f / (1.0f + expf(-v));
+    return sg * (1.0f + v * (1.0f - sg));
+  }
+  if (act == DV_ACT_GELU) {
+    const float cdf = 0.5f * (1.0f + erff(v * 0.70710678118654752440f));
+    return cdf + v * 0.39894228040143267794f * expf(-0.5f * v * v);
+  }
+  return 1.0f;
+}
+
+// dz[m][n] = dy[m][n] * post'(z[m][n]) (z recomputed), dropped rows -> dalt.  block = (128 outputs n, one row m)
+__global__ void __launch_bounds__(128) linear_small_bwd_dz_kernel(dv_linear_small_bwd_params q) {
+  extern __shared__ float xrow[];   // pre(x[m][:])
+  const dv_linear_small_params& p = q.fwd;
+  const int m = blockIdx.y, m1 = m / p.M2, m2 = m % p.M2;
+  const int n = blockIdx.x * 128 + threadIdx.x;
+  const bool need_z = p.post_act != DV_ACT_NONE;
+  if (need_z) {
+    const float* x = p.x + (int64_t)m1 * p.ldx1 + (int64_t)m2 * p.ldx2;
+    for (int k = threadIdx.x; k < p.K; k += 128) xrow[k] = apply_act(x[k], p.pre_act);
+    __syncthreads();
+  }
+  if (n >= p.N) return;
+  float g = q.dy[(int64_t)m1 * p.ldy1 + (int64_t)m2 * p.ldy2 + n];
+  if (p.keep && !p.keep[m1]) {
+    if (q.dalt) atomicAdd(&q.dalt[(int64_t)m2 * p.N + n], g);
+    g = 0.f;
+  } else if (need_z) {
+    float z = p.bias ? p.bias[n] : 0.f;
+    const float* w = p.w + (int64_t)n * p.K;
+    for (int k = 0; k < p.K; ++k) z = fmaf(xrow[k], w[k], z);
+    g *= act_grad(z, p.post_act);
+  }
+  q.dz[(int64_t)m * p.N + n] = g;
+}
+
+// dw[n][k] += sum_m dz[m][n] pre(x[m][k]);  db[n] += sum_m dz[m][n].  A 64 n x 64 k tile per block, the rows m staged 32 at a
+// time in shared memory (pre(x) evaluated once per tile element); thread = 4 n x 4 k.
+__global__ void __launch_bounds__(256) linear_small_bwd_dw_kernel(dv_linear_small_bwd_params q) {
+  __shared__ float dzs[32][65];
+  __shared__ float xs[32][65];
+  const dv_linear_small_params& p = q.fwd;
+  const int M = p.M1 * p.M2;
+  const int k0 = blockIdx.x * 64, n0 = blockIdx.y * 64;
+  const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
+  float acc[4][4], accb[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    accb[i] = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  }
+  for (int m0 = 0; m0 < M; m0 += 32) {
+    for (int idx = threadIdx.x; idx < 32 * 64; idx += 256) {
+      const int mm = idx >> 6, cc = idx & 63;
+      const int m = m0 + mm;
+      dzs[mm][cc] = (m < M && n0 + cc < p.N) ? q.dz[(int64_t)m * p.N + n0 + cc] : 0.f;
+      float xv = 0.f;
+      if (m < M && k0 + cc < p.K)
+        xv = apply_act(p.x[(int64_t)(m / p.M2) * p.ldx1 + (int64_t)(m % p.M2) * p.ldx2 + k0 + cc], p.pre_act);
+      xs[mm][cc] = xv;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int mm = 0; mm < 32; ++mm) {
+      float av[4], bv[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { av[i] = dzs[mm][ty * 4 + i]; bv[i] = xs[mm][tx * 4 + i]; }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        accb[i] += av[i];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int n = n0 + ty * 4 + i;
+    if (n >= p.N) continue;
+    if (q.dw) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int k = k0 + tx * 4 + j;
+        if (k < p.K) q.dw[(int64_t)n * p.K + k] += acc[i][j];
+      }
+    }
+    if (q.db && blockIdx.x == 0 && tx == 0) q.db[n] += accb[i];
+  }
+}
+
+// dx[m][k] += pre'(x[m][k]) sum_n dz[m][n] w[n][k]: a 32 m x 64 k tile per block over a chunk of LSB_NCHUNK outputs n
+// (blockIdx.z; atomic accumulation across chunks), n staged 32 at a time; thread = 2 m x 4 k.
+constexpr int LSB_NCHUNK = 256;
+__global__ void __launch_bounds__(256) linear_small_bwd_dx_kernel(dv_linear_small_bwd_params q) {
+  __shared__ float dzs[32][33];
+  __shared__ float ws[32][65];
+  const dv_linear_small_params& p = q.fwd;
+  const int M = p.M1 * p.M2;
+  const int k0 = blockIdx.x * 64, m0 = blockIdx.y * 32;
+  const int nlo = blockIdx.z * LSB_NCHUNK, nhi = min(nlo + LSB_NCHUNK, p.N);
+  const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
+  float acc[2][4];
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  for (int n0 = nlo; n0 < nhi; n0 += 32) {
+    for (int idx = threadIdx.x; idx < 32 * 32; idx += 256) {
+      const int mm = idx >> 5, nn = idx & 31;
+      dzs[mm][nn] = (m0 + mm < M && n0 + nn < nhi) ? q.dz[(int64_t)(m0 + mm) * p.N + n0 + nn] : 0.f;
+    }
+    for (int idx = threadIdx.x; idx < 32 * 64; idx += 256) {
+      const int nn = idx >> 6, kk = idx & 63;
+      ws[nn][kk] = (n0 + nn < nhi && k0 + kk < p.K) ? __ldg(p.w + (int64_t)(n0 + nn) * p.K + k0 + kk) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int nn = 0; nn < 32; ++nn) {
+      const float a0 = dzs[ty * 2][nn], a1 = dzs[ty * 2 + 1][nn];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float bv = ws[nn][tx * 4 + j];
+        acc[0][j] = fmaf(a0, bv, acc[0][j]);
+        acc[1][j] = fmaf(a1, bv, acc[1][j]);
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int m = m0 + ty * 2 + i;
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int k = k0 + tx * 4 + j;
+      if (k >= p.K) continue;
+      const int64_t off = (int64_t)(m / p.M2) * p.ldx1 + (int64_t)(m % p.M2) * p.ldx2 + k;
+      float v = acc[i][j];
+      if (p.pre_act != DV_ACT_NONE) v *= act_grad(p.x[off], p.pre_act);
+      atomicAdd(&q.dx[off], v);
+    }
+  }
+}
+
+// One warp per (sample, token) of [time | video]: both LayerNorm backwards, then the gradient goes to the token's source.
+__global__ void __launch_bounds__(128) cond_tokens_bwd_kernel(dv_cond_tokens_bwd_params q) {
+  const dv_cond_tokens_params& p = q.fwd;
+  const int lane = threadIdx.x & 31;
+  const int n_c = p.n_time + p.n_video;
+  const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (w >= p.B * n_c) return;
+  const int b = w / n_c, j = w % n_c;
+  const bool is_time = j < p.n_time;
+  const int v = j - p.n_time;
+  const bool kept = is_time || p.keep_video[b];
+  const float* src = is_time ? p.time_tokens + ((int64_t)b * p.n_time + j) * p.D
+                             : (kept ? p.video_tokens + ((int64_t)b * p.n_video + v) * p.D : p.null_video + (int64_t)v * p.D);
+  float x[4];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int d = lane + 32 * i;
+    x[i] = d < p.D ? src[d] : 0.f;
+    s += x[i];
+  }
+  const float mean = warp_sum(s) / (float)p.D;
+  float qq = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int d = lane + 32 * i;
+    if (d < p.D) { const float t = x[i] - mean; qq += t * t; }
+  }
+  const float rstd = rsqrtf(warp_sum(qq) / (float)p.D + p.eps);
+  float dx[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int which = 0; which < 2; ++which) {
+    const float* dy = which == 0 ? q.dc : q.dmid;
+    if (!dy) continue;
+    const float* lw = which == 0 ? p.ln_w : p.ln_mid_w;
+    float* dlw = which == 0 ? q.dln_w : q.dln_mid_w;
+    float* dlb = which == 0 ? q.dln_b : q.dln_mid_b;
+    float g[4], xn[4];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int d = lane + 32 * i;
+      g[i] = 0.f; xn[i] = 0.f;
+      if (d < p.D) {
+        const float dyv = dy[((int64_t)b * n_c + j) * p.D + d];
+        xn[i] = (x[i] - mean) * rstd;
+        atomicAdd(&dlw[d], dyv * xn[i]);
+        atomicAdd(&dlb[d], dyv);
+        g[i] = dyv * lw[d];
+        s1 += g[i];
+        s2 += g[i] * xn[i];
+      }
+    }
+    s1 = warp_sum(s1) / (float)p.D;
+    s2 = warp_sum(s2) / (float)p.D;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) dx[i] += rstd * (g[i] - s1 - xn[i] * s2);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int d = lane + 32 * i;
+    if (d >= p.D) continue;
+    if (is_time) {
+      q.dtime_tokens[((int64_t)b * p.n_time + j) * p.D + d] = dx[i];
+    } else {
+      if (q.dvideo_tokens) q.dvideo_tokens[((int64_t)b * p.n_video + v) * p.D + d] = kept ? dx[i] : 0.f;
+      if (!kept && q.dnull_video) atomicAdd(&q.dnull_video[(int64_t)v * p.D + d], dx[i]);
+    }
+  }
+}
+
 // to_out: thread per position, weights in shared memory, output planes written coalesced.
 template <typename T, int CO>
 __global__ void __launch_bounds__(256) to_out_kernel(dv_to_out_params p) {
@@ -298,6 +518,45 @@ extern "C" int dv_cond_tokens(const dv_cond_tokens_params* p, dv_stream_t stream
   const int warps = p->B * (p->tok_end - p->tok_begin);
   cond_tokens_kernel<<<(warps + 3) / 4, 128, 0, as_stream(stream)>>>(*p);
   DV_CHECK_LAUNCH("dv_cond_tokens");
+  return DV_OK;
+}
+
+extern "C" int dv_linear_small_bwd(const dv_linear_small_bwd_params* q, dv_stream_t stream) {
+  using namespace dv;
+  DV_REQUIRE(q && q->fwd.x && q->fwd.w && q->dy && q->dz, DV_EINVAL, "dv_linear_small_bwd: null pointer");
+  const dv_linear_small_params& p = q->fwd;
+  DV_REQUIRE(p.M1 > 0 && p.M2 > 0 && p.N > 0 && p.K > 0, DV_EINVAL, "dv_linear_small_bwd: bad dimensions");
+  DV_REQUIRE(!p.keep || q->dalt, DV_EINVAL, "dv_linear_small_bwd: keep needs dalt");
+  DV_REQUIRE(p.K * sizeof(float) <= 48 * 1024, DV_EUNSUPPORTED, "dv_linear_small_bwd: K = %d does not fit shared memory", p.K);
+  const int M = p.M1 * p.M2;
+  DV_REQUIRE(M <= 65535, DV_EUNSUPPORTED, "dv_linear_small_bwd: more than 65535 rows");
+  cudaStream_t s = as_stream(stream);
+  linear_small_bwd_dz_kernel<<<dim3((p.N + 127) / 128, M), 128, p.K * sizeof(float), s>>>(*q);
+  DV_CHECK_LAUNCH("dv_linear_small_bwd(dz)");
+  if (q->dw || q->db) {
+    linear_small_bwd_dw_kernel<<<dim3(q->dw ? (p.K + 63) / 64 : 1, (p.N + 63) / 64), 256, 0, s>>>(*q);
+    DV_CHECK_LAUNCH("dv_linear_small_bwd(dw)");
+  }
+  if (q->dx) {
+    linear_small_bwd_dx_kernel<<<dim3((p.K + 63) / 64, (M + 31) / 32, (p.N + LSB_NCHUNK - 1) / LSB_NCHUNK), 256, 0, s>>>(*q);
+    DV_CHECK_LAUNCH("dv_linear_small_bwd(dx)");
+  }
+  return DV_OK;
+}
+
+extern "C" int dv_cond_tokens_bwd(const dv_cond_tokens_bwd_params* q, dv_stream_t stream) {
+  using namespace dv;
+  DV_REQUIRE(q && q->fwd.time_tokens && q->dtime_tokens && (q->dc || q->dmid), DV_EINVAL, "dv_cond_tokens_bwd: null pointer");
+  const dv_cond_tokens_params& p = q->fwd;
+  DV_REQUIRE(p.B > 0 && p.D > 0 && p.D <= 128, DV_EUNSUPPORTED, "dv_cond_tokens_bwd: cond_dim must be <= 128 (got %d)", p.D);
+  DV_REQUIRE(p.max_text == 0 && p.n_text_in == 0, DV_EUNSUPPORTED, "dv_cond_tokens_bwd: text tokens have no backward");
+  DV_REQUIRE(!q->dc || (q->dln_w && q->dln_b), DV_EINVAL, "dv_cond_tokens_bwd: dc needs dln_w / dln_b");
+  DV_REQUIRE(!q->dmid || (q->dln_mid_w && q->dln_mid_b), DV_EINVAL, "dv_cond_tokens_bwd: dmid needs dln_mid_w / dln_mid_b");
+  DV_REQUIRE(p.n_video == 0 || (p.video_tokens && p.null_video && p.keep_video), DV_EINVAL,
+             "dv_cond_tokens_bwd: video tokens need video_tokens / null_video / keep_video");
+  const int warps = p.B * (p.n_time + p.n_video);
+  cond_tokens_bwd_kernel<<<(warps + 3) / 4, 128, 0, as_stream(stream)>>>(*q);
+  DV_CHECK_LAUNCH("dv_cond_tokens_bwd");
   return DV_OK;
 }
 

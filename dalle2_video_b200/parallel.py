@@ -47,7 +47,7 @@ class GradBuckets:
     segment after which that slice of `flat` is final (use `n_segments` for parameters whose gradient arrives later,
     e.g. through torch autograd after the native backward).  Consecutive parameters with the same segment form a run;
     runs smaller than `min_bytes` join the neighbouring run that becomes ready next (never delaying a large run when
-    it can be avoided; a small run that is only ready at the very end stays a bucket of its own), so there are few,
+    it can be avoided; a small run that is only ready with the last segment or later stays a bucket of its own), so there are few,
     large collectives.  launch(s) starts the buckets of segment s on the process group's own stream; finish() launches
     whatever is left, waits, and divides by the world size (sum-then-divide, as allreduce_mean_ does)."""
 
@@ -79,7 +79,8 @@ class GradBuckets:
             later = [j for j in nb if runs[j][2] >= runs[i][2]]
             if later:      # join the neighbour that is ready soonest after this run: delays only the small run
                 j = min(later, key=lambda k: runs[k][2])
-            elif runs[i][2] == n_segments:
+            elif runs[i][2] >= n_segments - 1:   # ready only with the last segment (the conditioning prologue's parameters,
+                                                   # the first layers) or after it: never delays an earlier neighbour
                 kept.add((runs[i][0], runs[i][2]))
                 continue
             else:          # a local maximum in the middle of the backward: delay the closer neighbour

@@ -14,9 +14,11 @@ attention cores, the pixel-shuffle and the head have their own backward kernels 
 multi-consumer activations (skip connections, residual branches) are accumulated in the epilogue of the data-gradient
 launches (`add`) or by the kernels' accumulate flags.
 
-What is NOT native yet: the conditioning prologue (time / video-embedding MLPs, token LayerNorms, the to_kv and time_mlp
-linears: M = batch-sized fp32 GEMVs, < 0.01 % of the step's FLOPs) runs as plain torch ops with torch autograd; its
-outputs (scale/shift rows, k/v rows) are copied into the plan's buffers and their gradients come back from the kernels.
+The conditioning prologue (time / video-embedding MLPs, the where(keep, ., null) selects, token LayerNorms, the to_kv and
+time_mlp linears: batch-sized fp32 GEMVs, < 0.01 % of the step's FLOPs) is part of the plan too (_build_prologue: the
+sampling engine's forward kernels, dv_linear_small_bwd / dv_cond_tokens_bwd backward), so no torch autograd op is left in
+the step; DV_TRAIN_NATIVE_PROLOGUE=0 keeps the earlier form (plain torch ops under autograd whose outputs are copied into
+the plan's buffers) as a cross-check.
 Text conditioning and the extensions (temporal conv / attention) have no backward and raise.
 """
 from __future__ import annotations
@@ -507,6 +509,9 @@ class _TrainPlan:
                 self.dkv[kind] = torch.zeros(B, n_tok, len(mods) * inner2, device=dev)
                 self.zero_each_step.append(self.dkv[kind])
         self.kv_kinds = [k for k in ("c", "mid") if k in self.kv]
+        self.native_prologue = os.environ.get("DV_TRAIN_NATIVE_PROLOGUE", "1") != "0" and cond <= 128
+        if self.native_prologue:
+            self._build_prologue()
 
         n_img, P = B * T, T * H * W
         rows = B * P
@@ -645,7 +650,179 @@ class _TrainPlan:
         self.tape.append(backward)
         return out
 
-    # -------------------------------------------------------------- conditioning prologue (torch autograd, see module doc)
+    # -------------------------------------------------------------- conditioning prologue, native (forward + backward launches)
+    def _build_prologue(self):
+        """The conditioning prologue (:755-865: time / video-embedding MLPs, the where(keep, ., null) selects, token
+        LayerNorms, every ResnetBlock3D.time_mlp as one GEMV and every CrossAttention.to_kv) as launches of the plan:
+        forward = the sampling engine's kernels (dv_time_embed / dv_linear_small / dv_cond_tokens) on refreshed float32
+        weight copies, backward = dv_linear_small_bwd / dv_cond_tokens_bwd into kernel-layout accumulators like every
+        other parameter gradient.  It is the FIRST tape entry, so its backward launches come last, after every d ss /
+        d kv contribution.  The inputs (time, video_embed, keep mask, low-resolution noise level) are plan buffers that
+        p_losses fills before the forward."""
+        u, B, dev = self.u, self.B, self.device
+        dim, cond, tcd = u.dim, u.cond_dim, u.time_cond_dim
+        nt, nv = u.num_time_tokens, (u.num_image_tokens if u.cond_on_video_embeds else 0)
+        n_c = nt + nv
+        ved = u.video_embed_dim or 1
+        z = lambda *shape, dtype=torch.float32: torch.zeros(*shape, dtype=dtype, device=dev)  # noqa: E731
+        self.pro_time = z(B, dtype=torch.int64)
+        self.pro_level = z(B, dtype=torch.int64)
+        self.pro_ve = z(B, ved)
+        self.pro_keep = z(B, dtype=torch.uint8)
+        sin_emb, hid, time_tok, t_emb = z(B, dim), z(B, tcd), z(B, nt * cond), z(B, tcd)
+        c_tok, mid_tok = z(B, n_c, cond), z(B, n_c, cond)
+        video_tok = z(B, max(nv, 1) * cond)
+        d_hid, d_time_tok, d_t_emb = z(B, tcd), z(B, nt * cond), z(B, tcd)
+        d_c, d_mid, d_video_tok = z(B, n_c, cond), z(B, n_c, cond), z(B, max(nv, 1) * cond)
+        self.zero_each_step += [d_hid, d_t_emb, d_c, d_mid]
+        half = dim // 2
+        freqs = torch.exp(torch.arange(half, dtype=torch.float32) * -(math.log(10000) / (half - 1))).to(dev)
+        kvN = max([self.kv[k].shape[-1] for k in self.kv_kinds], default=0)
+        dz = z(max(B * self.ss_total, B * n_c * kvN, B * tcd, B * max(nv, 1) * cond, B * nt * cond))
+        self.keep += [sin_emb, hid, time_tok, t_emb, c_tok, mid_tok, video_tok, d_hid, d_time_tok, d_t_emb, d_c, d_mid,
+                      d_video_tok, freqs, dz]
+        fwd_ops, bwd_ops = [], []   # bwd_ops in FORWARD order; replayed in reverse
+
+        def linear(x, lin_w, lin_b, y, M1, M2, N, K, ldx1, ldx2, ldy1, ldy2, *, w_fn, b_fn, dw_map, db_map, dy, dx=None,
+                   pre=L.ACT_NONE, post=L.ACT_NONE, accum=None, keep=None, alt=None, dalt=None):
+            """One dv_linear_small launch + its backward.  w_fn / b_fn: producers of the float32 [N][K] / [N] copies;
+            dw_map / db_map: lists of (parameter, row range) the accumulators scatter to."""
+            wt = self._f32(w_fn)
+            bt = self._f32(b_fn) if b_fn is not None else None
+            fp = L.LinearSmallParams(x=x, w=wt.data_ptr(), bias=bt.data_ptr() if bt is not None else None, y=y, accum=accum,
+                                     keep=keep, alt=alt, M1=M1, M2=M2, N=N, K=K, ldx1=ldx1, ldx2=ldx2, ldy1=ldy1, ldy2=ldy2,
+                                     pre_act=pre, post_act=post)
+            fwd_ops.append(("dv_linear_small", fp))
+            gw = self._galloc(N, K)
+            for prm, r0, r1 in dw_map:
+                self._gmap((prm, lambda r0=r0, r1=r1, gw=gw: self._g(gw)[r0:r1]))
+            gb = None
+            if bt is not None:
+                gb = self._galloc(N)
+                for prm, r0, r1 in db_map:
+                    self._gmap((prm, lambda r0=r0, r1=r1, gb=gb: self._g(gb)[r0:r1]))
+            bwd_ops.append(("dv_linear_small_bwd", L.LinearSmallBwdParams(
+                fwd=fp, dy=dy, dz=dz.data_ptr(), dw=self._gptr(gw), db=self._gptr(gb) if gb is not None else None, dx=dx,
+                dalt=dalt)))
+
+        whole = lambda lin: ([(lin.weight, 0, lin.weight.shape[0])], [(lin.bias, 0, lin.bias.shape[0])])  # noqa: E731
+        fwd_ops.append(("dv_time_embed", L.TimeEmbedParams(time=self.pro_time.data_ptr(), t_dev=None, freqs=freqs.data_ptr(),
+                                                           out=sin_emb.data_ptr(), B=B, dim=dim)))
+        # ---- t_static = where(keep, GELU(to_video_hiddens(video_embed)), null_video_hiddens) [+ to_lowres_noise_cond(level)]
+        t_static = None
+        if u.to_video_hiddens is not None:
+            lin = u.to_video_hiddens[0]
+            t_static = z(B, tcd)
+            g_nvh = self._galloc(1, tcd)
+            self._gmap((u.null_video_hiddens, lambda: self._g(g_nvh)))
+            alt = self._f32(lambda: u.null_video_hiddens.detach().float())
+            dw_map, db_map = whole(lin)
+            linear(self.pro_ve.data_ptr(), lin.weight, lin.bias, t_static.data_ptr(), B, 1, tcd, ved, ved, 0, tcd, 0,
+                   w_fn=lambda lin=lin: lin.weight.detach().float(), b_fn=lambda lin=lin: lin.bias.detach().float(),
+                   dw_map=dw_map, db_map=db_map, dy=d_t_emb.data_ptr(), post=L.ACT_GELU, keep=self.pro_keep.data_ptr(),
+                   alt=alt.data_ptr(), dalt=self._gptr(g_nvh))
+            self.keep.append(t_static)
+        self.uses_lowres_noise = u.to_lowres_noise_cond is not None
+        if self.uses_lowres_noise:
+            # t += to_lowres_noise_cond(level) (:765-768): SinusoidalPosEmb, Linear, GELU, Linear; only when a level is passed
+            # (p_losses sets plan.lowres_noise_on; without it the two launches still run on level 0 and are not added)
+            l1, l2 = u.to_lowres_noise_cond[1], u.to_lowres_noise_cond[3]
+            sin2, hid2, d_hid2, t_comb = z(B, dim), z(B, tcd), z(B, tcd), z(B, tcd)
+            self.zero_each_step.append(d_hid2)
+            self.keep += [sin2, hid2, d_hid2, t_comb]
+            fwd_ops.append(("dv_time_embed", L.TimeEmbedParams(time=self.pro_level.data_ptr(), t_dev=None, freqs=freqs.data_ptr(),
+                                                               out=sin2.data_ptr(), B=B, dim=dim)))
+            dw_map, db_map = whole(l1)
+            linear(sin2.data_ptr(), l1.weight, l1.bias, hid2.data_ptr(), B, 1, tcd, dim, dim, 0, tcd, 0,
+                   w_fn=lambda: l1.weight.detach().float(), b_fn=lambda: l1.bias.detach().float(), dw_map=dw_map,
+                   db_map=db_map, dy=d_hid2.data_ptr(), post=L.ACT_GELU)
+            dw_map, db_map = whole(l2)
+            linear(hid2.data_ptr(), l2.weight, l2.bias, t_comb.data_ptr(), B, 1, tcd, tcd, tcd, 0, tcd, 0,
+                   w_fn=lambda: l2.weight.detach().float(), b_fn=lambda: l2.bias.detach().float(), dw_map=dw_map,
+                   db_map=db_map, dy=d_t_emb.data_ptr(), dx=d_hid2.data_ptr(),
+                   accum=t_static.data_ptr() if t_static is not None else None)
+            t_static = t_comb
+        # ---- hid = GELU(to_time_hiddens(sinusoidal(time)))
+        lin = u.to_time_hiddens[1]
+        dw_map, db_map = whole(lin)
+        linear(sin_emb.data_ptr(), lin.weight, lin.bias, hid.data_ptr(), B, 1, tcd, dim, dim, 0, tcd, 0,
+               w_fn=lambda lin=lin: lin.weight.detach().float(), b_fn=lambda lin=lin: lin.bias.detach().float(),
+               dw_map=dw_map, db_map=db_map, dy=d_hid.data_ptr(), post=L.ACT_GELU)
+        # ---- time tokens, t = to_time_cond(hid) + t_static
+        lin = u.to_time_tokens[0]
+        dw_map, db_map = whole(lin)
+        linear(hid.data_ptr(), lin.weight, lin.bias, time_tok.data_ptr(), B, 1, nt * cond, tcd, tcd, 0, nt * cond, 0,
+               w_fn=lambda lin=lin: lin.weight.detach().float(), b_fn=lambda lin=lin: lin.bias.detach().float(),
+               dw_map=dw_map, db_map=db_map, dy=d_time_tok.data_ptr(), dx=d_hid.data_ptr())
+        lin = u.to_time_cond[0]
+        dw_map, db_map = whole(lin)
+        linear(hid.data_ptr(), lin.weight, lin.bias, t_emb.data_ptr(), B, 1, tcd, tcd, tcd, 0, tcd, 0,
+               w_fn=lambda lin=lin: lin.weight.detach().float(), b_fn=lambda lin=lin: lin.bias.detach().float(),
+               dw_map=dw_map, db_map=db_map, dy=d_t_emb.data_ptr(), dx=d_hid.data_ptr(),
+               accum=t_static.data_ptr() if t_static is not None else None)
+        # ---- every ResnetBlock3D.time_mlp as one GEMV: ss = Linear(SiLU(t))
+        ss_w, ss_b, r0 = [], [], 0
+        for m, _ in self.blocks:
+            lin = m.time_mlp[1]
+            ss_w.append((lin.weight, r0, r0 + lin.weight.shape[0]))
+            ss_b.append((lin.bias, r0, r0 + lin.weight.shape[0]))
+            r0 += lin.weight.shape[0]
+        assert r0 == self.ss_total
+        linear(t_emb.data_ptr(), None, None, self.ss.data_ptr(), B, 1, self.ss_total, tcd, tcd, 0, self.ss_total, 0,
+               w_fn=lambda: torch.cat([m.time_mlp[1].weight.detach().float() for m, _ in self.blocks], dim=0),
+               b_fn=lambda: torch.cat([m.time_mlp[1].bias.detach().float() for m, _ in self.blocks], dim=0),
+               dw_map=ss_w, db_map=ss_b, dy=self.dss.data_ptr(), dx=d_t_emb.data_ptr(), pre=L.ACT_SILU)
+        # ---- video tokens, where(keep, ., null_video_embed), cat with the time tokens, norm_cond / norm_mid_cond
+        g_nve = None
+        if nv:
+            lin = u.video_to_tokens[0]
+            dw_map, db_map = whole(lin)
+            linear(self.pro_ve.data_ptr(), lin.weight, lin.bias, video_tok.data_ptr(), B, 1, nv * cond, ved, ved, 0, nv * cond, 0,
+                   w_fn=lambda lin=lin: lin.weight.detach().float(), b_fn=lambda lin=lin: lin.bias.detach().float(),
+                   dw_map=dw_map, db_map=db_map, dy=d_video_tok.data_ptr())
+            g_nve = self._galloc(nv, cond)
+            self._gmap((u.null_video_embed, lambda: self._g(g_nve).reshape(u.null_video_embed.shape)))
+        lnp = {}
+        for name, mod in (("ln", u.norm_cond), ("ln_mid", u.norm_mid_cond)):
+            lnp[name + "_w"] = self._f32(lambda mod=mod: mod.weight.detach().float())
+            lnp[name + "_b"] = self._f32(lambda mod=mod: mod.bias.detach().float())
+        g_ln = {k: self._galloc(cond) for k in lnp}
+        self._gmap((u.norm_cond.weight, lambda: self._g(g_ln["ln_w"])))
+        self._gmap((u.norm_cond.bias, lambda: self._g(g_ln["ln_b"])))
+        self._gmap((u.norm_mid_cond.weight, lambda: self._g(g_ln["ln_mid_w"])))
+        self._gmap((u.norm_mid_cond.bias, lambda: self._g(g_ln["ln_mid_b"])))
+        nve = self._f32(lambda: u.null_video_embed.detach().float().reshape(-1)) if nv else None
+        tokp = L.CondTokensParams(
+            time_tokens=time_tok.data_ptr(), video_tokens=video_tok.data_ptr() if nv else None,
+            null_video=nve.data_ptr() if nv else None, text_tokens=None, text_enc=None, null_text=None,
+            keep_video=self.pro_keep.data_ptr(), keep_text=self.pro_keep.data_ptr(), c=c_tok.data_ptr(),
+            mid_c=mid_tok.data_ptr(), B=B, D=cond, n_time=nt, n_video=nv, n_text_in=0, max_text=0, text_dim=1,
+            tok_begin=0, tok_end=n_c, eps=float(u.norm_cond.eps), **{k: v.data_ptr() for k, v in lnp.items()})
+        fwd_ops.append(("dv_cond_tokens", tokp))
+        bwd_ops.append(("dv_cond_tokens_bwd", L.CondTokensBwdParams(
+            fwd=tokp, dc=d_c.data_ptr() if "c" in self.kv else None, dmid=d_mid.data_ptr() if "mid" in self.kv else None,
+            dtime_tokens=d_time_tok.data_ptr(), dvideo_tokens=d_video_tok.data_ptr() if nv else None,
+            dnull_video=self._gptr(g_nve) if nv else None, dln_w=self._gptr(g_ln["ln_w"]), dln_b=self._gptr(g_ln["ln_b"]),
+            dln_mid_w=self._gptr(g_ln["ln_mid_w"]), dln_mid_b=self._gptr(g_ln["ln_mid_b"]))))
+        # ---- every CrossAttention.to_kv of a context kind as one GEMM over the tokens
+        for kind, toks, dtoks in (("c", c_tok, d_c), ("mid", mid_tok, d_mid)):
+            if kind not in self.kv:
+                continue
+            mods = self.kv_mods[kind]
+            N = self.kv[kind].shape[-1]
+            per = N // len(mods)
+            kv_map = [(m.cross_attn.to_kv.weight, i * per, (i + 1) * per) for i, m in enumerate(mods)]
+            linear(toks.data_ptr(), None, None, self.kv[kind].data_ptr(), B, n_c, N, cond, n_c * cond, cond, n_c * N, N,
+                   w_fn=lambda mods=mods: torch.cat([m.cross_attn.to_kv.weight.detach().float() for m in mods], dim=0),
+                   b_fn=None, dw_map=kv_map, db_map=[], dy=self.dkv[kind].data_ptr(), dx=dtoks.data_ptr())
+        self.fwd += fwd_ops
+
+        def backward():
+            self.bwd += list(reversed(bwd_ops))
+
+        self.tape.append(backward)
+
+    # -------------------------------------------------------------- conditioning prologue (torch autograd; DV_TRAIN_NATIVE_PROLOGUE=0)
     def prologue(self, time, video_embed, keep_v, lowres_noise_level=None):
         u, B = self.u, self.B
         cond, nt = u.cond_dim, u.num_time_tokens
@@ -816,7 +993,7 @@ class _TrainPlan:
             torch.cuda.synchronize(dev)
             good = all(torch.equal(want[k], self._arena[k][0][: self._arena[k][1]]) for k in ("w", "f"))
             if good and ok:
-                g_buf[:g_used].normal_()
+                g_buf[:g_used].normal_(generator=torch.Generator(device=dev).manual_seed(1))   # not the global stream: RNG parity
                 ref = [fn().detach().float().reshape(-1).clone() for _, fn in self.grad_map]
                 L.call("dv_gather_scale", fz["grad_op"], torch.cuda.current_stream(dev).cuda_stream)
                 torch.cuda.synchronize(dev)
@@ -953,9 +1130,10 @@ class _PlanFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, plan, noise, ss, *kv):
-        plan.ss.copy_(ss)
-        for kind, t in zip(plan.kv_kinds, kv):
-            plan.kv[kind].copy_(t)
+        if not plan.native_prologue:
+            plan.ss.copy_(ss)
+            for kind, t in zip(plan.kv_kinds, kv):
+                plan.kv[kind].copy_(t)
         plan.run_forward()
         plan.generation += 1    # the plan owns ONE set of activation buffers: a backward must follow its own forward
         ctx.generation = plan.generation
@@ -983,6 +1161,8 @@ class _PlanFunction(torch.autograd.Function):
                                               loss=scratch.data_ptr(), n=noise.numel(), grad_scale=float(grad_out),
                                               **ctx.loss_kw), stream)
         plan.run_backward()
+        if plan.native_prologue:    # `ss` was the plan's anchor: every gradient has gone to .grad through the plan
+            return None, None, None
         return (None, None, plan.dss.clone(), *[plan.dkv[k].clone() for k in plan.kv_kinds])
 
 
@@ -1037,6 +1217,20 @@ def p_losses(decoder, unet: Unet3D, x_start, times, *, video_embed, noise_schedu
     # loss_fn (l1 / l2 / huber) and p2 reweighting (:1997-2003) are applied inside dv_mse_loss
     weight = noise_scheduler.p2_loss_weight[times].float().contiguous() if noise_scheduler.has_p2_loss_reweighting else None
     plan.loss_opts = (L.LOSS_KINDS[noise_scheduler.loss_type], weight)
+    if plan.native_prologue:
+        plan.pro_time.copy_(times)
+        plan.pro_ve.copy_(video_embed.float())
+        plan.pro_keep.copy_(keep_v.to(torch.uint8))
+        if lowres_noise_level is not None:
+            assert unet.to_lowres_noise_cond is not None, \
+                "lowres_noise_cond must be set to True on instantiation of the unet in order to conditiong on lowres noise"
+            plan.pro_level.copy_(lowres_noise_level)
+        elif plan.uses_lowres_noise:
+            raise NotImplementedError("training plan: a unet built with lowres_noise_cond=True is trained with a noise level "
+                                      "(use_noise_for_lowres_cond); DV_TRAIN_NATIVE_PROLOGUE=0 takes the call without one")
+        if getattr(plan, "anchor", None) is None:
+            plan.anchor = torch.zeros(1, device=dev, requires_grad=True)
+        return _PlanFunction.apply(plan, target, plan.anchor)
     outs = plan.prologue(times, video_embed.float(), keep_v, lowres_noise_level)
     return _PlanFunction.apply(plan, target, outs["ss"], *[outs[k] for k in plan.kv_kinds])
 

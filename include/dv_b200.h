@@ -506,6 +506,37 @@ typedef struct {
 } dv_cond_tokens_params;
 int dv_cond_tokens(const dv_cond_tokens_params* p, dv_stream_t stream);
 
+/* Backward of the conditioning prologue in the training step (autograd of :348-372, :386, :153-155, to_kv and the token
+ * LayerNorms inside p_losses :1908-2006).
+ * dv_linear_small_bwd: `fwd` is the forward call (x, w, bias, keep, dimensions, strides, activations; y / accum / alt are not
+ *   read).  dz = dy * post'(z) with z = w . pre(x) + bias recomputed; rows whose keep[m1] == 0 were replaced by `alt` in the
+ *   forward, so their dy goes to dalt[m2][n] instead.  dw[n][k] += sum_m dz[m][n] pre(x)[m][k];  db[n] += sum_m dz[m][n];
+ *   dx[m][k] += pre'(x[m][k]) sum_n dz[m][n] w[n][k]  (rows addressed like x).  The gradient of `accum` is dy itself.
+ * dv_cond_tokens_bwd: gradients of both LayerNorm outputs back to the time tokens, the video tokens (kept samples) or the
+ *   null video embedding (dropped samples), and to the LayerNorm parameters; no text tokens (training asserts them away,
+ *   :2252). */
+typedef struct {
+  dv_linear_small_params fwd;
+  const float* dy;   /* row (m1,m2) at dy + m1*ldy1 + m2*ldy2 (the forward's y strides) */
+  float* dz;         /* scratch [M1*M2][N] */
+  float* dw;         /* [N][K] += or NULL */
+  float* db;         /* [N] += or NULL */
+  float* dx;         /* rows like x, += ; NULL: not wanted */
+  float* dalt;       /* [M2][N] += ; required when fwd.keep != NULL */
+} dv_linear_small_bwd_params;
+int dv_linear_small_bwd(const dv_linear_small_bwd_params* p, dv_stream_t stream);
+
+typedef struct {
+  dv_cond_tokens_params fwd;   /* the forward call (n_text_in = max_text = 0); c / mid_c are not read */
+  const float* dc;             /* [B][n_time+n_video][D] or NULL */
+  const float* dmid;           /* [B][n_time+n_video][D] or NULL */
+  float* dtime_tokens;         /* [B][n_time][D]  = */
+  float* dvideo_tokens;        /* [B][n_video][D] = (zero rows for dropped samples) or NULL */
+  float* dnull_video;          /* [n_video][D] += or NULL */
+  float* dln_w; float* dln_b; float* dln_mid_w; float* dln_mid_b;   /* [D] += */
+} dv_cond_tokens_bwd_params;
+int dv_cond_tokens_bwd(const dv_cond_tokens_bwd_params* p, dv_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Head: to_out 1x1x1 convolution from channels-last activations to the reference's (B,C,T,H,W)
  * float32 layout (:637-642, :952).  w: float32 [Cout][C].

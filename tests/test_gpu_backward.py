@@ -410,3 +410,77 @@ def test_q_sample_mse_and_adamw():
                                           bias_correction1=1 - 0.9 ** step, bias_correction2=1 - 0.99 ** step,
                                           max_grad_norm=0.5), stream())
         assert rel_err(w, wt.detach()) < 1e-5
+
+
+# ------------------------------------------------------------------ conditioning prologue (dv_linear_small / dv_cond_tokens)
+@pytest.mark.parametrize("M1,M2,N,K,pre,post,use_keep,accum_dx", [
+    (4, 1, 96, 64, L.ACT_NONE, L.ACT_GELU, False, False),     # to_time_hiddens
+    (5, 1, 300, 128, L.ACT_SILU, L.ACT_NONE, False, True),    # the concatenated time_mlp GEMV (N not a multiple of 128)
+    (3, 6, 640, 64, L.ACT_NONE, L.ACT_NONE, False, True),     # to_kv over [B][tokens] (token rows strided inside a sample)
+    (6, 1, 128, 512, L.ACT_NONE, L.ACT_GELU, True, False),    # to_video_hiddens with the keep mask / null embedding
+])
+def test_linear_small_backward_matches_autograd(M1, M2, N, K, pre, post, use_keep, accum_dx):
+    act = {L.ACT_NONE: (lambda t: t), L.ACT_SILU: F.silu, L.ACT_GELU: F.gelu}
+    x = rnd(M1, M2, K, seed=1).requires_grad_(True)
+    w = rnd(N, K, seed=2, scale=K ** -0.5).requires_grad_(True)
+    b = rnd(N, seed=3).requires_grad_(True)
+    alt = rnd(M2, N, seed=4).requires_grad_(True)
+    keep = torch.tensor([1, 0, 1, 1, 0, 1][:M1], dtype=torch.uint8, device=dev()) if use_keep else None
+    dy = rnd(M1, M2, N, seed=5)
+    y = act[post](act[pre](x) @ w.t() + b)
+    if use_keep:
+        y = torch.where(keep.bool()[:, None, None], y, alt[None])
+    y.backward(dy)
+    fp = L.LinearSmallParams(x=ptr(x), w=ptr(w), bias=ptr(b), y=None, accum=None, keep=ptr(keep) if use_keep else None,
+                             alt=ptr(alt) if use_keep else None, M1=M1, M2=M2, N=N, K=K, ldx1=M2 * K, ldx2=K, ldy1=M2 * N,
+                             ldy2=N, pre_act=pre, post_act=post)
+    dz = torch.empty(M1 * M2 * N, device=dev())
+    dw, db, dalt = torch.zeros(N, K, device=dev()), torch.zeros(N, device=dev()), torch.zeros(M2, N, device=dev())
+    dx0 = rnd(M1, M2, K, seed=6) if accum_dx else torch.zeros(M1, M2, K, device=dev())
+    dx = dx0.clone()
+    L.call("dv_linear_small_bwd", L.LinearSmallBwdParams(fwd=fp, dy=ptr(dy), dz=ptr(dz), dw=ptr(dw), db=ptr(db), dx=ptr(dx),
+                                                         dalt=ptr(dalt) if use_keep else None), stream())
+    assert rel_err(dw, w.grad) < 2e-5
+    assert rel_err(db, b.grad) < 2e-5
+    assert rel_err(dx - dx0, x.grad) < 2e-5
+    if use_keep:
+        assert rel_err(dalt, alt.grad) < 2e-5
+    # += semantics of the parameter gradients
+    L.call("dv_linear_small_bwd", L.LinearSmallBwdParams(fwd=fp, dy=ptr(dy), dz=ptr(dz), dw=ptr(dw), db=ptr(db), dx=None,
+                                                         dalt=ptr(dalt) if use_keep else None), stream())
+    assert rel_err(dw, 2 * w.grad) < 2e-5 and rel_err(db, 2 * b.grad) < 2e-5
+
+
+@pytest.mark.parametrize("B,D,nt,nv,both", [(4, 64, 2, 4, True), (3, 128, 2, 4, False), (2, 32, 3, 0, True)])
+def test_cond_tokens_backward_matches_autograd(B, D, nt, nv, both):
+    n_c = nt + nv
+    tt = rnd(B, nt, D, seed=1).requires_grad_(True)
+    vt = rnd(B, max(nv, 1), D, seed=2).requires_grad_(True)
+    nullv = rnd(max(nv, 1), D, seed=3).requires_grad_(True)
+    keep = torch.tensor([1, 0, 1, 0][:B], dtype=torch.uint8, device=dev())
+    ln = [rnd(D, seed=4 + i).requires_grad_(True) for i in range(4)]
+    raw = tt if nv == 0 else torch.cat((tt, torch.where(keep.bool()[:, None, None], vt, nullv[None])), dim=1)
+    c = F.layer_norm(raw, (D,), ln[0], ln[1], 1e-5)
+    mid = F.layer_norm(raw, (D,), ln[2], ln[3], 1e-5)
+    dc, dmid = rnd(B, n_c, D, seed=9), rnd(B, n_c, D, seed=10)
+    ((c * dc).sum() + ((mid * dmid).sum() if both else 0.0)).backward()
+    c_out, mid_out = torch.empty(B, n_c, D, device=dev()), torch.empty(B, n_c, D, device=dev())
+    fp = L.CondTokensParams(time_tokens=ptr(tt), video_tokens=ptr(vt) if nv else None, null_video=ptr(nullv) if nv else None,
+                            text_tokens=None, text_enc=None, null_text=None, ln_w=ptr(ln[0]), ln_b=ptr(ln[1]),
+                            ln_mid_w=ptr(ln[2]), ln_mid_b=ptr(ln[3]), keep_video=ptr(keep), keep_text=ptr(keep),
+                            c=ptr(c_out), mid_c=ptr(mid_out), B=B, D=D, n_time=nt, n_video=nv, n_text_in=0, max_text=0,
+                            text_dim=1, tok_begin=0, tok_end=n_c, eps=1e-5)
+    L.call("dv_cond_tokens", fp, stream())
+    assert rel_err(c_out, c) < 1e-5 and rel_err(mid_out, mid) < 1e-5
+    dtt, dvt, dnull = torch.empty_like(tt), torch.empty_like(vt), torch.zeros_like(nullv)
+    dln = [torch.zeros(D, device=dev()) for _ in range(4)]
+    L.call("dv_cond_tokens_bwd", L.CondTokensBwdParams(
+        fwd=fp, dc=ptr(dc), dmid=ptr(dmid) if both else None, dtime_tokens=ptr(dtt), dvideo_tokens=ptr(dvt) if nv else None,
+        dnull_video=ptr(dnull) if nv else None, dln_w=ptr(dln[0]), dln_b=ptr(dln[1]), dln_mid_w=ptr(dln[2]),
+        dln_mid_b=ptr(dln[3])), stream())
+    assert rel_err(dtt, tt.grad) < 2e-5
+    if nv:
+        assert rel_err(dvt, vt.grad) < 2e-5 and rel_err(dnull, nullv.grad) < 2e-5
+    assert rel_err(dln[0], ln[0].grad) < 2e-5 and rel_err(dln[1], ln[1].grad) < 2e-5
+    if both:
+        assert rel_err(dln[2], ln[2].grad) < 2e-5 and rel_err(dln[3], ln[3].grad) < 2e-5
