@@ -145,6 +145,11 @@ class ToOutParams(C.Structure):
                 ("dtype", i32), ("extra", vp), ("Cextra", i32), ("k", i32), ("H", i32), ("W", i32)]
 
 
+class L2normHeadsParams(C.Structure):
+    _fields_ = [("x", vp), ("M1", i32), ("M2", i32), ("ld1", i64), ("ld2", i64), ("col_off", i32), ("n_groups", i32),
+                ("group_stride", i32), ("n_seg", i32), ("seg", i32), ("dtype", i32)]
+
+
 class UpsampleNearest2xParams(C.Structure):
     _fields_ = [("in_", vp), ("out", vp), ("n_img", i32), ("H", i32), ("W", i32), ("row_bytes", i32)]
 
@@ -258,7 +263,7 @@ ENTRY_POINTS = {
     "dv_attn_mqa": AttnMqaParams, "dv_attn_temporal": AttnTemporalParams,
     "dv_time_embed": TimeEmbedParams, "dv_linear_small": LinearSmallParams,
     "dv_cond_tokens": CondTokensParams, "dv_linear_small_bwd": LinearSmallBwdParams,
-    "dv_cond_tokens_bwd": CondTokensBwdParams, "dv_to_out": ToOutParams, "dv_upsample_nearest2x": UpsampleNearest2xParams, "dv_im2col_init": Im2colParams,
+    "dv_cond_tokens_bwd": CondTokensBwdParams, "dv_to_out": ToOutParams, "dv_upsample_nearest2x": UpsampleNearest2xParams, "dv_l2norm_heads": L2normHeadsParams, "dv_im2col_init": Im2colParams,
     "dv_init_conv": InitConvParams, "dv_resize_nearest": ResizeNearestParams,
     "dv_patchify": PatchifyParams, "dv_mha_small": MhaSmallParams,
     # training step (a16)

@@ -224,7 +224,50 @@ static int launch_ln(const dv_layernorm_params& p, cudaStream_t s) {
   return DV_OK;
 }
 
+// F.normalize(dim=-1) of head slices, in place: one warp per (row, slice), slices of <= 128 elements
+template <typename T>
+__global__ void __launch_bounds__(128) l2norm_heads_kernel(dv_l2norm_heads_params p) {
+  const int lane = threadIdx.x & 31;
+  const int per_row = p.n_groups * p.n_seg;
+  const int64_t w = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (w >= (int64_t)p.M1 * p.M2 * per_row) return;
+  const int64_t row = w / per_row;
+  const int sl = (int)(w - row * per_row);
+  const int g = sl / p.n_seg, sg = sl - g * p.n_seg;
+  T* x = reinterpret_cast<T*>(p.x) + (row / p.M2) * p.ld1 + (row % p.M2) * p.ld2 + p.col_off + (int64_t)g * p.group_stride +
+         (int64_t)sg * p.seg;
+  float v[4];
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int d = lane + 32 * i;
+    v[i] = d < p.seg ? to_f<T>(x[d]) : 0.f;
+    ss = fmaf(v[i], v[i], ss);
+  }
+  const float inv = 1.0f / fmaxf(sqrtf(warp_sum(ss)), 1e-12f);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int d = lane + 32 * i;
+    if (d < p.seg) x[d] = from_f<T>(v[i] * inv);
+  }
+}
+
 }  // namespace dv
+
+extern "C" int dv_l2norm_heads(const dv_l2norm_heads_params* p, dv_stream_t stream) {
+  using namespace dv;
+  DV_REQUIRE(p && p->x, DV_EINVAL, "dv_l2norm_heads: null pointer");
+  DV_REQUIRE(p->M1 > 0 && p->M2 > 0 && p->n_groups > 0 && p->n_seg > 0 && p->seg > 0 && p->seg <= 128, DV_EINVAL,
+             "dv_l2norm_heads: bad dimensions (slices of at most 128 elements)");
+  DV_REQUIRE(p->dtype == DV_F32 || p->dtype == DV_BF16, DV_EINVAL, "dv_l2norm_heads: bad dtype");
+  const int64_t warps = (int64_t)p->M1 * p->M2 * p->n_groups * p->n_seg;
+  const int64_t blocks = (warps + 3) / 4;
+  DV_REQUIRE(blocks < (1ll << 31), DV_EUNSUPPORTED, "dv_l2norm_heads: too many slices");
+  if (p->dtype == DV_F32) l2norm_heads_kernel<float><<<(unsigned)blocks, 128, 0, as_stream(stream)>>>(*p);
+  else l2norm_heads_kernel<__nv_bfloat16><<<(unsigned)blocks, 128, 0, as_stream(stream)>>>(*p);
+  DV_CHECK_LAUNCH("dv_l2norm_heads");
+  return DV_OK;
+}
 
 extern "C" int dv_gn_stats(const dv_gn_stats_params* p, dv_stream_t stream) {
   using namespace dv;

@@ -15,6 +15,7 @@ import os
 from functools import partial
 
 import torch
+import torch.nn.functional as F
 from torch import nn
 
 from . import _lib as L
@@ -48,8 +49,11 @@ class _CrossAttn(nn.Module):
     """Parameters of dalle2_pytorch.CrossAttention(dim, context_dim, heads=8, dim_head=64) (:160-162)."""
     heads, dim_head = 8, 64
 
-    def __init__(self, dim, context_dim):
+    def __init__(self, dim, context_dim, cosine_sim=False):
         super().__init__()
+        # cosine_sim (:161): q, k are l2-normalised per head and the logits scaled by cosine_sim_scale = 16
+        self.cosine_sim = cosine_sim
+        self.scale = 16.0 if cosine_sim else self.dim_head ** -0.5
         inner = self.heads * self.dim_head
         self.norm = _Gain(dim)
         self.null_kv = nn.Parameter(torch.randn(2, self.dim_head))
@@ -61,9 +65,13 @@ class _CrossAttn(nn.Module):
 class _SelfAttn(nn.Module):
     """Parameters of dalle2_pytorch.Attention(dim, heads, dim_head) — one shared k/v head (:424-432)."""
 
-    def __init__(self, dim, heads, dim_head):
+    def __init__(self, dim, heads, dim_head, cosine_sim=False):
         super().__init__()
         self.heads, self.dim_head = heads, dim_head
+        # logits = scale^2 q.k = q.k / dim_head (q * scale, then q, k * sqrt(scale); SURVEY.md A.3), or with cosine_sim
+        # (:425) 16 * l2norm(q).l2norm(k)
+        self.cosine_sim = cosine_sim
+        self.logit_scale = 16.0 if cosine_sim else 1.0 / dim_head
         inner = heads * dim_head
         self.norm = _Gain(dim)
         self.null_kv = nn.Parameter(torch.randn(2, dim_head))
@@ -122,11 +130,12 @@ class _Block(nn.Module):
 
 
 class _ResBlock(nn.Module):
-    def __init__(self, dim, dim_out, *, cond_dim=None, time_cond_dim=None, groups=8, temporal_conv=False):
+    def __init__(self, dim, dim_out, *, cond_dim=None, time_cond_dim=None, groups=8, temporal_conv=False,
+                 cosine_sim_cross_attn=False):
         super().__init__()
         self.dim, self.dim_out, self.groups = dim, dim_out, groups
         self.time_mlp = nn.Sequential(nn.SiLU(), nn.Linear(time_cond_dim, dim_out * 2)) if time_cond_dim else None
-        self.cross_attn = _CrossAttn(dim_out, cond_dim) if cond_dim else None
+        self.cross_attn = _CrossAttn(dim_out, cond_dim, cosine_sim_cross_attn) if cond_dim else None
         self.block1 = _Block(dim, dim_out, groups, temporal_conv)
         self.block2 = _Block(dim_out, dim_out, groups, temporal_conv)
         self.res_conv = nn.Conv3d(dim, dim_out, 1) if dim != dim_out else nn.Identity()
@@ -180,8 +189,7 @@ class Unet3D(nn.Module):
         super().__init__()
         self._locals = {k: v for k, v in locals().items() if k not in ("self", "__class__")}
 
-        unsupported = dict(sparse_attn=sparse_attn, cosine_sim_cross_attn=cosine_sim_cross_attn,
-                           cosine_sim_self_attn=cosine_sim_self_attn, cross_embed_downsample=cross_embed_downsample,
+        unsupported = dict(sparse_attn=sparse_attn, cross_embed_downsample=cross_embed_downsample,
                            combine_upsample_fmaps=combine_upsample_fmaps,
                            resnet_weight_standardization=resnet_weight_standardization)
         bad = [k for k, v in unsupported.items() if v]
@@ -193,6 +201,10 @@ class Unet3D(nn.Module):
                 "memory_efficient and the temporal_attn extension are not combined"
         self.memory_efficient, self.pixel_shuffle_upsample = memory_efficient, pixel_shuffle_upsample
         self.final_conv_ksize = final_conv_ksize
+        self.cosine_sim_cross_attn, self.cosine_sim_self_attn = cosine_sim_cross_attn, cosine_sim_self_attn
+        if cosine_sim_self_attn:
+            assert not temporal_attn or not any(_cast_tuple(temporal_attn, len(dim_mults))), \
+                "cosine_sim_self_attn and the temporal_attn extension are not combined"
 
         self.lowres_cond, self.self_cond = lowres_cond, self_cond
         self.lowres_noise_cond = lowres_noise_cond
@@ -255,8 +267,9 @@ class Unet3D(nn.Module):
         resnet_groups = _cast_tuple(resnet_groups, n_stages)
         num_resnet_blocks = _cast_tuple(num_resnet_blocks, n_stages)
         self._stage_self_attn, self._stage_groups, self._stage_blocks = self_attn, resnet_groups, num_resnet_blocks
-        make_attn = lambda d: _Fn(_Fn(_SelfAttn(d, attn_heads, attn_dim_head)))  # noqa: E731
-        res = partial(_ResBlock, time_cond_dim=time_cond_dim, temporal_conv=temporal_conv)
+        make_attn = lambda d: _Fn(_Fn(_SelfAttn(d, attn_heads, attn_dim_head, cosine_sim_self_attn)))  # noqa: E731
+        res = partial(_ResBlock, time_cond_dim=time_cond_dim, temporal_conv=temporal_conv,
+                      cosine_sim_cross_attn=cosine_sim_cross_attn)
         assert attn_mode in ("joint", "factorised"), "attn_mode must be 'joint' or 'factorised'"
         self.attn_mode, self.temporal_conv = attn_mode, temporal_conv
         temporal_attn = _cast_tuple(temporal_attn, n_stages)
@@ -389,10 +402,11 @@ class Unet3D(nn.Module):
     def train_plan(self, batch, frames, height, width, device):
         """Forward + backward launch plan of the training step (dalle2_video_b200/train.py)."""
         from .train import _TrainPlan
-        if self.memory_efficient or not self.pixel_shuffle_upsample or self.final_conv_ksize != 1:
+        if (self.memory_efficient or not self.pixel_shuffle_upsample or self.final_conv_ksize != 1
+                or self.cosine_sim_cross_attn or self.cosine_sim_self_attn):
             raise NotImplementedError("Unet3D(b200): the training plan is built for the default layer plan only "
-                                      "(memory_efficient / pixel_shuffle_upsample=False / final_conv_ksize != 1 sample, "
-                                      "but do not train, on the native path)")
+                                      "(memory_efficient / pixel_shuffle_upsample=False / final_conv_ksize != 1 / cosine_sim_* "
+                                      "sample, but do not train, on the native path)")
         # bf16 unless float32 is asked for explicitly (unet.compute_dtype = torch.float32: the parity mode)
         dtype = torch.float32 if self.compute_dtype == torch.float32 else torch.bfloat16
         key = ("train", batch, frames, height, width, str(device), dtype)
@@ -707,6 +721,11 @@ class _Engine:
                 self._linear(toks.data_ptr() + tok0 * cond * 4, kv_w[kind], None,
                              self.kv[kind].data_ptr() + tok0 * N * 4, B, hi - tok0, N, cond, n_tok * cond, cond,
                              n_tok * N, N, static=static)
+                if u.cosine_sim_cross_attn:   # k = l2norm(k) per head (:161): every layer's K slice of these token rows
+                    self._op("dv_l2norm_heads", L.L2normHeadsParams(
+                        x=self.kv[kind].data_ptr() + tok0 * N * 4, M1=B, M2=hi - tok0, ld1=n_tok * N, ld2=N, col_off=0,
+                        n_groups=N // inner2, group_stride=inner2, n_seg=_CrossAttn.heads, seg=_CrossAttn.dim_head,
+                        dtype=L.DV_F32), static)
 
         kv_ops(nt, n_mid, True)
 
@@ -1083,8 +1102,11 @@ class _Engine:
         kind, idx = self.kv_idx[id(m)]
         kv = self.kv[kind]
         n_ctx = kv.shape[1]
+        null_kv = ca.null_kv
+        if ca.cosine_sim:   # the null key is part of k when it is l2-normalised; the fold needs logits linear in LayerNorm(x)
+            null_kv = torch.stack((F.normalize(ca.null_kv.detach()[0], dim=-1), ca.null_kv.detach()[1]))
         if (self.dtype == torch.bfloat16 and self.u.fuse_short_context_attention and C in (64, 128, 256, 512)
-                and P % 128 == 0 and heads == 8 and dh == 64 and (n_ctx + 1) in (3, 7)):
+                and P % 128 == 0 and heads == 8 and dh == 64 and (n_ctx + 1) in (3, 7) and not ca.cosine_sim):
             # short context (time + video tokens): the whole block is one tcgen05 kernel on per-sample folded
             # matrices (include/dv_b200.h, "K5 fused"); the matrices are rebuilt every step (time tokens change)
             mq = self._zeros(self.B, 64, C, dtype=torch.bfloat16)
@@ -1107,9 +1129,12 @@ class _Engine:
                                                    eps=1e-5, dtype=self.code))
         q = self._new_act(rows, inner)
         self._conv([(xn.ptr, C)], self._w(ca.to_q.weight), None, q.ptr, inner, rows, 1, 1, frames=P)
-        xp = L.XattnParams(q=q.ptr, out=q.ptr, kv=kv.data_ptr(), null_kv=self._f32(ca.null_kv).data_ptr(), B=self.B,
+        if ca.cosine_sim:
+            self._op("dv_l2norm_heads", L.L2normHeadsParams(x=q.ptr, M1=rows, M2=1, ld1=inner, ld2=0, col_off=0, n_groups=1,
+                                                            group_stride=0, n_seg=heads, seg=dh, dtype=self.code))
+        xp = L.XattnParams(q=q.ptr, out=q.ptr, kv=kv.data_ptr(), null_kv=self._f32(null_kv).data_ptr(), B=self.B,
                            P=P, heads=heads, dh=dh, n_ctx=n_ctx, kv_ld=kv.shape[2], k_off=idx * 2 * inner,
-                           v_off=idx * 2 * inner + inner, scale=float(dh ** -0.5), dtype=self.code, workspace=None,
+                           v_off=idx * 2 * inner + inner, scale=float(ca.scale), dtype=self.code, workspace=None,
                            workspace_bytes=0)
         ws = None
         if n_ctx + 1 > 16:
@@ -1155,7 +1180,15 @@ class _Engine:
         kvb = self._new_act(rows, 2 * dh)
         self._conv([(xn.ptr, C)], self._w(at.to_q.weight), None, q.ptr, inner, rows, 1, 1, frames=P)
         self._conv([(xn.ptr, C)], self._w(at.to_kv.weight), None, kvb.ptr, 2 * dh, rows, 1, 1, frames=P)
-        # q*scale, then q,k *= sqrt(scale): logits = q.k * scale^2 = q.k / dim_head
+        # q*scale, then q,k *= sqrt(scale): logits = q.k * scale^2 = q.k / dim_head; cosine_sim_self_attn:
+        # 16 * l2norm(q).l2norm(k), the null key normalised with the keys it is concatenated to
+        null_kv = at.null_kv
+        if at.cosine_sim:
+            null_kv = torch.stack((F.normalize(at.null_kv.detach()[0], dim=-1), at.null_kv.detach()[1]))
+            self._op("dv_l2norm_heads", L.L2normHeadsParams(x=q.ptr, M1=rows, M2=1, ld1=inner, ld2=0, col_off=0, n_groups=1,
+                                                            group_stride=0, n_seg=heads, seg=dh, dtype=self.code))
+            self._op("dv_l2norm_heads", L.L2normHeadsParams(x=kvb.ptr, M1=rows, M2=1, ld1=2 * dh, ld2=0, col_off=0,
+                                                            n_groups=1, group_stride=0, n_seg=1, seg=dh, dtype=self.code))
         if mode == "temporal":
             bias = self._f32(at.rel_pos_bias.table(self.T, self.T + 1))
             self._op("dv_attn_temporal", L.AttnTemporalParams(
@@ -1163,9 +1196,9 @@ class _Engine:
                 T=self.T, HW=h * w, heads=heads, dh=dh, scale=float(1.0 / dh), dtype=self.code, impl=0))
         else:
             S, n = (B, P) if mode == "joint" else (B * self.T, h * w)
-            ap = L.AttnMqaParams(q=q.ptr, kv=kvb.ptr, out=q.ptr, null_kv=self._f32(at.null_kv).data_ptr(), bias=None,
+            ap = L.AttnMqaParams(q=q.ptr, kv=kvb.ptr, out=q.ptr, null_kv=self._f32(null_kv).data_ptr(), bias=None,
                                  workspace=None, workspace_bytes=0, S=S, n=n, heads=heads, dh=dh,
-                                 scale=float(1.0 / dh), dtype=self.code, impl=0)
+                                 scale=float(at.logit_scale), dtype=self.code, impl=0)
             ws_bytes = L.lib().dv_attn_mqa_workspace_bytes(ap)
             ws = None
             if ws_bytes > 0:

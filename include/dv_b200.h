@@ -506,6 +506,21 @@ typedef struct {
 } dv_cond_tokens_params;
 int dv_cond_tokens(const dv_cond_tokens_params* p, dv_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * cosine_sim_self_attn / cosine_sim_cross_attn (:268-269, :161, :425; dalle2_pytorch Attention / CrossAttention with
+ * cosine_sim=True): `q, k = map(l2norm, (q, k))` = F.normalize(dim=-1, eps 1e-12) of every head's dim_head slice, after
+ * which the attention cores run with scale = cosine_sim_scale (16).  In place on a projection buffer: row (m1, m2) at
+ * x + m1*ld1 + m2*ld2 elements; the slices normalised in a row start at col_off + g*group_stride + s*seg for g < n_groups,
+ * s < n_seg (cross-attention K of several layers side by side: one group per layer), seg <= 128 elements. */
+typedef struct {
+  void* x;
+  int M1, M2;
+  int64_t ld1, ld2;
+  int col_off, n_groups, group_stride, n_seg, seg;
+  dv_dtype dtype;
+} dv_l2norm_heads_params;
+int dv_l2norm_heads(const dv_l2norm_heads_params* p, dv_stream_t stream);
+
 /* Backward of the conditioning prologue in the training step (autograd of :348-372, :386, :153-155, to_kv and the token
  * LayerNorms inside p_losses :1908-2006).
  * dv_linear_small_bwd: `fwd` is the forward call (x, w, bias, keep, dimensions, strides, activations; y / accum / alt are not
