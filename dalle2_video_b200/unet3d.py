@@ -154,14 +154,18 @@ class _PixelShuffleUp(nn.Module):
 
 
 class _CrossEmbed(nn.Module):
-    def __init__(self, dim_in, kernel_sizes, dim_out):
+    """Parameters of CrossEmbedLayer3D (:208-244): stride 1 as the init conv (:320-327), stride 2 as the downsample of
+    cross_embed_downsample (:443-446)."""
+
+    def __init__(self, dim_in, kernel_sizes, dim_out, stride=1):
         super().__init__()
         ks = sorted(kernel_sizes)
+        assert all(k % 2 == stride % 2 for k in ks)
         scales = [int(dim_out / (2 ** i)) for i in range(1, len(ks))]
         scales = [*scales, dim_out - sum(scales)]
-        self.kernel_sizes = ks
+        self.kernel_sizes, self.stride = ks, stride
         self.convs = nn.ModuleList([
-            nn.Conv3d(dim_in, d, (1, k, k), stride=(1, 1, 1), padding=(0, (k - 1) // 2, (k - 1) // 2))
+            nn.Conv3d(dim_in, d, (1, k, k), stride=(1, stride, stride), padding=(0, (k - stride) // 2, (k - stride) // 2))
             for k, d in zip(ks, scales)])
 
 
@@ -189,12 +193,17 @@ class Unet3D(nn.Module):
         super().__init__()
         self._locals = {k: v for k, v in locals().items() if k not in ("self", "__class__")}
 
-        unsupported = dict(sparse_attn=sparse_attn, cross_embed_downsample=cross_embed_downsample,
-                           combine_upsample_fmaps=combine_upsample_fmaps,
-                           resnet_weight_standardization=resnet_weight_standardization)
+        # sparse_attn (dalle2_pytorch LinearAttention) and combine_upsample_fmaps (UpsampleCombiner) are 2-D image modules
+        # that the reference applies to the 5-D video tensor unchanged (:509-510, :619-624); resnet_weight_standardization
+        # is accepted and ignored exactly as the reference's Block3D ignores it (:100-104, a TODO there)
+        unsupported = dict(sparse_attn=sparse_attn, combine_upsample_fmaps=combine_upsample_fmaps)
         bad = [k for k, v in unsupported.items() if v]
         if bad:
             raise NotImplementedError(f"Unet3D(b200): options outside the accelerated hot path: {bad}")
+        if cross_embed_downsample:
+            assert tuple(sorted(cross_embed_downsample_kernel_sizes)) == (2, 4), \
+                "cross_embed_downsample is built for the kernel sizes (2, 4)"
+        self.cross_embed_downsample = cross_embed_downsample
         assert final_conv_ksize % 2 == 1 and final_conv_ksize <= 7, "final_conv_ksize must be odd and <= 7"
         if memory_efficient:
             assert not temporal_attn or not any(_cast_tuple(temporal_attn, len(dim_mults))), \
@@ -287,7 +296,8 @@ class Unet3D(nn.Module):
         # then run at the stage's output width and half its input resolution), a 1x1x1 convolution after them, and an
         # upsample after EVERY up stage
         self.init_resnet_block = res(init_dim, init_dim, groups=resnet_groups[0]) if memory_efficient else None
-        down = lambda a, b: nn.Sequential(nn.Identity(), nn.Conv3d(a * 4, b, 1))  # noqa: E731  Downsample3D (:19-26)
+        down = ((lambda a, b: _CrossEmbed(a, cross_embed_downsample_kernel_sizes, b, stride=2)) if cross_embed_downsample
+                else (lambda a, b: nn.Sequential(nn.Identity(), nn.Conv3d(a * 4, b, 1))))  # Downsample3D (:19-26)
         self.downs = nn.ModuleList([])
         self.ups = nn.ModuleList([])
         skip_dims = []
@@ -403,7 +413,7 @@ class Unet3D(nn.Module):
         """Forward + backward launch plan of the training step (dalle2_video_b200/train.py)."""
         from .train import _TrainPlan
         if (self.memory_efficient or not self.pixel_shuffle_upsample or self.final_conv_ksize != 1
-                or self.cosine_sim_cross_attn or self.cosine_sim_self_attn):
+                or self.cosine_sim_cross_attn or self.cosine_sim_self_attn or self.cross_embed_downsample):
             raise NotImplementedError("Unet3D(b200): the training plan is built for the default layer plan only "
                                       "(memory_efficient / pixel_shuffle_upsample=False / final_conv_ksize != 1 / cosine_sim_* "
                                       "sample, but do not train, on the native path)")
@@ -810,7 +820,41 @@ class _Engine:
         hiddens = []
         n_st = len(u.downs)
 
+        def cross_embed_down(x, ce, h, w):
+            """CrossEmbedLayer3D with stride 2 and kernel sizes (2, 4) (:208-244, :443-446).  The 2x2 stride-2 filter is the
+            pixel-unshuffle gather itself; the 4x4 stride-2 filter (padding 1) is a 3x3 stride-1 filter over the
+            pixel-unshuffled tensor U[Y][X][(s1, s2, c)] = x[2Y + s1][2X + s2][c]: input row 2y + dy - 1 is (Y = y - 1, s1 = 1),
+            (y, 0), (y, 1), (y + 1, 0) for dy = 0..3, so the taps that do not exist are zero weights.  U is written by an
+            unshuffle launch with an identity weight (an off-default layer: one extra pass)."""
+            c2, c4 = ce.convs
+            ci = c2.weight.shape[1]
+            co2, co4 = c2.weight.shape[0], c4.weight.shape[0]
+            y = self._new_act(B * T * (h // 2) * (w // 2), co2 + co4)
+            self._conv([(x.ptr, ci)], self._w(self._pack_conv(c2.weight)), self._f32(c2.bias), y.ptr, co2, n_img, h, w,
+                       mode=L.CONV_UNSHUFFLE, out_ld=co2 + co4, out_coff=0)
+            U = self._new_act(B * T * (h // 2) * (w // 2), 4 * ci)
+            self._conv([(x.ptr, ci)], self._w(torch.eye(4 * ci)), None, U.ptr, 4 * ci, n_img, h, w, mode=L.CONV_UNSHUFFLE)
+            w4 = c4.weight.detach()[:, :, 0]                       # [co][ci][dy][dx]
+            wp = torch.zeros(co4, 3, 3, 2, 2, ci, device=w4.device, dtype=w4.dtype)
+            for ty in range(3):
+                for s1 in range(2):
+                    dy = 2 * ty + s1 - 1
+                    if not 0 <= dy < 4:
+                        continue
+                    for tx in range(3):
+                        for s2 in range(2):
+                            dx = 2 * tx + s2 - 1
+                            if 0 <= dx < 4:
+                                wp[:, ty, tx, s1, s2] = w4[:, :, dy, dx]
+            self._conv([(U.ptr, 4 * ci)], self._w(wp.reshape(co4, 9 * 4 * ci)), self._f32(c4.bias), y.ptr, co4, n_img, h // 2,
+                       w // 2, k=3, out_ld=co2 + co4, out_coff=co2)
+            self._release(U)
+            self._release(x)
+            return y
+
         def unshuffle_conv(x, conv, h, w):
+            if isinstance(conv, _CrossEmbed):
+                return cross_embed_down(x, conv, h, w)
             co, c4 = conv.weight.shape[0], conv.weight.shape[1]
             ci = c4 // 4
             # in-channel index of the reference is (c s1 s2) (:24); K order here is [s1][s2][c]
@@ -824,7 +868,7 @@ class _Engine:
             x = self._resblock(u.init_resnet_block, [x], h, w)
         for s, st in enumerate(u.downs):
             if st[0] is not None:   # memory_efficient: downsample first (:898-899)
-                x = unshuffle_conv(x, st[0][1], h, w)
+                x = unshuffle_conv(x, st[0] if isinstance(st[0], _CrossEmbed) else st[0][1], h, w)
                 h, w = h // 2, w // 2
             x = self._resblock(st[1], [x], h, w)
             for m in st[2]:
@@ -838,8 +882,8 @@ class _Engine:
             x.refs += 1
             hiddens.append(x)
             post = st[4]
-            if isinstance(post, nn.Sequential):
-                x = unshuffle_conv(x, post[1], h, w)
+            if isinstance(post, (nn.Sequential, _CrossEmbed)):
+                x = unshuffle_conv(x, post if isinstance(post, _CrossEmbed) else post[1], h, w)
                 h, w = h // 2, w // 2
             else:
                 conv = post

@@ -120,9 +120,12 @@ OPTION_CASES = {
     "cosine_sim": dict(unet=dict(dim=32, video_embed_dim=512, dim_mults=(1, 2), cond_on_video_embeds=True,
                                  cosine_sim_cross_attn=True, cosine_sim_self_attn=True), shape=(2, 3, 4, 32, 32),
                        times=(7, 640)),
+    "cross_embed_down": dict(unet=dict(dim=32, video_embed_dim=512, dim_mults=(1, 2, 4), cond_on_video_embeds=True,
+                                       cross_embed_downsample=True, resnet_weight_standardization=True),
+                             shape=(2, 3, 4, 32, 32), times=(7, 640)),
     "all_three": dict(unet=dict(dim=32, video_embed_dim=512, dim_mults=(1, 2), cond_on_video_embeds=True,
                                 memory_efficient=True, pixel_shuffle_upsample=False, final_conv_ksize=3,
-                                lowres_cond=True), shape=(1, 3, 4, 32, 32), times=(311,), lowres=True),
+                                lowres_cond=True, cross_embed_downsample=True), shape=(1, 3, 4, 32, 32), times=(311,), lowres=True),
 }
 
 

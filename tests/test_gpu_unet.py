@@ -34,7 +34,7 @@ def test_forward_matches_reference_fixture(name, dtype, tol, layouts):
     assert err < tol, err
 
 
-@pytest.mark.parametrize("name", ["memory_efficient", "nearest_upsample", "final_conv3", "all_three", "cosine_sim"])
+@pytest.mark.parametrize("name", ["memory_efficient", "nearest_upsample", "final_conv3", "all_three", "cosine_sim", "cross_embed_down"])
 @pytest.mark.parametrize("dtype,tol", [(torch.float32, FP32_TOL), (torch.bfloat16, BF16_TOL)])
 def test_off_default_layer_plans_match_reference_fixture(name, dtype, tol):
     """memory_efficient (downsample first, initial resnet block, upsample after every up stage), NearestUpsample3D

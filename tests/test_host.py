@@ -29,7 +29,7 @@ def test_state_dict_layout_matches_reference(name, layouts):
     assert {k: list(v.shape) for k, v in sd.items()} == layouts[name]
 
 
-@pytest.mark.parametrize("name", ["memory_efficient", "nearest_upsample", "final_conv3", "all_three", "cosine_sim"])
+@pytest.mark.parametrize("name", ["memory_efficient", "nearest_upsample", "final_conv3", "all_three", "cosine_sim", "cross_embed_down"])
 def test_off_default_layer_plan_state_dict_layouts_match_reference(name):
     """memory_efficient / pixel_shuffle_upsample=False / final_conv_ksize=3: same parameter names and shapes as the
     reference's own modules (fixture: `python -m oracle.make_golden options`), and same-seed initialisation where the
@@ -48,8 +48,7 @@ def test_off_default_layer_plan_state_dict_layouts_match_reference(name):
 
 
 def test_off_default_options_without_a_kernel_raise():
-    for kw in (dict(cross_embed_downsample=True),
-               dict(combine_upsample_fmaps=True), dict(resnet_weight_standardization=True), dict(sparse_attn=True)):
+    for kw in (dict(combine_upsample_fmaps=True), dict(sparse_attn=True)):
         with pytest.raises(NotImplementedError):
             Unet3D(dim=32, video_embed_dim=512, dim_mults=(1, 2), cond_on_video_embeds=True, **kw)
 
