@@ -155,6 +155,28 @@ def options():
         json.dump(layouts, f, indent=0, sort_keys=True)
 
 
+OPTIONS_SAMPLE_UNET = dict(dim=32, video_embed_dim=512, dim_mults=(1, 2), cond_on_video_embeds=True, memory_efficient=True,
+                           pixel_shuffle_upsample=False, final_conv_ksize=3, cosine_sim_cross_attn=True,
+                           cosine_sim_self_attn=True, cross_embed_downsample=True)
+
+
+def options_sample():
+    """python -m oracle.make_golden options_sample -> tests/golden/sample_options_6.pt: the reference's own
+    VideoDecoder.sample() over a Unet3D with every off-default layer plan the native engine takes."""
+    ref = reference.load()
+    torch.manual_seed(0)
+    unet = ref.Unet3D(**OPTIONS_SAMPLE_UNET)
+    dec = ref.VideoDecoder(unet, frame_size=32, frame_numbers=(4,), timesteps=6, learned_variance=False)
+    shapes = shapes_of(dec.unets[0])
+    dec.unets[0].load_state_dict(synth_state_dict(shapes, seed=7), strict=True)
+    emb = torch.randn(2, 512, generator=torch.Generator().manual_seed(23))
+    torch.manual_seed(2468)
+    vid = dec.sample(video_embed=emb)
+    torch.save({"video_embed": emb, "sample": vid, "timesteps": 6, "sample_seed": 2468, "weight_seed": 7,
+                "unet_kwargs": OPTIONS_SAMPLE_UNET, "layout": shapes}, os.path.join(GOLDEN, "sample_options_6.pt"))
+    print("sample options", tuple(vid.shape), float(vid.mean()))
+
+
 CASCADE_U1 = dict(dim=32, video_embed_dim=512, dim_mults=(1, 2), cond_on_video_embeds=True)
 CASCADE_U2 = dict(dim=16, video_embed_dim=512, dim_mults=(1, 2), cond_on_video_embeds=True)
 
@@ -442,5 +464,7 @@ if __name__ == "__main__":
         decoder_layout()
     elif len(sys.argv) > 1 and sys.argv[1] == "options":
         options()
+    elif len(sys.argv) > 1 and sys.argv[1] == "options_sample":
+        options_sample()
     else:
         main()

@@ -47,6 +47,23 @@ def test_sample_fp32_matches_reference_fixture(steps, graph, layouts):
     assert 0.0 <= float(vid.min()) and float(vid.max()) <= 1.0
 
 
+@pytest.mark.parametrize("graph", [False, True])
+def test_sample_with_off_default_layer_plans_matches_reference_fixture(graph):
+    """The reference's own VideoDecoder.sample() over a Unet3D with memory_efficient, NearestUpsample3D, a 3x3 head, cosine-sim
+    attention and the CrossEmbed downsample (`python -m oracle.make_golden options_sample`): the same loop, eager and as
+    one CUDA graph per step; bf16 by PSNR."""
+    g = golden("sample_options_6.pt")
+    d = decoder(g["unet_kwargs"], g["layout"], g["timesteps"], 32, 4, seed=g["weight_seed"])
+    d.use_cuda_graph = graph
+    vid = d.sample(video_embed=g["video_embed"].cuda(), noise_fn=cpu_noise(g["sample_seed"]))
+    assert vid.shape == g["sample"].shape and d.last_launch_stats["graph"] == graph
+    err = float((vid.cpu() - g["sample"]).abs().max())
+    assert err < 2e-3, err
+    d.unets[0].compute_dtype = torch.bfloat16
+    vid16 = d.sample(video_embed=g["video_embed"].cuda(), noise_fn=cpu_noise(g["sample_seed"]))
+    assert psnr(vid16, g["sample"]) >= 30.0
+
+
 def test_sample_bf16_psnr_bound(layouts):
     g = golden("sample_tiny_50.pt")
     d = decoder(TINY, layouts["tiny"], 50, 32, 8)
