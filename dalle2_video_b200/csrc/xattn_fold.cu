@@ -6,7 +6,7 @@
 //   MMA 1   raw[128][64]  = x . Mq^T            (M=128, N=64, K=C)        -> TMEM columns [0,64)
 //   threads logits = rstd_x * (raw - mean_x * cs);  per-head softmax over nk keys;  P (bf16) -> shared memory
 //   MMA 2   y[128][C]     = P . U^T             (M=128, N=min(C,256), K=64) -> TMEM columns [0,C)
-//   threads LayerNorm(y) * g2 + x -> bf16 -> shared-memory slab -> TMA store
+//   threads LayerNorm(y) * g2 + x -> bf16, in place over the x tile -> TMA store
 // HBM traffic is the minimum: read x once, write out once; the 512-wide q / attention-output tensors of the
 // unfused formulation never exist.
 #include "tc_common.cuh"
@@ -109,6 +109,7 @@ constexpr int XF_THREADS = 192;  // warp 0 TMA, warp 1 MMA, warps 2-5 softmax + 
 
 struct XfoldParams {
   int alias_u;            // C = 512: U takes Mq's shared memory once MMA 1 has retired; one tile per CTA
+  int slack;              // bytes of alignment slack in the dynamic shared memory request (0: must start 1024-aligned)
   int C, chunks, NB, xs;  // channels, C/64, N of MMA 2 (min(C,256)), X stages
   int heads, nk;
   int64_t tiles, tiles_per_sample;
@@ -132,17 +133,18 @@ xattn_fold_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
                   const XfoldParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = align_smem_1024(smem_raw);
+  if ((int)(smem - smem_raw) > p.slack) __trap();   // the exact-fit request (C = 128) relies on a 1024-aligned start
   const uint32_t x_stage_bytes = (uint32_t)p.chunks * 16384;
   uint8_t* x_s = smem;                                           // [xs][chunks][128 rows x 128 B]
   uint8_t* mq_s = x_s + (size_t)p.xs * x_stage_bytes;            // [chunks][64 rows x 128 B]
   // C = 512: x (128 KB) + Mq (64 KB) + U (64 KB) do not fit; Mq is dead once MMA 1 has retired, so U is loaded over it
   uint8_t* u_s = p.alias_u ? mq_s : mq_s + (size_t)p.chunks * 8192;   // [C rows x 128 B]
-  uint8_t* p_s = mq_s + (size_t)p.chunks * 8192 + (p.alias_u ? 0 : (size_t)p.C * 128);  // [128 rows x 128 B]  P, then output slab
+  uint8_t* p_s = mq_s + (size_t)p.chunks * 8192 + (p.alias_u ? 0 : (size_t)p.C * 128);  // [128 rows x 128 B]  P
   float* cs_s = reinterpret_cast<float*>(p_s + 16384);           // [64]
   float* g2_s = cs_s + 64;                                       // [C]
   uint64_t* bars = reinterpret_cast<uint64_t*>(g2_s + p.C);
   uint64_t* x_full = bars;        // [2]
-  uint64_t* x_empty = bars + 2;   // [2]
+  uint64_t* out_ready = bars + 2; // [2]: the epilogue has written the tile's result over x in this stage (4 arrivals)
   uint64_t* w_full = bars + 4;
   uint64_t* w_free = bars + 5;
   uint64_t* s_full = bars + 6;
@@ -161,7 +163,7 @@ xattn_fold_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
     tma_prefetch_desc(&map_mq);
     tma_prefetch_desc(&map_u);
     tma_prefetch_desc(&map_out);
-    for (int s = 0; s < 2; ++s) { mbar_init(&x_full[s], 1); mbar_init(&x_empty[s], 4); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&x_full[s], 1); mbar_init(&out_ready[s], 4); }
     mbar_init(w_full, 1);
     mbar_init(s_full, 1);
     mbar_init(p_ready, 4);
@@ -201,19 +203,34 @@ xattn_fold_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
         if (!p.alias_u)
           for (int r0 = 0; r0 < p.C; r0 += p.NB) tma_load_3d(&map_u, w_full, u_s + (size_t)r0 * 128, 0, r0, b);
       }
-      for (int64_t tile = tile_begin; tile < tile_end; ++tile, ++t) {
-        const int st = t % p.xs;
-        mbar_wait(&x_empty[st], (uint32_t)(((t / p.xs) & 1) ^ 1));
+      // The producer also sends the results: the epilogue writes a tile's output over x in its stage (out_ready), this thread
+      // stores the stage and refills it with the x tile `xs` tiles ahead as soon as the store has read it.
+      const int n = (int)(tile_end - tile_begin);
+      auto load_x = [&](int i) {
+        const int st = i % p.xs;
         mbar_expect_tx(&x_full[st], x_stage_bytes);
         for (int c = 0; c < p.chunks; ++c)
           tma_load_2d(&map_x, &x_full[st], x_s + (size_t)st * x_stage_bytes + (size_t)c * 16384, c * 64,
-                      (int)(tile * TC_BM));
-        if (p.alias_u) {   // one tile per CTA (host): U over Mq as soon as nobody reads Mq any more
-          mbar_wait(mq_free, 0u);
-          mbar_expect_tx(u_full, (uint32_t)(p.C * 128));
-          for (int r0 = 0; r0 < p.C; r0 += p.NB) tma_load_3d(&map_u, u_full, u_s + (size_t)r0 * 128, 0, r0, b);
+                      (int)((tile_begin + i) * TC_BM));
+      };
+      for (int i = 0; i < p.xs && i < n; ++i) load_x(i);
+      if (p.alias_u && n > 0) {   // one tile per CTA (host): U over Mq as soon as nobody reads Mq any more
+        mbar_wait(mq_free, 0u);
+        mbar_expect_tx(u_full, (uint32_t)(p.C * 128));
+        for (int r0 = 0; r0 < p.C; r0 += p.NB) tma_load_3d(&map_u, u_full, u_s + (size_t)r0 * 128, 0, r0, b);
+      }
+      for (t = 0; t < n; ++t) {
+        const int st = t % p.xs;
+        mbar_wait(&out_ready[st], (uint32_t)((t / p.xs) & 1));
+        for (int c = 0; c < p.chunks; ++c)
+          tma_store_2d(&map_out, x_s + (size_t)st * x_stage_bytes + (size_t)c * 16384, c * 64, (int)((tile_begin + t) * TC_BM));
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        if (t + p.xs < n) {
+          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          load_x(t + p.xs);
         }
       }
+      asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
   } else if (warp == 1) {
     // ================================================================ MMA issuer
@@ -360,10 +377,11 @@ xattn_fold_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
       }
       const float mean_y = sy / (float)p.C;
       const float rstd_y = rsqrtf(fmaxf(syy / (float)p.C - mean_y * mean_y, 0.f) + p.eps_out);
+      // The result replaces x IN PLACE in the x stage (same rows, same swizzle as the TMA box that brought x in): every thread
+      // touches only its own row, so there is no staging buffer and no barrier among the epilogue warps: the producer thread
+      // stores the stage once all four warps have arrived on out_ready.
+      uint8_t* xw = x_s + (size_t)st * x_stage_bytes + (size_t)row * 128;
       for (int s0 = 0; s0 < p.C; s0 += 64) {
-        // the previous slab's TMA store (and, for the first slab, MMA 2's read of P) is done with p_s
-        if (et == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-        xf_bar();
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
           const int c0 = s0 + half * 32;
@@ -372,7 +390,8 @@ xattn_fold_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const int chunk = half * 4 + j;  // 16-byte chunk of the 64-column slab
-            const uint4 xr = *reinterpret_cast<const uint4*>(xrow + (size_t)(s0 / 64) * 16384 + ((chunk ^ (row & 7)) * 16));
+            uint4* cell = reinterpret_cast<uint4*>(xw + (size_t)(s0 / 64) * 16384 + ((chunk ^ (row & 7)) * 16));
+            const uint4 xr = *cell;
             const __nv_bfloat162* xh = reinterpret_cast<const __nv_bfloat162*>(&xr);
             uint4 pk;
             __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&pk);
@@ -383,27 +402,19 @@ xattn_fold_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
               const float o1 = (__uint_as_float(r[j * 8 + 2 * e + 1]) - mean_y) * rstd_y * g2_s[c + 1] + __high2float(xh[e]);
               oh[e] = __floats2bfloat162_rn(o0, o1);
             }
-            *reinterpret_cast<uint4*>(p_s + (size_t)row * 128 + ((chunk ^ (row & 7)) * 16)) = pk;
+            *cell = pk;
           }
         }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        xf_bar();
-        if (et == 0) {
-          tma_store_2d(&map_out, p_s, s0, (int)(tile * TC_BM));
-          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-        }
       }
-      // release TMEM and the x stage; make sure the last store has read p_s before the next tile writes P
+      // release TMEM and hand the stage (now holding the result) to the producer thread, which stores it
       tc_fence_before();
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       __syncwarp();
       if (lane == 0) {
         mbar_arrive(acc_free);
-        mbar_arrive(&x_empty[st]);
+        mbar_arrive(&out_ready[st]);
       }
-      if (et == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-      xf_bar();
     }
-    if (et == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
 
   tc_fence_before();
@@ -479,7 +490,7 @@ extern "C" int dv_xattn_fold(const dv_xattn_fold_params* p, dv_stream_t stream) 
   k.chunks = p->C / 64;
   k.NB = p->C < 256 ? p->C : 256;
   k.alias_u = p->C == 512;
-  k.xs = (p->C == 128 || p->C == 512) ? 1 : 2;  // C = 128: one x stage lets two CTAs share an SM, which hides more than the prefetch did
+  k.xs = p->C == 512 ? 1 : 2;   // two x stages: the result is written over x in place and leaves from the stage itself
   k.heads = p->heads;
   k.nk = p->nk;
   k.tiles_per_sample = p->P / TC_BM;
@@ -510,8 +521,13 @@ extern "C" int dv_xattn_fold(const dv_xattn_fold_params* p, dv_stream_t stream) 
     uint32_t box[3] = {64, (uint32_t)k.NB, 1};
     if ((rc = encode_map(&mu, p->u, 3, dims, strides, box)) != DV_OK) return rc;
   }
-  const size_t smem = (size_t)k.xs * k.chunks * 16384 + (size_t)k.chunks * 8192 + (k.alias_u ? 0 : (size_t)p->C * 128) + 16384 +
-                     64 * 4 + (size_t)p->C * 4 + 256 + 1024;
+  // C = 128 with two x stages and two CTAs per SM is an exact fit (2 x (112 KB + 880 B + the 1 KB the system reserves per CTA)
+  // = the SM's 228 KB), so there is no alignment slack there: the dynamic shared memory of a kernel without static shared
+  // memory starts 1024-aligned, and the kernel traps if it ever does not
+  const size_t smem_body = (size_t)k.xs * k.chunks * 16384 + (size_t)k.chunks * 8192 + (k.alias_u ? 0 : (size_t)p->C * 128) +
+                           16384 + 64 * 4 + (size_t)p->C * 4 + 112;
+  const size_t smem = p->C == 128 ? smem_body : smem_body + 1024;
+  k.slack = p->C == 128 ? 0 : 1024;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(xattn_fold_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -530,7 +546,7 @@ extern "C" int dv_xattn_fold(const dv_xattn_fold_params* p, dv_stream_t stream) 
   // the per-tile chain (LN statistics -> MMA 1 -> softmax -> MMA 2 -> LN -> store) is serial within a CTA: two CTAs per
   // SM overlap two chains whenever shared memory (and TMEM: C columns each) allow it
   const uint32_t tmem_cols = p->C < 64 ? 64u : (uint32_t)p->C;
-  const int per_sm = (2 * (smem + 1024) <= 227 * 1024 && 2 * tmem_cols <= 512) ? 2 : 1;
+  const int per_sm = (2 * (smem + 1024) <= 228 * 1024 && 2 * tmem_cols <= 512) ? 2 : 1;
   int gx = per_sm * sm_count / p->B;
   if (gx < 1) gx = 1;
   if (gx > k.tiles_per_sample) gx = (int)k.tiles_per_sample;
