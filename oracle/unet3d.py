@@ -57,6 +57,14 @@ class UnetConfig:
     init_conv_ksize: int = 7
     scale_skip_connection: bool = False
     final_conv_ksize: int = 1
+    # off-default layer plans (dalle2_video.py:268-269, :282-287)
+    memory_efficient: bool = False
+    pixel_shuffle_upsample: bool = True
+    cosine_sim_cross_attn: bool = False
+    cosine_sim_self_attn: bool = False
+    cross_embed_downsample: bool = False
+    cross_embed_downsample_kernel_sizes: Sequence[int] = (2, 4)
+    resnet_weight_standardization: bool = False   # accepted and ignored, as Block3D ignores it (:100-104)
     # extensions the reference Unet3D does not have (default off = reference behaviour);
     # their oracle is the composition of reference / upstream primitives on rearranged tensors stated there
     temporal_conv: bool = False      # Conv3d(C, C, (3,1,1), padding=(1,0,0)) after every Block3D.project
@@ -89,8 +97,9 @@ def _sinusoidal(t, dim):
     return torch.cat((a.sin(), a.cos()), dim=-1)
 
 
-def _cross_attention(sd, p, x, ctx, heads=8, dim_head=64):
-    """CrossAttention.forward; x (b,n,c), ctx (b,m,cond_dim); residual added by caller."""
+def _cross_attention(sd, p, x, ctx, heads=8, dim_head=64, cosine_sim=False):
+    """CrossAttention.forward; x (b,n,c), ctx (b,m,cond_dim); residual added by caller.  cosine_sim: q, k
+    l2-normalised per head (the null key with the keys) and scale = cosine_sim_scale = 16."""
     b, n, _ = x.shape
     xn = _ln_gain(x, sd[p + "norm.g"])
     q = xn @ sd[p + "to_q.weight"].t()
@@ -101,7 +110,9 @@ def _cross_attention(sd, p, x, ctx, heads=8, dim_head=64):
     nk, nv = sd[p + "null_kv"].unbind(dim=-2)
     k = torch.cat((nk.expand(b, heads, 1, dim_head), k), dim=-2)
     v = torch.cat((nv.expand(b, heads, 1, dim_head), v), dim=-2)
-    s = math.sqrt(dim_head ** -0.5)
+    if cosine_sim:
+        q, k = F.normalize(q, dim=-1), F.normalize(k, dim=-1)
+    s = math.sqrt(16.0 if cosine_sim else dim_head ** -0.5)
     sim = (q * s) @ (k * s).transpose(-1, -2)
     attn = sim.softmax(dim=-1, dtype=torch.float32).type(sim.dtype)
     out = (attn @ v).permute(0, 2, 1, 3).reshape(b, n, heads * dim_head)
@@ -109,17 +120,19 @@ def _cross_attention(sd, p, x, ctx, heads=8, dim_head=64):
     return _ln_gain(out, sd[p + "to_out.1.g"])
 
 
-def _self_attention(sd, p, x, heads, dim_head, attn_bias=None):
-    """Attention.forward with cosine_sim=False: multi-query, null kv, logits q·k/dim_head."""
+def _self_attention(sd, p, x, heads, dim_head, attn_bias=None, cosine_sim=False):
+    """Attention.forward: multi-query, null kv, logits q·k/dim_head; cosine_sim: 16 l2norm(q)·l2norm(k)."""
     b, n, _ = x.shape
     xn = _ln_gain(x, sd[p + "norm.g"])
     q = (xn @ sd[p + "to_q.weight"].t()).reshape(b, n, heads, dim_head).permute(0, 2, 1, 3)
     k, v = (xn @ sd[p + "to_kv.weight"].t()).chunk(2, dim=-1)
-    scale = dim_head ** -0.5
+    scale = 16.0 if cosine_sim else dim_head ** -0.5
     q = q * scale
     nk, nv = sd[p + "null_kv"].unbind(dim=-2)
     k = torch.cat((nk.expand(b, 1, dim_head), k), dim=-2)
     v = torch.cat((nv.expand(b, 1, dim_head), v), dim=-2)
+    if cosine_sim:
+        q, k = F.normalize(q, dim=-1), F.normalize(k, dim=-1)
     q, k = q * math.sqrt(scale), k * math.sqrt(scale)
     sim = torch.einsum("bhid,bjd->bhij", q, k)
     if attn_bias is not None:
@@ -153,7 +166,7 @@ def _block(sd, p, x, groups, scale_shift=None):
     return F.silu(x)
 
 
-def _resnet_block(sd, p, x, t_emb, cond, groups):
+def _resnet_block(sd, p, x, t_emb, cond, groups, cosine_sim=False):
     """ResnetBlock3D.forward (dalle2_video.py:172-205)."""
     ss = None
     if (p + "time_mlp.1.weight") in sd and t_emb is not None:
@@ -163,7 +176,7 @@ def _resnet_block(sd, p, x, t_emb, cond, groups):
     if (p + "cross_attn.to_q.weight") in sd:
         assert cond is not None
         tok = _tokens(h)
-        tok = _cross_attention(sd, p + "cross_attn.", tok, cond) + tok
+        tok = _cross_attention(sd, p + "cross_attn.", tok, cond, cosine_sim=cosine_sim) + tok
         h = _untokens(tok, h)
     h = _block(sd, p + "block2.", h, groups)
     if (p + "res_conv.weight") in sd:
@@ -171,16 +184,16 @@ def _resnet_block(sd, p, x, t_emb, cond, groups):
     return h + x
 
 
-def _joint_attention(sd, p, x, heads, dim_head, mode="joint"):
+def _joint_attention(sd, p, x, heads, dim_head, mode="joint", cosine_sim=False):
     """RearrangeToSequence(Residual(Attention)) (dalle2_video.py:430-432): joint over T*H*W.
     mode "factorised" (extension 2a): the same module on "(b t) (h w) c"."""
     if mode == "factorised":
         b, c, t, h, w = x.shape
         tok = x.permute(0, 2, 3, 4, 1).reshape(b * t, h * w, c)
-        tok = _self_attention(sd, p + "fn.fn.", tok, heads, dim_head) + tok
+        tok = _self_attention(sd, p + "fn.fn.", tok, heads, dim_head, cosine_sim=cosine_sim) + tok
         return tok.reshape(b, t, h, w, c).permute(0, 4, 1, 2, 3)
     tok = _tokens(x)
-    tok = _self_attention(sd, p + "fn.fn.", tok, heads, dim_head) + tok
+    tok = _self_attention(sd, p + "fn.fn.", tok, heads, dim_head, cosine_sim=cosine_sim) + tok
     return _untokens(tok, x)
 
 
@@ -208,6 +221,22 @@ def _pixel_unshuffle_down(sd, p, x):
     b, c, t, h, w = x.shape
     x = x.reshape(b, c, t, h // 2, 2, w // 2, 2).permute(0, 1, 4, 6, 2, 3, 5).reshape(b, c * 4, t, h // 2, w // 2)
     return F.conv3d(x, sd[p + "1.weight"], sd[p + "1.bias"])
+
+
+def _cross_embed_down(sd, p, x, kernel_sizes, stride=2):
+    """CrossEmbedLayer3D with stride 2 (dalle2_video.py:208-244; the downsample of cross_embed_downsample, :443-446)."""
+    fmaps = []
+    for i, k in enumerate(sorted(kernel_sizes)):
+        pad = (k - stride) // 2
+        fmaps.append(F.conv3d(x, sd[f"{p}convs.{i}.weight"], sd[f"{p}convs.{i}.bias"], stride=(1, stride, stride),
+                              padding=(0, pad, pad)))
+    return torch.cat(fmaps, dim=1)
+
+
+def _nearest_up(sd, p, x):
+    """NearestUpsample3D (dalle2_video.py:29-35): nn.Upsample(scale_factor=(1, 2, 2), mode="nearest") + Conv3d (1,3,3)."""
+    x = F.interpolate(x, scale_factor=(1, 2, 2), mode="nearest")
+    return F.conv3d(x, sd[p + "1.weight"], sd[p + "1.bias"], padding=(0, 1, 1))
 
 
 def _pixel_shuffle_up(sd, p, x):
@@ -301,48 +330,60 @@ def unet3d_forward(sd, cfg: UnetConfig, x, time, *, video_embed=None, text_encod
     skip_scale = 2 ** -0.5 if cfg.scale_skip_connection else 1.0
     hiddens = []
 
-    # down path (:903-917)
+    cs_x, cs_s = cfg.cosine_sim_cross_attn, cfg.cosine_sim_self_attn
+    res = lambda p, x, cond, g: _resnet_block(sd, p, x, t, cond, g, cosine_sim=cs_x)  # noqa: E731
+    down = ((lambda p, x: _cross_embed_down(sd, p, x, cfg.cross_embed_downsample_kernel_sizes)) if cfg.cross_embed_downsample
+            else (lambda p, x: _pixel_unshuffle_down(sd, p, x)))
+    up = (lambda p, x: _pixel_shuffle_up(sd, p, x)) if cfg.pixel_shuffle_upsample else (lambda p, x: _nearest_up(sd, p, x))
+
+    # memory_efficient: an initial resnet block (:466-477, :893-894)
+    if cfg.memory_efficient:
+        x = res("init_resnet_block.", x, None, groups[0])
+
+    # down path (:896-917); memory_efficient downsamples BEFORE the stage's blocks and ends every stage with a 1x1x1 conv
     for s in range(n):
-        x = _resnet_block(sd, f"downs.{s}.1.", x, t, c, groups[s])
+        if cfg.memory_efficient:
+            x = down(f"downs.{s}.0.", x)
+        x = res(f"downs.{s}.1.", x, c, groups[s])
         for j in range(n_blocks[s]):
-            x = _resnet_block(sd, f"downs.{s}.2.{j}.", x, t, c, groups[s])
+            x = res(f"downs.{s}.2.{j}.", x, c, groups[s])
             hiddens.append(x)
         if self_attn[s]:
-            x = _joint_attention(sd, f"downs.{s}.3.", x, cfg.attn_heads, cfg.attn_dim_head, cfg.attn_mode)
+            x = _joint_attention(sd, f"downs.{s}.3.", x, cfg.attn_heads, cfg.attn_dim_head, cfg.attn_mode, cs_s)
         if t_attn[s]:
             x = _temporal_attention(sd, f"down_temporal_attns.{s}.", x, cfg.attn_heads, cfg.attn_dim_head)
         hiddens.append(x)
-        if s < n - 1:
-            x = _pixel_unshuffle_down(sd, f"downs.{s}.4.", x)
+        if s < n - 1 and not cfg.memory_efficient:
+            x = down(f"downs.{s}.4.", x)
         else:
             x = F.conv3d(x, sd[f"downs.{s}.4.weight"], sd[f"downs.{s}.4.bias"])
 
     # middle (:919-924)
-    x = _resnet_block(sd, "mid_block1.", x, t, mid_c, groups[-1])
+    x = res("mid_block1.", x, mid_c, groups[-1])
     # mid_attn is built and applied unconditionally: `attend_at_middle` is accepted but never read (:551, :921)
-    x = _joint_attention(sd, "mid_attn.", x, cfg.attn_heads, cfg.attn_dim_head, cfg.attn_mode)
+    x = _joint_attention(sd, "mid_attn.", x, cfg.attn_heads, cfg.attn_dim_head, cfg.attn_mode, cs_s)
     if any(t_attn):
         x = _temporal_attention(sd, "mid_temporal_attn.", x, cfg.attn_heads, cfg.attn_dim_head)
-    x = _resnet_block(sd, "mid_block2.", x, t, mid_c, groups[-1])
+    x = res("mid_block2.", x, mid_c, groups[-1])
 
-    # up path (:930-941)
+    # up path (:930-941); memory_efficient upsamples after the last stage too (:611)
     rgroups, rblocks, rattn = groups[::-1], n_blocks[::-1], self_attn[::-1]
     for s in range(n):
         x = torch.cat((x, hiddens.pop() * skip_scale), dim=1)
-        x = _resnet_block(sd, f"ups.{s}.0.", x, t, c, rgroups[s])
+        x = res(f"ups.{s}.0.", x, c, rgroups[s])
         for j in range(rblocks[s]):
             x = torch.cat((x, hiddens.pop() * skip_scale), dim=1)
-            x = _resnet_block(sd, f"ups.{s}.1.{j}.", x, t, c, rgroups[s])
+            x = res(f"ups.{s}.1.{j}.", x, c, rgroups[s])
         if rattn[s]:
-            x = _joint_attention(sd, f"ups.{s}.2.", x, cfg.attn_heads, cfg.attn_dim_head, cfg.attn_mode)
+            x = _joint_attention(sd, f"ups.{s}.2.", x, cfg.attn_heads, cfg.attn_dim_head, cfg.attn_mode, cs_s)
         if t_attn[n - 1 - s]:
             x = _temporal_attention(sd, f"up_temporal_attns.{s}.", x, cfg.attn_heads, cfg.attn_dim_head)
-        if s < n - 1:
-            x = _pixel_shuffle_up(sd, f"ups.{s}.3.", x)
+        if s < n - 1 or cfg.memory_efficient:
+            x = up(f"ups.{s}.3.", x)
 
     # head (:945-952)
     x = torch.cat((x, r), dim=1)
-    x = _resnet_block(sd, "final_resnet_block.", x, t, None, groups[0])
+    x = res("final_resnet_block.", x, None, groups[0])
     if lowres_cond_video is not None:
         x = torch.cat((x, lowres_cond_video), dim=1)
     k = cfg.final_conv_ksize

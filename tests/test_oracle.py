@@ -24,6 +24,25 @@ def test_unet_forward_matches_reference_fixture(name, layouts):
     assert rel < 1e-5, rel  # fp32, same op order up to reduction order
 
 
+@pytest.mark.parametrize("name", ["memory_efficient", "nearest_upsample", "final_conv3", "cosine_sim", "cross_embed_down",
+                                  "all_three"])
+def test_off_default_layer_plans_match_reference_fixture(name):
+    """The restatement of memory_efficient / NearestUpsample3D / final_conv_ksize / cosine_sim_* / cross_embed_downsample against
+    outputs of the reference's own Unet3D (`python -m oracle.make_golden options`)."""
+    import json
+    import os
+    from conftest import ROOT
+    from oracle.weights import synth_state_dict
+    g = golden("unet3d_options.pt")[name]
+    layout = json.load(open(os.path.join(ROOT, "tests", "golden", "unet3d_options_layouts.json")))[name]
+    sd = synth_state_dict(layout, seed=g["weight_seed"])
+    with torch.no_grad():
+        out = unet3d_forward(sd, UnetConfig(**g["unet_kwargs"]), g["x"], g["times"], video_embed=g["video_embed"],
+                             lowres_cond_video=g["lowres_cond_video"])
+    err = float((out - g["eps"]).norm() / g["eps"].norm())
+    assert err < 1e-5, err
+
+
 def test_sampler_matches_reference_fixture(layouts):
     g = golden("sample_tiny_8.pt")
     cfg = UnetConfig(dim=32, video_embed_dim=512, dim_mults=(1, 2), cond_on_video_embeds=True)
