@@ -479,6 +479,8 @@ class _TrainPlan:
         nt, nv = u.num_time_tokens, (u.num_image_tokens if u.cond_on_video_embeds else 0)
         self.zero_each_step = []
         blocks = []
+        if u.init_resnet_block is not None:
+            blocks.append((u.init_resnet_block, "c"))
         for st in u.downs:
             blocks.append((st[1], "c"))
             blocks += [(m, "c") for m in st[2]]
@@ -572,7 +574,20 @@ class _TrainPlan:
         h, w = H, W
         hiddens = []
         n_st = len(u.downs)
+
+        def unshuffle_conv(x, conv, h, w):   # Downsample3D (:19-26)
+            co, ci = conv.weight.shape[0], conv.weight.shape[1] // 4
+            return self._conv([x], lambda conv=conv, co=co, ci=ci: conv.weight.detach().float().reshape(co, ci, 2, 2)[:, :, None],
+                              lambda conv=conv: conv.bias.detach().float(), conv.weight,
+                              lambda g5, co=co, ci=ci: g5[:, :, 0].reshape(co, 4 * ci, 1, 1, 1), conv.bias, co, n_img, h, w,
+                              mode=L.CONV_UNSHUFFLE)
+
+        if u.init_resnet_block is not None:   # memory_efficient (:466-477, :893-894)
+            x = self._resblock(u.init_resnet_block, [x], h, w)
         for s, st in enumerate(u.downs):
+            if st[0] is not None:             # memory_efficient: downsample first (:898-899)
+                x = unshuffle_conv(x, st[0][1], h, w)
+                h, w = h // 2, w // 2
             x = self._resblock(st[1], [x], h, w)
             for m in st[2]:
                 x = self._resblock(m, [x], h, w)
@@ -581,13 +596,8 @@ class _TrainPlan:
                 x = self._self_attention(st[3].fn.fn, x, T * h * w)
             hiddens.append(x)
             post = st[4]
-            if s < n_st - 1:
-                conv = post[1]
-                co, ci = conv.weight.shape[0], conv.weight.shape[1] // 4
-                x = self._conv([x], lambda conv=conv, co=co, ci=ci: conv.weight.detach().float().reshape(co, ci, 2, 2)[:, :, None],
-                               lambda conv=conv: conv.bias.detach().float(), conv.weight,
-                               lambda g5, co=co, ci=ci: g5[:, :, 0].reshape(co, 4 * ci, 1, 1, 1), conv.bias, co, n_img, h, w,
-                               mode=L.CONV_UNSHUFFLE)
+            if isinstance(post, nn.Sequential):
+                x = unshuffle_conv(x, post[1], h, w)
                 h, w = h // 2, w // 2
             else:
                 x = self._std_conv([x], post, n_img, h, w, 1)

@@ -412,11 +412,11 @@ class Unet3D(nn.Module):
     def train_plan(self, batch, frames, height, width, device):
         """Forward + backward launch plan of the training step (dalle2_video_b200/train.py)."""
         from .train import _TrainPlan
-        if (self.memory_efficient or not self.pixel_shuffle_upsample or self.final_conv_ksize != 1
+        if (not self.pixel_shuffle_upsample or self.final_conv_ksize != 1
                 or self.cosine_sim_cross_attn or self.cosine_sim_self_attn or self.cross_embed_downsample):
-            raise NotImplementedError("Unet3D(b200): the training plan is built for the default layer plan only "
-                                      "(memory_efficient / pixel_shuffle_upsample=False / final_conv_ksize != 1 / cosine_sim_* "
-                                      "sample, but do not train, on the native path)")
+            raise NotImplementedError("Unet3D(b200): the training plan takes the default layer plan and memory_efficient "
+                                      "(pixel_shuffle_upsample=False / final_conv_ksize != 1 / cosine_sim_* / "
+                                      "cross_embed_downsample sample, but do not train, on the native path)")
         # bf16 unless float32 is asked for explicitly (unet.compute_dtype = torch.float32: the parity mode)
         dtype = torch.float32 if self.compute_dtype == torch.float32 else torch.bfloat16
         key = ("train", batch, frames, height, width, str(device), dtype)

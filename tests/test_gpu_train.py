@@ -19,6 +19,9 @@ pytestmark = pytest.mark.gpu
 CASES = {
     "tiny": (dict(dim=32, video_embed_dim=512, dim_mults=(1, 2), cond_on_video_embeds=True), (2, 3, 4, 16, 16)),
     "headline_small": (dict(dim=64, video_embed_dim=512, dim_mults=(1, 2, 4, 8), cond_on_video_embeds=True), (2, 3, 4, 16, 16)),
+    # memory_efficient (:466-541, :611): initial resnet block, downsample before each stage's blocks, upsample after every up stage
+    "memory_efficient": (dict(dim=32, video_embed_dim=512, dim_mults=(1, 2), cond_on_video_embeds=True, memory_efficient=True),
+                         (2, 3, 4, 32, 32)),
 }
 
 
