@@ -390,7 +390,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
 // SAME (Q tile, key tile): they wait for S together, read TMEM together, exchange the row maximum, and only then use the
 // MUFU pipe (ncu: XU 46 %, issue 42 %, ~2100 cycles per tile against 1024 of exp2).  Here the CTA owns a PAIR of Q tiles of
 // one sequence and the K / V stream is shared by both:
-//   warps 0-3 = group 0 (Q tile 2k), warps 4-7 = group 1 (Q tile 2k+1), warp 8 TMA, warp 9 MMA (warps 10-11 idle: roles are
+//   warps 0-3 = group 0 (Q tile 2k), warps 4-7 = group 1 (Q tile 2k+1), warp 8 TMA, warps 9 / 10 the MMA issuers of group 0 / 1 (roles are
 //   aligned to warpgroups for setmaxnreg), ONE thread per (query, head) row holding all 128
 //   logits of a key tile in registers — no exchange of row maxima, no named barrier; each scheduler holds one warp of
 //   either group, and the groups drift apart, so one group's TMEM read / maximum runs under the other's exponentials.
@@ -455,7 +455,7 @@ attn_mqa_pp_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
     tma_prefetch_desc(&map_k);
     tma_prefetch_desc(&map_vt);
     for (int a = 0; a < 4; ++a) { mbar_init(&q_full[a], 1); mbar_init(&q_free[a], 4); }
-    for (int s = 0; s < PP_STAGES; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
+    for (int s = 0; s < PP_STAGES; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 2); }   // one commit per group's MMA warp
     for (int g = 0; g < 2; ++g) { mbar_init(&s_full[g], 1); mbar_init(&s_drained[g], 4); }
     for (int a = 0; a < 4; ++a) { mbar_init(&p_ready[a], 4); mbar_init(&pv_done[a], 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -506,8 +506,10 @@ attn_mqa_pp_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
         }
       }
     }
-  } else if (warp == 9) {
-    // ================================================================ MMA issuer: steps = (pair, key tile), flat
+  } else if (warp == 9 || warp == 10) {
+    // ================================================================ MMA issuers, one warp per group (their issue streams do not
+    // wait for each other: a single issuer stalled group 0's P.V behind group 1's barriers); steps = (pair, key tile), flat
+    const int mg = warp - 9;
     const uint32_t idesc_s = make_idesc(AT_KT), idesc_o = make_idesc(PP_N);
     const int64_t total = (pair_end - pair_begin) * nt;
     // S of step s for group g: needs the step's K stage, the group's Q tile, and the group's S buffer copied out (step s-1)
@@ -545,21 +547,16 @@ attn_mqa_pp_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
           const uint64_t vd = make_smem_desc(vbase + (uint32_t)(kk / 4) * VBLK) + (uint64_t)((kk % 4) * 2);
           umma_f16(d, pd, vd, idesc_o, kk != 0 ? 1u : first);
         }
-        if (g == 1) umma_commit(&kv_empty[st]);   // both groups' S and P.V of this stage have been issued before this point
+        umma_commit(&kv_empty[st]);   // this group's S and P.V of the stage have been issued; the stage is free after both groups' commits
         umma_commit(&pv_done[g * 2 + buf]);
       }
       __syncwarp();
     };
     if (total > 0) {
-      issue_s(0, 0);
-      issue_s(0, 1);
+      issue_s(0, mg);
       for (int64_t s = 0; s < total; ++s) {
-        if (s + 1 < total) {
-          issue_s(s + 1, 0);
-          issue_s(s + 1, 1);
-        }
-        issue_pv(s, 0);
-        issue_pv(s, 1);
+        if (s + 1 < total) issue_s(s + 1, mg);
+        issue_pv(s, mg);
       }
     }
   }

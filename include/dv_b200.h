@@ -403,7 +403,7 @@ int dv_xattn_fold(const dv_xattn_fold_params* p, dv_stream_t stream);
  * q: [S][n][heads*dh], kv: [S][n][2*dh] (k then v), out like q; S = independent sequences.
  * tcgen05 path (bf16, dh 32, n % 128 == 0, 128 % heads == 0, workspace): two Q tiles of a sequence in flight per CTA, one
  * thread per (query, head) row, O accumulated in TMEM against a lazily raised softmax reference (attn_mqa_pp_kernel;
- * 315-357 TFLOP/s at n = 1024..8192); sequences with an odd number of Q tiles (heads * n / 128) take the one-tile kernel.
+ * 319-373 TFLOP/s at n = 1024..8192); sequences with an odd number of Q tiles (heads * n / 128) take the one-tile kernel.
  */
 typedef struct {
   const void* q;
