@@ -3,7 +3,8 @@
 //
 // Per 128-token tile (one token per TMEM lane / epilogue thread):
 //   TMA     x tile [128][C] bf16 (kept in shared memory: GEMM operand, LayerNorm statistics and residual)
-//   MMA 1   raw[128][64]  = x . Mq^T            (M=128, N=64, K=C)        -> TMEM columns [0,64)
+//   MMA 1   raw[128][64]  = x . Mq^T            (M=128, N=64, K=C)        -> TMEM columns [C,C+64): issued for tile t+1 under
+//                                                                        tile t's output pass (C = 512: columns [0,64))
 //   threads logits = rstd_x * (raw - mean_x * cs);  per-head softmax over nk keys;  P (bf16) -> shared memory
 //   MMA 2   y[128][C]     = P . U^T             (M=128, N=min(C,256), K=64) -> TMEM columns [0,C)
 //   threads LayerNorm(y) * g2 + x -> bf16, in place over the x tile -> TMA store
@@ -156,7 +157,10 @@ xattn_fold_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t tmem_cols = p.C < 64 ? 64u : (uint32_t)p.C;  // 64 / 128 / 256 / 512
+  // y in columns [0, C); the logits of the NEXT tile in [C, C + 64) so that MMA 1 of tile t+1 runs under tile t's output pass
+  // (C = 512: one tile per CTA, the logits alias y as there is nothing to overlap)
+  const uint32_t tmem_cols = p.alias_u ? 512u : (p.C <= 64 ? 128u : p.C <= 128 ? 256u : 512u);
+  const uint32_t lg_col = p.alias_u ? 0u : (uint32_t)p.C;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_x);
@@ -236,11 +240,10 @@ xattn_fold_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
     // ================================================================ MMA issuer
     const uint32_t idesc1 = make_idesc(64), idesc2 = make_idesc(p.NB);
     int t = 0;
-    if (tile_begin < tile_end) mbar_wait(w_full, 0u);
-    for (int64_t tile = tile_begin; tile < tile_end; ++tile, ++t) {
-      const int st = t % p.xs;
-      mbar_wait(&x_full[st], (uint32_t)((t / p.xs) & 1));
-      if (t > 0) mbar_wait(acc_free, (uint32_t)((t - 1) & 1));  // previous tile's y has been read out of TMEM
+    const int n = (int)(tile_end - tile_begin);
+    auto issue_mma1 = [&](int i) {   // logits of tile i: needs its x stage; the logits columns are free once P of tile i-1 exists
+      const int st = i % p.xs;
+      mbar_wait(&x_full[st], (uint32_t)((i / p.xs) & 1));
       tc_fence_after();
       if (elect_one()) {
         for (int c = 0; c < p.chunks; ++c) {
@@ -248,13 +251,20 @@ xattn_fold_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
           const uint64_t bd = make_smem_desc(smem_u32(mq_s + (size_t)c * 8192));
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk)
-            umma_f16(tmem_base, ad + (uint64_t)(kk * 2), bd + (uint64_t)(kk * 2), idesc1, (c | kk) != 0);
+            umma_f16(tmem_base + lg_col, ad + (uint64_t)(kk * 2), bd + (uint64_t)(kk * 2), idesc1, (c | kk) != 0);
         }
         umma_commit(s_full);
         if (p.alias_u) umma_commit(mq_free);
       }
       __syncwarp();
+    };
+    if (n > 0) {
+      mbar_wait(w_full, 0u);
+      issue_mma1(0);
+    }
+    for (t = 0; t < n; ++t) {
       mbar_wait(p_ready, (uint32_t)(t & 1));  // P written (and the logits read out of TMEM)
+      if (t > 0) mbar_wait(acc_free, (uint32_t)((t - 1) & 1));  // previous tile's y has been read out of TMEM
       if (p.alias_u) mbar_wait(u_full, 0u);
       tc_fence_after();
       if (elect_one()) {
@@ -268,6 +278,7 @@ xattn_fold_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
         umma_commit(y_full);
       }
       __syncwarp();
+      if (t + 1 < n) issue_mma1(t + 1);   // the next tile's logits run under this tile's output pass
     }
   } else {
     // ================================================================ softmax + epilogue: one token per thread
@@ -323,8 +334,8 @@ xattn_fold_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
       float lg[64];
       {
         uint32_t r0[32], r1[32];
-        tmem_ld32(t_lane, r0);
-        tmem_ld32(t_lane + 32, r1);
+        tmem_ld32(t_lane + lg_col, r0);
+        tmem_ld32(t_lane + lg_col + 32, r1);
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
           lg[j] = rstd_x * (__uint_as_float(r0[j]) - mean_x * cs_s[j]);
@@ -545,7 +556,7 @@ extern "C" int dv_xattn_fold(const dv_xattn_fold_params* p, dv_stream_t stream) 
   }
   // the per-tile chain (LN statistics -> MMA 1 -> softmax -> MMA 2 -> LN -> store) is serial within a CTA: two CTAs per
   // SM overlap two chains whenever shared memory (and TMEM: C columns each) allow it
-  const uint32_t tmem_cols = p->C < 64 ? 64u : (uint32_t)p->C;
+  const uint32_t tmem_cols = p->C == 512 ? 512u : (p->C <= 64 ? 128u : p->C <= 128 ? 256u : 512u);   // y + the next tile's logits
   const int per_sm = (2 * (smem + 1024) <= 228 * 1024 && 2 * tmem_cols <= 512) ? 2 : 1;
   int gx = per_sm * sm_count / p->B;
   if (gx < 1) gx = 1;
