@@ -68,11 +68,14 @@ def _worker(rank, world, port, q):
 def test_two_rank_nccl_step_equals_one_gpu_step_on_the_concatenated_batch():
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 37500 + (os.getpid() % 2000)
+    import socket
+    with socket.socket() as sock:   # a port nobody holds (a fixed pid-derived port can collide with one in TIME_WAIT: the
+        sock.bind(("127.0.0.1", 0))  # rendezvous then hangs until the queue timeout)
+        port = sock.getsockname()[1]
     procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
-    losses, grad2, params2 = q.get(timeout=600)
+    losses, grad2, params2 = q.get(timeout=240)
     for p in procs:
         p.join(timeout=120)
         assert p.exitcode == 0
