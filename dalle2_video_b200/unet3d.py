@@ -470,6 +470,26 @@ class Unet3D(nn.Module):
         return eng.eps.clone().view(b, self.channels_out, *x.shape[2:]).to(x.dtype)
 
 
+def stride2_k4_as_3x3_over_unshuffled(w4):
+    """A 4x4 stride-2 padding-1 filter [co][ci][dy][dx] as the 3x3 stride-1 padding-1 filter over the pixel-unshuffled tensor
+    U[Y][X][(s1, s2, c)] = x[2Y + s1][2X + s2][c]: input row 2y + dy - 1 is (Y = y + ty - 1, s1) with dy = 2 ty + s1 - 1, so the
+    (ty, s1) pairs that map outside dy = 0..3 are zero weights.  Returns [co][9 * 4 * ci] with K ordered [ty][tx][s1][s2][c]
+    (the [tap][cin] order of dv_conv_igemm over 4 * ci input channels)."""
+    co, ci = w4.shape[0], w4.shape[1]
+    wp = torch.zeros(co, 3, 3, 2, 2, ci, device=w4.device, dtype=w4.dtype)
+    for ty in range(3):
+        for s1 in range(2):
+            dy = 2 * ty + s1 - 1
+            if not 0 <= dy < 4:
+                continue
+            for tx in range(3):
+                for s2 in range(2):
+                    dx = 2 * tx + s2 - 1
+                    if 0 <= dx < 4:
+                        wp[:, ty, tx, s1, s2] = w4[:, :, dy, dx]
+    return wp.reshape(co, 9 * 4 * ci)
+
+
 def _prob_mask(n, prob, device):
     """prob_mask_like (dalle2_pytorch): p in {0,1} consumes no RNG."""
     if prob == 1:
@@ -834,20 +854,8 @@ class _Engine:
                        mode=L.CONV_UNSHUFFLE, out_ld=co2 + co4, out_coff=0)
             U = self._new_act(B * T * (h // 2) * (w // 2), 4 * ci)
             self._conv([(x.ptr, ci)], self._w(torch.eye(4 * ci)), None, U.ptr, 4 * ci, n_img, h, w, mode=L.CONV_UNSHUFFLE)
-            w4 = c4.weight.detach()[:, :, 0]                       # [co][ci][dy][dx]
-            wp = torch.zeros(co4, 3, 3, 2, 2, ci, device=w4.device, dtype=w4.dtype)
-            for ty in range(3):
-                for s1 in range(2):
-                    dy = 2 * ty + s1 - 1
-                    if not 0 <= dy < 4:
-                        continue
-                    for tx in range(3):
-                        for s2 in range(2):
-                            dx = 2 * tx + s2 - 1
-                            if 0 <= dx < 4:
-                                wp[:, ty, tx, s1, s2] = w4[:, :, dy, dx]
-            self._conv([(U.ptr, 4 * ci)], self._w(wp.reshape(co4, 9 * 4 * ci)), self._f32(c4.bias), y.ptr, co4, n_img, h // 2,
-                       w // 2, k=3, out_ld=co2 + co4, out_coff=co2)
+            self._conv([(U.ptr, 4 * ci)], self._w(stride2_k4_as_3x3_over_unshuffled(c4.weight.detach()[:, :, 0])),
+                       self._f32(c4.bias), y.ptr, co4, n_img, h // 2, w // 2, k=3, out_ld=co2 + co4, out_coff=co2)
             self._release(U)
             self._release(x)
             return y

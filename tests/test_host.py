@@ -47,6 +47,24 @@ def test_off_default_layer_plan_state_dict_layouts_match_reference(name):
         assert all(torch.equal(a[k], sd[k]) for k in a)
 
 
+def test_stride2_filter_as_3x3_over_the_unshuffled_tensor():
+    """cross_embed_downsample's 4x4 stride-2 convolution (dalle2_video.py:208-244) runs as a 3x3 convolution over the
+    pixel-unshuffled tensor with remapped, partly zero weights: the remap against F.conv3d on the CPU."""
+    import torch.nn.functional as F
+    from dalle2_video_b200.unet3d import stride2_k4_as_3x3_over_unshuffled
+    g = torch.Generator().manual_seed(0)
+    ci, co, H, W = 5, 7, 8, 12
+    x = torch.randn(2, ci, 3, H, W, generator=g)
+    w = torch.randn(co, ci, 1, 4, 4, generator=g)
+    ref = F.conv3d(x, w, stride=(1, 2, 2), padding=(0, 1, 1))
+    b, _, t, _, _ = x.shape
+    # U[(s1, s2, c)][Y][X] = x[c][2Y + s1][2X + s2]
+    u = x.reshape(b, ci, t, H // 2, 2, W // 2, 2).permute(0, 4, 6, 1, 2, 3, 5).reshape(b, 4 * ci, t, H // 2, W // 2)
+    wp = stride2_k4_as_3x3_over_unshuffled(w[:, :, 0]).reshape(co, 3, 3, 4 * ci).permute(0, 3, 1, 2)[:, :, None]
+    out = F.conv3d(u, wp, padding=(0, 1, 1))
+    assert float((out - ref).abs().max()) < 1e-4
+
+
 def test_off_default_options_without_a_kernel_raise():
     for kw in (dict(combine_upsample_fmaps=True), dict(sparse_attn=True)):
         with pytest.raises(NotImplementedError):
