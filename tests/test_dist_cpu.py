@@ -120,6 +120,23 @@ def test_grad_buckets_partition_and_merge():
     assert len(gb.buckets) <= 5
 
 
+def test_small_runs_of_the_last_segment_do_not_delay_their_neighbours():
+    """The conditioning prologue's parameters (every time_mlp / to_kv weight) become final with the LAST backward segment and
+    sit between early-finished convolution weights in the flat buffer: merged into a neighbour they would push most of the
+    gradient behind the end of the backward; they stay buckets of their own, as late (autograd) arrivals always did."""
+    from dalle2_video_b200.parallel import GradBuckets
+    sizes = [6000, 50, 7000, 30, 5000]
+    segs = [0, 2, 1, 2, 0]
+    items, off = [], 0
+    for n, s in zip(sizes, segs):
+        items.append((off, n, s))
+        off += n
+    gb = GradBuckets(torch.zeros(off), items, n_segments=3, min_bytes=4 * 1000)
+    assert [b[2] for b in gb.buckets] == [0, 2, 1, 2, 0]
+    early = sum(hi - lo for lo, hi, seg in gb.buckets if seg < 2)
+    assert early == 18000
+
+
 def _bucket_worker(rank, world, port, q):
     import sys
     sys.path.insert(0, ROOT)
